@@ -1,0 +1,690 @@
+"""CPU oracle (pure Python) for miRge3.0's digest -> collapse -> annotate hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``mirge3.0_b200/`` may import this file; only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / ``--impl reference``
+legs use it, and there only as the checker.
+
+PARITY UNPINNED.  The arithmetic of this path lives in two third-party tools that are not
+vendored in /root/reference and are not installable here (no network): ``cutadapt``
+(unpinned in reference ``setup.py:17``; the reference says "ADOPTED FROM CUTADAPT 2.7",
+``mirge/libs/digest.py:21,41,61``) with ``dnaio``/``xopen``, and the ``bowtie`` 1.x binary
+(``mirge/libs/miRgeEssential.py:17``).  The reference has no tests and no golden files.  This
+module restates the *published* algorithms of those tools (cutadapt 2.x-3.x ``_align.pyx``
+``Aligner.locate``, ``qualtrim.pyx``, ``modifiers.py``; ``dnaio`` chunking/FASTQ parsing;
+bowtie 1 manual ``-v``/``-n``/``--best --strata`` semantics) and anchors on the reference's own
+call sites plus the ten known-answer reads in ``docs/source/quick_start.md:285-315``
+(see ``tests/test_oracle_golden.py``).
+
+Every function cites the reference ``file:line`` it follows (paths relative to /root/reference).
+Pure-Python loops: use for small cases only; ``oracle/mirge_oracle.c`` is the fast restatement,
+validated against this file.
+"""
+from __future__ import annotations
+
+import math
+import re
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+# --------------------------------------------------------------------------------------
+# FASTQ chunking + parsing  (dnaio; called from mirge/libs/digest.py:136,140,324)
+# --------------------------------------------------------------------------------------
+
+
+class FastqFormatError(ValueError):
+    """Mirrors dnaio.FastqFormatError for malformed records (digest.py:324 lets it propagate)."""
+
+
+def _fastq_head(buf: bytes, end: int) -> int:
+    """dnaio.chunks._fastq_head: offset just after the last complete 4-line record."""
+    linebreaks = buf.count(b"\n", 0, end)
+    right = end
+    for _ in range(linebreaks % 4 + 1):
+        right = buf.rfind(b"\n", 0, right)
+    return right + 1
+
+
+def read_chunks(data: bytes, buffer_size: int = 4_000_000) -> List[Tuple[int, int]]:
+    """(start, end) byte ranges dnaio.read_chunks(f, buffer_size) yields for a *plain* file
+    (digest.py:140; args.buffer_size default parse.py:100).  For a regular uncompressed file
+    every ``readinto`` fills the buffer, so the boundaries are a pure function of the bytes:
+    each chunk is the longest prefix of the next ``buffer_size`` bytes that ends on a record
+    boundary; the final partial tail is yielded as-is at EOF."""
+    if not data:
+        return []
+    if data[0:1] != b"@":
+        raise FastqFormatError("Input file format unknown (first byte is not '@')")
+    out = []
+    s = 0
+    n = len(data)
+    while s < n:
+        window_end = min(n, s + buffer_size)
+        if window_end == n:
+            # last fill: records that complete inside it are yielded, the tail afterwards
+            e = s + _fastq_head(data[s:window_end], window_end - s)
+            if e > s:
+                out.append((s, e))
+            if e < n:
+                if e == s and n - s >= buffer_size:
+                    raise OverflowError("FASTA/FASTQ record does not fit into buffer")
+                out.append((e, n))
+            break
+        e = s + _fastq_head(data[s:window_end], window_end - s)
+        if e == s:
+            raise OverflowError("FASTA/FASTQ record does not fit into buffer")
+        out.append((s, e))
+        s = e
+    return out
+
+
+def parse_fastq(data: bytes) -> List[Tuple[str, str, str]]:
+    """dnaio FastqIter semantics (digest.py:324-325): 4-line records, trailing '\\r' stripped,
+    line 1 starts with '@', line 3 with '+', len(seq) == len(qual).  Last line may lack '\\n'."""
+    if not data:
+        return []
+    lines = data.split(b"\n")
+    if lines and lines[-1] == b"":
+        lines.pop()
+    if len(lines) % 4 != 0:
+        raise FastqFormatError("Premature end of file (line count %d not a multiple of 4)" % len(lines))
+    recs = []
+    for i in range(0, len(lines), 4):
+        h, s, p, q = (x[:-1] if x.endswith(b"\r") else x for x in lines[i : i + 4])
+        if not h.startswith(b"@"):
+            raise FastqFormatError("Line %d expected to start with '@'" % (i + 1))
+        if not p.startswith(b"+"):
+            raise FastqFormatError("Line %d expected to start with '+'" % (i + 3))
+        if len(s) != len(q):
+            raise FastqFormatError("Length of sequence and qualities differ (record %d)" % (i // 4))
+        recs.append((h[1:].decode("latin-1"), s.decode("latin-1"), q.decode("latin-1")))
+    return recs
+
+
+# --------------------------------------------------------------------------------------
+# Quality trimming  (cutadapt qualtrim.pyx; constructed at digest.py:87-91)
+# --------------------------------------------------------------------------------------
+
+
+def nextseq_trim_index(seq: str, qual: str, cutoff: int, base: int = 33) -> int:
+    """cutadapt.qualtrim.nextseq_trim_index (NextseqQualityTrimmer, digest.py:87-88)."""
+    s = 0
+    max_qual = 0
+    max_i = len(qual)
+    for i in range(len(qual) - 1, -1, -1):
+        q = ord(qual[i]) - base
+        if seq[i] == "G":
+            q = cutoff - 1
+        s += cutoff - q
+        if s < 0:
+            break
+        if s > max_qual:
+            max_qual = s
+            max_i = i
+    return max_i
+
+
+def quality_trim_index(qual: str, cutoff_front: int, cutoff_back: int, base: int = 33) -> Tuple[int, int]:
+    """cutadapt.qualtrim.quality_trim_index (QualityTrimmer, digest.py:89-91)."""
+    s = 0
+    max_qual = 0
+    start = 0
+    stop = len(qual)
+    for i in range(len(qual)):
+        s += cutoff_front - (ord(qual[i]) - base)
+        if s < 0:
+            break
+        if s > max_qual:
+            max_qual = s
+            start = i + 1
+    max_qual = 0
+    s = 0
+    for i in range(len(qual) - 1, -1, -1):
+        s += cutoff_back - (ord(qual[i]) - base)
+        if s < 0:
+            break
+        if s > max_qual:
+            max_qual = s
+            stop = i
+    if start >= stop:
+        start, stop = 0, 0
+    return start, stop
+
+
+# --------------------------------------------------------------------------------------
+# Adapter alignment  (cutadapt _align.pyx Aligner.locate; AdapterCutter at digest.py:93-96)
+# --------------------------------------------------------------------------------------
+
+IUPAC = {
+    "A": 1, "C": 2, "G": 4, "T": 8, "U": 8,
+    "R": 1 | 4, "Y": 2 | 8, "S": 2 | 4, "W": 1 | 8, "K": 4 | 8, "M": 1 | 2,
+    "B": 2 | 4 | 8, "D": 1 | 4 | 8, "H": 1 | 2 | 8, "V": 1 | 2 | 4, "N": 15, "X": 0,
+}
+ACGT = {"A": 1, "C": 2, "G": 4, "T": 8, "U": 8}
+
+INDEL_OFF_COST = 100000  # cutadapt adapters.py: "indel_cost = 1 if self.indels else 100000"
+
+
+@dataclass
+class Adapter:
+    """One parsed adapter (subset of cutadapt's spec language that miRge's CLI can produce from
+    ``-a SEQ`` / ``-g SEQ``, parse.py:74-77: plain 3' ("back") and 5' ("front") adapters)."""
+
+    where: str  # "back" | "front"
+    sequence: str
+    max_error_rate: float = 0.12  # parse.py:91
+    min_overlap: int = 3  # parse.py:90
+    indels: bool = True  # parse.py:101
+    adapter_wildcards: bool = True  # parse.py:98 (only effective if sequence has non-ACGT)
+
+    def __post_init__(self):
+        self.sequence = self.sequence.upper().replace("U", "T")
+        if not self.sequence:
+            raise ValueError("Adapter sequence is empty")
+        self.wildcard_ref = self.adapter_wildcards and not set(self.sequence) <= set("ACGT")
+        if not self.wildcard_ref and not set(self.sequence) <= set("ACGT"):
+            raise ValueError("non-ACGT adapter characters need adapter wildcards (unsupported combination)")
+        m = len(self.sequence)
+        self.n_counts = [0] * (m + 1)
+        c = 0
+        for i, ch in enumerate(self.sequence):
+            self.n_counts[i] = c
+            if ch == "N":
+                c += 1
+        self.n_counts[m] = c
+        self.effective_length = m - c if self.wildcard_ref else m
+        if self.effective_length == 0:
+            raise ValueError("Cannot have only N wildcards in the sequence")
+        self.masks = [IUPAC[ch] for ch in self.sequence]
+
+
+def _allowed(length: int, rate: float) -> float:
+    return length * rate  # evaluated in double exactly as cutadapt's "cost <= length * max_error_rate"
+
+
+def locate(ad: Adapter, read: str) -> Optional[Tuple[int, int, int, int, int, int]]:
+    """cutadapt 2.x-3.x ``Aligner.locate(query)`` for back (3') and front (5') adapters.
+
+    Returns (astart, astop, rstart, rstop, matches, errors) or None.  Unit-cost semi-global DP,
+    adapter = rows, read = columns, one column kept; each cell carries (cost, origin, matches).
+    Cell choice: equal characters -> diagonal; else mismatch if cd<=cdel and cd<=cins, else
+    insertion if cins<=cdel, else deletion.  Candidates: row m after every column, then (after the
+    last column) rows first_i..m in ascending order; a candidate replaces the best iff it has more
+    matches, or equally many and a lower cost.  cutadapt's Ukkonen cut-off ("last") only skips
+    cells whose cost exceeds k=int(rate*m); no accepted cell depends on them, so the full DP used
+    here yields identical results.
+    """
+    m = len(ad.sequence)
+    n = len(read)
+    rate = ad.max_error_rate
+    ins_cost = del_cost = 1 if ad.indels else INDEL_OFF_COST
+    up = read.upper()
+    # read characters -> 4-bit class (non-ACGT never matches; match_read_wildcards=False, parse.py:97)
+    rmask = [ACGT.get(ch, 0) for ch in up]
+    back = ad.where == "back"
+    start_in_ref = not back  # FRONT: adapter start may be skipped
+    stop_in_ref = back  # BACK: adapter end may be skipped (overhang at the read's 3' end)
+    # start_in_query = stop_in_query = True for both  =>  min_n = 0, max_n = n
+    cost = [0] * (m + 1)
+    origin = [0] * (m + 1)
+    matches = [0] * (m + 1)
+    if start_in_ref:
+        for i in range(m + 1):
+            cost[i] = 0
+            origin[i] = -i
+    else:
+        for i in range(m + 1):
+            cost[i] = i * ins_cost
+            origin[i] = 0
+    k = int(rate * m)
+    best_cost = m + n
+    best_origin = 0
+    best_matches = 0
+    best_ref_stop = m
+    best_query_stop = n
+    stopped_early = False
+
+    def eff_len_row_m(length):
+        if ad.wildcard_ref:
+            if length < m:
+                return length - (ad.n_counts[m] - ad.n_counts[m - length])
+            return ad.effective_length
+        return length
+
+    for j in range(1, n + 1):
+        diag_c, diag_o, diag_m = cost[0], origin[0], matches[0]
+        origin[0] = j  # start_in_query
+        rc = rmask[j - 1]
+        for i in range(1, m + 1):
+            if ad.masks[i - 1] & rc:
+                c, o, mt = diag_c, diag_o, diag_m + 1
+            else:
+                cd = diag_c + 1
+                cdel = cost[i] + del_cost
+                cins = cost[i - 1] + ins_cost
+                if cd <= cdel and cd <= cins:
+                    c, o, mt = cd, diag_o, diag_m
+                elif cins <= cdel:
+                    c, o, mt = cins, origin[i - 1], matches[i - 1]
+                else:
+                    c, o, mt = cdel, origin[i], matches[i]
+            diag_c, diag_o, diag_m = cost[i], origin[i], matches[i]
+            cost[i], origin[i], matches[i] = c, o, mt
+        # row m is examined only when column[m].cost <= k ("last == m")
+        if cost[m] <= k:
+            length = m + min(origin[m], 0)
+            c = cost[m]
+            mt = matches[m]
+            if (
+                length >= ad.min_overlap
+                and c <= _allowed(eff_len_row_m(length), rate)
+                and (mt > best_matches or (mt == best_matches and c < best_cost))
+            ):
+                best_matches, best_cost, best_origin = mt, c, origin[m]
+                best_ref_stop, best_query_stop = m, j
+                if c == 0 and mt == m:
+                    stopped_early = True
+                    break
+    if not stopped_early:  # max_n == n always here
+        first_i = 0 if stop_in_ref else m
+        for i in range(first_i, m + 1):
+            length = i + min(origin[i], 0)
+            c = cost[i]
+            mt = matches[i]
+            if ad.wildcard_ref:
+                if length < m:
+                    ref_start = -min(origin[i], 0)
+                    eff = length - (ad.n_counts[i] - ad.n_counts[ref_start])
+                else:
+                    eff = ad.effective_length
+            else:
+                eff = length
+            if (
+                length >= ad.min_overlap
+                and c <= _allowed(eff, rate)
+                and (mt > best_matches or (mt == best_matches and c < best_cost))
+            ):
+                best_matches, best_cost, best_origin = mt, c, origin[i]
+                best_ref_stop, best_query_stop = i, n
+    if best_cost == m + n:
+        return None
+    if best_origin >= 0:
+        start1, start2 = 0, best_origin
+    else:
+        start1, start2 = -best_origin, 0
+    return (start1, best_ref_stop, start2, best_query_stop, best_matches, best_cost)
+
+
+def match_to(ad: Adapter, read: str) -> Optional[Tuple[int, int, int, int, int, int]]:
+    """cutadapt ``Adapter.match_to``: exact ``str.find`` on the upper-cased read first (only when
+    the adapter has no wildcards), otherwise ``Aligner.locate``.  The fast path returns what the
+    DP would (leftmost exact occurrence: the DP stops at the first column with cost 0, matches m).
+    """
+    up = read.upper()
+    if not ad.wildcard_ref:
+        pos = up.find(ad.sequence)
+        if pos >= 0:
+            m = len(ad.sequence)
+            return (0, m, pos, pos + m, m, 0)
+    return locate(ad, read)
+
+
+def best_match(adapters: Sequence[Adapter], read: str):
+    """cutadapt ``AdapterCutter._best_match``: most matches wins, then fewer errors; first adapter
+    wins remaining ties."""
+    best = None
+    best_ad = None
+    for ad in adapters:
+        mt = match_to(ad, read)
+        if mt is None:
+            continue
+        if best is None or mt[4] > best[4] or (mt[4] == best[4] and mt[5] < best[5]):
+            best, best_ad = mt, ad
+    return best_ad, best
+
+
+# --------------------------------------------------------------------------------------
+# Modifier pipeline  (stipulate(), digest.py:59-101) on (start, stop) windows of the original read
+# --------------------------------------------------------------------------------------
+
+
+def parse_cutoffs(s: str) -> List[int]:
+    """digest.py:19-35."""
+    cutoffs = [int(v) for v in str(s).split(",")]
+    if len(cutoffs) == 1:
+        cutoffs = [0, cutoffs[0]]
+    elif len(cutoffs) != 2:
+        raise ValueError("Expected one value or two values separated by comma for the quality cutoff")
+    return cutoffs
+
+
+@dataclass
+class TrimParams:
+    """The hot-path subset of miRge's ``args`` namespace (SURVEY.md section 5 / parse.py)."""
+
+    adapters: List[Adapter] = field(default_factory=list)
+    times: int = 1  # parse.py:96
+    nextseq_trim: Optional[int] = None  # parse.py:79
+    quality_cutoff: Optional[str] = "10"  # parse.py:80 (always on by default)
+    quality_base: int = 33  # parse.py:40 ("phred64", really the base)
+    trim_n: bool = False  # parse.py:82
+    cut: List[int] = field(default_factory=list)  # parse.py:78
+    minimum_length: int = 16  # parse.py:83
+    umi: Optional[Tuple[int, int]] = None  # parse.py:84 "-umi f,b"
+    qiagenumi: bool = False  # parse.py:85
+    count_mode: str = "head"  # "head": digest.py:354-373 as written; "release": dist/ 0.1.x
+
+    def modifiers(self) -> List[Tuple[str, tuple]]:
+        """Ordered modifier list exactly as stipulate() builds it (digest.py:87-99):
+        NextSeq -> Quality -> AdapterCutter -> NEnd -> UnconditionalCutter(s)."""
+        mods: List[Tuple[str, tuple]] = []
+        if self.nextseq_trim is not None:
+            mods.append(("nextseq", (int(self.nextseq_trim), self.quality_base)))
+        if self.quality_cutoff is not None:
+            q5, q3 = parse_cutoffs(self.quality_cutoff)
+            mods.append(("quality", (q5, q3, self.quality_base)))
+        if self.adapters:
+            mods.append(("adapter", ()))
+        if self.trim_n:
+            mods.append(("nend", ()))
+        cut = [c for c in self.cut]
+        if cut:
+            if len(cut) > 2:
+                raise ValueError("You cannot remove bases from more than two ends.")
+            if len(cut) == 2 and cut[0] * cut[1] > 0:
+                raise ValueError("You cannot remove bases from the same end twice.")
+            for c in cut:
+                if c != 0:
+                    mods.append(("cut", (int(c),)))
+        return mods
+
+
+def apply_modifier(mod, seq: str, qual: str, start: int, stop: int, p: TrimParams) -> Tuple[int, int]:
+    """Apply one modifier to the window read[start:stop]; returns the new window."""
+    kind, a = mod
+    cur_s = seq[start:stop]
+    cur_q = qual[start:stop]
+    if kind == "nextseq":
+        return start, start + nextseq_trim_index(cur_s, cur_q, a[0], a[1])
+    if kind == "quality":
+        s, e = quality_trim_index(cur_q, a[0], a[1], a[2])
+        return start + s, start + e
+    if kind == "adapter":
+        for _ in range(p.times):
+            ad, mt = best_match(p.adapters, seq[start:stop])
+            if mt is None:
+                break
+            if ad.where == "back":
+                stop = start + mt[2]  # read[:rstart]
+            else:
+                start = start + mt[3]  # read[rstop:]
+        return start, stop
+    if kind == "nend":
+        # NEndTrimmer: regex ^N+ and N+$ (uppercase N only)
+        s, e = start, stop
+        while s < e and seq[s] == "N":
+            s += 1
+        while e > s and seq[e - 1] == "N":
+            e -= 1
+        return s, e
+    if kind == "cut":
+        c = a[0]
+        ln = stop - start
+        if c > 0:
+            return start + min(c, ln), stop  # read[c:]
+        return start, start + max(ln + c, 0)  # read[:c], c < 0
+    raise ValueError(kind)
+
+
+def umi_parser(s: str, f: int, b: int) -> Tuple[str, str]:
+    """UMIParser (digest.py:305-315) incl. the b == 0 quirk (s[-0:] is the whole string)."""
+    front = s[:f]
+    center = s[f:-b] if int(b) != 0 else s[f:]
+    end = s[-b:]
+    return center, front + end
+
+
+def digest_read(seq: str, qual: str, p: TrimParams) -> List[Tuple[str, List[Tuple[int, int, int, int]]]]:
+    """Per-read body of the worker ``cutadapt(n)`` (digest.py:325-373).
+
+    Returns the list of emitted keys for this read, each with its window description
+    (start, stop, ustart, ustop): key == seq[start:stop] + seq[ustart:ustop].
+    """
+    mods = p.modifiers()
+    out = []
+    start, stop = 0, len(seq)
+    min_len = int(p.minimum_length)
+    if p.qiagenumi:
+        # digest.py:332-352 -- whole pipeline first, then UMI = text after the trimmed read
+        for mod in mods:
+            start, stop = apply_modifier(mod, seq, qual, start, stop, p)
+        trimmed = seq[start:stop]
+        U = int(p.umi[1])
+        m_ad = len(p.adapters[0].sequence)  # qiaAdapter = args.adapters[0][1] (digest.py:121)
+        ustart = ustop = 0
+        if trimmed == "":
+            umi_seq = ""  # "".split("") raises ValueError -> umi_seq = "" (digest.py:345-346)
+        else:
+            first = seq.find(trimmed)
+            after = first + len(trimmed)
+            nxt = seq.find(trimmed, after)
+            seg_end = len(seq) if nxt < 0 else nxt
+            # umi_seq = seg[:max_ad][-U:]
+            seg_end = min(seg_end, after + m_ad + U)
+            ustop = seg_end
+            ustart = max(after, seg_end - U) if U != 0 else after  # [-0:] keeps the whole string
+            umi_seq = seq[after:seg_end]
+            umi_seq = umi_seq[-U:] if U != 0 else umi_seq
+            assert umi_seq == seq[ustart:ustop]
+            assert seq.split(trimmed)[1][: m_ad + U][-U:] == umi_seq if U != 0 else True
+        if len(trimmed) >= min_len:
+            out.append((trimmed + umi_seq, (start, stop, ustart, ustop)))
+        return out
+    emit_each = p.count_mode == "head"
+    for si, mod in enumerate(mods):
+        start, stop = apply_modifier(mod, seq, qual, start, stop, p)
+        if emit_each or si == len(mods) - 1:
+            cur = seq[start:stop]
+            if p.umi is not None:
+                ln = len(umi_parser(cur, p.umi[0], p.umi[1])[0])
+            else:
+                ln = len(cur)
+            if ln >= min_len:
+                out.append((cur, (start, stop, 0, 0)))
+    return out
+
+
+def digest_chunk(data: bytes, p: TrimParams) -> Tuple[int, Dict[str, int]]:
+    """The worker ``cutadapt(n)`` (digest.py:320-375): (records parsed, chunk-local dict)."""
+    read_dict: Dict[str, int] = {}
+    count = 0
+    for _name, seq, qual in parse_fastq(data):
+        count += 1
+        for key, _w in digest_read(seq, qual, p):
+            read_dict[key] = read_dict.get(key, 0) + 1
+    return count, read_dict
+
+
+@dataclass
+class SampleDigest:
+    count: int  # sampleReadCounts (digest.py:214)
+    trimmed: int  # trimmedReadCounts (digest.py:183/204/208)
+    table: Dict[str, int]  # completeDict after the optional UMI level (digest.py:182/203)
+    rlen: List[int]  # visual_treat['rlen'] (digest.py:146-157): one length per chunk-unique key
+    hist: List[int]  # visual_treat['hist'] (digest.py:172/192)
+    umi_rows: List[Tuple[str, str, int]]  # <sample>_umiCounts.csv rows (digest.py:196)
+
+
+def digest_sample(data: bytes, p: TrimParams, umi_dedup: bool = False, buffer_size: int = 4_000_000) -> SampleDigest:
+    """One iteration of baking()'s per-sample loop (digest.py:133-217)."""
+    count = trimmed = 0
+    complete: Dict[str, int] = {}
+    rlen: List[int] = []
+    for s, e in read_chunks(data, buffer_size):
+        a, b = digest_chunk(data[s:e], p)
+        count += a
+        for k, c in b.items():
+            if p.umi is not None:
+                rlen.append(len(umi_parser(k, p.umi[0], p.umi[1])[0]))
+            else:
+                rlen.append(len(k))
+            complete[k] = complete.get(k, 0) + c
+            trimmed += c
+    hist: List[int] = []
+    umi_rows: List[Tuple[str, str, int]] = []
+    if p.umi is not None:
+        trimmed = 0
+        second: Dict[str, int] = {}
+        for s_, c in complete.items():
+            pure, cut = umi_parser(s_, p.umi[0], p.umi[1])
+            hist.append(c)
+            if len(pure) >= int(p.minimum_length):
+                if umi_dedup:
+                    umi_rows.append((cut, pure, c))
+                    second[pure] = second.get(pure, 0) + 1
+                    trimmed += 1
+                else:
+                    second[pure] = second.get(pure, 0) + c
+                    trimmed += c
+        complete = second
+    return SampleDigest(count, trimmed, complete, rlen, hist, umi_rows)
+
+
+# --------------------------------------------------------------------------------------
+# Annotation rounds  (bwtAlign, manifoldAlign.py:68-146; bowtie 1.x semantics)
+# --------------------------------------------------------------------------------------
+
+ROUND_COLUMNS = ["exact miRNA", "hairpin miRNA", "mature tRNA", "primary tRNA", "snoRNA", "rRNA",
+                 "ncrna others", "mRNA", "isomiR miRNA", "spike-in"]  # digest.py:253
+ROUND_LIBS = ["mirna", "hairpin", "mature_trna", "pre_trna", "snorna", "rrna", "ncrna_others", "mrna",
+              "mirna", "spike-in"]  # manifoldAlign.py:84
+
+
+@dataclass(frozen=True)
+class RoundPolicy:
+    """Effective bowtie policy of one round (manifoldAlign.py:85).  FASTA input => every quality
+    is 'I' (Phred 40, Maq-rounded to 30); ``-e 70`` => at most 2 mismatches in total in -n mode."""
+
+    seed_len: int  # -l 28 in -n mode; 0 => whole read (-v mode)
+    seed_mm: int  # -n N / -v N
+    total_mm: int  # 2 in -n mode (floor(70/30)); N in -v mode
+    trim5: int = 0  # -5
+    trim3: int = 0  # -3
+    strip_polyT: bool = False  # round 3 query rewrite (manifoldAlign.py:118-126)
+
+
+def _n(nmm):
+    return RoundPolicy(28, nmm, 2)
+
+
+ROUND_POLICIES = [
+    _n(0),  # 0: -n 0
+    _n(1),  # 1: -n 1
+    RoundPolicy(0, 1, 1),  # 2: -v 1 -a --best --strata
+    RoundPolicy(0, 0, 0, strip_polyT=True),  # 3: -v 0 -a --best --strata
+    _n(1), _n(1), _n(1),  # 4,5,6: -n 1
+    _n(0),  # 7: -n 0
+    RoundPolicy(0, 2, 2, trim5=1, trim3=2),  # 8: -5 1 -3 2 -v 2 --best
+    _n(0),  # 9: -n 0 (spike-in, only with -spk)
+]
+
+_POLYT = re.compile("T{3,}$")
+
+
+@dataclass
+class Library:
+    names: List[str]  # FASTA header up to first whitespace (bowtie RNAME)
+    seqs: List[str]
+
+
+def read_fasta(text: str) -> Library:
+    names, seqs, cur = [], [], None
+    for line in text.splitlines():
+        if line.startswith(">"):
+            hdr = line[1:].split()
+            names.append(hdr[0] if hdr else "")
+            seqs.append([])
+            cur = seqs[-1]
+        elif cur is not None:
+            cur.append(line.strip())
+    return Library(names, ["".join(s).upper() for s in seqs])
+
+
+def round_query(seq: str, rnd: int) -> Optional[str]:
+    """Query string bowtie sees for ``seq`` in round ``rnd`` (None => not submitted)."""
+    pol = ROUND_POLICIES[rnd]
+    if pol.strip_polyT:
+        mt = _POLYT.search(seq)
+        if mt is None:
+            return None
+        q = seq[: mt.span(0)[0]]
+    else:
+        q = seq
+    if pol.trim5 or pol.trim3:
+        q = q[pol.trim5 : max(len(q) - pol.trim3, pol.trim5)]
+    return q
+
+
+def hits(query: str, lib: Library, pol: RoundPolicy) -> List[Tuple[int, int, int, int]]:
+    """All valid end-to-end ungapped forward-strand alignments (n_mismatch, ref, offset, seed_mm).
+    A read character other than ACGT always mismatches; a reference position other than ACGT may
+    not be overlapped."""
+    q = query.upper()
+    L = len(q)
+    out = []
+    if L == 0:
+        return out
+    seed = L if pol.seed_len == 0 else min(pol.seed_len, L)
+    for r, ref in enumerate(lib.seqs):
+        for off in range(0, len(ref) - L + 1):
+            mm = smm = 0
+            ok = True
+            for j in range(L):
+                rc = ref[off + j]
+                if rc not in "ACGT":
+                    ok = False
+                    break
+                if q[j] != rc or q[j] not in "ACGT":
+                    mm += 1
+                    if j < seed:
+                        smm += 1
+                    if mm > pol.total_mm or smm > pol.seed_mm:
+                        ok = False
+                        break
+            if ok:
+                out.append((mm, r, off, smm))
+    return out
+
+
+def canonical_pick(hitlist):
+    """min over (n_mismatch, ref index in library order, 0-based offset) -- the documented
+    replacement for bowtie's irreproducible choice."""
+    return min((h[0], h[1], h[2]) for h in hitlist) if hitlist else None
+
+
+def annotate(seqs: Sequence[str], libs: Dict[str, Library], spike_in: bool = False):
+    """bwtAlign's round loop (manifoldAlign.py:90-135) over the unique sequences.
+
+    Returns {seq: (round, ref_name, offset, n_mismatch)} for annotated sequences; a sequence is
+    annotated by the first round that hits it (rounds 0 and 1 partition by length and ignore
+    annotFlag, manifoldAlign.py:93,104)."""
+    annot: Dict[str, Tuple[int, str, int, int]] = {}
+    rounds = 10 if spike_in else 9
+    for rnd in range(rounds):
+        lib = libs[ROUND_LIBS[rnd]]
+        pol = ROUND_POLICIES[rnd]
+        for s in seqs:
+            if rnd == 0:
+                if not len(s) < 26:
+                    continue
+            elif rnd == 1:
+                if not len(s) > 25:
+                    continue
+            elif s in annot:
+                continue
+            q = round_query(s, rnd)
+            if q is None:
+                continue
+            pick = canonical_pick(hits(q, lib, pol))
+            if pick is not None:
+                annot[s] = (rnd, lib.names[pick[1]], pick[2], pick[0])
+    return annot
