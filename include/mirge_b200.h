@@ -1,0 +1,249 @@
+/*
+ * mirge_b200.h -- C ABI of libmirge_b200.so: the B200 (sm_100a) implementation of miRge3.0's
+ * per-read hot path (digest -> collapse -> ordered annotation rounds).
+ *
+ * This is the drop-in boundary.  miRge3.0 is pure Python and reaches its
+ * hot path through two function calls; the entry points below are what a ctypes binding inside
+ * the reference would call instead (see INTEGRATION.md for the stub):
+ *
+ *   reference interface (under /root/reference)                    replaced by
+ *   ---------------------------------------------------------------------------------------------
+ *   mirge/libs/digest.py:105   baking(args, files, names, workDir)   mirge_set_trim_params,
+ *     :140  dnaio.read_chunks + executor.submit(cutadapt, chunk)      mirge_tokenise_sync,
+ *     :320  cutadapt(n) worker: parse + modifiers + key emission      mirge_line_index, mirge_trim,
+ *     :141-163 parent merge (collapse)                                mirge_collapse_insert,
+ *     :164-205 UMI second-level collapse                              mirge_umi_collapse,
+ *     :237-261 sample x sequence matrix                               mirge_table_drain,
+ *                                                                     mirge_table_export_keys
+ *   mirge/libs/manifoldAlign.py:68 bwtAlign(args, df, workDir, db)   mirge_lib_kmers,
+ *     :12   alignPlusParse (bowtie subprocess + SAM parse)            mirge_annotate_round
+ *
+ * Conventions: every function returns 0 on success or a negative MIRGE_ERR_* code and records a
+ * message retrievable with mirge_last_error().  All pointers named d_* are DEVICE pointers owned
+ * by the caller (torch.Tensor.data_ptr() in the Python host); the library never allocates data
+ * buffers, it only owns a small control block per context.  Calls enqueue work on `stream`
+ * (a cudaStream_t passed as void*) and return immediately unless suffixed _sync.  There is no
+ * CPU fallback: without a CUDA device mirge_ctx_create fails.
+ */
+#ifndef MIRGE_B200_H
+#define MIRGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIRGE_ABI_VERSION 1
+
+#define MIRGE_OK 0
+#define MIRGE_ERR_CUDA (-1)     /* CUDA runtime error (message has the cudaError string) */
+#define MIRGE_ERR_ARG (-2)      /* invalid argument / unsupported parameter combination */
+#define MIRGE_ERR_FORMAT (-3)   /* malformed FASTQ (dnaio FastqFormatError equivalent) */
+#define MIRGE_ERR_CAPACITY (-4) /* a caller-provided buffer / table is too small */
+#define MIRGE_ERR_NODEVICE (-5) /* no usable CUDA device */
+
+#define MIRGE_MAX_ADAPTERS 4
+#define MIRGE_MAX_ADAPTER_LEN 64
+#define MIRGE_MAX_MODS 8
+#define MIRGE_MAX_READ_LEN 512 /* bases per read handled by the trim kernel */
+
+/* modifier kinds, in the order stipulate() may add them (mirge/libs/digest.py:87-99) */
+#define MIRGE_MOD_NEXTSEQ 1 /* a = cutoff, b = quality base          (NextseqQualityTrimmer) */
+#define MIRGE_MOD_QUALITY 2 /* a = 5' cutoff, b = 3' cutoff, c = base (QualityTrimmer)        */
+#define MIRGE_MOD_ADAPTER 3 /*                                       (AdapterCutter)         */
+#define MIRGE_MOD_NEND 4    /*                                       (NEndTrimmer)           */
+#define MIRGE_MOD_CUT 5     /* a = length (>0: 5' end, <0: 3' end)   (UnconditionalCutter)   */
+
+#define MIRGE_UMI_NONE 0
+#define MIRGE_UMI_FLANKS 1 /* -umi f,b            (digest.py:359-366) */
+#define MIRGE_UMI_QIAGEN 2 /* --qiagenumi -umi 0,U (digest.py:332-352) */
+
+#define MIRGE_COUNT_HEAD 0    /* count after every modifier, as digest.py:354-373 is written */
+#define MIRGE_COUNT_RELEASE 1 /* count once after the pipeline (released 0.1.x behaviour)   */
+
+/* One adapter in cutadapt's Aligner terms (restated in oracle/pyoracle.py::locate). */
+typedef struct mirge_adapter {
+  int32_t where;        /* 0 = back (3', -a), 1 = front (5', -g) */
+  int32_t m;            /* adapter length, <= MIRGE_MAX_ADAPTER_LEN */
+  int32_t min_overlap;  /* args.overlap, parse.py:90 */
+  int32_t indel_cost;   /* 1, or 100000 when --no-indels (cutadapt adapters.py) */
+  int32_t wildcard_ref; /* adapter contains IUPAC wildcards and -N was not given */
+  int32_t k;            /* int(error_rate * m) */
+  int32_t effective_length;
+  int32_t reserved;
+  uint8_t mask[MIRGE_MAX_ADAPTER_LEN];  /* 4-bit IUPAC set per adapter base (A=1,C=2,G=4,T=8) */
+  uint8_t ascii[MIRGE_MAX_ADAPTER_LEN]; /* upper-cased adapter text */
+  int32_t n_counts[MIRGE_MAX_ADAPTER_LEN + 1]; /* number of 'N' before position i */
+  int32_t max_err[MIRGE_MAX_ADAPTER_LEN + 1];  /* floor(L * error_rate) evaluated in double */
+} mirge_adapter;
+
+/* The hot-path subset of miRge's args namespace (mirge/libs/parse.py), resolved on the host. */
+typedef struct mirge_trim_params {
+  int32_t n_mods;
+  int32_t mod_kind[MIRGE_MAX_MODS];
+  int32_t mod_a[MIRGE_MAX_MODS];
+  int32_t mod_b[MIRGE_MAX_MODS];
+  int32_t mod_c[MIRGE_MAX_MODS];
+  int32_t n_adapters;
+  int32_t times;      /* args.times (parse.py:96) */
+  int32_t min_len;    /* args.minimum_length (parse.py:83) */
+  int32_t umi_mode;   /* MIRGE_UMI_* */
+  int32_t umi5, umi3; /* -umi f,b */
+  int32_t qia_adapter_len; /* len(args.adapters[0][1]) (digest.py:121,343) */
+  int32_t count_mode; /* MIRGE_COUNT_* */
+  mirge_adapter adapters[MIRGE_MAX_ADAPTERS];
+} mirge_trim_params;
+
+/* Hash table slot (collapse).  tag == 0: empty.  ref == 0: claimed, key not yet published. */
+typedef struct mirge_slot {
+  uint32_t tag;   /* 32-bit filter derived from the 64-bit key hash, never 0 */
+  uint32_t ref;   /* 1 + word offset of the key in the arena */
+  uint32_t id;    /* dense key id (creation order) */
+  uint32_t count; /* occurrences since the last drain (current sample) */
+} mirge_slot;
+
+/* A collapse table: open addressing over `capacity` slots (power of two) + key arena.
+ * Packed key = u32 words: [len | n_exc << 16][ceil(len/16) words, 2 bits/base, base j in bits
+ * 2*(j%16) of word j/16, A=0 C=1 G=2 T=3][n_exc words: (pos << 8) | raw byte for every character
+ * that is not one of "ACGT" (its 2-bit code is 0)].  Key identity is word-wise equality, i.e.
+ * exact string equality of the original read text.
+ * ctrl (device, 8 x u64): [0] arena words used  [1] number of keys  [2] error flags
+ *                         [3] deferred count     [4] deferred count (second list) [5..7] scratch */
+typedef struct mirge_table {
+  mirge_slot *d_slots;
+  uint64_t capacity;
+  uint32_t *d_arena;
+  uint64_t arena_words;
+  uint32_t *d_key_ref; /* [max_keys] arena word offset of key id */
+  uint64_t max_keys;
+  uint64_t *d_ctrl;
+} mirge_table;
+
+/* One annotation library resident on the device (bowtie index replacement). */
+typedef struct mirge_library {
+  const uint32_t *d_packed;  /* 2 bits/base, all references concatenated */
+  const uint32_t *d_nmask;   /* 1 bit/base, 1 = reference base is not ACGT */
+  const uint32_t *d_ref_off; /* [n_refs + 1] first base of each reference */
+  uint32_t n_refs;
+  uint32_t n_bases;
+  const uint32_t *d_idx_kmer; /* [n_idx] sorted 16-mers (first base most significant, zero padded) */
+  const uint32_t *d_idx_pos;  /* [n_idx] base position of each k-mer */
+  uint32_t n_idx;
+  uint32_t bucket_bits;         /* d_idx_bucket is indexed by the top bucket_bits bits of a 16-mer */
+  const uint32_t *d_idx_bucket; /* [2^bucket_bits + 1] */
+} mirge_library;
+
+#define MIRGE_SELECT_LEN_LT26 0    /* round 0 (manifoldAlign.py:93)  */
+#define MIRGE_SELECT_LEN_GT25 1    /* round 1 (manifoldAlign.py:104) */
+#define MIRGE_SELECT_UNANNOTATED 2 /* rounds 2.. (manifoldAlign.py:120,129) */
+
+/* Effective bowtie policy of one round (manifoldAlign.py:85). */
+typedef struct mirge_round_policy {
+  int32_t round;       /* 0..9, stored into d_annot_round on a hit */
+  int32_t select;      /* MIRGE_SELECT_* */
+  int32_t seed_len;    /* 28 for -n mode, 0 = whole read (-v mode) */
+  int32_t seed_mm;     /* -n N / -v N */
+  int32_t total_mm;    /* 2 in -n mode (-e 70 with all-'I' qualities), N in -v mode */
+  int32_t trim5;       /* -5 */
+  int32_t trim3;       /* -3 */
+  int32_t strip_polyT; /* round 3: query = sequence without its trailing T{3,} run */
+} mirge_round_policy;
+
+#define MIRGE_NO_HIT 0xFFFFFFFFFFFFFFFFull
+/* hit word: (n_mismatch << 56) | (ref_index << 28) | offset ; canonical pick = minimum */
+#define MIRGE_HIT_MM(h) ((uint32_t)((h) >> 56))
+#define MIRGE_HIT_REF(h) ((uint32_t)(((h) >> 28) & 0xFFFFFFFu))
+#define MIRGE_HIT_OFF(h) ((uint32_t)((h)&0xFFFFFFFu))
+
+typedef struct mirge_ctx mirge_ctx;
+
+int mirge_abi_version(void);
+int mirge_ctx_create(int device, mirge_ctx **out);
+void mirge_ctx_destroy(mirge_ctx *ctx);
+const char *mirge_last_error(const mirge_ctx *ctx);
+
+/* stipulate() equivalent: install the resolved modifier pipeline (digest.py:59-101,110-122). */
+int mirge_set_trim_params(mirge_ctx *ctx, const mirge_trim_params *p);
+/* Emission slots per read: n_mods in HEAD mode (digest.py:354-373), else 1. */
+int mirge_trim_slots(const mirge_ctx *ctx);
+
+/* ---- stage 1a: FASTQ tokeniser (dnaio.read_chunks + FastqIter, digest.py:140,324) ---------- */
+uint64_t mirge_tokenise_scratch_bytes(uint64_t nbytes);
+/* Count line breaks of d_fastq[0:nbytes) (must start at a record boundary).  *n_records = number
+ * of complete 4-line records, *consumed = bytes they occupy.  is_final != 0: a last line without
+ * '\n' is complete (EOF rule) and trailing bytes that do not form a record are a format error. */
+int mirge_tokenise_sync(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, int is_final,
+                        void *d_scratch, uint64_t *n_records, uint64_t *consumed, void *stream);
+/* d_line_start[4r .. 4r+3] = first byte of the header / sequence / '+' / quality line of record r;
+ * d_line_start[4 * n_records] = one past the last record's '\n'.  Uses the scratch of the
+ * preceding mirge_tokenise_sync on the same bytes. */
+int mirge_line_index(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, const void *d_scratch,
+                     uint32_t *d_line_start, uint64_t n_records, void *stream);
+
+/* ---- stage 1b: trim + key emission (cutadapt(n) worker body, digest.py:325-373) ------------ */
+/* For record r and emission slot s (e = r * slots + s):
+ *   d_win[4e..4e+3] = (start, stop, ustart, ustop): emitted text = read[start:stop] + read[ustart:ustop]
+ *   d_key_off[e]    = word offset of the packed key in d_keys, or 0xFFFFFFFF when the slot is not
+ *                     counted (length filter, digest.py:348,362,368).
+ * d_trim_ctrl (8 x u64, zeroed by the caller): [0] key words used [1] emitted keys [2] error flags
+ * [3] first malformed record. */
+int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, const uint32_t *d_line_start,
+               uint64_t n_records, uint16_t *d_win, uint32_t *d_key_off, uint32_t *d_keys,
+               uint64_t keys_capacity_words, uint64_t *d_trim_ctrl, void *stream);
+
+/* ---- stage 2: collapse (digest.py:141-163,164-205,237-245) --------------------------------- */
+int mirge_table_reset(mirge_ctx *ctx, const mirge_table *t, void *stream);
+/* completeDict[key] += 1 for every emitted key of a batch.  d_deferred: u32[2 * n_slots] scratch. */
+int mirge_collapse_insert(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_keys,
+                          const uint32_t *d_key_off, uint64_t n_slots, uint32_t *d_deferred,
+                          void *stream);
+/* Merge (key, count) records: d_rec = [count][key words...] back to back, d_rec_off[i] = word
+ * offset of record i.  Used by the owner side of the hash-partitioned exchange. */
+int mirge_collapse_merge(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_rec,
+                         const uint32_t *d_rec_off, uint64_t n_rec, uint32_t *d_deferred, void *stream);
+/* Checks error flags / deferred leftovers of the table after a batch (synchronises `stream`). */
+int mirge_table_check_sync(mirge_ctx *ctx, const mirge_table *t, uint64_t *n_keys,
+                           uint64_t *arena_used, void *stream);
+/* End of a sample: append (key id, count) of every key seen since the last drain to d_ids/d_counts,
+ * zero the per-sample counts.  *d_n_out (u64 on device) receives the number of pairs. */
+int mirge_table_drain(mirge_ctx *ctx, const mirge_table *t, uint32_t *d_ids, uint32_t *d_counts,
+                      uint64_t out_capacity, uint64_t *d_n_out, void *stream);
+/* UMI second level (digest.py:164-205): for every (key, c) drained from `first`:
+ * centre = key[umi5 : len - umi3]; if len(centre) >= min_len: second[centre] += (dedup ? 1 : c). */
+int mirge_umi_collapse(mirge_ctx *ctx, const mirge_table *first, const uint32_t *d_ids,
+                       const uint32_t *d_counts, uint64_t n_pairs, const mirge_table *second,
+                       int umi5, int umi3, int min_len, int dedup, uint32_t *d_deferred,
+                       void *stream);
+/* Decode keys [id0, id0 + n) to ASCII rows of `stride` bytes (zero padded); d_len[i] = length. */
+int mirge_table_export_keys(mirge_ctx *ctx, const mirge_table *t, uint64_t id0, uint64_t n,
+                            uint8_t *d_ascii, uint32_t stride, uint32_t *d_len, void *stream);
+/* Hash partition for the multi-GPU exchange: d_dest[i] = hash64(centre of key id i) % n_parts,
+ * d_words[i] = 1 + key words (size of its exchange record). */
+int mirge_partition_plan(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_ids, uint64_t n,
+                         int umi5, int umi3, uint32_t n_parts, uint32_t *d_dest, uint32_t *d_words,
+                         void *stream);
+/* Write exchange records [count][key words] of pairs (d_ids[i], d_counts[i]) at word offsets
+ * d_rec_off[i] of d_rec. */
+int mirge_partition_pack(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_ids,
+                         const uint32_t *d_counts, uint64_t n, const uint32_t *d_rec_off,
+                         uint32_t *d_rec, void *stream);
+
+/* ---- stage 3: annotation rounds (bwtAlign, manifoldAlign.py:68-146) ------------------------ */
+/* 16-mer (zero padded, truncated at reference ends / ambiguous bases) of every base position:
+ * d_kmer[n_bases], d_valid[n_bases] = number of usable bases (0..16).  Input to the host-side
+ * sort that builds mirge_library.d_idx_*. */
+int mirge_lib_kmers(mirge_ctx *ctx, const mirge_library *lib, uint32_t *d_kmer, uint8_t *d_valid,
+                    void *stream);
+/* One bowtie round over the keys of table t.  Keys selected by policy->select that have a valid
+ * alignment get d_annot_round[id] = policy->round and d_hit[id] = canonical pick (minimum of
+ * (n_mismatch, reference index, offset) over the valid hit set). */
+int mirge_annotate_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_round_policy *policy,
+                         const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round,
+                         uint64_t *d_hit, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIRGE_B200_H */

@@ -1,0 +1,100 @@
+"""Shared helpers for the tests: small seeded FASTQ generator and parameter conversion."""
+import numpy as np
+
+import mirge_b200  # noqa: F401
+from mirge_b200 import params as P
+from oracle import pyoracle as po
+
+ILL = "TGGAATTCTCGGGTGCCAAGGAACTCCAG"
+QIA = "AACTGTAGGCACCATCAAT"
+LONG_AD = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACATCACGATCTCGTATGCC"
+
+
+def py_params(cfg: P.TrimConfig) -> po.TrimParams:
+    ads = []
+    for k, s in cfg.adapters:
+        sp = P.parse_adapter_spec(k, s)
+        ads.append(po.Adapter(sp.where, sp.sequence, cfg.error_rate, cfg.overlap, cfg.indels,
+                              cfg.match_adapter_wildcards))
+    return po.TrimParams(adapters=ads, times=cfg.times, nextseq_trim=cfg.nextseq_trim,
+                         quality_cutoff=cfg.quality_cutoff, quality_base=cfg.quality_base, trim_n=cfg.trim_n,
+                         cut=list(cfg.cut), minimum_length=cfg.minimum_length, umi=cfg.umi(),
+                         qiagenumi=cfg.qiagenumi, count_mode=cfg.count_mode)
+
+
+def random_fastq(n, seed=0, L=50, adapter=ILL, umi3=0, n_rate=0.01, lower_rate=0.0, err=0.03, indel=0.01,
+                 pool=200, crlf=False, final_newline=True, varlen=False, front=None):
+    """Small-RNA-like reads: insert (from a pool, so keys repeat) + adapter (with errors) + tail."""
+    rng = np.random.default_rng(seed)
+    B = np.array(list("ACGT"))
+    inserts = ["".join(rng.choice(B, rng.integers(10, 40))) for _ in range(pool)]
+    out = []
+    for i in range(n):
+        if rng.random() < 0.9:
+            ins = inserts[int(rng.zipf(1.3)) % pool]
+        else:
+            ins = "".join(rng.choice(B, rng.integers(0, 45)))
+        ad = list(adapter)
+        j = 0
+        while j < len(ad):
+            r = rng.random()
+            if r < err:
+                ad[j] = str(rng.choice(B))
+            elif r < err + indel / 2:
+                del ad[j]
+                continue
+            elif r < err + indel:
+                ad.insert(j, str(rng.choice(B)))
+                j += 1
+            j += 1
+        umi = "".join(rng.choice(B, umi3)) if umi3 else ""
+        s = (front or "") + ins + ("".join(ad) if rng.random() < 0.9 else "") + umi + "".join(rng.choice(B, L))
+        ln = L if not varlen else int(rng.integers(0, L + 1))
+        s = list(s[:ln])
+        for j in range(len(s)):
+            r = rng.random()
+            if r < n_rate:
+                s[j] = "N"
+            elif r < n_rate + lower_rate:
+                s[j] = s[j].lower()
+        s = "".join(s)
+        q0, q1 = rng.integers(25, 41), rng.integers(2, 30)
+        q = np.clip(np.linspace(q0, q1, max(len(s), 1))[: len(s)] + rng.integers(-5, 6, len(s)), 0, 41).astype(int)
+        if rng.random() < 0.1 and len(s) > 12:  # NextSeq dark-cycle poly-G tail with high quality
+            t = int(rng.integers(1, 12))
+            s = s[:-t] + "G" * t
+            q[-t:] = 35
+        nl = "\r\n" if crlf else "\n"
+        out.append("@SYN.%d %d length=%d%s%s%s+%s%s%s"
+                   % (i, i, len(s), nl, s, nl, nl, "".join(chr(33 + int(v)) for v in q), nl))
+    data = "".join(out)
+    if not final_newline:
+        data = data.rstrip("\r\n")
+    return data.encode()
+
+
+CONFIGS = {
+    "default": P.TrimConfig(adapters=[("back", ILL)]),
+    "release": P.TrimConfig(adapters=[("back", ILL)], count_mode="release"),
+    "nextseq": P.TrimConfig(adapters=[("back", ILL)], nextseq_trim=20, quality_cutoff="20"),
+    "q5q3_nx_cut": P.TrimConfig(adapters=[("back", ILL)], quality_cutoff="15,20", trim_n=True, cut=[2, -1]),
+    "umi44": P.TrimConfig(adapters=[("back", ILL)], uniq_mol_ids="4,4"),
+    "umi40": P.TrimConfig(adapters=[("back", ILL)], uniq_mol_ids="4,0", count_mode="release"),
+    "qiagen": P.TrimConfig(adapters=[("back", QIA)], uniq_mol_ids="0,12", qiagenumi=True),
+    "front_back": P.TrimConfig(adapters=[("back", ILL), ("front", "GTTCAGAGTTCTACAGTCCGACGATC")]),
+    "noindel": P.TrimConfig(adapters=[("back", ILL)], indels=False),
+    "wild": P.TrimConfig(adapters=[("back", "TGGAATTCNNGGGTGCCAAGGRACTCCAG")], error_rate=0.2, overlap=5),
+    "noq_m1": P.TrimConfig(adapters=[("back", ILL)], quality_cutoff=None, minimum_length=1, times=2),
+    "long_adapter": P.TrimConfig(adapters=[("back", LONG_AD)]),
+}
+
+# keyword arguments for random_fastq that exercise each configuration
+CONFIG_DATA = {
+    "qiagen": dict(adapter=QIA, umi3=12, L=75),
+    "umi44": dict(L=60),
+    "umi40": dict(L=60),
+    "front_back": dict(front="CAGTCCGACGATC"),
+    "wild": dict(adapter=ILL),
+    "long_adapter": dict(adapter=LONG_AD, L=90),
+    "noq_m1": dict(varlen=True),
+}
