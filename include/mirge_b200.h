@@ -189,7 +189,7 @@ int mirge_line_index(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, co
  *                     counted (length filter, digest.py:348,362,368).
  * d_trim_ctrl (8 x u64, zeroed by the caller): [0] key words used [1] emitted keys [2] error flags
  * [3] first malformed record. */
-int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, const uint32_t *d_line_start,
+int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, const uint32_t *d_line_start,
                uint64_t n_records, uint16_t *d_win, uint32_t *d_key_off, uint32_t *d_keys,
                uint64_t keys_capacity_words, uint64_t *d_trim_ctrl, void *stream);
 
@@ -203,6 +203,10 @@ int mirge_collapse_insert(mirge_ctx *ctx, const mirge_table *t, const uint32_t *
  * offset of record i.  Used by the owner side of the hash-partitioned exchange. */
 int mirge_collapse_merge(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_rec,
                          const uint32_t *d_rec_off, uint64_t n_rec, uint32_t *d_deferred, void *stream);
+/* Growth: re-insert every slot of old_t into the larger slot array of new_t (zeroed here).  Both
+ * tables must reference the same key text (new_t->d_arena holds a copy of the used arena words),
+ * the same d_key_ref contents and the same d_ctrl.  Key ids, refs and counts are preserved. */
+int mirge_table_rehash(mirge_ctx *ctx, const mirge_table *old_t, const mirge_table *new_t, void *stream);
 /* Checks error flags / deferred leftovers of the table after a batch (synchronises `stream`). */
 int mirge_table_check_sync(mirge_ctx *ctx, const mirge_table *t, uint64_t *n_keys,
                            uint64_t *arena_used, void *stream);

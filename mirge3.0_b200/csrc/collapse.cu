@@ -1,0 +1,482 @@
+// collapse.cu -- GPU hash-table collapse of emitted keys into (unique sequence -> count).
+// Replaces the per-chunk dict of the worker and the parent merge loop (mirge/libs/digest.py:349-373
+// and :141-163), the UMI second level (:164-205) and the per-sample column extraction feeding the
+// sample x sequence matrix (:237-245).
+//
+// Table: open addressing (linear probing) over 16-byte slots {tag, ref, id, count}.  A slot is
+// claimed with one 32-bit CAS on the tag; the owner then copies the packed key into an append-only
+// arena (warp-aggregated bump allocation) and publishes `ref`.  Key identity is decided by comparing
+// the full packed key in the arena, never by the hash alone, so counts are exact.  A thread that
+// meets a claimed-but-unpublished slot polls a bounded number of times and otherwise defers its key
+// to a retry list that a follow-up kernel drains with one lane per warp (no intra-warp waiting),
+// so the insert path cannot dead-lock.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+namespace cg = cooperative_groups;
+
+#define COL_THREADS 256
+#define SPIN_POLLS 64
+#define MAX_PROBES 8192ull  // the host keeps the load factor <= 0.5; longer runs mean "table too small"
+#define ERR_ARENA_FULL 1ull
+#define ERR_KEYS_FULL 2ull
+#define ERR_TABLE_FULL 4ull
+#define ERR_STUCK 8ull
+#define ERR_OUT_FULL 16ull
+
+#define MAX_KEY_WORDS (1 + (MIRGE_MAX_READ_LEN + 15) / 16 + MIRGE_MAX_READ_LEN)
+
+__device__ __forceinline__ uint64_t hash_key(const uint32_t *key, uint32_t nw) {
+  uint64_t h = 0x243F6A8885A308D3ull;
+  for (uint32_t i = 0; i < nw; ++i) h = hash_step(h, key[i]);
+  return mix64(h);
+}
+
+enum { INS_OK = 0, INS_DEFER = 1, INS_FAIL = 2 };
+
+// completeDict[key] += add.  `unbounded`: keep polling an unpublished slot (retry kernel only).
+__device__ __forceinline__ int table_insert(const mirge_table &t, const uint32_t *key, uint32_t nw, uint32_t add,
+                                            uint64_t h, bool unbounded) {
+  unsigned long long *ctrl = (unsigned long long *)t.d_ctrl;
+  const uint64_t mask = t.capacity - 1;
+  uint32_t tag = (uint32_t)(h >> 32);
+  if (tag == 0) tag = 1;
+  uint64_t idx = h & mask;
+  const uint64_t max_probe = t.capacity < MAX_PROBES ? t.capacity : MAX_PROBES;
+  for (uint64_t probe = 0; probe < max_probe; ++probe) {
+    mirge_slot *s = t.d_slots + idx;
+    uint4 v = ld_volatile_u4(s);
+    if (v.x == 0) {
+      const uint32_t old = atomicCAS(&s->tag, 0u, tag);
+      if (old == 0) {
+        // owner: allocate id + arena space (aggregated over the lanes that are here together)
+        cg::coalesced_group g = cg::coalesced_threads();
+        uint32_t pre = nw;
+        for (int d = 1; d < (int)g.size(); d <<= 1) {
+          uint32_t x = g.shfl_up(pre, d);
+          if ((int)g.thread_rank() >= d) pre += x;
+        }
+        const uint32_t total = g.shfl(pre, g.size() - 1);
+        unsigned long long base_w = 0, base_id = 0;
+        if (g.thread_rank() == 0) {
+          base_w = atomicAdd(ctrl + 0, (unsigned long long)total);
+          base_id = atomicAdd(ctrl + 1, (unsigned long long)g.size());
+        }
+        base_w = g.shfl(base_w, 0);
+        base_id = g.shfl(base_id, 0);
+        const unsigned long long aoff = base_w + pre - nw, id = base_id + g.thread_rank();
+        if (aoff + nw > t.arena_words || aoff + nw >= 0xFFFFFFF0ull || id >= t.max_keys) {
+          atomicOr(ctrl + 2, id >= t.max_keys ? ERR_KEYS_FULL : ERR_ARENA_FULL);
+          atomicExch(&s->ref, 0xFFFFFFFFu);  // poison: waiters give up immediately
+          return INS_FAIL;
+        }
+        uint32_t *dst = t.d_arena + aoff;
+        for (uint32_t i = 0; i < nw; ++i) dst[i] = key[i];
+        t.d_key_ref[id] = (uint32_t)aoff;
+        s->id = (uint32_t)id;
+        atomicAdd(&s->count, add);
+        __threadfence();
+        atomicExch(&s->ref, (uint32_t)aoff + 1u);
+        return INS_OK;
+      }
+      v.x = old;
+      v.y = 0;  // re-read below
+    }
+    if (v.x == tag) {
+      uint32_t ref = v.y;
+      if (ref == 0) {
+        for (int k = 0; ref == 0 && (unbounded ? k < (1 << 16) : k < SPIN_POLLS); ++k) {
+          __nanosleep(40);
+          ref = ld_volatile_u32(&s->ref);
+        }
+        if (ref == 0) {
+          if (unbounded) { atomicOr(ctrl + 2, ERR_STUCK); return INS_FAIL; }
+          return INS_DEFER;
+        }
+      }
+      if (ref == 0xFFFFFFFFu) return INS_FAIL;  // owner ran out of space (error already flagged)
+      __threadfence();
+      const uint32_t *k2 = t.d_arena + (ref - 1u);
+      bool same = true;
+      for (uint32_t i = 0; i < nw; ++i) {
+        if (ld_cg_u32(k2 + i) != key[i]) { same = false; break; }
+      }
+      if (same) {
+        atomicAdd(&s->count, add);
+        return INS_OK;
+      }
+    }
+    idx = (idx + 1) & mask;
+  }
+  atomicOr(ctrl + 2, ERR_TABLE_FULL);
+  return INS_FAIL;
+}
+
+__device__ __forceinline__ void defer_item(unsigned long long *counter, uint32_t *list, uint32_t item) {
+  cg::coalesced_group g = cg::coalesced_threads();
+  unsigned long long base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(counter, (unsigned long long)g.size());
+  base = g.shfl(base, 0);
+  list[base + g.thread_rank()] = item;
+}
+
+// mode 0: items are emission slots (keys/key_off, add = 1)
+// mode 1: items are exchange records [count][key...] at rec_off[i]
+__device__ __forceinline__ void item_key(int mode, const uint32_t *keys, const uint32_t *off, uint64_t i,
+                                         const uint32_t *&key, uint32_t &add) {
+  const uint32_t o = off[i];
+  if (o == 0xFFFFFFFFu) { key = nullptr; add = 0; return; }
+  if (mode == 0) { key = keys + o; add = 1; }
+  else { key = keys + o + 1; add = keys[o]; }
+}
+
+__global__ void __launch_bounds__(COL_THREADS)
+collapse_insert_kernel(mirge_table t, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ off, uint64_t n,
+                       int mode, uint32_t *__restrict__ deferred) {
+  const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t *key; uint32_t add;
+  item_key(mode, keys, off, i, key, add);
+  if (!key || add == 0) return;
+  const uint32_t nw = key_words(key[0]);
+  const uint64_t h = hash_key(key, nw);
+  if (table_insert(t, key, nw, add, h, false) == INS_DEFER)
+    defer_item((unsigned long long *)t.d_ctrl + 3, deferred, (uint32_t)i);
+}
+
+// drains the deferred list: one lane per warp, so a waiter never shares a warp with its claimant
+__global__ void __launch_bounds__(COL_THREADS)
+collapse_retry_kernel(mirge_table t, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ off, int mode,
+                      const uint32_t *__restrict__ deferred) {
+  if (threadIdx.x & 31) return;
+  const unsigned long long nd = ((unsigned long long *)t.d_ctrl)[3];
+  const uint64_t warp = ((uint64_t)blockIdx.x * COL_THREADS + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * COL_THREADS) >> 5;
+  for (uint64_t j = warp; j < nd; j += nwarps) {
+    const uint64_t i = deferred[j];
+    const uint32_t *key; uint32_t add;
+    item_key(mode, keys, off, i, key, add);
+    if (!key) continue;
+    const uint32_t nw = key_words(key[0]);
+    table_insert(t, key, nw, add, hash_key(key, nw), true);
+  }
+}
+
+__global__ void clear_deferred_kernel(unsigned long long *ctrl) { ctrl[3] = 0; }
+
+static int check_table(mirge_ctx *ctx, const mirge_table *t) {
+  if (!t || !t->d_slots || !t->d_arena || !t->d_key_ref || !t->d_ctrl) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "table: null buffer");
+  if (t->capacity < 2 || (t->capacity & (t->capacity - 1))) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "table: capacity must be a power of two");
+  if (((uintptr_t)t->d_slots & 15)) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "table: slots must be 16-byte aligned");
+  return MIRGE_OK;
+}
+
+extern "C" int mirge_table_reset(mirge_ctx *ctx, const mirge_table *t, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  int rc = check_table(ctx, t);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  MIRGE_CUDA(ctx, cudaMemsetAsync(t->d_slots, 0, t->capacity * sizeof(mirge_slot), stream));
+  MIRGE_CUDA(ctx, cudaMemsetAsync(t->d_ctrl, 0, 8 * sizeof(uint64_t), stream));
+  return MIRGE_OK;
+}
+
+static int run_insert(mirge_ctx *ctx, const mirge_table *t, const uint32_t *keys, const uint32_t *off, uint64_t n, int mode,
+                      uint32_t *d_deferred, cudaStream_t stream) {
+  int rc = check_table(ctx, t);
+  if (rc) return rc;
+  if (n == 0) return MIRGE_OK;
+  if (!keys || !off || !d_deferred) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "collapse: null buffer");
+  if (n > 0xFFFFFFFFull) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "collapse: more than 2^32 items in one batch");
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  const unsigned grid = (unsigned)((n + COL_THREADS - 1) / COL_THREADS);
+  collapse_insert_kernel<<<grid, COL_THREADS, 0, stream>>>(*t, keys, off, n, mode, d_deferred);
+  MIRGE_LAUNCH_CHECK(ctx, "collapse_insert_kernel");
+  collapse_retry_kernel<<<ctx->sm_count, COL_THREADS, 0, stream>>>(*t, keys, off, mode, d_deferred);
+  MIRGE_LAUNCH_CHECK(ctx, "collapse_retry_kernel");
+  clear_deferred_kernel<<<1, 1, 0, stream>>>((unsigned long long *)t->d_ctrl);
+  MIRGE_LAUNCH_CHECK(ctx, "clear_deferred_kernel");
+  return MIRGE_OK;
+}
+
+extern "C" int mirge_collapse_insert(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_keys, const uint32_t *d_key_off,
+                                     uint64_t n_slots, uint32_t *d_deferred, void *stream) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  return run_insert(ctx, t, d_keys, d_key_off, n_slots, 0, d_deferred, (cudaStream_t)stream);
+}
+
+extern "C" int mirge_collapse_merge(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_rec, const uint32_t *d_rec_off,
+                                    uint64_t n_rec, uint32_t *d_deferred, void *stream) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  return run_insert(ctx, t, d_rec, d_rec_off, n_rec, 1, d_deferred, (cudaStream_t)stream);
+}
+
+extern "C" int mirge_table_check_sync(mirge_ctx *ctx, const mirge_table *t, uint64_t *n_keys, uint64_t *arena_used, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  int rc = check_table(ctx, t);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  MIRGE_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, t->d_ctrl, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+  MIRGE_CUDA(ctx, cudaStreamSynchronize(stream));
+  const uint64_t *c = ctx->h_pinned;
+  if (n_keys) *n_keys = c[1];
+  if (arena_used) *arena_used = c[0];
+  if (c[2] & ERR_STUCK) MIRGE_FAIL(ctx, MIRGE_ERR_CUDA, "collapse: a claimed slot was never published (internal error)");
+  if (c[2] & (ERR_ARENA_FULL | ERR_KEYS_FULL | ERR_TABLE_FULL | ERR_OUT_FULL))
+    MIRGE_FAIL(ctx, MIRGE_ERR_CAPACITY, "collapse: table capacity exceeded (flags 0x%llx: 1 arena, 2 key ids, 4 slots, 16 output)",
+               (unsigned long long)c[2]);
+  return MIRGE_OK;
+}
+
+// ------------------------------------------------------------------ growth (rehash) ---------
+
+// Re-insert every occupied slot of `o` into the (larger, zeroed) slot array of `n`.  Keys are
+// distinct already, so no comparison is needed; ids, refs and counts are preserved.
+__global__ void __launch_bounds__(COL_THREADS) rehash_kernel(mirge_table o, mirge_table n) {
+  const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
+  if (i >= o.capacity) return;
+  const uint4 v = *(const uint4 *)(o.d_slots + i);
+  if (v.x == 0) return;
+  const uint32_t *key = n.d_arena + (v.y - 1u);
+  const uint64_t h = hash_key(key, key_words(key[0]));
+  const uint64_t mask = n.capacity - 1;
+  uint64_t idx = h & mask;
+  for (uint64_t probe = 0; probe < n.capacity; ++probe) {
+    mirge_slot *s = n.d_slots + idx;
+    if (atomicCAS(&s->tag, 0u, v.x) == 0u) {
+      s->ref = v.y; s->id = v.z; s->count = v.w;
+      return;
+    }
+    idx = (idx + 1) & mask;
+  }
+  atomicOr((unsigned long long *)n.d_ctrl + 2, ERR_TABLE_FULL);
+}
+
+extern "C" int mirge_table_rehash(mirge_ctx *ctx, const mirge_table *old_t, const mirge_table *new_t, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  int rc = check_table(ctx, old_t);
+  if (rc) return rc;
+  rc = check_table(ctx, new_t);
+  if (rc) return rc;
+  if (new_t->capacity < old_t->capacity) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "rehash: new table is smaller");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  MIRGE_CUDA(ctx, cudaMemsetAsync(new_t->d_slots, 0, new_t->capacity * sizeof(mirge_slot), stream));
+  rehash_kernel<<<(unsigned)((old_t->capacity + COL_THREADS - 1) / COL_THREADS), COL_THREADS, 0, stream>>>(*old_t, *new_t);
+  MIRGE_LAUNCH_CHECK(ctx, "rehash_kernel");
+  return MIRGE_OK;
+}
+
+// ------------------------------------------------------------------ per-sample drain --------
+
+__global__ void __launch_bounds__(COL_THREADS)
+drain_kernel(mirge_table t, uint32_t *__restrict__ ids, uint32_t *__restrict__ counts, uint64_t cap, unsigned long long *n_out) {
+  const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
+  if (i >= t.capacity) return;
+  mirge_slot *s = t.d_slots + i;
+  const uint4 v = *(const uint4 *)s;
+  if (v.x == 0 || v.w == 0) return;
+  cg::coalesced_group g = cg::coalesced_threads();
+  unsigned long long base = 0;
+  if (g.thread_rank() == 0) base = atomicAdd(n_out, (unsigned long long)g.size());
+  base = g.shfl(base, 0) + g.thread_rank();
+  if (base < cap) {
+    ids[base] = v.z;
+    counts[base] = v.w;
+  } else {
+    atomicOr((unsigned long long *)t.d_ctrl + 2, ERR_OUT_FULL);
+  }
+  s->count = 0;
+}
+
+extern "C" int mirge_table_drain(mirge_ctx *ctx, const mirge_table *t, uint32_t *d_ids, uint32_t *d_counts, uint64_t out_capacity,
+                                 uint64_t *d_n_out, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  int rc = check_table(ctx, t);
+  if (rc) return rc;
+  if (!d_ids || !d_counts || !d_n_out) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "drain: null buffer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  MIRGE_CUDA(ctx, cudaMemsetAsync(d_n_out, 0, 8, stream));
+  const unsigned grid = (unsigned)((t->capacity + COL_THREADS - 1) / COL_THREADS);
+  drain_kernel<<<grid, COL_THREADS, 0, stream>>>(*t, d_ids, d_counts, out_capacity, (unsigned long long *)d_n_out);
+  MIRGE_LAUNCH_CHECK(ctx, "drain_kernel");
+  return MIRGE_OK;
+}
+
+// ------------------------------------------------------------------ key slicing --------------
+
+__device__ __forceinline__ uint32_t key_base(const uint32_t *key, uint32_t j) { return (key[1 + (j >> 4)] >> (2 * (j & 15))) & 3u; }
+
+// out = key[f : len - b] as a packed key (exceptions re-based); returns its word count
+__device__ __forceinline__ uint32_t slice_key(const uint32_t *key, int f, int b, uint32_t *out) {
+  const uint32_t hdr = key[0];
+  const int len = (int)key_len(hdr), nexc = (int)key_nexc(hdr);
+  int cl = len - f - b;
+  if (cl < 0) cl = 0;
+  const int lo = (cl > 0) ? f : 0;
+  const uint32_t npay_in = (uint32_t)(len + 15) >> 4, npay = (uint32_t)(cl + 15) >> 4;
+  for (uint32_t w = 0; w < npay; ++w) {
+    uint32_t word = 0;
+    for (int q = 0; q < 16; ++q) {
+      const int j = (int)w * 16 + q;
+      if (j < cl) word |= key_base(key, (uint32_t)(lo + j)) << (2 * q);
+    }
+    out[1 + w] = word;
+  }
+  uint32_t xo = 0;
+  for (int x = 0; x < nexc; ++x) {
+    const uint32_t e = key[1 + npay_in + x];
+    const int pos = (int)(e >> 8);
+    if (pos >= lo && pos < lo + cl) out[1 + npay + xo++] = ((uint32_t)(pos - lo) << 8) | (e & 0xFFu);
+  }
+  out[0] = (uint32_t)cl | (xo << 16);
+  return 1u + npay + xo;
+}
+
+__global__ void __launch_bounds__(128)
+umi_collapse_kernel(mirge_table first, const uint32_t *__restrict__ ids, const uint32_t *__restrict__ counts, uint64_t n,
+                    mirge_table second, int f, int b, int min_len, int dedup, uint32_t *__restrict__ deferred, int retry) {
+  uint32_t buf[MAX_KEY_WORDS];
+  unsigned long long *ctrl2 = (unsigned long long *)second.d_ctrl;
+  uint64_t i, stride;
+  uint64_t n_items = n;
+  if (retry) {
+    if (threadIdx.x & 31) return;
+    n_items = ctrl2[3];
+    i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    stride = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  } else {
+    i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    stride = (uint64_t)gridDim.x * blockDim.x;
+  }
+  for (; i < n_items; i += stride) {
+    const uint64_t item = retry ? deferred[i] : i;
+    const uint32_t *key = first.d_arena + first.d_key_ref[ids[item]];
+    const int len = (int)key_len(key[0]);
+    int cl = len - f - b;
+    if (cl < 0) cl = 0;
+    if (cl < min_len) continue;
+    const uint32_t nw = slice_key(key, f, b, buf);
+    const uint32_t add = dedup ? 1u : counts[item];
+    const int rc = table_insert(second, buf, nw, add, hash_key(buf, nw), retry != 0);
+    if (rc == INS_DEFER) defer_item(ctrl2 + 3, deferred, (uint32_t)item);
+  }
+}
+
+extern "C" int mirge_umi_collapse(mirge_ctx *ctx, const mirge_table *first, const uint32_t *d_ids, const uint32_t *d_counts,
+                                  uint64_t n_pairs, const mirge_table *second, int umi5, int umi3, int min_len, int dedup,
+                                  uint32_t *d_deferred, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  int rc = check_table(ctx, first);
+  if (rc) return rc;
+  rc = check_table(ctx, second);
+  if (rc) return rc;
+  if (n_pairs == 0) return MIRGE_OK;
+  if (!d_ids || !d_counts || !d_deferred) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "umi_collapse: null buffer");
+  if (umi5 < 0 || umi3 < 0) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "umi_collapse: negative UMI length");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  const unsigned grid = (unsigned)((n_pairs + 127) / 128);
+  umi_collapse_kernel<<<grid, 128, 0, stream>>>(*first, d_ids, d_counts, n_pairs, *second, umi5, umi3, min_len, dedup, d_deferred, 0);
+  MIRGE_LAUNCH_CHECK(ctx, "umi_collapse_kernel");
+  umi_collapse_kernel<<<ctx->sm_count, 128, 0, stream>>>(*first, d_ids, d_counts, n_pairs, *second, umi5, umi3, min_len, dedup, d_deferred, 1);
+  MIRGE_LAUNCH_CHECK(ctx, "umi_collapse_kernel(retry)");
+  clear_deferred_kernel<<<1, 1, 0, stream>>>((unsigned long long *)second->d_ctrl);
+  return MIRGE_OK;
+}
+
+// ------------------------------------------------------------------ export -------------------
+
+__global__ void __launch_bounds__(COL_THREADS)
+export_keys_kernel(mirge_table t, uint64_t id0, uint64_t n, uint8_t *__restrict__ ascii, uint32_t stride, uint32_t *__restrict__ lens) {
+  const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t *key = t.d_arena + t.d_key_ref[id0 + i];
+  const uint32_t hdr = key[0], len = key_len(hdr), nexc = key_nexc(hdr), npay = (len + 15) >> 4;
+  uint8_t *row = ascii + i * stride;
+  const uint32_t lim = len < stride ? len : stride;
+  for (uint32_t j = 0; j < lim; ++j) row[j] = "ACGT"[key_base(key, j)];
+  for (uint32_t j = lim; j < stride; ++j) row[j] = 0;
+  for (uint32_t x = 0; x < nexc; ++x) {
+    const uint32_t e = key[1 + npay + x];
+    if ((e >> 8) < lim) row[e >> 8] = (uint8_t)(e & 0xFFu);
+  }
+  lens[i] = len;
+}
+
+extern "C" int mirge_table_export_keys(mirge_ctx *ctx, const mirge_table *t, uint64_t id0, uint64_t n, uint8_t *d_ascii,
+                                       uint32_t stride, uint32_t *d_len, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  int rc = check_table(ctx, t);
+  if (rc) return rc;
+  if (n == 0) return MIRGE_OK;
+  if (!d_ascii || !d_len || stride == 0) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "export: null buffer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  export_keys_kernel<<<(unsigned)((n + COL_THREADS - 1) / COL_THREADS), COL_THREADS, 0, stream>>>(*t, id0, n, d_ascii, stride, d_len);
+  MIRGE_LAUNCH_CHECK(ctx, "export_keys_kernel");
+  return MIRGE_OK;
+}
+
+// ------------------------------------------------------------------ hash partition -----------
+
+__global__ void __launch_bounds__(128)
+partition_plan_kernel(mirge_table t, const uint32_t *__restrict__ ids, uint64_t n, int f, int b, uint32_t n_parts,
+                      uint32_t *__restrict__ dest, uint32_t *__restrict__ words) {
+  uint32_t buf[MAX_KEY_WORDS];
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t *key = t.d_arena + t.d_key_ref[ids[i]];
+  uint64_t h;
+  if (f == 0 && b == 0) {
+    h = hash_key(key, key_words(key[0]));
+  } else {
+    const uint32_t nw = slice_key(key, f, b, buf);
+    h = hash_key(buf, nw);
+  }
+  dest[i] = (uint32_t)(mix64(h ^ 0x5851F42D4C957F2Dull) % n_parts);
+  words[i] = 1u + key_words(key[0]);
+}
+
+extern "C" int mirge_partition_plan(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_ids, uint64_t n, int umi5, int umi3,
+                                    uint32_t n_parts, uint32_t *d_dest, uint32_t *d_words, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  int rc = check_table(ctx, t);
+  if (rc) return rc;
+  if (n == 0) return MIRGE_OK;
+  if (!d_ids || !d_dest || !d_words || n_parts == 0) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "partition_plan: bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  partition_plan_kernel<<<(unsigned)((n + 127) / 128), 128, 0, stream>>>(*t, d_ids, n, umi5, umi3, n_parts, d_dest, d_words);
+  MIRGE_LAUNCH_CHECK(ctx, "partition_plan_kernel");
+  return MIRGE_OK;
+}
+
+__global__ void __launch_bounds__(COL_THREADS)
+partition_pack_kernel(mirge_table t, const uint32_t *__restrict__ ids, const uint32_t *__restrict__ counts, uint64_t n,
+                      const uint32_t *__restrict__ rec_off, uint32_t *__restrict__ rec) {
+  const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t *key = t.d_arena + t.d_key_ref[ids[i]];
+  const uint32_t nw = key_words(key[0]);
+  uint32_t *o = rec + rec_off[i];
+  o[0] = counts[i];
+  for (uint32_t w = 0; w < nw; ++w) o[1 + w] = key[w];
+}
+
+extern "C" int mirge_partition_pack(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_ids, const uint32_t *d_counts, uint64_t n,
+                                    const uint32_t *d_rec_off, uint32_t *d_rec, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  int rc = check_table(ctx, t);
+  if (rc) return rc;
+  if (n == 0) return MIRGE_OK;
+  if (!d_ids || !d_counts || !d_rec_off || !d_rec) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "partition_pack: null buffer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  partition_pack_kernel<<<(unsigned)((n + COL_THREADS - 1) / COL_THREADS), COL_THREADS, 0, stream>>>(*t, d_ids, d_counts, n, d_rec_off, d_rec);
+  MIRGE_LAUNCH_CHECK(ctx, "partition_pack_kernel");
+  return MIRGE_OK;
+}

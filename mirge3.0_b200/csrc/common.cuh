@@ -1,0 +1,87 @@
+// common.cuh -- shared device/host helpers of libmirge_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/mirge_b200.h"
+
+struct mirge_ctx {
+  int device;
+  char err[512];
+  uint64_t *h_pinned;  // 8 x u64 pinned staging for small D2H reads
+  uint64_t *d_small;   // 8 x u64 device scratch
+  mirge_trim_params params;
+  int params_set;
+  int max_adapter_len;
+  int sm_count;
+};
+
+#define MIRGE_FAIL(ctx, code, ...)                         \
+  do {                                                     \
+    snprintf((ctx)->err, sizeof((ctx)->err), __VA_ARGS__); \
+    return (code);                                         \
+  } while (0)
+
+#define MIRGE_CUDA(ctx, expr)                                                                     \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess) MIRGE_FAIL(ctx, MIRGE_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define MIRGE_LAUNCH_CHECK(ctx, name)                                                               \
+  do {                                                                                              \
+    cudaError_t _e = cudaGetLastError();                                                            \
+    if (_e != cudaSuccess) MIRGE_FAIL(ctx, MIRGE_ERR_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+// ---------------------------------------------------------------- packed keys ----------------
+// key[0] = len | n_exc << 16 ; payload ceil(len/16) words ; n_exc exception words (pos << 8 | byte)
+__host__ __device__ __forceinline__ uint32_t key_len(uint32_t hdr) { return hdr & 0xFFFFu; }
+__host__ __device__ __forceinline__ uint32_t key_nexc(uint32_t hdr) { return hdr >> 16; }
+__host__ __device__ __forceinline__ uint32_t key_words(uint32_t hdr) {
+  return 1u + ((key_len(hdr) + 15u) >> 4) + key_nexc(hdr);
+}
+
+// base byte -> 2-bit code (A=0 C=1 G=2 T=3) or 4 for anything that is not exactly one of "ACGT"
+__device__ __forceinline__ uint32_t base_code_exact(uint32_t c) {
+  // 'A'=0x41 'C'=0x43 'G'=0x47 'T'=0x54
+  uint32_t code = (c == 'A') ? 0u : (c == 'C') ? 1u : (c == 'G') ? 2u : (c == 'T') ? 3u : 4u;
+  return code;
+}
+// case-insensitive class used for matching: a/A.. -> 0..3, everything else (incl. U? no: cutadapt
+// upper-cases the read, bowtie treats non-ACGT as N) -> 4
+__device__ __forceinline__ uint32_t base_code_upper(uint32_t c) {
+  c &= ~0x20u;
+  return (c == 'A') ? 0u : (c == 'C') ? 1u : (c == 'G') ? 2u : (c == 'T') ? 3u : 4u;
+}
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t h) {
+  h ^= h >> 33;
+  h *= 0xff51afd7ed558ccdull;
+  h ^= h >> 33;
+  h *= 0xc4ceb9fe1a85ec53ull;
+  h ^= h >> 33;
+  return h;
+}
+__host__ __device__ __forceinline__ uint64_t hash_step(uint64_t h, uint32_t w) {
+  return (h ^ w) * 0x9E3779B97F4A7C15ull + 0x7F4A7C15u + (h >> 29);
+}
+
+__device__ __forceinline__ uint4 ld_volatile_u4(const void *p) {
+  uint4 r;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const void *p) {
+  uint32_t r;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint32_t ld_cg_u32(const uint32_t *p) { return __ldcg(p); }
+__device__ __forceinline__ uint4 ld_stream_u4(const void *p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}

@@ -1,0 +1,300 @@
+// tokenise.cu -- FASTQ tokeniser: line-break census + record/line index.
+// Replaces dnaio.read_chunks' record-boundary search and the line splitting of dnaio's FastqIter
+// (reference call sites: mirge/libs/digest.py:140 and :324).
+//
+// Layout: the byte stream is cut into tiles of TOK_TILE bytes (one CTA each, 32 contiguous bytes
+// per thread, two coalesced 128-bit loads).  Pass 1 counts '\n' per tile and per group of
+// TOK_GROUP tiles; a one-CTA scan turns group totals into prefixes; pass 2 re-reads the tile
+// (L2-resident for batches below the 126 MB L2, otherwise streamed) and scatters the start offset
+// of every line: line_start[g + 1] = position after the g-th '\n'.  Four consecutive entries are
+// the header / sequence / '+' / quality line of one record, so the trim kernel fetches one
+// aligned uint4 per read.
+#include "common.cuh"
+
+#define TOK_TILE 8192
+#define TOK_THREADS 256
+#define TOK_GROUP 1024
+
+struct TokScratch {
+  uint32_t *tile_counts;
+  uint32_t *group_totals;
+  uint64_t *group_prefix;
+  uint64_t n_tiles, n_groups;
+};
+
+static inline uint64_t align16(uint64_t x) { return (x + 15) & ~15ull; }
+
+static TokScratch tok_layout(void *scratch, uint64_t nbytes) {
+  TokScratch s;
+  s.n_tiles = (nbytes + TOK_TILE - 1) / TOK_TILE;
+  s.n_groups = (s.n_tiles + TOK_GROUP - 1) / TOK_GROUP;
+  uint8_t *p = (uint8_t *)scratch;
+  s.tile_counts = (uint32_t *)p;
+  p += align16(s.n_tiles * 4 + 4);
+  s.group_totals = (uint32_t *)p;
+  p += align16(s.n_groups * 4 + 4);
+  s.group_prefix = (uint64_t *)p;
+  return s;
+}
+
+extern "C" uint64_t mirge_tokenise_scratch_bytes(uint64_t nbytes) {
+  nbytes += 16;  // alignment skew
+  uint64_t n_tiles = (nbytes + TOK_TILE - 1) / TOK_TILE;
+  uint64_t n_groups = (n_tiles + TOK_GROUP - 1) / TOK_GROUP;
+  return align16(n_tiles * 4 + 4) + align16(n_groups * 4 + 4) + align16((n_groups + 1) * 8) + 64;
+}
+
+// 32 bytes of the stream starting at pos -> 8 words (zero filled past n)
+__device__ __forceinline__ void load32(const uint8_t *fq, uint64_t n, uint64_t pos, uint32_t w[8]) {
+  if (pos + 32 <= n) {
+    uint4 a = ld_stream_u4(fq + pos), b = ld_stream_u4(fq + pos + 16);
+    w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+    w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        uint64_t q = pos + 4 * k + b;
+        if (q < n) v |= (uint32_t)fq[q] << (8 * b);
+      }
+      w[k] = v;
+    }
+  }
+}
+
+// bit i set <=> byte i of the 32 bytes is '\n'
+__device__ __forceinline__ uint32_t newline_mask(const uint32_t w[8]) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    uint32_t eq = __vcmpeq4(w[k], 0x0A0A0A0Au) & 0x80808080u;
+    m |= ((eq * 0x00204081u) >> 28) << (4 * k);
+  }
+  return m;
+}
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *smem, uint32_t *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t s = lane < (TOK_THREADS / 32) ? smem[lane] : 0;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, s, d);
+      if (lane >= d) s += t;
+    }
+    if (lane < (TOK_THREADS / 32)) smem[lane] = s;
+  }
+  __syncthreads();
+  uint32_t base = warp ? smem[warp - 1] : 0;
+  *total = smem[TOK_THREADS / 32 - 1];
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(TOK_THREADS) tok_count_kernel(const uint8_t *__restrict__ fq, uint64_t n, uint32_t skew,
+                                                                 uint32_t *__restrict__ tile_counts,
+                                                                 uint32_t *__restrict__ group_totals) {
+  __shared__ uint32_t sm[TOK_THREADS / 32];
+  const uint64_t tile = blockIdx.x;
+  const uint64_t pos = tile * TOK_TILE + (uint64_t)threadIdx.x * 32;
+  uint32_t c = 0;
+  if (pos < n) {
+    uint32_t w[8];
+    load32(fq, n, pos, w);
+    uint32_t mk = newline_mask(w);
+    if (pos == 0) mk &= ~((1u << skew) - 1u);  // bytes before the stream start are not ours
+    c = __popc(mk);
+  }
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int i = 0; i < TOK_THREADS / 32; ++i) t += sm[i];
+    tile_counts[tile] = t;
+    atomicAdd(&group_totals[tile / TOK_GROUP], t);
+  }
+}
+
+__global__ void tok_scan_groups_kernel(const uint32_t *__restrict__ group_totals, uint64_t n_groups,
+                                       uint64_t *__restrict__ group_prefix, uint64_t *__restrict__ out_total) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    uint64_t s = 0;
+    for (uint64_t g = 0; g < n_groups; ++g) {
+      group_prefix[g] = s;
+      s += group_totals[g];
+    }
+    group_prefix[n_groups] = s;
+    *out_total = s;
+  }
+}
+
+// number of '\n' before this tile
+__device__ __forceinline__ uint64_t tile_prefix(const uint32_t *tile_counts, const uint64_t *group_prefix,
+                                                uint64_t tile, uint32_t *smem) {
+  const uint64_t g = tile / TOK_GROUP, first = g * TOK_GROUP;
+  uint32_t s = 0;
+  for (uint64_t t = first + threadIdx.x; t < tile; t += TOK_THREADS) s += tile_counts[t];
+  s = __reduce_add_sync(0xffffffffu, s);
+  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = s;
+  __syncthreads();
+  uint32_t tot = 0;
+#pragma unroll
+  for (int i = 0; i < TOK_THREADS / 32; ++i) tot += smem[i];
+  __syncthreads();
+  return group_prefix[g] + tot;
+}
+
+__global__ void __launch_bounds__(TOK_THREADS) tok_index_kernel(const uint8_t *__restrict__ fq, uint64_t n,
+                                                                 const uint32_t *__restrict__ tile_counts,
+                                                                 const uint64_t *__restrict__ group_prefix,
+                                                                 uint32_t *__restrict__ line_start, uint64_t max_lines,
+                                                                 uint32_t skew) {
+  __shared__ uint32_t sm[TOK_THREADS / 32];
+  const uint64_t tile = blockIdx.x;
+  const uint64_t before = tile_prefix(tile_counts, group_prefix, tile, sm);
+  const uint64_t pos = tile * TOK_TILE + (uint64_t)threadIdx.x * 32;
+  uint32_t mask = 0;
+  if (pos < n) {
+    uint32_t w[8];
+    load32(fq, n, pos, w);
+    mask = newline_mask(w);
+    if (pos == 0) mask &= ~((1u << skew) - 1u);
+  }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(__popc(mask), sm, &total);
+  uint64_t g = before + ex;  // ordinal (0-based) of this thread's first '\n'
+  while (mask) {
+    int b = __ffs(mask) - 1;
+    mask &= mask - 1;
+    if (g + 1 <= max_lines) line_start[g + 1] = (uint32_t)(pos + b + 1);
+    ++g;
+  }
+  if (tile == 0 && threadIdx.x == 0) line_start[0] = skew;
+}
+
+__global__ void tok_fixup_kernel(uint32_t *last, uint32_t virtual_end) {
+  if (*last == 0) *last = virtual_end;
+}
+
+// position just after the target-th '\n' (1-based ordinal); 0 when target == 0
+__global__ void __launch_bounds__(TOK_THREADS) tok_find_kernel(const uint8_t *__restrict__ fq, uint64_t n,
+                                                                const uint32_t *__restrict__ tile_counts,
+                                                                const uint64_t *__restrict__ group_prefix,
+                                                                uint64_t n_groups, uint64_t n_tiles, uint64_t target,
+                                                                uint32_t skew, uint64_t *__restrict__ out) {
+  __shared__ uint32_t sm[TOK_THREADS / 32];
+  __shared__ uint64_t s_tile, s_before;
+  if (target == 0) {
+    if (threadIdx.x == 0) *out = skew;
+    return;
+  }
+  if (threadIdx.x == 0) {
+    uint64_t g = 0;
+    while (g + 1 < n_groups && group_prefix[g + 1] < target) ++g;
+    uint64_t before = group_prefix[g], t = g * TOK_GROUP;
+    while (t + 1 < n_tiles && before + tile_counts[t] < target) {
+      before += tile_counts[t];
+      ++t;
+    }
+    s_tile = t;
+    s_before = before;
+  }
+  __syncthreads();
+  const uint64_t pos = s_tile * TOK_TILE + (uint64_t)threadIdx.x * 32;
+  uint32_t mask = 0;
+  if (pos < n) {
+    uint32_t w[8];
+    load32(fq, n, pos, w);
+    mask = newline_mask(w);
+    if (pos == 0) mask &= ~((1u << skew) - 1u);
+  }
+  uint32_t total;
+  uint32_t ex = block_exclusive_scan(__popc(mask), sm, &total);
+  uint64_t g = s_before + ex;
+  while (mask) {
+    int b = __ffs(mask) - 1;
+    mask &= mask - 1;
+    ++g;
+    if (g == target) *out = pos + b + 1;
+  }
+}
+
+extern "C" int mirge_tokenise_sync(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, int is_final,
+                                   void *d_scratch, uint64_t *n_records, uint64_t *consumed, void *stream_) {
+  if (!ctx || !n_records || !consumed) return MIRGE_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  *n_records = 0;
+  *consumed = 0;
+  if (nbytes == 0) return MIRGE_OK;
+  if (!d_fastq || !d_scratch) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "tokenise: null buffer");
+  if (nbytes > 0xFFFFFF00ull) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "tokenise: batch larger than 4 GiB - 256");
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  // kernels work on the 16-byte aligned stream that contains the batch; offsets are relative to it
+  const uint32_t skew = (uint32_t)((uintptr_t)d_fastq & 15);
+  const uint8_t *fq_al = d_fastq - skew;
+  const uint64_t n_al = nbytes + skew;
+  TokScratch s = tok_layout(d_scratch, n_al);
+  MIRGE_CUDA(ctx, cudaMemsetAsync(s.group_totals, 0, s.n_groups * 4, stream));
+  tok_count_kernel<<<(unsigned)s.n_tiles, TOK_THREADS, 0, stream>>>(fq_al, n_al, skew, s.tile_counts, s.group_totals);
+  MIRGE_LAUNCH_CHECK(ctx, "tok_count_kernel");
+  tok_scan_groups_kernel<<<1, 32, 0, stream>>>(s.group_totals, s.n_groups, s.group_prefix, ctx->d_small);
+  MIRGE_LAUNCH_CHECK(ctx, "tok_scan_groups_kernel");
+  MIRGE_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_small, 8, cudaMemcpyDeviceToHost, stream));
+  MIRGE_CUDA(ctx, cudaMemcpyAsync((uint8_t *)(ctx->h_pinned + 1), d_fastq + nbytes - 1, 1, cudaMemcpyDeviceToHost, stream));
+  MIRGE_CUDA(ctx, cudaStreamSynchronize(stream));
+  uint64_t n_nl = ctx->h_pinned[0];
+  uint8_t last = *(uint8_t *)(ctx->h_pinned + 1);
+  if (is_final) {
+    uint64_t n_lines = n_nl + (last != '\n' ? 1 : 0);
+    if (n_lines % 4 != 0)
+      MIRGE_FAIL(ctx, MIRGE_ERR_FORMAT, "FASTQ format error: %llu lines is not a multiple of 4 (premature end of file)",
+                 (unsigned long long)n_lines);
+    *n_records = n_lines / 4;
+    *consumed = nbytes;
+    return MIRGE_OK;
+  }
+  *n_records = n_nl / 4;
+  tok_find_kernel<<<1, TOK_THREADS, 0, stream>>>(fq_al, n_al, s.tile_counts, s.group_prefix, s.n_groups, s.n_tiles,
+                                                 4 * (*n_records), skew, ctx->d_small + 1);
+  MIRGE_LAUNCH_CHECK(ctx, "tok_find_kernel");
+  MIRGE_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_small + 1, 8, cudaMemcpyDeviceToHost, stream));
+  MIRGE_CUDA(ctx, cudaStreamSynchronize(stream));
+  *consumed = ctx->h_pinned[0] - skew;
+  return MIRGE_OK;
+}
+
+extern "C" int mirge_line_index(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, const void *d_scratch,
+                                uint32_t *d_line_start, uint64_t n_records, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!d_line_start) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "line_index: null output");
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (nbytes == 0 || n_records == 0) {
+    MIRGE_CUDA(ctx, cudaMemsetAsync(d_line_start, 0, 4, stream));
+    return MIRGE_OK;
+  }
+  const uint32_t skew = (uint32_t)((uintptr_t)d_fastq & 15);
+  const uint8_t *fq_al = d_fastq - skew;
+  const uint64_t n_al = nbytes + skew;
+  TokScratch s = tok_layout((void *)d_scratch, n_al);
+  // EOF rule: when the last line has no '\n' the 4n-th line break does not exist; the entry is
+  // zeroed first and a fix-up kernel turns a still-zero entry into the virtual break nbytes + 1.
+  MIRGE_CUDA(ctx, cudaMemsetAsync(d_line_start + 4 * n_records, 0, 4, stream));
+  tok_index_kernel<<<(unsigned)s.n_tiles, TOK_THREADS, 0, stream>>>(fq_al, n_al, s.tile_counts, s.group_prefix,
+                                                                    d_line_start, 4 * n_records, skew);
+  MIRGE_LAUNCH_CHECK(ctx, "tok_index_kernel");
+  tok_fixup_kernel<<<1, 1, 0, stream>>>(d_line_start + 4 * n_records, (uint32_t)(n_al + 1));
+  MIRGE_LAUNCH_CHECK(ctx, "tok_fixup_kernel");
+  return MIRGE_OK;
+}

@@ -1,0 +1,298 @@
+"""Host-side driver of the CUDA library: contexts, torch-owned device buffers, the collapse table
+and the per-batch digest pipeline (tokenise -> line index -> trim -> collapse).
+
+PyTorch is plumbing only here (device memory, streams, the sort used when an index is built);
+every byte of the hot path is touched by the kernels in ``csrc/`` through the C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import abi
+from . import params as P
+
+
+class MirgeError(RuntimeError):
+    pass
+
+
+class FastqFormatError(MirgeError):
+    """Malformed FASTQ input (the reference lets dnaio.FastqFormatError propagate, digest.py:324)."""
+
+
+class CapacityError(MirgeError):
+    pass
+
+
+def _pow2_at_least(n: int) -> int:
+    c = 1
+    while c < n:
+        c <<= 1
+    return c
+
+
+class Device:
+    """One CUDA context of the library bound to ``cuda:<index>`` (one per process / GPU)."""
+
+    def __init__(self, index: int = 0):
+        if not torch.cuda.is_available():
+            raise MirgeError("mirge_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = abi.load_library()
+        self.index = index
+        self.tdev = torch.device("cuda", index)
+        torch.cuda.set_device(self.tdev)
+        ctx = C.c_void_p()
+        rc = self.lib.mirge_ctx_create(index, C.byref(ctx))
+        if rc != 0:
+            raise MirgeError("mirge_ctx_create failed: %s" % self.lib.mirge_last_error(None).decode())
+        self.ctx = ctx
+        self.trim_params: Optional[abi.TrimParams] = None
+        self.slots = 0
+        self.launches = 0  # kernels launched through this context (bench.py reports it)
+
+    def __del__(self):
+        try:
+            if getattr(self, "ctx", None):
+                self.lib.mirge_ctx_destroy(self.ctx)
+                self.ctx = None
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc == 0:
+            return
+        msg = self.lib.mirge_last_error(self.ctx).decode(errors="replace")
+        if rc == abi.ERR_FORMAT:
+            raise FastqFormatError(msg)
+        if rc == abi.ERR_CAPACITY:
+            raise CapacityError(msg)
+        raise MirgeError("%s (code %d)" % (msg, rc))
+
+    def stream(self) -> C.c_void_p:
+        return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
+
+    def set_trim_config(self, cfg: P.TrimConfig):
+        p = P.build_trim_params(cfg)
+        self.check(self.lib.mirge_set_trim_params(self.ctx, C.byref(p)))
+        self.trim_params = p
+        self.slots = self.lib.mirge_trim_slots(self.ctx)
+        self.cfg = cfg
+
+    def empty(self, n: int, dtype) -> torch.Tensor:
+        return torch.empty(max(int(n), 1), dtype=dtype, device=self.tdev)
+
+    def zeros(self, n: int, dtype) -> torch.Tensor:
+        return torch.zeros(max(int(n), 1), dtype=dtype, device=self.tdev)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+class CollapseTable:
+    """Torch-owned storage of one ``mirge_table`` plus host mirrors of its counters.  The load factor
+    is kept <= 0.5 by ``reserve`` (growth = rehash kernel), so probe sequences stay short."""
+
+    def __init__(self, dev: Device, min_keys: int = 1 << 16, words_per_key: int = 6):
+        self.dev = dev
+        self.capacity = _pow2_at_least(max(2 * min_keys, 1024))
+        self.max_keys = self.capacity // 2
+        self.slots = dev.zeros(self.capacity * 4, torch.int32)
+        self.arena = dev.empty(self.max_keys * words_per_key, torch.int32)
+        self.key_ref = dev.empty(self.max_keys, torch.int32)
+        self.ctrl = dev.zeros(8, torch.int64)
+        self.n_keys = 0
+        self.arena_used = 0
+        self._struct()
+
+    def _struct(self):
+        self.struct = abi.Table(self.slots.data_ptr(), self.capacity, self.arena.data_ptr(), self.arena.numel(),
+                                self.key_ref.data_ptr(), self.max_keys, self.ctrl.data_ptr())
+        return self.struct
+
+    def reset(self):
+        d = self.dev
+        d.check(d.lib.mirge_table_reset(d.ctx, C.byref(self.struct), d.stream()))
+        self.n_keys = 0
+        self.arena_used = 0
+
+    def check(self):
+        """Synchronise, raise on table errors, refresh n_keys / arena_used."""
+        d = self.dev
+        nk, au = C.c_uint64(0), C.c_uint64(0)
+        rc = d.lib.mirge_table_check_sync(d.ctx, C.byref(self.struct), C.byref(nk), C.byref(au), d.stream())
+        self.n_keys, self.arena_used = int(nk.value), int(au.value)
+        d.check(rc)
+        return self.n_keys
+
+    def reserve(self, extra_keys: int, extra_words: int):
+        """Make room for ``extra_keys`` new keys / ``extra_words`` arena words (worst case of a batch)."""
+        need_keys = self.n_keys + int(extra_keys)
+        need_words = self.arena_used + int(extra_words)
+        grow_slots = need_keys > self.max_keys
+        grow_arena = need_words > self.arena.numel()
+        if not grow_slots and not grow_arena:
+            return
+        d = self.dev
+        old = abi.Table(self.slots.data_ptr(), self.capacity, self.arena.data_ptr(), self.arena.numel(),
+                        self.key_ref.data_ptr(), self.max_keys, self.ctrl.data_ptr())
+        keep = (self.slots, self.arena, self.key_ref)  # keep alive until the rehash has run
+        if grow_arena:
+            new_arena = d.empty(max(need_words * 3 // 2, 2 * self.arena.numel()), torch.int32)
+            new_arena[: self.arena_used].copy_(self.arena[: self.arena_used])
+            self.arena = new_arena
+        if grow_slots:
+            self.capacity = _pow2_at_least(4 * need_keys)
+            self.max_keys = self.capacity // 2
+            new_ref = d.empty(self.max_keys, torch.int32)
+            new_ref[: self.n_keys].copy_(self.key_ref[: self.n_keys])
+            self.key_ref = new_ref
+            self.slots = d.empty(self.capacity * 4, torch.int32)
+            self._struct()
+            d.check(d.lib.mirge_table_rehash(d.ctx, C.byref(old), C.byref(self.struct), d.stream()))
+            d.launches += 1
+        else:
+            self._struct()
+        torch.cuda.current_stream(d.tdev).synchronize()
+        del keep
+
+    def drain(self):
+        """(ids int32[n], counts int32[n]) of every key counted since the last drain; zeroes counts."""
+        d = self.dev
+        self.check()
+        n_max = max(self.n_keys, 1)
+        ids = d.empty(n_max, torch.int32)
+        cnt = d.empty(n_max, torch.int32)
+        n_out = d.zeros(1, torch.int64)
+        d.check(d.lib.mirge_table_drain(d.ctx, C.byref(self.struct), _ptr(ids), _ptr(cnt), n_max, _ptr(n_out), d.stream()))
+        d.launches += 1
+        n = int(n_out.item())
+        self.check()
+        return ids[:n], cnt[:n]
+
+    def export_keys(self, id0: int = 0, n: Optional[int] = None) -> np.ndarray:
+        """Keys [id0, id0+n) decoded to a numpy 'S<maxlen>' array (exact original read text)."""
+        d = self.dev
+        if n is None:
+            n = self.n_keys - id0
+        if n <= 0:
+            return np.zeros(0, dtype="S1")
+        # first pass with a narrow stride to learn the lengths, second pass only if needed
+        stride = 64
+        while True:
+            asc = d.empty(n * stride, torch.uint8)
+            lens = d.empty(n, torch.int32)
+            d.check(d.lib.mirge_table_export_keys(d.ctx, C.byref(self.struct), id0, n, _ptr(asc), stride, _ptr(lens), d.stream()))
+            d.launches += 1
+            mx = int(lens.max().item())
+            if mx <= stride:
+                break
+            stride = (mx + 15) // 16 * 16
+        host = asc.cpu().numpy().reshape(n, stride)
+        return np.ascontiguousarray(host).view("S%d" % stride).reshape(n)
+
+
+@dataclass
+class BatchResult:
+    n_records: int
+    consumed: int
+    n_emitted: int
+    key_words: int
+    line_start: Optional[torch.Tensor] = None
+    win: Optional[torch.Tensor] = None
+    key_off: Optional[torch.Tensor] = None
+    keys: Optional[torch.Tensor] = None
+
+
+class DigestEngine:
+    """tokenise -> trim -> collapse for batches of FASTQ bytes resident on the device."""
+
+    def __init__(self, dev: Device, cfg: P.TrimConfig):
+        self.dev = dev
+        dev.set_trim_config(cfg)
+        self.cfg = cfg
+        self.E = dev.slots
+
+    def trim_batch(self, buf: torch.Tensor, nbytes: int, is_final: bool, keep: bool = True) -> BatchResult:
+        """Run the tokeniser and the trim kernel on buf[:nbytes] (uint8, device).  Returns the device
+        arrays the collapse consumes (and the parity tests read)."""
+        d, lib, E = self.dev, self.dev.lib, self.E
+        if nbytes == 0:
+            return BatchResult(0, 0, 0, 0)
+        st = d.stream()
+        scratch = d.empty(lib.mirge_tokenise_scratch_bytes(nbytes), torch.uint8)
+        n_rec, consumed = C.c_uint64(0), C.c_uint64(0)
+        d.check(lib.mirge_tokenise_sync(d.ctx, _ptr(buf), nbytes, 1 if is_final else 0, _ptr(scratch),
+                                        C.byref(n_rec), C.byref(consumed), st))
+        d.launches += 3 if not is_final else 2
+        n = int(n_rec.value)
+        if n == 0:
+            return BatchResult(0, int(consumed.value), 0, 0)
+        used = int(consumed.value)
+        line_start = d.empty(4 * n + 4, torch.int32)
+        # same nbytes as the census: the scratch layout depends on it
+        d.check(lib.mirge_line_index(d.ctx, _ptr(buf), nbytes, _ptr(scratch), _ptr(line_start), n, st))
+        d.launches += 2
+        win = d.empty(n * E * 4, torch.int16)
+        key_off = d.empty(n * E, torch.int32)
+        cap = E * (2 * n + used // 24) + 4096
+        for attempt in range(2):
+            keys = d.empty(cap, torch.int32)
+            ctrl = d.zeros(8, torch.int64)
+            d.check(lib.mirge_trim(d.ctx, _ptr(buf), used, _ptr(line_start), n, _ptr(win), _ptr(key_off),
+                                   _ptr(keys), cap, _ptr(ctrl), st))
+            d.launches += 1
+            c = ctrl.cpu().numpy().view(np.uint64)
+            flags = int(c[2])
+            if flags & 1:
+                rec = int(np.uint64(~c[3]))
+                raise FastqFormatError("FASTQ format error in record %d of the batch (header must start with '@', "
+                                       "line 3 with '+', sequence and qualities must have equal length)" % rec)
+            if flags & 4:
+                raise MirgeError("read longer than %d bases is not supported" % abi.MAX_READ_LEN)
+            if flags & 2:
+                if attempt == 1:
+                    raise CapacityError("trim: key buffer overflow")
+                cap = E * (n + used // 2 + used // 32 + 64) + 4096  # worst case: every base an exception
+                continue
+            break
+        return BatchResult(n, used, int(c[1]), int(c[0]), line_start if keep else None, win if keep else None,
+                           key_off, keys)
+
+    def collapse_batch(self, table: CollapseTable, br: BatchResult):
+        """completeDict[key] += 1 for every key the trim kernel emitted."""
+        if br.n_records == 0 or br.n_emitted == 0:
+            return
+        d, lib = self.dev, self.dev.lib
+        table.check()
+        table.reserve(br.n_emitted, br.key_words)
+        n_slots = br.n_records * self.E
+        deferred = d.empty(n_slots, torch.int32)
+        d.check(lib.mirge_collapse_insert(d.ctx, C.byref(table.struct), _ptr(br.keys), _ptr(br.key_off), n_slots,
+                                          _ptr(deferred), d.stream()))
+        d.launches += 3
+        table.check()
+
+    def digest_device(self, buf: torch.Tensor, table: CollapseTable, batch_bytes: int = 256 << 20) -> int:
+        """Whole sample resident on the device: returns the number of records parsed."""
+        total = int(buf.numel())
+        pos = 0
+        n_records = 0
+        while pos < total:
+            end = min(total, pos + batch_bytes)
+            final = end == total
+            view = buf[pos:end]
+            br = self.trim_batch(view, end - pos, final, keep=False)
+            if br.n_records == 0 and not final:
+                if end - pos >= batch_bytes and batch_bytes >= (1 << 20):
+                    raise FastqFormatError("FASTQ record does not fit into a batch")
+            self.collapse_batch(table, br)
+            n_records += br.n_records
+            if br.consumed == 0 and not final:
+                raise FastqFormatError("no complete FASTQ record in batch")
+            pos += br.consumed if not final else (end - pos)
+        return n_records
