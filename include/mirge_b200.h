@@ -223,6 +223,15 @@ int mirge_umi_collapse(mirge_ctx *ctx, const mirge_table *first, const uint32_t 
 /* Decode keys [id0, id0 + n) to ASCII rows of `stride` bytes (zero padded); d_len[i] = length. */
 int mirge_table_export_keys(mirge_ctx *ctx, const mirge_table *t, uint64_t id0, uint64_t n,
                             uint8_t *d_ascii, uint32_t stride, uint32_t *d_len, void *stream);
+/* Import of sequences that are already collapsed (the DataFrame index bwtAlign receives,
+ * manifoldAlign.py:93-131): string i = d_ascii[d_str_off[i] : d_str_off[i+1]].  mirge_key_sizes
+ * gives the packed size of each key in words; after an exclusive scan of those sizes into
+ * d_key_off, mirge_pack_keys writes the keys, which makes (d_arena, d_key_off) usable as the
+ * (d_arena, d_key_ref) of a mirge_table for mirge_annotate_round with key id = string index. */
+int mirge_key_sizes(mirge_ctx *ctx, const uint8_t *d_ascii, const uint64_t *d_str_off, uint64_t n,
+                    uint32_t *d_words, void *stream);
+int mirge_pack_keys(mirge_ctx *ctx, const uint8_t *d_ascii, const uint64_t *d_str_off, uint64_t n,
+                    const uint32_t *d_key_off, uint32_t *d_arena, void *stream);
 /* Hash partition for the multi-GPU exchange: d_dest[i] = hash64(centre of key id i) % n_parts,
  * d_words[i] = 1 + key words (size of its exchange record). */
 int mirge_partition_plan(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_ids, uint64_t n,

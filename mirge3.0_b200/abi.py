@@ -124,6 +124,8 @@ SYMBOLS = {
         [_P, C.POINTER(Table), _P, _P, _U64, C.POINTER(Table), C.c_int, C.c_int, C.c_int, C.c_int, _P, _P],
     ),
     "mirge_table_export_keys": (C.c_int, [_P, C.POINTER(Table), _U64, _U64, _P, C.c_uint32, _P, _P]),
+    "mirge_key_sizes": (C.c_int, [_P, _P, _P, _U64, _P, _P]),
+    "mirge_pack_keys": (C.c_int, [_P, _P, _P, _U64, _P, _P, _P]),
     "mirge_partition_plan": (
         C.c_int,
         [_P, C.POINTER(Table), _P, _U64, C.c_int, C.c_int, C.c_uint32, _P, _P, _P],

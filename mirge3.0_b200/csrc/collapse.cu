@@ -421,6 +421,59 @@ extern "C" int mirge_table_export_keys(mirge_ctx *ctx, const mirge_table *t, uin
   return MIRGE_OK;
 }
 
+// ------------------------------------------------------------------ import (ASCII -> keys) ---
+
+// mode 0: words[i] = size of the packed key of string i; mode 1: write the key at key_off[i]
+__global__ void __launch_bounds__(COL_THREADS)
+pack_keys_kernel(const uint8_t *__restrict__ ascii, const uint64_t *__restrict__ str_off, uint64_t n, int mode,
+                 uint32_t *__restrict__ words, const uint32_t *__restrict__ key_off, uint32_t *__restrict__ arena) {
+  const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const uint8_t *s = ascii + str_off[i];
+  const uint32_t len = (uint32_t)(str_off[i + 1] - str_off[i]);
+  const uint32_t npay = (len + 15) >> 4;
+  if (mode == 0) {
+    uint32_t nexc = 0;
+    for (uint32_t p = 0; p < len; ++p) nexc += base_code_exact(s[p]) == 4u;
+    words[i] = 1u + npay + nexc;
+    return;
+  }
+  uint32_t *k = arena + key_off[i];
+  uint32_t word = 0, xi = 0;
+  for (uint32_t p = 0; p < len; ++p) {
+    const uint32_t ch = s[p], code = base_code_exact(ch);
+    if (code == 4u) k[1 + npay + xi++] = (p << 8) | ch;
+    else word |= code << (2 * (p & 15));
+    if ((p & 15) == 15) { k[1 + (p >> 4)] = word; word = 0; }
+  }
+  if (len & 15) k[1 + (len >> 4)] = word;
+  k[0] = len | (xi << 16);
+}
+
+extern "C" int mirge_key_sizes(mirge_ctx *ctx, const uint8_t *d_ascii, const uint64_t *d_str_off, uint64_t n, uint32_t *d_words,
+                               void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  if (n == 0) return MIRGE_OK;
+  if (!d_ascii || !d_str_off || !d_words) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "key_sizes: null buffer");
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  pack_keys_kernel<<<(unsigned)((n + COL_THREADS - 1) / COL_THREADS), COL_THREADS, 0, (cudaStream_t)stream_>>>(
+      d_ascii, d_str_off, n, 0, d_words, nullptr, nullptr);
+  MIRGE_LAUNCH_CHECK(ctx, "pack_keys_kernel(sizes)");
+  return MIRGE_OK;
+}
+
+extern "C" int mirge_pack_keys(mirge_ctx *ctx, const uint8_t *d_ascii, const uint64_t *d_str_off, uint64_t n,
+                               const uint32_t *d_key_off, uint32_t *d_arena, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  if (n == 0) return MIRGE_OK;
+  if (!d_ascii || !d_str_off || !d_key_off || !d_arena) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "pack_keys: null buffer");
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  pack_keys_kernel<<<(unsigned)((n + COL_THREADS - 1) / COL_THREADS), COL_THREADS, 0, (cudaStream_t)stream_>>>(
+      d_ascii, d_str_off, n, 1, nullptr, d_key_off, d_arena);
+  MIRGE_LAUNCH_CHECK(ctx, "pack_keys_kernel");
+  return MIRGE_OK;
+}
+
 // ------------------------------------------------------------------ hash partition -----------
 
 __global__ void __launch_bounds__(128)

@@ -1,0 +1,304 @@
+"""``baking`` -- drop-in for mirge/libs/digest.py:105 (same signature, same return tuple, same
+run.log / _umiCounts.csv / .trim.collapse.fa side effects) that digests FASTQ on the GPU:
+tokenise -> trim (cutadapt semantics) -> collapse -> optional UMI level -> sample x sequence matrix.
+
+The reference fans 4 MB chunks out to a process pool running cutadapt modifiers per read
+(digest.py:139-140,320-375) and merges Python dicts in the parent (digest.py:141-163); here each
+batch of the stream goes through the kernels of csrc/ and never comes back to the host until the
+final table is exported."""
+from __future__ import annotations
+
+import ctypes as C
+import gzip
+import os
+import time
+from pathlib import Path
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import pandas as pd
+import torch
+
+from . import abi
+from . import params as P
+from .device import CollapseTable, Device, DigestEngine, FastqFormatError, MirgeError, _ptr
+from .manifoldAlign import get_device
+
+INITIAL_FLAGS = ["exact miRNA", "hairpin miRNA", "mature tRNA", "primary tRNA", "snoRNA", "rRNA", "ncrna others", "mRNA",
+                 "isomiR miRNA", "spike-in"]  # digest.py:253
+
+DEFAULT_BATCH_BYTES = 256 << 20
+
+
+def default_count_mode() -> str:
+    """HEAD counts after every modifier (digest.py:354-373); the released 0.1.x packages count once
+    (SURVEY.md section 0 item 3).  HEAD is the default; MIRGE_B200_COUNT_MODE=release switches."""
+    return os.environ.get("MIRGE_B200_COUNT_MODE", "head")
+
+
+def _open_fastq(path: str):
+    with open(path, "rb") as f:
+        magic = f.read(2)
+    if magic == b"\x1f\x8b":
+        return gzip.open(path, "rb")
+    return open(path, "rb", buffering=0)
+
+
+class HostStreamer:
+    """Feeds a host byte stream (file object or memoryview) to the engine batch by batch through two
+    pinned staging buffers and two device buffers; the tail of a batch that does not end on a
+    record boundary is carried to the front of the next device buffer (device-to-device)."""
+
+    def __init__(self, eng: DigestEngine, batch_bytes: int = DEFAULT_BATCH_BYTES, max_record: int = 1 << 20):
+        self.eng = eng
+        self.dev = eng.dev
+        self.batch = int(batch_bytes)
+        self.cap = self.batch + max_record + 64
+        self.h = [torch.empty(self.batch, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        self.d = [torch.empty(self.cap, dtype=torch.uint8, device=self.dev.tdev) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=self.dev.tdev)
+        self.h2d_bytes = 0
+
+    def _fill(self, src, hbuf: torch.Tensor) -> int:
+        mv = memoryview(hbuf.numpy())
+        got = 0
+        while got < self.batch:
+            k = src.readinto(mv[got:])
+            if not k:
+                break
+            got += k
+        return got
+
+    def run(self, src, table: CollapseTable) -> int:
+        """Digest the whole stream into ``table``; returns the number of records parsed."""
+        eng, dev = self.eng, self.dev
+        main = torch.cuda.current_stream(dev.tdev)
+        n_records = 0
+        leftover = 0
+        cur = 0
+        got = self._fill(src, self.h[cur])
+        first = True
+        prev_buf = None
+        prev_tail = (0, 0)
+        while True:
+            final = got < self.batch
+            nxt_got = 0
+            dbuf = self.d[cur]
+            if leftover:
+                a, b = prev_tail
+                dbuf[:leftover].copy_(prev_buf[a:b])
+            if got:
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_stream(main)
+                    dbuf[leftover : leftover + got].copy_(self.h[cur][:got], non_blocking=True)
+                self.h2d_bytes += got
+            # overlap: read the next piece from the host stream while the copy is in flight
+            if not final:
+                nxt_got = self._fill(src, self.h[cur ^ 1])
+            main.wait_stream(self.copy_stream)
+            nbytes = leftover + got
+            if nbytes == 0:
+                break
+            if final and nxt_got == 0:
+                br = eng.trim_batch(dbuf, nbytes, True, keep=False)
+            else:
+                br = eng.trim_batch(dbuf, nbytes, False, keep=False)
+            eng.collapse_batch(table, br)
+            n_records += br.n_records
+            if final:
+                break
+            if br.consumed == 0 and nbytes >= self.cap - 64:
+                raise FastqFormatError("FASTQ record does not fit into the staging buffer")
+            prev_buf, prev_tail = dbuf, (br.consumed, nbytes)
+            leftover = nbytes - br.consumed
+            if leftover > self.cap - self.batch:
+                raise FastqFormatError("FASTQ record longer than %d bytes" % (self.cap - self.batch))
+            cur ^= 1
+            got = nxt_got
+            first = False
+        return n_records
+
+
+class _BytesSource:
+    def __init__(self, data):
+        self.mv = memoryview(data).cast("B")
+        self.pos = 0
+
+    def readinto(self, out) -> int:
+        k = min(len(out), len(self.mv) - self.pos)
+        out[:k] = self.mv[self.pos : self.pos + k]
+        self.pos += k
+        return k
+
+
+def umi_collapse(dev: Device, first: CollapseTable, ids: torch.Tensor, cnt: torch.Tensor, second: CollapseTable,
+                 umi: Tuple[int, int], min_len: int, dedup: bool):
+    """Second-level collapse (digest.py:164-205) of the drained first-level pairs into ``second``."""
+    n = int(ids.numel())
+    if n == 0:
+        return
+    second.check()
+    second.reserve(n, int(first.arena_used))
+    deferred = dev.empty(n, torch.int32)
+    dev.check(dev.lib.mirge_umi_collapse(dev.ctx, C.byref(first.struct), _ptr(ids), _ptr(cnt), n, C.byref(second.struct),
+                                         int(umi[0]), int(umi[1]), int(min_len), 1 if dedup else 0, _ptr(deferred), dev.stream()))
+    dev.launches += 3
+    second.check()
+
+
+class SampleResult:
+    __slots__ = ("count", "trimmed", "unique", "ids", "counts", "rlen", "hist")
+
+
+def digest_sample(eng: DigestEngine, source, table: CollapseTable, first_level: Optional[CollapseTable], umi_dedup: bool,
+                  batch_bytes: int = DEFAULT_BATCH_BYTES, umi_csv: Optional[str] = None,
+                  streamer: Optional[HostStreamer] = None) -> SampleResult:
+    """One iteration of baking()'s per-sample loop (digest.py:133-217).  ``source`` is a device uint8
+    tensor (already resident) or an object with readinto() / a bytes-like host buffer."""
+    dev, cfg = eng.dev, eng.cfg
+    umi = cfg.umi()
+    target = first_level if umi is not None else table
+    if isinstance(source, torch.Tensor) and source.is_cuda:
+        count = eng.digest_device(source, target, batch_bytes)
+    else:
+        if not hasattr(source, "readinto"):
+            source = _BytesSource(source)
+        st = streamer or HostStreamer(eng, batch_bytes)
+        count = st.run(source, target)
+    res = SampleResult()
+    res.count = count
+    res.hist = np.zeros(0, dtype=np.int64)
+    if umi is not None:
+        ids1, cnt1 = first_level.drain()
+        res.hist = cnt1.cpu().numpy().astype(np.int64)  # visual_treat['hist'] (digest.py:172,192)
+        umi_collapse(dev, first_level, ids1, cnt1, table, umi, cfg.minimum_length, umi_dedup)
+        if umi_dedup and umi_csv is not None:
+            _write_umi_csv(umi_csv, first_level, ids1.cpu().numpy(), res.hist, umi, cfg.minimum_length)
+        first_level.reset()
+    ids, cnt = table.drain()
+    res.ids = ids.cpu().numpy().astype(np.int64)
+    res.counts = cnt.cpu().numpy().astype(np.int64)
+    res.trimmed = int(res.counts.sum())  # digest.py:160-163 / 178-181 / 199-202
+    res.unique = int(res.ids.size)  # len(completeDict), digest.py:212
+    return res
+
+
+def _write_umi_csv(path: str, first: CollapseTable, ids: np.ndarray, counts: np.ndarray, umi: Tuple[int, int], min_len: int):
+    """<sample>_umiCounts.csv (digest.py:185-205): header + one row per first-level key whose centre
+    passes the length filter; opened in append mode like the reference (quirk 4)."""
+    keys = first.export_keys()
+    f_, b_ = umi
+    with open(path, "a+") as fh:
+        fh.write("UMISeq" + "," + "transcriptSeq," + "UMICounts" + "\n")
+        for i, c in zip(ids.tolist(), counts.tolist()):
+            s = keys[i].decode("latin-1")
+            center = s[f_:-b_] if int(b_) != 0 else s[f_:]
+            if len(center) >= int(min_len):
+                fh.write(s[:f_] + s[-b_:] + "," + center + "," + str(c) + "\n")  # UMIParser incl. the b == 0 quirk
+
+
+def build_matrix(table: CollapseTable, samples: List[SampleResult], names: List[str]) -> pd.DataFrame:
+    """digest.py:237-261: unique sequences x samples, rows in lexicographic order (what pandas' outer
+    join produces for > 1 sample; the single-sample order of the reference is not deterministic)."""
+    keys = table.export_keys()
+    n = keys.shape[0]
+    mat = np.zeros((n, len(samples)), dtype=np.int64)
+    for j, s in enumerate(samples):
+        mat[s.ids, j] = s.counts
+    seen = mat.any(axis=1) if n else np.zeros(0, dtype=bool)
+    order = np.argsort(keys, kind="stable")
+    order = order[seen[order]]
+    index = pd.Index([k.decode("latin-1") for k in keys[order].tolist()], name="Sequence", dtype=object)
+    df = pd.DataFrame(mat[order], index=index, columns=list(names))
+    df = df.assign(**dict.fromkeys(INITIAL_FLAGS, ""))
+    df = df.assign(annotFlag=0)
+    df = df.reindex(columns=["annotFlag"] + INITIAL_FLAGS + list(names))
+    df = df.astype({"annotFlag": int})
+    return df
+
+
+def baking(args, inFileArray, inFileBaseArray, workDir, device: Optional[Device] = None, count_mode: Optional[str] = None,
+           batch_bytes: int = DEFAULT_BATCH_BYTES, keep_table: bool = False):
+    """Same contract as the reference ``baking(args, inFileArray, inFileBaseArray, workDir)``:
+    returns (complete_set DataFrame, sampleReadCounts, trimmedReadCounts, trimmedReadCountsUnique)."""
+    begningTime = time.perf_counter()
+    cfg = P.TrimConfig.from_args(args, count_mode or default_count_mode())
+    dev = device or get_device()
+    eng = DigestEngine(dev, cfg)
+    umi = cfg.umi()
+    table = CollapseTable(dev, min_keys=1 << 20)
+    first_level = CollapseTable(dev, min_keys=1 << 20) if umi is not None else None
+    streamer = HostStreamer(eng, batch_bytes)
+    sampleReadCounts: Dict[str, int] = {}
+    trimmedReadCounts: Dict[str, int] = {}
+    trimmedReadCountsUnique: Dict[str, int] = {}
+    results: List[SampleResult] = []
+    runlogFile = Path(workDir) / "run.log"
+    outlog = open(str(runlogFile), "a+")
+    quiet = bool(getattr(args, "quiet", False))
+    for index, FQfile in enumerate(inFileArray):
+        start = time.perf_counter()
+        base = inFileBaseArray[index]
+        umi_csv = str(Path(workDir) / (base + "_umiCounts.csv")) if (umi is not None and getattr(args, "umiDedup", False)) else None
+        with _open_fastq(FQfile) as f:
+            res = digest_sample(eng, f, table, first_level, bool(getattr(args, "umiDedup", False)), batch_bytes, umi_csv, streamer)
+        results.append(res)
+        sampleReadCounts[base] = res.count
+        trimmedReadCounts[base] = res.trimmed
+        trimmedReadCountsUnique[base] = res.unique
+        finish2 = time.perf_counter()
+        if not quiet:
+            print(f"Cutadapt finished for file {base} in {round(finish2-start, 4)} second(s)")
+        outlog.write(f"Cutadapt finished for file {base} in {round(finish2-start, 4)} second(s)\n")
+        if getattr(args, "tcf_out", False):
+            keys = table.export_keys()
+            order = np.argsort(-res.counts, kind="stable")
+            with open(Path(workDir) / (str(base) + ".trim.collapse.fa"), "w") as fo:  # digest.py:226-235
+                for hc, j in enumerate(order.tolist(), 1):
+                    fo.write(">seq" + str(hc) + "_" + str(int(res.counts[j])) + "\n")
+                    fo.write(keys[res.ids[j]].decode("latin-1") + "\n")
+        finish3 = time.perf_counter()
+        if not quiet:
+            print(f"Collapsing finished for file {base} in {round(finish3-finish2, 4)} second(s)\n")
+        outlog.write(f"Collapsing finished for file {base} in {round(finish3-finish2, 4)} second(s)\n")
+    finish3 = time.perf_counter()
+    complete_set = build_matrix(table, results, list(inFileBaseArray))
+    finish4 = time.perf_counter()
+    if not quiet:
+        print(f"Matrix creation finished in {round(finish4-finish3, 4)} second(s)\n")
+    outlog.write(f"Matrix creation finished in {round(finish4-finish3, 4)} second(s)\n")
+    _write_histograms(workDir, complete_set, results, list(inFileBaseArray), umi)
+    EndTime = time.perf_counter()
+    if not quiet:
+        print(f"Data pre-processing completed in {round(EndTime-begningTime, 4)} second(s)\n")
+    outlog.write(f"\nData pre-processing completed in {round(EndTime-begningTime, 4)} second(s)\n\n")
+    outlog.close()
+    if keep_table:
+        return complete_set, sampleReadCounts, trimmedReadCounts, trimmedReadCountsUnique, table
+    return (complete_set, sampleReadCounts, trimmedReadCounts, trimmedReadCountsUnique)
+
+
+def _write_histograms(workDir, df: pd.DataFrame, results: List[SampleResult], names: List[str], umi):
+    """index_data.js read-length / UMI histograms (digest.py:270-295) through the reference's own
+    FormatJS when miRge is importable.  Deviation: the reference appends one length per
+    *chunk-unique* key (digest.py:146-157), which depends on its 4 MB chunk boundaries; here every
+    sample-unique key contributes once."""
+    try:
+        from mirge.classes.exportHTML import FormatJS  # the reference's visualisation writer
+    except Exception:
+        return
+    histData = FormatJS(workDir)
+    lens = df.index.str.len().to_numpy()
+    for div_idnum, (name, res) in enumerate(zip(names, results), 1):
+        val = lens[df[name].to_numpy() > 0]
+        if val.size == 0:
+            continue
+        maxVal, minVal = int(val.max()), int(val.min())
+        if maxVal > minVal:
+            hist, bins = np.histogram(val, bins=(maxVal - minVal))
+            histData.readLenDist("readLengthID_" + str(div_idnum), name, str(hist.tolist()), str(list(bins)))
+        if umi is not None and res.hist.size:
+            maxVal, minVal = int(res.hist.max()), int(res.hist.min())
+            if maxVal > minVal:
+                hist, bins = np.histogram(res.hist, bins=(maxVal - minVal))
+                histData.sampleUMIDist("umiDivID_" + str(div_idnum), name, str(hist.tolist()), str(bins.tolist()))

@@ -1,0 +1,154 @@
+"""``bwtAlign`` -- drop-in for mirge/libs/manifoldAlign.py:68 (same signature, same DataFrame and
+run.log side effects) that runs the ordered annotation rounds on the GPU instead of spawning
+bowtie ten times and parsing SAM text (manifoldAlign.py:12-64)."""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from pathlib import Path
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import abi
+from .device import CollapseTable, Device, MirgeError, _ptr
+from .libraries import ROUND_COLUMNS, ROUND_LIBS, LibrarySet, round_policies
+
+_DEVICE: Optional[Device] = None
+_LIB_CACHE: Dict[Tuple, LibrarySet] = {}
+
+
+def get_device(index: int = 0) -> Device:
+    """Process-wide context (one per GPU process)."""
+    global _DEVICE
+    if _DEVICE is None or _DEVICE.index != index:
+        _DEVICE = Device(index)
+    return _DEVICE
+
+
+class KeySet:
+    """Unique sequences resident on the device in packed-key form, id = row index."""
+
+    def __init__(self, dev: Device, arena: torch.Tensor, key_ref: torch.Tensor, n: int):
+        self.dev, self.arena, self.key_ref, self.n = dev, arena, key_ref, n
+        self._dummy_slots = dev.zeros(8, torch.int32)
+        self._ctrl = dev.zeros(8, torch.int64)
+        self.struct = abi.Table(self._dummy_slots.data_ptr(), 2, arena.data_ptr(), arena.numel(), key_ref.data_ptr(),
+                                max(n, 1), self._ctrl.data_ptr())
+
+    @classmethod
+    def from_table(cls, table: CollapseTable) -> "KeySet":
+        table.check()
+        return cls(table.dev, table.arena, table.key_ref, table.n_keys)
+
+    @classmethod
+    def from_strings(cls, dev: Device, seqs: Sequence) -> "KeySet":
+        """Pack Python strings / bytes (the DataFrame index) with the mirge_pack_keys kernel."""
+        n = len(seqs)
+        if n == 0:
+            return cls(dev, dev.zeros(1, torch.int32), dev.zeros(1, torch.int32), 0)
+        if isinstance(seqs, np.ndarray) and seqs.dtype.kind == "S":
+            lens = np.char.str_len(seqs).astype(np.int64)
+            blob = b"".join(seqs.tolist())
+        else:
+            enc = [s.encode("latin-1") if isinstance(s, str) else bytes(s) for s in seqs]
+            lens = np.fromiter((len(b) for b in enc), dtype=np.int64, count=n)
+            blob = b"".join(enc)
+        if len(lens) and int(lens.max()) > abi.MAX_READ_LEN:
+            raise MirgeError("sequence longer than %d bases" % abi.MAX_READ_LEN)
+        off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=off[1:])
+        d_ascii = torch.frombuffer(bytearray(blob) if blob else bytearray(1), dtype=torch.uint8).to(dev.tdev)
+        d_off = torch.from_numpy(off).to(dev.tdev)
+        words = dev.empty(n, torch.int32)
+        dev.check(dev.lib.mirge_key_sizes(dev.ctx, _ptr(d_ascii), _ptr(d_off), n, _ptr(words), dev.stream()))
+        csum = torch.cumsum(words.to(torch.int64), 0)
+        total = int(csum[-1].item())
+        if total >= (1 << 32) - 16:
+            raise MirgeError("too many sequences for one key set")
+        key_off64 = csum - words.to(torch.int64)
+        key_off = torch.where(key_off64 >= (1 << 31), key_off64 - (1 << 32), key_off64).to(torch.int32)
+        arena = dev.empty(total, torch.int32)
+        dev.check(dev.lib.mirge_pack_keys(dev.ctx, _ptr(d_ascii), _ptr(d_off), n, _ptr(key_off), _ptr(arena), dev.stream()))
+        dev.launches += 2
+        return cls(dev, arena, key_off, n)
+
+
+def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = False):
+    """Run rounds 0..8 (0..9 with spike-ins) in miRge's order (manifoldAlign.py:86-135).
+    Returns device tensors (annot_round uint8[n] with 0xFF = unannotated, hit int64[n])."""
+    n = keys.n
+    annot = torch.full((max(n, 1),), 0xFF, dtype=torch.uint8, device=dev.tdev)
+    hit = torch.full((max(n, 1),), -1, dtype=torch.int64, device=dev.tdev)
+    if n == 0:
+        return annot[:0], hit[:0]
+    pols = round_policies()
+    for rnd in range(10 if spike_in else 9):
+        lib = libs[ROUND_LIBS[rnd]]
+        dev.check(dev.lib.mirge_annotate_round(dev.ctx, C.byref(lib.struct), C.byref(pols[rnd]), C.byref(keys.struct), n,
+                                               _ptr(annot), _ptr(hit), dev.stream()))
+        dev.launches += 1
+    return annot[:n], hit[:n]
+
+
+def decode_hits(annot: np.ndarray, hit: np.ndarray):
+    """(round, n_mismatch, ref_index, offset) numpy arrays from the packed hit words."""
+    h = hit.view(np.uint64)
+    return annot, (h >> np.uint64(56)).astype(np.int64), ((h >> np.uint64(28)) & np.uint64(0xFFFFFFF)).astype(np.int64), \
+        (h & np.uint64(0xFFFFFFF)).astype(np.int64)
+
+
+def load_libraries(args, ref_db: str, dev: Device) -> LibrarySet:
+    key = (str(args.libraries_path), str(args.organism_name), str(ref_db), bool(args.spikeIn), dev.index)
+    if key not in _LIB_CACHE:
+        _LIB_CACHE[key] = LibrarySet.from_mirge_lib(dev, str(args.libraries_path), str(args.organism_name), str(ref_db),
+                                                    bool(args.spikeIn))
+    return _LIB_CACHE[key]
+
+
+def bwtAlign(args, pdDataFrame, workDir, ref_db, libraries: Optional[LibrarySet] = None, device: Optional[Device] = None):
+    """Same contract as the reference ``bwtAlign(args, pdDataFrame, workDir, ref_db)``
+    (manifoldAlign.py:68-146): fills the annotation column of the first round that hits each
+    sequence (column index 1 + round, manifoldAlign.py:17-18,55), sets annotFlag = 1 (:56), drops the
+    'spike-in' column unless -spk (:137-138), fillna('') (:141) and logs to run.log (:83,144)."""
+    begningTime = time.perf_counter()
+    runlogFile = Path(workDir) / "run.log"
+    outlog = open(str(runlogFile), "a+")
+    if not getattr(args, "quiet", False):
+        print("Alignment in progress ...")
+    outlog.write("Alignment in progress ...\n")
+    if getattr(args, "bam_out", False) or getattr(args, "tRNA_frag", False):
+        outlog.close()
+        raise MirgeError("-bam / -trf need per-round SAM files, which the B200 path does not emit yet (DESIGN.md, out of scope)")
+    dev = device or get_device()
+    libs = libraries or load_libraries(args, ref_db, dev)
+    spike = bool(getattr(args, "spikeIn", False))
+    seqs = pdDataFrame.index.to_numpy()
+    keys = KeySet.from_strings(dev, list(seqs))
+    annot_d, hit_d = annotate_keys(dev, libs, keys, spike)
+    annot = annot_d.cpu().numpy()
+    hit = hit_d.cpu().numpy()
+    _, _mm, ref, _off = decode_hits(annot, hit)
+    colnames = list(pdDataFrame.columns)
+    for rnd in range(10 if spike else 9):
+        rows = np.nonzero(annot == rnd)[0]
+        if rows.size == 0:
+            continue
+        names = np.asarray(libs[ROUND_LIBS[rnd]].names, dtype=object)
+        ci = 1 + rnd
+        col = pdDataFrame[colnames[ci]].to_numpy(dtype=object, copy=True)
+        col[rows] = names[ref[rows]]
+        pdDataFrame[colnames[ci]] = col
+    flag = pdDataFrame[colnames[0]].to_numpy(copy=True)
+    flag[annot != 0xFF] = 1
+    pdDataFrame[colnames[0]] = flag
+    finish = time.perf_counter()
+    if not spike:
+        pdDataFrame = pdDataFrame.drop(columns=["spike-in"])
+    pdDataFrame = pdDataFrame.fillna("")
+    if not getattr(args, "quiet", False):
+        print(f"Alignment completed in {round(finish-begningTime, 4)} second(s)\n")
+    outlog.write(f"Alignment completed in {round(finish-begningTime, 4)} second(s)\n")
+    outlog.close()
+    return pdDataFrame
