@@ -145,14 +145,15 @@ class DeviceLibrary:
         pos = torch.nonzero(valid >= MIN_INDEX_K).squeeze(1)
         k64 = kmer[pos].to(torch.int64) & 0xFFFFFFFF
         del kmer, valid
-        comp, _ = torch.sort((k64 << 32) | pos)
-        del k64, pos
-        ks = comp >> 32
-        self.n_idx = int(comp.numel())
+        # positions are ascending already, so a stable sort on the k-mer orders by (k-mer, position)
+        ks, perm = torch.sort(k64, stable=True)
+        pos = pos[perm]
+        del k64, perm
+        self.n_idx = int(ks.numel())
         to_i32 = lambda x: torch.where(x >= (1 << 31), x - (1 << 32), x).to(torch.int32)
         self.idx_kmer = to_i32(ks)
-        self.idx_pos = to_i32(comp & 0xFFFFFFFF)
-        del comp
+        self.idx_pos = to_i32(pos)
+        del pos
         if self.n_idx == 0:
             self.idx_kmer = torch.zeros(1, dtype=torch.int32, device=d.tdev)
             self.idx_pos = torch.zeros(1, dtype=torch.int32, device=d.tdev)

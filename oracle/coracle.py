@@ -50,6 +50,12 @@ def lib():
         L.oracle_table_free.argtypes = [P]
         L.oracle_annotate_round.restype = None
         L.oracle_annotate_round.argtypes = [P, P, U64, P, P, C.c_uint32, C.POINTER(abi.RoundPolicy), P, P, C.c_int]
+        L.oracle_index_build.restype = P
+        L.oracle_index_build.argtypes = [P, P, C.c_uint32, C.c_int]
+        L.oracle_index_free.restype = None
+        L.oracle_index_free.argtypes = [P]
+        L.oracle_annotate_round_indexed.restype = None
+        L.oracle_annotate_round_indexed.argtypes = [P, P, U64, P, C.POINTER(abi.RoundPolicy), P, P, C.c_int]
         _lib = L
     return _lib
 
@@ -87,9 +93,12 @@ class Table:
         self.h = handle
 
     def __del__(self):
-        if self.h:
-            lib().oracle_table_free(self.h)
-            self.h = None
+        try:
+            if self.h:
+                lib().oracle_table_free(self.h)
+                self.h = None
+        except Exception:  # interpreter shutdown
+            pass
 
     @property
     def total(self):
@@ -133,3 +142,24 @@ def annotate_round(keys: np.ndarray, key_off: np.ndarray, refs: np.ndarray, ref_
                    policy: abi.RoundPolicy, annot_round: np.ndarray, hit: np.ndarray, nthreads: int = 1):
     lib().oracle_annotate_round(_ptr(keys), _ptr(key_off), len(key_off) - 1, _ptr(refs), _ptr(ref_off),
                                 len(ref_off) - 1, C.byref(policy), _ptr(annot_round), _ptr(hit), nthreads)
+
+
+class Index:
+    """Sorted 16-mer index of one library for the indexed CPU search (keeps its inputs alive)."""
+
+    def __init__(self, refs: np.ndarray, ref_off: np.ndarray):
+        self.refs, self.ref_off = np.ascontiguousarray(refs), np.ascontiguousarray(ref_off, dtype=np.uint32)
+        self.h = lib().oracle_index_build(_ptr(self.refs), _ptr(self.ref_off), len(self.ref_off) - 1, 1)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().oracle_index_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def annotate_round_indexed(keys, key_off, index: Index, policy, annot_round, hit, nthreads=1):
+    lib().oracle_annotate_round_indexed(_ptr(keys), _ptr(key_off), len(key_off) - 1, index.h, C.byref(policy),
+                                        _ptr(annot_round), _ptr(hit), nthreads)

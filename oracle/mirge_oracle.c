@@ -433,3 +433,115 @@ void oracle_annotate_round(const uint8_t *keys, const uint64_t *key_off, uint64_
     if (h != MIRGE_NO_HIT) { annot_round[i] = (uint8_t)pol->round; hit[i] = h; }
   }
 }
+
+/* ------------------------------------------------------------------ indexed search (CPU port) -
+ * Same valid-hit definition as scan_query, but candidates come from a sorted 16-mer index of the
+ * library and pigeonhole seeds, the way an FM-index aligner avoids scanning the text.  Used as the
+ * CPU baseline on libraries where the exhaustive scan is impractical (mRNA); checked against
+ * scan_query in tests/test_oracle_c.py. */
+typedef struct {
+  const uint8_t *text; const uint32_t *ref_off; uint32_t n_refs; uint64_t n_bases;
+  uint32_t *kmer, *pos; uint64_t n; uint32_t *bucket; int bucket_bits;
+} oidx_t;
+
+void oracle_index_free(void *h) { oidx_t *x = h; if (!x) return; free(x->kmer); free(x->pos); free(x->bucket); free(x); }
+
+void *oracle_index_build(const uint8_t *text, const uint32_t *ref_off, uint32_t n_refs, int nthreads) {
+  oidx_t *x = calloc(1, sizeof(oidx_t));
+  x->text = text; x->ref_off = ref_off; x->n_refs = n_refs; x->n_bases = ref_off[n_refs];
+  uint64_t nb = x->n_bases;
+  uint32_t *km = malloc((nb + 1) * 4), *ps = malloc((nb + 1) * 4);
+  uint64_t n = 0;
+  (void)nthreads;
+  for (uint32_t r = 0; r < n_refs; ++r) {
+    uint32_t lo = ref_off[r], hi = ref_off[r + 1];
+    for (uint32_t p = lo; p < hi; ++p) {
+      uint32_t k = 0; int v = 0;
+      for (int i = 0; i < 16 && p + i < hi; ++i) { int c = base_code(text[p + i]); if (c == 4) break; k |= (uint32_t)c << (2 * (15 - i)); ++v; }
+      if (v >= 4) { km[n] = k; ps[n] = p; ++n; }
+    }
+  }
+  /* stable LSD radix sort on the k-mer (positions are ascending already) */
+  uint32_t *km2 = malloc((n + 1) * 4), *ps2 = malloc((n + 1) * 4);
+  for (int pass = 0; pass < 2; ++pass) {
+    uint64_t *cnt = calloc(65537, sizeof(uint64_t));
+    int sh = 16 * pass;
+    for (uint64_t i = 0; i < n; ++i) cnt[((km[i] >> sh) & 0xFFFF) + 1]++;
+    for (int b = 0; b < 65536; ++b) cnt[b + 1] += cnt[b];
+    for (uint64_t i = 0; i < n; ++i) { uint64_t d = cnt[(km[i] >> sh) & 0xFFFF]++; km2[d] = km[i]; ps2[d] = ps[i]; }
+    free(cnt);
+    uint32_t *t = km; km = km2; km2 = t; t = ps; ps = ps2; ps2 = t;
+  }
+  free(km2); free(ps2);
+  x->kmer = km; x->pos = ps; x->n = n;
+  int bb = 4; while ((1ull << (bb + 2)) < n && bb < 24) ++bb;
+  x->bucket_bits = bb;
+  x->bucket = malloc(((1ull << bb) + 1) * 4);
+  uint64_t j = 0;
+  for (uint64_t b = 0; b <= (1ull << bb); ++b) {
+    uint64_t bound = b << (32 - bb);
+    while (j < n && (uint64_t)km[j] < bound) ++j;
+    x->bucket[b] = (uint32_t)j;
+  }
+  return x;
+}
+
+static uint64_t verify_at(const oidx_t *x, const uint8_t *qc, int L, int seed, const mirge_round_policy *pol, uint32_t r, uint32_t astart) {
+  const uint8_t *ref = x->text + astart;
+  int mm = 0, smm = 0;
+  for (int j = 0; j < L; ++j) {
+    int rc = base_code(ref[j]);
+    if (rc == 4) return MIRGE_NO_HIT;
+    if (qc[j] != rc) { ++mm; if (j < seed) ++smm; if (mm > pol->total_mm || smm > pol->seed_mm) return MIRGE_NO_HIT; }
+  }
+  return ((uint64_t)mm << 56) | ((uint64_t)r << 28) | (uint64_t)(astart - x->ref_off[r]);
+}
+
+static uint64_t search_query(const oidx_t *x, const uint8_t *q, int L, const mirge_round_policy *pol) {
+  uint64_t best = MIRGE_NO_HIT;
+  if (L <= 0) return best;
+  int seed = pol->seed_len == 0 ? L : (pol->seed_len < L ? pol->seed_len : L);
+  int np = pol->seed_mm + 1;
+  if (seed / np < 4) return scan_query(q, L, x->text, x->ref_off, x->n_refs, pol);
+  uint8_t qc[MIRGE_MAX_READ_LEN];
+  for (int j = 0; j < L; ++j) qc[j] = (uint8_t)base_code(q[j]);
+  for (int pi = 0; pi < np; ++pi) {
+    int a = (int)((long long)pi * seed / np), b = (int)((long long)(pi + 1) * seed / np);
+    int s = b - a < 16 ? b - a : 16, has_n = 0;
+    uint32_t k = 0;
+    for (int i = 0; i < b - a; ++i) { if (qc[a + i] == 4) has_n = 1; else if (i < s) k |= (uint32_t)qc[a + i] << (2 * (15 - i)); }
+    if (has_n) continue;
+    uint32_t span = s == 16 ? 0u : ((1u << (2 * (16 - s))) - 1u), k_hi = k | span;
+    int bsh = 32 - x->bucket_bits;
+    uint64_t lo = x->bucket[k >> bsh], hi = x->bucket[(k_hi >> bsh) + 1], l, h;
+    l = lo; h = hi; while (l < h) { uint64_t m = (l + h) >> 1; if (x->kmer[m] < k) l = m + 1; else h = m; } lo = l;
+    h = hi; while (l < h) { uint64_t m = (l + h) >> 1; if (x->kmer[m] <= k_hi) l = m + 1; else h = m; } hi = l;
+    for (uint64_t e = lo; e < hi; ++e) {
+      uint32_t pos = x->pos[e];
+      if (pos < (uint32_t)a) continue;
+      uint32_t astart = pos - (uint32_t)a;
+      uint32_t rl = 0, rh = x->n_refs;
+      while (rh - rl > 1) { uint32_t m = (rl + rh) >> 1; if (x->ref_off[m] <= pos) rl = m; else rh = m; }
+      if (astart < x->ref_off[rl] || (uint64_t)astart + (uint64_t)L > x->ref_off[rl + 1]) continue;
+      uint64_t hh = verify_at(x, qc, L, seed, pol, rl, astart);
+      if (hh < best) best = hh;
+    }
+  }
+  return best;
+}
+
+void oracle_annotate_round_indexed(const uint8_t *keys, const uint64_t *key_off, uint64_t n, void *index,
+                                   const mirge_round_policy *pol, uint8_t *annot_round, uint64_t *hit, int nthreads) {
+  const oidx_t *x = index;
+#pragma omp parallel for schedule(dynamic, 256) num_threads(nthreads > 0 ? nthreads : 1)
+  for (int64_t i = 0; i < (int64_t)n; ++i) {
+    const uint8_t *s = keys + key_off[i]; int len = (int)(key_off[i + 1] - key_off[i]);
+    if (pol->select == MIRGE_SELECT_LEN_LT26) { if (!(len < 26)) continue; }
+    else if (pol->select == MIRGE_SELECT_LEN_GT25) { if (!(len > 25)) continue; }
+    else if (annot_round[i] != 0xFF) continue;
+    int qs = 0, ql = round_query(s, len, pol, &qs);
+    if (ql < 0) continue;
+    uint64_t h = search_query(x, s + qs, ql, pol);
+    if (h != MIRGE_NO_HIT) { annot_round[i] = (uint8_t)pol->round; hit[i] = h; }
+  }
+}
