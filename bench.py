@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the digest -> collapse -> annotate hot path on synthetic reads.
+
+    python bench.py --gpus N --steps K --warmup W            (this repo's CUDA path)
+    python bench.py --impl reference --gpus N --steps K ...   (CPU path: the oracle port, all host threads)
+
+Workload (BASELINE.json configs[1]): 50 M-read single sample, L = 75, NextSeq poly-G
+tails, ``-a illumina -nxt 20 -q 20``, all ordered libraries incl. a 100 000-entry mRNA library.  A step is
+one whole pass of the hot path over that sample: tokenise -> trim -> collapse -> 9 annotation rounds.
+``value``: inputs resident in HBM.  ``e2e``: the same pass fed from pinned HOST memory through the
+streaming entry point (H2D of every input byte and D2H of the result table inside the timed region).
+Multi-GPU (weak scaling): every rank digests its own 50 M-read shard, unique sequences are hash-
+partitioned to their owner rank with one all-to-all, owners merge and annotate their slice.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "M reads/s trim+collapse+annotate"
+UNIT = "M reads/s"
+CFG_ID = 2
+WORKLOAD = "C2: 50M-read single sample, L=75, -a illumina -nxt 20 -q 20, full ordered library annotation (mRNA 100k entries)"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--reads", type=int, default=50_000_000, help="reads per GPU (default: the C2 sample size)")
+    ap.add_argument("--mrna", type=int, default=100_000, help="mRNA library entries")
+    ap.add_argument("--count-mode", default="head", choices=["head", "release"])
+    ap.add_argument("--cpu-sample", type=int, default=400_000, help="reads of the bounded CPU-baseline sample")
+    ap.add_argument("--batch-mb", type=int, default=512)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle port) -- cpu_baseline of the b200 line and the whole of --impl reference
+# ------------------------------------------------------------------------------------------------
+
+
+class CpuPath:
+    """The reference's CPU path restated (oracle/mirge_oracle.c): cutadapt-semantics digest + dict collapse
+    + the ordered rounds with an indexed bowtie-semantics search.  kind = "port": cutadapt / bowtie are not
+    installable here, so the reference itself cannot be timed."""
+
+    def __init__(self, libs, cfg, threads):
+        from mirge_b200 import params as P
+        from mirge_b200.libraries import ROUND_LIBS, round_policies
+        from oracle import coracle
+
+        self.co = coracle
+        self.threads = threads
+        self.cp = P.build_trim_params(cfg)
+        self.pols = round_policies()
+        self.round_libs = ROUND_LIBS
+        self.index = {}
+        lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+        for key, L in libs.libs.items():
+            self.index[key] = coracle.Index(lut[L.codes], L.off.astype(np.uint32))
+
+    def step(self, fq: np.ndarray, spike=False):
+        co = self.co
+        n, tab = co.digest_collapse(fq, self.cp, nthreads=self.threads)
+        keys, off, cnt = tab.export()
+        ar = np.full(len(cnt), 0xFF, dtype=np.uint8)
+        hit = np.full(len(cnt), 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+        for rnd in range(10 if spike else 9):
+            co.annotate_round_indexed(keys, off, self.index[self.round_libs[rnd]], self.pols[rnd], ar, hit, self.threads)
+        return n, len(cnt), int((ar != 0xFF).sum())
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import mirge_b200  # noqa: F401
+    from mirge_b200 import synth
+
+    threads = host_threads()
+    libs = synth.make_libraries(mrna_count=args.mrna)
+    cfg = synth.trim_config_for(CFG_ID, args.count_mode)
+    cpu = CpuPath(libs, cfg, threads)
+    gen = synth.ReadGenerator(libs, synth.CONFIGS[CFG_ID], "cpu")
+    sample = args.cpu_sample
+    fq = gen.fastq(sample).numpy()
+    for _ in range(args.warmup):
+        cpu.step(fq)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n, nu, na = cpu.step(fq)
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
+    v = sample / dt / 1e6
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "count_mode": args.count_mode, "reads_per_step": sample,
+                   "note": "bounded sample of the workload per step; CPU only"},
+        "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d reads of the C2 workload per step (oracle port: cutadapt/bowtie not installable)" % sample},
+        "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_b200(args):
+    import torch.distributed as dist
+
+    import mirge_b200  # noqa: F401
+    from mirge_b200 import device as D
+    from mirge_b200 import digest as DG
+    from mirge_b200 import distributed as MD
+    from mirge_b200 import libraries as LB
+    from mirge_b200 import manifoldAlign as MA
+    from mirge_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = D.Device(local)
+    torch.cuda.set_device(dev.tdev)
+    batch_bytes = args.batch_mb << 20
+
+    t_setup = time.perf_counter()
+    libs = synth.make_libraries(mrna_count=args.mrna)
+    lset = LB.LibrarySet.from_fasta_dict(dev, libs.fasta_dict())
+    cfg = synth.trim_config_for(CFG_ID, args.count_mode)
+    eng = D.DigestEngine(dev, cfg)
+    rc = synth.CONFIGS[CFG_ID]
+    if world > 1:
+        import dataclasses
+
+        rc = dataclasses.replace(rc, sample_seed=0)
+    gen = synth.ReadGenerator(libs, rc, dev.tdev)
+    gen.gen.manual_seed(2000 + CFG_ID + 7919 * rank)
+    fq = gen.fastq(args.reads, first_index=rank * args.reads)
+    del gen
+    torch.cuda.synchronize()
+    nbytes = int(fq.numel())
+    setup_s = time.perf_counter() - t_setup
+
+    table = D.CollapseTable(dev, min_keys=1 << 22)
+    owner = D.CollapseTable(dev, min_keys=1 << 22) if world > 1 else None
+    state = {}
+
+    def finish(tab_local):
+        """collapse done on this rank -> (exchange) -> annotate; returns (table, n_keys)"""
+        ids, cnt = tab_local.drain()
+        if world > 1:
+            owner.reset()
+            MD.exchange_and_merge(dev, tab_local, ids, cnt, owner, world)
+            ids, cnt = owner.drain()
+            tab = owner
+        else:
+            tab = tab_local
+        keys = MA.KeySet.from_table(tab)
+        annot, hit = MA.annotate_keys(dev, lset, keys, False)
+        state.update(ids=ids, cnt=cnt, annot=annot, hit=hit, tab=tab)
+        return tab
+
+    def step_resident():
+        table.reset()
+        n = eng.digest_device(fq, table, batch_bytes)
+        finish(table)
+        return n
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value")
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    dev.timing = True
+    dev.timer_totals()
+    launches0 = dev.launches
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        n_rec = step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / max(args.steps, 1)
+    timers = dev.timer_totals()
+    dev.timing = False
+    launches = (dev.launches - launches0) // max(args.steps, 1)
+    clk = clocks.stop() if clocks else None
+    tms = torch.tensor([ms], device=dev.tdev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms_max = float(tms.item())
+    n_unique = int(state["tab"].n_keys)
+    n_annot = int((state["annot"] != 0xFF).sum().item())
+    emitted_words = None
+
+    # ---- end to end from pinned host memory
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        host.copy_(fq)
+        torch.cuda.synchronize()
+        streamer = DG.HostStreamer(eng, batch_bytes)
+
+        def step_e2e():
+            table.reset()
+            n = streamer.run(host, table)
+            tab = finish(table)
+            # result table -> host: packed unique sequences, per-key counts and annotation
+            nk = tab.n_keys
+            out = [tab.arena[: tab.arena_used].cpu(), tab.key_ref[:nk].cpu(), state["ids"].cpu(), state["cnt"].cpu(),
+                   state["annot"].cpu(), state["hit"].cpu()]
+            return n, sum(int(t.numel()) * t.element_size() for t in out)
+
+        for _ in range(min(args.warmup, 2)):
+            step_e2e()
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        f0.record()
+        for _ in range(args.steps):
+            _, d2h = step_e2e()
+        f1.record()
+        barrier()
+        wall = (time.perf_counter() - t0) / max(args.steps, 1) * 1e3
+        ems = max(f0.elapsed_time(f1) / max(args.steps, 1), wall * 0.0)
+        tme = torch.tensor([ems], device=dev.tdev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tme, op=dist.ReduceOp.MAX)
+        e2e = {"value": round(args.reads * world / (float(tme.item()) / 1e3) / 1e6, 3), "unit": UNIT,
+               "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h), "ms_per_step": round(float(tme.item()), 3)}
+        del host, streamer
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (CUDA events on the launch stream, timed region above)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    E = eng.E
+    rec_bytes = nbytes / args.reads
+    steps = max(args.steps, 1)
+    kinfo = {}
+    for name, (cnt_l, tot_ms) in timers.items():
+        kinfo[name] = {"launches_per_step": cnt_l // steps, "ms_per_step": round(tot_ms / steps, 3)}
+    # algorithmic bytes per read: trim R + 8E ; collapse sum over emitted keys (2K + 16)
+    b_trim = rec_bytes + 8 * E
+    trim_ms = timers.get("trim", (0, 0.0))[1] / steps
+    col_ms = timers.get("collapse", (0, 0.0))[1] / steps
+    ann_ms = timers.get("annotate", (0, 0.0))[1] / steps
+    trim_gbs = args.reads * b_trim / (trim_ms / 1e3) / 1e9 if trim_ms else 0.0
+    kinfo.setdefault("trim", {})["achieved_gbs"] = round(trim_gbs, 1)
+    kinfo["trim"]["frac_hbm"] = round(trim_gbs / peak, 4)
+    dom = max((("trim", trim_ms), ("collapse", col_ms), ("annotate", ann_ms)), key=lambda kv: kv[1])[0]
+    roofline = {"kernel": "trim_kernel", "bound": "hbm", "achieved": round(trim_gbs, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(trim_gbs / peak, 4), "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_read": round(b_trim, 1), "dominant_by_time": dom,
+                "launches_per_step": kinfo["trim"].get("launches_per_step")}
+
+    # ---- CPU baseline on a bounded sample of the same bytes (rank 0, N = 1 only)
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = host_threads()
+        sample = min(args.cpu_sample, args.reads)
+        sb = int(sample * rec_bytes * 1.02) + 4096
+        raw = fq[: min(sb, nbytes)].cpu().numpy()
+        # cut at the end of read `sample`
+        nl = np.flatnonzero(raw == 10)
+        raw = raw[: int(nl[4 * sample - 1]) + 1] if nl.size >= 4 * sample else raw[: int(nl[(nl.size // 4) * 4 - 1]) + 1]
+        sample = min(sample, nl.size // 4)
+        cpu = CpuPath(libs, cfg, threads)
+        cpu.step(raw[: len(raw) // 8])
+        t0 = time.perf_counter()
+        cpu.step(raw)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {"value": round(sample / dt / 1e6, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": "first %d reads of the same synthetic workload, oracle port of cutadapt+bowtie semantics, %d threads, %.1f s"
+                                  % (sample, threads, dt)}
+
+    value = args.reads * world / (ms_max / 1e3) / 1e6
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_max, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "reads_per_gpu": args.reads, "read_len": rc.L, "count_mode": args.count_mode,
+                   "fastq_bytes_per_gpu": nbytes, "l2": "inputs (%.1f GB per pass) larger than L2" % (nbytes / 1e9),
+                   "batch_mb": args.batch_mb, "unique_sequences": n_unique, "annotated_sequences": n_annot,
+                   "emission_slots_per_read": E, "setup_s": round(setup_s, 1)},
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kinfo,
+        "clocks": clk, "bit_exact": "tests/ -m gpu (oracle parity); bench does not re-check",
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

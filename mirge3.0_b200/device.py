@@ -5,6 +5,7 @@ PyTorch is plumbing only here (device memory, streams, the sort used when an ind
 every byte of the hot path is touched by the kernels in ``csrc/`` through the C ABI."""
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from dataclasses import dataclass
 from typing import Optional
@@ -53,6 +54,8 @@ class Device:
         self.trim_params: Optional[abi.TrimParams] = None
         self.slots = 0
         self.launches = 0  # kernels launched through this context (bench.py reports it)
+        self.timing = False  # bench.py: CUDA-event timing of the hot kernels on their launch stream
+        self._timers = {}
 
     def __del__(self):
         try:
@@ -71,6 +74,27 @@ class Device:
         if rc == abi.ERR_CAPACITY:
             raise CapacityError(msg)
         raise MirgeError("%s (code %d)" % (msg, rc))
+
+    @contextlib.contextmanager
+    def timed(self, name: str):
+        """Bracket the kernels enqueued inside with CUDA events on the current (launch) stream."""
+        if not self.timing:
+            yield
+            return
+        st = torch.cuda.current_stream(self.tdev)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        yield
+        b.record(st)
+        self._timers.setdefault(name, []).append((a, b))
+
+    def timer_totals(self, reset: bool = True):
+        """{name: (n_launch_groups, total_ms)} after synchronising the device."""
+        torch.cuda.synchronize(self.tdev)
+        out = {k: (len(v), float(sum(a.elapsed_time(b) for a, b in v))) for k, v in self._timers.items()}
+        if reset:
+            self._timers = {}
+        return out
 
     def stream(self) -> C.c_void_p:
         return C.c_void_p(torch.cuda.current_stream(self.tdev).cuda_stream)
@@ -226,8 +250,9 @@ class DigestEngine:
         st = d.stream()
         scratch = d.empty(lib.mirge_tokenise_scratch_bytes(nbytes), torch.uint8)
         n_rec, consumed = C.c_uint64(0), C.c_uint64(0)
-        d.check(lib.mirge_tokenise_sync(d.ctx, _ptr(buf), nbytes, 1 if is_final else 0, _ptr(scratch),
-                                        C.byref(n_rec), C.byref(consumed), st))
+        with d.timed("tokenise"):
+            d.check(lib.mirge_tokenise_sync(d.ctx, _ptr(buf), nbytes, 1 if is_final else 0, _ptr(scratch),
+                                            C.byref(n_rec), C.byref(consumed), st))
         d.launches += 3 if not is_final else 2
         n = int(n_rec.value)
         if n == 0:
@@ -235,7 +260,8 @@ class DigestEngine:
         used = int(consumed.value)
         line_start = d.empty(4 * n + 4, torch.int32)
         # same nbytes as the census: the scratch layout depends on it
-        d.check(lib.mirge_line_index(d.ctx, _ptr(buf), nbytes, _ptr(scratch), _ptr(line_start), n, st))
+        with d.timed("line_index"):
+            d.check(lib.mirge_line_index(d.ctx, _ptr(buf), nbytes, _ptr(scratch), _ptr(line_start), n, st))
         d.launches += 2
         win = d.empty(n * E * 4, torch.int16)
         key_off = d.empty(n * E, torch.int32)
@@ -243,8 +269,9 @@ class DigestEngine:
         for attempt in range(2):
             keys = d.empty(cap, torch.int32)
             ctrl = d.zeros(8, torch.int64)
-            d.check(lib.mirge_trim(d.ctx, _ptr(buf), used, _ptr(line_start), n, _ptr(win), _ptr(key_off),
-                                   _ptr(keys), cap, _ptr(ctrl), st))
+            with d.timed("trim"):
+                d.check(lib.mirge_trim(d.ctx, _ptr(buf), used, _ptr(line_start), n, _ptr(win), _ptr(key_off),
+                                       _ptr(keys), cap, _ptr(ctrl), st))
             d.launches += 1
             c = ctrl.cpu().numpy().view(np.uint64)
             flags = int(c[2])
@@ -272,8 +299,9 @@ class DigestEngine:
         table.reserve(br.n_emitted, br.key_words)
         n_slots = br.n_records * self.E
         deferred = d.empty(n_slots, torch.int32)
-        d.check(lib.mirge_collapse_insert(d.ctx, C.byref(table.struct), _ptr(br.keys), _ptr(br.key_off), n_slots,
-                                          _ptr(deferred), d.stream()))
+        with d.timed("collapse"):
+            d.check(lib.mirge_collapse_insert(d.ctx, C.byref(table.struct), _ptr(br.keys), _ptr(br.key_off), n_slots,
+                                              _ptr(deferred), d.stream()))
         d.launches += 3
         table.check()
 

@@ -59,63 +59,73 @@ class HostStreamer:
         self.copy_stream = torch.cuda.Stream(device=self.dev.tdev)
         self.h2d_bytes = 0
 
-    def _fill(self, src, hbuf: torch.Tensor) -> int:
-        mv = memoryview(hbuf.numpy())
-        got = 0
-        while got < self.batch:
-            k = src.readinto(mv[got:])
-            if not k:
-                break
-            got += k
-        return got
+    def _pieces(self, src):
+        """Yield pinned host tensors of <= batch bytes covering the stream, in order.  A pinned torch
+        tensor is sliced in place (no staging copy); anything with readinto() is staged through the
+        two pinned buffers."""
+        if isinstance(src, torch.Tensor):
+            if src.is_cuda or src.dtype != torch.uint8 or not src.is_pinned():
+                raise MirgeError("host tensor source must be a pinned uint8 tensor")
+            for pos in range(0, int(src.numel()), self.batch):
+                yield src[pos : pos + self.batch]
+            return
+        cur = 0
+        while True:
+            mv = memoryview(self.h[cur].numpy())
+            got = 0
+            while got < self.batch:
+                k = src.readinto(mv[got:])
+                if not k:
+                    break
+                got += k
+            if got == 0:
+                return
+            yield self.h[cur][:got]
+            if got < self.batch:
+                return
+            cur ^= 1
 
     def run(self, src, table: CollapseTable) -> int:
-        """Digest the whole stream into ``table``; returns the number of records parsed."""
+        """Digest the whole stream into ``table``; returns the number of records parsed.  The H2D copy
+        of piece k+1 (copy stream) overlaps the kernels of piece k (main stream)."""
         eng, dev = self.eng, self.dev
         main = torch.cuda.current_stream(dev.tdev)
+        it = self._pieces(src)
         n_records = 0
-        leftover = 0
         cur = 0
-        got = self._fill(src, self.h[cur])
-        first = True
-        prev_buf = None
-        prev_tail = (0, 0)
+        nxt = next(it, None)
+        if nxt is None:
+            return 0
+        # prime: first piece into d[0]
+        with torch.cuda.stream(self.copy_stream):
+            self.d[0][: nxt.numel()].copy_(nxt, non_blocking=True)
+        self.h2d_bytes += int(nxt.numel())
+        filled = int(nxt.numel())  # bytes of the *new* piece sitting in d[cur] after `leftover`
+        leftover = 0
         while True:
-            final = got < self.batch
-            nxt_got = 0
             dbuf = self.d[cur]
-            if leftover:
-                a, b = prev_tail
-                dbuf[:leftover].copy_(prev_buf[a:b])
-            if got:
-                with torch.cuda.stream(self.copy_stream):
-                    self.copy_stream.wait_stream(main)
-                    dbuf[leftover : leftover + got].copy_(self.h[cur][:got], non_blocking=True)
-                self.h2d_bytes += got
-            # overlap: read the next piece from the host stream while the copy is in flight
-            if not final:
-                nxt_got = self._fill(src, self.h[cur ^ 1])
             main.wait_stream(self.copy_stream)
-            nbytes = leftover + got
-            if nbytes == 0:
-                break
-            if final and nxt_got == 0:
-                br = eng.trim_batch(dbuf, nbytes, True, keep=False)
-            else:
-                br = eng.trim_batch(dbuf, nbytes, False, keep=False)
+            nbytes = leftover + filled
+            nxt = next(it, None)  # host-side read of the next piece overlaps the work queued below
+            final = nxt is None
+            br = eng.trim_batch(dbuf, nbytes, final, keep=False)
+            if not final:
+                tail = nbytes - br.consumed
+                if tail > self.cap - self.batch:
+                    raise FastqFormatError("FASTQ record longer than %d bytes" % (self.cap - self.batch))
+                obuf = self.d[cur ^ 1]
+                if tail:
+                    obuf[:tail].copy_(dbuf[br.consumed : nbytes])
+                with torch.cuda.stream(self.copy_stream):
+                    self.copy_stream.wait_stream(main)  # obuf's previous kernels and the tail copy are done
+                    obuf[tail : tail + nxt.numel()].copy_(nxt, non_blocking=True)
+                self.h2d_bytes += int(nxt.numel())
             eng.collapse_batch(table, br)
             n_records += br.n_records
             if final:
                 break
-            if br.consumed == 0 and nbytes >= self.cap - 64:
-                raise FastqFormatError("FASTQ record does not fit into the staging buffer")
-            prev_buf, prev_tail = dbuf, (br.consumed, nbytes)
-            leftover = nbytes - br.consumed
-            if leftover > self.cap - self.batch:
-                raise FastqFormatError("FASTQ record longer than %d bytes" % (self.cap - self.batch))
+            leftover, filled = tail, int(nxt.numel())
             cur ^= 1
-            got = nxt_got
-            first = False
         return n_records
 
 
@@ -161,7 +171,7 @@ def digest_sample(eng: DigestEngine, source, table: CollapseTable, first_level: 
     if isinstance(source, torch.Tensor) and source.is_cuda:
         count = eng.digest_device(source, target, batch_bytes)
     else:
-        if not hasattr(source, "readinto"):
+        if not hasattr(source, "readinto") and not isinstance(source, torch.Tensor):
             source = _BytesSource(source)
         st = streamer or HostStreamer(eng, batch_bytes)
         count = st.run(source, target)
