@@ -355,7 +355,7 @@ def run_b200(args):
         raw = raw[: int(nl[4 * sample - 1]) + 1] if nl.size >= 4 * sample else raw[: int(nl[(nl.size // 4) * 4 - 1]) + 1]
         sample = min(sample, nl.size // 4)
         cpu = CpuPath(libs, cfg, threads)
-        cpu.step(raw[: len(raw) // 8])
+        cpu.step(raw[: int(nl[4 * max(sample // 8, 1) - 1]) + 1])  # warm-up on a record-aligned prefix
         t0 = time.perf_counter()
         cpu.step(raw)
         dt = time.perf_counter() - t0
