@@ -193,6 +193,12 @@ int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, const ui
                uint64_t n_records, uint16_t *d_win, uint32_t *d_key_off, uint32_t *d_keys,
                uint64_t keys_capacity_words, uint64_t *d_trim_ctrl, void *stream);
 
+/* Kernel selection for mirge_trim: 0 = automatic (bit-parallel kernel when every adapter is a 3'
+ * adapter with indels and <= 32 nt, else the generic full-DP kernel), 1 = always generic.  When the
+ * bit-parallel kernel meets a record group that does not fit its shared-memory staging it sets bit 3
+ * of d_trim_ctrl[2]; the caller then repeats the batch with mode 1. */
+int mirge_trim_mode(mirge_ctx *ctx, int mode);
+
 /* ---- stage 2: collapse (digest.py:141-163,164-205,237-245) --------------------------------- */
 int mirge_table_reset(mirge_ctx *ctx, const mirge_table *t, void *stream);
 /* completeDict[key] += 1 for every emitted key of a batch.  d_deferred: u32[2 * n_slots] scratch. */

@@ -15,6 +15,8 @@ struct mirge_ctx {
   mirge_trim_params params;
   int params_set;
   int max_adapter_len;
+  int fast_ok;    // every adapter is a 3' adapter with indels and m <= 32: bit-parallel trim kernel applies
+  int trim_mode;  // 0 = auto, 1 = force the generic full-DP kernel (tests)
   int sm_count;
 };
 

@@ -21,6 +21,7 @@ struct DevAdapter {
   uint64_t peq[5];  // bit i-1 set <=> adapter row i matches read class c (A,C,G,T,other)
   int n_counts[MIRGE_MAX_ADAPTER_LEN + 1];
   int max_err[MIRGE_MAX_ADAPTER_LEN + 1];
+  int acc[MIRGE_MAX_ADAPTER_LEN + 1];  // 3' adapters: max errors of a candidate ending in adapter row i, -1 = never
 };
 struct DevParams {
   int n_mods, kind[MIRGE_MAX_MODS], a[MIRGE_MAX_MODS], b[MIRGE_MAX_MODS], c[MIRGE_MAX_MODS];
@@ -63,7 +64,7 @@ extern "C" int mirge_set_trim_params(mirge_ctx *ctx, const mirge_trim_params *p)
   if (p->umi_mode < MIRGE_UMI_NONE || p->umi_mode > MIRGE_UMI_QIAGEN) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "bad umi_mode");
   if (p->umi_mode != MIRGE_UMI_NONE && (p->umi5 < 0 || p->umi3 < 0)) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "negative UMI length");
   if (p->umi_mode == MIRGE_UMI_QIAGEN && p->n_adapters < 1) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "qiagen UMI mode needs an adapter");
-  int maxm = 0;
+  int maxm = 0, fast_ok = 1;
   for (int a = 0; a < p->n_adapters; ++a) {
     const mirge_adapter *s = &p->adapters[a];
     if (s->m < 1 || s->m > MIRGE_MAX_ADAPTER_LEN) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "adapter %d length %d unsupported", a, s->m);
@@ -80,6 +81,11 @@ extern "C" int mirge_set_trim_params(mirge_ctx *ctx, const mirge_trim_params *p)
     o->peq[4] = 0;  // a read character outside ACGT never matches (match_read_wildcards=False)
     memcpy(o->n_counts, s->n_counts, sizeof(o->n_counts));
     memcpy(o->max_err, s->max_err, sizeof(o->max_err));
+    for (int i = 0; i <= s->m; ++i) {
+      const int eff = s->wildcard_ref ? i - s->n_counts[i] : i;
+      o->acc[i] = (i >= s->min_overlap && i >= 1 && eff >= 0) ? s->max_err[eff] : -1;
+    }
+    if (s->where != 0 || s->indel_cost != 1 || s->m > 32 || s->min_overlap < 1) fast_ok = 0;
     if (s->m > maxm) maxm = s->m;
   }
   MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -87,6 +93,7 @@ extern "C" int mirge_set_trim_params(mirge_ctx *ctx, const mirge_trim_params *p)
   ctx->params = *p;
   ctx->params_set = 1;
   ctx->max_adapter_len = maxm;
+  ctx->fast_ok = fast_ok;
   return MIRGE_OK;
 }
 
@@ -204,13 +211,133 @@ __device__ __noinline__ bool locate(const int a, const uint8_t *read, const int 
   return true;
 }
 
+// ------------------------------------------------------------------ bit-parallel locate ------
+// Same result as locate() for 3' adapters with unit indel cost and m <= 32, at ~15 instructions per
+// read base instead of ~15 per DP cell:
+//   1. Myers/Hyyro bit-vector recurrence gives the exact DP cost column (vertical deltas VP/VN) for
+//      every read position; the cost of adapter row m is tracked incrementally.
+//   2. cutadapt's candidates are the row-m cell of every column and all rows of the last column; their
+//      costs come from (1).  A candidate's (origin, matches) are those of the path cutadapt's
+//      tie-breaking (mismatch, then insertion, then deletion) would propagate into that cell; that path
+//      is recovered by a traceback that needs only DP costs of neighbouring cells, read from a ring of
+//      the last m + k + 2 cost columns kept in shared memory (a path with <= k errors into row i spans
+//      at most i + k columns).  cost == 0 cells need no traceback (pure diagonal).
+//   3. The winner is the maximum of (matches, -cost, -scan order) as in Aligner.locate; candidates
+//      that cannot win (row index <= best matches) are skipped without a traceback.
+struct FastCtx {
+  const uint32_t *s_eq;  // [n_adapters][256]: bit i-1 set <=> adapter row i matches this read byte
+  uint32_t *ring_vp;     // this thread's column slots, stride TRIM_THREADS words
+  uint32_t *ring_vn;
+};
+
+__device__ __forceinline__ int cell_cost(uint32_t vp, uint32_t vn, int r) {
+  const uint32_t mask = r >= 32 ? 0xFFFFFFFFu : ((1u << r) - 1u);
+  return __popc(vp & mask) - __popc(vn & mask);
+}
+
+// (matches, origin) cutadapt's DP holds in cell (i, j) whose cost is c > 0; slot_j = ring slot of column j
+__device__ __noinline__ void traceback(const uint32_t *eqt, const uint8_t *read, const FastCtx &fc, int W, int i, int j, int c,
+                                       int slot_j, int &matches, int &origin) {
+  int r = i, col = j, cost = c, nonmatch = 0;
+  while (r > 0 && cost > 0) {
+    if (col == 0) {  // initial column: cost r, origin 0, no further matches
+      nonmatch += r;
+      r = 0;
+      break;
+    }
+    if ((eqt[read[col - 1]] >> (r - 1)) & 1u) {  // equal characters: diagonal, cost unchanged
+      --r; --col;
+      continue;
+    }
+    int s0 = slot_j - (j - col);
+    if (s0 < 0) s0 += W;
+    int s1 = s0 == 0 ? W - 1 : s0 - 1;
+    const uint32_t vp0 = fc.ring_vp[s0 * TRIM_THREADS], vn0 = fc.ring_vn[s0 * TRIM_THREADS];
+    const uint32_t vp1 = fc.ring_vp[s1 * TRIM_THREADS], vn1 = fc.ring_vn[s1 * TRIM_THREADS];
+    const int cd = cell_cost(vp1, vn1, r - 1) + 1, cdel = cell_cost(vp1, vn1, r) + 1, cins = cell_cost(vp0, vn0, r - 1) + 1;
+    if (cd <= cdel && cd <= cins) { --r; --col; ++nonmatch; cost = cd - 1; }
+    else if (cins <= cdel) { --r; ++nonmatch; cost = cins - 1; }
+    else { --col; cost = cdel - 1; }
+  }
+  origin = col - r;  // r > 0 here means cost == 0: r more diagonal matches
+  matches = i - nonmatch;
+}
+
+__device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, const int n, const FastCtx &fc, Match &out) {
+  const DevAdapter &ad = c_p.ad[a];
+  const int m = ad.m, k = ad.k, W = m + k + 2;
+  const uint32_t *eqt = fc.s_eq + a * 256;
+  const uint32_t top = 1u << (m - 1);
+  const int acc_m = ad.acc[m];
+  uint32_t vp = 0xFFFFFFFFu, vn = 0u;
+  int score = m, slot = 0;
+  fc.ring_vp[0] = vp;
+  fc.ring_vn[0] = vn;
+  bool have = false;
+  int b_m = 0, b_c = 0, b_o = 0, b_idx = 0;
+  bool stopped = false;
+  for (int j = 1; j <= n; ++j) {
+    const uint32_t eq = eqt[read[j - 1]];
+    const uint32_t xv = eq | vn;
+    const uint32_t xh = (((eq & vp) + vp) ^ vp) | eq;
+    uint32_t hp = vn | ~(xh | vp);
+    uint32_t hn = vp & xh;
+    score += (hp & top) ? 1 : 0;
+    score -= (hn & top) ? 1 : 0;
+    hp <<= 1;
+    hn <<= 1;
+    vp = hn | ~(xv | hp);
+    vn = hp & xv;
+    slot = (slot + 1 == W) ? 0 : slot + 1;
+    fc.ring_vp[slot * TRIM_THREADS] = vp;
+    fc.ring_vn[slot * TRIM_THREADS] = vn;
+    if (score <= acc_m && j < n) {  // row-m candidate (column n is handled with the last column)
+      if (score == 0) {              // exact full adapter: cutadapt stops here
+        have = true; b_m = m; b_c = 0; b_o = j - m; b_idx = j;
+        stopped = true;
+        break;
+      }
+      if (!have || m > b_m || (m == b_m && score < b_c)) {
+        int mt, org;
+        traceback(eqt, read, fc, W, m, j, score, slot, mt, org);
+        if (!have || mt > b_m || (mt == b_m && score < b_c)) { have = true; b_m = mt; b_c = score; b_o = org; b_idx = j; }
+      }
+    }
+  }
+  if (!stopped) {
+    int c = 0;
+    for (int i = 1; i <= m; ++i) {
+      c += (int)((vp >> (i - 1)) & 1u) - (int)((vn >> (i - 1)) & 1u);  // D[i][n]
+      if (c > ad.acc[i]) continue;
+      const int idx = (i == m) ? n : n + 1 + i;  // row m of column n precedes the last-column scan
+      if (c == 0) {
+        if (!have || i > b_m || (i == b_m && (0 < b_c || (b_c == 0 && idx < b_idx)))) { have = true; b_m = i; b_c = 0; b_o = n - i; b_idx = idx; }
+        continue;
+      }
+      const bool may_win = !have || i > b_m || (i == b_m && (c < b_c || (c == b_c && idx < b_idx)));
+      if (!may_win) continue;
+      int mt, org;
+      traceback(eqt, read, fc, W, i, n, c, slot, mt, org);
+      if (!have || mt > b_m || (mt == b_m && (c < b_c || (c == b_c && idx < b_idx)))) { have = true; b_m = mt; b_c = c; b_o = org; b_idx = idx; }
+    }
+  }
+  if (!have) return false;
+  out.rstart = b_o;
+  out.rstop = b_idx <= n ? b_idx : n;
+  out.matches = b_m;
+  out.errors = b_c;
+  return true;
+}
+
 // AdapterCutter._best_match: most matches, then fewer errors, first adapter wins ties.
-template <int MAXM>
-__device__ __forceinline__ int best_match(const uint8_t *read, int n, Match &best) {
+template <int MAXM, bool FAST>
+__device__ __forceinline__ int best_match(const uint8_t *read, int n, Match &best, const FastCtx &fc) {
   int which = -1;
   for (int a = 0; a < c_p.n_adapters; ++a) {
     Match mt;
-    if (!locate<MAXM>(a, read, n, mt)) continue;
+    if (FAST) {
+      if (!locate_fast(a, read, n, fc, mt)) continue;
+    } else if (!locate<MAXM>(a, read, n, mt)) continue;
     if (which < 0 || mt.matches > best.matches || (mt.matches == best.matches && mt.errors < best.errors)) {
       best = mt;
       which = a;
@@ -219,8 +346,8 @@ __device__ __forceinline__ int best_match(const uint8_t *read, int n, Match &bes
   return which;
 }
 
-template <int MAXM>
-__device__ __forceinline__ void apply_mod(int mi, const uint8_t *seq, const uint8_t *qual, int &start, int &stop) {
+template <int MAXM, bool FAST>
+__device__ __forceinline__ void apply_mod(int mi, const uint8_t *seq, const uint8_t *qual, int &start, int &stop, const FastCtx &fc) {
   const int len = stop - start;
   switch (c_p.kind[mi]) {
     case MIRGE_MOD_NEXTSEQ:
@@ -236,7 +363,7 @@ __device__ __forceinline__ void apply_mod(int mi, const uint8_t *seq, const uint
     case MIRGE_MOD_ADAPTER:
       for (int t = 0; t < c_p.times; ++t) {
         Match mt;
-        const int a = best_match<MAXM>(seq + start, stop - start, mt);
+        const int a = best_match<MAXM, FAST>(seq + start, stop - start, mt, fc);
         if (a < 0) break;
         if (c_p.ad[a].where == 0) stop = start + mt.rstart;
         else start = start + mt.rstop;
@@ -270,16 +397,33 @@ __device__ __forceinline__ uint32_t key_byte(const uint8_t *seq, int start, int 
   return p < l1 ? seq[start + p] : seq[us + p - l1];
 }
 
-template <int MAXM>
+#define PACK_WORDS 8  // reads up to 128 bases keep their 2-bit text in registers for key emission
+
+// FAST = bit-parallel adapter search (locate_fast) + register-resident key packing; requires the CTA's
+// span to be staged in shared memory, otherwise the batch is flagged (ctrl[2] bit 3) for the generic kernel.
+template <int MAXM, bool FAST>
 __global__ void __launch_bounds__(TRIM_THREADS)
 trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__restrict__ line_start, uint64_t n_records,
             ushort4 *__restrict__ win, uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys, uint64_t keys_cap,
-            unsigned long long *__restrict__ ctrl, uint32_t smem_bytes) {
+            unsigned long long *__restrict__ ctrl, uint32_t smem_bytes, uint32_t ring_depth) {
   extern __shared__ uint4 smem4[];
   __shared__ uint32_t s_scan[TRIM_THREADS / 32];
   __shared__ unsigned long long s_base;
   uint8_t *sbuf = (uint8_t *)smem4;
   const int tid = threadIdx.x;
+  FastCtx fc;
+  fc.s_eq = nullptr; fc.ring_vp = nullptr; fc.ring_vn = nullptr;
+  if (FAST) {
+    // smem: [staging smem_bytes][eq tables n_adapters * 256 words][ring vp W * T words][ring vn W * T words]
+    uint32_t *eq = (uint32_t *)(sbuf + smem_bytes);
+    for (int e = tid; e < c_p.n_adapters * 256; e += TRIM_THREADS) {
+      const uint32_t code = base_code_upper((uint32_t)(e & 255));
+      eq[e] = code < 4u ? (uint32_t)c_p.ad[e >> 8].peq[code] : 0u;
+    }
+    fc.s_eq = eq;
+    fc.ring_vp = eq + c_p.n_adapters * 256 + tid;
+    fc.ring_vn = fc.ring_vp + ring_depth * TRIM_THREADS;
+  }
   const uint64_t r0 = (uint64_t)blockIdx.x * TRIM_THREADS;
   const uint64_t r = r0 + tid;
   const bool valid = r < n_records;
@@ -288,6 +432,10 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
   const uint64_t span_hi = min((uint64_t)line_start[4 * r_end], nbytes);
   const uint32_t alo = span_lo & ~15u;
   const bool staged = (span_hi - alo) <= smem_bytes;
+  if (FAST && !staged) {  // uniform per CTA
+    if (tid == 0) atomicOr(ctrl + 2, 8ull);
+    return;
+  }
   if (staged) {
     for (uint64_t o = (uint64_t)tid * 16; alo + o < span_hi; o += TRIM_THREADS * 16) {
       const uint64_t g = alo + o;
@@ -308,6 +456,9 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
   for (int s = 0; s < MIRGE_MAX_MODS; ++s) { w_start[s] = w_stop[s] = w_us[s] = w_ue[s] = 0; w_words[s] = 0; }
   const uint8_t *seq = nullptr;
   uint32_t my_words = 0, my_kept = 0;
+  uint32_t P[PACK_WORDS];
+  int p0 = 0;
+  bool fast_emit = FAST;
   if (valid) {
     const uint4 ls = *(const uint4 *)(line_start + 4 * r);
     const uint32_t nxt = line_start[4 * r + 4];
@@ -323,7 +474,7 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
       const uint8_t *qual = B + ls.w;
       int start = 0, stop = sl;
       if (c_p.umi_mode == MIRGE_UMI_QIAGEN) {
-        for (int mi = 0; mi < c_p.n_mods; ++mi) apply_mod<MAXM>(mi, seq, qual, start, stop);
+        for (int mi = 0; mi < c_p.n_mods; ++mi) apply_mod<MAXM, FAST>(mi, seq, qual, start, stop, fc);
         const int tl = stop - start, U = c_p.umi3;
         int us = 0, ue = 0;
         if (tl > 0) {
@@ -341,7 +492,7 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
 #pragma unroll
         for (int mi = 0; mi < MIRGE_MAX_MODS; ++mi) {
           if (mi < c_p.n_mods) {
-            apply_mod<MAXM>(mi, seq, qual, start, stop);
+            apply_mod<MAXM, FAST>(mi, seq, qual, start, stop, fc);
             if (E != 1 || mi == c_p.n_mods - 1) {
               const int slot = (E == 1) ? 0 : mi;
               int ln = stop - start;
@@ -353,10 +504,49 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
           }
         }
       }
+      // FAST: 2-bit text of read[p0 : p0 + 16 * PACK_WORDS) once, in registers
+      if (FAST) {
+        p0 = -1;
+        int pe = 0;
+#pragma unroll
+        for (int s = 0; s < MIRGE_MAX_MODS; ++s)
+          if (s < E && w_words[s]) {
+            if (p0 < 0 || w_start[s] < p0) p0 = w_start[s];
+            pe = max(pe, w_stop[s]);
+            if (w_ue[s] > w_us[s]) fast_emit = false;
+          }
+        if (p0 < 0 || pe - p0 > 16 * PACK_WORDS) fast_emit = false;
+        if (fast_emit) {
+          uint32_t anyexc = 0;
+#pragma unroll
+          for (int w = 0; w < PACK_WORDS; ++w) {
+            uint32_t word = 0;
+            if (p0 + 16 * w < pe) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int p = p0 + 16 * w + q;
+                if (p < pe) {
+                  const uint32_t ch = seq[p];
+                  word |= (((ch >> 1) ^ (ch >> 2)) & 3u) << (2 * q);
+                  anyexc |= (ch != 'A') & (ch != 'C') & (ch != 'G') & (ch != 'T');
+                }
+              }
+            }
+            P[w] = word;
+          }
+          if (anyexc) fast_emit = false;
+        }
+      }
       // size of every kept key: header + payload + exceptions
 #pragma unroll
       for (int s = 0; s < MIRGE_MAX_MODS; ++s) {
-        if (s < E && w_words[s]) {
+        if (FAST && fast_emit) {
+          if (s < E && w_words[s]) {
+            w_words[s] = 1u + ((uint32_t)(w_stop[s] - w_start[s] + 15) >> 4);
+            my_words += w_words[s];
+            ++my_kept;
+          }
+        } else if (s < E && w_words[s]) {
           const int l1 = w_stop[s] - w_start[s], len = l1 + (w_ue[s] - w_us[s]);
           uint32_t nexc = 0;
           for (int p = 0; p < len; ++p) nexc += base_code_exact(key_byte(seq, w_start[s], l1, w_us[s], p)) == 4u;
@@ -403,6 +593,31 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
         const uint32_t npay = (uint32_t)(len + 15) >> 4;
         const uint32_t nexc = w_words[s] - 1u - npay;
         uint32_t *k = keys + off;
+        if (FAST && fast_emit) {
+          // key = 2-bit text of read[w_start : w_stop), a slice of the register-resident words
+          k[0] = (uint32_t)len;
+          const int sh = w_start[s] - p0;  // bases to skip (0 in the common case)
+#pragma unroll
+          for (int w = 0; w < PACK_WORDS; ++w) {
+            if (16 * w < len) {
+              uint32_t v;
+              if (sh == 0) v = P[w];
+              else {
+                // dynamic base shift: select words by comparing indices (keeps P in registers)
+                const int wi = (sh >> 4) + w, bs = 2 * (sh & 15);
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int x = 0; x < PACK_WORDS; ++x) { if (x == wi) lo = P[x]; if (x == wi + 1) hi = P[x]; }
+                v = bs ? __funnelshift_r(lo, hi, bs) : lo;
+              }
+              const int rem = len - 16 * w;
+              if (rem < 16) v &= (1u << (2 * rem)) - 1u;
+              k[1 + w] = v;
+            }
+          }
+          off += w_words[s];
+          continue;
+        }
         k[0] = (uint32_t)len | (nexc << 16);
         uint32_t word = 0, xi = 0;
         for (int p = 0; p < len; ++p) {
@@ -446,15 +661,31 @@ extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbyte
   const unsigned grid = (unsigned)((n_records + TRIM_THREADS - 1) / TRIM_THREADS);
   unsigned long long *ctrl = (unsigned long long *)d_trim_ctrl;
   ushort4 *win = (ushort4 *)d_win;
-  if (ctx->max_adapter_len <= 32) {
-    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    trim_kernel<32><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
-                                                          keys_capacity_words, ctrl, smem);
+  if (ctx->fast_ok && ctx->trim_mode == 0) {
+    int ring = 4;
+    for (int a = 0; a < ctx->params.n_adapters; ++a) {
+      const int w = ctx->params.adapters[a].m + ctx->params.adapters[a].k + 2;
+      if (w > ring) ring = w;
+    }
+    const size_t total = (size_t)smem + (size_t)ctx->params.n_adapters * 1024 + 2ull * ring * TRIM_THREADS * 4;
+    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    trim_kernel<32, true><<<grid, TRIM_THREADS, total, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
+                                                                 keys_capacity_words, ctrl, smem, (uint32_t)ring);
+  } else if (ctx->max_adapter_len <= 32) {
+    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    trim_kernel<32, false><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
+                                                                 keys_capacity_words, ctrl, smem, 0u);
   } else {
-    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    trim_kernel<64><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
-                                                          keys_capacity_words, ctrl, smem);
+    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    trim_kernel<64, false><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
+                                                                 keys_capacity_words, ctrl, smem, 0u);
   }
   MIRGE_LAUNCH_CHECK(ctx, "trim_kernel");
+  return MIRGE_OK;
+}
+
+extern "C" int mirge_trim_mode(mirge_ctx *ctx, int mode) {
+  if (!ctx || mode < 0 || mode > 1) return MIRGE_ERR_ARG;
+  ctx->trim_mode = mode;
   return MIRGE_OK;
 }

@@ -240,6 +240,12 @@ class DigestEngine:
         dev.set_trim_config(cfg)
         self.cfg = cfg
         self.E = dev.slots
+        self.trim_mode = 0  # 0 = automatic kernel choice, 1 = always the generic full-DP kernel
+        dev.check(dev.lib.mirge_trim_mode(dev.ctx, 0))
+
+    def set_trim_mode(self, mode: int):
+        self.dev.check(self.dev.lib.mirge_trim_mode(self.dev.ctx, int(mode)))
+        self.trim_mode = int(mode)
 
     def trim_batch(self, buf: torch.Tensor, nbytes: int, is_final: bool, keep: bool = True) -> BatchResult:
         """Run the tokeniser and the trim kernel on buf[:nbytes] (uint8, device).  Returns the device
@@ -266,15 +272,27 @@ class DigestEngine:
         win = d.empty(n * E * 4, torch.int16)
         key_off = d.empty(n * E, torch.int32)
         cap = E * (2 * n + used // 24) + 4096
-        for attempt in range(2):
+        mode = self.trim_mode
+        for attempt in range(4):
             keys = d.empty(cap, torch.int32)
             ctrl = d.zeros(8, torch.int64)
-            with d.timed("trim"):
-                d.check(lib.mirge_trim(d.ctx, _ptr(buf), used, _ptr(line_start), n, _ptr(win), _ptr(key_off),
-                                       _ptr(keys), cap, _ptr(ctrl), st))
+            if mode != self.trim_mode:
+                d.check(lib.mirge_trim_mode(d.ctx, mode))
+            try:
+                with d.timed("trim"):
+                    d.check(lib.mirge_trim(d.ctx, _ptr(buf), used, _ptr(line_start), n, _ptr(win), _ptr(key_off),
+                                           _ptr(keys), cap, _ptr(ctrl), st))
+            finally:
+                if mode != self.trim_mode:
+                    d.check(lib.mirge_trim_mode(d.ctx, self.trim_mode))
             d.launches += 1
             c = ctrl.cpu().numpy().view(np.uint64)
             flags = int(c[2])
+            if flags & 8 and mode == 0:
+                # a record group did not fit the bit-parallel kernel's shared-memory staging:
+                # repeat the batch with the generic kernel (same results, slower)
+                mode = 1
+                continue
             if flags & 1:
                 rec = int(np.uint64(~c[3]))
                 raise FastqFormatError("FASTQ format error in record %d of the batch (header must start with '@', "
@@ -282,7 +300,7 @@ class DigestEngine:
             if flags & 4:
                 raise MirgeError("read longer than %d bases is not supported" % abi.MAX_READ_LEN)
             if flags & 2:
-                if attempt == 1:
+                if attempt >= 2:
                     raise CapacityError("trim: key buffer overflow")
                 cap = E * (n + used // 2 + used // 32 + 64) + 4096  # worst case: every base an exception
                 continue

@@ -39,8 +39,10 @@ def gpu_windows(eng, br):
     return win, kept
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("name", sorted(CONFIGS))
-def test_trim_and_collapse_match_oracle(dev, name):
+def test_trim_and_collapse_match_oracle(dev, name, mode):
+    """mode 0: automatic kernel choice (bit-parallel kernel where it applies); mode 1: generic full DP."""
     from mirge_b200 import device as D
 
     cfg = CONFIGS[name]
@@ -48,6 +50,7 @@ def test_trim_and_collapse_match_oracle(dev, name):
                         **CONFIG_DATA.get(name, {}))
     fq = np.frombuffer(data, dtype=np.uint8)
     eng = D.DigestEngine(dev, cfg)
+    eng.set_trim_mode(mode)
     n, win_o, kept_o = coracle.trim(fq, dev.trim_params)
     buf = to_dev(dev, data)
     br = eng.trim_batch(buf, buf.numel(), True)
@@ -149,3 +152,50 @@ def test_hot_key_contention(dev):
     _, tab = coracle.digest_collapse(np.frombuffer(data, dtype=np.uint8), dev.trim_params, nthreads=4)
     assert got == tab.to_dict()
     assert got["TGAGGTAGTAGGTTGTATAGTT"] >= 200000
+
+
+@pytest.mark.parametrize("cfg_id", [1, 2, 3])
+def test_synthetic_workloads_match_oracle(dev, cfg_id):
+    """The benchmark's own read model at 300k reads: windows and table bit-exact."""
+    from mirge_b200 import device as D
+    from mirge_b200 import synth
+
+    libs = synth.make_libraries(scale=0.1, mrna_count=200)
+    gen = synth.ReadGenerator(libs, synth.CONFIGS[cfg_id], dev.tdev)
+    buf = gen.fastq(300_000)
+    cfg = synth.trim_config_for(cfg_id)
+    eng = D.DigestEngine(dev, cfg)
+    fq = buf.cpu().numpy()
+    n, win_o, kept_o = coracle.trim(fq, dev.trim_params, nthreads=8)
+    br = eng.trim_batch(buf, buf.numel(), True)
+    win_g, kept_g = gpu_windows(eng, br)
+    assert br.n_records == n == 300_000
+    assert np.array_equal(kept_g, kept_o)
+    bad = np.argwhere((win_g != win_o).any(axis=2))
+    assert bad.size == 0, "first differing (record, slot): %s gpu=%s oracle=%s" % (
+        bad[0], win_g[tuple(bad[0])], win_o[tuple(bad[0])])
+    table = D.CollapseTable(dev, min_keys=1 << 12)
+    eng.collapse_batch(table, br)
+    _, tab = coracle.digest_collapse(fq, dev.trim_params, nthreads=8)
+    assert table_dict(table) == tab.to_dict()
+
+
+def test_long_records_fall_back_to_generic_kernel(dev):
+    """Records too large for the bit-parallel kernel's staging trigger the generic kernel (same results)."""
+    from mirge_b200 import device as D
+
+    cfg = CONFIGS["default"]
+    eng = D.DigestEngine(dev, cfg)
+    rng = np.random.default_rng(4)
+    recs = []
+    for i in range(300):
+        L = int(rng.integers(300, 500))
+        s = "".join(rng.choice(list("ACGT"), L))
+        if i % 3 == 0:
+            s = s[:100] + ILL + s[100 + len(ILL):]
+        recs.append("@%s\n%s\n+\n%s\n" % ("h" * 700, s, "I" * L))
+    data = "".join(recs).encode()
+    table = D.CollapseTable(dev, min_keys=1 << 10)
+    assert eng.digest_device(to_dev(dev, data), table) == 300
+    _, tab = coracle.digest_collapse(np.frombuffer(data, dtype=np.uint8), dev.trim_params)
+    assert table_dict(table) == tab.to_dict()
