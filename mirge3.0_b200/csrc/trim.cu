@@ -228,6 +228,7 @@ struct FastCtx {
   const uint32_t *s_eq;  // [n_adapters][256]: bit i-1 set <=> adapter row i matches this read byte
   uint32_t *ring_vp;     // this thread's column slots, stride TRIM_THREADS words
   uint32_t *ring_vn;
+  int depth;             // columns the buffer holds
 };
 
 __device__ __forceinline__ int cell_cost(uint32_t vp, uint32_t vn, int r) {
@@ -263,9 +264,18 @@ __device__ __noinline__ void traceback(const uint32_t *eqt, const uint8_t *read,
   matches = i - nonmatch;
 }
 
+// candidate (row i, cost c, scan index idx) can still beat the best so far: its matches are <= i
+#define MAY_WIN(i, c, idx) (!have || (i) > b_m || ((i) == b_m && ((c) < b_c || ((c) == b_c && (idx) < b_idx))))
+#define TAKE_IF_BETTER(mt, c, org, idx)                                                      \
+  if (!have || (mt) > b_m || ((mt) == b_m && ((c) < b_c || ((c) == b_c && (idx) < b_idx)))) { \
+    have = true; b_m = (mt); b_c = (c); b_o = (org); b_idx = (idx);                          \
+  }
+
 __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, const int n, const FastCtx &fc, Match &out) {
+  const unsigned lanes = __activemask();  // lanes searching together; re-converged after the divergent loops
   const DevAdapter &ad = c_p.ad[a];
-  const int m = ad.m, k = ad.k, W = m + k + 2;
+  const int m = ad.m;
+  const int W = fc.depth;  // >= m + k + 3 columns
   const uint32_t *eqt = fc.s_eq + a * 256;
   const uint32_t top = 1u << (m - 1);
   const int acc_m = ad.acc[m];
@@ -276,8 +286,13 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
   bool have = false;
   int b_m = 0, b_c = 0, b_o = 0, b_idx = 0;
   bool stopped = false;
+  // A row-m candidate waits one column: the next column may prove it dominated (rule 2 below).
+  bool pend = false, pend_ins = false;
+  int pend_c = 0;
   for (int j = 1; j <= n; ++j) {
     const uint32_t eq = eqt[read[j - 1]];
+    const int score_prev = score;
+    const int slot_prev = slot;
     const uint32_t xv = eq | vn;
     const uint32_t xh = (((eq & vp) + vp) ^ vp) | eq;
     uint32_t hp = vn | ~(xh | vp);
@@ -291,34 +306,70 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
     slot = (slot + 1 == W) ? 0 : slot + 1;
     fc.ring_vp[slot * TRIM_THREADS] = vp;
     fc.ring_vn[slot * TRIM_THREADS] = vn;
+    if (pend) {
+      // Rule 2: the candidate (m, j-1) was entered by an insertion from (m-1, j-1) and cell (m, j) is a
+      // character match from that same cell: (m, j) has one more match and one error less, is itself a
+      // candidate (row m of column j, or of the last column) and therefore beats (m, j-1).
+      const bool dominated = pend_ins && (eq & top);
+      if (!dominated && MAY_WIN(m, pend_c, j - 1)) {
+        int mt, org;
+        traceback(eqt, read, fc, W, m, j - 1, pend_c, slot_prev, mt, org);
+        TAKE_IF_BETTER(mt, pend_c, org, j - 1)
+      }
+      pend = false;
+    }
     if (score <= acc_m && j < n) {  // row-m candidate (column n is handled with the last column)
       if (score == 0) {              // exact full adapter: cutadapt stops here
         have = true; b_m = m; b_c = 0; b_o = j - m; b_idx = j;
         stopped = true;
         break;
       }
-      if (!have || m > b_m || (m == b_m && score < b_c)) {
-        int mt, org;
-        traceback(eqt, read, fc, W, m, j, score, slot, mt, org);
-        if (!have || mt > b_m || (mt == b_m && score < b_c)) { have = true; b_m = mt; b_c = score; b_o = org; b_idx = j; }
+      // first traceback step of cell (m, j) from the two cost columns at hand
+      bool is_del = false, is_ins = false;
+      if (!(eq & top)) {
+        const uint32_t pvp = fc.ring_vp[slot_prev * TRIM_THREADS], pvn = fc.ring_vn[slot_prev * TRIM_THREADS];
+        const int dm1_prev = score_prev - (int)((pvp >> (m - 1)) & 1u) + (int)((pvn >> (m - 1)) & 1u);  // D[m-1][j-1]
+        const int dm1_cur = score - (int)((vp >> (m - 1)) & 1u) + (int)((vn >> (m - 1)) & 1u);          // D[m-1][j]
+        const int cd = dm1_prev + 1, cdel = score_prev + 1, cins = dm1_cur + 1;
+        if (!(cd <= cdel && cd <= cins)) {
+          if (cins <= cdel) is_ins = true;
+          else is_del = true;
+        }
       }
+      // Rule 1: entered by a deletion from (m, j-1): same matches and origin as that cell, one error
+      // more; (m, j-1) is an accepted earlier candidate, so (m, j) can never win.
+      if (!is_del) { pend = true; pend_ins = is_ins; pend_c = score; }
     }
   }
+  __syncwarp(lanes);
+  const unsigned scan_lanes = __ballot_sync(lanes, !stopped);
   if (!stopped) {
+    // last column: rows with cost 0 are pure diagonals; the others wait in rowmask for a traceback,
+    // executed in a loop all lanes of the warp run together (descending rows: the first traceback
+    // usually prunes the rest)
+    uint32_t rowmask = 0;
     int c = 0;
     for (int i = 1; i <= m; ++i) {
       c += (int)((vp >> (i - 1)) & 1u) - (int)((vn >> (i - 1)) & 1u);  // D[i][n]
       if (c > ad.acc[i]) continue;
-      const int idx = (i == m) ? n : n + 1 + i;  // row m of column n precedes the last-column scan
       if (c == 0) {
-        if (!have || i > b_m || (i == b_m && (0 < b_c || (b_c == 0 && idx < b_idx)))) { have = true; b_m = i; b_c = 0; b_o = n - i; b_idx = idx; }
-        continue;
+        const int idx = (i == m) ? n : n + 1 + i;  // row m of column n precedes the last-column scan
+        TAKE_IF_BETTER(i, 0, n - i, idx)
+      } else {
+        rowmask |= 1u << (i - 1);
       }
-      const bool may_win = !have || i > b_m || (i == b_m && (c < b_c || (c == b_c && idx < b_idx)));
-      if (!may_win) continue;
-      int mt, org;
-      traceback(eqt, read, fc, W, i, n, c, slot, mt, org);
-      if (!have || mt > b_m || (mt == b_m && (c < b_c || (c == b_c && idx < b_idx)))) { have = true; b_m = mt; b_c = c; b_o = org; b_idx = idx; }
+    }
+    __syncwarp(scan_lanes);
+    while (rowmask) {
+      const int i = 32 - __clz(rowmask);
+      rowmask &= ~(1u << (i - 1));
+      const int ci = cell_cost(vp, vn, i);
+      const int idx = (i == m) ? n : n + 1 + i;
+      if (MAY_WIN(i, ci, idx)) {
+        int mt, org;
+        traceback(eqt, read, fc, W, i, n, ci, slot, mt, org);
+        TAKE_IF_BETTER(mt, ci, org, idx)
+      }
     }
   }
   if (!have) return false;
@@ -412,7 +463,7 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
   uint8_t *sbuf = (uint8_t *)smem4;
   const int tid = threadIdx.x;
   FastCtx fc;
-  fc.s_eq = nullptr; fc.ring_vp = nullptr; fc.ring_vn = nullptr;
+  fc.s_eq = nullptr; fc.ring_vp = nullptr; fc.ring_vn = nullptr; fc.depth = 0;
   if (FAST) {
     // smem: [staging smem_bytes][eq tables n_adapters * 256 words][ring vp W * T words][ring vn W * T words]
     uint32_t *eq = (uint32_t *)(sbuf + smem_bytes);
@@ -423,6 +474,7 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
     fc.s_eq = eq;
     fc.ring_vp = eq + c_p.n_adapters * 256 + tid;
     fc.ring_vn = fc.ring_vp + ring_depth * TRIM_THREADS;
+    fc.depth = (int)ring_depth;
   }
   const uint64_t r0 = (uint64_t)blockIdx.x * TRIM_THREADS;
   const uint64_t r = r0 + tid;
@@ -466,6 +518,9 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
     if (sl > 0 && B[ls.y + sl - 1] == '\r') --sl;
     if (ql > 0 && B[ls.w + ql - 1] == '\r') --ql;
     const bool bad = B[ls.x] != '@' || B[ls.z] != '+' || sl != ql || sl > MIRGE_MAX_READ_LEN;
+    // lanes that run the modifier pipeline together; used to re-converge them after every modifier,
+    // whose data-dependent loops (quality scans, adapter search) otherwise leave the warp split
+    const unsigned good_lanes = __ballot_sync(__activemask(), !bad) ;
     if (bad) {
       atomicOr(ctrl + 2, (sl > MIRGE_MAX_READ_LEN && sl == ql) ? 4ull : 1ull);
       atomicMax(ctrl + 3, ~(unsigned long long)r);
@@ -474,7 +529,10 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
       const uint8_t *qual = B + ls.w;
       int start = 0, stop = sl;
       if (c_p.umi_mode == MIRGE_UMI_QIAGEN) {
-        for (int mi = 0; mi < c_p.n_mods; ++mi) apply_mod<MAXM, FAST>(mi, seq, qual, start, stop, fc);
+        for (int mi = 0; mi < c_p.n_mods; ++mi) {
+          apply_mod<MAXM, FAST>(mi, seq, qual, start, stop, fc);
+          __syncwarp(good_lanes);
+        }
         const int tl = stop - start, U = c_p.umi3;
         int us = 0, ue = 0;
         if (tl > 0) {
@@ -493,6 +551,7 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
         for (int mi = 0; mi < MIRGE_MAX_MODS; ++mi) {
           if (mi < c_p.n_mods) {
             apply_mod<MAXM, FAST>(mi, seq, qual, start, stop, fc);
+            __syncwarp(good_lanes);
             if (E != 1 || mi == c_p.n_mods - 1) {
               const int slot = (E == 1) ? 0 : mi;
               int ln = stop - start;
@@ -664,7 +723,7 @@ extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbyte
   if (ctx->fast_ok && ctx->trim_mode == 0) {
     int ring = 4;
     for (int a = 0; a < ctx->params.n_adapters; ++a) {
-      const int w = ctx->params.adapters[a].m + ctx->params.adapters[a].k + 2;
+      const int w = ctx->params.adapters[a].m + ctx->params.adapters[a].k + 3;
       if (w > ring) ring = w;
     }
     const size_t total = (size_t)smem + (size_t)ctx->params.n_adapters * 1024 + 2ull * ring * TRIM_THREADS * 4;
