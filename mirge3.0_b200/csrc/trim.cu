@@ -22,6 +22,7 @@ struct DevAdapter {
   int n_counts[MIRGE_MAX_ADAPTER_LEN + 1];
   int max_err[MIRGE_MAX_ADAPTER_LEN + 1];
   int acc[MIRGE_MAX_ADAPTER_LEN + 1];  // 3' adapters: max errors of a candidate ending in adapter row i, -1 = never
+  uint64_t a2;                         // 2-bit text of the adapter (row t at bits 2(t-1)); plain ACGT adapters <= 32 nt
 };
 struct DevParams {
   int n_mods, kind[MIRGE_MAX_MODS], a[MIRGE_MAX_MODS], b[MIRGE_MAX_MODS], c[MIRGE_MAX_MODS];
@@ -85,7 +86,13 @@ extern "C" int mirge_set_trim_params(mirge_ctx *ctx, const mirge_trim_params *p)
       const int eff = s->wildcard_ref ? i - s->n_counts[i] : i;
       o->acc[i] = (i >= s->min_overlap && i >= 1 && eff >= 0) ? s->max_err[eff] : -1;
     }
-    if (s->where != 0 || s->indel_cost != 1 || s->m > 32 || s->min_overlap < 1) fast_ok = 0;
+    o->a2 = 0;
+    if (!s->wildcard_ref && s->m <= 32)
+      for (int i = 0; i < s->m; ++i) {
+        const uint64_t code = s->ascii[i] == 'A' ? 0 : s->ascii[i] == 'C' ? 1 : s->ascii[i] == 'G' ? 2 : 3;
+        o->a2 |= code << (2 * i);
+      }
+    if (s->where != 0 || s->indel_cost != 1 || s->m > 32 || s->min_overlap < 1 || s->m + 2 * s->k + 3 > 48) fast_ok = 0;
     if (s->m > maxm) maxm = s->m;
   }
   MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -215,20 +222,33 @@ __device__ __noinline__ bool locate(const int a, const uint8_t *read, const int 
 // Same result as locate() for 3' adapters with unit indel cost and m <= 32, at ~15 instructions per
 // read base instead of ~15 per DP cell:
 //   1. Myers/Hyyro bit-vector recurrence gives the exact DP cost column (vertical deltas VP/VN) for
-//      every read position; the cost of adapter row m is tracked incrementally.
+//      every read position; the cost of adapter row m is tracked incrementally.  Nothing is stored.
 //   2. cutadapt's candidates are the row-m cell of every column and all rows of the last column; their
 //      costs come from (1).  A candidate's (origin, matches) are those of the path cutadapt's
-//      tie-breaking (mismatch, then insertion, then deletion) would propagate into that cell; that path
-//      is recovered by a traceback that needs only DP costs of neighbouring cells, read from a ring of
-//      the last m + k + 2 cost columns kept in shared memory (a path with <= k errors into row i spans
-//      at most i + k columns).  cost == 0 cells need no traceback (pure diagonal).
-//   3. The winner is the maximum of (matches, -cost, -scan order) as in Aligner.locate; candidates
-//      that cannot win (row index <= best matches) are skipped without a traceback.
+//      tie-breaking (mismatch, then insertion, then deletion) propagates into that cell; the path is
+//      recovered by a traceback that needs only DP *costs* of neighbouring cells.  Those are recomputed
+//      on demand for the last m + 2k + 2 columns before the candidate with a fresh-start Myers pass into
+//      a thread-local buffer: a path with <= k errors into row i spans <= i + k columns, and every
+//      neighbour whose cost can tie has an optimal path starting inside that window, so the costs the
+//      rule compares are exact (larger values only lose).  cost == 0 cells are pure diagonals.
+//   3. The winner is the maximum of (matches, -cost, -scan order) as in Aligner.locate, so candidates
+//      may be evaluated in any order.  Cheap exact pruning keeps tracebacks rare: a row-m candidate
+//      entered by a deletion is dominated by its left neighbour; one entered by an insertion is dominated
+//      when the next column's cell is a character match; a candidate whose first step is not a match has
+//      at most row-1 matches; candidates are tried best-first and skipped when they cannot win.
+//   All tracebacks run after the column loop, so the lanes of a warp execute them together.
+#define RB 48  // recompute window capacity in columns (m + 2k + 3 <= RB is checked on the host)
+
 struct FastCtx {
   const uint32_t *s_eq;  // [n_adapters][256]: bit i-1 set <=> adapter row i matches this read byte
-  uint32_t *ring_vp;     // this thread's column slots, stride TRIM_THREADS words
-  uint32_t *ring_vn;
-  int depth;             // columns the buffer holds
+  const uint32_t *ps;    // this thread's 2-bit packed read (16 bases per word), stride TRIM_THREADS words
+  bool jump_ok;          // ps is valid and the read is pure "ACGT": match runs can be skipped with bit tricks
+  int rbase;             // offset of the window being searched inside the read
+};
+
+struct ColBuf {
+  uint32_t vp[RB], vn[RB];
+  int j0;  // entry t holds column j0 + t
 };
 
 __device__ __forceinline__ int cell_cost(uint32_t vp, uint32_t vn, int r) {
@@ -236,9 +256,52 @@ __device__ __forceinline__ int cell_cost(uint32_t vp, uint32_t vn, int r) {
   return __popc(vp & mask) - __popc(vn & mask);
 }
 
-// (matches, origin) cutadapt's DP holds in cell (i, j) whose cost is c > 0; slot_j = ring slot of column j
-__device__ __noinline__ void traceback(const uint32_t *eqt, const uint8_t *read, const FastCtx &fc, int W, int i, int j, int c,
-                                       int slot_j, int &matches, int &origin) {
+#define MYERS_STEP(eq, vp, vn, hp_out, hn_out)                    \
+  {                                                               \
+    const uint32_t xv_ = (eq) | (vn);                             \
+    const uint32_t xh_ = ((((eq) & (vp)) + (vp)) ^ (vp)) | (eq);  \
+    uint32_t hp_ = (vn) | ~(xh_ | (vp));                          \
+    uint32_t hn_ = (vp) & xh_;                                    \
+    hp_out = hp_;                                                 \
+    hn_out = hn_;                                                 \
+    hp_ <<= 1;                                                    \
+    hn_ <<= 1;                                                    \
+    (vp) = hn_ | ~(xv_ | hp_);                                    \
+    (vn) = hp_ & xv_;                                             \
+  }
+
+// cost columns jc - span .. jc recomputed with a fresh start (exact where it matters, see above)
+__device__ __noinline__ void recompute(const uint32_t *eqt, const uint8_t *read, int jc, int span, ColBuf &cb) {
+  const int j0 = max(0, jc - span);
+  uint32_t vp = 0xFFFFFFFFu, vn = 0u;
+  cb.j0 = j0;
+  cb.vp[0] = vp;
+  cb.vn[0] = vn;
+  int t = 1;
+  for (int j = j0 + 1; j <= jc; ++j, ++t) {
+    const uint32_t eq = eqt[read[j - 1]];
+    uint32_t hp, hn;
+    MYERS_STEP(eq, vp, vn, hp, hn)
+    cb.vp[t] = vp;
+    cb.vn[t] = vn;
+  }
+}
+
+// 64 bits = 32 bases of the packed read starting at base `a0` (zero beyond the packed words)
+__device__ __forceinline__ uint64_t read_window(const uint32_t *ps, int a0) {
+  const int wi = a0 >> 4, sh = 2 * (a0 & 15);
+  const uint32_t w0 = ps[wi * TRIM_THREADS], w1 = ps[(wi + 1) * TRIM_THREADS], w2 = ps[(wi + 2) * TRIM_THREADS];
+  const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// (matches, origin) cutadapt's DP holds in cell (i, j) whose cost is c > 0, from the cost columns in cb.
+// jump: adapter without wildcards and a pure-ACGT packed read -- the run of matches up a diagonal is skipped
+// with one XOR + count-leading-zeros instead of one step per cell.
+__device__ __noinline__ void traceback(const int a, const uint32_t *eqt, const uint8_t *read, const FastCtx &fc, const ColBuf &cb,
+                                          int i, int j, int c, int &matches, int &origin) {
+  const bool jump = fc.jump_ok && !c_p.ad[a].wildcard_ref;
+  const uint64_t a2 = c_p.ad[a].a2;
   int r = i, col = j, cost = c, nonmatch = 0;
   while (r > 0 && cost > 0) {
     if (col == 0) {  // initial column: cost r, origin 0, no further matches
@@ -246,15 +309,26 @@ __device__ __noinline__ void traceback(const uint32_t *eqt, const uint8_t *read,
       r = 0;
       break;
     }
-    if ((eqt[read[col - 1]] >> (r - 1)) & 1u) {  // equal characters: diagonal, cost unchanged
+    const int delta = col - r;
+    if (jump && delta >= 0) {
+      // rows t = 1..r of this diagonal face read bases delta + t - 1 (all in columns >= 1)
+      uint64_t x = a2 ^ read_window(fc.ps, fc.rbase + delta);
+      x = (x | (x >> 1)) & 0x5555555555555555ull;
+      if (r < 32) x &= (1ull << (2 * r)) - 1ull;
+      if (x == 0) {  // cannot happen while cost > 0 (an all-match diagonal has cost 0); kept for safety
+        col -= r;
+        r = 0;
+        break;
+      }
+      const int t = (64 - __clzll((long long)x) + 1) >> 1;  // highest mismatching row <= r
+      col -= r - t;
+      r = t;
+    } else if ((eqt[read[col - 1]] >> (r - 1)) & 1u) {  // equal characters: diagonal, cost unchanged
       --r; --col;
       continue;
     }
-    int s0 = slot_j - (j - col);
-    if (s0 < 0) s0 += W;
-    int s1 = s0 == 0 ? W - 1 : s0 - 1;
-    const uint32_t vp0 = fc.ring_vp[s0 * TRIM_THREADS], vn0 = fc.ring_vn[s0 * TRIM_THREADS];
-    const uint32_t vp1 = fc.ring_vp[s1 * TRIM_THREADS], vn1 = fc.ring_vn[s1 * TRIM_THREADS];
+    const int t0 = col - cb.j0;  // >= 1 by the window bound
+    const uint32_t vp0 = cb.vp[t0], vn0 = cb.vn[t0], vp1 = cb.vp[t0 - 1], vn1 = cb.vn[t0 - 1];
     const int cd = cell_cost(vp1, vn1, r - 1) + 1, cdel = cell_cost(vp1, vn1, r) + 1, cins = cell_cost(vp0, vn0, r - 1) + 1;
     if (cd <= cdel && cd <= cins) { --r; --col; ++nonmatch; cost = cd - 1; }
     else if (cins <= cdel) { --r; ++nonmatch; cost = cins - 1; }
@@ -264,57 +338,79 @@ __device__ __noinline__ void traceback(const uint32_t *eqt, const uint8_t *read,
   matches = i - nonmatch;
 }
 
-// candidate (row i, cost c, scan index idx) can still beat the best so far: its matches are <= i
-#define MAY_WIN(i, c, idx) (!have || (i) > b_m || ((i) == b_m && ((c) < b_c || ((c) == b_c && (idx) < b_idx))))
+// candidate with at most `u` matches, cost c, scan index idx can still beat the best so far
+#define MAY_WIN(u, c, idx) (!have || (u) > b_m || ((u) == b_m && ((c) < b_c || ((c) == b_c && (idx) < b_idx))))
 #define TAKE_IF_BETTER(mt, c, org, idx)                                                      \
   if (!have || (mt) > b_m || ((mt) == b_m && ((c) < b_c || ((c) == b_c && (idx) < b_idx)))) { \
     have = true; b_m = (mt); b_c = (c); b_o = (org); b_idx = (idx);                          \
   }
+// queued row-m candidate: column | cost << 16 | (first step is a match) << 24
+#define Q_COL(v) ((int)((v)&0xFFFFu))
+#define Q_COST(v) ((int)(((v) >> 16) & 0xFFu))
+#define Q_UB(v, m) ((((v) >> 24) & 1u) ? (m) : (m)-1)
 
 __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, const int n, const FastCtx &fc, Match &out) {
   const unsigned lanes = __activemask();  // lanes searching together; re-converged after the divergent loops
   const DevAdapter &ad = c_p.ad[a];
   const int m = ad.m;
-  const int W = fc.depth;  // >= m + k + 3 columns
+  const int span = m + 2 * ad.k + 2;
   const uint32_t *eqt = fc.s_eq + a * 256;
   const uint32_t top = 1u << (m - 1);
   const int acc_m = ad.acc[m];
-  uint32_t vp = 0xFFFFFFFFu, vn = 0u;
-  int score = m, slot = 0;
-  fc.ring_vp[0] = vp;
-  fc.ring_vn[0] = vn;
+  uint32_t vp = 0xFFFFFFFFu, vn = 0u, pvp = vp, pvn = vn, eq = 0;
+  int score = m;
   bool have = false;
   int b_m = 0, b_c = 0, b_o = 0, b_idx = 0;
   bool stopped = false;
-  // A row-m candidate waits one column: the next column may prove it dominated (rule 2 below).
+  ColBuf cb;
+  // row-m candidates wait here until the column loop is over (0 = empty slot)
+  uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+  // a new candidate waits one column: the next column may prove it dominated
   bool pend = false, pend_ins = false;
-  int pend_c = 0;
+  uint32_t pend_v = 0;
+
+// trace the queued candidates best-first (lowest cost, then leftmost), skipping those that cannot win
+#define FLUSH_QUEUE()                                                                            \
+  for (int it_ = 0; it_ < 4; ++it_) {                                                            \
+    uint32_t v_ = 0;                                                                             \
+    int which_ = -1;                                                                             \
+    if (q0 && (!v_ || (q0 >> 16 & 0xFF) < (v_ >> 16 & 0xFF))) { v_ = q0; which_ = 0; }           \
+    if (q1 && (!v_ || (q1 >> 16 & 0xFF) < (v_ >> 16 & 0xFF))) { v_ = q1; which_ = 1; }           \
+    if (q2 && (!v_ || (q2 >> 16 & 0xFF) < (v_ >> 16 & 0xFF))) { v_ = q2; which_ = 2; }           \
+    if (q3 && (!v_ || (q3 >> 16 & 0xFF) < (v_ >> 16 & 0xFF))) { v_ = q3; which_ = 3; }           \
+    if (which_ < 0) break;                                                                       \
+    if (which_ == 0) q0 = 0; else if (which_ == 1) q1 = 0; else if (which_ == 2) q2 = 0; else q3 = 0; \
+    const int jc_ = Q_COL(v_), cc_ = Q_COST(v_);                                                 \
+    if (MAY_WIN(Q_UB(v_, m), cc_, jc_)) {                                                        \
+      int mt_, org_;                                                                             \
+      recompute(eqt, read, jc_, span, cb);                                                       \
+      traceback(a, eqt, read, fc, cb, m, jc_, cc_, mt_, org_);                                   \
+      TAKE_IF_BETTER(mt_, cc_, org_, jc_)                                                        \
+    }                                                                                            \
+  }
+
   for (int j = 1; j <= n; ++j) {
-    const uint32_t eq = eqt[read[j - 1]];
+    eq = eqt[read[j - 1]];
     const int score_prev = score;
-    const int slot_prev = slot;
-    const uint32_t xv = eq | vn;
-    const uint32_t xh = (((eq & vp) + vp) ^ vp) | eq;
-    uint32_t hp = vn | ~(xh | vp);
-    uint32_t hn = vp & xh;
+    pvp = vp;
+    pvn = vn;
+    uint32_t hp, hn;
+    MYERS_STEP(eq, vp, vn, hp, hn)
     score += (hp & top) ? 1 : 0;
     score -= (hn & top) ? 1 : 0;
-    hp <<= 1;
-    hn <<= 1;
-    vp = hn | ~(xv | hp);
-    vn = hp & xv;
-    slot = (slot + 1 == W) ? 0 : slot + 1;
-    fc.ring_vp[slot * TRIM_THREADS] = vp;
-    fc.ring_vn[slot * TRIM_THREADS] = vn;
     if (pend) {
       // Rule 2: the candidate (m, j-1) was entered by an insertion from (m-1, j-1) and cell (m, j) is a
       // character match from that same cell: (m, j) has one more match and one error less, is itself a
       // candidate (row m of column j, or of the last column) and therefore beats (m, j-1).
-      const bool dominated = pend_ins && (eq & top);
-      if (!dominated && MAY_WIN(m, pend_c, j - 1)) {
-        int mt, org;
-        traceback(eqt, read, fc, W, m, j - 1, pend_c, slot_prev, mt, org);
-        TAKE_IF_BETTER(mt, pend_c, org, j - 1)
+      if (!(pend_ins && (eq & top))) {
+        if (!q0) q0 = pend_v;
+        else if (!q1) q1 = pend_v;
+        else if (!q2) q2 = pend_v;
+        else if (!q3) q3 = pend_v;
+        else {  // queue full (low-complexity read): resolve what is queued, then go on
+          FLUSH_QUEUE()
+          q0 = pend_v;
+        }
       }
       pend = false;
     }
@@ -325,9 +421,9 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
         break;
       }
       // first traceback step of cell (m, j) from the two cost columns at hand
-      bool is_del = false, is_ins = false;
+      bool is_del = false, is_ins = false, is_match = true;
       if (!(eq & top)) {
-        const uint32_t pvp = fc.ring_vp[slot_prev * TRIM_THREADS], pvn = fc.ring_vn[slot_prev * TRIM_THREADS];
+        is_match = false;
         const int dm1_prev = score_prev - (int)((pvp >> (m - 1)) & 1u) + (int)((pvn >> (m - 1)) & 1u);  // D[m-1][j-1]
         const int dm1_cur = score - (int)((vp >> (m - 1)) & 1u) + (int)((vn >> (m - 1)) & 1u);          // D[m-1][j]
         const int cd = dm1_prev + 1, cdel = score_prev + 1, cins = dm1_cur + 1;
@@ -338,36 +434,53 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
       }
       // Rule 1: entered by a deletion from (m, j-1): same matches and origin as that cell, one error
       // more; (m, j-1) is an accepted earlier candidate, so (m, j) can never win.
-      if (!is_del) { pend = true; pend_ins = is_ins; pend_c = score; }
+      if (!is_del) {
+        pend = true;
+        pend_ins = is_ins;
+        pend_v = (uint32_t)j | ((uint32_t)score << 16) | (is_match ? (1u << 24) : 0u);
+      }
     }
   }
   __syncwarp(lanes);
   const unsigned scan_lanes = __ballot_sync(lanes, !stopped);
   if (!stopped) {
-    // last column: rows with cost 0 are pure diagonals; the others wait in rowmask for a traceback,
-    // executed in a loop all lanes of the warp run together (descending rows: the first traceback
-    // usually prunes the rest)
-    uint32_t rowmask = 0;
-    int c = 0;
+    // last column: rows with cost 0 are pure diagonals; the others wait in rowmask / rowub
+    uint32_t rowmask = 0, rowub = 0;  // rowub bit: first step of that cell is a match (up to i matches), else i - 1
+    int c = 0, cprev = 0;             // D[i][n], D[i][n-1]
     for (int i = 1; i <= m; ++i) {
-      c += (int)((vp >> (i - 1)) & 1u) - (int)((vn >> (i - 1)) & 1u);  // D[i][n]
+      const int c_up = c, cprev_up = cprev;  // row i - 1
+      c += (int)((vp >> (i - 1)) & 1u) - (int)((vn >> (i - 1)) & 1u);
+      cprev += (int)((pvp >> (i - 1)) & 1u) - (int)((pvn >> (i - 1)) & 1u);
       if (c > ad.acc[i]) continue;
       if (c == 0) {
         const int idx = (i == m) ? n : n + 1 + i;  // row m of column n precedes the last-column scan
         TAKE_IF_BETTER(i, 0, n - i, idx)
       } else {
         rowmask |= 1u << (i - 1);
+        bool full = true;  // may reach i matches only if its first step is a match or a deletion
+        if (!((eq >> (i - 1)) & 1u) && n >= 1) {
+          const int cd = cprev_up + 1, cdel = cprev + 1, cins = c_up + 1;
+          if ((cd <= cdel && cd <= cins) || cins <= cdel) full = false;
+        }
+        if (full) rowub |= 1u << (i - 1);
       }
     }
     __syncwarp(scan_lanes);
-    while (rowmask) {
+    FLUSH_QUEUE()
+    bool have_cols = false;
+    while (rowmask) {  // descending rows: the first traceback usually prunes the rest
       const int i = 32 - __clz(rowmask);
       rowmask &= ~(1u << (i - 1));
       const int ci = cell_cost(vp, vn, i);
       const int idx = (i == m) ? n : n + 1 + i;
-      if (MAY_WIN(i, ci, idx)) {
+      const int ub = ((rowub >> (i - 1)) & 1u) ? i : i - 1;
+      if (MAY_WIN(ub, ci, idx)) {
+        if (!have_cols) {
+          recompute(eqt, read, n, span, cb);
+          have_cols = true;
+        }
         int mt, org;
-        traceback(eqt, read, fc, W, i, n, ci, slot, mt, org);
+        traceback(a, eqt, read, fc, cb, i, n, ci, mt, org);
         TAKE_IF_BETTER(mt, ci, org, idx)
       }
     }
@@ -382,7 +495,7 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
 
 // AdapterCutter._best_match: most matches, then fewer errors, first adapter wins ties.
 template <int MAXM, bool FAST>
-__device__ __forceinline__ int best_match(const uint8_t *read, int n, Match &best, const FastCtx &fc) {
+__device__ __noinline__ int best_match(const uint8_t *read, int n, Match &best, const FastCtx &fc) {
   int which = -1;
   for (int a = 0; a < c_p.n_adapters; ++a) {
     Match mt;
@@ -398,7 +511,7 @@ __device__ __forceinline__ int best_match(const uint8_t *read, int n, Match &bes
 }
 
 template <int MAXM, bool FAST>
-__device__ __forceinline__ void apply_mod(int mi, const uint8_t *seq, const uint8_t *qual, int &start, int &stop, const FastCtx &fc) {
+__device__ __forceinline__ void apply_mod(int mi, const uint8_t *seq, const uint8_t *qual, int &start, int &stop, FastCtx &fc) {
   const int len = stop - start;
   switch (c_p.kind[mi]) {
     case MIRGE_MOD_NEXTSEQ:
@@ -414,6 +527,7 @@ __device__ __forceinline__ void apply_mod(int mi, const uint8_t *seq, const uint
     case MIRGE_MOD_ADAPTER:
       for (int t = 0; t < c_p.times; ++t) {
         Match mt;
+        fc.rbase = start;
         const int a = best_match<MAXM, FAST>(seq + start, stop - start, mt, fc);
         if (a < 0) break;
         if (c_p.ad[a].where == 0) stop = start + mt.rstart;
@@ -463,18 +577,18 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
   uint8_t *sbuf = (uint8_t *)smem4;
   const int tid = threadIdx.x;
   FastCtx fc;
-  fc.s_eq = nullptr; fc.ring_vp = nullptr; fc.ring_vn = nullptr; fc.depth = 0;
+  fc.s_eq = nullptr; fc.ps = nullptr; fc.jump_ok = false; fc.rbase = 0;
+  uint32_t *ps_mine = nullptr;
   if (FAST) {
-    // smem: [staging smem_bytes][eq tables n_adapters * 256 words][ring vp W * T words][ring vn W * T words]
+    // smem: [staging smem_bytes][eq tables n_adapters * 256 words][packed reads (PACK_WORDS + 2) * T words]
     uint32_t *eq = (uint32_t *)(sbuf + smem_bytes);
     for (int e = tid; e < c_p.n_adapters * 256; e += TRIM_THREADS) {
       const uint32_t code = base_code_upper((uint32_t)(e & 255));
       eq[e] = code < 4u ? (uint32_t)c_p.ad[e >> 8].peq[code] : 0u;
     }
     fc.s_eq = eq;
-    fc.ring_vp = eq + c_p.n_adapters * 256 + tid;
-    fc.ring_vn = fc.ring_vp + ring_depth * TRIM_THREADS;
-    fc.depth = (int)ring_depth;
+    ps_mine = eq + c_p.n_adapters * 256 + tid;
+    fc.ps = ps_mine;
   }
   const uint64_t r0 = (uint64_t)blockIdx.x * TRIM_THREADS;
   const uint64_t r = r0 + tid;
@@ -528,6 +642,34 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
       seq = B + ls.y;
       const uint8_t *qual = B + ls.w;
       int start = 0, stop = sl;
+      if (FAST) {
+        // 2-bit text of the whole read once: registers (key emission) + shared memory (traceback jumps)
+        fast_emit = sl <= 16 * PACK_WORDS;
+        if (fast_emit) {
+          uint32_t anyexc = 0;
+#pragma unroll
+          for (int w = 0; w < PACK_WORDS; ++w) {
+            uint32_t word = 0;
+            if (16 * w < sl) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int p = 16 * w + q;
+                if (p < sl) {
+                  const uint32_t ch = seq[p];
+                  word |= (((ch >> 1) ^ (ch >> 2)) & 3u) << (2 * q);
+                  anyexc |= (ch != 'A') & (ch != 'C') & (ch != 'G') & (ch != 'T');
+                }
+              }
+            }
+            P[w] = word;
+            ps_mine[w * TRIM_THREADS] = word;
+          }
+          ps_mine[PACK_WORDS * TRIM_THREADS] = 0;
+          ps_mine[(PACK_WORDS + 1) * TRIM_THREADS] = 0;
+          if (anyexc) fast_emit = false;
+        }
+        fc.jump_ok = fast_emit;
+      }
       if (c_p.umi_mode == MIRGE_UMI_QIAGEN) {
         for (int mi = 0; mi < c_p.n_mods; ++mi) {
           apply_mod<MAXM, FAST>(mi, seq, qual, start, stop, fc);
@@ -563,38 +705,10 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
           }
         }
       }
-      // FAST: 2-bit text of read[p0 : p0 + 16 * PACK_WORDS) once, in registers
       if (FAST) {
-        p0 = -1;
-        int pe = 0;
 #pragma unroll
         for (int s = 0; s < MIRGE_MAX_MODS; ++s)
-          if (s < E && w_words[s]) {
-            if (p0 < 0 || w_start[s] < p0) p0 = w_start[s];
-            pe = max(pe, w_stop[s]);
-            if (w_ue[s] > w_us[s]) fast_emit = false;
-          }
-        if (p0 < 0 || pe - p0 > 16 * PACK_WORDS) fast_emit = false;
-        if (fast_emit) {
-          uint32_t anyexc = 0;
-#pragma unroll
-          for (int w = 0; w < PACK_WORDS; ++w) {
-            uint32_t word = 0;
-            if (p0 + 16 * w < pe) {
-#pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const int p = p0 + 16 * w + q;
-                if (p < pe) {
-                  const uint32_t ch = seq[p];
-                  word |= (((ch >> 1) ^ (ch >> 2)) & 3u) << (2 * q);
-                  anyexc |= (ch != 'A') & (ch != 'C') & (ch != 'G') & (ch != 'T');
-                }
-              }
-            }
-            P[w] = word;
-          }
-          if (anyexc) fast_emit = false;
-        }
+          if (s < E && w_words[s] && w_ue[s] > w_us[s]) fast_emit = false;  // concatenated (qiagen) keys: generic packing
       }
       // size of every kept key: header + payload + exceptions
 #pragma unroll
@@ -726,7 +840,7 @@ extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbyte
       const int w = ctx->params.adapters[a].m + ctx->params.adapters[a].k + 3;
       if (w > ring) ring = w;
     }
-    const size_t total = (size_t)smem + (size_t)ctx->params.n_adapters * 1024 + 2ull * ring * TRIM_THREADS * 4;
+    const size_t total = (size_t)smem + (size_t)ctx->params.n_adapters * 1024 + (size_t)(PACK_WORDS + 2) * TRIM_THREADS * 4;
     MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     trim_kernel<32, true><<<grid, TRIM_THREADS, total, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
                                                                  keys_capacity_words, ctrl, smem, (uint32_t)ring);
