@@ -511,7 +511,7 @@ __device__ __noinline__ int best_match(const uint8_t *read, int n, Match &best, 
 }
 
 template <int MAXM, bool FAST>
-__device__ __forceinline__ void apply_mod(int mi, const uint8_t *seq, const uint8_t *qual, int &start, int &stop, FastCtx &fc) {
+__device__ __noinline__ void apply_mod(int mi, const uint8_t *seq, const uint8_t *qual, int &start, int &stop, FastCtx &fc) {
   const int len = stop - start;
   switch (c_p.kind[mi]) {
     case MIRGE_MOD_NEXTSEQ:
@@ -572,8 +572,6 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
             ushort4 *__restrict__ win, uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys, uint64_t keys_cap,
             unsigned long long *__restrict__ ctrl, uint32_t smem_bytes, uint32_t ring_depth) {
   extern __shared__ uint4 smem4[];
-  __shared__ uint32_t s_scan[TRIM_THREADS / 32];
-  __shared__ unsigned long long s_base;
   uint8_t *sbuf = (uint8_t *)smem4;
   const int tid = threadIdx.x;
   FastCtx fc;
@@ -616,14 +614,13 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
   const uint8_t *B = staged ? (const uint8_t *)(sbuf - alo) : fq;  // B[absolute stream offset]
 
   const int E = c_p.slots;
+  // per-slot windows live in local memory (dynamic slot index keeps the code small)
   int w_start[MIRGE_MAX_MODS], w_stop[MIRGE_MAX_MODS], w_us[MIRGE_MAX_MODS], w_ue[MIRGE_MAX_MODS];
   uint32_t w_words[MIRGE_MAX_MODS];  // 0 = not kept
-#pragma unroll
-  for (int s = 0; s < MIRGE_MAX_MODS; ++s) { w_start[s] = w_stop[s] = w_us[s] = w_ue[s] = 0; w_words[s] = 0; }
+#pragma unroll 1
+  for (int s = 0; s < E; ++s) { w_start[s] = w_stop[s] = w_us[s] = w_ue[s] = 0; w_words[s] = 0; }
   const uint8_t *seq = nullptr;
   uint32_t my_words = 0, my_kept = 0;
-  uint32_t P[PACK_WORDS];
-  int p0 = 0;
   bool fast_emit = FAST;
   if (valid) {
     const uint4 ls = *(const uint4 *)(line_start + 4 * r);
@@ -634,7 +631,7 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
     const bool bad = B[ls.x] != '@' || B[ls.z] != '+' || sl != ql || sl > MIRGE_MAX_READ_LEN;
     // lanes that run the modifier pipeline together; used to re-converge them after every modifier,
     // whose data-dependent loops (quality scans, adapter search) otherwise leave the warp split
-    const unsigned good_lanes = __ballot_sync(__activemask(), !bad) ;
+    const unsigned good_lanes = __ballot_sync(__activemask(), !bad);
     if (bad) {
       atomicOr(ctrl + 2, (sl > MIRGE_MAX_READ_LEN && sl == ql) ? 4ull : 1ull);
       atomicMax(ctrl + 3, ~(unsigned long long)r);
@@ -643,34 +640,45 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
       const uint8_t *qual = B + ls.w;
       int start = 0, stop = sl;
       if (FAST) {
-        // 2-bit text of the whole read once: registers (key emission) + shared memory (traceback jumps)
+        // 2-bit text of the whole read once, four bytes per step (SIMD-in-register), into shared memory:
+        // used by the traceback jumps and by key emission
         fast_emit = sl <= 16 * PACK_WORDS;
         if (fast_emit) {
-          uint32_t anyexc = 0;
-#pragma unroll
-          for (int w = 0; w < PACK_WORDS; ++w) {
+          const uint32_t *ap = (const uint32_t *)((uintptr_t)seq & ~(uintptr_t)3);
+          const uint32_t bs = ((uint32_t)(uintptr_t)seq & 3u) * 8u;
+          const int nwords = (sl + 15) >> 4;
+          uint32_t anyexc = 0, prev = ap[0];
+          int k = 1;
+#pragma unroll 1
+          for (int w = 0; w < nwords; ++w) {
             uint32_t word = 0;
-            if (16 * w < sl) {
 #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                const int p = 16 * w + q;
-                if (p < sl) {
-                  const uint32_t ch = seq[p];
-                  word |= (((ch >> 1) ^ (ch >> 2)) & 3u) << (2 * q);
-                  anyexc |= (ch != 'A') & (ch != 'C') & (ch != 'G') & (ch != 'T');
-                }
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint32_t nx = ap[k++];
+              const uint32_t quad = __funnelshift_r(prev, nx, bs);
+              prev = nx;
+              const int nb = sl - (16 * w + 4 * q4);  // bytes of this quad that belong to the read
+              uint32_t ok = __vcmpeq4(quad, 0x41414141u) | __vcmpeq4(quad, 0x43434343u) | __vcmpeq4(quad, 0x47474747u) |
+                            __vcmpeq4(quad, 0x54545454u);
+              uint32_t codes = ((quad >> 1) ^ (quad >> 2)) & 0x03030303u;
+              if (nb < 4) {
+                const uint32_t tm = nb <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - nb)));
+                codes &= tm;
+                ok |= ~tm;
               }
+              anyexc |= ~ok;
+              word |= ((codes * 0x01041040u) >> 24) << (8 * q4);
             }
-            P[w] = word;
             ps_mine[w * TRIM_THREADS] = word;
           }
-          ps_mine[PACK_WORDS * TRIM_THREADS] = 0;
-          ps_mine[(PACK_WORDS + 1) * TRIM_THREADS] = 0;
+#pragma unroll 1
+          for (int w = nwords; w < PACK_WORDS + 2; ++w) ps_mine[w * TRIM_THREADS] = 0;
           if (anyexc) fast_emit = false;
         }
         fc.jump_ok = fast_emit;
       }
       if (c_p.umi_mode == MIRGE_UMI_QIAGEN) {
+#pragma unroll 1
         for (int mi = 0; mi < c_p.n_mods; ++mi) {
           apply_mod<MAXM, FAST>(mi, seq, qual, start, stop, fc);
           __syncwarp(good_lanes);
@@ -688,124 +696,98 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
         }
         w_start[0] = start; w_stop[0] = stop; w_us[0] = us; w_ue[0] = ue;
         w_words[0] = (tl >= c_p.min_len) ? 1u : 0u;
+        if (ue > us) fast_emit = false;  // concatenated key: generic packing
       } else {
-#pragma unroll
-        for (int mi = 0; mi < MIRGE_MAX_MODS; ++mi) {
-          if (mi < c_p.n_mods) {
-            apply_mod<MAXM, FAST>(mi, seq, qual, start, stop, fc);
-            __syncwarp(good_lanes);
-            if (E != 1 || mi == c_p.n_mods - 1) {
-              const int slot = (E == 1) ? 0 : mi;
-              int ln = stop - start;
-              if (c_p.umi_mode == MIRGE_UMI_FLANKS) ln = max(ln - c_p.umi5 - c_p.umi3, 0);
-              // slot is compile-time mi in HEAD mode; in release mode only slot 0 is used
-              if (slot == 0) { w_start[0] = start; w_stop[0] = stop; w_words[0] = ln >= c_p.min_len; }
-              else { w_start[mi] = start; w_stop[mi] = stop; w_words[mi] = ln >= c_p.min_len; }
-            }
+#pragma unroll 1
+        for (int mi = 0; mi < c_p.n_mods; ++mi) {
+          apply_mod<MAXM, FAST>(mi, seq, qual, start, stop, fc);
+          __syncwarp(good_lanes);
+          if (E != 1 || mi == c_p.n_mods - 1) {
+            const int slot = (E == 1) ? 0 : mi;
+            int ln = stop - start;
+            if (c_p.umi_mode == MIRGE_UMI_FLANKS) ln = max(ln - c_p.umi5 - c_p.umi3, 0);
+            w_start[slot] = start; w_stop[slot] = stop; w_words[slot] = ln >= c_p.min_len;
           }
         }
       }
-      if (FAST) {
-#pragma unroll
-        for (int s = 0; s < MIRGE_MAX_MODS; ++s)
-          if (s < E && w_words[s] && w_ue[s] > w_us[s]) fast_emit = false;  // concatenated (qiagen) keys: generic packing
-      }
       // size of every kept key: header + payload + exceptions
-#pragma unroll
-      for (int s = 0; s < MIRGE_MAX_MODS; ++s) {
+#pragma unroll 1
+      for (int s = 0; s < E; ++s) {
+        if (!w_words[s]) continue;
         if (FAST && fast_emit) {
-          if (s < E && w_words[s]) {
-            w_words[s] = 1u + ((uint32_t)(w_stop[s] - w_start[s] + 15) >> 4);
-            my_words += w_words[s];
-            ++my_kept;
-          }
-        } else if (s < E && w_words[s]) {
+          w_words[s] = 1u + ((uint32_t)(w_stop[s] - w_start[s] + 15) >> 4);
+        } else {
           const int l1 = w_stop[s] - w_start[s], len = l1 + (w_ue[s] - w_us[s]);
           uint32_t nexc = 0;
           for (int p = 0; p < len; ++p) nexc += base_code_exact(key_byte(seq, w_start[s], l1, w_us[s], p)) == 4u;
           w_words[s] = 1u + ((uint32_t)(len + 15) >> 4) + nexc;
-          my_words += w_words[s];
-          ++my_kept;
         }
+        my_words += w_words[s];
+        ++my_kept;
       }
     }
   }
-  // CTA-level allocation of key space: one atomic per CTA
-  const int lane = tid & 31, warp = tid >> 5;
+  // key space: one atomic per warp (warps finish independently, no CTA barrier)
+  const int lane = tid & 31;
   uint32_t inc = my_words;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
     if (lane >= d) inc += t;
   }
+  const uint32_t warp_total = __shfl_sync(0xffffffffu, inc, 31);
   const uint32_t kept_warp = __reduce_add_sync(0xffffffffu, my_kept);
-  if (lane == 31) s_scan[warp] = inc;
-  __syncthreads();
-  uint32_t warp_base = 0, cta_total = 0;
-#pragma unroll
-  for (int w = 0; w < TRIM_THREADS / 32; ++w) {
-    if (w < warp) warp_base += s_scan[w];
-    cta_total += s_scan[w];
+  unsigned long long warp_base = 0;
+  if (lane == 0) {
+    if (warp_total) warp_base = atomicAdd(ctrl + 0, (unsigned long long)warp_total);
+    if (kept_warp) atomicAdd(ctrl + 1, (unsigned long long)kept_warp);
   }
-  if (tid == 0) s_base = cta_total ? atomicAdd(ctrl + 0, (unsigned long long)cta_total) : 0ull;
-  if (lane == 0 && kept_warp) atomicAdd(ctrl + 1, (unsigned long long)kept_warp);
-  __syncthreads();
-  const unsigned long long cta_base = s_base;
-  const bool overflow = cta_base + cta_total > keys_cap || cta_base + cta_total > 0xFFFFFFF0ull;
-  if (overflow && tid == 0 && cta_total) atomicOr(ctrl + 2, 2ull);
+  warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+  const bool overflow = warp_base + warp_total > keys_cap || warp_base + warp_total > 0xFFFFFFF0ull;
+  if (overflow && lane == 0 && warp_total) atomicOr(ctrl + 2, 2ull);
   if (!valid) return;
-  uint32_t off = (uint32_t)cta_base + warp_base + inc - my_words;
-#pragma unroll
-  for (int s = 0; s < MIRGE_MAX_MODS; ++s) {
-    if (s < E) {
-      const uint64_t e = r * (uint64_t)E + s;
-      win[e] = make_ushort4((unsigned short)w_start[s], (unsigned short)w_stop[s], (unsigned short)w_us[s], (unsigned short)w_ue[s]);
-      if (w_words[s] && !overflow) {
-        key_off[e] = off;
-        const int l1 = w_stop[s] - w_start[s], len = l1 + (w_ue[s] - w_us[s]);
-        const uint32_t npay = (uint32_t)(len + 15) >> 4;
-        const uint32_t nexc = w_words[s] - 1u - npay;
-        uint32_t *k = keys + off;
-        if (FAST && fast_emit) {
-          // key = 2-bit text of read[w_start : w_stop), a slice of the register-resident words
-          k[0] = (uint32_t)len;
-          const int sh = w_start[s] - p0;  // bases to skip (0 in the common case)
-#pragma unroll
-          for (int w = 0; w < PACK_WORDS; ++w) {
-            if (16 * w < len) {
-              uint32_t v;
-              if (sh == 0) v = P[w];
-              else {
-                // dynamic base shift: select words by comparing indices (keeps P in registers)
-                const int wi = (sh >> 4) + w, bs = 2 * (sh & 15);
-                uint32_t lo = 0, hi = 0;
-#pragma unroll
-                for (int x = 0; x < PACK_WORDS; ++x) { if (x == wi) lo = P[x]; if (x == wi + 1) hi = P[x]; }
-                v = bs ? __funnelshift_r(lo, hi, bs) : lo;
-              }
-              const int rem = len - 16 * w;
-              if (rem < 16) v &= (1u << (2 * rem)) - 1u;
-              k[1 + w] = v;
-            }
-          }
-          off += w_words[s];
-          continue;
-        }
-        k[0] = (uint32_t)len | (nexc << 16);
-        uint32_t word = 0, xi = 0;
-        for (int p = 0; p < len; ++p) {
-          const uint32_t ch = key_byte(seq, w_start[s], l1, w_us[s], p);
-          const uint32_t code = base_code_exact(ch);
-          if (code == 4u) k[1 + npay + xi++] = ((uint32_t)p << 8) | ch;
-          else word |= code << (2 * (p & 15));
-          if ((p & 15) == 15) { k[1 + (p >> 4)] = word; word = 0; }
-        }
-        if (len & 15) k[1 + (len >> 4)] = word;
-        off += w_words[s];
-      } else {
-        key_off[e] = 0xFFFFFFFFu;
-      }
+  uint32_t off = (uint32_t)warp_base + inc - my_words;
+#pragma unroll 1
+  for (int s = 0; s < E; ++s) {
+    const uint64_t e = r * (uint64_t)E + s;
+    win[e] = make_ushort4((unsigned short)w_start[s], (unsigned short)w_stop[s], (unsigned short)w_us[s], (unsigned short)w_ue[s]);
+    if (!w_words[s] || overflow) {
+      key_off[e] = 0xFFFFFFFFu;
+      continue;
     }
+    key_off[e] = off;
+    const int l1 = w_stop[s] - w_start[s], len = l1 + (w_ue[s] - w_us[s]);
+    const uint32_t npay = (uint32_t)(len + 15) >> 4;
+    uint32_t *k = keys + off;
+    if (FAST && fast_emit) {
+      // key = 2-bit text of read[w_start : w_stop): a slice of the packed read in shared memory
+      k[0] = (uint32_t)len;
+      const int wi = w_start[s] >> 4;
+      const uint32_t bs = 2u * (uint32_t)(w_start[s] & 15);
+      uint32_t lo = ps_mine[wi * TRIM_THREADS];
+#pragma unroll 1
+      for (uint32_t w = 0; w < npay; ++w) {
+        const uint32_t hi = ps_mine[(wi + w + 1) * TRIM_THREADS];
+        uint32_t v = __funnelshift_r(lo, hi, bs);
+        lo = hi;
+        const int rem = len - 16 * (int)w;
+        if (rem < 16) v &= (1u << (2 * rem)) - 1u;
+        k[1 + w] = v;
+      }
+    } else {
+      const uint32_t nexc = w_words[s] - 1u - npay;
+      k[0] = (uint32_t)len | (nexc << 16);
+      uint32_t word = 0, xi = 0;
+      for (int p = 0; p < len; ++p) {
+        const uint32_t ch = key_byte(seq, w_start[s], l1, w_us[s], p);
+        const uint32_t code = base_code_exact(ch);
+        if (code == 4u) k[1 + npay + xi++] = ((uint32_t)p << 8) | ch;
+        else word |= code << (2 * (p & 15));
+        if ((p & 15) == 15) { k[1 + (p >> 4)] = word; word = 0; }
+      }
+      if (len & 15) k[1 + (len >> 4)] = word;
+    }
+    off += w_words[s];
   }
 }
 
