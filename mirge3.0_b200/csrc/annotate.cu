@@ -78,20 +78,11 @@ struct Query {
   int len;
 };
 
-// Hamming verification of the query against library text at astart; returns packed hit or NO_HIT
-__device__ __forceinline__ uint64_t verify(const mirge_library &lib, const Query &q, const mirge_round_policy &pol, int R,
-                                           uint64_t astart, uint32_t r, uint32_t ref_lo) {
+// Hamming distance of the query against library text at astart under the round policy, text only
+// (cheap: XOR + popcount on packed words); returns the mismatch count or -1 when the policy is violated.
+__device__ __forceinline__ int verify_text(const mirge_library &lib, const Query &q, const mirge_round_policy &pol, int R,
+                                           uint64_t astart) {
   const int L = q.len;
-  // reference N anywhere under the alignment -> invalid
-  {
-    const uint64_t a = astart, b = astart + L;  // [a, b)
-    for (uint64_t w = a >> 5; w <= (b - 1) >> 5; ++w) {
-      uint32_t bits = lib.d_nmask[w];
-      if (w == (a >> 5)) bits &= 0xFFFFFFFFu << (a & 31);
-      if (w == ((b - 1) >> 5) && (b & 31)) bits &= 0xFFFFFFFFu >> (32 - (b & 31));
-      if (bits) return MIRGE_NO_HIT;
-    }
-  }
   const uint64_t n_words = ((uint64_t)lib.n_bases + 15) >> 4;
   int mm = 0, smm = 0;
   const int nw = (L + 15) >> 4;
@@ -106,10 +97,34 @@ __device__ __forceinline__ uint64_t verify(const mirge_library &lib, const Query
       const int srem = R - 16 * w;
       if (srem >= 16) smm += __popc(x);
       else if (srem > 0) smm += __popc(x & ((1u << (2 * srem)) - 1u));
-      if (mm > pol.total_mm || smm > pol.seed_mm) return MIRGE_NO_HIT;
+      if (mm > pol.total_mm || smm > pol.seed_mm) return -1;
     }
   }
-  return ((uint64_t)mm << 56) | ((uint64_t)r << 28) | (uint64_t)(astart - ref_lo);
+  return mm;
+}
+
+// any ambiguous reference base under [a, b)
+__device__ __forceinline__ bool ref_has_n(const mirge_library &lib, uint64_t a, uint64_t b) {
+  for (uint64_t w = a >> 5; w <= (b - 1) >> 5; ++w) {
+    uint32_t bits = lib.d_nmask[w];
+    if (w == (a >> 5)) bits &= 0xFFFFFFFFu << (a & 31);
+    if (w == ((b - 1) >> 5) && (b & 31)) bits &= 0xFFFFFFFFu >> (32 - (b & 31));
+    if (bits) return true;
+  }
+  return false;
+}
+
+// full check of one alignment start: text first (rejects almost every candidate), then the reference
+// it falls in, its bounds and ambiguous bases; returns the packed hit or NO_HIT
+__device__ __forceinline__ uint64_t verify(const mirge_library &lib, const Query &q, const mirge_round_policy &pol, int R,
+                                           uint64_t astart, uint32_t pos_in_ref) {
+  const int mm = verify_text(lib, q, pol, R, astart);
+  if (mm < 0) return MIRGE_NO_HIT;
+  const uint32_t r = find_ref(lib.d_ref_off, lib.n_refs, pos_in_ref);
+  const uint32_t rlo = lib.d_ref_off[r], rhi = lib.d_ref_off[r + 1];
+  if (astart < rlo || astart + (uint64_t)q.len > rhi) return MIRGE_NO_HIT;
+  if (ref_has_n(lib, astart, astart + q.len)) return MIRGE_NO_HIT;
+  return ((uint64_t)mm << 56) | ((uint64_t)r << 28) | (uint64_t)(astart - rlo);
 }
 
 __global__ void __launch_bounds__(ANN_THREADS)
@@ -174,7 +189,7 @@ annotate_kernel(mirge_library lib, mirge_round_policy pol, mirge_table t, uint64
     for (uint32_t r = 0; r < lib.n_refs; ++r) {
       const uint32_t lo = lib.d_ref_off[r], hi = lib.d_ref_off[r + 1];
       for (uint64_t a = lo; a + L <= hi; ++a) {
-        const uint64_t h = verify(lib, q, pol, R, a, r, lo);
+        const uint64_t h = verify(lib, q, pol, R, a, (uint32_t)a);
         if (h < best) best = h;
       }
     }
@@ -208,10 +223,7 @@ annotate_kernel(mirge_library lib, mirge_round_policy pol, mirge_table t, uint64
         const uint32_t pos = lib.d_idx_pos[e];
         if (pos < (uint32_t)a) continue;
         const uint32_t astart = pos - (uint32_t)a;
-        const uint32_t r = find_ref(lib.d_ref_off, lib.n_refs, pos);
-        const uint32_t rlo = lib.d_ref_off[r], rhi = lib.d_ref_off[r + 1];
-        if (astart < rlo || (uint64_t)astart + L > rhi) continue;
-        const uint64_t h = verify(lib, q, pol, R, astart, r, rlo);
+        const uint64_t h = verify(lib, q, pol, R, astart, pos);
         if (h < best) best = h;
       }
     }
