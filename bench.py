@@ -333,7 +333,9 @@ def run_b200(args):
     b_trim = rec_bytes + 8 * E
     trim_ms = timers.get("trim", (0, 0.0))[1] / steps
     col_ms = timers.get("collapse", (0, 0.0))[1] / steps
-    ann_ms = timers.get("annotate", (0, 0.0))[1] / steps
+    ann_ms = sum(v[1] for k, v in timers.items() if k.startswith("annotate")) / steps
+    kinfo["annotate"] = {"launches_per_step": sum(v[0] for k, v in timers.items() if k.startswith("annotate")) // steps,
+                         "ms_per_step": round(ann_ms, 3)}
     trim_gbs = args.reads * b_trim / (trim_ms / 1e3) / 1e9 if trim_ms else 0.0
     kinfo.setdefault("trim", {})["achieved_gbs"] = round(trim_gbs, 1)
     kinfo["trim"]["frac_hbm"] = round(trim_gbs / peak, 4)

@@ -11,8 +11,8 @@
 // Search = pigeonhole seeds: the seed region is cut into seed_mm + 1 pieces, at least one of which
 // must match exactly; each piece is looked up in a sorted 16-mer index of the library (bucket table
 // + binary search, prefix ranges for pieces shorter than 16) and every candidate is verified with
-// XOR/popcount on the packed text.  One thread per unique sequence; libraries and indexes are
-// L2-resident for all but the mRNA library.
+// XOR/popcount on the packed text.  One thread prepares one unique sequence; long candidate lists are
+// verified warp-cooperatively.  Libraries and indexes are L2-resident for all but the mRNA library.
 #include "common.cuh"
 
 #define ANN_THREADS 128
@@ -72,24 +72,21 @@ extern "C" int mirge_lib_kmers(mirge_ctx *ctx, const mirge_library *lib, uint32_
 
 // ------------------------------------------------------------------ search -------------------
 
-struct Query {
-  uint32_t w[QW_MAX];   // 2-bit codes, 16 per word
-  uint32_t nx[QW_MAX];  // bit 2q set <=> base 16w+q of the query is not ACGT (always mismatches)
-  int len;
-};
+#define MAX_PIECES 4
+#define COOP_MIN 8  // candidate lists longer than this are verified by the whole warp
 
-// Hamming distance of the query against library text at astart under the round policy, text only
-// (cheap: XOR + popcount on packed words); returns the mismatch count or -1 when the policy is violated.
-__device__ __forceinline__ int verify_text(const mirge_library &lib, const Query &q, const mirge_round_policy &pol, int R,
-                                           uint64_t astart) {
-  const int L = q.len;
+// Hamming distance of the query (2-bit words qw, always-mismatch mask qnx, L bases) against library text
+// at astart under the round policy, text only (XOR + popcount on packed words); returns the mismatch
+// count or -1 when the policy is violated.
+__device__ __forceinline__ int verify_text(const mirge_library &lib, const uint32_t *qw, const uint32_t *qnx, int L,
+                                           const mirge_round_policy &pol, int R, uint64_t astart) {
   const uint64_t n_words = ((uint64_t)lib.n_bases + 15) >> 4;
   int mm = 0, smm = 0;
   const int nw = (L + 15) >> 4;
   for (int w = 0; w < nw; ++w) {
     const uint32_t refw = lib_word16(lib.d_packed, astart + 16 * (uint64_t)w, n_words);
-    uint32_t x = q.w[w] ^ refw;
-    x = ((x | (x >> 1)) & 0x55555555u) | q.nx[w];
+    uint32_t x = qw[w] ^ refw;
+    x = ((x | (x >> 1)) & 0x55555555u) | qnx[w];
     const int rem = L - 16 * w;
     if (rem < 16) x &= (1u << (2 * rem)) - 1u;
     if (x) {
@@ -116,119 +113,179 @@ __device__ __forceinline__ bool ref_has_n(const mirge_library &lib, uint64_t a, 
 
 // full check of one alignment start: text first (rejects almost every candidate), then the reference
 // it falls in, its bounds and ambiguous bases; returns the packed hit or NO_HIT
-__device__ __forceinline__ uint64_t verify(const mirge_library &lib, const Query &q, const mirge_round_policy &pol, int R,
-                                           uint64_t astart, uint32_t pos_in_ref) {
-  const int mm = verify_text(lib, q, pol, R, astart);
+__device__ __forceinline__ uint64_t verify(const mirge_library &lib, const uint32_t *qw, const uint32_t *qnx, int L,
+                                           const mirge_round_policy &pol, int R, uint64_t astart, uint32_t pos_in_ref) {
+  const int mm = verify_text(lib, qw, qnx, L, pol, R, astart);
   if (mm < 0) return MIRGE_NO_HIT;
   const uint32_t r = find_ref(lib.d_ref_off, lib.n_refs, pos_in_ref);
   const uint32_t rlo = lib.d_ref_off[r], rhi = lib.d_ref_off[r + 1];
-  if (astart < rlo || astart + (uint64_t)q.len > rhi) return MIRGE_NO_HIT;
-  if (ref_has_n(lib, astart, astart + q.len)) return MIRGE_NO_HIT;
+  if (astart < rlo || astart + (uint64_t)L > rhi) return MIRGE_NO_HIT;
+  if (ref_has_n(lib, astart, astart + L)) return MIRGE_NO_HIT;
   return ((uint64_t)mm << 56) | ((uint64_t)r << 28) | (uint64_t)(astart - rlo);
 }
 
+// One thread prepares one unique sequence (query window, pigeonhole pieces, index ranges); short candidate
+// lists are verified by that thread, long ones by all 32 lanes of the warp (query broadcast through
+// shared memory, min-reduction with shuffles), so one sequence with hundreds of candidates does not
+// stall the other 31.
 __global__ void __launch_bounds__(ANN_THREADS)
 annotate_kernel(mirge_library lib, mirge_round_policy pol, mirge_table t, uint64_t n_keys, uint8_t *__restrict__ annot_round,
                 uint64_t *__restrict__ hit) {
+  __shared__ uint32_t s_qw[ANN_THREADS / 32][QW_MAX], s_qnx[ANN_THREADS / 32][QW_MAX];
+  __shared__ uint32_t s_meta[ANN_THREADS / 32][4 + 3 * MAX_PIECES];
   const uint64_t id = (uint64_t)blockIdx.x * ANN_THREADS + threadIdx.x;
-  if (id >= n_keys) return;
-  const uint32_t *key = t.d_arena + t.d_key_ref[id];
-  const uint32_t hdr = key[0];
-  const int len = (int)key_len(hdr), nexc = (int)key_nexc(hdr);
-  if (pol.select == MIRGE_SELECT_LEN_LT26) { if (!(len < 26)) return; }
-  else if (pol.select == MIRGE_SELECT_LEN_GT25) { if (!(len > 25)) return; }
-  else if (annot_round[id] != 0xFF) return;
-  const uint32_t *pay = key + 1;
-  const uint32_t *exc = key + 1 + ((len + 15) >> 4);
-  // query window [qs, qe) of the key (manifoldAlign.py:118-126; -5/-3 of round 8)
-  int qs = 0, qe = len;
-  if (pol.strip_polyT) {
-    int tpos = len;
-    while (tpos > 0) {
-      const int j = tpos - 1;
-      if (((pay[j >> 4] >> (2 * (j & 15))) & 3u) != 3u) break;
-      bool is_exc = false;  // a lower-case 't' (or any non-"ACGT" byte) is stored as an exception
-      for (int x = 0; x < nexc; ++x) is_exc |= (int)(exc[x] >> 8) == j;
-      if (is_exc) break;
-      --tpos;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool active = id < n_keys;
+  uint32_t qw[QW_MAX], qnx[QW_MAX];
+  int L = 0, R = 0, np = 0;
+  uint32_t p_lo[MAX_PIECES], p_hi[MAX_PIECES], p_off[MAX_PIECES];
+#pragma unroll
+  for (int i = 0; i < MAX_PIECES; ++i) p_lo[i] = p_hi[i] = p_off[i] = 0;
+  bool degenerate = false;
+  if (active) {
+    const uint32_t *key = t.d_arena + t.d_key_ref[id];
+    const uint32_t hdr = key[0];
+    const int len = (int)key_len(hdr), nexc = (int)key_nexc(hdr);
+    if (pol.select == MIRGE_SELECT_LEN_LT26) active = len < 26;
+    else if (pol.select == MIRGE_SELECT_LEN_GT25) active = len > 25;
+    else active = annot_round[id] == 0xFF;
+    if (active) {
+      const uint32_t *pay = key + 1;
+      const uint32_t *exc = key + 1 + ((len + 15) >> 4);
+      // query window [qs, qe) of the key (manifoldAlign.py:118-126; -5/-3 of round 8)
+      int qs = 0, qe = len;
+      if (pol.strip_polyT) {
+        int tpos = len;
+        while (tpos > 0) {
+          const int j = tpos - 1;
+          if (((pay[j >> 4] >> (2 * (j & 15))) & 3u) != 3u) break;
+          bool is_exc = false;  // a lower-case 't' (or any non-"ACGT" byte) is stored as an exception
+          for (int x = 0; x < nexc; ++x) is_exc |= (int)(exc[x] >> 8) == j;
+          if (is_exc) break;
+          --tpos;
+        }
+        if (len - tpos < 3) active = false;
+        qe = tpos;
+      }
+      qs += pol.trim5;
+      qe -= pol.trim3;
+      if (qe <= qs) active = false;
+      if (active) {
+        L = qe - qs;
+        const int nw = (L + 15) >> 4, npay = (len + 15) >> 4;
+        for (int w = 0; w < nw; ++w) {
+          const int p = qs + 16 * w, wi = p >> 4, sh = 2 * (p & 15);
+          const uint32_t lo = pay[wi], hi = (wi + 1 < npay) ? pay[wi + 1] : 0u;
+          uint32_t v = sh ? __funnelshift_r(lo, hi, sh) : lo;
+          const int rem = L - 16 * w;
+          if (rem < 16) v &= (1u << (2 * rem)) - 1u;
+          qw[w] = v;
+          qnx[w] = 0;
+        }
+        for (int x = 0; x < nexc; ++x) {
+          const int pos = (int)(exc[x] >> 8) - qs;
+          if (pos < 0 || pos >= L) continue;
+          const uint32_t code = base_code_upper(exc[x] & 0xFFu);
+          const int w = pos >> 4, sh = 2 * (pos & 15);
+          if (code < 4u) qw[w] = (qw[w] & ~(3u << sh)) | (code << sh);
+          else qnx[w] |= 1u << sh;
+        }
+        R = pol.seed_len == 0 ? L : min(pol.seed_len, L);
+        np = pol.seed_mm + 1;
+        degenerate = R / np < MIN_SEED;
+        if (!degenerate) {
+          for (int pi = 0; pi < np; ++pi) {
+            const int a = (int)((long long)pi * R / np), b = (int)((long long)(pi + 1) * R / np);
+            const int s = min(16, b - a);
+            // piece k-mer, first base most significant; a piece with a non-ACGT read base cannot be exact
+            uint32_t kmer = 0;
+            bool has_n = false;
+            for (int i = 0; i < b - a; ++i) {
+              const int p = a + i;
+              has_n |= (qnx[p >> 4] >> (2 * (p & 15))) & 1u;
+              if (i < s) kmer |= ((qw[p >> 4] >> (2 * (p & 15))) & 3u) << (2 * (15 - i));
+            }
+            if (has_n) continue;
+            const uint32_t span = (s == 16) ? 0u : ((1u << (2 * (16 - s))) - 1u);
+            const uint32_t k_lo = kmer, k_hi = kmer | span;
+            const uint32_t bsh = 32 - lib.bucket_bits;
+            uint32_t lo = lib.d_idx_bucket[k_lo >> bsh], hi = lib.d_idx_bucket[(k_hi >> bsh) + 1];
+            uint32_t l = lo, h = hi;  // lower_bound(k_lo) and upper_bound(k_hi) inside [lo, hi)
+            while (l < h) { const uint32_t mid = (l + h) >> 1; if (lib.d_idx_kmer[mid] < k_lo) l = mid + 1; else h = mid; }
+            lo = l;
+            h = hi;
+            while (l < h) { const uint32_t mid = (l + h) >> 1; if (lib.d_idx_kmer[mid] <= k_hi) l = mid + 1; else h = mid; }
+            p_lo[pi] = lo;
+            p_hi[pi] = l;
+            p_off[pi] = (uint32_t)a;
+          }
+        }
+      }
     }
-    if (len - tpos < 3) return;
-    qe = tpos;
   }
-  qs += pol.trim5;
-  qe -= pol.trim3;
-  if (qe <= qs) return;
-  Query q;
-  q.len = qe - qs;
-  const int L = q.len, nw = (L + 15) >> 4;
-  {
-    const int npay = (len + 15) >> 4;
-    for (int w = 0; w < nw; ++w) {
-      const int p = qs + 16 * w, wi = p >> 4, sh = 2 * (p & 15);
-      const uint32_t lo = pay[wi], hi = (wi + 1 < npay) ? pay[wi + 1] : 0u;
-      uint32_t v = sh ? __funnelshift_r(lo, hi, sh) : lo;
-      const int rem = L - 16 * w;
-      if (rem < 16) v &= (1u << (2 * rem)) - 1u;
-      q.w[w] = v;
-      q.nx[w] = 0;
-    }
-    for (int x = 0; x < nexc; ++x) {
-      const int pos = (int)(exc[x] >> 8) - qs;
-      if (pos < 0 || pos >= L) continue;
-      const uint32_t code = base_code_upper(exc[x] & 0xFFu);
-      const int w = pos >> 4, sh = 2 * (pos & 15);
-      if (code < 4u) q.w[w] = (q.w[w] & ~(3u << sh)) | (code << sh);
-      else q.nx[w] |= 1u << sh;
-    }
-  }
-  const int R = pol.seed_len == 0 ? L : min(pol.seed_len, L);
-  const int np = pol.seed_mm + 1;
   uint64_t best = MIRGE_NO_HIT;
-  if (R / np < MIN_SEED) {
-    // degenerate (very short query): exhaustive scan keeps the result exact
+  uint32_t total = 0;
+#pragma unroll
+  for (int i = 0; i < MAX_PIECES; ++i) total += p_hi[i] - p_lo[i];
+  const bool big = active && !degenerate && total > COOP_MIN;
+  if (active && degenerate) {
+    // very short query: exhaustive scan keeps the result exact
     for (uint32_t r = 0; r < lib.n_refs; ++r) {
       const uint32_t lo = lib.d_ref_off[r], hi = lib.d_ref_off[r + 1];
       for (uint64_t a = lo; a + L <= hi; ++a) {
-        const uint64_t h = verify(lib, q, pol, R, a, (uint32_t)a);
+        const uint64_t h = verify(lib, qw, qnx, L, pol, R, a, (uint32_t)a);
         if (h < best) best = h;
       }
     }
-  } else {
-    for (int pi = 0; pi < np; ++pi) {
-      const int a = (int)((long long)pi * R / np), b = (int)((long long)(pi + 1) * R / np);
-      const int s = min(16, b - a);
-      // piece k-mer, first base most significant; a piece containing a non-ACGT read base cannot be exact
-      uint32_t kmer = 0;
-      bool has_n = false;
-      for (int i = 0; i < b - a; ++i) {
-        const int p = a + i;
-        has_n |= (q.nx[p >> 4] >> (2 * (p & 15))) & 1u;
-        if (i < s) kmer |= ((q.w[p >> 4] >> (2 * (p & 15))) & 3u) << (2 * (15 - i));
-      }
-      if (has_n) continue;
-      const uint32_t span = (s == 16) ? 0u : ((1u << (2 * (16 - s))) - 1u);
-      const uint32_t k_lo = kmer, k_hi = kmer | span;
-      const uint32_t bsh = 32 - lib.bucket_bits;
-      uint32_t lo = lib.d_idx_bucket[k_lo >> bsh], hi = lib.d_idx_bucket[(k_hi >> bsh) + 1];
-      // lower_bound(k_lo) and upper_bound(k_hi) inside [lo, hi)
-      {
-        uint32_t l = lo, h = hi;
-        while (l < h) { const uint32_t m = (l + h) >> 1; if (lib.d_idx_kmer[m] < k_lo) l = m + 1; else h = m; }
-        lo = l;
-        h = hi;
-        while (l < h) { const uint32_t m = (l + h) >> 1; if (lib.d_idx_kmer[m] <= k_hi) l = m + 1; else h = m; }
-        hi = l;
-      }
-      for (uint32_t e = lo; e < hi; ++e) {
+  } else if (active && !big) {
+#pragma unroll
+    for (int pi = 0; pi < MAX_PIECES; ++pi)
+      for (uint32_t e = p_lo[pi]; e < p_hi[pi]; ++e) {
         const uint32_t pos = lib.d_idx_pos[e];
-        if (pos < (uint32_t)a) continue;
-        const uint32_t astart = pos - (uint32_t)a;
-        const uint64_t h = verify(lib, q, pol, R, astart, pos);
+        if (pos < p_off[pi]) continue;
+        const uint64_t h = verify(lib, qw, qnx, L, pol, R, pos - p_off[pi], pos);
         if (h < best) best = h;
       }
-    }
   }
-  if (best != MIRGE_NO_HIT) {
+  // long candidate lists: the whole warp verifies them, one owner lane at a time
+  unsigned todo = __ballot_sync(0xffffffffu, big);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    todo &= todo - 1;
+    if (lane == leader) {
+      const int nw = (L + 15) >> 4;
+      for (int w = 0; w < nw; ++w) { s_qw[warp][w] = qw[w]; s_qnx[warp][w] = qnx[w]; }
+      s_meta[warp][0] = (uint32_t)L;
+      s_meta[warp][1] = (uint32_t)R;
+#pragma unroll
+      for (int pi = 0; pi < MAX_PIECES; ++pi) {
+        s_meta[warp][4 + 3 * pi] = p_lo[pi];
+        s_meta[warp][5 + 3 * pi] = p_hi[pi];
+        s_meta[warp][6 + 3 * pi] = p_off[pi];
+      }
+    }
+    __syncwarp();
+    const int cL = (int)s_meta[warp][0], cR = (int)s_meta[warp][1];
+    uint64_t b = MIRGE_NO_HIT;
+#pragma unroll
+    for (int pi = 0; pi < MAX_PIECES; ++pi) {
+      const uint32_t lo = s_meta[warp][4 + 3 * pi], hi = s_meta[warp][5 + 3 * pi], off = s_meta[warp][6 + 3 * pi];
+      for (uint32_t e = lo + lane; e < hi; e += 32) {
+        const uint32_t pos = lib.d_idx_pos[e];
+        if (pos < off) continue;
+        const uint64_t h = verify(lib, s_qw[warp], s_qnx[warp], cL, pol, cR, pos - off, pos);
+        if (h < b) b = h;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const uint64_t o = __shfl_xor_sync(0xffffffffu, b, d);
+      if (o < b) b = o;
+    }
+    if (lane == leader) best = b;
+    __syncwarp();
+  }
+  if (active && best != MIRGE_NO_HIT) {
     annot_round[id] = (uint8_t)pol.round;
     hit[id] = best;
   }

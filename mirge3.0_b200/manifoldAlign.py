@@ -86,7 +86,7 @@ def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = 
     pols = round_policies()
     for rnd in range(10 if spike_in else 9):
         lib = libs[ROUND_LIBS[rnd]]
-        with dev.timed("annotate"):
+        with dev.timed("annotate_r%d" % rnd):
             dev.check(dev.lib.mirge_annotate_round(dev.ctx, C.byref(lib.struct), C.byref(pols[rnd]), C.byref(keys.struct), n,
                                                    _ptr(annot), _ptr(hit), dev.stream()))
         dev.launches += 1
