@@ -110,3 +110,47 @@ def test_annotate_round_c_vs_python():
                 h = int(hit[i])
                 assert ar[i] == rnd and (h >> 56, (h >> 28) & 0xFFFFFFF, h & 0xFFFFFFF) == exp, (rnd, s)
     assert nhit > 200
+
+
+def test_indexed_search_equals_exhaustive_scan():
+    """The indexed CPU search (used as the CPU baseline on large libraries) must return exactly what the
+    exhaustive scan -- the definition -- returns, round by round."""
+    from mirge_b200 import synth
+
+    libs = synth.make_libraries(scale=0.03, mrna_count=40)
+    gen = synth.ReadGenerator(libs, synth.CONFIGS[1], "cpu")
+    fq = gen.fastq(4000).numpy()
+    cp = P.build_trim_params(synth.trim_config_for(1))
+    _, tab = coracle.digest_collapse(fq, cp, nthreads=4)
+    keys, off, cnt = tab.export()
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    from mirge_b200.libraries import ROUND_LIBS, round_policies
+
+    pols = round_policies()
+    a1 = np.full(len(cnt), 0xFF, dtype=np.uint8)
+    h1 = np.full(len(cnt), abi.NO_HIT, dtype=np.uint64)
+    a2, h2 = a1.copy(), h1.copy()
+    for rnd in range(10):
+        L = libs.libs[ROUND_LIBS[rnd]]
+        text, roff = lut[L.codes], L.off.astype(np.uint32)
+        coracle.annotate_round(keys, off, text, roff, pols[rnd], a1, h1, nthreads=8)
+        coracle.annotate_round_indexed(keys, off, coracle.Index(text, roff), pols[rnd], a2, h2, nthreads=8)
+        assert np.array_equal(a1, a2) and np.array_equal(h1, h2), rnd
+    assert (a1 != 0xFF).sum() > 100 and len(set(a1.tolist())) >= 6
+
+
+def test_synthetic_generator_is_seeded_and_well_formed():
+    from mirge_b200 import synth
+
+    libs = synth.make_libraries(scale=0.02, mrna_count=20)
+    for cid in (1, 2, 3):
+        a = synth.ReadGenerator(libs, synth.CONFIGS[cid], "cpu").fastq(3000).numpy().tobytes()
+        b = synth.ReadGenerator(libs, synth.CONFIGS[cid], "cpu").fastq(3000).numpy().tobytes()
+        assert a == b
+        recs = po.parse_fastq(a)
+        assert len(recs) == 3000 and all(len(s) == synth.CONFIGS[cid].L == len(q) for _, s, q in recs)
+        assert recs[12][0].startswith("SYN%d.12 12 length=" % cid)
+    # most C1 reads carry the (possibly partial) illumina adapter
+    ad = po.Adapter("back", synth.ILLUMINA)
+    recs = po.parse_fastq(synth.ReadGenerator(libs, synth.CONFIGS[1], "cpu").fastq(300).numpy().tobytes())
+    assert sum(po.match_to(ad, s) is not None for _, s, _ in recs) > 250
