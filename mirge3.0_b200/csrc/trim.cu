@@ -338,6 +338,43 @@ __device__ __noinline__ void traceback(const int a, const uint32_t *eqt, const u
   matches = i - nonmatch;
 }
 
+// Cost-1 cells need no cost columns: slide up the diagonal to the only error and decide its kind by asking
+// which neighbour has cost 0 -- a cost-0 cell (a, b) simply means adapter[0:a] == read[b-a:b], one packed
+// compare.  cutadapt's rule picks mismatch if (t-1, col-1) is such a cell, else insertion if (t-1, col) is,
+// else deletion.  Needs the packed pure-ACGT read and a plain adapter; returns false when it does not apply.
+__device__ __forceinline__ bool traceback_cost1(const int a, const FastCtx &fc, int i, int j, int &matches, int &origin) {
+  const int delta = j - i;
+  if (!fc.jump_ok || c_p.ad[a].wildcard_ref || delta < 0) return false;
+  const uint64_t a2 = c_p.ad[a].a2;
+  const uint64_t even = 0x5555555555555555ull;
+  uint64_t x = a2 ^ read_window(fc.ps, fc.rbase + delta);
+  x = (x | (x >> 1)) & even;
+  if (i < 32) x &= (1ull << (2 * i)) - 1ull;
+  if (x == 0) return false;  // not a cost-1 cell of this diagonal (cannot happen); use the general path
+  const int t = (64 - __clzll((long long)x) + 1) >> 1;  // row of the error
+  const uint64_t below = t - 1 >= 32 ? ~0ull : ((1ull << (2 * (t - 1))) - 1ull);  // rows 1..t-1
+  if ((x & below) == 0) {  // mismatch: rows above continue cleanly on the same diagonal
+    matches = i - 1;
+    origin = delta;
+    return true;
+  }
+  uint64_t y = a2 ^ read_window(fc.ps, fc.rbase + delta + 1);
+  y = (y | (y >> 1)) & even & below;
+  if (y == 0) {  // insertion: adapter[0:t-1] ends at the same read base
+    matches = i - 1;
+    origin = delta + 1;
+    return true;
+  }
+  if (delta < 1) return false;
+  const uint64_t upto = t >= 32 ? ~0ull : ((1ull << (2 * t)) - 1ull);  // rows 1..t
+  uint64_t z = a2 ^ read_window(fc.ps, fc.rbase + delta - 1);
+  z = (z | (z >> 1)) & even & upto;
+  if (z != 0) return false;  // inconsistent with cost 1: let the general path decide
+  matches = i;  // deletion: a read base is skipped, every adapter row matches
+  origin = delta - 1;
+  return true;
+}
+
 // candidate with at most `u` matches, cost c, scan index idx can still beat the best so far
 #define MAY_WIN(u, c, idx) (!have || (u) > b_m || ((u) == b_m && ((c) < b_c || ((c) == b_c && (idx) < b_idx))))
 #define TAKE_IF_BETTER(mt, c, org, idx)                                                      \
@@ -383,8 +420,10 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
     const int jc_ = Q_COL(v_), cc_ = Q_COST(v_);                                                 \
     if (MAY_WIN(Q_UB(v_, m), cc_, jc_)) {                                                        \
       int mt_, org_;                                                                             \
-      recompute(eqt, read, jc_, span, cb);                                                       \
-      traceback(a, eqt, read, fc, cb, m, jc_, cc_, mt_, org_);                                   \
+      if (!(cc_ == 1 && traceback_cost1(a, fc, m, jc_, mt_, org_))) {                            \
+        recompute(eqt, read, jc_, span, cb);                                                     \
+        traceback(a, eqt, read, fc, cb, m, jc_, cc_, mt_, org_);                                 \
+      }                                                                                          \
       TAKE_IF_BETTER(mt_, cc_, org_, jc_)                                                        \
     }                                                                                            \
   }
@@ -456,12 +495,19 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
         const int idx = (i == m) ? n : n + 1 + i;  // row m of column n precedes the last-column scan
         TAKE_IF_BETTER(i, 0, n - i, idx)
       } else {
-        rowmask |= 1u << (i - 1);
         bool full = true;  // may reach i matches only if its first step is a match or a deletion
         if (!((eq >> (i - 1)) & 1u) && n >= 1) {
           const int cd = cprev_up + 1, cdel = cprev + 1, cins = c_up + 1;
-          if ((cd <= cdel && cd <= cins) || cins <= cdel) full = false;
+          if (cd <= cdel && cd <= cins) full = false;  // mismatch
+          else if (cins <= cdel) {
+            // Rule 3: entered by an insertion from (i-1, n): same matches and origin as that cell, one
+            // error more; when (i-1, n) is an accepted candidate of the same column (scanned earlier),
+            // (i, n) can never win.
+            if (ad.acc[i - 1] >= c - 1) continue;
+            full = false;
+          }
         }
+        rowmask |= 1u << (i - 1);
         if (full) rowub |= 1u << (i - 1);
       }
     }
@@ -475,12 +521,14 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
       const int idx = (i == m) ? n : n + 1 + i;
       const int ub = ((rowub >> (i - 1)) & 1u) ? i : i - 1;
       if (MAY_WIN(ub, ci, idx)) {
-        if (!have_cols) {
-          recompute(eqt, read, n, span, cb);
-          have_cols = true;
-        }
         int mt, org;
-        traceback(a, eqt, read, fc, cb, i, n, ci, mt, org);
+        if (!(ci == 1 && traceback_cost1(a, fc, i, n, mt, org))) {
+          if (!have_cols) {
+            recompute(eqt, read, n, span, cb);
+            have_cols = true;
+          }
+          traceback(a, eqt, read, fc, cb, i, n, ci, mt, org);
+        }
         TAKE_IF_BETTER(mt, ci, org, idx)
       }
     }

@@ -1,0 +1,92 @@
+"""Run under torchrun (one rank per GPU): every rank digests its shard of one synthetic sample, the
+unique sequences are hash-partitioned to their owners with the NCCL all-to-all, owners annotate their
+slice; rank 0 gathers everything and compares with the single-process oracle on the whole sample.
+Used by tests/test_gpu_multi.py; exits non-zero on any mismatch."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import mirge_b200  # noqa: E402,F401
+from mirge_b200 import device as D  # noqa: E402
+from mirge_b200 import distributed as MD  # noqa: E402
+from mirge_b200 import libraries as LB  # noqa: E402
+from mirge_b200 import manifoldAlign as MA  # noqa: E402
+from mirge_b200 import synth  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = D.Device(local)
+    cfg_id = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    n_reads = 120_000
+    libs = synth.make_libraries(scale=0.05, mrna_count=100)
+    lset = LB.LibrarySet.from_fasta_dict(dev, libs.fasta_dict())
+    cfg = synth.trim_config_for(cfg_id)
+    eng = D.DigestEngine(dev, cfg)
+    umi = cfg.umi() or (0, 0)
+    # the same sample on every rank (seeded), each rank takes its contiguous share of the records
+    fq = synth.ReadGenerator(libs, synth.CONFIGS[cfg_id], "cpu").fastq(n_reads).numpy()
+    nl = np.flatnonzero(fq == 10)
+    lo, hi = MD.shard_ranges(n_reads, world)[rank]
+    b0 = 0 if lo == 0 else int(nl[4 * lo - 1]) + 1
+    b1 = int(nl[4 * hi - 1]) + 1
+    shard = torch.from_numpy(fq[b0:b1].copy()).to(dev.tdev)
+    local_t = D.CollapseTable(dev, min_keys=1 << 12)
+    owner_t = D.CollapseTable(dev, min_keys=1 << 12)
+    n = eng.digest_device(shard, local_t, batch_bytes=3 << 20)
+    assert n == hi - lo
+    ids, cnt = local_t.drain()
+    MD.exchange_and_merge(dev, local_t, ids, cnt, owner_t, world, umi=umi)
+    ids, cnt = owner_t.drain()
+    keys = owner_t.export_keys()
+    annot, hit = MA.annotate_keys(dev, lset, MA.KeySet.from_table(owner_t), True)
+    mine = {keys[i].decode(): (int(c), int(a), int(h)) for i, c, a, h in
+            zip(ids.cpu().tolist(), cnt.cpu().tolist(), annot.cpu()[ids.cpu().long()].tolist(),
+                hit.cpu().numpy().view(np.uint64)[ids.cpu().numpy()].tolist())}
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    ok = True
+    if rank == 0:
+        from oracle import coracle
+
+        union = {}
+        for g in gathered:
+            assert not (set(g) & set(union)), "a sequence is owned by two ranks"
+            union.update(g)
+        _, tab = coracle.digest_collapse(fq, dev.trim_params, nthreads=8)
+        exp = tab.to_dict()
+        ok = {k: v[0] for k, v in union.items()} == exp
+        seqs = sorted(exp)
+        blob = np.frombuffer("".join(seqs).encode(), dtype=np.uint8)
+        off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(s) for s in seqs])
+        a_o = np.full(len(seqs), 0xFF, dtype=np.uint8)
+        h_o = np.full(len(seqs), 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+        lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+        pols = LB.round_policies()
+        for rnd in range(10):
+            L = libs.libs[LB.ROUND_LIBS[rnd]]
+            coracle.annotate_round(blob, off, lut[L.codes], L.off.astype(np.uint32), pols[rnd], a_o, h_o, nthreads=8)
+        for i, s in enumerate(seqs):
+            if union[s][1] != int(a_o[i]) or union[s][2] != int(h_o[i]):
+                ok = False
+                print("annotation mismatch", s, union[s], int(a_o[i]), int(h_o[i]))
+                break
+        sizes = [len(g) for g in gathered]
+        print("multi-GPU check: world=%d reads=%d uniques=%d per-rank=%s annotated=%d ok=%s"
+              % (world, n_reads, len(exp), sizes, int((a_o != 0xFF).sum()), ok))
+    flag = torch.tensor([1 if ok else 0], device=dev.tdev)
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,23 @@
+"""Two-GPU parity of the sharded path (NCCL all-to-all exchange + owner-side annotation) against the
+single-process oracle.  Needs >= 2 GPUs (skipped otherwise; run with `gpurun --gpus 2`)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("cfg_id", [1, 3])
+def test_two_gpu_exchange_matches_oracle(cfg_id):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + cfg_id), os.path.join(ROOT, "tests", "multi_gpu_check.py"), str(cfg_id)]
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "ok=True" in p.stdout
