@@ -262,6 +262,12 @@ int mirge_annotate_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_r
                          const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round,
                          uint64_t *d_hit, void *stream);
 
+/* The same for several consecutive rounds in one launch (libs[i] / policies[i] = round i of the call):
+ * every key is read once and leaves at the first round that hits it.  At most 10 rounds per call. */
+int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, const mirge_round_policy *policies,
+                          int n_rounds, const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round,
+                          uint64_t *d_hit, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

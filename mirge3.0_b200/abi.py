@@ -133,6 +133,10 @@ SYMBOLS = {
     ),
     "mirge_partition_pack": (C.c_int, [_P, C.POINTER(Table), _P, _P, _U64, _P, _P, _P]),
     "mirge_lib_kmers": (C.c_int, [_P, C.POINTER(Library), _P, _P, _P]),
+    "mirge_annotate_rounds": (
+        C.c_int,
+        [_P, C.POINTER(Library), C.POINTER(RoundPolicy), C.c_int, C.POINTER(Table), _U64, _P, _P, _P],
+    ),
     "mirge_annotate_round": (
         C.c_int,
         [_P, C.POINTER(Library), C.POINTER(RoundPolicy), C.POINTER(Table), _U64, _P, _P, _P],

@@ -73,7 +73,14 @@ extern "C" int mirge_lib_kmers(mirge_ctx *ctx, const mirge_library *lib, uint32_
 // ------------------------------------------------------------------ search -------------------
 
 #define MAX_PIECES 4
+#define MAX_ROUNDS 10
 #define COOP_MIN 8  // candidate lists longer than this are verified by the whole warp
+
+struct RoundSet {
+  int n;
+  mirge_library lib[MAX_ROUNDS];
+  mirge_round_policy pol[MAX_ROUNDS];
+};
 
 // Hamming distance of the query (2-bit words qw, always-mismatch mask qnx, L bases) against library text
 // at astart under the round policy, text only (XOR + popcount on packed words); returns the mismatch
@@ -124,103 +131,52 @@ __device__ __forceinline__ uint64_t verify(const mirge_library &lib, const uint3
   return ((uint64_t)mm << 56) | ((uint64_t)r << 28) | (uint64_t)(astart - rlo);
 }
 
-// One thread prepares one unique sequence (query window, pigeonhole pieces, index ranges); short candidate
-// lists are verified by that thread, long ones by all 32 lanes of the warp (query broadcast through
-// shared memory, min-reduction with shuffles), so one sequence with hundreds of candidates does not
-// stall the other 31.
-__global__ void __launch_bounds__(ANN_THREADS)
-annotate_kernel(mirge_library lib, mirge_round_policy pol, mirge_table t, uint64_t n_keys, uint8_t *__restrict__ annot_round,
-                uint64_t *__restrict__ hit) {
-  __shared__ uint32_t s_qw[ANN_THREADS / 32][QW_MAX], s_qnx[ANN_THREADS / 32][QW_MAX];
-  __shared__ uint32_t s_meta[ANN_THREADS / 32][4 + 3 * MAX_PIECES];
-  const uint64_t id = (uint64_t)blockIdx.x * ANN_THREADS + threadIdx.x;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  bool active = id < n_keys;
-  uint32_t qw[QW_MAX], qnx[QW_MAX];
-  int L = 0, R = 0, np = 0;
+// 16 query bases starting at base a, first base most significant (the index's k-mer order)
+__device__ __forceinline__ uint32_t query_kmer16(const uint32_t *qw, int a, int nw) {
+  const int wi = a >> 4, sh = 2 * (a & 15);
+  const uint32_t lo = qw[wi], hi = (wi + 1 < nw) ? qw[wi + 1] : 0u;
+  const uint32_t v = sh ? __funnelshift_r(lo, hi, sh) : lo;
+  const uint32_t r = __brev(v);  // reverses base order and the two bits inside each base
+  return ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+}
+
+// any always-mismatch (non-ACGT) query base in [a, b)
+__device__ __forceinline__ bool query_has_n(const uint32_t *qnx, int a, int b) {
+  for (int p = a; p < b; ++p)
+    if ((qnx[p >> 4] >> (2 * (p & 15))) & 1u) return true;
+  return false;
+}
+
+// One bowtie round for the query of this lane (active lanes only); all 32 lanes must call it together:
+// long candidate lists are verified by the whole warp (query broadcast through shared memory,
+// min-reduction with shuffles), so one sequence with hundreds of candidates does not stall the others.
+__device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const mirge_round_policy &pol, bool active,
+                                                 const uint32_t *qw, const uint32_t *qnx, int L, bool has_exc,
+                                                 uint32_t *s_qw, uint32_t *s_qnx, uint32_t *s_meta, int lane) {
   uint32_t p_lo[MAX_PIECES], p_hi[MAX_PIECES], p_off[MAX_PIECES];
 #pragma unroll
   for (int i = 0; i < MAX_PIECES; ++i) p_lo[i] = p_hi[i] = p_off[i] = 0;
-  bool degenerate = false;
-  if (active) {
-    const uint32_t *key = t.d_arena + t.d_key_ref[id];
-    const uint32_t hdr = key[0];
-    const int len = (int)key_len(hdr), nexc = (int)key_nexc(hdr);
-    if (pol.select == MIRGE_SELECT_LEN_LT26) active = len < 26;
-    else if (pol.select == MIRGE_SELECT_LEN_GT25) active = len > 25;
-    else active = annot_round[id] == 0xFF;
-    if (active) {
-      const uint32_t *pay = key + 1;
-      const uint32_t *exc = key + 1 + ((len + 15) >> 4);
-      // query window [qs, qe) of the key (manifoldAlign.py:118-126; -5/-3 of round 8)
-      int qs = 0, qe = len;
-      if (pol.strip_polyT) {
-        int tpos = len;
-        while (tpos > 0) {
-          const int j = tpos - 1;
-          if (((pay[j >> 4] >> (2 * (j & 15))) & 3u) != 3u) break;
-          bool is_exc = false;  // a lower-case 't' (or any non-"ACGT" byte) is stored as an exception
-          for (int x = 0; x < nexc; ++x) is_exc |= (int)(exc[x] >> 8) == j;
-          if (is_exc) break;
-          --tpos;
-        }
-        if (len - tpos < 3) active = false;
-        qe = tpos;
-      }
-      qs += pol.trim5;
-      qe -= pol.trim3;
-      if (qe <= qs) active = false;
-      if (active) {
-        L = qe - qs;
-        const int nw = (L + 15) >> 4, npay = (len + 15) >> 4;
-        for (int w = 0; w < nw; ++w) {
-          const int p = qs + 16 * w, wi = p >> 4, sh = 2 * (p & 15);
-          const uint32_t lo = pay[wi], hi = (wi + 1 < npay) ? pay[wi + 1] : 0u;
-          uint32_t v = sh ? __funnelshift_r(lo, hi, sh) : lo;
-          const int rem = L - 16 * w;
-          if (rem < 16) v &= (1u << (2 * rem)) - 1u;
-          qw[w] = v;
-          qnx[w] = 0;
-        }
-        for (int x = 0; x < nexc; ++x) {
-          const int pos = (int)(exc[x] >> 8) - qs;
-          if (pos < 0 || pos >= L) continue;
-          const uint32_t code = base_code_upper(exc[x] & 0xFFu);
-          const int w = pos >> 4, sh = 2 * (pos & 15);
-          if (code < 4u) qw[w] = (qw[w] & ~(3u << sh)) | (code << sh);
-          else qnx[w] |= 1u << sh;
-        }
-        R = pol.seed_len == 0 ? L : min(pol.seed_len, L);
-        np = pol.seed_mm + 1;
-        degenerate = R / np < MIN_SEED;
-        if (!degenerate) {
-          for (int pi = 0; pi < np; ++pi) {
-            const int a = (int)((long long)pi * R / np), b = (int)((long long)(pi + 1) * R / np);
-            const int s = min(16, b - a);
-            // piece k-mer, first base most significant; a piece with a non-ACGT read base cannot be exact
-            uint32_t kmer = 0;
-            bool has_n = false;
-            for (int i = 0; i < b - a; ++i) {
-              const int p = a + i;
-              has_n |= (qnx[p >> 4] >> (2 * (p & 15))) & 1u;
-              if (i < s) kmer |= ((qw[p >> 4] >> (2 * (p & 15))) & 3u) << (2 * (15 - i));
-            }
-            if (has_n) continue;
-            const uint32_t span = (s == 16) ? 0u : ((1u << (2 * (16 - s))) - 1u);
-            const uint32_t k_lo = kmer, k_hi = kmer | span;
-            const uint32_t bsh = 32 - lib.bucket_bits;
-            uint32_t lo = lib.d_idx_bucket[k_lo >> bsh], hi = lib.d_idx_bucket[(k_hi >> bsh) + 1];
-            uint32_t l = lo, h = hi;  // lower_bound(k_lo) and upper_bound(k_hi) inside [lo, hi)
-            while (l < h) { const uint32_t mid = (l + h) >> 1; if (lib.d_idx_kmer[mid] < k_lo) l = mid + 1; else h = mid; }
-            lo = l;
-            h = hi;
-            while (l < h) { const uint32_t mid = (l + h) >> 1; if (lib.d_idx_kmer[mid] <= k_hi) l = mid + 1; else h = mid; }
-            p_lo[pi] = lo;
-            p_hi[pi] = l;
-            p_off[pi] = (uint32_t)a;
-          }
-        }
-      }
+  const int R = pol.seed_len == 0 ? L : min(pol.seed_len, L);
+  const int np = pol.seed_mm + 1;
+  const bool degenerate = active && (R / np < MIN_SEED);
+  const int nw = (L + 15) >> 4;
+  if (active && !degenerate) {
+    for (int pi = 0; pi < np; ++pi) {
+      const int a = (int)((long long)pi * R / np), b = (int)((long long)(pi + 1) * R / np);
+      const int s = min(16, b - a);
+      // a piece with a non-ACGT read base cannot be exact
+      if (has_exc && query_has_n(qnx, a, b)) continue;
+      const uint32_t span = (s == 16) ? 0u : ((1u << (2 * (16 - s))) - 1u);
+      const uint32_t k_lo = query_kmer16(qw, a, nw) & ~span, k_hi = k_lo | span;
+      const uint32_t bsh = 32 - lib.bucket_bits;
+      uint32_t l = lib.d_idx_bucket[k_lo >> bsh], h = lib.d_idx_bucket[(k_hi >> bsh) + 1];
+      const uint32_t hi0 = h;  // lower_bound(k_lo), then upper_bound(k_hi), inside the bucket range
+      while (l < h) { const uint32_t mid = (l + h) >> 1; if (lib.d_idx_kmer[mid] < k_lo) l = mid + 1; else h = mid; }
+      p_lo[pi] = l;
+      h = hi0;
+      while (l < h) { const uint32_t mid = (l + h) >> 1; if (lib.d_idx_kmer[mid] <= k_hi) l = mid + 1; else h = mid; }
+      p_hi[pi] = l;
+      p_off[pi] = (uint32_t)a;
     }
   }
   uint64_t best = MIRGE_NO_HIT;
@@ -228,7 +184,7 @@ annotate_kernel(mirge_library lib, mirge_round_policy pol, mirge_table t, uint64
 #pragma unroll
   for (int i = 0; i < MAX_PIECES; ++i) total += p_hi[i] - p_lo[i];
   const bool big = active && !degenerate && total > COOP_MIN;
-  if (active && degenerate) {
+  if (degenerate) {
     // very short query: exhaustive scan keeps the result exact
     for (uint32_t r = 0; r < lib.n_refs; ++r) {
       const uint32_t lo = lib.d_ref_off[r], hi = lib.d_ref_off[r + 1];
@@ -247,33 +203,31 @@ annotate_kernel(mirge_library lib, mirge_round_policy pol, mirge_table t, uint64
         if (h < best) best = h;
       }
   }
-  // long candidate lists: the whole warp verifies them, one owner lane at a time
   unsigned todo = __ballot_sync(0xffffffffu, big);
   while (todo) {
     const int leader = __ffs(todo) - 1;
     todo &= todo - 1;
     if (lane == leader) {
-      const int nw = (L + 15) >> 4;
-      for (int w = 0; w < nw; ++w) { s_qw[warp][w] = qw[w]; s_qnx[warp][w] = qnx[w]; }
-      s_meta[warp][0] = (uint32_t)L;
-      s_meta[warp][1] = (uint32_t)R;
+      for (int w = 0; w < nw; ++w) { s_qw[w] = qw[w]; s_qnx[w] = qnx[w]; }
+      s_meta[0] = (uint32_t)L;
 #pragma unroll
       for (int pi = 0; pi < MAX_PIECES; ++pi) {
-        s_meta[warp][4 + 3 * pi] = p_lo[pi];
-        s_meta[warp][5 + 3 * pi] = p_hi[pi];
-        s_meta[warp][6 + 3 * pi] = p_off[pi];
+        s_meta[4 + 3 * pi] = p_lo[pi];
+        s_meta[5 + 3 * pi] = p_hi[pi];
+        s_meta[6 + 3 * pi] = p_off[pi];
       }
     }
     __syncwarp();
-    const int cL = (int)s_meta[warp][0], cR = (int)s_meta[warp][1];
+    const int cL = (int)s_meta[0];
+    const int cR = pol.seed_len == 0 ? cL : min(pol.seed_len, cL);
     uint64_t b = MIRGE_NO_HIT;
 #pragma unroll
     for (int pi = 0; pi < MAX_PIECES; ++pi) {
-      const uint32_t lo = s_meta[warp][4 + 3 * pi], hi = s_meta[warp][5 + 3 * pi], off = s_meta[warp][6 + 3 * pi];
+      const uint32_t lo = s_meta[4 + 3 * pi], hi = s_meta[5 + 3 * pi], off = s_meta[6 + 3 * pi];
       for (uint32_t e = lo + lane; e < hi; e += 32) {
         const uint32_t pos = lib.d_idx_pos[e];
         if (pos < off) continue;
-        const uint64_t h = verify(lib, s_qw[warp], s_qnx[warp], cL, pol, cR, pos - off, pos);
+        const uint64_t h = verify(lib, s_qw, s_qnx, cL, pol, cR, pos - off, pos);
         if (h < b) b = h;
       }
     }
@@ -285,27 +239,142 @@ annotate_kernel(mirge_library lib, mirge_round_policy pol, mirge_table t, uint64
     if (lane == leader) best = b;
     __syncwarp();
   }
-  if (active && best != MIRGE_NO_HIT) {
-    annot_round[id] = (uint8_t)pol.round;
-    hit[id] = best;
+  return best;
+}
+
+// All rounds of bwtAlign for one unique sequence per thread, in order; a sequence leaves at the first round
+// that hits it (manifoldAlign.py:120,129).  The key is read once and the query words are rebuilt only when
+// a round's window differs (poly-T stripping of round 3, -5/-3 trimming of round 8).
+__global__ void __launch_bounds__(ANN_THREADS)
+annotate_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_keys, uint8_t *__restrict__ annot_round,
+                uint64_t *__restrict__ hit) {
+  __shared__ uint32_t s_qw[ANN_THREADS / 32][QW_MAX], s_qnx[ANN_THREADS / 32][QW_MAX];
+  __shared__ uint32_t s_meta[ANN_THREADS / 32][4 + 3 * MAX_PIECES];
+  const uint64_t id = (uint64_t)blockIdx.x * ANN_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool in_range = id < n_keys;
+  uint32_t qw[QW_MAX], qnx[QW_MAX];
+  const uint32_t *key = nullptr, *pay = nullptr, *exc = nullptr;
+  int len = 0, nexc = 0, cur_qs = -1, cur_qe = -1, tlen = -1;
+  uint32_t state = 0xFF;  // round that annotated this sequence, 0xFF = none yet
+  if (in_range) {
+    key = t.d_arena + t.d_key_ref[id];
+    const uint32_t hdr = key[0];
+    len = (int)key_len(hdr);
+    nexc = (int)key_nexc(hdr);
+    pay = key + 1;
+    exc = key + 1 + ((len + 15) >> 4);
+    state = annot_round[id];
+  }
+  uint64_t my_hit = MIRGE_NO_HIT;
+  int my_round = -1;
+  for (int ri = 0; ri < rs.n; ++ri) {
+    const mirge_round_policy &pol = rs.pol[ri];
+    bool active = in_range;
+    if (active) {
+      if (pol.select == MIRGE_SELECT_LEN_LT26) active = len < 26;
+      else if (pol.select == MIRGE_SELECT_LEN_GT25) active = len > 25;
+      else active = state == 0xFF;
+    }
+    int L = 0;
+    if (active) {
+      // query window [qs, qe) of the key (manifoldAlign.py:118-126; -5/-3 of round 8)
+      int qs = 0, qe = len;
+      if (pol.strip_polyT) {
+        if (tlen < 0) {  // length without the trailing run of upper-case T
+          int tpos = len;
+          while (tpos > 0) {
+            const int j = tpos - 1;
+            if (((pay[j >> 4] >> (2 * (j & 15))) & 3u) != 3u) break;
+            bool is_exc = false;  // a lower-case 't' (or any non-"ACGT" byte) is stored as an exception
+            for (int x = 0; x < nexc; ++x) is_exc |= (int)(exc[x] >> 8) == j;
+            if (is_exc) break;
+            --tpos;
+          }
+          tlen = tpos;
+        }
+        if (len - tlen < 3) active = false;
+        qe = tlen;
+      }
+      qs += pol.trim5;
+      qe -= pol.trim3;
+      if (qe <= qs) active = false;
+      if (active) {
+        L = qe - qs;
+        if (qs != cur_qs || qe != cur_qe) {
+          const int nw = (L + 15) >> 4, npay = (len + 15) >> 4;
+          for (int w = 0; w < nw; ++w) {
+            const int p = qs + 16 * w, wi = p >> 4, sh = 2 * (p & 15);
+            const uint32_t lo = pay[wi], hi = (wi + 1 < npay) ? pay[wi + 1] : 0u;
+            uint32_t v = sh ? __funnelshift_r(lo, hi, sh) : lo;
+            const int rem = L - 16 * w;
+            if (rem < 16) v &= (1u << (2 * rem)) - 1u;
+            qw[w] = v;
+            qnx[w] = 0;
+          }
+          for (int x = 0; x < nexc; ++x) {
+            const int pos = (int)(exc[x] >> 8) - qs;
+            if (pos < 0 || pos >= L) continue;
+            const uint32_t code = base_code_upper(exc[x] & 0xFFu);
+            const int w = pos >> 4, sh = 2 * (pos & 15);
+            if (code < 4u) qw[w] = (qw[w] & ~(3u << sh)) | (code << sh);
+            else qnx[w] |= 1u << sh;
+          }
+          cur_qs = qs;
+          cur_qe = qe;
+        }
+      }
+    }
+    const uint64_t best = search_round(rs.lib[ri], pol, active, qw, qnx, L, nexc > 0, s_qw[warp], s_qnx[warp], s_meta[warp], lane);
+    if (active && best != MIRGE_NO_HIT) {
+      state = (uint32_t)pol.round;
+      my_round = pol.round;
+      my_hit = best;
+    }
+  }
+  if (my_round >= 0) {
+    annot_round[id] = (uint8_t)my_round;
+    hit[id] = my_hit;
   }
 }
 
-extern "C" int mirge_annotate_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_round_policy *policy, const mirge_table *t,
-                                    uint64_t n_keys, uint8_t *d_annot_round, uint64_t *d_hit, void *stream_) {
-  if (!ctx) return MIRGE_ERR_ARG;
-  if (!lib || !policy || !t || !d_annot_round || !d_hit) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: null argument");
-  if (n_keys == 0 || lib->n_refs == 0 || lib->n_bases == 0) return MIRGE_OK;
+static int check_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_round_policy *policy) {
   if (!lib->d_packed || !lib->d_nmask || !lib->d_ref_off || !lib->d_idx_kmer || !lib->d_idx_pos || !lib->d_idx_bucket)
     MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: library has no index");
   if (lib->bucket_bits < 1 || lib->bucket_bits > 28) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: bucket_bits out of range");
   if (policy->seed_mm < 0 || policy->seed_mm > 3 || policy->total_mm < policy->seed_mm || policy->trim5 < 0 || policy->trim3 < 0)
     MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: unsupported policy");
   if (lib->n_refs >= (1u << 28)) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: too many references");
+  return MIRGE_OK;
+}
+
+extern "C" int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, const mirge_round_policy *policies, int n_rounds,
+                                     const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round, uint64_t *d_hit, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  if (!libs || !policies || !t || !d_annot_round || !d_hit) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: null argument");
+  if (n_rounds < 0 || n_rounds > MAX_ROUNDS) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: at most %d rounds per call", MAX_ROUNDS);
+  if (n_keys == 0 || n_rounds == 0) return MIRGE_OK;
+  RoundSet rs;
+  rs.n = 0;
+  for (int i = 0; i < n_rounds; ++i) {
+    if (libs[i].n_refs == 0 || libs[i].n_bases == 0) continue;  // empty library: nothing can hit
+    int rc = check_round(ctx, &libs[i], &policies[i]);
+    if (rc) return rc;
+    rs.lib[rs.n] = libs[i];
+    rs.pol[rs.n] = policies[i];
+    ++rs.n;
+  }
+  if (rs.n == 0) return MIRGE_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
-  annotate_kernel<<<(unsigned)((n_keys + ANN_THREADS - 1) / ANN_THREADS), ANN_THREADS, 0, stream>>>(*lib, *policy, *t, n_keys,
-                                                                                                   d_annot_round, d_hit);
+  annotate_kernel<<<(unsigned)((n_keys + ANN_THREADS - 1) / ANN_THREADS), ANN_THREADS, 0, stream>>>(rs, *t, n_keys, d_annot_round, d_hit);
   MIRGE_LAUNCH_CHECK(ctx, "annotate_kernel");
   return MIRGE_OK;
+}
+
+extern "C" int mirge_annotate_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_round_policy *policy, const mirge_table *t,
+                                    uint64_t n_keys, uint8_t *d_annot_round, uint64_t *d_hit, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  if (!lib || !policy) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: null argument");
+  return mirge_annotate_rounds(ctx, lib, policy, 1, t, n_keys, d_annot_round, d_hit, stream_);
 }

@@ -75,7 +75,7 @@ class KeySet:
         return cls(dev, arena, key_off, n)
 
 
-def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = False):
+def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = False, fused: bool = True):
     """Run rounds 0..8 (0..9 with spike-ins) in miRge's order (manifoldAlign.py:86-135).
     Returns device tensors (annot_round uint8[n] with 0xFF = unannotated, hit int64[n])."""
     n = keys.n
@@ -84,7 +84,17 @@ def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = 
     if n == 0:
         return annot[:0], hit[:0]
     pols = round_policies()
-    for rnd in range(10 if spike_in else 9):
+    n_rounds = 10 if spike_in else 9
+    if fused:
+        # all rounds in one launch: every key is read once and leaves at the first round that hits it
+        lib_arr = (abi.Library * n_rounds)(*[libs[ROUND_LIBS[r]].struct for r in range(n_rounds)])
+        pol_arr = (abi.RoundPolicy * n_rounds)(*pols[:n_rounds])
+        with dev.timed("annotate"):
+            dev.check(dev.lib.mirge_annotate_rounds(dev.ctx, lib_arr, pol_arr, n_rounds, C.byref(keys.struct), n,
+                                                    _ptr(annot), _ptr(hit), dev.stream()))
+        dev.launches += 1
+        return annot[:n], hit[:n]
+    for rnd in range(n_rounds):
         lib = libs[ROUND_LIBS[rnd]]
         with dev.timed("annotate_r%d" % rnd):
             dev.check(dev.lib.mirge_annotate_round(dev.ctx, C.byref(lib.struct), C.byref(pols[rnd]), C.byref(keys.struct), n,
