@@ -205,6 +205,11 @@ int mirge_table_reset(mirge_ctx *ctx, const mirge_table *t, void *stream);
 int mirge_collapse_insert(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_keys,
                           const uint32_t *d_key_off, uint64_t n_slots, uint32_t *d_deferred,
                           void *stream);
+/* The same when the trim kernel wrote the keys straight into the table's arena (mirge_trim called with
+ * d_keys = t->d_arena and d_trim_ctrl[0] preset to the arena words in use): the first occurrence of a key
+ * becomes the table's copy, nothing is moved.  d_key_off holds arena word offsets. */
+int mirge_collapse_insert_inplace(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_key_off,
+                                  uint64_t n_slots, uint32_t *d_deferred, void *stream);
 /* Merge (key, count) records: d_rec = [count][key words...] back to back, d_rec_off[i] = word
  * offset of record i.  Used by the owner side of the hash-partitioned exchange. */
 int mirge_collapse_merge(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_rec,

@@ -116,6 +116,7 @@ SYMBOLS = {
     "mirge_trim_mode": (C.c_int, [_P, C.c_int]),
     "mirge_table_reset": (C.c_int, [_P, C.POINTER(Table), _P]),
     "mirge_collapse_insert": (C.c_int, [_P, C.POINTER(Table), _P, _P, _U64, _P, _P]),
+    "mirge_collapse_insert_inplace": (C.c_int, [_P, C.POINTER(Table), _P, _U64, _P, _P]),
     "mirge_collapse_merge": (C.c_int, [_P, C.POINTER(Table), _P, _P, _U64, _P, _P]),
     "mirge_table_rehash": (C.c_int, [_P, C.POINTER(Table), C.POINTER(Table), _P]),
     "mirge_table_check_sync":(C.c_int, [_P, C.POINTER(Table), _PU64, _PU64, _P]),

@@ -34,48 +34,62 @@ __device__ __forceinline__ uint64_t hash_key(const uint32_t *key, uint32_t nw) {
 
 enum { INS_OK = 0, INS_DEFER = 1, INS_FAIL = 2 };
 
+#define NOT_IN_ARENA 0xFFFFFFFFu
+
 // completeDict[key] += add.  `unbounded`: keep polling an unpublished slot (retry kernel only).
+// in_arena: word offset of the key when it already lives in the table's arena (the trim kernel wrote it
+// there): the owner then publishes that offset instead of allocating and copying.
 __device__ __forceinline__ int table_insert(const mirge_table &t, const uint32_t *key, uint32_t nw, uint32_t add,
-                                            uint64_t h, bool unbounded) {
+                                            uint64_t h, bool unbounded, uint32_t in_arena) {
   unsigned long long *ctrl = (unsigned long long *)t.d_ctrl;
   const uint64_t mask = t.capacity - 1;
   uint32_t tag = (uint32_t)(h >> 32);
   if (tag == 0) tag = 1;
   uint64_t idx = h & mask;
   const uint64_t max_probe = t.capacity < MAX_PROBES ? t.capacity : MAX_PROBES;
+  const unsigned lane = threadIdx.x & 31;
   for (uint64_t probe = 0; probe < max_probe; ++probe) {
     mirge_slot *s = t.d_slots + idx;
     uint4 v = ld_volatile_u4(s);
     if (v.x == 0) {
       const uint32_t old = atomicCAS(&s->tag, 0u, tag);
       if (old == 0) {
-        // owner: allocate id + arena space (aggregated over the lanes that are here together)
-        cg::coalesced_group g = cg::coalesced_threads();
-        uint32_t pre = nw;
-        for (int d = 1; d < (int)g.size(); d <<= 1) {
-          uint32_t x = g.shfl_up(pre, d);
-          if ((int)g.thread_rank() >= d) pre += x;
+        // owner: dense id (and arena space unless the key is in place), one atomic for the lanes that
+        // claimed a slot together
+        const unsigned grp = __activemask();
+        const int leader = __ffs(grp) - 1;
+        const unsigned rank = __popc(grp & ((1u << lane) - 1u));
+        unsigned long long base_id = 0, base_w = 0;
+        uint32_t pre = 0, total = 0;
+        if (in_arena == NOT_IN_ARENA) {
+          for (unsigned m = grp; m; m &= m - 1) {  // exclusive prefix of the key sizes over the group
+            const int src = __ffs(m) - 1;
+            const uint32_t x = __shfl_sync(grp, nw, src);
+            if ((unsigned)src < lane) pre += x;
+            total += x;
+          }
         }
-        const uint32_t total = g.shfl(pre, g.size() - 1);
-        unsigned long long base_w = 0, base_id = 0;
-        if (g.thread_rank() == 0) {
-          base_w = atomicAdd(ctrl + 0, (unsigned long long)total);
-          base_id = atomicAdd(ctrl + 1, (unsigned long long)g.size());
+        if ((int)lane == leader) {
+          base_id = atomicAdd(ctrl + 1, (unsigned long long)__popc(grp));
+          if (in_arena == NOT_IN_ARENA) base_w = atomicAdd(ctrl + 0, (unsigned long long)total);
         }
-        base_w = g.shfl(base_w, 0);
-        base_id = g.shfl(base_id, 0);
-        const unsigned long long aoff = base_w + pre - nw, id = base_id + g.thread_rank();
+        base_id = __shfl_sync(grp, base_id, leader);
+        base_w = __shfl_sync(grp, base_w, leader);
+        const unsigned long long id = base_id + rank;
+        const unsigned long long aoff = in_arena == NOT_IN_ARENA ? base_w + pre : (unsigned long long)in_arena;
         if (aoff + nw > t.arena_words || aoff + nw >= 0xFFFFFFF0ull || id >= t.max_keys) {
           atomicOr(ctrl + 2, id >= t.max_keys ? ERR_KEYS_FULL : ERR_ARENA_FULL);
           atomicExch(&s->ref, 0xFFFFFFFFu);  // poison: waiters give up immediately
           return INS_FAIL;
         }
-        uint32_t *dst = t.d_arena + aoff;
-        for (uint32_t i = 0; i < nw; ++i) dst[i] = key[i];
+        if (in_arena == NOT_IN_ARENA) {
+          uint32_t *dst = t.d_arena + aoff;
+          for (uint32_t i = 0; i < nw; ++i) dst[i] = key[i];
+        }
         t.d_key_ref[id] = (uint32_t)aoff;
         s->id = (uint32_t)id;
         atomicAdd(&s->count, add);
-        __threadfence();
+        __threadfence();  // release: key text, id and count are visible before ref
         atomicExch(&s->ref, (uint32_t)aoff + 1u);
         return INS_OK;
       }
@@ -95,7 +109,8 @@ __device__ __forceinline__ int table_insert(const mirge_table &t, const uint32_t
         }
       }
       if (ref == 0xFFFFFFFFu) return INS_FAIL;  // owner ran out of space (error already flagged)
-      __threadfence();
+      // the key address depends on ref, and the text is read from L2 (ld.cg), where the owner's
+      // release made it visible before ref: no fence needed on this side
       const uint32_t *k2 = t.d_arena + (ref - 1u);
       bool same = true;
       for (uint32_t i = 0; i < nw; ++i) {
@@ -113,21 +128,24 @@ __device__ __forceinline__ int table_insert(const mirge_table &t, const uint32_t
 }
 
 __device__ __forceinline__ void defer_item(unsigned long long *counter, uint32_t *list, uint32_t item) {
-  cg::coalesced_group g = cg::coalesced_threads();
+  const unsigned grp = __activemask(), lane = threadIdx.x & 31;
+  const int leader = __ffs(grp) - 1;
   unsigned long long base = 0;
-  if (g.thread_rank() == 0) base = atomicAdd(counter, (unsigned long long)g.size());
-  base = g.shfl(base, 0);
-  list[base + g.thread_rank()] = item;
+  if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(grp));
+  base = __shfl_sync(grp, base, leader);
+  list[base + __popc(grp & ((1u << lane) - 1u))] = item;
 }
 
 // mode 0: items are emission slots (keys/key_off, add = 1)
 // mode 1: items are exchange records [count][key...] at rec_off[i]
+// mode 2: emission slots whose keys the trim kernel wrote straight into the table's arena (keys == arena)
 __device__ __forceinline__ void item_key(int mode, const uint32_t *keys, const uint32_t *off, uint64_t i,
-                                         const uint32_t *&key, uint32_t &add) {
+                                         const uint32_t *&key, uint32_t &add, uint32_t &in_arena) {
   const uint32_t o = off[i];
+  in_arena = NOT_IN_ARENA;
   if (o == 0xFFFFFFFFu) { key = nullptr; add = 0; return; }
-  if (mode == 0) { key = keys + o; add = 1; }
-  else { key = keys + o + 1; add = keys[o]; }
+  if (mode == 1) { key = keys + o + 1; add = keys[o]; }
+  else { key = keys + o; add = 1; if (mode == 2) in_arena = o; }
 }
 
 __global__ void __launch_bounds__(COL_THREADS)
@@ -135,12 +153,12 @@ collapse_insert_kernel(mirge_table t, const uint32_t *__restrict__ keys, const u
                        int mode, uint32_t *__restrict__ deferred) {
   const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
   if (i >= n) return;
-  const uint32_t *key; uint32_t add;
-  item_key(mode, keys, off, i, key, add);
+  const uint32_t *key; uint32_t add, in_arena;
+  item_key(mode, keys, off, i, key, add, in_arena);
   if (!key || add == 0) return;
   const uint32_t nw = key_words(key[0]);
   const uint64_t h = hash_key(key, nw);
-  if (table_insert(t, key, nw, add, h, false) == INS_DEFER)
+  if (table_insert(t, key, nw, add, h, false, in_arena) == INS_DEFER)
     defer_item((unsigned long long *)t.d_ctrl + 3, deferred, (uint32_t)i);
 }
 
@@ -154,11 +172,11 @@ collapse_retry_kernel(mirge_table t, const uint32_t *__restrict__ keys, const ui
   const uint64_t nwarps = ((uint64_t)gridDim.x * COL_THREADS) >> 5;
   for (uint64_t j = warp; j < nd; j += nwarps) {
     const uint64_t i = deferred[j];
-    const uint32_t *key; uint32_t add;
-    item_key(mode, keys, off, i, key, add);
+    const uint32_t *key; uint32_t add, in_arena;
+    item_key(mode, keys, off, i, key, add, in_arena);
     if (!key) continue;
     const uint32_t nw = key_words(key[0]);
-    table_insert(t, key, nw, add, hash_key(key, nw), true);
+    table_insert(t, key, nw, add, hash_key(key, nw), true, in_arena);
   }
 }
 
@@ -204,6 +222,13 @@ extern "C" int mirge_collapse_insert(mirge_ctx *ctx, const mirge_table *t, const
                                      uint64_t n_slots, uint32_t *d_deferred, void *stream) {
   if (!ctx) return MIRGE_ERR_ARG;
   return run_insert(ctx, t, d_keys, d_key_off, n_slots, 0, d_deferred, (cudaStream_t)stream);
+}
+
+extern "C" int mirge_collapse_insert_inplace(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_key_off, uint64_t n_slots,
+                                             uint32_t *d_deferred, void *stream) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  if (!t) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "collapse: null table");
+  return run_insert(ctx, t, t->d_arena, d_key_off, n_slots, 2, d_deferred, (cudaStream_t)stream);
 }
 
 extern "C" int mirge_collapse_merge(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_rec, const uint32_t *d_rec_off,
@@ -278,10 +303,11 @@ drain_kernel(mirge_table t, uint32_t *__restrict__ ids, uint32_t *__restrict__ c
   mirge_slot *s = t.d_slots + i;
   const uint4 v = *(const uint4 *)s;
   if (v.x == 0 || v.w == 0) return;
-  cg::coalesced_group g = cg::coalesced_threads();
+  const unsigned grp = __activemask(), lane = threadIdx.x & 31;
+  const int leader = __ffs(grp) - 1;
   unsigned long long base = 0;
-  if (g.thread_rank() == 0) base = atomicAdd(n_out, (unsigned long long)g.size());
-  base = g.shfl(base, 0) + g.thread_rank();
+  if ((int)lane == leader) base = atomicAdd(n_out, (unsigned long long)__popc(grp));
+  base = __shfl_sync(grp, base, leader) + __popc(grp & ((1u << lane) - 1u));
   if (base < cap) {
     ids[base] = v.z;
     counts[base] = v.w;
@@ -361,7 +387,7 @@ umi_collapse_kernel(mirge_table first, const uint32_t *__restrict__ ids, const u
     if (cl < min_len) continue;
     const uint32_t nw = slice_key(key, f, b, buf);
     const uint32_t add = dedup ? 1u : counts[item];
-    const int rc = table_insert(second, buf, nw, add, hash_key(buf, nw), retry != 0);
+    const int rc = table_insert(second, buf, nw, add, hash_key(buf, nw), retry != 0, NOT_IN_ARENA);
     if (rc == INS_DEFER) defer_item(ctrl2 + 3, deferred, (uint32_t)item);
   }
 }

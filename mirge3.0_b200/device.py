@@ -230,6 +230,7 @@ class BatchResult:
     win: Optional[torch.Tensor] = None
     key_off: Optional[torch.Tensor] = None
     keys: Optional[torch.Tensor] = None
+    in_place: bool = False  # keys were written straight into the collapse table's arena
 
 
 class DigestEngine:
@@ -247,9 +248,11 @@ class DigestEngine:
         self.dev.check(self.dev.lib.mirge_trim_mode(self.dev.ctx, int(mode)))
         self.trim_mode = int(mode)
 
-    def trim_batch(self, buf: torch.Tensor, nbytes: int, is_final: bool, keep: bool = True) -> BatchResult:
+    def trim_batch(self, buf: torch.Tensor, nbytes: int, is_final: bool, keep: bool = True,
+                   table: Optional["CollapseTable"] = None) -> BatchResult:
         """Run the tokeniser and the trim kernel on buf[:nbytes] (uint8, device).  Returns the device
-        arrays the collapse consumes (and the parity tests read)."""
+        arrays the collapse consumes (and the parity tests read).  With ``table`` the packed keys are
+        written straight into that table's arena (zero-copy collapse); otherwise into a batch buffer."""
         d, lib, E = self.dev, self.dev.lib, self.E
         if nbytes == 0:
             return BatchResult(0, 0, 0, 0)
@@ -273,15 +276,26 @@ class DigestEngine:
         key_off = d.empty(n * E, torch.int32)
         cap = E * (2 * n + used // 24) + 4096
         mode = self.trim_mode
+        base_words = 0
+        if table is not None:
+            table.check()
+            base_words = table.arena_used
         for attempt in range(4):
-            keys = d.empty(cap, torch.int32)
             ctrl = d.zeros(8, torch.int64)
+            if table is not None:
+                table.reserve(0, cap)  # room in the arena for this batch's keys
+                keys = table.arena
+                ctrl[0] = base_words
+                cap_abs = int(table.arena.numel())
+            else:
+                keys = d.empty(cap, torch.int32)
+                cap_abs = cap
             if mode != self.trim_mode:
                 d.check(lib.mirge_trim_mode(d.ctx, mode))
             try:
                 with d.timed("trim"):
                     d.check(lib.mirge_trim(d.ctx, _ptr(buf), used, _ptr(line_start), n, _ptr(win), _ptr(key_off),
-                                           _ptr(keys), cap, _ptr(ctrl), st))
+                                           _ptr(keys), cap_abs, _ptr(ctrl), st))
             finally:
                 if mode != self.trim_mode:
                     d.check(lib.mirge_trim_mode(d.ctx, self.trim_mode))
@@ -305,6 +319,11 @@ class DigestEngine:
                 cap = E * (n + used // 2 + used // 32 + 64) + 4096  # worst case: every base an exception
                 continue
             break
+        if table is not None:
+            table.arena_used = int(c[0])
+            table.ctrl[0] = table.arena_used  # the table's own counter of arena words in use
+            return BatchResult(n, used, int(c[1]), int(c[0]) - base_words, line_start if keep else None,
+                               win if keep else None, key_off, None, True)
         return BatchResult(n, used, int(c[1]), int(c[0]), line_start if keep else None, win if keep else None,
                            key_off, keys)
 
@@ -313,13 +332,19 @@ class DigestEngine:
         if br.n_records == 0 or br.n_emitted == 0:
             return
         d, lib = self.dev, self.dev.lib
-        table.check()
-        table.reserve(br.n_emitted, br.key_words)
         n_slots = br.n_records * self.E
         deferred = d.empty(n_slots, torch.int32)
-        with d.timed("collapse"):
-            d.check(lib.mirge_collapse_insert(d.ctx, C.byref(table.struct), _ptr(br.keys), _ptr(br.key_off), n_slots,
-                                              _ptr(deferred), d.stream()))
+        if br.in_place:
+            table.reserve(br.n_emitted, 0)
+            with d.timed("collapse"):
+                d.check(lib.mirge_collapse_insert_inplace(d.ctx, C.byref(table.struct), _ptr(br.key_off), n_slots,
+                                                          _ptr(deferred), d.stream()))
+        else:
+            table.check()
+            table.reserve(br.n_emitted, br.key_words)
+            with d.timed("collapse"):
+                d.check(lib.mirge_collapse_insert(d.ctx, C.byref(table.struct), _ptr(br.keys), _ptr(br.key_off), n_slots,
+                                                  _ptr(deferred), d.stream()))
         d.launches += 3
         table.check()
 
@@ -332,7 +357,7 @@ class DigestEngine:
             end = min(total, pos + batch_bytes)
             final = end == total
             view = buf[pos:end]
-            br = self.trim_batch(view, end - pos, final, keep=False)
+            br = self.trim_batch(view, end - pos, final, keep=False, table=table)
             if br.n_records == 0 and not final:
                 if end - pos >= batch_bytes and batch_bytes >= (1 << 20):
                     raise FastqFormatError("FASTQ record does not fit into a batch")

@@ -108,7 +108,7 @@ class HostStreamer:
             nbytes = leftover + filled
             nxt = next(it, None)  # host-side read of the next piece overlaps the work queued below
             final = nxt is None
-            br = eng.trim_batch(dbuf, nbytes, final, keep=False)
+            br = eng.trim_batch(dbuf, nbytes, final, keep=False, table=table)
             if not final:
                 tail = nbytes - br.consumed
                 if tail > self.cap - self.batch:
