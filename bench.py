@@ -252,6 +252,8 @@ def run_b200(args):
     barrier()
     dev.timing = True
     dev.timer_totals()
+    for k_ in eng.stats:
+        eng.stats[k_] = 0
     launches0 = dev.launches
     clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -263,6 +265,7 @@ def run_b200(args):
     ms = e0.elapsed_time(e1) / max(args.steps, 1)
     timers = dev.timer_totals()
     dev.timing = False
+    stats = dict(eng.stats)
     launches = (dev.launches - launches0) // max(args.steps, 1)
     clk = clocks.stop() if clocks else None
     tms = torch.tensor([ms], device=dev.tdev, dtype=torch.float64)
@@ -353,6 +356,12 @@ def run_b200(args):
     trim_gbs = args.reads * b_trim / (trim_ms / 1e3) / 1e9 if trim_ms else 0.0
     kinfo.setdefault("trim", {})["achieved_gbs"] = round(trim_gbs, 1)
     kinfo["trim"]["frac_hbm"] = round(trim_gbs / peak, 4)
+    # collapse: every emitted key is read once and probes/updates one slot: sum over keys of (2K + 16) bytes
+    b_col_total = (2 * 4 * stats["key_words"] + 16 * stats["emitted"]) / steps
+    col_gbs = b_col_total / (col_ms / 1e3) / 1e9 if col_ms else 0.0
+    kinfo.setdefault("collapse", {})["achieved_gbs"] = round(col_gbs, 1)
+    kinfo["collapse"]["frac_hbm"] = round(col_gbs / peak, 4)
+    kinfo["collapse"]["algorithmic_bytes_per_read"] = round(b_col_total / args.reads, 1)
     dom = max((("trim", trim_ms), ("collapse", col_ms), ("annotate", ann_ms)), key=lambda kv: kv[1])[0]
     roofline = {"kernel": "trim_kernel", "bound": "hbm", "achieved": round(trim_gbs, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(trim_gbs / peak, 4), "traffic": None, "peak_source": peak_src,

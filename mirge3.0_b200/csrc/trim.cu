@@ -375,6 +375,13 @@ __device__ __forceinline__ bool traceback_cost1(const int a, const FastCtx &fc, 
   return true;
 }
 
+// A cell (i, j) of cost c reaches i matches only if every error is a deletion; that path leaves row 0 at
+// column j - i - c with a match, so adapter[0] must equal that read base (cheap necessary condition).
+__device__ __forceinline__ bool all_deletions_possible(const uint32_t *eqt, const uint8_t *read, int i, int j, int c) {
+  const int o = j - i - c;
+  return o >= 0 && (eqt[read[o]] & 1u);
+}
+
 // candidate with at most `u` matches, cost c, scan index idx can still beat the best so far
 #define MAY_WIN(u, c, idx) (!have || (u) > b_m || ((u) == b_m && ((c) < b_c || ((c) == b_c && (idx) < b_idx))))
 #define TAKE_IF_BETTER(mt, c, org, idx)                                                      \
@@ -418,7 +425,9 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
     if (which_ < 0) break;                                                                       \
     if (which_ == 0) q0 = 0; else if (which_ == 1) q1 = 0; else if (which_ == 2) q2 = 0; else q3 = 0; \
     const int jc_ = Q_COL(v_), cc_ = Q_COST(v_);                                                 \
-    if (MAY_WIN(Q_UB(v_, m), cc_, jc_)) {                                                        \
+    int ub_ = Q_UB(v_, m);                                                                       \
+    if (ub_ == m && !all_deletions_possible(eqt, read, m, jc_, cc_)) ub_ = m - 1;               \
+    if (MAY_WIN(ub_, cc_, jc_)) {                                                                \
       int mt_, org_;                                                                             \
       if (!(cc_ == 1 && traceback_cost1(a, fc, m, jc_, mt_, org_))) {                            \
         recompute(eqt, read, jc_, span, cb);                                                     \
@@ -519,7 +528,8 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
       rowmask &= ~(1u << (i - 1));
       const int ci = cell_cost(vp, vn, i);
       const int idx = (i == m) ? n : n + 1 + i;
-      const int ub = ((rowub >> (i - 1)) & 1u) ? i : i - 1;
+      int ub = ((rowub >> (i - 1)) & 1u) ? i : i - 1;
+      if (ub == i && !all_deletions_possible(eqt, read, i, n, ci)) ub = i - 1;
       if (MAY_WIN(ub, ci, idx)) {
         int mt, org;
         if (!(ci == 1 && traceback_cost1(a, fc, i, n, mt, org))) {

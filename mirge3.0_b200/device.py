@@ -243,6 +243,7 @@ class DigestEngine:
         self.E = dev.slots
         self.trim_mode = 0  # 0 = automatic kernel choice, 1 = always the generic full-DP kernel
         dev.check(dev.lib.mirge_trim_mode(dev.ctx, 0))
+        self.stats = {"records": 0, "bytes": 0, "emitted": 0, "key_words": 0}  # running totals (bench.py rooflines)
 
     def set_trim_mode(self, mode: int):
         self.dev.check(self.dev.lib.mirge_trim_mode(self.dev.ctx, int(mode)))
@@ -329,6 +330,11 @@ class DigestEngine:
 
     def collapse_batch(self, table: CollapseTable, br: BatchResult):
         """completeDict[key] += 1 for every key the trim kernel emitted."""
+        st_ = self.stats
+        st_["records"] += br.n_records
+        st_["bytes"] += br.consumed
+        st_["emitted"] += br.n_emitted
+        st_["key_words"] += br.key_words
         if br.n_records == 0 or br.n_emitted == 0:
             return
         d, lib = self.dev, self.dev.lib
