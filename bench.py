@@ -363,8 +363,16 @@ def run_b200(args):
     kinfo["collapse"]["frac_hbm"] = round(col_gbs / peak, 4)
     kinfo["collapse"]["algorithmic_bytes_per_read"] = round(b_col_total / args.reads, 1)
     dom = max((("trim", trim_ms), ("collapse", col_ms), ("annotate", ann_ms)), key=lambda kv: kv[1])[0]
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["trim_kernel"]
+        traffic = int(tr["bytes_per_read"] * args.reads / max(kinfo["trim"].get("launches_per_step", 1), 1))
+    except Exception:
+        pass
     roofline = {"kernel": "trim_kernel", "bound": "hbm", "achieved": round(trim_gbs, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(trim_gbs / peak, 4), "traffic": None, "peak_source": peak_src,
+                "frac": round(trim_gbs / peak, 4), "traffic": traffic,
+                "traffic_source": "ncu dram bytes per read (profiles/r1_traffic.json) x reads per launch",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_read": round(b_trim, 1), "dominant_by_time": dom,
                 "launches_per_step": kinfo["trim"].get("launches_per_step")}
 
