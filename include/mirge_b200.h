@@ -188,10 +188,13 @@ int mirge_line_index(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, co
  *   d_key_off[e]    = word offset of the packed key in d_keys, or 0xFFFFFFFF when the slot is not
  *                     counted (length filter, digest.py:348,362,368).
  * d_trim_ctrl (8 x u64, zeroed by the caller): [0] key words used [1] emitted keys [2] error flags
- * [3] first malformed record. */
+ * [3] first malformed record, [5] reads deferred to the second pass.
+ * d_slow: u32[n_records] scratch.  The bit-parallel kernel runs in two passes: the first resolves every
+ * read whose adapter search needs no cost columns, the second re-does the rest (a few percent) with
+ * full warps. */
 int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, const uint32_t *d_line_start,
                uint64_t n_records, uint16_t *d_win, uint32_t *d_key_off, uint32_t *d_keys,
-               uint64_t keys_capacity_words, uint64_t *d_trim_ctrl, void *stream);
+               uint64_t keys_capacity_words, uint64_t *d_trim_ctrl, uint32_t *d_slow, void *stream);
 
 /* Kernel selection for mirge_trim: 0 = automatic (bit-parallel kernel when every adapter is a 3'
  * adapter with indels and <= 32 nt, else the generic full-DP kernel), 1 = always generic.  When the

@@ -393,7 +393,12 @@ __device__ __forceinline__ bool all_deletions_possible(const uint32_t *eqt, cons
 #define Q_COST(v) ((int)(((v) >> 16) & 0xFFu))
 #define Q_UB(v, m) ((((v) >> 24) & 1u) ? (m) : (m)-1)
 
-__device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, const int n, const FastCtx &fc, Match &out) {
+// DEFER (first pass of the two-pass scheme): as soon as a candidate would need cost columns (recompute +
+// general traceback) the search gives up with 2 and the read is queued for the second pass, which runs
+// this function without DEFER on a compacted list, so that the rare expensive path executes with full warps.
+// Returns 0 = no match, 1 = match in `out`, 2 = deferred.
+template <bool DEFER>
+__device__ __forceinline__ int locate_fast(const int a, const uint8_t *read, const int n, const FastCtx &fc, Match &out) {
   const unsigned lanes = __activemask();  // lanes searching together; re-converged after the divergent loops
   const DevAdapter &ad = c_p.ad[a];
   const int m = ad.m;
@@ -410,7 +415,7 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
   // row-m candidates wait here until the column loop is over (0 = empty slot)
   uint32_t q0 = 0, q1 = 0, q2 = 0, q3 = 0;
   // a new candidate waits one column: the next column may prove it dominated
-  bool pend = false, pend_ins = false;
+  bool pend = false, pend_ins = false, need_slow = false;
   uint32_t pend_v = 0;
 
 // trace the queued candidates best-first (lowest cost, then leftmost), skipping those that cannot win
@@ -430,6 +435,7 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
     if (MAY_WIN(ub_, cc_, jc_)) {                                                                \
       int mt_, org_;                                                                             \
       if (!(cc_ == 1 && traceback_cost1(a, fc, m, jc_, mt_, org_))) {                            \
+        if (DEFER) { need_slow = true; break; }                                                  \
         recompute(eqt, read, jc_, span, cb);                                                     \
         traceback(a, eqt, read, fc, cb, m, jc_, cc_, mt_, org_);                                 \
       }                                                                                          \
@@ -457,6 +463,7 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
         else if (!q3) q3 = pend_v;
         else {  // queue full (low-complexity read): resolve what is queued, then go on
           FLUSH_QUEUE()
+          if (DEFER && need_slow) break;
           q0 = pend_v;
         }
       }
@@ -490,8 +497,8 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
     }
   }
   __syncwarp(lanes);
-  const unsigned scan_lanes = __ballot_sync(lanes, !stopped);
-  if (!stopped) {
+  const unsigned scan_lanes = __ballot_sync(lanes, !stopped && !need_slow);
+  if (!stopped && !need_slow) {
     // last column: rows with cost 0 are pure diagonals; the others wait in rowmask / rowub
     uint32_t rowmask = 0, rowub = 0;  // rowub bit: first step of that cell is a match (up to i matches), else i - 1
     int c = 0, cprev = 0;             // D[i][n], D[i][n-1]
@@ -533,6 +540,7 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
       if (MAY_WIN(ub, ci, idx)) {
         int mt, org;
         if (!(ci == 1 && traceback_cost1(a, fc, i, n, mt, org))) {
+          if (DEFER) { need_slow = true; break; }
           if (!have_cols) {
             recompute(eqt, read, n, span, cb);
             have_cols = true;
@@ -543,22 +551,26 @@ __device__ __forceinline__ bool locate_fast(const int a, const uint8_t *read, co
       }
     }
   }
-  if (!have) return false;
+  if (DEFER && need_slow) return 2;
+  if (!have) return 0;
   out.rstart = b_o;
   out.rstop = b_idx <= n ? b_idx : n;
   out.matches = b_m;
   out.errors = b_c;
-  return true;
+  return 1;
 }
 
 // AdapterCutter._best_match: most matches, then fewer errors, first adapter wins ties.
-template <int MAXM, bool FAST>
+// returns the index of the winning adapter, -1 for none, -2 when the search was deferred (DEFER only)
+template <int MAXM, bool FAST, bool DEFER>
 __device__ __noinline__ int best_match(const uint8_t *read, int n, Match &best, const FastCtx &fc) {
   int which = -1;
   for (int a = 0; a < c_p.n_adapters; ++a) {
     Match mt;
     if (FAST) {
-      if (!locate_fast(a, read, n, fc, mt)) continue;
+      const int rc = locate_fast<DEFER>(a, read, n, fc, mt);
+      if (rc == 2) return -2;
+      if (rc == 0) continue;
     } else if (!locate<MAXM>(a, read, n, mt)) continue;
     if (which < 0 || mt.matches > best.matches || (mt.matches == best.matches && mt.errors < best.errors)) {
       best = mt;
@@ -568,8 +580,9 @@ __device__ __noinline__ int best_match(const uint8_t *read, int n, Match &best, 
   return which;
 }
 
-template <int MAXM, bool FAST>
-__device__ __noinline__ void apply_mod(int mi, const uint8_t *seq, const uint8_t *qual, int &start, int &stop, FastCtx &fc) {
+// returns true when the adapter search was deferred to the second pass (DEFER only)
+template <int MAXM, bool FAST, bool DEFER>
+__device__ __noinline__ bool apply_mod(int mi, const uint8_t *seq, const uint8_t *qual, int &start, int &stop, FastCtx &fc) {
   const int len = stop - start;
   switch (c_p.kind[mi]) {
     case MIRGE_MOD_NEXTSEQ:
@@ -586,7 +599,8 @@ __device__ __noinline__ void apply_mod(int mi, const uint8_t *seq, const uint8_t
       for (int t = 0; t < c_p.times; ++t) {
         Match mt;
         fc.rbase = start;
-        const int a = best_match<MAXM, FAST>(seq + start, stop - start, mt, fc);
+        const int a = best_match<MAXM, FAST, DEFER>(seq + start, stop - start, mt, fc);
+        if (a == -2) return true;
         if (a < 0) break;
         if (c_p.ad[a].where == 0) stop = start + mt.rstart;
         else start = start + mt.rstop;
@@ -604,6 +618,7 @@ __device__ __noinline__ void apply_mod(int mi, const uint8_t *seq, const uint8_t
     }
     default: break;
   }
+  return false;
 }
 
 __device__ __forceinline__ int find_sub(const uint8_t *s, int n, const uint8_t *t, int tl, int from) {
@@ -622,55 +637,17 @@ __device__ __forceinline__ uint32_t key_byte(const uint8_t *seq, int start, int 
 
 #define PACK_WORDS 8  // reads up to 128 bases keep their 2-bit text in registers for key emission
 
-// FAST = bit-parallel adapter search (locate_fast) + register-resident key packing; requires the CTA's
-// span to be staged in shared memory, otherwise the batch is flagged (ctrl[2] bit 3) for the generic kernel.
-template <int MAXM, bool FAST>
-__global__ void __launch_bounds__(TRIM_THREADS)
-trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__restrict__ line_start, uint64_t n_records,
-            ushort4 *__restrict__ win, uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys, uint64_t keys_cap,
-            unsigned long long *__restrict__ ctrl, uint32_t smem_bytes, uint32_t ring_depth) {
-  extern __shared__ uint4 smem4[];
-  uint8_t *sbuf = (uint8_t *)smem4;
+// Everything a thread does for record r once its bytes are addressable through B (shared-memory staging or
+// the global stream).  PASS 0: single pass; PASS 1: first pass (reads whose adapter search needs cost
+// columns are appended to d_slow and emit nothing); PASS 2: second pass over those reads.
+template <int MAXM, bool FAST, int PASS>
+__device__ __forceinline__ void process_record(const bool valid, const uint64_t r, const uint8_t *B, uint64_t nbytes,
+                                               const uint32_t *__restrict__ line_start, ushort4 *__restrict__ win,
+                                               uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys, uint64_t keys_cap,
+                                               unsigned long long *__restrict__ ctrl, uint32_t *__restrict__ d_slow, FastCtx &fc,
+                                               uint32_t *ps_mine) {
   const int tid = threadIdx.x;
-  FastCtx fc;
-  fc.s_eq = nullptr; fc.ps = nullptr; fc.jump_ok = false; fc.rbase = 0;
-  uint32_t *ps_mine = nullptr;
-  if (FAST) {
-    // smem: [staging smem_bytes][eq tables n_adapters * 256 words][packed reads (PACK_WORDS + 2) * T words]
-    uint32_t *eq = (uint32_t *)(sbuf + smem_bytes);
-    for (int e = tid; e < c_p.n_adapters * 256; e += TRIM_THREADS) {
-      const uint32_t code = base_code_upper((uint32_t)(e & 255));
-      eq[e] = code < 4u ? (uint32_t)c_p.ad[e >> 8].peq[code] : 0u;
-    }
-    fc.s_eq = eq;
-    ps_mine = eq + c_p.n_adapters * 256 + tid;
-    fc.ps = ps_mine;
-  }
-  const uint64_t r0 = (uint64_t)blockIdx.x * TRIM_THREADS;
-  const uint64_t r = r0 + tid;
-  const bool valid = r < n_records;
-  const uint64_t r_end = min(r0 + (uint64_t)TRIM_THREADS, n_records);
-  const uint32_t span_lo = line_start[4 * r0];
-  const uint64_t span_hi = min((uint64_t)line_start[4 * r_end], nbytes);
-  const uint32_t alo = span_lo & ~15u;
-  const bool staged = (span_hi - alo) <= smem_bytes;
-  if (FAST && !staged) {  // uniform per CTA
-    if (tid == 0) atomicOr(ctrl + 2, 8ull);
-    return;
-  }
-  if (staged) {
-    for (uint64_t o = (uint64_t)tid * 16; alo + o < span_hi; o += TRIM_THREADS * 16) {
-      const uint64_t g = alo + o;
-      if (g + 16 <= nbytes) {
-        *(uint4 *)(sbuf + o) = ld_stream_u4(fq + g);
-      } else {
-        for (int b = 0; b < 16 && g + b < nbytes; ++b) sbuf[o + b] = fq[g + b];
-      }
-    }
-  }
-  __syncthreads();
-  const uint8_t *B = staged ? (const uint8_t *)(sbuf - alo) : fq;  // B[absolute stream offset]
-
+  bool is_slow = false;
   const int E = c_p.slots;
   // per-slot windows live in local memory (dynamic slot index keeps the code small)
   int w_start[MIRGE_MAX_MODS], w_stop[MIRGE_MAX_MODS], w_us[MIRGE_MAX_MODS], w_ue[MIRGE_MAX_MODS];
@@ -701,6 +678,7 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
         // 2-bit text of the whole read once, four bytes per step (SIMD-in-register), into shared memory:
         // used by the traceback jumps and by key emission
         fast_emit = sl <= 16 * PACK_WORDS;
+        if (PASS == 2 && (uint64_t)ls.y + 16 * ((sl + 15) >> 4) + 8 > nbytes) fast_emit = false;  // no over-read past the stream
         if (fast_emit) {
           const uint32_t *ap = (const uint32_t *)((uintptr_t)seq & ~(uintptr_t)3);
           const uint32_t bs = ((uint32_t)(uintptr_t)seq & 3u) * 8u;
@@ -738,7 +716,7 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
       if (c_p.umi_mode == MIRGE_UMI_QIAGEN) {
 #pragma unroll 1
         for (int mi = 0; mi < c_p.n_mods; ++mi) {
-          apply_mod<MAXM, FAST>(mi, seq, qual, start, stop, fc);
+          if (!is_slow) is_slow = apply_mod<MAXM, FAST, PASS == 1>(mi, seq, qual, start, stop, fc);
           __syncwarp(good_lanes);
         }
         const int tl = stop - start, U = c_p.umi3;
@@ -758,7 +736,7 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
       } else {
 #pragma unroll 1
         for (int mi = 0; mi < c_p.n_mods; ++mi) {
-          apply_mod<MAXM, FAST>(mi, seq, qual, start, stop, fc);
+          if (!is_slow) is_slow = apply_mod<MAXM, FAST, PASS == 1>(mi, seq, qual, start, stop, fc);
           __syncwarp(good_lanes);
           if (E != 1 || mi == c_p.n_mods - 1) {
             const int slot = (E == 1) ? 0 : mi;
@@ -767,6 +745,11 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
             w_start[slot] = start; w_stop[slot] = stop; w_words[slot] = ln >= c_p.min_len;
           }
         }
+      }
+      if (PASS == 1 && is_slow) {
+        // second pass will redo this read from scratch; emit nothing now
+#pragma unroll 1
+        for (int s = 0; s < E; ++s) { w_start[s] = w_stop[s] = w_us[s] = w_ue[s] = 0; w_words[s] = 0; }
       }
       // size of every kept key: header + payload + exceptions
 #pragma unroll 1
@@ -803,6 +786,15 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
   warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
   const bool overflow = warp_base + warp_total > keys_cap || warp_base + warp_total > 0xFFFFFFF0ull;
   if (overflow && lane == 0 && warp_total) atomicOr(ctrl + 2, 2ull);
+  if (PASS == 1) {  // queue the deferred reads for the second pass (one atomic per warp)
+    const unsigned sm_ = __ballot_sync(0xffffffffu, is_slow);
+    if (sm_) {
+      unsigned long long base = 0;
+      if (lane == __ffs(sm_) - 1) base = atomicAdd(ctrl + 5, (unsigned long long)__popc(sm_));
+      base = __shfl_sync(0xffffffffu, base, __ffs(sm_) - 1);
+      if (is_slow) d_slow[base + __popc(sm_ & ((1u << lane) - 1u))] = (uint32_t)r;
+    }
+  }
   if (!valid) return;
   uint32_t off = (uint32_t)warp_base + inc - my_words;
 #pragma unroll 1
@@ -849,9 +841,75 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
   }
 }
 
+// FAST = bit-parallel adapter search (locate_fast) + packed-read key emission; requires the CTA's span to be
+// staged in shared memory, otherwise the batch is flagged (ctrl[2] bit 3) for the generic kernel.
+template <int MAXM, bool FAST, int PASS>
+__global__ void __launch_bounds__(TRIM_THREADS)
+trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__restrict__ line_start, uint64_t n_records,
+            ushort4 *__restrict__ win, uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys, uint64_t keys_cap,
+            unsigned long long *__restrict__ ctrl, uint32_t smem_bytes, uint32_t *__restrict__ d_slow) {
+  extern __shared__ uint4 smem4[];
+  uint8_t *sbuf = (uint8_t *)smem4;
+  const int tid = threadIdx.x;
+  FastCtx fc;
+  fc.s_eq = nullptr; fc.ps = nullptr; fc.jump_ok = false; fc.rbase = 0;
+  uint32_t *ps_mine = nullptr;
+  if (FAST) {
+    // smem: [staging smem_bytes][eq tables n_adapters * 256 words][packed reads (PACK_WORDS + 2) * T words]
+    uint32_t *eq = (uint32_t *)(sbuf + smem_bytes);
+    for (int e = tid; e < c_p.n_adapters * 256; e += TRIM_THREADS) {
+      const uint32_t code = base_code_upper((uint32_t)(e & 255));
+      eq[e] = code < 4u ? (uint32_t)c_p.ad[e >> 8].peq[code] : 0u;
+    }
+    fc.s_eq = eq;
+    ps_mine = eq + c_p.n_adapters * 256 + tid;
+    fc.ps = ps_mine;
+  }
+  if (PASS == 2) {
+    // second pass: the deferred reads, addressed in the global stream; whole warps iterate together
+    __syncthreads();
+    const unsigned long long n_slow = ctrl[5];
+    const uint64_t first = (uint64_t)blockIdx.x * TRIM_THREADS + (tid & ~31);
+    for (uint64_t base = first; base < n_slow; base += (uint64_t)gridDim.x * TRIM_THREADS) {
+      const uint64_t idx = base + (tid & 31);
+      const bool valid = idx < n_slow;
+      const uint64_t r = valid ? d_slow[idx] : 0;
+      fc.jump_ok = false;
+      process_record<MAXM, FAST, 2>(valid, r, fq, nbytes, line_start, win, key_off, keys, keys_cap, ctrl, d_slow, fc, ps_mine);
+      __syncwarp();
+    }
+    return;
+  }
+  const uint64_t r0 = (uint64_t)blockIdx.x * TRIM_THREADS;
+  const uint64_t r = r0 + tid;
+  const bool valid = r < n_records;
+  const uint64_t r_end = min(r0 + (uint64_t)TRIM_THREADS, n_records);
+  const uint32_t span_lo = line_start[4 * r0];
+  const uint64_t span_hi = min((uint64_t)line_start[4 * r_end], nbytes);
+  const uint32_t alo = span_lo & ~15u;
+  const bool staged = (span_hi - alo) <= smem_bytes;
+  if (FAST && !staged) {  // uniform per CTA
+    if (tid == 0) atomicOr(ctrl + 2, 8ull);
+    return;
+  }
+  if (staged) {
+    for (uint64_t o = (uint64_t)tid * 16; alo + o < span_hi; o += TRIM_THREADS * 16) {
+      const uint64_t g = alo + o;
+      if (g + 16 <= nbytes) {
+        *(uint4 *)(sbuf + o) = ld_stream_u4(fq + g);
+      } else {
+        for (int b = 0; b < 16 && g + b < nbytes; ++b) sbuf[o + b] = fq[g + b];
+      }
+    }
+  }
+  __syncthreads();
+  const uint8_t *B = staged ? (const uint8_t *)(sbuf - alo) : fq;  // B[absolute stream offset]
+  process_record<MAXM, FAST, PASS>(valid, r, B, nbytes, line_start, win, key_off, keys, keys_cap, ctrl, d_slow, fc, ps_mine);
+}
+
 extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, const uint32_t *d_line_start, uint64_t n_records,
                           uint16_t *d_win, uint32_t *d_key_off, uint32_t *d_keys, uint64_t keys_capacity_words,
-                          uint64_t *d_trim_ctrl, void *stream_) {
+                          uint64_t *d_trim_ctrl, uint32_t *d_slow, void *stream_) {
   if (!ctx) return MIRGE_ERR_ARG;
   if (!ctx->params_set) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: mirge_set_trim_params has not been called");
   if (n_records == 0) return MIRGE_OK;
@@ -875,23 +933,26 @@ extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbyte
   unsigned long long *ctrl = (unsigned long long *)d_trim_ctrl;
   ushort4 *win = (ushort4 *)d_win;
   if (ctx->fast_ok && ctx->trim_mode == 0) {
-    int ring = 4;
-    for (int a = 0; a < ctx->params.n_adapters; ++a) {
-      const int w = ctx->params.adapters[a].m + ctx->params.adapters[a].k + 3;
-      if (w > ring) ring = w;
-    }
-    const size_t total = (size_t)smem + (size_t)ctx->params.n_adapters * 1024 + (size_t)(PACK_WORDS + 2) * TRIM_THREADS * 4;
-    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    trim_kernel<32, true><<<grid, TRIM_THREADS, total, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
-                                                                 keys_capacity_words, ctrl, smem, (uint32_t)ring);
+    if (!d_slow) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: d_slow scratch (u32 per record) is required");
+    const size_t extra = (size_t)ctx->params.n_adapters * 1024 + (size_t)(PACK_WORDS + 2) * TRIM_THREADS * 4;
+    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    // pass 1: every read; adapter searches that need cost columns are deferred to the list d_slow
+    trim_kernel<32, true, 1><<<grid, TRIM_THREADS, smem + extra, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off,
+                                                                          d_keys, keys_capacity_words, ctrl, smem, d_slow);
+    MIRGE_LAUNCH_CHECK(ctx, "trim_kernel(pass 1)");
+    // pass 2: the deferred reads with full warps (count read on the device; grid-stride over the list)
+    unsigned grid2 = grid / 16 + 1;
+    if (grid2 > (unsigned)ctx->sm_count * 8) grid2 = (unsigned)ctx->sm_count * 8;
+    trim_kernel<32, true, 2><<<grid2, TRIM_THREADS, extra, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
+                                                                   keys_capacity_words, ctrl, 0u, d_slow);
   } else if (ctx->max_adapter_len <= 32) {
-    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    trim_kernel<32, false><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
-                                                                 keys_capacity_words, ctrl, smem, 0u);
+    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    trim_kernel<32, false, 0><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
+                                                                    keys_capacity_words, ctrl, smem, nullptr);
   } else {
-    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    trim_kernel<64, false><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
-                                                                 keys_capacity_words, ctrl, smem, 0u);
+    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<64, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    trim_kernel<64, false, 0><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
+                                                                    keys_capacity_words, ctrl, smem, nullptr);
   }
   MIRGE_LAUNCH_CHECK(ctx, "trim_kernel");
   return MIRGE_OK;

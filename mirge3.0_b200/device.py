@@ -275,6 +275,7 @@ class DigestEngine:
         d.launches += 2
         win = d.empty(n * E * 4, torch.int16)
         key_off = d.empty(n * E, torch.int32)
+        slow = d.empty(n, torch.int32)  # reads deferred to the second trim pass
         cap = E * (2 * n + used // 24) + 4096
         mode = self.trim_mode
         base_words = 0
@@ -296,11 +297,11 @@ class DigestEngine:
             try:
                 with d.timed("trim"):
                     d.check(lib.mirge_trim(d.ctx, _ptr(buf), used, _ptr(line_start), n, _ptr(win), _ptr(key_off),
-                                           _ptr(keys), cap_abs, _ptr(ctrl), st))
+                                           _ptr(keys), cap_abs, _ptr(ctrl), _ptr(slow), st))
             finally:
                 if mode != self.trim_mode:
                     d.check(lib.mirge_trim_mode(d.ctx, self.trim_mode))
-            d.launches += 1
+            d.launches += 2
             c = ctrl.cpu().numpy().view(np.uint64)
             flags = int(c[2])
             if flags & 8 and mode == 0:
