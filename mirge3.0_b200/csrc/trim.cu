@@ -844,7 +844,7 @@ __device__ __forceinline__ void process_record(const bool valid, const uint64_t 
 // FAST = bit-parallel adapter search (locate_fast) + packed-read key emission; requires the CTA's span to be
 // staged in shared memory, otherwise the batch is flagged (ctrl[2] bit 3) for the generic kernel.
 template <int MAXM, bool FAST, int PASS>
-__global__ void __launch_bounds__(TRIM_THREADS)
+__global__ void __launch_bounds__(TRIM_THREADS, (FAST && PASS == 1) ? 7 : 1)
 trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__restrict__ line_start, uint64_t n_records,
             ushort4 *__restrict__ win, uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys, uint64_t keys_cap,
             unsigned long long *__restrict__ ctrl, uint32_t smem_bytes, uint32_t *__restrict__ d_slow) {
@@ -889,6 +889,18 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
   const uint32_t alo = span_lo & ~15u;
   const bool staged = (span_hi - alo) <= smem_bytes;
   if (FAST && !staged) {  // uniform per CTA
+    if (PASS == 1) {
+      // this group's bytes do not fit the staging buffer: hand all of its reads to the second pass
+      const unsigned vm = __ballot_sync(0xffffffffu, valid);
+      if (vm) {
+        const int lane = tid & 31;
+        unsigned long long base = 0;
+        if (lane == __ffs(vm) - 1) base = atomicAdd(ctrl + 5, (unsigned long long)__popc(vm));
+        base = __shfl_sync(0xffffffffu, base, __ffs(vm) - 1);
+        if (valid) d_slow[base + __popc(vm & ((1u << lane) - 1u))] = (uint32_t)r;
+      }
+      return;
+    }
     if (tid == 0) atomicOr(ctrl + 2, 8ull);
     return;
   }
@@ -924,15 +936,18 @@ extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbyte
   cudaStream_t stream = (cudaStream_t)stream_;
   MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
   const uint64_t avg = (nbytes + n_records - 1) / n_records;
-  uint64_t want = avg * TRIM_THREADS * 5 / 4 + 64;
-  want = (want + 1023) & ~1023ull;
-  if (want < 8192) want = 8192;
+  const bool fast = ctx->fast_ok && ctx->trim_mode == 0;
+  // staging buffer: the bit-parallel kernel keeps it tight (7 CTAs per SM); a record group that does not fit
+  // is handed to its second pass.  The generic kernel reads such groups straight from global memory.
+  uint64_t want = fast ? avg * TRIM_THREADS * 33 / 32 + 512 : avg * TRIM_THREADS * 5 / 4 + 64;
+  want = (want + 255) & ~255ull;
+  if (want < 4096) want = 4096;
   if (want > 96 * 1024) want = 96 * 1024;
   const uint32_t smem = (uint32_t)want;
   const unsigned grid = (unsigned)((n_records + TRIM_THREADS - 1) / TRIM_THREADS);
   unsigned long long *ctrl = (unsigned long long *)d_trim_ctrl;
   ushort4 *win = (ushort4 *)d_win;
-  if (ctx->fast_ok && ctx->trim_mode == 0) {
+  if (fast) {
     if (!d_slow) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: d_slow scratch (u32 per record) is required");
     const size_t extra = (size_t)ctx->params.n_adapters * 1024 + (size_t)(PACK_WORDS + 2) * TRIM_THREADS * 4;
     MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
