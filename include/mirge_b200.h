@@ -133,6 +133,9 @@ typedef struct mirge_library {
   uint32_t n_idx;
   uint32_t bucket_bits;         /* d_idx_bucket is indexed by the top bucket_bits bits of a 16-mer */
   const uint32_t *d_idx_bucket; /* [2^bucket_bits + 1] */
+  const uint32_t *d_ref_block;  /* [(n_bases >> ref_block_shift) + 1] reference holding base b << ref_block_shift */
+  uint32_t ref_block_shift;
+  uint32_t reserved;
 } mirge_library;
 
 #define MIRGE_SELECT_LEN_LT26 0    /* round 0 (manifoldAlign.py:93)  */

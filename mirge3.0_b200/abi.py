@@ -82,6 +82,9 @@ class Library(C.Structure):
         ("n_idx", C.c_uint32),
         ("bucket_bits", C.c_uint32),
         ("d_idx_bucket", C.c_void_p),
+        ("d_ref_block", C.c_void_p),
+        ("ref_block_shift", C.c_uint32),
+        ("reserved", C.c_uint32),
     ]
 
 

@@ -30,13 +30,11 @@ __device__ __forceinline__ uint32_t lib_word16(const uint32_t *packed, uint64_t 
   return sh ? __funnelshift_r(lo, hi, sh) : lo;
 }
 
-__device__ __forceinline__ uint32_t find_ref(const uint32_t *ref_off, uint32_t n_refs, uint32_t pos) {
-  uint32_t lo = 0, hi = n_refs;  // largest r with ref_off[r] <= pos
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (ref_off[mid] <= pos) lo = mid; else hi = mid;
-  }
-  return lo;
+// reference holding base `pos`: coarse block table, then a short forward scan (largest r with ref_off[r] <= pos)
+__device__ __forceinline__ uint32_t find_ref(const mirge_library &lib, uint32_t pos) {
+  uint32_t r = lib.d_ref_block[pos >> lib.ref_block_shift];
+  while (r + 1 < lib.n_refs && lib.d_ref_off[r + 1] <= pos) ++r;
+  return r;
 }
 
 // ------------------------------------------------------------------ index construction -------
@@ -45,7 +43,7 @@ __global__ void __launch_bounds__(256)
 lib_kmers_kernel(mirge_library lib, uint32_t *__restrict__ kmer, uint8_t *__restrict__ valid) {
   const uint32_t p = blockIdx.x * 256u + threadIdx.x;
   if (p >= lib.n_bases) return;
-  const uint32_t r = find_ref(lib.d_ref_off, lib.n_refs, p);
+  const uint32_t r = find_ref(lib, p);
   const uint32_t end = lib.d_ref_off[r + 1];
   uint32_t k = 0, v = 0;
   for (uint32_t i = 0; i < 16; ++i) {
@@ -61,7 +59,8 @@ lib_kmers_kernel(mirge_library lib, uint32_t *__restrict__ kmer, uint8_t *__rest
 
 extern "C" int mirge_lib_kmers(mirge_ctx *ctx, const mirge_library *lib, uint32_t *d_kmer, uint8_t *d_valid, void *stream_) {
   if (!ctx) return MIRGE_ERR_ARG;
-  if (!lib || !lib->d_packed || !lib->d_nmask || !lib->d_ref_off || !d_kmer || !d_valid) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "lib_kmers: null buffer");
+  if (!lib || !lib->d_packed || !lib->d_nmask || !lib->d_ref_off || !lib->d_ref_block || !d_kmer || !d_valid)
+    MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "lib_kmers: null buffer");
   if (lib->n_bases == 0 || lib->n_refs == 0) return MIRGE_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -124,7 +123,7 @@ __device__ __forceinline__ uint64_t verify(const mirge_library &lib, const uint3
                                            const mirge_round_policy &pol, int R, uint64_t astart, uint32_t pos_in_ref) {
   const int mm = verify_text(lib, qw, qnx, L, pol, R, astart);
   if (mm < 0) return MIRGE_NO_HIT;
-  const uint32_t r = find_ref(lib.d_ref_off, lib.n_refs, pos_in_ref);
+  const uint32_t r = find_ref(lib, pos_in_ref);
   const uint32_t rlo = lib.d_ref_off[r], rhi = lib.d_ref_off[r + 1];
   if (astart < rlo || astart + (uint64_t)L > rhi) return MIRGE_NO_HIT;
   if (ref_has_n(lib, astart, astart + L)) return MIRGE_NO_HIT;
@@ -162,7 +161,7 @@ __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const
   const int nw = (L + 15) >> 4;
   if (active && !degenerate) {
     for (int pi = 0; pi < np; ++pi) {
-      const int a = (int)((long long)pi * R / np), b = (int)((long long)(pi + 1) * R / np);
+      const int a = (int)((uint32_t)(pi * R) / (uint32_t)np), b = (int)((uint32_t)((pi + 1) * R) / (uint32_t)np);
       const int s = min(16, b - a);
       // a piece with a non-ACGT read base cannot be exact
       if (has_exc && query_has_n(qnx, a, b)) continue;
@@ -339,8 +338,10 @@ annotate_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_k
 }
 
 static int check_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_round_policy *policy) {
-  if (!lib->d_packed || !lib->d_nmask || !lib->d_ref_off || !lib->d_idx_kmer || !lib->d_idx_pos || !lib->d_idx_bucket)
+  if (!lib->d_packed || !lib->d_nmask || !lib->d_ref_off || !lib->d_idx_kmer || !lib->d_idx_pos || !lib->d_idx_bucket ||
+      !lib->d_ref_block)
     MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: library has no index");
+  if (lib->ref_block_shift > 20) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: ref_block_shift out of range");
   if (lib->bucket_bits < 1 || lib->bucket_bits > 28) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: bucket_bits out of range");
   if (policy->seed_mm < 0 || policy->seed_mm > 3 || policy->total_mm < policy->seed_mm || policy->trim5 < 0 || policy->trim3 < 0)
     MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: unsupported policy");

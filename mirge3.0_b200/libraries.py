@@ -124,13 +124,19 @@ class DeviceLibrary:
         self.idx_kmer = self.idx_pos = self.idx_bucket = None
         self.n_idx = 0
         self.bucket_bits = 4
+        # coarse position -> reference map (one entry per 64 bases) replacing a binary search over ref_off
+        self.ref_block_shift = 6
+        starts = torch.arange((self.n_bases >> self.ref_block_shift) + 1, device=dev.tdev, dtype=torch.int64) << self.ref_block_shift
+        off_d = torch.from_numpy(off).to(dev.tdev)
+        self.ref_block = (torch.searchsorted(off_d, starts, right=True) - 1).clamp_(0, max(self.n_refs - 1, 0)).to(torch.int32)
         self._build_index()
 
     def _base_struct(self) -> abi.Library:
         return abi.Library(self.packed.data_ptr(), self.nmask.data_ptr(), self.ref_off.data_ptr(), self.n_refs, self.n_bases,
                            0 if self.idx_kmer is None else self.idx_kmer.data_ptr(),
                            0 if self.idx_pos is None else self.idx_pos.data_ptr(), self.n_idx, self.bucket_bits,
-                           0 if self.idx_bucket is None else self.idx_bucket.data_ptr())
+                           0 if self.idx_bucket is None else self.idx_bucket.data_ptr(),
+                           self.ref_block.data_ptr(), self.ref_block_shift, 0)
 
     def _build_index(self):
         d = self.dev
@@ -157,7 +163,9 @@ class DeviceLibrary:
         if self.n_idx == 0:
             self.idx_kmer = torch.zeros(1, dtype=torch.int32, device=d.tdev)
             self.idx_pos = torch.zeros(1, dtype=torch.int32, device=d.tdev)
-        bb = int(min(24, max(4, math.ceil(math.log2(max(self.n_idx, 2))) - 2)))
+        # about one index entry per bucket: most lookups of sequences that are not in the library end at
+        # the bucket table (empty range) without touching the k-mer array
+        bb = int(min(26, max(4, math.ceil(math.log2(max(self.n_idx, 2))) + 1)))
         self.bucket_bits = bb
         bounds = torch.arange((1 << bb) + 1, device=d.tdev, dtype=torch.int64) << (32 - bb)
         self.idx_bucket = torch.searchsorted(ks.contiguous(), bounds).to(torch.int32)
