@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--count-mode", default="head", choices=["head", "release"])
     ap.add_argument("--cpu-sample", type=int, default=400_000, help="reads of the bounded CPU-baseline sample")
     ap.add_argument("--batch-mb", type=int, default=2048)
+    ap.add_argument("--e2e-batch-mb", type=int, default=256, help="piece size of the host-fed (e2e) pipeline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -257,11 +258,13 @@ def run_b200(args):
     launches0 = dev.launches
     clocks = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.profiler.start()  # ncu --profile-from-start off: the launch list covers exactly the timed region
     e0.record()
     for _ in range(args.steps):
         n_rec = step_resident()
     e1.record()
     barrier()
+    torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1) / max(args.steps, 1)
     timers = dev.timer_totals()
     dev.timing = False
@@ -282,7 +285,7 @@ def run_b200(args):
         host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
         host.copy_(fq)
         torch.cuda.synchronize()
-        streamer = DG.HostStreamer(eng, batch_bytes)
+        streamer = DG.HostStreamer(eng, args.e2e_batch_mb << 20)
 
         pinned = {}
 
@@ -296,8 +299,17 @@ def run_b200(args):
             buf[:n_el].copy_(t, non_blocking=True)
             return n_el * t.element_size()
 
+        sa = MA.StreamedAnnotator(dev, lset, False) if world == 1 else None
+
         def step_e2e():
             table.reset()
+            if sa is not None:
+                # single GPU: annotation and the D2H of the result table are streamed piece by piece behind
+                # the H2D of the following pieces; only the per-sample counts remain for the end
+                sa.reset()
+                n = streamer.run(host, table, on_piece=sa)
+                sa.finish(table)
+                return n, sa.d2h_bytes
             n = streamer.run(host, table)
             tab = finish(table)
             # result table -> host: packed unique sequences, per-key counts and annotation

@@ -296,25 +296,56 @@ extern "C" int mirge_table_rehash(mirge_ctx *ctx, const mirge_table *old_t, cons
 
 // ------------------------------------------------------------------ per-sample drain --------
 
+#define DRAIN_PER_THREAD 4
+// Sweep of the slot array: every CTA owns COL_THREADS * DRAIN_PER_THREAD consecutive slots (coalesced 16-byte
+// loads), compacts the counted ones with a block-wide scan and reserves its output range with ONE atomic, so
+// the sweep runs at streaming bandwidth instead of at the rate of same-address atomics.
 __global__ void __launch_bounds__(COL_THREADS)
 drain_kernel(mirge_table t, uint32_t *__restrict__ ids, uint32_t *__restrict__ counts, uint64_t cap, unsigned long long *n_out) {
-  const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
-  if (i >= t.capacity) return;
-  mirge_slot *s = t.d_slots + i;
-  const uint4 v = *(const uint4 *)s;
-  if (v.x == 0 || v.w == 0) return;
-  const unsigned grp = __activemask(), lane = threadIdx.x & 31;
-  const int leader = __ffs(grp) - 1;
-  unsigned long long base = 0;
-  if ((int)lane == leader) base = atomicAdd(n_out, (unsigned long long)__popc(grp));
-  base = __shfl_sync(grp, base, leader) + __popc(grp & ((1u << lane) - 1u));
-  if (base < cap) {
-    ids[base] = v.z;
-    counts[base] = v.w;
-  } else {
-    atomicOr((unsigned long long *)t.d_ctrl + 2, ERR_OUT_FULL);
+  __shared__ uint32_t warp_tot[COL_THREADS / 32];
+  __shared__ unsigned long long block_base;
+  const uint64_t first = (uint64_t)blockIdx.x * (COL_THREADS * DRAIN_PER_THREAD) + threadIdx.x;
+  uint4 v[DRAIN_PER_THREAD];
+  uint32_t mine = 0;
+#pragma unroll
+  for (int k = 0; k < DRAIN_PER_THREAD; ++k) {
+    const uint64_t i = first + (uint64_t)k * COL_THREADS;
+    v[k] = make_uint4(0, 0, 0, 0);
+    if (i < t.capacity) v[k] = *(const uint4 *)(t.d_slots + i);
+    if (v[k].x != 0 && v[k].w != 0) ++mine;
   }
-  s->count = 0;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= (unsigned)d) inc += x;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < COL_THREADS / 32; ++w) {
+    const uint32_t x = warp_tot[w];
+    if ((unsigned)w < warp) before += x;
+    total += x;
+  }
+  if (total == 0) return;
+  if (threadIdx.x == 0) block_base = atomicAdd(n_out, (unsigned long long)total);
+  __syncthreads();
+  unsigned long long o = block_base + before + inc - mine;
+#pragma unroll
+  for (int k = 0; k < DRAIN_PER_THREAD; ++k) {
+    if (v[k].x == 0 || v[k].w == 0) continue;
+    if (o < cap) {
+      ids[o] = v[k].z;
+      counts[o] = v[k].w;
+    } else {
+      atomicOr((unsigned long long *)t.d_ctrl + 2, ERR_OUT_FULL);
+    }
+    ++o;
+    t.d_slots[first + (uint64_t)k * COL_THREADS].count = 0;
+  }
 }
 
 extern "C" int mirge_table_drain(mirge_ctx *ctx, const mirge_table *t, uint32_t *d_ids, uint32_t *d_counts, uint64_t out_capacity,
@@ -326,7 +357,8 @@ extern "C" int mirge_table_drain(mirge_ctx *ctx, const mirge_table *t, uint32_t 
   cudaStream_t stream = (cudaStream_t)stream_;
   MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
   MIRGE_CUDA(ctx, cudaMemsetAsync(d_n_out, 0, 8, stream));
-  const unsigned grid = (unsigned)((t->capacity + COL_THREADS - 1) / COL_THREADS);
+  const uint64_t per_cta = (uint64_t)COL_THREADS * DRAIN_PER_THREAD;
+  const unsigned grid = (unsigned)((t->capacity + per_cta - 1) / per_cta);
   drain_kernel<<<grid, COL_THREADS, 0, stream>>>(*t, d_ids, d_counts, out_capacity, (unsigned long long *)d_n_out);
   MIRGE_LAUNCH_CHECK(ctx, "drain_kernel");
   return MIRGE_OK;

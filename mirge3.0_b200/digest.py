@@ -45,32 +45,43 @@ def _open_fastq(path: str):
 
 
 class HostStreamer:
-    """Feeds a host byte stream (file object or memoryview) to the engine batch by batch through two
-    pinned staging buffers and two device buffers; the tail of a batch that does not end on a
-    record boundary is carried to the front of the next device buffer (device-to-device)."""
+    """Feeds a host byte stream (file object, bytes-like or pinned tensor) to the engine piece by piece.
 
-    def __init__(self, eng: DigestEngine, batch_bytes: int = DEFAULT_BATCH_BYTES, max_record: int = 1 << 20):
+    Pipeline: ``n_buf`` device buffers; the H2D copy of a piece goes to a fixed offset (``headroom``) of its
+    buffer, so it does not depend on where the previous piece's last complete record ended and is enqueued
+    ``n_buf - 1`` pieces ahead on its own stream -- the copy engine never waits for a kernel.  The tail of a
+    piece that does not end on a record boundary is moved (device to device) in front of the next piece,
+    into the headroom of that buffer.  ``on_piece(table)`` runs after every collapsed piece on the main
+    stream (streamed annotation / D2H of the table's new keys)."""
+
+    def __init__(self, eng: DigestEngine, batch_bytes: int = DEFAULT_BATCH_BYTES, max_record: int = 1 << 20, n_buf: int = 3):
         self.eng = eng
         self.dev = eng.dev
         self.batch = int(batch_bytes)
-        self.cap = self.batch + max_record + 64
-        self.h = [torch.empty(self.batch, dtype=torch.uint8).pin_memory() for _ in range(2)]
-        self.d = [torch.empty(self.cap, dtype=torch.uint8, device=self.dev.tdev) for _ in range(2)]
+        self.n_buf = max(int(n_buf), 2)
+        self.headroom = (int(max_record) + 64 + 255) & ~255
+        self.d = [torch.empty(self.headroom + self.batch, dtype=torch.uint8, device=self.dev.tdev) for _ in range(self.n_buf)]
+        self.h: List[Optional[torch.Tensor]] = [None] * self.n_buf  # pinned staging, only for readinto() sources
+        self.h_busy: List[Optional[torch.cuda.Event]] = [None] * self.n_buf
         self.copy_stream = torch.cuda.Stream(device=self.dev.tdev)
         self.h2d_bytes = 0
 
     def _pieces(self, src):
-        """Yield pinned host tensors of <= batch bytes covering the stream, in order.  A pinned torch
-        tensor is sliced in place (no staging copy); anything with readinto() is staged through the
-        two pinned buffers."""
+        """Yield (pinned host tensor of <= batch bytes, staging index or -1) covering the stream, in order.
+        A pinned torch tensor is sliced in place (no staging copy); anything with readinto() is staged
+        through pinned buffers, each reused only after its previous H2D copy has completed."""
         if isinstance(src, torch.Tensor):
             if src.is_cuda or src.dtype != torch.uint8 or not src.is_pinned():
                 raise MirgeError("host tensor source must be a pinned uint8 tensor")
             for pos in range(0, int(src.numel()), self.batch):
-                yield src[pos : pos + self.batch]
+                yield src[pos : pos + self.batch], -1
             return
         cur = 0
         while True:
+            if self.h[cur] is None:
+                self.h[cur] = torch.empty(self.batch, dtype=torch.uint8).pin_memory()
+            if self.h_busy[cur] is not None:
+                self.h_busy[cur].synchronize()
             mv = memoryview(self.h[cur].numpy())
             got = 0
             while got < self.batch:
@@ -80,52 +91,70 @@ class HostStreamer:
                 got += k
             if got == 0:
                 return
-            yield self.h[cur][:got]
+            yield self.h[cur][:got], cur
             if got < self.batch:
                 return
-            cur ^= 1
+            cur = (cur + 1) % self.n_buf
 
-    def run(self, src, table: CollapseTable) -> int:
-        """Digest the whole stream into ``table``; returns the number of records parsed.  The H2D copy
-        of piece k+1 (copy stream) overlaps the kernels of piece k (main stream)."""
-        eng, dev = self.eng, self.dev
+    def run(self, src, table: CollapseTable, on_piece=None) -> int:
+        """Digest the whole stream into ``table``; returns the number of records parsed."""
+        eng, dev, H = self.eng, self.dev, self.headroom
         main = torch.cuda.current_stream(dev.tdev)
         it = self._pieces(src)
+        pending = []  # (buffer index, piece bytes, copy-done event)
+        free_ev: List[Optional[torch.cuda.Event]] = [None] * self.n_buf
+        state = {"k": 0, "done": False}
+
+        def enqueue():
+            if state["done"]:
+                return
+            nxt = next(it, None)
+            if nxt is None:
+                state["done"] = True
+                return
+            piece, hi = nxt
+            b = state["k"] % self.n_buf
+            n = int(piece.numel())
+            with torch.cuda.stream(self.copy_stream):
+                if free_ev[b] is not None:
+                    self.copy_stream.wait_event(free_ev[b])  # kernels that read this buffer are done
+                self.d[b][H : H + n].copy_(piece, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+            if hi >= 0:
+                self.h_busy[hi] = ev
+            pending.append((b, n, ev))
+            self.h2d_bytes += n
+            state["k"] += 1
+
+        for _ in range(self.n_buf - 1):
+            enqueue()
         n_records = 0
-        cur = 0
-        nxt = next(it, None)
-        if nxt is None:
-            return 0
-        # prime: first piece into d[0]
-        with torch.cuda.stream(self.copy_stream):
-            self.d[0][: nxt.numel()].copy_(nxt, non_blocking=True)
-        self.h2d_bytes += int(nxt.numel())
-        filled = int(nxt.numel())  # bytes of the *new* piece sitting in d[cur] after `leftover`
-        leftover = 0
-        while True:
-            dbuf = self.d[cur]
-            main.wait_stream(self.copy_stream)
-            nbytes = leftover + filled
-            nxt = next(it, None)  # host-side read of the next piece overlaps the work queued below
-            final = nxt is None
-            br = eng.trim_batch(dbuf, nbytes, final, keep=False, table=table)
+        tail = 0  # bytes of the previous piece's incomplete last record, sitting just below the headroom mark
+        while pending:
+            b, n, ev = pending.pop(0)
+            enqueue()
+            final = not pending
+            main.wait_event(ev)
+            nbytes = tail + n
+            view = self.d[b][H - tail : H + n]
+            br = eng.trim_batch(view, nbytes, final, keep=False, table=table)
             if not final:
-                tail = nbytes - br.consumed
-                if tail > self.cap - self.batch:
-                    raise FastqFormatError("FASTQ record longer than %d bytes" % (self.cap - self.batch))
-                obuf = self.d[cur ^ 1]
-                if tail:
-                    obuf[:tail].copy_(dbuf[br.consumed : nbytes])
-                with torch.cuda.stream(self.copy_stream):
-                    self.copy_stream.wait_stream(main)  # obuf's previous kernels and the tail copy are done
-                    obuf[tail : tail + nxt.numel()].copy_(nxt, non_blocking=True)
-                self.h2d_bytes += int(nxt.numel())
+                new_tail = nbytes - br.consumed
+                if new_tail > H:
+                    raise FastqFormatError("FASTQ record longer than %d bytes" % H)
+                if br.n_records == 0 and new_tail == 0:
+                    raise FastqFormatError("no complete FASTQ record in batch")
+                if new_tail:
+                    self.d[pending[0][0]][H - new_tail : H].copy_(view[br.consumed : nbytes])
+                tail = new_tail
             eng.collapse_batch(table, br)
+            fe = torch.cuda.Event()
+            fe.record(main)
+            free_ev[b] = fe
             n_records += br.n_records
-            if final:
-                break
-            leftover, filled = tail, int(nxt.numel())
-            cur ^= 1
+            if on_piece is not None:
+                on_piece(table)
         return n_records
 
 

@@ -103,6 +103,76 @@ def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = 
     return annot[:n], hit[:n]
 
 
+class StreamedAnnotator:
+    """``HostStreamer.run(on_piece=...)`` hook for single-GPU runs: after every collapsed piece the keys that
+    piece created are annotated (a key's annotation depends on nothing but its text) and the new arena
+    words, key offsets, annotation rounds and hit words are copied to pinned host buffers on a separate
+    stream, so the D2H of the result table overlaps the H2D of the following pieces.  Only the per-sample
+    counts are left for the end of the sample."""
+
+    def __init__(self, dev: Device, libs: LibrarySet, spike_in: bool = False):
+        self.dev, self.libs, self.spike = dev, libs, spike_in
+        self.d2h = torch.cuda.Stream(device=dev.tdev)
+        self.host: Dict[str, torch.Tensor] = {}
+        self.reset()
+
+    def reset(self):
+        self.n_done = 0
+        self.w_done = 0
+        self.d2h_bytes = 0
+        self.n_annotated = None
+
+    def _host(self, name: str, dtype, need: int, used: int) -> torch.Tensor:
+        buf = self.host.get(name)
+        if buf is None or buf.numel() < need:
+            new = torch.empty(max(int(need * 1.5), 1 << 20), dtype=dtype).pin_memory()
+            if buf is not None and used:
+                self.d2h.synchronize()
+                new[:used].copy_(buf[:used])
+            self.host[name] = buf = new
+        return buf
+
+    def to_host(self, name: str, src: torch.Tensor, at: int, used: int):
+        """src -> host[name][at : at + len(src)] on the D2H stream (after the work queued on the main stream)."""
+        n = int(src.numel())
+        if n == 0:
+            return
+        dst = self._host(name, src.dtype, at + n, used)
+        src.record_stream(self.d2h)
+        dst[at : at + n].copy_(src, non_blocking=True)
+        self.d2h_bytes += n * src.element_size()
+
+    def __call__(self, table: CollapseTable):
+        n0, w0, n1, w1 = self.n_done, self.w_done, table.n_keys, table.arena_used
+        if n1 <= n0:
+            return
+        dev = self.dev
+        ks = KeySet(dev, table.arena, table.key_ref[n0:n1], n1 - n0)
+        annot, hit = annotate_keys(dev, self.libs, ks, self.spike)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev.tdev))
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(ev)
+            self.to_host("arena", table.arena[w0:w1], w0, w0)
+            self.to_host("key_ref", table.key_ref[n0:n1], n0, n0)
+            self.to_host("annot", annot, n0, n0)
+            self.to_host("hit", hit, n0, n0)
+        self.n_done, self.w_done = n1, w1
+
+    def finish(self, table: CollapseTable):
+        """End of the sample: per-sample counts to the host; returns when every byte has arrived."""
+        dev = self.dev
+        ids, cnt = table.drain()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev.tdev))
+        with torch.cuda.stream(self.d2h):
+            self.d2h.wait_event(ev)
+            self.to_host("ids", ids, 0, 0)
+            self.to_host("cnt", cnt, 0, 0)
+        self.d2h.synchronize()
+        return int(ids.numel())
+
+
 def decode_hits(annot: np.ndarray, hit: np.ndarray):
     """(round, n_mismatch, ref_index, offset) numpy arrays from the packed hit words."""
     h = hit.view(np.uint64)

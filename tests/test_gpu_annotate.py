@@ -240,3 +240,37 @@ def test_baking_and_bwtalign_end_to_end(dev, tmp_path):
     df2, *_ = DG.baking(args2, files[:1], names[:1], str(tmp_path), device=dev)
     out2 = MA.bwtAlign(args2, df2, str(tmp_path), "miRBase", device=dev)
     assert "spike-in" not in out2.columns
+
+
+def test_streamed_annotation_matches_whole_table(dev):
+    """StreamedAnnotator (annotate + D2H the keys each piece created) == annotating the finished table."""
+    from mirge_b200 import device as D
+    from mirge_b200 import digest as DG
+    from mirge_b200 import libraries as LB
+    from mirge_b200 import manifoldAlign as MA
+    from mirge_b200 import params as P
+    from mirge_b200 import synth
+
+    libs = synth.make_libraries(scale=0.02, mrna_count=30)
+    lset = LB.LibrarySet.from_fasta_dict(dev, libs.fasta_dict())
+    eng = D.DigestEngine(dev, synth.trim_config_for(2, "head"))
+    fq = synth.ReadGenerator(libs, synth.CONFIGS[2], dev.tdev).fastq(20000)
+    host = fq.cpu().pin_memory()
+    table = D.CollapseTable(dev, min_keys=1 << 10)
+    sa = MA.StreamedAnnotator(dev, lset, True)
+    n = DG.HostStreamer(eng, 300_000, max_record=4096).run(host, table, on_piece=sa)
+    n_pairs = sa.finish(table)
+    assert n == 20000 and sa.n_done == table.n_keys == n_pairs
+    annot, hit = MA.annotate_keys(dev, lset, MA.KeySet.from_table(table), True)
+    nk, nw = table.n_keys, table.arena_used
+    assert np.array_equal(sa.host["annot"][:nk].numpy(), annot.cpu().numpy())
+    assert np.array_equal(sa.host["hit"][:nk].numpy(), hit.cpu().numpy())
+    assert (annot.cpu().numpy() != 0xFF).sum() > 100
+    assert np.array_equal(sa.host["key_ref"][:nk].numpy(), table.key_ref[:nk].cpu().numpy())
+    # arena words referenced by keys arrived intact (dead space of duplicate emissions is copied too)
+    assert np.array_equal(sa.host["arena"][:nw].numpy(), table.arena[:nw].cpu().numpy())
+    # counts: same multiset as a resident pass
+    t2 = D.CollapseTable(dev, min_keys=1 << 10)
+    eng.digest_device(fq, t2)
+    ids2, cnt2 = t2.drain()
+    assert sorted(sa.host["cnt"][:n_pairs].tolist()) == sorted(cnt2.cpu().tolist())

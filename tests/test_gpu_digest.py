@@ -199,3 +199,32 @@ def test_long_records_fall_back_to_generic_kernel(dev):
     assert eng.digest_device(to_dev(dev, data), table) == 300
     _, tab = coracle.digest_collapse(np.frombuffer(data, dtype=np.uint8), dev.trim_params)
     assert table_dict(table) == tab.to_dict()
+
+
+def test_host_streamer_pipeline_matches_device_path(dev):
+    """HostStreamer (pipelined H2D, tails carried in the headroom) vs the resident path, odd piece sizes."""
+    import io
+
+    from mirge_b200 import device as D
+    from mirge_b200 import digest as DG
+
+    cfg = CONFIGS["default"]
+    data = random_fastq(6000, seed=91)
+    eng = D.DigestEngine(dev, cfg)
+    _, tab = coracle.digest_collapse(np.frombuffer(data, dtype=np.uint8), dev.trim_params)
+    exp = tab.to_dict()
+    pinned = torch.frombuffer(bytearray(data), dtype=torch.uint8).pin_memory()
+    for batch, n_buf, max_record in ((1 << 20, 3, 1 << 12), (50_000, 3, 1 << 12), (7_777, 2, 1 << 10), (301, 4, 1 << 10)):
+        for src in (io.BytesIO(data), data, pinned):
+            table = D.CollapseTable(dev, min_keys=1 << 10)
+            st = DG.HostStreamer(eng, batch, max_record=max_record, n_buf=n_buf)
+            seen = []
+            n = st.run(src if not isinstance(src, bytes) else DG._BytesSource(src), table, on_piece=lambda t: seen.append(t.n_keys))
+            assert n == 6000 and st.h2d_bytes == len(data)
+            assert seen == sorted(seen) and seen[-1] == len(exp)
+            assert table_dict(table) == exp, (batch, n_buf)
+    # a record that does not fit the headroom is a format error, not a silent truncation
+    table = D.CollapseTable(dev, min_keys=1 << 10)
+    with pytest.raises(D.FastqFormatError):
+        long_rec = b"@r\n" + b"A" * 400 + b"\n+\n" + b"I" * 400 + b"\n"
+        DG.HostStreamer(eng, 64, max_record=64, n_buf=2).run(io.BytesIO(long_rec * 3), table)
