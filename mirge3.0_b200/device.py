@@ -243,7 +243,7 @@ class DigestEngine:
         self.E = dev.slots
         self.trim_mode = 0  # 0 = automatic kernel choice, 1 = always the generic full-DP kernel
         dev.check(dev.lib.mirge_trim_mode(dev.ctx, 0))
-        self.stats = {"records": 0, "bytes": 0, "emitted": 0, "key_words": 0}  # running totals (bench.py rooflines)
+        self.stats = {"records": 0, "bytes": 0, "emitted": 0, "key_words": 0, "deferred": 0}  # running totals (bench.py rooflines)
 
     def set_trim_mode(self, mode: int):
         self.dev.check(self.dev.lib.mirge_trim_mode(self.dev.ctx, int(mode)))
@@ -304,6 +304,7 @@ class DigestEngine:
             d.launches += 2
             c = ctrl.cpu().numpy().view(np.uint64)
             flags = int(c[2])
+            self.stats["deferred"] += int(c[5])  # reads handed to the second trim pass (diagnostics)
             if flags & 8 and mode == 0:
                 # a record group did not fit the bit-parallel kernel's shared-memory staging:
                 # repeat the batch with the generic kernel (same results, slower)
