@@ -17,6 +17,8 @@
  *                                                                     mirge_table_export_keys
  *   mirge/libs/manifoldAlign.py:68 bwtAlign(args, df, workDir, db)   mirge_lib_kmers,
  *     :12   alignPlusParse (bowtie subprocess + SAM parse)            mirge_annotate_round
+ *   mirge/libs/summary.py:677 summarize(...): per-library read sums   mirge_report_reduce
+ *     (:692-698) and per-miRNA exact / isomiR sums (:716-770)
  *
  * Conventions: every function returns 0 on success or a negative MIRGE_ERR_* code and records a
  * message retrievable with mirge_last_error().  All pointers named d_* are DEVICE pointers owned
@@ -278,6 +280,16 @@ int mirge_annotate_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_r
 int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, const mirge_round_policy *policies,
                           int n_rounds, const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round,
                           uint64_t *d_hit, void *stream);
+
+/* ---- stage 4: counters of annotation.report.csv (summarize, summary.py:692-698,716-770) ---- */
+/* For every (key id, count) pair of ONE sample (the output of mirge_table_drain):
+ *   d_round_sum[round of the key] += count            (u64[10]; unannotated keys are skipped)
+ *   d_can[ref] += count for round 0 (exact miRNA), d_iso[ref] += count for round 8 (isomiR),
+ *   ref = MIRGE_HIT_REF(d_hit[id]) < n_mirna  (both rounds search the same miRNA library).
+ * Accumulates into the caller-zeroed arrays; synchronises `stream` (error check). */
+int mirge_report_reduce(mirge_ctx *ctx, const uint8_t *d_annot_round, const uint64_t *d_hit,
+                        const uint32_t *d_ids, const uint32_t *d_counts, uint64_t n_pairs, uint32_t n_mirna,
+                        uint64_t *d_round_sum, uint64_t *d_can, uint64_t *d_iso, void *stream);
 
 #ifdef __cplusplus
 }

@@ -688,3 +688,131 @@ def annotate(seqs: Sequence[str], libs: Dict[str, Library], spike_in: bool = Fal
             if pick is not None:
                 annot[s] = (rnd, lib.names[pick[1]], pick[2], pick[0])
     return annot
+
+
+# ---------------------------------------------------------------------------------------------------
+# Split + summarize counters: mirge/__main__.py:164-173 and the parts of
+# mirge/libs/summary.py::summarize that feed annotation.report.csv and miR.Counts.csv.  Pure Python over
+# dicts; pinned byte-for-byte on files the unmodified reference wrote (tests/golden/ref_case1, generated by
+# tests/golden/make_reference_golden.py).
+# ---------------------------------------------------------------------------------------------------
+
+REPORT_COLUMNS = ["Total Input Reads", "Trimmed Reads (all)", "Trimmed Reads (unique)", "All miRNA Reads", "Filtered miRNA Reads",
+                  "Unique miRNAs", "Hairpin miRNAs", "mature tRNA Reads", "primary tRNA Reads", "snoRNA Reads", "rRNA Reads",
+                  "ncRNA others", "mRNA Reads", "Spike-in", "Remaining Reads"]  # summary.py:897,901 (colRearrange)
+_REPORT_ROUND = {"Hairpin miRNAs": 1, "mature tRNA Reads": 2, "primary tRNA Reads": 3, "snoRNA Reads": 4, "rRNA Reads": 5,
+                 "ncRNA others": 6, "mRNA Reads": 7, "Spike-in": 9}  # summary.py:686-691 col_headers -> round
+
+
+def read_merges(text: str) -> Tuple[Dict[str, str], List[str]]:
+    """<organism>_merges_<db>.csv (summary.py:705-714): member name -> merged name, and the merged names."""
+    member, merged = {}, []
+    for line in text.splitlines():
+        c = line.strip().split(",")
+        for item in c[1:]:
+            member[item] = c[0]
+        merged.append(c[0])
+    return member, merged
+
+
+def table_csv(rows: Sequence[Tuple[str, int, Sequence[str], Sequence[int]]], samples: Sequence[str], spike_in: bool) -> str:
+    """``DataFrame.to_csv`` of mapped.csv / unmapped.csv (__main__.py:172-173): index label Sequence, annotFlag,
+    the annotation columns ('spike-in' only with -spk, manifoldAlign.py:137-138), one column per sample."""
+    cols = ROUND_COLUMNS if spike_in else ROUND_COLUMNS[:9]
+    out = ["Sequence,annotFlag," + ",".join(cols) + "," + ",".join(samples)]
+    for seq, flag, names, counts in rows:
+        out.append("%s,%d,%s,%s" % (seq, flag, ",".join(names[: len(cols)]), ",".join(str(int(c)) for c in counts)))
+    return "\n".join(out) + "\n"
+
+
+def split_tables(annot: Dict[str, Tuple[int, str, int, int]], counts: Dict[str, Sequence[int]], samples: Sequence[str],
+                 spike_in: bool) -> Tuple[str, str]:
+    """(mapped.csv, unmapped.csv) texts: rows in the DataFrame's order (sorted sequences), annotFlag split
+    of __main__.py:164-165."""
+    mapped, unmapped = [], []
+    for seq in sorted(counts):
+        names = [""] * 10
+        a = annot.get(seq)
+        if a is not None:
+            names[a[0]] = a[1]
+            mapped.append((seq, 1, names, counts[seq]))
+        else:
+            unmapped.append((seq, 0, names, counts[seq]))
+    return table_csv(mapped, samples, spike_in), table_csv(unmapped, samples, spike_in)
+
+
+def canonical_filter(can: int, iso: int, ca_thr: float) -> int:
+    """mirge_can (summary.py:25-45) for one miRNA of one sample: exact reads ``can``, isomiR reads ``iso``."""
+    if can < 2:  # :36-37
+        can, iso = 0, 0
+    ratio = can / iso if iso > 0 else float(can)  # :38-39
+    return can + iso if ratio > ca_thr else 0  # :41-42
+
+
+def summarize_counts(annot: Dict[str, Tuple[int, str, int, int]], counts: Dict[str, Sequence[int]], samples: Sequence[str],
+                     sample_reads: Dict[str, int], trimmed: Dict[str, int], trimmed_unique: Dict[str, int], merges_text: str,
+                     mirna_names: Sequence[str], ca_thr: float = 0.1, spike_in: bool = False):
+    """annotation.report.csv rows and miR.Counts.csv rows as summarize() computes them.
+    Returns (report {sample: {column: int}}, mir_counts {merged miRNA name: [float per sample]})."""
+    S = len(samples)
+    member, merged_names = read_merges(merges_text)
+    lib_sum = {k: [0] * S for k in _REPORT_ROUND}
+    all_mir = [0] * S
+    can: Dict[str, List[int]] = {}
+    iso: Dict[str, List[int]] = {}
+    for seq, (rnd, name, _off, _mm) in annot.items():
+        c = counts[seq]
+        for col, r in _REPORT_ROUND.items():  # summary.py:692-698
+            if r == rnd:
+                for j in range(S):
+                    lib_sum[col][j] += c[j]
+        if rnd in (0, 8):  # summary.py:720,764-766 ('All miRNA Reads')
+            tgt = can if rnd == 0 else iso
+            row = tgt.setdefault(name, [0] * S)
+            for j in range(S):
+                row[j] += c[j]
+                all_mir[j] += c[j]
+    grouped: Dict[str, List[float]] = {}
+    for name in sorted(can):  # cann_collapse rows (groupby sorts), left-merged with iso_collapse (summary.py:741-748)
+        y = iso.get(name, [0] * S)
+        out_name = member.get(name, name)  # :750-752
+        row = grouped.setdefault(out_name, [0.0] * S)
+        for j in range(S):
+            row[j] += float(canonical_filter(can[name][j], y[j], ca_thr))
+    report = {}
+    for j, s in enumerate(samples):
+        r = {"Total Input Reads": sample_reads[s], "Trimmed Reads (all)": trimmed[s], "Trimmed Reads (unique)": trimmed_unique[s],
+             "All miRNA Reads": all_mir[j], "Filtered miRNA Reads": int(sum(v[j] for v in grouped.values())),
+             "Unique miRNAs": sum(1 for v in grouped.values() if v[j] > 0)}  # :757-758, :882-887
+        for col in _REPORT_ROUND:
+            if col == "Spike-in" and not spike_in:
+                continue
+            r[col] = lib_sum[col][j]
+        tosum = ["All miRNA Reads"] + [c for c in _REPORT_ROUND if c in r]  # :896,900 col_tosum
+        r["Remaining Reads"] = r["Trimmed Reads (all)"] - sum(r[c] for c in tosum)  # :1224
+        report[s] = r
+    # miR.Counts.csv: every library miRNA (bowtie-inspect -n, 'segs:' names cut at the first blank) that is not a
+    # member of a merge, plus the merged names, outer-joined with the grouped counts (summary.py:774-797)
+    names = list(merged_names)
+    for srow in mirna_names:
+        if "segs:" in srow:
+            srow = srow.split(" ")[0]
+        if srow not in member:
+            names.append(srow)
+    mir_counts = {n: grouped.get(n, [0.0] * S) for n in sorted(set(names) | set(grouped))}
+    return report, mir_counts
+
+
+def report_csv(report: Dict[str, Dict[str, int]], samples: Sequence[str], spike_in: bool) -> str:
+    cols = [c for c in REPORT_COLUMNS if spike_in or c != "Spike-in"]
+    out = ["Sample name(s)," + ",".join(cols)]
+    for s in samples:
+        out.append(s + "," + ",".join(str(int(report[s][c])) for c in cols))
+    return "\n".join(out) + "\n"
+
+
+def mir_counts_csv(mir_counts: Dict[str, Sequence[float]], samples: Sequence[str]) -> str:
+    out = ["miRNA," + ",".join(samples)]
+    for n, v in mir_counts.items():
+        out.append(n + "," + ",".join(repr(float(x)) for x in v))
+    return "\n".join(out) + "\n"

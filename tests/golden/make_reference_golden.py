@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""Generates the ``ref_*`` fixtures of this directory by running UNMODIFIED reference code.
+
+    python tests/golden/make_reference_golden.py            (needs /root/reference; writes tests/golden/ref_case1/)
+
+What runs from the reference (imported from /root/reference, not copied):
+  * ``mirge.libs.manifoldAlign.bwtAlign``  -- the round driver: length / annotFlag masks, the ``T{3,}$`` query
+    rewrite of round 3, FASTA writing, command assembly, SAM parsing with "later lines overwrite earlier
+    ones" (manifoldAlign.py:12-146);
+  * the annotFlag split + ``to_csv`` of ``mirge/__main__.py:164-173`` (restated here in the two lines it is);
+  * ``mirge.libs.summary.summarize``       -- annotation.report.csv, miR.Counts.csv, miR.RPM.csv
+    (summary.py:677-1290).
+
+What cannot run here and is stood in for (no network, nothing vendored): the third-party tools.
+  * ``cutadapt`` / ``Bio`` are stubbed as empty modules so that the reference modules import; none of
+    their functions is reached by the code above.
+  * ``bowtie`` and ``bowtie-inspect`` are small scripts written into a temporary directory that
+    ``args.bowtie_path`` points at.  The stand-in bowtie answers with the oracle's definition of the
+    valid hit set (oracle/pyoracle.py: end-to-end, ungapped, forward strand, -n / -v / -e 70 policy, best
+    stratum) and prints the canonical pick LAST, so the reference's "last SAM line wins" parser lands on
+    it.  bowtie's own choice among equally good alignments is therefore NOT pinned by these fixtures
+    (DESIGN.md section 2); everything the reference itself does around bowtie is.
+  * the input DataFrame comes from the oracle's digest of the two FASTQ fixtures (the reference's ``baking``
+    needs cutadapt), built with the pandas calls of digest.py:237-261.
+
+pandas here is 3.x, the reference was written against 1.x; the script fails loudly if the reference code
+does not run under it.
+"""
+import argparse
+import gzip
+import os
+import shutil
+import stat
+import sys
+import tempfile
+import types
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(ROOT))
+REFERENCE = Path(os.environ.get("MIRGE_REFERENCE", "/root/reference"))
+
+import numpy as np  # noqa: E402
+import pandas as pd  # noqa: E402
+
+CASE = HERE / "ref_case1"
+ORG = "synth"
+DB = "miRBase"
+SAMPLES = ["sampleA", "sampleB"]
+
+
+def stub_third_party():
+    for name in ("cutadapt", "Bio", "Bio.Seq", "Bio.SeqIO", "Bio.pairwise2"):
+        m = types.ModuleType(name)
+        sys.modules[name] = m
+    sys.modules["cutadapt"].__version__ = "0 (stub)"
+    sys.modules["Bio.Seq"].Seq = object
+    sys.modules["Bio"].Seq = sys.modules["Bio.Seq"]
+    sys.modules["Bio"].SeqIO = sys.modules["Bio.SeqIO"]
+    sys.modules["Bio"].pairwise2 = sys.modules["Bio.pairwise2"]
+    sys.path.insert(0, str(REFERENCE))
+
+
+FAKE_BOWTIE = r'''#!%(python)s
+"""Stand-in for bowtie 1.x used ONLY to drive the reference's round loop (see make_reference_golden.py)."""
+import sys
+sys.path.insert(0, %(root)r)
+from oracle import pyoracle as po
+
+argv = sys.argv[1:]
+opts = {"-n": None, "-v": None, "-5": 0, "-3": 0, "--threads": 1}
+flags = set()
+pos = []
+i = 0
+while i < len(argv):
+    a = argv[i]
+    if a in opts:
+        opts[a] = int(argv[i + 1]); i += 2
+    elif a.startswith("-"):
+        flags.add(a); i += 1
+    else:
+        pos.append(a); i += 1
+index, fasta = pos[0], pos[1]
+lib = po.read_fasta(open(index + ".fa").read())
+if opts["-v"] is not None:
+    pol = po.RoundPolicy(0, opts["-v"], opts["-v"], trim5=opts["-5"], trim3=opts["-3"])
+else:
+    pol = po.RoundPolicy(28, opts["-n"] if opts["-n"] is not None else 2, 2, trim5=opts["-5"], trim3=opts["-3"])
+out = sys.stdout
+out.write("@HD\tVN:1.0\tSO:unsorted\n")
+for n, s in zip(lib.names, lib.seqs):
+    out.write("@SQ\tSN:%%s\tLN:%%d\n" %% (n, len(s)))
+out.write("@PG\tID:Bowtie\tVN:stand-in\tCL:\"%%s\"\n" %% " ".join(sys.argv))
+name = None
+for line in open(fasta):
+    line = line.rstrip("\n")
+    if line.startswith(">"):
+        name = line[1:]
+        continue
+    q = line[pol.trim5: max(len(line) - pol.trim3, pol.trim5)]
+    hs = po.hits(q, lib, pol)
+    if not hs:
+        out.write("%%s\t4\t*\t0\t0\t*\t*\t0\t0\t%%s\t%%s\tXM:i:0\n" %% (name, q, "I" * len(q)))
+        continue
+    best = min(h[0] for h in hs)
+    hs = sorted((h[0], h[1], h[2]) for h in hs if h[0] == best)
+    if "-a" not in flags:
+        hs = hs[:1]
+    for mm, r, off in reversed(hs):  # canonical pick (minimum) last: the reference keeps the last line
+        out.write("%%s\t0\t%%s\t%%d\t255\t%%dM\t*\t0\t0\t%%s\t%%s\tXA:i:%%d\tNM:i:%%d\n"
+                  %% (name, lib.names[r], off + 1, len(q), q, "I" * len(q), mm, mm))
+'''
+
+FAKE_INSPECT = r'''#!%(python)s
+"""Stand-in for ``bowtie-inspect -n <index>``: reference names of <index>.fa, one per line."""
+import sys
+index = [a for a in sys.argv[1:] if not a.startswith("-")][-1]
+for line in open(index + ".fa"):
+    if line.startswith(">"):
+        print(line[1:].rstrip("\n"))
+'''
+
+
+def make_libraries(rng):
+    B = np.array(list("ACGT"))
+
+    def rnd(n, lo, hi):
+        return ["".join(rng.choice(B, rng.integers(lo, hi + 1))) for _ in range(n)]
+
+    mir = rnd(48, 20, 24)  # summarize() draws a 5 x 8 tile map of the top 40 miRNAs: needs >= 40 names after merging
+    libs = {
+        "mirna": (["hsa-miR-%d-%dp" % (i // 2 + 1, 5 if i % 2 == 0 else 3) for i in range(48)], mir),
+        "hairpin": (["hsa-mir-%d" % (i + 1) for i in range(24)], rnd(24, 70, 100)),
+        "mature_trna": (["tRNA-%d" % i for i in range(12)], [s + "CCA" for s in rnd(12, 70, 80)]),
+        "pre_trna": (["pre-tRNA-%d" % i for i in range(12)], rnd(12, 90, 110)),
+        "snorna": (["SNORD%d" % i for i in range(15)], rnd(15, 60, 120)),
+        "rrna": (["RNA5S%d" % i for i in range(3)], rnd(3, 120, 400)),
+        "ncrna_others": (["ncRNA%d" % i for i in range(20)], rnd(20, 100, 300)),
+        "mrna": (["NM_%06d" % i for i in range(20)], rnd(20, 300, 600)),
+        "spike-in": (["spike%d" % i for i in range(5)], rnd(5, 22, 22)),
+    }
+    # hairpins carry their two mature arms
+    hp = libs["hairpin"][1]
+    for i in range(24):
+        a, b = mir[2 * i], mir[2 * i + 1]
+        hp[i] = hp[i][:5] + a + hp[i][5 + len(a): 45] + b + hp[i][45 + len(b):]
+    return libs
+
+
+def make_fastq(rng, libs, n, sample_idx):
+    """Reads = library fragments (exact, isomiR-like, with substitutions, polyT tails) + adapter, two length
+    classes, with a few N / low-quality tails; HEAD counting makes every pre-adapter read a key as well."""
+    from tests.util import ILL
+
+    B = np.array(list("ACGT"))
+    keys = list(libs)
+    w = np.array([8, 1, 1.5, 1, 1, 1, 1, 1, 0.5])
+    w = w / w.sum()
+    out = []
+    for i in range(n):
+        k = keys[int(rng.choice(len(keys), p=w))]
+        names, seqs = libs[k]
+        j = int(rng.zipf(1.6) + sample_idx) % len(seqs)
+        ref = seqs[j]
+        if k == "mirna":
+            ins = ref
+            r = rng.random()
+            if r < 0.25:  # isomiR: shifted ends (templated from nothing: random flanks)
+                ins = str(rng.choice(B)) + ref + "".join(rng.choice(B, 2))
+            elif r < 0.35:
+                ins = ref[1:-1]
+            elif r < 0.40:
+                p = int(rng.integers(len(ref)))
+                ins = ref[:p] + str(rng.choice(B)) + ref[p + 1:]
+        else:
+            L = int(rng.integers(18, 40))
+            a = int(rng.integers(0, max(1, len(ref) - L + 1)))
+            ins = ref[a:a + L]
+            if k == "pre_trna" and rng.random() < 0.7:
+                ins = ins[:25] + "TTTT"
+            if rng.random() < 0.2:
+                p = int(rng.integers(len(ins)))
+                ins = ins[:p] + str(rng.choice(B)) + ins[p + 1:]
+        if rng.random() < 0.05:
+            ins = "".join(rng.choice(B, int(rng.integers(16, 35))))
+        s = (ins + ILL + "".join(rng.choice(B, 50)))[:50]
+        if rng.random() < 0.02:
+            p = int(rng.integers(len(s)))
+            s = s[:p] + "N" + s[p + 1:]
+        q = np.clip(rng.integers(28, 41, len(s)) - (np.arange(len(s)) > 40) * rng.integers(0, 30), 2, 41)
+        out.append("@%s.%d\n%s\n+\n%s\n" % (SAMPLES[sample_idx], i, s, "".join(chr(33 + int(v)) for v in q)))
+    return "".join(out).encode()
+
+
+def reference_args(libdir, bindir):
+    return argparse.Namespace(threads=1, bowtie_path=str(bindir), bowtieVersion="True", quiet=True, organism_name=ORG,
+                              libraries_path=str(libdir), spikeIn=True, bam_out=False, tRNA_frag=False, crThreshold="0.1",
+                              gff_out=False, AtoI=False, isoform_entropy=False, novel_miRNA=False)
+
+
+def oracle_matrix(fastqs, cfg):
+    """digest.py:237-261 with the pandas calls of the reference, fed by the oracle's per-sample dicts."""
+    from oracle import pyoracle as po
+    from tests.util import py_params
+
+    p = py_params(cfg)
+    counts = {}
+    src, trc, tru = {}, {}, {}
+    frames = []
+    for name, data in zip(SAMPLES, fastqs):
+        d = po.digest_sample(data, p)
+        src[name], trc[name], tru[name] = d.count, d.trimmed, len(d.table)
+        frames.append(pd.DataFrame(list(d.table.items()), columns=["Sequence", name]).set_index("Sequence"))
+    collapsed_df = frames[0]
+    for f in frames[1:]:
+        collapsed_df = collapsed_df.join(f, how="outer")
+    collapsed_df = collapsed_df.fillna(0).astype(int)
+    flags = ["exact miRNA", "hairpin miRNA", "mature tRNA", "primary tRNA", "snoRNA", "rRNA", "ncrna others", "mRNA",
+             "isomiR miRNA", "spike-in"]
+    complete_set = collapsed_df.assign(**dict.fromkeys(flags, ""))
+    complete_set = complete_set.assign(annotFlag=0)
+    complete_set = complete_set.reindex(columns=["annotFlag"] + flags + SAMPLES)
+    complete_set = complete_set.astype({"annotFlag": int})
+    return complete_set, src, trc, tru
+
+
+def main():
+    if not REFERENCE.exists():
+        sys.exit("reference checkout %s not found" % REFERENCE)
+    stub_third_party()
+    from mirge.libs.manifoldAlign import bwtAlign  # the reference's own code
+    from mirge.libs.summary import summarize
+
+    from mirge_b200 import params as P
+
+    rng = np.random.default_rng(20260117)
+    libs = make_libraries(rng)
+    if CASE.exists():
+        shutil.rmtree(CASE)
+    libdir = CASE / "lib"
+    idx = libdir / ORG / "index.Libs"
+    idx.mkdir(parents=True)
+    (libdir / ORG / "annotation.Libs").mkdir()
+    suffix = {"mirna": "_mirna_" + DB, "hairpin": "_hairpin_" + DB, "mature_trna": "_mature_trna", "pre_trna": "_pre_trna",
+              "snorna": "_snorna", "rrna": "_rrna", "ncrna_others": "_ncrna_others", "mrna": "_mrna", "spike-in": "_spike-in"}
+    for k, (names, seqs) in libs.items():
+        with open(idx / (ORG + suffix[k] + ".fa"), "w") as f:
+            for n, s in zip(names, seqs):
+                f.write(">%s\n%s\n" % (n, s))
+    # merges file: miR-1-5p and miR-2-5p are reported under one name (summary.py:705-714)
+    (libdir / ORG / "annotation.Libs" / ("%s_merges_%s.csv" % (ORG, DB))).write_text(
+        "hsa-miR-1-5p/2-5p,hsa-miR-1-5p,hsa-miR-2-5p\nhsa-miR-7-3p/9-3p,hsa-miR-7-3p,hsa-miR-9-3p\n")
+    fastqs = [make_fastq(rng, libs, 2500, si) for si in range(2)]
+    for name, data in zip(SAMPLES, fastqs):
+        with gzip.GzipFile(CASE / (name + ".fastq.gz"), "wb", mtime=0) as f:
+            f.write(data)
+
+    cfg = P.TrimConfig(adapters=[("back", "TGGAATTCTCGGGTGCCAAGGAACTCCAG")], quality_cutoff="20", count_mode="head")
+    df, src, trc, tru = oracle_matrix(fastqs, cfg)
+
+    with tempfile.TemporaryDirectory() as tmp:
+        bindir = Path(tmp) / "bin"
+        bindir.mkdir()
+        for fname, text in (("bowtie", FAKE_BOWTIE), ("bowtie-inspect", FAKE_INSPECT)):
+            p = bindir / fname
+            p.write_text(text % {"python": sys.executable, "root": str(ROOT)})
+            p.chmod(p.stat().st_mode | stat.S_IEXEC)
+        work = Path(tmp) / "work"
+        work.mkdir()
+        args = reference_args(libdir, bindir)
+        out = bwtAlign(args, df, work, DB)                                   # manifoldAlign.py:68
+        pdMapped = out[out.annotFlag.eq(1)]                                  # __main__.py:164
+        pdUnmapped = out[out.annotFlag.eq(0)]                                # __main__.py:165
+        summarize(args, work, DB, SAMPLES, pdMapped, src, trc, tru)          # __main__.py:166
+        pdMapped.to_csv(work / "mapped.csv")                                 # __main__.py:172
+        pdUnmapped.to_csv(work / "unmapped.csv")                             # __main__.py:173
+        for f in ("mapped.csv", "unmapped.csv", "annotation.report.csv", "miR.Counts.csv", "miR.RPM.csv"):
+            shutil.copy(work / f, CASE / f)
+    n_map, n_un = len(pdMapped), len(pdUnmapped)
+    (CASE / "README.txt").write_text(
+        "Generated by tests/golden/make_reference_golden.py (pandas %s) from the unmodified reference's bwtAlign,\n"
+        "annotFlag split and summarize; third-party tools stood in for as the script header explains.\n"
+        "Trim settings: -a illumina -q 20, count_mode=head, -spk, crThreshold 0.1.  %d mapped / %d unmapped sequences.\n"
+        % (pd.__version__, n_map, n_un))
+    print("wrote", CASE, "mapped", n_map, "unmapped", n_un)
+    print((CASE / "annotation.report.csv").read_text())
+
+
+if __name__ == "__main__":
+    main()
