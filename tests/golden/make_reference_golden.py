@@ -4,6 +4,10 @@
     python tests/golden/make_reference_golden.py            (needs /root/reference; writes tests/golden/ref_case1/)
 
 What runs from the reference (imported from /root/reference, not copied):
+  * ``mirge.libs.digest.baking``           -- stipulate(), the chunk fan-out, the worker ``cutadapt(n)`` with its
+    per-modifier (HEAD) counting, the qiagen split trick and UMIParser, the parent merge, both UMI levels,
+    the sample x sequence matrix, the three counter dicts, ``_umiCounts.csv`` and ``.trim.collapse.fa``
+    (digest.py:59-375);
   * ``mirge.libs.manifoldAlign.bwtAlign``  -- the round driver: length / annotFlag masks, the ``T{3,}$`` query
     rewrite of round 3, FASTA writing, command assembly, SAM parsing with "later lines overwrite earlier
     ones" (manifoldAlign.py:12-146);
@@ -12,16 +16,17 @@ What runs from the reference (imported from /root/reference, not copied):
     (summary.py:677-1290).
 
 What cannot run here and is stood in for (no network, nothing vendored): the third-party tools.
-  * ``cutadapt`` / ``Bio`` are stubbed as empty modules so that the reference modules import; none of
-    their functions is reached by the code above.
+  * ``cutadapt``, ``dnaio``, ``xopen`` are stand-in modules (tests/golden/standins.py) exposing the API subset
+    digest.py touches, implemented with the oracle's restatement of their semantics; ``Bio`` is an empty
+    stub (nothing of it is reached).
   * ``bowtie`` and ``bowtie-inspect`` are small scripts written into a temporary directory that
     ``args.bowtie_path`` points at.  The stand-in bowtie answers with the oracle's definition of the
     valid hit set (oracle/pyoracle.py: end-to-end, ungapped, forward strand, -n / -v / -e 70 policy, best
     stratum) and prints the canonical pick LAST, so the reference's "last SAM line wins" parser lands on
     it.  bowtie's own choice among equally good alignments is therefore NOT pinned by these fixtures
     (DESIGN.md section 2); everything the reference itself does around bowtie is.
-  * the input DataFrame comes from the oracle's digest of the two FASTQ fixtures (the reference's ``baking``
-    needs cutadapt), built with the pandas calls of digest.py:237-261.
+So the fixtures pin everything the reference does itself and leave the third-party arithmetic (cutadapt's
+alignment, bowtie's search) to the oracle's restatement, which has no real install to be checked against here.
 
 pandas here is 3.x, the reference was written against 1.x; the script fails loudly if the reference code
 does not run under it.
@@ -48,18 +53,6 @@ CASE = HERE / "ref_case1"
 ORG = "synth"
 DB = "miRBase"
 SAMPLES = ["sampleA", "sampleB"]
-
-
-def stub_third_party():
-    for name in ("cutadapt", "Bio", "Bio.Seq", "Bio.SeqIO", "Bio.pairwise2"):
-        m = types.ModuleType(name)
-        sys.modules[name] = m
-    sys.modules["cutadapt"].__version__ = "0 (stub)"
-    sys.modules["Bio.Seq"].Seq = object
-    sys.modules["Bio"].Seq = sys.modules["Bio.Seq"]
-    sys.modules["Bio"].SeqIO = sys.modules["Bio.SeqIO"]
-    sys.modules["Bio"].pairwise2 = sys.modules["Bio.pairwise2"]
-    sys.path.insert(0, str(REFERENCE))
 
 
 FAKE_BOWTIE = r'''#!%(python)s
@@ -193,46 +186,120 @@ def make_fastq(rng, libs, n, sample_idx):
     return "".join(out).encode()
 
 
-def reference_args(libdir, bindir):
-    return argparse.Namespace(threads=1, bowtie_path=str(bindir), bowtieVersion="True", quiet=True, organism_name=ORG,
-                              libraries_path=str(libdir), spikeIn=True, bam_out=False, tRNA_frag=False, crThreshold="0.1",
-                              gff_out=False, AtoI=False, isoform_entropy=False, novel_miRNA=False)
+ILLUMINA = "TGGAATTCTCGGGTGCCAAGGAACTCCAG"
+QIA_INNER = "AACTGTAGGCACCATCAAT"
 
 
-def oracle_matrix(fastqs, cfg):
-    """digest.py:237-261 with the pandas calls of the reference, fed by the oracle's per-sample dicts."""
-    from oracle import pyoracle as po
-    from tests.util import py_params
+def reference_args(libdir=None, bindir=None, **kw):
+    """The args namespace fields the reference code reads (mirge/libs/parse.py defaults unless overridden)."""
+    a = argparse.Namespace(threads=2, bowtie_path=str(bindir) if bindir else None, bowtieVersion="True", quiet=True,
+                           organism_name=ORG, libraries_path=str(libdir) if libdir else None, spikeIn=True, bam_out=False,
+                           tRNA_frag=False, crThreshold="0.1", gff_out=False, AtoI=False, isoform_entropy=False,
+                           novel_miRNA=False,
+                           adapters=[("back", ILLUMINA)], error_rate=0.12, overlap=3, indels=True, match_adapter_wildcards=True,
+                           match_read_wildcards=False, times=1, action="trim", nextseq_trim=None, quality_cutoff="10",
+                           phred64=33, trim_n=False, cut=[], minimum_length=16, uniq_mol_ids=None, qiagenumi=False,
+                           umiDedup=False, tcf_out=False, fasta=False, buffer_size=60000, cutadaptVersion=("3", "1"))
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
 
-    p = py_params(cfg)
-    counts = {}
-    src, trc, tru = {}, {}, {}
-    frames = []
-    for name, data in zip(SAMPLES, fastqs):
-        d = po.digest_sample(data, p)
-        src[name], trc[name], tru[name] = d.count, d.trimmed, len(d.table)
-        frames.append(pd.DataFrame(list(d.table.items()), columns=["Sequence", name]).set_index("Sequence"))
-    collapsed_df = frames[0]
-    for f in frames[1:]:
-        collapsed_df = collapsed_df.join(f, how="outer")
-    collapsed_df = collapsed_df.fillna(0).astype(int)
-    flags = ["exact miRNA", "hairpin miRNA", "mature tRNA", "primary tRNA", "snoRNA", "rRNA", "ncrna others", "mRNA",
-             "isomiR miRNA", "spike-in"]
-    complete_set = collapsed_df.assign(**dict.fromkeys(flags, ""))
-    complete_set = complete_set.assign(annotFlag=0)
-    complete_set = complete_set.reindex(columns=["annotFlag"] + flags + SAMPLES)
-    complete_set = complete_set.astype({"annotFlag": int})
-    return complete_set, src, trc, tru
+
+def digest_cases(rng):
+    """Extra digest-only cases: (directory name, args overrides, FASTQ bytes per sample)."""
+    B = np.array(list("ACGT"))
+
+    def reads(n, build, L=60, lowq_tail=True, tag="r"):
+        out = []
+        for i in range(n):
+            s = build(i)[:L]
+            q = np.clip(rng.integers(25, 41, len(s)) - (np.arange(len(s)) > L - 12) * rng.integers(0, 32) * lowq_tail, 2, 41)
+            out.append("@%s.%d\n%s\n+\n%s\n" % (tag, i, s, "".join(chr(33 + int(v)) for v in q)))
+        return "".join(out).encode()
+
+    pool = ["".join(rng.choice(B, rng.integers(17, 28))) for _ in range(60)]
+
+    def insert():
+        r = rng.random()
+        if r < 0.85:
+            return pool[int(rng.zipf(1.4)) % len(pool)]
+        if r < 0.93:
+            return "".join(rng.choice(B, rng.integers(5, 15)))  # shorter than -m after trimming
+        return "".join(rng.choice(B, rng.integers(16, 40)))
+
+    def noisy(ad, p=0.03):
+        return "".join(str(rng.choice(B)) if rng.random() < p else c for c in ad)
+
+    def rnd(k):
+        return "".join(rng.choice(B, k))
+
+    umi_pool = [rnd(8) for _ in range(12)]  # few UMIs: PCR duplicates collapse at the first level
+
+    def ill4n(i):  # 4N + insert + 4N + adapter (docs/source/quick_start.md "-umi 4,4")
+        u = umi_pool[int(rng.integers(len(umi_pool)))]
+        return u[:4] + insert() + u[4:] + noisy(ILLUMINA) + rnd(40)
+
+    def qia(i):  # insert + inner adapter + 12-nt UMI + outer adapter (--qiagenumi -umi 0,12)
+        ins = insert()
+        if rng.random() < 0.05:
+            ins = ins + ins[:6] + ins  # the trimmed read occurs twice: exercises str.split(trimmed)[1]
+        tail = noisy(QIA_INNER) + rnd(12) + "AGATCGGAAGAGCACACGTCTGAACTCCAGTCAC"
+        if rng.random() < 0.1:
+            tail = tail[: int(rng.integers(3, 25))]
+        return ins + tail + rnd(30)
+
+    def nxt(i):  # poly-G tails, N ends, cuts
+        s = insert() + noisy(ILLUMINA) + "G" * int(rng.integers(0, 30)) + rnd(30)
+        if rng.random() < 0.2:
+            s = "N" * int(rng.integers(1, 3)) + s
+        return s
+
+    return [
+        ("ref_case2_umi", dict(uniq_mol_ids="4,4", umiDedup=False, tcf_out=True), [reads(1500, ill4n, tag="u%d" % k) for k in range(2)]),
+        ("ref_case3_umi_dedup", dict(uniq_mol_ids="4,4", umiDedup=True), [reads(1500, ill4n, tag="d")]),
+        ("ref_case4_qiagen", dict(adapters=[("back", QIA_INNER)], uniq_mol_ids="0,12", qiagenumi=True, umiDedup=True, tcf_out=True),
+         [reads(1500, qia, L=75, tag="q%d" % k) for k in range(2)]),
+        ("ref_case5_nextseq_cuts", dict(nextseq_trim=20, quality_cutoff="5,15", trim_n=True, cut=[2, -3], times=2, minimum_length=14),
+         [reads(1500, nxt, L=75, tag="n")]),
+    ]
+
+
+def run_digest_case(baking, name, overrides, fastqs):
+    """Reference baking() on the case's FASTQ files; writes inputs, the DataFrame and the counters."""
+    import json
+
+    case = HERE / name
+    if case.exists():
+        shutil.rmtree(case)
+    case.mkdir()
+    samples = ["s%d" % (i + 1) for i in range(len(fastqs))]
+    files = []
+    for sname, data in zip(samples, fastqs):
+        f = case / (sname + ".fastq")
+        f.write_bytes(data)
+        files.append(str(f))
+    args = reference_args(**overrides)
+    with tempfile.TemporaryDirectory() as tmp:
+        df, src, trc, tru = baking(args, files, samples, Path(tmp))            # digest.py:105
+        df.sort_index(kind="stable").to_csv(case / "complete_set.csv")         # single-sample order is arbitrary: sorted
+        for extra in sorted(os.listdir(tmp)):
+            if extra.endswith("_umiCounts.csv") or extra.endswith(".trim.collapse.fa"):
+                shutil.copy(Path(tmp) / extra, case / extra)
+    json.dump({"args": {k: v for k, v in overrides.items()}, "samples": samples, "sampleReadCounts": src, "trimmedReadCounts": trc,
+               "trimmedReadCountsUnique": tru, "dtypes": {c: str(t) for c, t in df.dtypes.items()}},
+              open(case / "counters.json", "w"), indent=1, sort_keys=True)
+    print("wrote", case, "rows", len(df), src, trc, tru)
 
 
 def main():
     if not REFERENCE.exists():
         sys.exit("reference checkout %s not found" % REFERENCE)
-    stub_third_party()
+    from tests.golden import standins
+
+    standins.install(REFERENCE)
+    from mirge.libs.digest import baking
     from mirge.libs.manifoldAlign import bwtAlign  # the reference's own code
     from mirge.libs.summary import summarize
-
-    from mirge_b200 import params as P
 
     rng = np.random.default_rng(20260117)
     libs = make_libraries(rng)
@@ -256,8 +323,7 @@ def main():
         with gzip.GzipFile(CASE / (name + ".fastq.gz"), "wb", mtime=0) as f:
             f.write(data)
 
-    cfg = P.TrimConfig(adapters=[("back", "TGGAATTCTCGGGTGCCAAGGAACTCCAG")], quality_cutoff="20", count_mode="head")
-    df, src, trc, tru = oracle_matrix(fastqs, cfg)
+    files = [str(CASE / (name + ".fastq.gz")) for name in SAMPLES]
 
     with tempfile.TemporaryDirectory() as tmp:
         bindir = Path(tmp) / "bin"
@@ -268,7 +334,8 @@ def main():
             p.chmod(p.stat().st_mode | stat.S_IEXEC)
         work = Path(tmp) / "work"
         work.mkdir()
-        args = reference_args(libdir, bindir)
+        args = reference_args(libdir, bindir, quality_cutoff="20")
+        df, src, trc, tru = baking(args, files, SAMPLES, work)               # digest.py:105
         out = bwtAlign(args, df, work, DB)                                   # manifoldAlign.py:68
         pdMapped = out[out.annotFlag.eq(1)]                                  # __main__.py:164
         pdUnmapped = out[out.annotFlag.eq(0)]                                # __main__.py:165
@@ -285,6 +352,8 @@ def main():
         % (pd.__version__, n_map, n_un))
     print("wrote", CASE, "mapped", n_map, "unmapped", n_un)
     print((CASE / "annotation.report.csv").read_text())
+    for name, overrides, fq in digest_cases(rng):
+        run_digest_case(baking, name, overrides, fq)
 
 
 if __name__ == "__main__":

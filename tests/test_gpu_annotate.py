@@ -9,7 +9,7 @@ import pytest
 
 from mirge_b200 import abi
 from oracle import coracle, pyoracle as po
-from tests.util import ILL, random_fastq
+from tests.util import ILL, make_args, random_fastq  # noqa: F401
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -162,18 +162,6 @@ def write_lib_dir(tmp, libs, organism="human", db="miRBase"):
                 for i in range(0, len(s), 60):
                     f.write(s[i:i + 60] + "\n")
     return tmp
-
-
-def make_args(**kw):
-    a = argparse.Namespace(
-        adapters=[("back", ILL)], error_rate=0.12, overlap=3, indels=True, match_adapter_wildcards=True,
-        match_read_wildcards=False, times=1, action="trim", nextseq_trim=None, quality_cutoff="10", phred64=33,
-        trim_n=False, cut=[], minimum_length=16, uniq_mol_ids=None, qiagenumi=False, umiDedup=False, quiet=True,
-        tcf_out=False, bam_out=False, tRNA_frag=False, spikeIn=False, threads=1, organism_name="human",
-        libraries_path=None, bowtie_path=None, bowtieVersion="1.3.0", cutadaptVersion=(3, 1), buffer_size=4000000, fasta=False)
-    for k, v in kw.items():
-        setattr(a, k, v)
-    return a
 
 
 def test_baking_and_bwtalign_end_to_end(dev, tmp_path):

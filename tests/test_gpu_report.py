@@ -69,3 +69,27 @@ def test_device_resident_sums_match_dataframe_path(dev, tmp_path):
         for name, rnd in RP._ROUND_OF.items():
             assert int(rs[rnd]) == int(row[col[name]]), name
         assert int(can.sum()) == int(rs[0]) and int(iso.sum()) == int(rs[8])
+
+
+from tests.test_reference_golden import DIGEST_CASES, load_digest_case, sorted_lines, tcf_pairs  # noqa: E402
+
+
+@pytest.mark.parametrize("name", DIGEST_CASES)
+def test_baking_matches_reference_baking(dev, tmp_path, name):
+    """Product baking() vs the files the reference's own baking() wrote (UMI flanks with and without -udd,
+    qiagen UMIs, NextSeq + two-sided quality cut-offs + -NX + -u cuts + times=2; side files included)."""
+    from mirge_b200 import digest as DG
+
+    d, meta, args, files = load_digest_case(name)
+    df, src, trc, tru = DG.baking(args, files, meta["samples"], str(tmp_path), device=dev, batch_bytes=70_000)
+    assert src == meta["sampleReadCounts"] and trc == meta["trimmedReadCounts"] and tru == meta["trimmedReadCountsUnique"]
+    df.to_csv(tmp_path / "complete_set.csv")
+    assert (tmp_path / "complete_set.csv").read_text() == open(os.path.join(d, "complete_set.csv")).read()
+    assert {c: str(t) for c, t in df.dtypes.items() if str(t) == "int64"} == {c: t for c, t in meta["dtypes"].items() if t == "int64"}
+    for s in meta["samples"]:
+        umi_csv = os.path.join(d, s + "_umiCounts.csv")
+        if os.path.exists(umi_csv):
+            assert sorted_lines(str(tmp_path / (s + "_umiCounts.csv"))) == sorted_lines(umi_csv)
+        tcf = os.path.join(d, s + ".trim.collapse.fa")
+        if os.path.exists(tcf):
+            assert tcf_pairs(str(tmp_path / (s + ".trim.collapse.fa"))) == tcf_pairs(tcf)

@@ -63,3 +63,66 @@ def test_annotation_report_matches_reference(oracle_run):
     report, mir = po.summarize_counts(annot, counts, SAMPLES, src, trc, tru, merges, libs["mirna"].names, 0.1, True)
     assert po.report_csv(report, SAMPLES, True) == golden("annotation.report.csv")
     assert po.mir_counts_csv(mir, SAMPLES) == golden("miR.Counts.csv")
+
+
+# ---- digest-only cases: the reference's baking() (worker, parent merge, UMI levels, matrix, counters, side files)
+
+DIGEST_CASES = ["ref_case2_umi", "ref_case3_umi_dedup", "ref_case4_qiagen", "ref_case5_nextseq_cuts"]
+
+
+def load_digest_case(name):
+    import json
+
+    from tests.util import make_args
+
+    d = os.path.join(os.path.dirname(__file__), "golden", name)
+    meta = json.load(open(os.path.join(d, "counters.json")))
+    ov = dict(meta["args"])
+    if "adapters" in ov:
+        ov["adapters"] = [tuple(a) for a in ov["adapters"]]
+    args = make_args(**ov)
+    files = [os.path.join(d, s + ".fastq") for s in meta["samples"]]
+    return d, meta, args, files
+
+
+def sorted_lines(path, skip_header=True):
+    with open(path) as f:
+        lines = f.read().splitlines()
+    return sorted(lines[1:] if skip_header else lines)
+
+
+def tcf_pairs(path):
+    """(count, sequence) pairs of a .trim.collapse.fa and the check that headers are numbered by descending count."""
+    with open(path) as f:
+        lines = f.read().splitlines()
+    pairs = []
+    for i in range(0, len(lines), 2):
+        n, c = lines[i][4:].split("_")
+        assert int(n) == i // 2 + 1
+        pairs.append((int(c), lines[i + 1]))
+    assert [c for c, _ in pairs] == sorted((c for c, _ in pairs), reverse=True)
+    return sorted(pairs)
+
+
+@pytest.mark.parametrize("name", DIGEST_CASES)
+def test_oracle_digest_matches_reference_baking(name):
+    d, meta, args, files = load_digest_case(name)
+    p = py_params(P.TrimConfig.from_args(args, "head"))
+    tables, src, trc, tru = [], {}, {}, {}
+    for s, f in zip(meta["samples"], files):
+        dg = po.digest_sample(open(f, "rb").read(), p, umi_dedup=bool(args.umiDedup), buffer_size=60000)
+        tables.append(dg.table)
+        src[s], trc[s], tru[s] = dg.count, dg.trimmed, len(dg.table)
+        umi_csv = os.path.join(d, s + "_umiCounts.csv")
+        if os.path.exists(umi_csv):
+            assert sorted("%s,%s,%d" % r for r in dg.umi_rows) == sorted_lines(umi_csv)
+        tcf = os.path.join(d, s + ".trim.collapse.fa")
+        if os.path.exists(tcf):
+            assert sorted((c, k) for k, c in dg.table.items()) == tcf_pairs(tcf)
+    assert src == meta["sampleReadCounts"] and trc == meta["trimmedReadCounts"] and tru == meta["trimmedReadCountsUnique"]
+    counts = {}
+    for j, t in enumerate(tables):
+        for k, c in t.items():
+            counts.setdefault(k, [0] * len(tables))[j] = c
+    rows = [(k, 0, [""] * 10, counts[k]) for k in sorted(counts)]
+    assert po.table_csv(rows, meta["samples"], True) == open(os.path.join(d, "complete_set.csv")).read()

@@ -1,4 +1,6 @@
 """Shared helpers for the tests: small seeded FASTQ generator and parameter conversion."""
+import argparse
+
 import numpy as np
 
 import mirge_b200  # noqa: F401
@@ -98,3 +100,15 @@ CONFIG_DATA = {
     "long_adapter": dict(adapter=LONG_AD, L=90),
     "noq_m1": dict(varlen=True),
 }
+
+
+def make_args(**kw):
+    a = argparse.Namespace(
+        adapters=[("back", ILL)], error_rate=0.12, overlap=3, indels=True, match_adapter_wildcards=True,
+        match_read_wildcards=False, times=1, action="trim", nextseq_trim=None, quality_cutoff="10", phred64=33,
+        trim_n=False, cut=[], minimum_length=16, uniq_mol_ids=None, qiagenumi=False, umiDedup=False, quiet=True,
+        tcf_out=False, bam_out=False, tRNA_frag=False, spikeIn=False, threads=1, organism_name="human",
+        libraries_path=None, bowtie_path=None, bowtieVersion="1.3.0", cutadaptVersion=(3, 1), buffer_size=4000000, fasta=False)
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
