@@ -137,7 +137,8 @@ typedef struct mirge_library {
   const uint32_t *d_idx_bucket; /* [2^bucket_bits + 1] */
   const uint32_t *d_ref_block;  /* [(n_bases >> ref_block_shift) + 1] reference holding base b << ref_block_shift */
   uint32_t ref_block_shift;
-  uint32_t reserved;
+  uint32_t filter_bases;        /* 0 = no prefix filter, else 4..16: d_filter has 4^filter_bases bits */
+  const uint32_t *d_filter;     /* presence bitmap of the first filter_bases bases of every indexed position */
 } mirge_library;
 
 #define MIRGE_SELECT_LEN_LT26 0    /* round 0 (manifoldAlign.py:93)  */
@@ -268,6 +269,11 @@ int mirge_partition_pack(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d
  * sort that builds mirge_library.d_idx_*. */
 int mirge_lib_kmers(mirge_ctx *ctx, const mirge_library *lib, uint32_t *d_kmer, uint8_t *d_valid,
                     void *stream);
+/* Presence bitmap over the first prefix_bases (4..16) bases of every position with at least that many usable
+ * bases (d_kmer / d_valid as written by mirge_lib_kmers): d_filter (4^prefix_bases bits, zeroed here) becomes
+ * mirge_library.d_filter.  A seed piece whose prefix bit is clear has no occurrence in the library. */
+int mirge_lib_filter(mirge_ctx *ctx, const uint32_t *d_kmer, const uint8_t *d_valid, uint32_t n_bases,
+                     uint32_t prefix_bases, uint32_t *d_filter, void *stream);
 /* One bowtie round over the keys of table t.  Keys selected by policy->select that have a valid
  * alignment get d_annot_round[id] = policy->round and d_hit[id] = canonical pick (minimum of
  * (n_mismatch, reference index, offset) over the valid hit set). */
@@ -276,10 +282,13 @@ int mirge_annotate_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_r
                          uint64_t *d_hit, void *stream);
 
 /* The same for several consecutive rounds in one launch (libs[i] / policies[i] = round i of the call):
- * every key is read once and leaves at the first round that hits it.  At most 10 rounds per call. */
+ * every key is read once and leaves at the first round that hits it.  At most 10 rounds per call.
+ * d_order_scratch: NULL, or u32[MIRGE_ANNOTATE_ORDER_BINS + n_keys] scratch; with it the sequences are
+ * processed grouped by length (homogeneous warps), which changes the speed, never the result. */
+#define MIRGE_ANNOTATE_ORDER_BINS 1024
 int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, const mirge_round_policy *policies,
                           int n_rounds, const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round,
-                          uint64_t *d_hit, void *stream);
+                          uint64_t *d_hit, uint32_t *d_order_scratch, void *stream);
 
 /* ---- stage 4: counters of annotation.report.csv (summarize, summary.py:692-698,716-770) ---- */
 /* For every (key id, count) pair of ONE sample (the output of mirge_table_drain):

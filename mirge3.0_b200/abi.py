@@ -11,6 +11,7 @@ MAX_ADAPTERS = 4
 MAX_ADAPTER_LEN = 64
 MAX_MODS = 8
 MAX_READ_LEN = 512
+ANNOTATE_ORDER_BINS = 1024  # MIRGE_ANNOTATE_ORDER_BINS
 
 MOD_NEXTSEQ, MOD_QUALITY, MOD_ADAPTER, MOD_NEND, MOD_CUT = 1, 2, 3, 4, 5
 UMI_NONE, UMI_FLANKS, UMI_QIAGEN = 0, 1, 2
@@ -84,7 +85,8 @@ class Library(C.Structure):
         ("d_idx_bucket", C.c_void_p),
         ("d_ref_block", C.c_void_p),
         ("ref_block_shift", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("filter_bases", C.c_uint32),
+        ("d_filter", C.c_void_p),
     ]
 
 
@@ -137,9 +139,10 @@ SYMBOLS = {
     ),
     "mirge_partition_pack": (C.c_int, [_P, C.POINTER(Table), _P, _P, _U64, _P, _P, _P]),
     "mirge_lib_kmers": (C.c_int, [_P, C.POINTER(Library), _P, _P, _P]),
+    "mirge_lib_filter": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     "mirge_annotate_rounds": (
         C.c_int,
-        [_P, C.POINTER(Library), C.POINTER(RoundPolicy), C.c_int, C.POINTER(Table), _U64, _P, _P, _P],
+        [_P, C.POINTER(Library), C.POINTER(RoundPolicy), C.c_int, C.POINTER(Table), _U64, _P, _P, _P, _P],
     ),
     "mirge_report_reduce": (C.c_int, [_P, _P, _P, _P, _P, _U64, C.c_uint32, _P, _P, _P, _P]),
     "mirge_annotate_round": (

@@ -69,6 +69,33 @@ extern "C" int mirge_lib_kmers(mirge_ctx *ctx, const mirge_library *lib, uint32_
   return MIRGE_OK;
 }
 
+// Presence bitmap over the first `bases` bases of every indexed position: bit (k-mer >> (32 - 2 * bases)) is set
+// when some position has at least `bases` usable bases starting with that prefix.  A seed piece of >= `bases`
+// bases whose prefix bit is clear cannot occur in the library (no false negatives), which ends most look-ups
+// of sequences the library does not contain with one load from a table small enough to stay in L2.
+__global__ void __launch_bounds__(256)
+lib_filter_kernel(const uint32_t *__restrict__ kmer, const uint8_t *__restrict__ valid, uint32_t n, uint32_t bases,
+                  uint32_t *__restrict__ filter) {
+  const uint32_t p = blockIdx.x * 256u + threadIdx.x;
+  if (p >= n || valid[p] < bases) return;
+  const uint32_t fi = bases >= 16 ? kmer[p] : (kmer[p] >> (32 - 2 * bases));
+  atomicOr(filter + (fi >> 5), 1u << (fi & 31));
+}
+
+extern "C" int mirge_lib_filter(mirge_ctx *ctx, const uint32_t *d_kmer, const uint8_t *d_valid, uint32_t n_bases, uint32_t prefix_bases,
+                                uint32_t *d_filter, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  if (!d_kmer || !d_valid || !d_filter) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "lib_filter: null buffer");
+  if (prefix_bases < 4 || prefix_bases > 16) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "lib_filter: prefix length must be 4..16");
+  if (n_bases == 0) return MIRGE_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  MIRGE_CUDA(ctx, cudaMemsetAsync(d_filter, 0, (size_t)1 << (2 * prefix_bases - 3), stream));
+  lib_filter_kernel<<<(n_bases + 255) / 256, 256, 0, stream>>>(d_kmer, d_valid, n_bases, prefix_bases, d_filter);
+  MIRGE_LAUNCH_CHECK(ctx, "lib_filter_kernel");
+  return MIRGE_OK;
+}
+
 // ------------------------------------------------------------------ search -------------------
 
 #define MAX_PIECES 4
@@ -167,6 +194,10 @@ __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const
       if (has_exc && query_has_n(qnx, a, b)) continue;
       const uint32_t span = (s == 16) ? 0u : ((1u << (2 * (16 - s))) - 1u);
       const uint32_t k_lo = query_kmer16(qw, a, nw) & ~span, k_hi = k_lo | span;
+      if (lib.filter_bases && (uint32_t)s >= lib.filter_bases) {  // prefix absent from the library: no candidates
+        const uint32_t fi = lib.filter_bases >= 16 ? k_lo : (k_lo >> (32 - 2 * lib.filter_bases));
+        if (!((lib.d_filter[fi >> 5] >> (fi & 31)) & 1u)) continue;
+      }
       const uint32_t bsh = 32 - lib.bucket_bits;
       uint32_t l = lib.d_idx_bucket[k_lo >> bsh], h = lib.d_idx_bucket[(k_hi >> bsh) + 1];
       const uint32_t hi0 = h;  // lower_bound(k_lo), then upper_bound(k_hi), inside the bucket range
@@ -246,12 +277,14 @@ __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const
 // a round's window differs (poly-T stripping of round 3, -5/-3 trimming of round 8).
 __global__ void __launch_bounds__(ANN_THREADS)
 annotate_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_keys, uint8_t *__restrict__ annot_round,
-                uint64_t *__restrict__ hit) {
+                uint64_t *__restrict__ hit, const uint32_t *__restrict__ order) {
   __shared__ uint32_t s_qw[ANN_THREADS / 32][QW_MAX], s_qnx[ANN_THREADS / 32][QW_MAX];
   __shared__ uint32_t s_meta[ANN_THREADS / 32][4 + 3 * MAX_PIECES];
-  const uint64_t id = (uint64_t)blockIdx.x * ANN_THREADS + threadIdx.x;
+  const uint64_t slot = (uint64_t)blockIdx.x * ANN_THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool in_range = id < n_keys;
+  const bool in_range = slot < n_keys;
+  // with `order` the threads of a warp hold sequences of the same length (see order_* kernels below)
+  const uint64_t id = (in_range && order) ? order[slot] : slot;
   uint32_t qw[QW_MAX], qnx[QW_MAX];
   const uint32_t *key = nullptr, *pay = nullptr, *exc = nullptr;
   int len = 0, nexc = 0, cur_qs = -1, cur_qe = -1, tlen = -1;
@@ -337,11 +370,58 @@ annotate_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_k
   }
 }
 
+// ---- sequences ordered by length (counting sort) -----------------------------------------------------------
+// Key ids are handed out in emission order, so a warp would hold a mix of short, library-derived sequences
+// (several verified candidates per round) and long ones that no library contains (a few look-ups per round) and
+// run at the pace of its busiest lane.  Grouping by length makes warps homogeneous: same rounds selected, same
+// query word count, similar candidate work.  order[] = key ids, shortest first; bins[] = MIRGE_MAX_READ_LEN + 2
+// cursors.  The order inside a bin is arbitrary; results do not depend on it.
+#define ORDER_BINS (MIRGE_MAX_READ_LEN + 2)
+static_assert(ORDER_BINS <= MIRGE_ANNOTATE_ORDER_BINS, "scratch layout");
+
+__global__ void __launch_bounds__(256) order_hist_kernel(mirge_table t, uint64_t n_keys, uint32_t *__restrict__ bins) {
+  __shared__ uint32_t s_bins[ORDER_BINS];
+  for (int b = threadIdx.x; b < ORDER_BINS; b += 256) s_bins[b] = 0;
+  __syncthreads();
+  for (uint64_t id = (uint64_t)blockIdx.x * 256 + threadIdx.x; id < n_keys; id += (uint64_t)gridDim.x * 256) {
+    const uint32_t len = min(key_len(t.d_arena[t.d_key_ref[id]]), (uint32_t)(ORDER_BINS - 1));
+    atomicAdd(&s_bins[len], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < ORDER_BINS; b += 256)
+    if (s_bins[b]) atomicAdd(&bins[b], s_bins[b]);
+}
+
+__global__ void order_scan_kernel(uint32_t *bins) {  // one thread: 514 bins
+  uint32_t run = 0;
+  for (int b = 0; b < ORDER_BINS; ++b) {
+    const uint32_t c = bins[b];
+    bins[b] = run;
+    run += c;
+  }
+}
+
+__global__ void __launch_bounds__(256) order_scatter_kernel(mirge_table t, uint64_t n_keys, uint32_t *__restrict__ bins,
+                                                            uint32_t *__restrict__ order) {
+  const uint64_t id = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  if (id >= n_keys) return;
+  const uint32_t len = min(key_len(t.d_arena[t.d_key_ref[id]]), (uint32_t)(ORDER_BINS - 1));
+  // one atomic per group of lanes with the same length
+  const unsigned peers = __match_any_sync(__activemask(), len);
+  const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(&bins[len], (uint32_t)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  order[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)id;
+}
+
 static int check_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_round_policy *policy) {
   if (!lib->d_packed || !lib->d_nmask || !lib->d_ref_off || !lib->d_idx_kmer || !lib->d_idx_pos || !lib->d_idx_bucket ||
       !lib->d_ref_block)
     MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: library has no index");
   if (lib->ref_block_shift > 20) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: ref_block_shift out of range");
+  if (lib->filter_bases && (!lib->d_filter || lib->filter_bases < 4 || lib->filter_bases > 16))
+    MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: bad prefix filter");
   if (lib->bucket_bits < 1 || lib->bucket_bits > 28) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: bucket_bits out of range");
   if (policy->seed_mm < 0 || policy->seed_mm > 3 || policy->total_mm < policy->seed_mm || policy->trim5 < 0 || policy->trim3 < 0)
     MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: unsupported policy");
@@ -350,9 +430,11 @@ static int check_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_rou
 }
 
 extern "C" int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, const mirge_round_policy *policies, int n_rounds,
-                                     const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round, uint64_t *d_hit, void *stream_) {
+                                     const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round, uint64_t *d_hit,
+                                     uint32_t *d_order_scratch, void *stream_) {
   if (!ctx) return MIRGE_ERR_ARG;
   if (!libs || !policies || !t || !d_annot_round || !d_hit) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: null argument");
+  if (n_keys > 0xFFFFFFFFull) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: more than 2^32 sequences in one call");
   if (n_rounds < 0 || n_rounds > MAX_ROUNDS) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: at most %d rounds per call", MAX_ROUNDS);
   if (n_keys == 0 || n_rounds == 0) return MIRGE_OK;
   RoundSet rs;
@@ -368,7 +450,20 @@ extern "C" int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, 
   if (rs.n == 0) return MIRGE_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
-  annotate_kernel<<<(unsigned)((n_keys + ANN_THREADS - 1) / ANN_THREADS), ANN_THREADS, 0, stream>>>(rs, *t, n_keys, d_annot_round, d_hit);
+  const uint32_t *order = nullptr;
+  if (d_order_scratch) {
+    uint32_t *bins = d_order_scratch, *ord = d_order_scratch + MIRGE_ANNOTATE_ORDER_BINS;
+    MIRGE_CUDA(ctx, cudaMemsetAsync(bins, 0, ORDER_BINS * sizeof(uint32_t), stream));
+    uint64_t hg = (n_keys + 255) / 256;
+    if (hg > (uint64_t)ctx->sm_count * 8) hg = (uint64_t)ctx->sm_count * 8;
+    order_hist_kernel<<<(unsigned)hg, 256, 0, stream>>>(*t, n_keys, bins);
+    order_scan_kernel<<<1, 1, 0, stream>>>(bins);
+    order_scatter_kernel<<<(unsigned)((n_keys + 255) / 256), 256, 0, stream>>>(*t, n_keys, bins, ord);
+    MIRGE_LAUNCH_CHECK(ctx, "order kernels");
+    order = ord;
+  }
+  annotate_kernel<<<(unsigned)((n_keys + ANN_THREADS - 1) / ANN_THREADS), ANN_THREADS, 0, stream>>>(rs, *t, n_keys, d_annot_round, d_hit,
+                                                                                                  order);
   MIRGE_LAUNCH_CHECK(ctx, "annotate_kernel");
   return MIRGE_OK;
 }
@@ -377,5 +472,5 @@ extern "C" int mirge_annotate_round(mirge_ctx *ctx, const mirge_library *lib, co
                                     uint64_t n_keys, uint8_t *d_annot_round, uint64_t *d_hit, void *stream_) {
   if (!ctx) return MIRGE_ERR_ARG;
   if (!lib || !policy) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: null argument");
-  return mirge_annotate_rounds(ctx, lib, policy, 1, t, n_keys, d_annot_round, d_hit, stream_);
+  return mirge_annotate_rounds(ctx, lib, policy, 1, t, n_keys, d_annot_round, d_hit, nullptr, stream_);
 }

@@ -121,7 +121,8 @@ class DeviceLibrary:
         self.packed, self.nmask = pack_text(text)
         if self.packed.numel() == 0:
             self.packed = torch.zeros(1, dtype=torch.int32, device=dev.tdev)
-        self.idx_kmer = self.idx_pos = self.idx_bucket = None
+        self.idx_kmer = self.idx_pos = self.idx_bucket = self.filter = None
+        self.filter_bases = 0
         self.n_idx = 0
         self.bucket_bits = 4
         # coarse position -> reference map (one entry per 64 bases) replacing a binary search over ref_off
@@ -136,7 +137,8 @@ class DeviceLibrary:
                            0 if self.idx_kmer is None else self.idx_kmer.data_ptr(),
                            0 if self.idx_pos is None else self.idx_pos.data_ptr(), self.n_idx, self.bucket_bits,
                            0 if self.idx_bucket is None else self.idx_bucket.data_ptr(),
-                           self.ref_block.data_ptr(), self.ref_block_shift, 0)
+                           self.ref_block.data_ptr(), self.ref_block_shift, self.filter_bases,
+                           0 if self.filter is None else self.filter.data_ptr())
 
     def _build_index(self):
         d = self.dev
@@ -148,6 +150,13 @@ class DeviceLibrary:
         st = self._base_struct()
         d.check(d.lib.mirge_lib_kmers(d.ctx, C.byref(st), _ptr(kmer), _ptr(valid), d.stream()))
         d.launches += 1
+        # prefix presence bitmap, about 16 bits per indexed position (4^f bits, f = 10..16): 128 KB for a miRNA
+        # library, 32 MB for 10^7 bases, 512 MB (direct 16-mer addressing) for an mRNA library
+        fb = int(min(16, max(10, math.ceil(math.log(max(16 * self.n_bases, 4), 4)))))
+        self.filter = d.empty(1 << (2 * fb - 5), torch.int32)
+        d.check(d.lib.mirge_lib_filter(d.ctx, _ptr(kmer), _ptr(valid), self.n_bases, fb, _ptr(self.filter), d.stream()))
+        d.launches += 1
+        self.filter_bases = fb
         pos = torch.nonzero(valid >= MIN_INDEX_K).squeeze(1)
         k64 = kmer[pos].to(torch.int64) & 0xFFFFFFFF
         del kmer, valid
