@@ -75,7 +75,7 @@ class KeySet:
         return cls(dev, arena, key_off, n)
 
 
-def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = False, fused: bool = True, ordered: bool = True):
+def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = False, fused: bool = True, ordered: bool = False):
     """Run rounds 0..8 (0..9 with spike-ins) in miRge's order (manifoldAlign.py:86-135).
     Returns device tensors (annot_round uint8[n] with 0xFF = unannotated, hit int64[n])."""
     n = keys.n
