@@ -41,7 +41,8 @@ def parse_args():
     ap.add_argument("--reads", type=int, default=50_000_000, help="reads per GPU (default: the C2 sample size)")
     ap.add_argument("--mrna", type=int, default=100_000, help="mRNA library entries")
     ap.add_argument("--count-mode", default="head", choices=["head", "release"])
-    ap.add_argument("--cpu-sample", type=int, default=400_000, help="reads of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="reads of the bounded CPU sample (0 = 12 M for the cpu_baseline leg, 4 M per step for --impl reference)")
     ap.add_argument("--batch-mb", type=int, default=2048)
     ap.add_argument("--e2e-batch-mb", type=int, default=256, help="piece size of the host-fed (e2e) pipeline")
     ap.add_argument("--no-e2e", action="store_true")
@@ -104,7 +105,7 @@ def run_reference(args):
     cfg = synth.trim_config_for(CFG_ID, args.count_mode)
     cpu = CpuPath(libs, cfg, threads)
     gen = synth.ReadGenerator(libs, synth.CONFIGS[CFG_ID], "cpu")
-    sample = args.cpu_sample
+    sample = args.cpu_sample or 4_000_000
     fq = gen.fastq(sample).numpy()
     for _ in range(args.warmup):
         cpu.step(fq)
@@ -393,7 +394,7 @@ def run_b200(args):
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        sample = min(args.cpu_sample, args.reads)
+        sample = min(args.cpu_sample or 12_000_000, args.reads)
         sb = int(sample * rec_bytes * 1.02) + 4096
         raw = fq[: min(sb, nbytes)].cpu().numpy()
         # cut at the end of read `sample`
@@ -428,10 +429,29 @@ def run_b200(args):
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_b200(args)
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, for one) are sent to stderr for the duration of the run
+    real_stdout = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    import io
+
+    buf = io.StringIO()
+    old, sys.stdout = sys.stdout, buf
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_b200(args)
+    finally:
+        sys.stdout = old
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    out = buf.getvalue()
+    if out:
+        sys.stdout.write(out)
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":
