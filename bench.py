@@ -375,6 +375,8 @@ def run_b200(args):
     kinfo.setdefault("collapse", {})["achieved_gbs"] = round(col_gbs, 1)
     kinfo["collapse"]["frac_hbm"] = round(col_gbs / peak, 4)
     kinfo["collapse"]["algorithmic_bytes_per_read"] = round(b_col_total / args.reads, 1)
+    kinfo["trim"]["dp_search_frac"] = round(stats.get("dp_reads", 0) / max(stats["records"], 1), 4)
+    kinfo["trim"]["cost_column_frac"] = round(stats.get("dp_redo", 0) / max(stats["records"], 1), 4)
     kinfo["trim"]["second_pass_frac"] = round(stats.get("deferred", 0) / max(stats["records"], 1), 4)
     dom = max((("trim", trim_ms), ("collapse", col_ms), ("annotate", ann_ms)), key=lambda kv: kv[1])[0]
     traffic = None

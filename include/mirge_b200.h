@@ -194,18 +194,21 @@ int mirge_line_index(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, co
  *   d_key_off[e]    = word offset of the packed key in d_keys, or 0xFFFFFFFF when the slot is not
  *                     counted (length filter, digest.py:348,362,368).
  * d_trim_ctrl (8 x u64, zeroed by the caller): [0] key words used [1] emitted keys [2] error flags
- * [3] first malformed record, [5] reads deferred to the second pass.
- * d_slow: u32[n_records] scratch.  The bit-parallel kernel runs in two passes: the first resolves every
- * read whose adapter search needs no cost columns, the second re-does the rest (a few percent) with
- * full warps. */
+ * [3] first malformed record, [5] reads left to the whole-pipeline second pass, [6] reads whose adapter search
+ * ran the bit-vector DP, [7] of those, the ones that needed cost columns.
+ * d_scratch: mirge_trim_scratch_bytes(n_records) bytes, 16-byte aligned.  With 3' adapters of <= 32 nt the work
+ * is split at the adapter modifier: stage 1 handles every read up to there (an exact occurrence of the whole
+ * adapter settles the search), the reads that need the DP are listed in the scratch (record, window, packed
+ * text) and searched by list-driven kernels with sorted, full warps. */
+uint64_t mirge_trim_scratch_bytes(uint64_t n_records);
 int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, const uint32_t *d_line_start,
                uint64_t n_records, uint16_t *d_win, uint32_t *d_key_off, uint32_t *d_keys,
-               uint64_t keys_capacity_words, uint64_t *d_trim_ctrl, uint32_t *d_slow, void *stream);
+               uint64_t keys_capacity_words, uint64_t *d_trim_ctrl, void *d_scratch, void *stream);
 
-/* Kernel selection for mirge_trim: 0 = automatic (bit-parallel kernel when every adapter is a 3'
- * adapter with indels and <= 32 nt, else the generic full-DP kernel), 1 = always generic.  When the
- * bit-parallel kernel meets a record group that does not fit its shared-memory staging it sets bit 3
- * of d_trim_ctrl[2]; the caller then repeats the batch with mode 1. */
+/* Kernel selection for mirge_trim: 0 = automatic (split bit-parallel pipeline when every adapter is a 3'
+ * adapter with indels and <= 32 nt, else the generic full-DP kernel), 1 = always generic, 2 = bit-parallel
+ * kernel without the split (one kernel + second pass; kept for the parity tests).  When the generic-free
+ * path meets a record group that does not fit its shared-memory staging the group goes to the second pass. */
 int mirge_trim_mode(mirge_ctx *ctx, int mode);
 
 /* ---- stage 2: collapse (digest.py:141-163,164-205,237-245) --------------------------------- */

@@ -117,6 +117,7 @@ SYMBOLS = {
     "mirge_tokenise_scratch_bytes": (_U64, [_U64]),
     "mirge_tokenise_sync": (C.c_int, [_P, _P, _U64, C.c_int, _P, _PU64, _PU64, _P]),
     "mirge_line_index": (C.c_int, [_P, _P, _U64, _P, _P, _U64, _P]),
+    "mirge_trim_scratch_bytes": (_U64, [_U64]),
     "mirge_trim": (C.c_int, [_P, _P, _U64, _P, _U64, _P, _P, _P, _U64, _P, _P, _P]),
     "mirge_trim_mode": (C.c_int, [_P, C.c_int]),
     "mirge_table_reset": (C.c_int, [_P, C.POINTER(Table), _P]),

@@ -16,7 +16,8 @@ struct mirge_ctx {
   int params_set;
   int max_adapter_len;
   int fast_ok;    // every adapter is a 3' adapter with indels and m <= 32: bit-parallel trim kernel applies
-  int trim_mode;  // 0 = auto, 1 = force the generic full-DP kernel (tests)
+  int split_ok;   // the split pipeline (exact search + list-driven DP kernels) applies
+  int trim_mode;  // 0 = auto, 1 = force the generic full-DP kernel, 2 = bit-parallel kernel without the split (tests)
   int sm_count;
 };
 

@@ -101,6 +101,14 @@ extern "C" int mirge_set_trim_params(mirge_ctx *ctx, const mirge_trim_params *p)
   ctx->params_set = 1;
   ctx->max_adapter_len = maxm;
   ctx->fast_ok = fast_ok;
+  // split pipeline: not with qiagen UMIs (their key needs the read bytes after the pipeline) and only when no
+  // quality modifier follows the first adapter modifier (stipulate() never builds such a pipeline)
+  int split_ok = fast_ok && p->umi_mode != MIRGE_UMI_QIAGEN, seen_ad = 0;
+  for (int i = 0; i < p->n_mods; ++i) {
+    if (p->mod_kind[i] == MIRGE_MOD_ADAPTER) seen_ad = 1;
+    else if (seen_ad && (p->mod_kind[i] == MIRGE_MOD_NEXTSEQ || p->mod_kind[i] == MIRGE_MOD_QUALITY)) split_ok = 0;
+  }
+  ctx->split_ok = split_ok && seen_ad;
   return MIRGE_OK;
 }
 
@@ -246,6 +254,23 @@ struct FastCtx {
   int rbase;             // offset of the window being searched inside the read
 };
 
+// How the adapter search sees the read window: eq(eqt, j) = match mask of window base j (bit i-1 set <=> adapter
+// row i matches it).  ByteRead: ASCII bytes (shared-memory staging or the global stream), eqt indexed by byte.
+// PackedRead: the 2-bit packed pure-ACGT read of this thread (row stride TRIM_THREADS words), eqt indexed by the
+// 2-bit code -- used by the split pipeline, whose search kernel never touches the FASTQ bytes again.
+struct ByteRead {
+  const uint8_t *p;
+  __device__ __forceinline__ uint32_t eq(const uint32_t *eqt, int j) const { return eqt[p[j]]; }
+};
+struct PackedRead {
+  const uint32_t *ps;
+  int base;  // offset of the window inside the read
+  __device__ __forceinline__ uint32_t eq(const uint32_t *eqt, int j) const {
+    const int a = base + j;
+    return eqt[(ps[(a >> 4) * TRIM_THREADS] >> (2 * (a & 15))) & 3u];
+  }
+};
+
 struct ColBuf {
   uint32_t vp[RB], vn[RB];
   int j0;  // entry t holds column j0 + t
@@ -271,7 +296,8 @@ __device__ __forceinline__ int cell_cost(uint32_t vp, uint32_t vn, int r) {
   }
 
 // cost columns jc - span .. jc recomputed with a fresh start (exact where it matters, see above)
-__device__ __noinline__ void recompute(const uint32_t *eqt, const uint8_t *read, int jc, int span, ColBuf &cb) {
+template <class RV>
+__device__ __noinline__ void recompute(const uint32_t *eqt, const RV read, int jc, int span, ColBuf &cb) {
   const int j0 = max(0, jc - span);
   uint32_t vp = 0xFFFFFFFFu, vn = 0u;
   cb.j0 = j0;
@@ -279,7 +305,7 @@ __device__ __noinline__ void recompute(const uint32_t *eqt, const uint8_t *read,
   cb.vn[0] = vn;
   int t = 1;
   for (int j = j0 + 1; j <= jc; ++j, ++t) {
-    const uint32_t eq = eqt[read[j - 1]];
+    const uint32_t eq = read.eq(eqt, j - 1);
     uint32_t hp, hn;
     MYERS_STEP(eq, vp, vn, hp, hn)
     cb.vp[t] = vp;
@@ -298,7 +324,8 @@ __device__ __forceinline__ uint64_t read_window(const uint32_t *ps, int a0) {
 // (matches, origin) cutadapt's DP holds in cell (i, j) whose cost is c > 0, from the cost columns in cb.
 // jump: adapter without wildcards and a pure-ACGT packed read -- the run of matches up a diagonal is skipped
 // with one XOR + count-leading-zeros instead of one step per cell.
-__device__ __noinline__ void traceback(const int a, const uint32_t *eqt, const uint8_t *read, const FastCtx &fc, const ColBuf &cb,
+template <class RV>
+__device__ __noinline__ void traceback(const int a, const uint32_t *eqt, const RV read, const FastCtx &fc, const ColBuf &cb,
                                           int i, int j, int c, int &matches, int &origin) {
   const bool jump = fc.jump_ok && !c_p.ad[a].wildcard_ref;
   const uint64_t a2 = c_p.ad[a].a2;
@@ -323,7 +350,7 @@ __device__ __noinline__ void traceback(const int a, const uint32_t *eqt, const u
       const int t = (64 - __clzll((long long)x) + 1) >> 1;  // highest mismatching row <= r
       col -= r - t;
       r = t;
-    } else if ((eqt[read[col - 1]] >> (r - 1)) & 1u) {  // equal characters: diagonal, cost unchanged
+    } else if ((read.eq(eqt, col - 1) >> (r - 1)) & 1u) {  // equal characters: diagonal, cost unchanged
       --r; --col;
       continue;
     }
@@ -377,9 +404,10 @@ __device__ __forceinline__ bool traceback_cost1(const int a, const FastCtx &fc, 
 
 // A cell (i, j) of cost c reaches i matches only if every error is a deletion; that path leaves row 0 at
 // column j - i - c with a match, so adapter[0] must equal that read base (cheap necessary condition).
-__device__ __forceinline__ bool all_deletions_possible(const uint32_t *eqt, const uint8_t *read, int i, int j, int c) {
+template <class RV>
+__device__ __forceinline__ bool all_deletions_possible(const uint32_t *eqt, const RV read, int i, int j, int c) {
   const int o = j - i - c;
-  return o >= 0 && (eqt[read[o]] & 1u);
+  return o >= 0 && (read.eq(eqt, o) & 1u);
 }
 
 // candidate with at most `u` matches, cost c, scan index idx can still beat the best so far
@@ -397,8 +425,8 @@ __device__ __forceinline__ bool all_deletions_possible(const uint32_t *eqt, cons
 // general traceback) the search gives up with 2 and the read is queued for the second pass, which runs
 // this function without DEFER on a compacted list, so that the rare expensive path executes with full warps.
 // Returns 0 = no match, 1 = match in `out`, 2 = deferred.
-template <bool DEFER>
-__device__ __forceinline__ int locate_fast(const int a, const uint8_t *read, const int n, const FastCtx &fc, Match &out) {
+template <bool DEFER, class RV>
+__device__ __forceinline__ int locate_fast(const int a, const RV read, const int n, const FastCtx &fc, Match &out) {
   const unsigned lanes = __activemask();  // lanes searching together; re-converged after the divergent loops
   const DevAdapter &ad = c_p.ad[a];
   const int m = ad.m;
@@ -444,7 +472,7 @@ __device__ __forceinline__ int locate_fast(const int a, const uint8_t *read, con
   }
 
   for (int j = 1; j <= n; ++j) {
-    eq = eqt[read[j - 1]];
+    eq = read.eq(eqt, j - 1);
     const int score_prev = score;
     pvp = vp;
     pvn = vn;
@@ -568,7 +596,7 @@ __device__ __noinline__ int best_match(const uint8_t *read, int n, Match &best, 
   for (int a = 0; a < c_p.n_adapters; ++a) {
     Match mt;
     if (FAST) {
-      const int rc = locate_fast<DEFER>(a, read, n, fc, mt);
+      const int rc = locate_fast<DEFER>(a, ByteRead{read}, n, fc, mt);
       if (rc == 2) return -2;
       if (rc == 0) continue;
     } else if (!locate<MAXM>(a, read, n, mt)) continue;
@@ -635,143 +663,97 @@ __device__ __forceinline__ uint32_t key_byte(const uint8_t *seq, int start, int 
   return p < l1 ? seq[start + p] : seq[us + p - l1];
 }
 
-#define PACK_WORDS 8  // reads up to 128 bases keep their 2-bit text in registers for key emission
+#define PACK_WORDS 8             // reads up to 128 bases keep their 2-bit text in shared memory
+#define PS_ROWS (PACK_WORDS + 3)  // + zero words so that 64-bit windows may start at any base
 
-// Everything a thread does for record r once its bytes are addressable through B (shared-memory staging or
-// the global stream).  PASS 0: single pass; PASS 1: first pass (reads whose adapter search needs cost
-// columns are appended to d_slow and emit nothing); PASS 2: second pass over those reads.
-template <int MAXM, bool FAST, int PASS>
-__device__ __forceinline__ void process_record(const bool valid, const uint64_t r, const uint8_t *B, uint64_t nbytes,
-                                               const uint32_t *__restrict__ line_start, ushort4 *__restrict__ win,
-                                               uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys, uint64_t keys_cap,
-                                               unsigned long long *__restrict__ ctrl, uint32_t *__restrict__ d_slow, FastCtx &fc,
-                                               uint32_t *ps_mine) {
-  const int tid = threadIdx.x;
-  bool is_slow = false;
-  const int E = c_p.slots;
-  // per-slot windows live in local memory (dynamic slot index keeps the code small)
-  int w_start[MIRGE_MAX_MODS], w_stop[MIRGE_MAX_MODS], w_us[MIRGE_MAX_MODS], w_ue[MIRGE_MAX_MODS];
-  uint32_t w_words[MIRGE_MAX_MODS];  // 0 = not kept
+// ---- split pipeline ----------------------------------------------------------------------------------------
+// When every adapter qualifies for the bit-parallel search, the work of a read is cut at the first adapter
+// modifier into kernels whose threads all do the same kind of work:
+//   stage 1 (trim_kernel<32, true, 1>, all reads, bytes staged in shared memory): parse, 2-bit pack, the quality
+//     modifiers, and an exact search for the whole adapter -- cutadapt stops at the leftmost exact occurrence, so
+//     a hit settles the search.  Reads that need the DP are appended to a list (record index, window, packed
+//     text); the keys of the modifiers before the adapter are emitted here.
+//   stage 2 (trim_dp_kernel<true>, listed reads only, packed text only): counting sort of the CTA's reads by
+//     window length, bit-vector search, remaining modifiers, emission.  Searches that need cost columns go to a
+//     second list and
+//   stage 3 (trim_dp_kernel<false>) runs them with recompute + traceback, again with full, sorted warps.
+// Reads the split cannot take (non-ACGT characters, record groups larger than the staging buffer) go through
+// trim_kernel<32, true, 2>, the whole pipeline per read from the global stream.
+struct DpEntry {
+  uint32_t r;      // record index in the batch
+  uint32_t se;     // window at the adapter modifier: start | stop << 16
+  uint32_t sl;     // read length
+  uint32_t pad;
+};
+
+// first adapter modifier, and the number of emission slots stage 1 owns for a read that goes on to the search
+__device__ __forceinline__ int first_adapter_mod() {
+  int mi_ad = c_p.n_mods;
 #pragma unroll 1
-  for (int s = 0; s < E; ++s) { w_start[s] = w_stop[s] = w_us[s] = w_ue[s] = 0; w_words[s] = 0; }
-  const uint8_t *seq = nullptr;
-  uint32_t my_words = 0, my_kept = 0;
-  bool fast_emit = FAST;
-  if (valid) {
-    const uint4 ls = *(const uint4 *)(line_start + 4 * r);
-    const uint32_t nxt = line_start[4 * r + 4];
-    int sl = (int)(ls.z - 1 - ls.y), ql = (int)(nxt - 1 - ls.w);
-    if (sl > 0 && B[ls.y + sl - 1] == '\r') --sl;
-    if (ql > 0 && B[ls.w + ql - 1] == '\r') --ql;
-    const bool bad = B[ls.x] != '@' || B[ls.z] != '+' || sl != ql || sl > MIRGE_MAX_READ_LEN;
-    // lanes that run the modifier pipeline together; used to re-converge them after every modifier,
-    // whose data-dependent loops (quality scans, adapter search) otherwise leave the warp split
-    const unsigned good_lanes = __ballot_sync(__activemask(), !bad);
-    if (bad) {
-      atomicOr(ctrl + 2, (sl > MIRGE_MAX_READ_LEN && sl == ql) ? 4ull : 1ull);
-      atomicMax(ctrl + 3, ~(unsigned long long)r);
-    } else {
-      seq = B + ls.y;
-      const uint8_t *qual = B + ls.w;
-      int start = 0, stop = sl;
-      if (FAST) {
-        // 2-bit text of the whole read once, four bytes per step (SIMD-in-register), into shared memory:
-        // used by the traceback jumps and by key emission
-        fast_emit = sl <= 16 * PACK_WORDS;
-        if (PASS == 2 && (uint64_t)ls.y + 16 * ((sl + 15) >> 4) + 8 > nbytes) fast_emit = false;  // no over-read past the stream
-        if (fast_emit) {
-          const uint32_t *ap = (const uint32_t *)((uintptr_t)seq & ~(uintptr_t)3);
-          const uint32_t bs = ((uint32_t)(uintptr_t)seq & 3u) * 8u;
-          const int nwords = (sl + 15) >> 4;
-          uint32_t anyexc = 0, prev = ap[0];
-          int k = 1;
+  for (int i = c_p.n_mods - 1; i >= 0; --i)
+    if (c_p.kind[i] == MIRGE_MOD_ADAPTER) mi_ad = i;
+  return mi_ad;
+}
+
+// Leftmost p in [start, stop - m] with read[p : p + m] == adapter, or -1.  Pure-ACGT read packed two bits per
+// base (row stride TRIM_THREADS words, zero words after the text), plain adapter of m <= 32 bases in a2.  One
+// funnel shift + compare per position; the upper half is only looked at when the first 16 bases agree.
+__device__ __forceinline__ int exact_find(const uint32_t *ps, uint64_t a2, int m, int start, int stop) {
+  const int last = stop - m;
+  if (last < start) return -1;
+  const uint32_t a_lo = (uint32_t)a2, a_hi = (uint32_t)(a2 >> 32);
+  const uint32_t lo_mask = m >= 16 ? 0xFFFFFFFFu : ((1u << (2 * m)) - 1u);
+  const uint32_t hi_mask = m <= 16 ? 0u : (m >= 32 ? 0xFFFFFFFFu : ((1u << (2 * (m - 16))) - 1u));
+  int wb = start >> 4;
+  uint32_t x0 = ps[wb * TRIM_THREADS], x1 = ps[(wb + 1) * TRIM_THREADS], x2 = ps[(wb + 2) * TRIM_THREADS];
 #pragma unroll 1
-          for (int w = 0; w < nwords; ++w) {
-            uint32_t word = 0;
+  for (; 16 * wb <= last; ++wb) {
 #pragma unroll
-            for (int q4 = 0; q4 < 4; ++q4) {
-              const uint32_t nx = ap[k++];
-              const uint32_t quad = __funnelshift_r(prev, nx, bs);
-              prev = nx;
-              const int nb = sl - (16 * w + 4 * q4);  // bytes of this quad that belong to the read
-              uint32_t codes = ((quad >> 1) ^ (quad >> 2)) & 0x03030303u;
-              // the byte each 2-bit code stands for, looked up with one PRMT: a byte that differs is not ACGT
-              uint32_t sel = codes | (codes >> 4);
-              sel = (sel & 0xFFu) | ((sel >> 8) & 0xFF00u);
-              uint32_t diff = __byte_perm(0x54474341u, 0u, sel) ^ quad;
-              if (nb < 4) {
-                const uint32_t tm = nb <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - nb)));
-                codes &= tm;
-                diff &= tm;
-              }
-              anyexc |= diff;
-              word |= ((codes * 0x01041040u) >> 24) << (8 * q4);
-            }
-            ps_mine[w * TRIM_THREADS] = word;
-          }
-#pragma unroll 1
-          for (int w = nwords; w < PACK_WORDS + 2; ++w) ps_mine[w * TRIM_THREADS] = 0;
-          if (anyexc) fast_emit = false;
-        }
-        fc.jump_ok = fast_emit;
-      }
-      if (c_p.umi_mode == MIRGE_UMI_QIAGEN) {
-#pragma unroll 1
-        for (int mi = 0; mi < c_p.n_mods; ++mi) {
-          if (!is_slow) is_slow = apply_mod<MAXM, FAST, PASS == 1>(mi, seq, qual, start, stop, fc);
-          __syncwarp(good_lanes);
-        }
-        const int tl = stop - start, U = c_p.umi3;
-        int us = 0, ue = 0;
-        if (tl > 0) {
-          const int first = find_sub(seq, sl, seq + start, tl, 0);
-          const int after = first + tl;
-          const int nx = find_sub(seq, sl, seq + start, tl, after);
-          int seg_end = nx < 0 ? sl : nx;
-          seg_end = min(seg_end, after + c_p.qia_len + U);
-          ue = seg_end;
-          us = (U != 0) ? max(seg_end - U, after) : after;
-        }
-        w_start[0] = start; w_stop[0] = stop; w_us[0] = us; w_ue[0] = ue;
-        w_words[0] = (tl >= c_p.min_len) ? 1u : 0u;
-        if (ue > us) fast_emit = false;  // concatenated key: generic packing
-      } else {
-#pragma unroll 1
-        for (int mi = 0; mi < c_p.n_mods; ++mi) {
-          if (!is_slow) is_slow = apply_mod<MAXM, FAST, PASS == 1>(mi, seq, qual, start, stop, fc);
-          __syncwarp(good_lanes);
-          if (E != 1 || mi == c_p.n_mods - 1) {
-            const int slot = (E == 1) ? 0 : mi;
-            int ln = stop - start;
-            if (c_p.umi_mode == MIRGE_UMI_FLANKS) ln = max(ln - c_p.umi5 - c_p.umi3, 0);
-            w_start[slot] = start; w_stop[slot] = stop; w_words[slot] = ln >= c_p.min_len;
-          }
-        }
-      }
-      if (PASS == 1 && is_slow) {
-        // second pass will redo this read from scratch; emit nothing now
-#pragma unroll 1
-        for (int s = 0; s < E; ++s) { w_start[s] = w_stop[s] = w_us[s] = w_ue[s] = 0; w_words[s] = 0; }
-      }
-      // size of every kept key: header + payload + exceptions
-#pragma unroll 1
-      for (int s = 0; s < E; ++s) {
-        if (!w_words[s]) continue;
-        if (FAST && fast_emit) {
-          w_words[s] = 1u + ((uint32_t)(w_stop[s] - w_start[s] + 15) >> 4);
-        } else {
-          const int l1 = w_stop[s] - w_start[s], len = l1 + (w_ue[s] - w_us[s]);
-          uint32_t nexc = 0;
-          for (int p = 0; p < len; ++p) nexc += base_code_exact(key_byte(seq, w_start[s], l1, w_us[s], p)) == 4u;
-          w_words[s] = 1u + ((uint32_t)(len + 15) >> 4) + nexc;
-        }
-        my_words += w_words[s];
-        ++my_kept;
+    for (int s = 0; s < 16; ++s) {
+      const uint32_t lo = s ? __funnelshift_r(x0, x1, 2 * s) : x0;
+      if (((lo ^ a_lo) & lo_mask) == 0u) {
+        const uint32_t hi = s ? __funnelshift_r(x1, x2, 2 * s) : x1;
+        const int p = 16 * wb + s;
+        if (((hi ^ a_hi) & hi_mask) == 0u && p >= start && p <= last) return p;
       }
     }
+    x0 = x1;
+    x1 = x2;
+    x2 = (wb + 3 < PS_ROWS) ? ps[(wb + 3) * TRIM_THREADS] : 0u;
   }
-  // key space: one atomic per warp (warps finish independently, no CTA barrier)
-  const int lane = tid & 31;
+  return -1;
+}
+
+// Sizes, key space (one atomic per warp), second-pass queue and the writes of emission slots [slot_lo, slot_hi)
+// of record r.  All 32 lanes of a warp must call it together.  fast_emit: the keys are slices of the packed
+// pure-ACGT read in ps_mine; otherwise they are packed from the bytes in seq (exceptions included).
+// to_slow: PASS 1 only, queues the record for the second pass (which redoes it from scratch).
+template <bool FAST, int PASS>
+__device__ __forceinline__ void emit_record(const bool valid, const uint64_t r, const int E, const int slot_lo, const int slot_hi,
+                                            const uint8_t *seq, const bool fast_emit, const int *w_start, const int *w_stop,
+                                            const int *w_us, const int *w_ue, uint32_t *w_words, const bool to_slow,
+                                            ushort4 *__restrict__ win, uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys,
+                                            uint64_t keys_cap, unsigned long long *__restrict__ ctrl, uint32_t *__restrict__ d_slow,
+                                            const uint32_t *ps_mine) {
+  const int lane = threadIdx.x & 31;
+  uint32_t my_words = 0, my_kept = 0;
+  if (valid) {
+    // size of every kept key: header + payload + exceptions
+#pragma unroll 1
+    for (int s = slot_lo; s < slot_hi; ++s) {
+      if (!w_words[s]) continue;
+      if (FAST && fast_emit) {
+        w_words[s] = 1u + ((uint32_t)(w_stop[s] - w_start[s] + 15) >> 4);
+      } else {
+        const int l1 = w_stop[s] - w_start[s], len = l1 + (w_ue[s] - w_us[s]);
+        uint32_t nexc = 0;
+        for (int p = 0; p < len; ++p) nexc += base_code_exact(key_byte(seq, w_start[s], l1, w_us[s], p)) == 4u;
+        w_words[s] = 1u + ((uint32_t)(len + 15) >> 4) + nexc;
+      }
+      my_words += w_words[s];
+      ++my_kept;
+    }
+  }
   uint32_t inc = my_words;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
@@ -789,18 +771,18 @@ __device__ __forceinline__ void process_record(const bool valid, const uint64_t 
   const bool overflow = warp_base + warp_total > keys_cap || warp_base + warp_total > 0xFFFFFFF0ull;
   if (overflow && lane == 0 && warp_total) atomicOr(ctrl + 2, 2ull);
   if (PASS == 1) {  // queue the deferred reads for the second pass (one atomic per warp)
-    const unsigned sm_ = __ballot_sync(0xffffffffu, is_slow);
+    const unsigned sm_ = __ballot_sync(0xffffffffu, to_slow);
     if (sm_) {
       unsigned long long base = 0;
       if (lane == __ffs(sm_) - 1) base = atomicAdd(ctrl + 5, (unsigned long long)__popc(sm_));
       base = __shfl_sync(0xffffffffu, base, __ffs(sm_) - 1);
-      if (is_slow) d_slow[base + __popc(sm_ & ((1u << lane) - 1u))] = (uint32_t)r;
+      if (to_slow) d_slow[base + __popc(sm_ & ((1u << lane) - 1u))] = (uint32_t)r;
     }
   }
   if (!valid) return;
   uint32_t off = (uint32_t)warp_base + inc - my_words;
 #pragma unroll 1
-  for (int s = 0; s < E; ++s) {
+  for (int s = slot_lo; s < slot_hi; ++s) {
     const uint64_t e = r * (uint64_t)E + s;
     win[e] = make_ushort4((unsigned short)w_start[s], (unsigned short)w_stop[s], (unsigned short)w_us[s], (unsigned short)w_ue[s]);
     if (!w_words[s] || overflow) {
@@ -843,13 +825,215 @@ __device__ __forceinline__ void process_record(const bool valid, const uint64_t 
   }
 }
 
+// window of the read after modifier mi_ -> its emission slot (HEAD: one slot per modifier, digest.py:354-373)
+#define RECORD_SLOT(mi_)                                                                         \
+  if (!qia && (E != 1 || (mi_) == n_mods - 1)) {                                                 \
+    const int slot_ = (E == 1) ? 0 : (mi_);                                                      \
+    int ln_ = stop - start;                                                                      \
+    if (c_p.umi_mode == MIRGE_UMI_FLANKS) ln_ = max(ln_ - c_p.umi5 - c_p.umi3, 0);               \
+    w_start[slot_] = start; w_stop[slot_] = stop; w_words[slot_] = ln_ >= c_p.min_len;           \
+  }
+
+struct SplitOut {  // where stage 1 leaves the reads that need the DP
+  DpEntry *entries;
+  uint32_t *pk;   // packed text, word w of list entry e at pk[w * cap + e]
+  uint64_t cap;
+};
+
+// Everything a thread does for record r once its bytes are addressable through B (shared-memory staging or
+// the global stream).  PASS 0: single pass; PASS 1: first pass (reads whose adapter search needs cost
+// columns are appended to d_slow and emit nothing); PASS 2: second pass over those reads.
+// SPLIT (PASS 1 of the bit-parallel kernel): stage 1 of the split pipeline described above.
+template <int MAXM, bool FAST, int PASS, bool SPLIT>
+__device__ __forceinline__ void process_record(const bool valid, const uint64_t r, const uint8_t *B, uint64_t nbytes,
+                                               const uint32_t *__restrict__ line_start, ushort4 *__restrict__ win,
+                                               uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys, uint64_t keys_cap,
+                                               unsigned long long *__restrict__ ctrl, uint32_t *__restrict__ d_slow, FastCtx &fc,
+                                               uint32_t *ps_mine, const SplitOut so) {
+  const int lane = threadIdx.x & 31;
+  bool is_slow = false;
+  const int E = c_p.slots;
+  const int n_mods = c_p.n_mods;
+  const bool qia = c_p.umi_mode == MIRGE_UMI_QIAGEN;
+  // per-slot windows live in local memory (dynamic slot index keeps the code small)
+  int w_start[MIRGE_MAX_MODS], w_stop[MIRGE_MAX_MODS], w_us[MIRGE_MAX_MODS], w_ue[MIRGE_MAX_MODS];
+  uint32_t w_words[MIRGE_MAX_MODS];  // 0 = not kept
+#pragma unroll 1
+  for (int s = 0; s < E; ++s) { w_start[s] = w_stop[s] = w_us[s] = w_ue[s] = 0; w_words[s] = 0; }
+  const uint8_t *seq = nullptr, *qual = nullptr;
+  uint32_t seq_off = 0;
+  bool fast_emit = FAST, good = false;
+  int sl = 0, start = 0, stop = 0;
+  if (valid) {
+    const uint4 ls = *(const uint4 *)(line_start + 4 * r);
+    const uint32_t nxt = line_start[4 * r + 4];
+    sl = (int)(ls.z - 1 - ls.y);
+    int ql = (int)(nxt - 1 - ls.w);
+    if (sl > 0 && B[ls.y + sl - 1] == '\r') --sl;
+    if (ql > 0 && B[ls.w + ql - 1] == '\r') --ql;
+    const bool bad = B[ls.x] != '@' || B[ls.z] != '+' || sl != ql || sl > MIRGE_MAX_READ_LEN;
+    if (bad) {
+      atomicOr(ctrl + 2, (sl > MIRGE_MAX_READ_LEN && sl == ql) ? 4ull : 1ull);
+      atomicMax(ctrl + 3, ~(unsigned long long)r);
+    } else {
+      good = true;
+      seq_off = ls.y;
+      seq = B + ls.y;
+      qual = B + ls.w;
+      stop = sl;
+    }
+  }
+  // lanes that run the modifier pipeline together; used to re-converge them after every modifier,
+  // whose data-dependent loops (quality scans, adapter search) otherwise leave the warp split
+  const unsigned good_lanes = __ballot_sync(0xffffffffu, good);
+  if (good && FAST) {
+    // 2-bit text of the whole read once, four bytes per step (SIMD-in-register), into shared memory:
+    // used by the exact search, the traceback jumps and by key emission
+    fast_emit = sl <= 16 * PACK_WORDS;
+    if (PASS == 2 && (uint64_t)seq_off + 16 * ((sl + 15) >> 4) + 8 > nbytes) fast_emit = false;  // no over-read past the stream
+    if (fast_emit) {
+      const uint32_t *ap = (const uint32_t *)((uintptr_t)seq & ~(uintptr_t)3);
+      const uint32_t bs = ((uint32_t)(uintptr_t)seq & 3u) * 8u;
+      const int nwords = (sl + 15) >> 4;
+      uint32_t anyexc = 0, prev = ap[0];
+      int k = 1;
+#pragma unroll 1
+      for (int w = 0; w < nwords; ++w) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const uint32_t nx = ap[k++];
+          const uint32_t quad = __funnelshift_r(prev, nx, bs);
+          prev = nx;
+          const int nb = sl - (16 * w + 4 * q4);  // bytes of this quad that belong to the read
+          uint32_t codes = ((quad >> 1) ^ (quad >> 2)) & 0x03030303u;
+          // the byte each 2-bit code stands for, looked up with one PRMT: a byte that differs is not ACGT
+          uint32_t sel = codes | (codes >> 4);
+          sel = (sel & 0xFFu) | ((sel >> 8) & 0xFF00u);
+          uint32_t diff = __byte_perm(0x54474341u, 0u, sel) ^ quad;
+          if (nb < 4) {
+            const uint32_t tm = nb <= 0 ? 0u : (0xFFFFFFFFu >> (8 * (4 - nb)));
+            codes &= tm;
+            diff &= tm;
+          }
+          anyexc |= diff;
+          word |= ((codes * 0x01041040u) >> 24) << (8 * q4);
+        }
+        ps_mine[w * TRIM_THREADS] = word;
+      }
+#pragma unroll 1
+      for (int w = nwords; w < PS_ROWS; ++w) ps_mine[w * TRIM_THREADS] = 0;
+      if (anyexc) fast_emit = false;
+    }
+    fc.jump_ok = fast_emit;
+  }
+
+#define RUN_MODS(from_, to_)                                                                     \
+  _Pragma("unroll 1") for (int mi = (from_); mi < (to_); ++mi) {                                 \
+    if (!is_slow) is_slow = apply_mod<MAXM, FAST, PASS == 1>(mi, seq, qual, start, stop, fc);    \
+    __syncwarp(good_lanes);                                                                      \
+    RECORD_SLOT(mi)                                                                              \
+  }
+
+  int slot_lo = 0, slot_hi = E;
+  bool to_slow = false;
+  if constexpr (!SPLIT) {
+    if (good) { RUN_MODS(0, n_mods) }
+  } else {
+    const int mi_ad = first_adapter_mod();
+    if (good) { RUN_MODS(0, mi_ad) }
+    bool to_dp = false, resolved = false;
+    if (good && mi_ad < n_mods) {
+      if (!fc.jump_ok) {
+        is_slow = true;  // non-ACGT characters or a long read: whole record in the second pass
+      } else {
+        const DevAdapter &ad0 = c_p.ad[0];
+        const bool exact_ok = c_p.n_adapters == 1 && c_p.times == 1 && !ad0.wildcard_ref && ad0.acc[ad0.m] >= 0;
+        const int p = exact_ok ? exact_find(ps_mine, ad0.a2, ad0.m, start, stop) : -1;
+        if (p >= 0) {
+          stop = p;
+          resolved = true;
+          RECORD_SLOT(mi_ad)
+        } else {
+          to_dp = true;
+        }
+      }
+    }
+    if (good) {  // the modifiers after the adapter, for the reads the exact search settled (all good lanes re-converge)
+      _Pragma("unroll 1") for (int mi = mi_ad + 1; mi < n_mods; ++mi) {
+        if (resolved && !is_slow) {
+          const int kind = c_p.kind[mi];
+          if (kind == MIRGE_MOD_NEND) {
+            while (start < stop && seq[start] == 'N') ++start;
+            while (stop > start && seq[stop - 1] == 'N') --stop;
+          } else if (kind == MIRGE_MOD_CUT) {
+            const int c = c_p.a[mi], len = stop - start;
+            if (c > 0) start += min(c, len);
+            else stop = start + max(len + c, 0);
+          } else {
+            is_slow = true;  // a second adapter modifier (stipulate() builds one at most): whole record in the second pass
+          }
+        }
+        __syncwarp(good_lanes);
+        if (resolved) { RECORD_SLOT(mi) }
+      }
+    }
+    // the reads that need the DP: one list slot per read, one atomic per warp
+    const unsigned dm = __ballot_sync(0xffffffffu, to_dp);
+    if (dm) {
+      const int leader = __ffs(dm) - 1;
+      unsigned long long base = 0;
+      if (lane == leader) base = atomicAdd(ctrl + 6, (unsigned long long)__popc(dm));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (to_dp) {
+        const uint64_t e = base + __popc(dm & ((1u << lane) - 1u));
+        DpEntry de;
+        de.r = (uint32_t)r; de.se = (uint32_t)start | ((uint32_t)stop << 16); de.sl = (uint32_t)sl; de.pad = 0;
+        *(uint4 *)(so.entries + e) = *(const uint4 *)&de;
+        const int nwords = (sl + 15) >> 4;
+#pragma unroll 1
+        for (int w = 0; w < nwords; ++w) so.pk[(uint64_t)w * so.cap + e] = ps_mine[w * TRIM_THREADS];
+      }
+    }
+    if (to_dp) slot_hi = (E == 1) ? 0 : mi_ad;  // the later slots belong to stage 2
+  }
+#undef RUN_MODS
+
+  if (good) {
+    if (qia) {
+      const int tl = stop - start, U = c_p.umi3;
+      int us = 0, ue = 0;
+      if (tl > 0) {
+        const int first = find_sub(seq, sl, seq + start, tl, 0);
+        const int after = first + tl;
+        const int nx = find_sub(seq, sl, seq + start, tl, after);
+        int seg_end = nx < 0 ? sl : nx;
+        seg_end = min(seg_end, after + c_p.qia_len + U);
+        ue = seg_end;
+        us = (U != 0) ? max(seg_end - U, after) : after;
+      }
+      w_start[0] = start; w_stop[0] = stop; w_us[0] = us; w_ue[0] = ue;
+      w_words[0] = (tl >= c_p.min_len) ? 1u : 0u;
+      if (ue > us) fast_emit = false;  // concatenated key: generic packing
+    }
+    if (PASS == 1 && is_slow) {
+      // second pass will redo this read from scratch; emit nothing now
+      slot_hi = slot_lo;
+      to_slow = true;
+    }
+  }
+  emit_record<FAST, PASS>(valid, r, E, slot_lo, slot_hi, seq, fast_emit, w_start, w_stop, w_us, w_ue, w_words, to_slow, win, key_off,
+                          keys, keys_cap, ctrl, d_slow, ps_mine);
+}
+
 // FAST = bit-parallel adapter search (locate_fast) + packed-read key emission; requires the CTA's span to be
 // staged in shared memory, otherwise the batch is flagged (ctrl[2] bit 3) for the generic kernel.
-template <int MAXM, bool FAST, int PASS>
+// SPLIT: stage 1 of the split pipeline (only with FAST and PASS 1).
+template <int MAXM, bool FAST, int PASS, bool SPLIT>
 __global__ void __launch_bounds__(TRIM_THREADS, (FAST && PASS == 1) ? 7 : 1)
 trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__restrict__ line_start, uint64_t n_records,
             ushort4 *__restrict__ win, uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys, uint64_t keys_cap,
-            unsigned long long *__restrict__ ctrl, uint32_t smem_bytes, uint32_t *__restrict__ d_slow) {
+            unsigned long long *__restrict__ ctrl, uint32_t smem_bytes, uint32_t *__restrict__ d_slow, const SplitOut so) {
   extern __shared__ uint4 smem4[];
   uint8_t *sbuf = (uint8_t *)smem4;
   const int tid = threadIdx.x;
@@ -857,7 +1041,7 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
   fc.s_eq = nullptr; fc.ps = nullptr; fc.jump_ok = false; fc.rbase = 0;
   uint32_t *ps_mine = nullptr;
   if (FAST) {
-    // smem: [staging smem_bytes][eq tables n_adapters * 256 words][packed reads (PACK_WORDS + 2) * T words]
+    // smem: [staging smem_bytes][eq tables n_adapters * 256 words][packed reads PS_ROWS * T words]
     uint32_t *eq = (uint32_t *)(sbuf + smem_bytes);
     for (int e = tid; e < c_p.n_adapters * 256; e += TRIM_THREADS) {
       const uint32_t code = base_code_upper((uint32_t)(e & 255));
@@ -877,7 +1061,8 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
       const bool valid = idx < n_slow;
       const uint64_t r = valid ? d_slow[idx] : 0;
       fc.jump_ok = false;
-      process_record<MAXM, FAST, 2>(valid, r, fq, nbytes, line_start, win, key_off, keys, keys_cap, ctrl, d_slow, fc, ps_mine);
+      process_record<MAXM, FAST, 2, false>(valid, r, fq, nbytes, line_start, win, key_off, keys, keys_cap, ctrl,
+                                           d_slow, fc, ps_mine, so);
       __syncwarp();
     }
     return;
@@ -918,17 +1103,149 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
   }
   __syncthreads();
   const uint8_t *B = staged ? (const uint8_t *)(sbuf - alo) : fq;  // B[absolute stream offset]
-  process_record<MAXM, FAST, PASS>(valid, r, B, nbytes, line_start, win, key_off, keys, keys_cap, ctrl, d_slow, fc, ps_mine);
+  process_record<MAXM, FAST, PASS, SPLIT>(valid, r, B, nbytes, line_start, win, key_off, keys, keys_cap, ctrl, d_slow, fc, ps_mine, so);
+}
+
+// Stages 2 and 3 of the split pipeline: the adapter search (and everything after it) of the listed reads, from
+// their packed text alone.  FIRST: stage 2 -- entries [0, ctrl[6]), searches that need cost columns are appended
+// to `redo` (ctrl[7]); !FIRST: stage 3 -- the entries listed in `redo`, resolved with recompute + traceback.
+template <bool FIRST>
+__global__ void __launch_bounds__(TRIM_THREADS, FIRST ? 7 : 4)
+trim_dp_kernel(const DpEntry *__restrict__ entries, const uint32_t *__restrict__ pk, uint64_t cap, uint32_t *__restrict__ redo,
+               ushort4 *__restrict__ win, uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys, uint64_t keys_cap,
+               unsigned long long *__restrict__ ctrl) {
+  extern __shared__ uint4 smem4[];
+  // smem: [eq tables n_adapters * 256 words, entries 0..3 used][packed reads PS_ROWS * T words][entries T][hist T][order T]
+  uint32_t *eq = (uint32_t *)smem4;
+  uint32_t *ps_base = eq + c_p.n_adapters * 256;
+  DpEntry *s_ent = (DpEntry *)(ps_base + PS_ROWS * TRIM_THREADS);
+  uint32_t *s_hist = (uint32_t *)(s_ent + TRIM_THREADS);
+  uint16_t *s_order = (uint16_t *)(s_hist + TRIM_THREADS);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const unsigned long long n_items = FIRST ? ctrl[6] : ctrl[7];
+  const uint64_t base = (uint64_t)blockIdx.x * TRIM_THREADS;
+  if (base >= n_items) return;  // uniform per CTA
+  for (int e = tid; e < c_p.n_adapters * 4; e += TRIM_THREADS) eq[(e >> 2) * 256 + (e & 3)] = (uint32_t)c_p.ad[e >> 2].peq[e & 3];
+  const int n_here = (int)min((unsigned long long)TRIM_THREADS, n_items - base);
+  // this CTA's entries, then a counting sort by window length (longest first): the lanes of a warp run column
+  // loops of similar trip count
+  uint32_t my_e = 0;
+  int bin = TRIM_THREADS - 1;
+  if (tid < n_here) {
+    my_e = FIRST ? (uint32_t)(base + tid) : redo[base + tid];
+    const uint4 v = *(const uint4 *)(entries + my_e);
+    DpEntry de = *(const DpEntry *)&v;
+    de.pad = my_e;
+    s_ent[tid] = de;
+    const int wl = (int)(de.se >> 16) - (int)(de.se & 0xFFFFu);
+    bin = TRIM_THREADS - 1 - min(wl, TRIM_THREADS - 1);
+  }
+  s_hist[tid] = 0;
+  __syncthreads();
+  if (tid < n_here) atomicAdd(&s_hist[bin], 1u);
+  __syncthreads();
+  if (tid < 32) {
+    uint32_t h[TRIM_THREADS / 32], sum = 0;
+#pragma unroll
+    for (int q = 0; q < TRIM_THREADS / 32; ++q) { h[q] = s_hist[(TRIM_THREADS / 32) * tid + q]; sum += h[q]; }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += x;
+    }
+    uint32_t run = incl - sum;
+#pragma unroll
+    for (int q = 0; q < TRIM_THREADS / 32; ++q) { s_hist[(TRIM_THREADS / 32) * tid + q] = run; run += h[q]; }
+  }
+  __syncthreads();
+  if (tid < n_here) s_order[atomicAdd(&s_hist[bin], 1u)] = (uint16_t)tid;
+  __syncthreads();
+  const bool valid = tid < n_here;
+  const int E = c_p.slots, n_mods = c_p.n_mods;
+  const bool qia = false;  // the split pipeline is not used with qiagen UMIs
+  int w_start[MIRGE_MAX_MODS], w_stop[MIRGE_MAX_MODS], w_us[MIRGE_MAX_MODS], w_ue[MIRGE_MAX_MODS];
+  uint32_t w_words[MIRGE_MAX_MODS];
+#pragma unroll 1
+  for (int s = 0; s < E; ++s) { w_start[s] = w_stop[s] = w_us[s] = w_ue[s] = 0; w_words[s] = 0; }
+  uint32_t *ps_mine = ps_base + tid;
+  const int mi_ad = first_adapter_mod();
+  uint64_t r = 0;
+  bool need_redo = false;
+  int slot_lo = (E == 1) ? 0 : mi_ad, slot_hi = E;
+  uint32_t ent_id = 0;
+  if (valid) {
+    const DpEntry de = s_ent[s_order[tid]];
+    r = de.r;
+    ent_id = de.pad;
+    int start = (int)(de.se & 0xFFFFu), stop = (int)(de.se >> 16);
+    const int nwords = ((int)de.sl + 15) >> 4;
+#pragma unroll 1
+    for (int w = 0; w < PS_ROWS; ++w) ps_mine[w * TRIM_THREADS] = w < nwords ? pk[(uint64_t)w * cap + ent_id] : 0u;
+    FastCtx fc;
+    fc.s_eq = eq; fc.ps = ps_mine; fc.jump_ok = true; fc.rbase = 0;
+#pragma unroll 1
+    for (int mi = mi_ad; mi < n_mods && !need_redo; ++mi) {
+      const int kind = c_p.kind[mi];
+      if (kind == MIRGE_MOD_ADAPTER) {
+#pragma unroll 1
+        for (int t = 0; t < c_p.times; ++t) {
+          fc.rbase = start;
+          const PackedRead rv{ps_mine, start};
+          const int n = stop - start;
+          Match best;
+          int which = -1;
+#pragma unroll 1
+          for (int a = 0; a < c_p.n_adapters; ++a) {
+            Match mt;
+            const int rc = locate_fast<FIRST>(a, rv, n, fc, mt);
+            if (rc == 2) { need_redo = true; break; }
+            if (rc == 0) continue;
+            if (which < 0 || mt.matches > best.matches || (mt.matches == best.matches && mt.errors < best.errors)) { best = mt; which = a; }
+          }
+          if (need_redo || which < 0) break;
+          stop = start + best.rstart;  // every adapter of the bit-parallel path is a 3' adapter
+        }
+      } else if (kind == MIRGE_MOD_CUT) {
+        const int c = c_p.a[mi], len = stop - start;
+        if (c > 0) start += min(c, len);
+        else stop = start + max(len + c, 0);
+      }  // MIRGE_MOD_NEND: a pure-ACGT read has no N to strip; quality modifiers cannot follow (checked on the host)
+      if (!need_redo) { RECORD_SLOT(mi) }
+    }
+  }
+  if (FIRST) {  // searches that need cost columns: third stage
+    const unsigned rm = __ballot_sync(0xffffffffu, need_redo);
+    if (rm) {
+      const int leader = __ffs(rm) - 1;
+      unsigned long long b2 = 0;
+      if (lane == leader) b2 = atomicAdd(ctrl + 7, (unsigned long long)__popc(rm));
+      b2 = __shfl_sync(0xffffffffu, b2, leader);
+      if (need_redo) redo[b2 + __popc(rm & ((1u << lane) - 1u))] = ent_id;
+    }
+    if (need_redo) slot_hi = slot_lo;
+  }
+  emit_record<true, 0>(valid, r, E, slot_lo, slot_hi, nullptr, true, w_start, w_stop, w_us, w_ue, w_words, false, win, key_off, keys, keys_cap,
+                       ctrl, nullptr, ps_mine);
+}
+
+// scratch layout of mirge_trim: [second-pass list u32[n]][stage-3 list u32[n]][DpEntry[n]][packed text u32[PACK_WORDS][n]]
+static uint64_t align16(uint64_t x) { return (x + 15) & ~15ull; }
+extern "C" uint64_t mirge_trim_scratch_bytes(uint64_t n_records) {
+  const uint64_t n = n_records ? n_records : 1;
+  return 2 * align16(4 * n) + align16(sizeof(DpEntry) * n) + align16(4ull * PACK_WORDS * n) + 64;
 }
 
 extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, const uint32_t *d_line_start, uint64_t n_records,
                           uint16_t *d_win, uint32_t *d_key_off, uint32_t *d_keys, uint64_t keys_capacity_words,
-                          uint64_t *d_trim_ctrl, uint32_t *d_slow, void *stream_) {
+                          uint64_t *d_trim_ctrl, void *d_scratch, void *stream_) {
   if (!ctx) return MIRGE_ERR_ARG;
   if (!ctx->params_set) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: mirge_set_trim_params has not been called");
   if (n_records == 0) return MIRGE_OK;
   if (!d_fastq || !d_line_start || !d_win || !d_key_off || !d_keys || !d_trim_ctrl) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: null buffer");
-  if (((uintptr_t)d_line_start & 15) || ((uintptr_t)d_win & 7)) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: misaligned buffer");
+  if (((uintptr_t)d_line_start & 15) || ((uintptr_t)d_win & 7) || ((uintptr_t)d_scratch & 15))
+    MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: misaligned buffer");
+  if (n_records >= 0x80000000ull) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: more than 2^31 records in one batch");
   // same convention as the tokeniser: line_start offsets are relative to the 16-byte aligned stream
   {
     const uint32_t skew = (uint32_t)((uintptr_t)d_fastq & 15);
@@ -938,7 +1255,8 @@ extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbyte
   cudaStream_t stream = (cudaStream_t)stream_;
   MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
   const uint64_t avg = (nbytes + n_records - 1) / n_records;
-  const bool fast = ctx->fast_ok && ctx->trim_mode == 0;
+  const bool fast = ctx->fast_ok && ctx->trim_mode != 1;
+  const bool split = fast && ctx->split_ok && ctx->trim_mode == 0;
   // staging buffer: the bit-parallel kernel keeps it tight (7 CTAs per SM); a record group that does not fit
   // is handed to its second pass.  The generic kernel reads such groups straight from global memory.
   uint64_t want = fast ? avg * TRIM_THREADS * 33 / 32 + 512 : avg * TRIM_THREADS * 5 / 4 + 64;
@@ -949,34 +1267,59 @@ extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbyte
   const unsigned grid = (unsigned)((n_records + TRIM_THREADS - 1) / TRIM_THREADS);
   unsigned long long *ctrl = (unsigned long long *)d_trim_ctrl;
   ushort4 *win = (ushort4 *)d_win;
+  SplitOut so;
+  so.entries = nullptr; so.pk = nullptr; so.cap = 0;
   if (fast) {
-    if (!d_slow) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: d_slow scratch (u32 per record) is required");
-    const size_t extra = (size_t)ctx->params.n_adapters * 1024 + (size_t)(PACK_WORDS + 2) * TRIM_THREADS * 4;
-    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    // pass 1: every read; adapter searches that need cost columns are deferred to the list d_slow
-    trim_kernel<32, true, 1><<<grid, TRIM_THREADS, smem + extra, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off,
-                                                                          d_keys, keys_capacity_words, ctrl, smem, d_slow);
-    MIRGE_LAUNCH_CHECK(ctx, "trim_kernel(pass 1)");
-    // pass 2: the deferred reads with full warps (count read on the device; grid-stride over the list)
+    if (!d_scratch) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: scratch of mirge_trim_scratch_bytes(n_records) bytes is required");
+    uint8_t *sc = (uint8_t *)d_scratch;
+    uint32_t *d_slow = (uint32_t *)sc;
+    uint32_t *d_redo = (uint32_t *)(sc + align16(4 * n_records));
+    so.entries = (DpEntry *)(sc + 2 * align16(4 * n_records));
+    so.pk = (uint32_t *)(sc + 2 * align16(4 * n_records) + align16(sizeof(DpEntry) * n_records));
+    so.cap = n_records;
+    const size_t extra = (size_t)ctx->params.n_adapters * 1024 + (size_t)PS_ROWS * TRIM_THREADS * 4;
+    if (split) {
+      // stage 1: every read up to the adapter modifier; exact adapter occurrences are settled here
+      MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      trim_kernel<32, true, 1, true><<<grid, TRIM_THREADS, smem + extra, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off,
+                                                                                 d_keys, keys_capacity_words, ctrl, smem, d_slow, so);
+      MIRGE_LAUNCH_CHECK(ctx, "trim_kernel(stage 1)");
+      // stages 2 and 3: the listed reads (counts live on the device: CTAs beyond the list exit at once)
+      const size_t dp_smem = extra + (size_t)TRIM_THREADS * (sizeof(DpEntry) + 4 + 2);
+      trim_dp_kernel<true><<<grid, TRIM_THREADS, dp_smem, stream>>>(so.entries, so.pk, so.cap, d_redo, win, d_key_off, d_keys,
+                                                                    keys_capacity_words, ctrl);
+      MIRGE_LAUNCH_CHECK(ctx, "trim_dp_kernel(stage 2)");
+      trim_dp_kernel<false><<<grid, TRIM_THREADS, dp_smem, stream>>>(so.entries, so.pk, so.cap, d_redo, win, d_key_off, d_keys,
+                                                                     keys_capacity_words, ctrl);
+      MIRGE_LAUNCH_CHECK(ctx, "trim_dp_kernel(stage 3)");
+    } else {
+      MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      // pass 1: every read; adapter searches that need cost columns are deferred to the list d_slow
+      trim_kernel<32, true, 1, false><<<grid, TRIM_THREADS, smem + extra, stream>>>(d_fastq, nbytes, d_line_start, n_records, win,
+                                                                                  d_key_off, d_keys, keys_capacity_words, ctrl, smem,
+                                                                                  d_slow, so);
+      MIRGE_LAUNCH_CHECK(ctx, "trim_kernel(pass 1)");
+    }
+    // pass 2: the reads left over (whole pipeline per read, from the global stream; grid-stride over the list)
     unsigned grid2 = grid / 16 + 1;
     if (grid2 > (unsigned)ctx->sm_count * 8) grid2 = (unsigned)ctx->sm_count * 8;
-    trim_kernel<32, true, 2><<<grid2, TRIM_THREADS, extra, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
-                                                                   keys_capacity_words, ctrl, 0u, d_slow);
+    trim_kernel<32, true, 2, false><<<grid2, TRIM_THREADS, extra, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off,
+                                                                          d_keys, keys_capacity_words, ctrl, 0u, d_slow, so);
   } else if (ctx->max_adapter_len <= 32) {
-    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    trim_kernel<32, false, 0><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
-                                                                    keys_capacity_words, ctrl, smem, nullptr);
+    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    trim_kernel<32, false, 0, false><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off,
+                                                                           d_keys, keys_capacity_words, ctrl, smem, nullptr, so);
   } else {
-    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<64, false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    trim_kernel<64, false, 0><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off, d_keys,
-                                                                    keys_capacity_words, ctrl, smem, nullptr);
+    MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<64, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    trim_kernel<64, false, 0, false><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off,
+                                                                           d_keys, keys_capacity_words, ctrl, smem, nullptr, so);
   }
   MIRGE_LAUNCH_CHECK(ctx, "trim_kernel");
   return MIRGE_OK;
 }
 
 extern "C" int mirge_trim_mode(mirge_ctx *ctx, int mode) {
-  if (!ctx || mode < 0 || mode > 1) return MIRGE_ERR_ARG;
+  if (!ctx || mode < 0 || mode > 2) return MIRGE_ERR_ARG;
   ctx->trim_mode = mode;
   return MIRGE_OK;
 }

@@ -243,7 +243,7 @@ class DigestEngine:
         self.E = dev.slots
         self.trim_mode = 0  # 0 = automatic kernel choice, 1 = always the generic full-DP kernel
         dev.check(dev.lib.mirge_trim_mode(dev.ctx, 0))
-        self.stats = {"records": 0, "bytes": 0, "emitted": 0, "key_words": 0, "deferred": 0}  # running totals (bench.py rooflines)
+        self.stats = {"records": 0, "bytes": 0, "emitted": 0, "key_words": 0, "deferred": 0, "dp_reads": 0, "dp_redo": 0}  # running totals (bench.py rooflines)
 
     def set_trim_mode(self, mode: int):
         self.dev.check(self.dev.lib.mirge_trim_mode(self.dev.ctx, int(mode)))
@@ -275,7 +275,7 @@ class DigestEngine:
         d.launches += 2
         win = d.empty(n * E * 4, torch.int16)
         key_off = d.empty(n * E, torch.int32)
-        slow = d.empty(n, torch.int32)  # reads deferred to the second trim pass
+        slow = d.empty(lib.mirge_trim_scratch_bytes(n), torch.uint8)  # work lists of the split trim pipeline
         cap = E * (2 * n + used // 24) + 4096
         mode = self.trim_mode
         base_words = 0
@@ -301,11 +301,13 @@ class DigestEngine:
             finally:
                 if mode != self.trim_mode:
                     d.check(lib.mirge_trim_mode(d.ctx, self.trim_mode))
-            d.launches += 2
+            d.launches += 4
             c = ctrl.cpu().numpy().view(np.uint64)
             flags = int(c[2])
-            self.stats["deferred"] += int(c[5])  # reads handed to the second trim pass (diagnostics)
-            if flags & 8 and mode == 0:
+            self.stats["deferred"] += int(c[5])  # reads handed to the whole-pipeline second pass (diagnostics)
+            self.stats["dp_reads"] += int(c[6])  # reads whose adapter search ran the bit-vector DP
+            self.stats["dp_redo"] += int(c[7])  # of those, searches that needed cost columns
+            if flags & 8 and mode != 1:
                 # a record group did not fit the bit-parallel kernel's shared-memory staging:
                 # repeat the batch with the generic kernel (same results, slower)
                 mode = 1

@@ -39,10 +39,11 @@ def gpu_windows(eng, br):
     return win, kept
 
 
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 @pytest.mark.parametrize("name", sorted(CONFIGS))
 def test_trim_and_collapse_match_oracle(dev, name, mode):
-    """mode 0: automatic kernel choice (bit-parallel kernel where it applies); mode 1: generic full DP."""
+    """mode 0: automatic kernel choice (split bit-parallel pipeline where it applies); mode 1: generic full DP;
+    mode 2: bit-parallel kernel without the split."""
     from mirge_b200 import device as D
 
     cfg = CONFIGS[name]
