@@ -416,10 +416,18 @@ __device__ __forceinline__ bool all_deletions_possible(const uint32_t *eqt, cons
   if (!have || (mt) > b_m || ((mt) == b_m && ((c) < b_c || ((c) == b_c && (idx) < b_idx)))) { \
     have = true; b_m = (mt); b_c = (c); b_o = (org); b_idx = (idx);                          \
   }
-// queued row-m candidate: column | cost << 16 | (first step is a match) << 24
+// queued row-m candidate: column | cost << 16 | (first step is a match) << 24 | insertion-chain length << 25
 #define Q_COL(v) ((int)((v)&0xFFFFu))
 #define Q_COST(v) ((int)(((v) >> 16) & 0xFFu))
 #define Q_UB(v, m) ((((v) >> 24) & 1u) ? (m) : (m)-1)
+#define Q_CHAIN(v) ((int)((v) >> 25))
+// Cells of one column that cutadapt's rule enters by an insertion, for all rows at once: characters differ, the
+// vertical delta is +1 (cins attains the cell's cost) and the diagonal predecessor does not (its cost is the
+// cell's cost, i.e. the horizontal delta one row up is -1).  A run of t such cells ending in row i means the
+// traceback of (i, j) walks straight up to (i - t, j): same matches and origin, t errors fewer -- which settles
+// most candidates whose extra cost is adapter overhang without any cost column.
+#define INS_MASK(eq, vp, hn) (~(eq) & (vp) & ((hn) << 1))
+#define CHAIN_LEN(ins, i) (__clz((int)~((ins) << (32 - (i)))))
 
 // DEFER (first pass of the two-pass scheme): as soon as a candidate would need cost columns (recompute +
 // general traceback) the search gives up with 2 and the read is queued for the second pass, which runs
@@ -451,32 +459,35 @@ __device__ __forceinline__ int locate_fast(const int a, const RV read, const int
   for (int it_ = 0; it_ < 4; ++it_) {                                                            \
     uint32_t v_ = 0;                                                                             \
     int which_ = -1;                                                                             \
-    if (q0 && (!v_ || (q0 >> 16 & 0xFF) < (v_ >> 16 & 0xFF))) { v_ = q0; which_ = 0; }           \
-    if (q1 && (!v_ || (q1 >> 16 & 0xFF) < (v_ >> 16 & 0xFF))) { v_ = q1; which_ = 1; }           \
-    if (q2 && (!v_ || (q2 >> 16 & 0xFF) < (v_ >> 16 & 0xFF))) { v_ = q2; which_ = 2; }           \
-    if (q3 && (!v_ || (q3 >> 16 & 0xFF) < (v_ >> 16 & 0xFF))) { v_ = q3; which_ = 3; }           \
+    if (q0 && (!v_ || Q_COST(q0) < Q_COST(v_))) { v_ = q0; which_ = 0; }                         \
+    if (q1 && (!v_ || Q_COST(q1) < Q_COST(v_))) { v_ = q1; which_ = 1; }                         \
+    if (q2 && (!v_ || Q_COST(q2) < Q_COST(v_))) { v_ = q2; which_ = 2; }                         \
+    if (q3 && (!v_ || Q_COST(q3) < Q_COST(v_))) { v_ = q3; which_ = 3; }                         \
     if (which_ < 0) break;                                                                       \
     if (which_ == 0) q0 = 0; else if (which_ == 1) q1 = 0; else if (which_ == 2) q2 = 0; else q3 = 0; \
-    const int jc_ = Q_COL(v_), cc_ = Q_COST(v_);                                                 \
-    int ub_ = Q_UB(v_, m);                                                                       \
-    if (ub_ == m && !all_deletions_possible(eqt, read, m, jc_, cc_)) ub_ = m - 1;               \
+    const int jc_ = Q_COL(v_), cc_ = Q_COST(v_), t_ = Q_CHAIN(v_);                               \
+    const int ir_ = m - t_, cr_ = cc_ - t_; /* the cell the insertion chain leads to */          \
+    int ub_ = t_ ? ir_ : Q_UB(v_, m);                                                            \
+    if (!t_ && ub_ == m && !all_deletions_possible(eqt, read, m, jc_, cc_)) ub_ = m - 1;        \
     if (MAY_WIN(ub_, cc_, jc_)) {                                                                \
       int mt_, org_;                                                                             \
-      if (!(cc_ == 1 && traceback_cost1(a, fc, m, jc_, mt_, org_))) {                            \
+      if (cr_ == 0) {                                                                            \
+        mt_ = ir_; org_ = jc_ - ir_;                                                             \
+      } else if (!(cr_ == 1 && traceback_cost1(a, fc, ir_, jc_, mt_, org_))) {                   \
         if (DEFER) { need_slow = true; break; }                                                  \
         recompute(eqt, read, jc_, span, cb);                                                     \
-        traceback(a, eqt, read, fc, cb, m, jc_, cc_, mt_, org_);                                 \
+        traceback(a, eqt, read, fc, cb, ir_, jc_, cr_, mt_, org_);                               \
       }                                                                                          \
       TAKE_IF_BETTER(mt_, cc_, org_, jc_)                                                        \
     }                                                                                            \
   }
 
+  uint32_t hp = 0, hn = 0;  // horizontal deltas of the column just computed
   for (int j = 1; j <= n; ++j) {
     eq = read.eq(eqt, j - 1);
     const int score_prev = score;
     pvp = vp;
     pvn = vn;
-    uint32_t hp, hn;
     MYERS_STEP(eq, vp, vn, hp, hn)
     score += (hp & top) ? 1 : 0;
     score -= (hn & top) ? 1 : 0;
@@ -520,39 +531,39 @@ __device__ __forceinline__ int locate_fast(const int a, const RV read, const int
       if (!is_del) {
         pend = true;
         pend_ins = is_ins;
-        pend_v = (uint32_t)j | ((uint32_t)score << 16) | (is_match ? (1u << 24) : 0u);
+        // insertion chain: row m by the rule above, the rows below it from the column's insertion mask
+        const uint32_t chain = is_ins ? 1u + (uint32_t)CHAIN_LEN(INS_MASK(eq, vp, hn), m - 1) : 0u;
+        pend_v = (uint32_t)j | ((uint32_t)score << 16) | (is_match ? (1u << 24) : 0u) | (chain << 25);
       }
     }
   }
   __syncwarp(lanes);
   const unsigned scan_lanes = __ballot_sync(lanes, !stopped && !need_slow);
   if (!stopped && !need_slow) {
-    // last column: rows with cost 0 are pure diagonals; the others wait in rowmask / rowub
-    uint32_t rowmask = 0, rowub = 0;  // rowub bit: first step of that cell is a match (up to i matches), else i - 1
-    int c = 0, cprev = 0;             // D[i][n], D[i][n-1]
+    // last column: rows with cost 0 are pure diagonals; the others wait in rowmask / rowub.  First traceback step
+    // of every row at once: entered by an insertion (ins), by a mismatch (mis: the diagonal predecessor attains
+    // cost - 1, i.e. vertical delta + horizontal delta one row up == 1), else match or deletion.
+    uint32_t rowmask = 0, rowub = 0;  // rowub bit: first step is a match or a deletion (up to i matches), else i - 1
+    const uint32_t hps = hp << 1, hns = hn << 1;
+    const uint32_t ins = n >= 1 ? INS_MASK(eq, vp, hn) : 0u;
+    const uint32_t mis = n >= 1 ? (~eq & ((vp & ~hps & ~hns) | (~vp & ~vn & hps))) : 0u;
+    int c = 0;  // D[i][n]
     for (int i = 1; i <= m; ++i) {
-      const int c_up = c, cprev_up = cprev;  // row i - 1
+      const uint32_t bit = 1u << (i - 1);
       c += (int)((vp >> (i - 1)) & 1u) - (int)((vn >> (i - 1)) & 1u);
-      cprev += (int)((pvp >> (i - 1)) & 1u) - (int)((pvn >> (i - 1)) & 1u);
       if (c > ad.acc[i]) continue;
       if (c == 0) {
         const int idx = (i == m) ? n : n + 1 + i;  // row m of column n precedes the last-column scan
         TAKE_IF_BETTER(i, 0, n - i, idx)
+      } else if (ins & bit) {
+        // Rule 3: a chain of t insertions from (i - t, n): same matches and origin as that cell, t errors more;
+        // when (i - t, n) is an accepted candidate of this column, (i, n) can never win.
+        const int t = CHAIN_LEN(ins, i);
+        if (ad.acc[i - t] >= c - t) continue;
+        rowmask |= bit;
       } else {
-        bool full = true;  // may reach i matches only if its first step is a match or a deletion
-        if (!((eq >> (i - 1)) & 1u) && n >= 1) {
-          const int cd = cprev_up + 1, cdel = cprev + 1, cins = c_up + 1;
-          if (cd <= cdel && cd <= cins) full = false;  // mismatch
-          else if (cins <= cdel) {
-            // Rule 3: entered by an insertion from (i-1, n): same matches and origin as that cell, one
-            // error more; when (i-1, n) is an accepted candidate of the same column (scanned earlier),
-            // (i, n) can never win.
-            if (ad.acc[i - 1] >= c - 1) continue;
-            full = false;
-          }
-        }
-        rowmask |= 1u << (i - 1);
-        if (full) rowub |= 1u << (i - 1);
+        rowmask |= bit;
+        if ((eq & bit) || !(mis & bit)) rowub |= bit;
       }
     }
     __syncwarp(scan_lanes);
@@ -560,20 +571,26 @@ __device__ __forceinline__ int locate_fast(const int a, const RV read, const int
     bool have_cols = false;
     while (rowmask) {  // descending rows: the first traceback usually prunes the rest
       const int i = 32 - __clz(rowmask);
-      rowmask &= ~(1u << (i - 1));
+      const uint32_t bit = 1u << (i - 1);
+      rowmask &= ~bit;
       const int ci = cell_cost(vp, vn, i);
       const int idx = (i == m) ? n : n + 1 + i;
-      int ub = ((rowub >> (i - 1)) & 1u) ? i : i - 1;
-      if (ub == i && !all_deletions_possible(eqt, read, i, n, ci)) ub = i - 1;
+      const int t = (ins & bit) ? CHAIN_LEN(ins, i) : 0;
+      const int ir = i - t, cr = ci - t;  // the cell the insertion chain leads to
+      int ub = t ? ir : ((rowub & bit) ? i : i - 1);
+      if (!t && ub == i && !all_deletions_possible(eqt, read, i, n, ci)) ub = i - 1;
       if (MAY_WIN(ub, ci, idx)) {
         int mt, org;
-        if (!(ci == 1 && traceback_cost1(a, fc, i, n, mt, org))) {
+        if (cr == 0) {
+          mt = ir;
+          org = n - ir;
+        } else if (!(cr == 1 && traceback_cost1(a, fc, ir, n, mt, org))) {
           if (DEFER) { need_slow = true; break; }
           if (!have_cols) {
             recompute(eqt, read, n, span, cb);
             have_cols = true;
           }
-          traceback(a, eqt, read, fc, cb, i, n, ci, mt, org);
+          traceback(a, eqt, read, fc, cb, ir, n, cr, mt, org);
         }
         TAKE_IF_BETTER(mt, ci, org, idx)
       }
@@ -944,20 +961,20 @@ __device__ __forceinline__ void process_record(const bool valid, const uint64_t 
     if (good) { RUN_MODS(0, mi_ad) }
     bool to_dp = false, resolved = false;
     if (good && mi_ad < n_mods) {
+      const DevAdapter &ad0 = c_p.ad[0];
+      const bool exact_ok = c_p.n_adapters == 1 && c_p.times == 1 && !ad0.wildcard_ref && ad0.acc[ad0.m] >= 0;
+      int p = -1;
+      if (fc.jump_ok && exact_ok) p = exact_find(ps_mine, ad0.a2, ad0.m, start, stop);
+      __syncwarp(good_lanes);  // the search leaves its loop at a different word in every lane
       if (!fc.jump_ok) {
         is_slow = true;  // non-ACGT characters or a long read: whole record in the second pass
+      } else if (p >= 0) {
+        stop = p;
+        resolved = true;
       } else {
-        const DevAdapter &ad0 = c_p.ad[0];
-        const bool exact_ok = c_p.n_adapters == 1 && c_p.times == 1 && !ad0.wildcard_ref && ad0.acc[ad0.m] >= 0;
-        const int p = exact_ok ? exact_find(ps_mine, ad0.a2, ad0.m, start, stop) : -1;
-        if (p >= 0) {
-          stop = p;
-          resolved = true;
-          RECORD_SLOT(mi_ad)
-        } else {
-          to_dp = true;
-        }
+        to_dp = true;
       }
+      if (resolved) { RECORD_SLOT(mi_ad) }
     }
     if (good) {  // the modifiers after the adapter, for the reads the exact search settled (all good lanes re-converge)
       _Pragma("unroll 1") for (int mi = mi_ad + 1; mi < n_mods; ++mi) {
@@ -1301,8 +1318,10 @@ extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbyte
       MIRGE_LAUNCH_CHECK(ctx, "trim_kernel(pass 1)");
     }
     // pass 2: the reads left over (whole pipeline per read, from the global stream; grid-stride over the list)
-    unsigned grid2 = grid / 16 + 1;
-    if (grid2 > (unsigned)ctx->sm_count * 8) grid2 = (unsigned)ctx->sm_count * 8;
+    // (one read per thread where possible: a read's whole pipeline is a long dependent chain, so the list is
+    // spread over many warps instead of looping inside few)
+    unsigned grid2 = split ? grid / 4 + 1 : grid / 16 + 1;
+    if (grid2 > (unsigned)ctx->sm_count * (split ? 64u : 8u)) grid2 = (unsigned)ctx->sm_count * (split ? 64u : 8u);
     trim_kernel<32, true, 2, false><<<grid2, TRIM_THREADS, extra, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off,
                                                                           d_keys, keys_capacity_words, ctrl, 0u, d_slow, so);
   } else if (ctx->max_adapter_len <= 32) {
