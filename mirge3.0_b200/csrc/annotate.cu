@@ -100,7 +100,6 @@ extern "C" int mirge_lib_filter(mirge_ctx *ctx, const uint32_t *d_kmer, const ui
 
 #define MAX_PIECES 4
 #define MAX_ROUNDS 10
-#define COOP_MIN 8  // candidate lists longer than this are verified by the whole warp
 
 struct RoundSet {
   int n;
@@ -173,12 +172,23 @@ __device__ __forceinline__ bool query_has_n(const uint32_t *qnx, int a, int b) {
   return false;
 }
 
-// One bowtie round for the query of this lane (active lanes only); all 32 lanes must call it together:
-// long candidate lists are verified by the whole warp (query broadcast through shared memory,
-// min-reduction with shuffles), so one sequence with hundreds of candidates does not stall the others.
+// Per-warp scratch of the candidate redistribution: every lane publishes its query (up to COOP_QW words) and the
+// index ranges of its seed pieces; the candidates of all 32 lanes then form one list that the lanes share out
+// evenly, so a sequence with many candidates does not hold up 31 idle lanes and candidate-free lanes help.
+#define COOP_QW 6  // queries of up to 96 bases take part; longer ones verify their own candidates
+struct WarpScratch {
+  uint32_t qw[32][COOP_QW], qnx[32][COOP_QW];
+  uint32_t lo[32][MAX_PIECES], hi[32][MAX_PIECES], off[32][MAX_PIECES];
+  uint32_t len[32];
+  uint32_t pref[33];  // exclusive prefix of the candidate counts
+  unsigned long long best[32];
+};
+
+// One bowtie round for the query of this lane (active lanes only); all 32 lanes must call it together.
+// republish: this lane's query words changed since the last round (window change) and must be copied again.
 __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const mirge_round_policy &pol, bool active,
-                                                 const uint32_t *qw, const uint32_t *qnx, int L, bool has_exc,
-                                                 uint32_t *s_qw, uint32_t *s_qnx, uint32_t *s_meta, int lane) {
+                                                 const uint32_t *qw, const uint32_t *qnx, int L, bool has_exc, WarpScratch &ws,
+                                                 bool &republish, int lane) {
   uint32_t p_lo[MAX_PIECES], p_hi[MAX_PIECES], p_off[MAX_PIECES];
 #pragma unroll
   for (int i = 0; i < MAX_PIECES; ++i) p_lo[i] = p_hi[i] = p_off[i] = 0;
@@ -213,7 +223,7 @@ __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const
   uint32_t total = 0;
 #pragma unroll
   for (int i = 0; i < MAX_PIECES; ++i) total += p_hi[i] - p_lo[i];
-  const bool big = active && !degenerate && total > COOP_MIN;
+  const bool shared = active && !degenerate && total > 0 && nw <= COOP_QW;
   if (degenerate) {
     // very short query: exhaustive scan keeps the result exact
     for (uint32_t r = 0; r < lib.n_refs; ++r) {
@@ -223,7 +233,7 @@ __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const
         if (h < best) best = h;
       }
     }
-  } else if (active && !big) {
+  } else if (active && total > 0 && !shared) {  // long query: its own candidates, serially
 #pragma unroll
     for (int pi = 0; pi < MAX_PIECES; ++pi)
       for (uint32_t e = p_lo[pi]; e < p_hi[pi]; ++e) {
@@ -233,41 +243,53 @@ __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const
         if (h < best) best = h;
       }
   }
-  unsigned todo = __ballot_sync(0xffffffffu, big);
-  while (todo) {
-    const int leader = __ffs(todo) - 1;
-    todo &= todo - 1;
-    if (lane == leader) {
-      for (int w = 0; w < nw; ++w) { s_qw[w] = qw[w]; s_qnx[w] = qnx[w]; }
-      s_meta[0] = (uint32_t)L;
+  // ---- the candidates of all lanes as one list
+  const unsigned sm = __ballot_sync(0xffffffffu, shared);
+  if (sm == 0) return best;
+  uint32_t incl = shared ? total : 0u;
 #pragma unroll
-      for (int pi = 0; pi < MAX_PIECES; ++pi) {
-        s_meta[4 + 3 * pi] = p_lo[pi];
-        s_meta[5 + 3 * pi] = p_hi[pi];
-        s_meta[6 + 3 * pi] = p_off[pi];
-      }
-    }
-    __syncwarp();
-    const int cL = (int)s_meta[0];
-    const int cR = pol.seed_len == 0 ? cL : min(pol.seed_len, cL);
-    uint64_t b = MIRGE_NO_HIT;
-#pragma unroll
-    for (int pi = 0; pi < MAX_PIECES; ++pi) {
-      const uint32_t lo = s_meta[4 + 3 * pi], hi = s_meta[5 + 3 * pi], off = s_meta[6 + 3 * pi];
-      for (uint32_t e = lo + lane; e < hi; e += 32) {
-        const uint32_t pos = lib.d_idx_pos[e];
-        if (pos < off) continue;
-        const uint64_t h = verify(lib, s_qw, s_qnx, cL, pol, cR, pos - off, pos);
-        if (h < b) b = h;
-      }
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += x;
+  }
+  const uint32_t T = __shfl_sync(0xffffffffu, incl, 31);
+  ws.pref[lane + 1] = incl;
+  if (lane == 0) ws.pref[0] = 0;
+  if (shared) {
+    if (republish) {
+      for (int w = 0; w < nw; ++w) { ws.qw[lane][w] = qw[w]; ws.qnx[lane][w] = qnx[w]; }
+      republish = false;
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const uint64_t o = __shfl_xor_sync(0xffffffffu, b, d);
-      if (o < b) b = o;
+    for (int pi = 0; pi < MAX_PIECES; ++pi) { ws.lo[lane][pi] = p_lo[pi]; ws.hi[lane][pi] = p_hi[pi]; ws.off[lane][pi] = p_off[pi]; }
+    ws.len[lane] = (uint32_t)L;
+    ws.best[lane] = MIRGE_NO_HIT;
+  }
+  __syncwarp();
+  for (uint32_t w = lane; w < T; w += 32) {
+    // owner = last lane whose prefix is <= w (binary search over the 32 prefixes)
+    int o = 0;
+#pragma unroll
+    for (int st = 16; st > 0; st >>= 1)
+      if (ws.pref[o + st] <= w) o += st;
+    uint32_t j = w - ws.pref[o];
+    int pi = 0;
+#pragma unroll
+    for (int q = 0; q < MAX_PIECES - 1; ++q) {
+      const uint32_t c = ws.hi[o][pi] - ws.lo[o][pi];
+      if (j >= c && pi == q) { j -= c; ++pi; }
     }
-    if (lane == leader) best = b;
-    __syncwarp();
+    const uint32_t pos = lib.d_idx_pos[ws.lo[o][pi] + j], off = ws.off[o][pi];
+    if (pos < off) continue;
+    const int oL = (int)ws.len[o];
+    const int oR = pol.seed_len == 0 ? oL : min(pol.seed_len, oL);
+    const uint64_t h = verify(lib, ws.qw[o], ws.qnx[o], oL, pol, oR, pos - off, pos);
+    if (h != MIRGE_NO_HIT) atomicMin(&ws.best[o], (unsigned long long)h);
+  }
+  __syncwarp();
+  if (shared) {
+    const uint64_t b = ws.best[lane];
+    if (b < best) best = b;
   }
   return best;
 }
@@ -278,8 +300,7 @@ __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const
 __global__ void __launch_bounds__(ANN_THREADS)
 annotate_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_keys, uint8_t *__restrict__ annot_round,
                 uint64_t *__restrict__ hit, const uint32_t *__restrict__ order) {
-  __shared__ uint32_t s_qw[ANN_THREADS / 32][QW_MAX], s_qnx[ANN_THREADS / 32][QW_MAX];
-  __shared__ uint32_t s_meta[ANN_THREADS / 32][4 + 3 * MAX_PIECES];
+  __shared__ WarpScratch s_ws[ANN_THREADS / 32];
   const uint64_t slot = (uint64_t)blockIdx.x * ANN_THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool in_range = slot < n_keys;
@@ -300,6 +321,7 @@ annotate_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_k
   }
   uint64_t my_hit = MIRGE_NO_HIT;
   int my_round = -1;
+  bool republish = true;  // the warp scratch does not hold this lane's current query words yet
   for (int ri = 0; ri < rs.n; ++ri) {
     const mirge_round_policy &pol = rs.pol[ri];
     bool active = in_range;
@@ -354,10 +376,11 @@ annotate_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_k
           }
           cur_qs = qs;
           cur_qe = qe;
+          republish = true;
         }
       }
     }
-    const uint64_t best = search_round(rs.lib[ri], pol, active, qw, qnx, L, nexc > 0, s_qw[warp], s_qnx[warp], s_meta[warp], lane);
+    const uint64_t best = search_round(rs.lib[ri], pol, active, qw, qnx, L, nexc > 0, s_ws[warp], republish, lane);
     if (active && best != MIRGE_NO_HIT) {
       state = (uint32_t)pol.round;
       my_round = pol.round;

@@ -73,7 +73,9 @@ def exchange_and_merge(dev, local_table, ids: torch.Tensor, cnt: torch.Tensor, o
                                            _ptr(dest), _ptr(words), dev.stream()))
         dev.launches += 1
     dest, words = dest[:n], words[:n]
-    order = torch.argsort(dest.to(torch.int64), stable=True)
+    # group by destination: world <= 256, so one 8-bit radix pass (torch.sort is plumbing here; order inside a
+    # destination does not matter, the owner-side merge is order independent)
+    order = torch.sort(dest.to(torch.uint8), stable=True)[1] if world <= 256 else torch.argsort(dest.to(torch.int64), stable=True)
     ids_s, cnt_s, words_s = ids[order].contiguous(), cnt[order].contiguous(), words[order].contiguous()
     send_recs = torch.bincount(dest.to(torch.int64), minlength=world)[:world]
     off64 = torch.cumsum(words_s.to(torch.int64), 0) - words_s.to(torch.int64)
