@@ -262,3 +262,30 @@ def test_streamed_annotation_matches_whole_table(dev):
     eng.digest_device(fq, t2)
     ids2, cnt2 = t2.drain()
     assert sorted(sa.host["cnt"][:n_pairs].tolist()) == sorted(cnt2.cpu().tolist())
+
+
+def test_libraries_load_from_bowtie_index_files(dev, tmp_path):
+    """A library directory that ships only .ebwt files (stock miRge3_Lib) gives the same annotation as FASTA."""
+    from mirge_b200 import libraries as LB
+    from mirge_b200 import manifoldAlign as MA
+    from mirge_b200.libraries import INDEX_SUFFIX, ROUND_LIBS
+    from tests.util import write_ebwt
+
+    rng = np.random.default_rng(33)
+    libs = make_libs(rng, scale=0.3)
+    write_lib_dir(str(tmp_path / "fa"), libs)
+    d = tmp_path / "eb" / "human" / "index.Libs"
+    d.mkdir(parents=True)
+    for rnd, key in enumerate(ROUND_LIBS):
+        names, seqs = libs[key]
+        write_ebwt(str(d / ("human" + INDEX_SUFFIX[rnd] + ("miRBase" if rnd in (0, 1, 8) else ""))),
+                   ["%s some description" % n for n in names], seqs)
+    a = LB.LibrarySet.from_mirge_lib(dev, str(tmp_path / "fa"), "human", "miRBase", True)
+    b = LB.LibrarySet.from_mirge_lib(dev, str(tmp_path / "eb"), "human", "miRBase", True)
+    seqs = make_queries(rng, libs, 1500)
+    ks = MA.KeySet.from_strings(dev, seqs)
+    ra, ha = MA.annotate_keys(dev, a, ks, True)
+    rb, hb = MA.annotate_keys(dev, b, ks, True)
+    assert torch.equal(ra, rb) and torch.equal(ha, hb) and int((ra != 0xFF).sum()) > 200
+    for key in set(ROUND_LIBS):
+        assert a[key].names == b[key].names

@@ -112,3 +112,53 @@ def make_args(**kw):
     for k, v in kw.items():
         setattr(a, k, v)
     return a
+
+
+def write_ebwt(basename, names, seqs, line_rate=6, lines_per_side=1, ftab_chars=4, bwt_pad=0):
+    """Minimal bowtie 1 index writer for the loader tests: real ``.3.ebwt`` / ``.4.ebwt`` and a ``.1.ebwt`` whose
+    header, table sizes and name block follow the published layout (the BWT region itself is zero bytes of the
+    right size; ``bwt_pad`` adds bytes there to emulate a layout the header arithmetic does not predict)."""
+    import struct
+
+    recs, bases = [], []
+    for s in seqs:
+        s = s.upper()
+        first, i, n = 1, 0, len(s)
+        while i < n:
+            j = i
+            while j < n and s[j] not in "ACGT":
+                j += 1
+            k = j
+            while k < n and s[k] in "ACGT":
+                k += 1
+            if k > j:
+                recs.append((j - i, k - j, first))
+                first = 0
+                bases.append(s[j:k])
+            i = k
+        if first:  # reference without any unambiguous base: an empty first record keeps the name aligned
+            recs.append((0, 0, 1))
+    text = "".join(bases)
+    total = len(text)
+    with open(basename + ".3.ebwt", "wb") as f:
+        f.write(struct.pack("<iI", 1, len(recs)))
+        for off, ln, first in recs:
+            f.write(struct.pack("<IIB", off, ln, first))
+    codes = np.array(["ACGT".index(c) for c in text] + [0] * ((-total) % 4), dtype=np.uint8).reshape(-1, 4)
+    packed = (codes[:, 0] | (codes[:, 1] << 2) | (codes[:, 2] << 4) | (codes[:, 3] << 6)).astype(np.uint8)
+    packed.tofile(basename + ".4.ebwt")
+    side_sz = (1 << line_rate) * lines_per_side
+    side_bwt_sz = side_sz - 8
+    bwt_sz = total // 4 + 1
+    n_side_pairs = (bwt_sz + 2 * side_bwt_sz - 1) // (2 * side_bwt_sz)
+    with open(basename + ".1.ebwt", "wb") as f:
+        f.write(struct.pack("<7i", 1, total, line_rate, lines_per_side, 5, ftab_chars, 0))
+        f.write(struct.pack("<I", len(seqs)))
+        f.write(struct.pack("<%dI" % len(seqs), *[len(s) for s in seqs]))
+        f.write(struct.pack("<I", len(recs)))
+        f.write(b"\x00" * (12 * len(recs)))
+        f.write(b"\x00" * (n_side_pairs * 2 * side_sz + bwt_pad))
+        f.write(struct.pack("<I", 0) + struct.pack("<5I", 0, 1, 2, 3, total))
+        f.write(b"\x00" * (4 * ((1 << (2 * ftab_chars)) + 1)))
+        f.write(b"\x00" * (4 * 2 * ftab_chars))
+        f.write(("\n".join(names) + "\n").encode() + b"\x00")
