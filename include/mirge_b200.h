@@ -293,6 +293,15 @@ int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, const mirge
                           int n_rounds, const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round,
                           uint64_t *d_hit, uint32_t *d_order_scratch, void *stream);
 
+/* Every hit of the best stratum for the sequences d_ids[0..n_ids) that `policy`'s round annotated (bowtie
+ * -a --best --strata, rounds 2 and 3; feeds the per-round SAM files of -trf / -bam, manifoldAlign.py:20-62).
+ * Two calls: fill = 0 writes d_counts[i] = hits found for d_ids[i]; after an exclusive scan into d_offs, fill = 1
+ * writes the hit words to d_out[d_offs[i] ...].  An alignment reachable through several seed pieces appears once
+ * per piece; callers remove duplicates. */
+int mirge_annotate_allhits(mirge_ctx *ctx, const mirge_library *lib, const mirge_round_policy *policy,
+                           const mirge_table *t, const uint32_t *d_ids, uint64_t n_ids, const uint64_t *d_hit,
+                           int fill, uint32_t *d_counts, const uint64_t *d_offs, uint64_t *d_out, void *stream);
+
 /* ---- stage 4: counters of annotation.report.csv (summarize, summary.py:692-698,716-770) ---- */
 /* For every (key id, count) pair of ONE sample (the output of mirge_table_drain):
  *   d_round_sum[round of the key] += count            (u64[10]; unannotated keys are skipped)

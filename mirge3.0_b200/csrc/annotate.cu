@@ -294,6 +294,71 @@ __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const
   return best;
 }
 
+// A packed key as the rounds see it
+struct KeyView {
+  const uint32_t *pay, *exc;
+  int len, nexc;
+};
+
+__device__ __forceinline__ KeyView key_view(const uint32_t *key) {
+  KeyView k;
+  const uint32_t hdr = key[0];
+  k.len = (int)key_len(hdr);
+  k.nexc = (int)key_nexc(hdr);
+  k.pay = key + 1;
+  k.exc = key + 1 + ((k.len + 15) >> 4);
+  return k;
+}
+
+// query window [qs, qe) of the key in one round (manifoldAlign.py:118-126: round 3 searches the sequence without
+// its trailing T{3,} run; -5/-3 of round 8); false = the round does not search this key.  tlen caches the length
+// without the trailing run of upper-case T (-1 = not computed yet).
+__device__ __forceinline__ bool round_window(const KeyView &k, const mirge_round_policy &pol, int &tlen, int &qs, int &qe) {
+  qs = 0;
+  qe = k.len;
+  if (pol.strip_polyT) {
+    if (tlen < 0) {
+      int tpos = k.len;
+      while (tpos > 0) {
+        const int j = tpos - 1;
+        if (((k.pay[j >> 4] >> (2 * (j & 15))) & 3u) != 3u) break;
+        bool is_exc = false;  // a lower-case 't' (or any non-"ACGT" byte) is stored as an exception
+        for (int x = 0; x < k.nexc; ++x) is_exc |= (int)(k.exc[x] >> 8) == j;
+        if (is_exc) break;
+        --tpos;
+      }
+      tlen = tpos;
+    }
+    if (k.len - tlen < 3) return false;
+    qe = tlen;
+  }
+  qs += pol.trim5;
+  qe -= pol.trim3;
+  return qe > qs;
+}
+
+// 2-bit query words and always-mismatch mask of key[qs:qe)
+__device__ __forceinline__ void build_query(const KeyView &k, int qs, int qe, uint32_t *qw, uint32_t *qnx) {
+  const int L = qe - qs, nw = (L + 15) >> 4, npay = (k.len + 15) >> 4;
+  for (int w = 0; w < nw; ++w) {
+    const int p = qs + 16 * w, wi = p >> 4, sh = 2 * (p & 15);
+    const uint32_t lo = k.pay[wi], hi = (wi + 1 < npay) ? k.pay[wi + 1] : 0u;
+    uint32_t v = sh ? __funnelshift_r(lo, hi, sh) : lo;
+    const int rem = L - 16 * w;
+    if (rem < 16) v &= (1u << (2 * rem)) - 1u;
+    qw[w] = v;
+    qnx[w] = 0;
+  }
+  for (int x = 0; x < k.nexc; ++x) {
+    const int pos = (int)(k.exc[x] >> 8) - qs;
+    if (pos < 0 || pos >= L) continue;
+    const uint32_t code = base_code_upper(k.exc[x] & 0xFFu);
+    const int w = pos >> 4, sh = 2 * (pos & 15);
+    if (code < 4u) qw[w] = (qw[w] & ~(3u << sh)) | (code << sh);
+    else qnx[w] |= 1u << sh;
+  }
+}
+
 // All rounds of bwtAlign for one unique sequence per thread, in order; a sequence leaves at the first round
 // that hits it (manifoldAlign.py:120,129).  The key is read once and the query words are rebuilt only when
 // a round's window differs (poly-T stripping of round 3, -5/-3 trimming of round 8).
@@ -307,18 +372,15 @@ annotate_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_k
   // with `order` the threads of a warp hold sequences of the same length (see order_* kernels below)
   const uint64_t id = (in_range && order) ? order[slot] : slot;
   uint32_t qw[QW_MAX], qnx[QW_MAX];
-  const uint32_t *key = nullptr, *pay = nullptr, *exc = nullptr;
-  int len = 0, nexc = 0, cur_qs = -1, cur_qe = -1, tlen = -1;
+  KeyView kv;
+  kv.pay = kv.exc = nullptr; kv.len = kv.nexc = 0;
+  int cur_qs = -1, cur_qe = -1, tlen = -1;
   uint32_t state = 0xFF;  // round that annotated this sequence, 0xFF = none yet
   if (in_range) {
-    key = t.d_arena + t.d_key_ref[id];
-    const uint32_t hdr = key[0];
-    len = (int)key_len(hdr);
-    nexc = (int)key_nexc(hdr);
-    pay = key + 1;
-    exc = key + 1 + ((len + 15) >> 4);
+    kv = key_view(t.d_arena + t.d_key_ref[id]);
     state = annot_round[id];
   }
+  const int len = kv.len, nexc = kv.nexc;
   uint64_t my_hit = MIRGE_NO_HIT;
   int my_round = -1;
   bool republish = true;  // the warp scratch does not hold this lane's current query words yet
@@ -332,48 +394,12 @@ annotate_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_k
     }
     int L = 0;
     if (active) {
-      // query window [qs, qe) of the key (manifoldAlign.py:118-126; -5/-3 of round 8)
-      int qs = 0, qe = len;
-      if (pol.strip_polyT) {
-        if (tlen < 0) {  // length without the trailing run of upper-case T
-          int tpos = len;
-          while (tpos > 0) {
-            const int j = tpos - 1;
-            if (((pay[j >> 4] >> (2 * (j & 15))) & 3u) != 3u) break;
-            bool is_exc = false;  // a lower-case 't' (or any non-"ACGT" byte) is stored as an exception
-            for (int x = 0; x < nexc; ++x) is_exc |= (int)(exc[x] >> 8) == j;
-            if (is_exc) break;
-            --tpos;
-          }
-          tlen = tpos;
-        }
-        if (len - tlen < 3) active = false;
-        qe = tlen;
-      }
-      qs += pol.trim5;
-      qe -= pol.trim3;
-      if (qe <= qs) active = false;
+      int qs, qe;
+      active = round_window(kv, pol, tlen, qs, qe);
       if (active) {
         L = qe - qs;
-        if (qs != cur_qs || qe != cur_qe) {
-          const int nw = (L + 15) >> 4, npay = (len + 15) >> 4;
-          for (int w = 0; w < nw; ++w) {
-            const int p = qs + 16 * w, wi = p >> 4, sh = 2 * (p & 15);
-            const uint32_t lo = pay[wi], hi = (wi + 1 < npay) ? pay[wi + 1] : 0u;
-            uint32_t v = sh ? __funnelshift_r(lo, hi, sh) : lo;
-            const int rem = L - 16 * w;
-            if (rem < 16) v &= (1u << (2 * rem)) - 1u;
-            qw[w] = v;
-            qnx[w] = 0;
-          }
-          for (int x = 0; x < nexc; ++x) {
-            const int pos = (int)(exc[x] >> 8) - qs;
-            if (pos < 0 || pos >= L) continue;
-            const uint32_t code = base_code_upper(exc[x] & 0xFFu);
-            const int w = pos >> 4, sh = 2 * (pos & 15);
-            if (code < 4u) qw[w] = (qw[w] & ~(3u << sh)) | (code << sh);
-            else qnx[w] |= 1u << sh;
-          }
+        if (qs != cur_qs || qe != cur_qe) {  // the query words are rebuilt only when the window changes
+          build_query(kv, qs, qe, qw, qnx);
           cur_qs = qs;
           cur_qe = qe;
           republish = true;
@@ -391,6 +417,69 @@ annotate_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_k
     annot_round[id] = (uint8_t)my_round;
     hit[id] = my_hit;
   }
+}
+
+// ---- every hit of the best stratum (rounds run with -a --best --strata; SAM emission) ------------------------
+// For the listed sequences (annotated by this round, best stratum = MIRGE_HIT_MM(hit[id])): all valid alignments
+// with that many mismatches.  fill == 0: counts[i] = number of hits found (an alignment reachable through
+// several seed pieces is found once per piece; the host removes duplicates); fill != 0: the hits are written to
+// out[offs[i] ...].  Thread per sequence: these lists are short (tRNA libraries).
+__global__ void __launch_bounds__(ANN_THREADS)
+allhits_kernel(mirge_library lib, mirge_round_policy pol, mirge_table t, const uint32_t *__restrict__ ids, uint64_t n,
+               const uint64_t *__restrict__ hit, int fill, uint32_t *__restrict__ counts, const uint64_t *__restrict__ offs,
+               uint64_t *__restrict__ out) {
+  const uint64_t i = (uint64_t)blockIdx.x * ANN_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t id = ids[i];
+  const uint64_t want_mm = hit[id] >> 56;
+  const KeyView kv = key_view(t.d_arena + t.d_key_ref[id]);
+  uint32_t qw[QW_MAX], qnx[QW_MAX];
+  int tlen = -1, qs, qe;
+  uint32_t k = 0;
+  const uint64_t o0 = fill ? offs[i] : 0;
+  if (round_window(kv, pol, tlen, qs, qe)) {
+    build_query(kv, qs, qe, qw, qnx);
+    const int L = qe - qs, nw = (L + 15) >> 4;
+    const int R = pol.seed_len == 0 ? L : min(pol.seed_len, L);
+    const int np = pol.seed_mm + 1;
+#define ALLHITS_TAKE(h_)                                    \
+    if ((h_) != MIRGE_NO_HIT && ((h_) >> 56) == want_mm) {  \
+      if (fill) out[o0 + k] = (h_);                         \
+      ++k;                                                  \
+    }
+    if (R / np < MIN_SEED) {
+      for (uint32_t r = 0; r < lib.n_refs; ++r) {
+        const uint32_t lo = lib.d_ref_off[r], hi = lib.d_ref_off[r + 1];
+        for (uint64_t a = lo; a + L <= hi; ++a) {
+          const uint64_t h = verify(lib, qw, qnx, L, pol, R, a, (uint32_t)a);
+          ALLHITS_TAKE(h)
+        }
+      }
+    } else {
+      for (int pi = 0; pi < np; ++pi) {
+        const int a = (int)((uint32_t)(pi * R) / (uint32_t)np), b = (int)((uint32_t)((pi + 1) * R) / (uint32_t)np);
+        const int s = min(16, b - a);
+        if (kv.nexc > 0 && query_has_n(qnx, a, b)) continue;
+        const uint32_t span = (s == 16) ? 0u : ((1u << (2 * (16 - s))) - 1u);
+        const uint32_t k_lo = query_kmer16(qw, a, nw) & ~span, k_hi = k_lo | span;
+        const uint32_t bsh = 32 - lib.bucket_bits;
+        uint32_t l = lib.d_idx_bucket[k_lo >> bsh], h = lib.d_idx_bucket[(k_hi >> bsh) + 1];
+        const uint32_t hi0 = h;
+        while (l < h) { const uint32_t mid = (l + h) >> 1; if (lib.d_idx_kmer[mid] < k_lo) l = mid + 1; else h = mid; }
+        const uint32_t e0 = l;
+        h = hi0;
+        while (l < h) { const uint32_t mid = (l + h) >> 1; if (lib.d_idx_kmer[mid] <= k_hi) l = mid + 1; else h = mid; }
+        for (uint32_t e = e0; e < l; ++e) {
+          const uint32_t pos = lib.d_idx_pos[e];
+          if (pos < (uint32_t)a) continue;
+          const uint64_t hh = verify(lib, qw, qnx, L, pol, R, pos - (uint32_t)a, pos);
+          ALLHITS_TAKE(hh)
+        }
+      }
+    }
+#undef ALLHITS_TAKE
+  }
+  if (!fill) counts[i] = k;
 }
 
 // ---- sequences ordered by length (counting sort) -----------------------------------------------------------
@@ -496,4 +585,21 @@ extern "C" int mirge_annotate_round(mirge_ctx *ctx, const mirge_library *lib, co
   if (!ctx) return MIRGE_ERR_ARG;
   if (!lib || !policy) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: null argument");
   return mirge_annotate_rounds(ctx, lib, policy, 1, t, n_keys, d_annot_round, d_hit, nullptr, stream_);
+}
+
+extern "C" int mirge_annotate_allhits(mirge_ctx *ctx, const mirge_library *lib, const mirge_round_policy *policy, const mirge_table *t,
+                                      const uint32_t *d_ids, uint64_t n_ids, const uint64_t *d_hit, int fill, uint32_t *d_counts,
+                                      const uint64_t *d_offs, uint64_t *d_out, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  if (!lib || !policy || !t || !d_ids || !d_hit) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "allhits: null argument");
+  if (fill ? (!d_offs || !d_out) : !d_counts) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "allhits: null output buffer");
+  if (n_ids == 0) return MIRGE_OK;
+  int rc = check_round(ctx, lib, policy);
+  if (rc) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  allhits_kernel<<<(unsigned)((n_ids + ANN_THREADS - 1) / ANN_THREADS), ANN_THREADS, 0, stream>>>(*lib, *policy, *t, d_ids, n_ids, d_hit,
+                                                                                                   fill, d_counts, d_offs, d_out);
+  MIRGE_LAUNCH_CHECK(ctx, "allhits_kernel");
+  return MIRGE_OK;
 }

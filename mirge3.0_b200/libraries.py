@@ -132,6 +132,19 @@ class DeviceLibrary:
         self.ref_block = (torch.searchsorted(off_d, starts, right=True) - 1).clamp_(0, max(self.n_refs - 1, 0)).to(torch.int32)
         self._build_index()
 
+    def host_text(self) -> np.ndarray:
+        """ASCII text of the concatenated references on the host (decoded once from the device copy; only the SAM
+        writers need it, for MD:Z tags)."""
+        if getattr(self, "_host_text", None) is None:
+            words = self.packed.cpu().numpy().view(np.uint32)
+            codes = ((words[:, None] >> (2 * np.arange(16, dtype=np.uint32))) & 3).astype(np.uint8).reshape(-1)[: self.n_bases]
+            text = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+            nm = self.nmask.cpu().numpy().view(np.uint32)
+            isn = ((nm[:, None] >> np.arange(32, dtype=np.uint32)) & 1).astype(bool).reshape(-1)[: self.n_bases]
+            text[isn] = ord("N")
+            self._host_text = text
+        return self._host_text
+
     def _base_struct(self) -> abi.Library:
         return abi.Library(self.packed.data_ptr(), self.nmask.data_ptr(), self.ref_off.data_ptr(), self.n_refs, self.n_bases,
                            0 if self.idx_kmer is None else self.idx_kmer.data_ptr(),

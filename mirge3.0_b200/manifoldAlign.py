@@ -189,6 +189,81 @@ def load_libraries(args, ref_db: str, dev: Device) -> LibrarySet:
     return _LIB_CACHE[key]
 
 
+# per-round SAM files (alignPlusParse, manifoldAlign.py:20-45,57-62): -bam keeps rounds 0/8, 1, 4, 5, 6, 7; -trf rounds 2, 3
+_SAM_BAM = {0: "miRge3_miRNA.sam", 8: "miRge3_miRNA.sam", 1: "miRge3_hairpin_miRNA.sam", 4: "miRge3_snorna.sam",
+            5: "miRge3_rrna.sam", 6: "miRge3_ncrna_others.sam", 7: "miRge3_mrna.sam"}
+_SAM_TRF = {2: "miRge3_tRNA.sam", 3: "miRge3_pre_tRNA.sam"}
+
+
+def best_stratum_hits(dev: Device, lib, pol, keys: KeySet, ids: np.ndarray, hit_d: torch.Tensor):
+    """All hits of the best stratum for the sequences ``ids`` of a -a --best --strata round: (row index into ids,
+    hit word) pairs, unique, grouped by row, ascending hit word inside a row."""
+    n = int(ids.size)
+    if n == 0:
+        return np.zeros(0, dtype=np.int64), np.zeros(0, dtype=np.uint64)
+    ids_d = torch.from_numpy(ids.astype(np.int32)).to(dev.tdev)
+    counts = dev.zeros(n, torch.int32)
+    call = lambda fill, offs, out: dev.check(dev.lib.mirge_annotate_allhits(
+        dev.ctx, C.byref(lib.struct), C.byref(pol), C.byref(keys.struct), _ptr(ids_d), n, _ptr(hit_d), fill, _ptr(counts),
+        _ptr(offs), _ptr(out), dev.stream()))
+    call(0, None, None)
+    offs = torch.cumsum(counts.to(torch.int64), 0) - counts.to(torch.int64)
+    total = int((offs[-1] + counts[-1]).item())
+    out = dev.empty(total, torch.int64)
+    call(1, offs, out)
+    dev.launches += 2
+    rows = np.repeat(np.arange(n, dtype=np.int64), counts.cpu().numpy())
+    words = out[:total].cpu().numpy().view(np.uint64)
+    pairs = np.unique(np.stack([rows.astype(np.uint64), words], axis=1), axis=0)  # drops per-piece duplicates, sorts
+    return pairs[:, 0].astype(np.int64), pairs[:, 1]
+
+
+def _md_tag(query: str, ref_seg: str, seed: int):
+    """(XA stratum, MD:Z string, NM) of an ungapped alignment, bowtie style."""
+    q = np.frombuffer(query.upper().encode("latin-1"), dtype=np.uint8)
+    r = np.frombuffer(ref_seg.upper().encode("latin-1"), dtype=np.uint8)
+    acgt = (q == 65) | (q == 67) | (q == 71) | (q == 84)
+    mis = np.nonzero(~((q == r) & acgt))[0]
+    if mis.size == 0:
+        return 0, str(len(query)), 0
+    parts, prev = [], 0
+    for p in mis.tolist():
+        parts.append(str(p - prev))
+        parts.append(ref_seg[p].upper())
+        prev = p + 1
+    parts.append(str(len(query) - prev))
+    return int((mis < seed).sum()), "".join(parts), int(mis.size)
+
+
+def round_query_text(seq: str, pol) -> str:
+    """What bowtie aligns (and prints as SEQ) for ``seq`` in a round: round 3 strips the trailing T{3,} run
+    (manifoldAlign.py:118-126), -5 / -3 trim the ends."""
+    q = seq
+    if pol.strip_polyT:
+        e = len(q)
+        while e > 0 and q[e - 1] == "T":
+            e -= 1
+        q = q[:e]
+    return q[pol.trim5 : max(len(q) - pol.trim3, pol.trim5)]
+
+
+def write_round_sam(path, seqs, rows: np.ndarray, hits: np.ndarray, lib, pol):
+    """Append bowtie-format SAM records (one per (row, hit word) pair, in the given order) to ``path``."""
+    text = lib.host_text()
+    off_h = lib.ref_off_host
+    with open(path, "a+") as fh:
+        for row, h in zip(rows.tolist(), hits.tolist()):
+            ref, off = (h >> 28) & 0xFFFFFFF, h & 0xFFFFFFF
+            name = seqs[row]
+            q = round_query_text(name, pol)
+            a = int(off_h[ref]) + off
+            seg = text[a : a + len(q)].tobytes().decode("latin-1")
+            seed = len(q) if pol.seed_len == 0 else min(pol.seed_len, len(q))
+            xa, md, nm = _md_tag(q, seg, seed)
+            fh.write("%s\t0\t%s\t%d\t255\t%dM\t*\t0\t0\t%s\t%s\tXA:i:%d\tMD:Z:%s\tNM:i:%d\n"
+                     % (name, lib.names[ref], off + 1, len(q), q, "I" * len(q), xa, md, nm))
+
+
 def bwtAlign(args, pdDataFrame, workDir, ref_db, libraries: Optional[LibrarySet] = None, device: Optional[Device] = None):
     """Same contract as the reference ``bwtAlign(args, pdDataFrame, workDir, ref_db)``
     (manifoldAlign.py:68-146): fills the annotation column of the first round that hits each
@@ -200,9 +275,6 @@ def bwtAlign(args, pdDataFrame, workDir, ref_db, libraries: Optional[LibrarySet]
     if not getattr(args, "quiet", False):
         print("Alignment in progress ...")
     outlog.write("Alignment in progress ...\n")
-    if getattr(args, "bam_out", False) or getattr(args, "tRNA_frag", False):
-        outlog.close()
-        raise MirgeError("-bam / -trf need per-round SAM files, which the B200 path does not emit yet (DESIGN.md, out of scope)")
     dev = device or get_device()
     libs = libraries or load_libraries(args, ref_db, dev)
     spike = bool(getattr(args, "spikeIn", False))
@@ -225,6 +297,27 @@ def bwtAlign(args, pdDataFrame, workDir, ref_db, libraries: Optional[LibrarySet]
     flag = pdDataFrame[colnames[0]].to_numpy(copy=True)
     flag[annot != 0xFF] = 1
     pdDataFrame[colnames[0]] = flag
+    # per-round SAM files for bamFmt.bow2bam (-bam) and the tRF block of summarize (-trf): records in the order
+    # bowtie prints them (input order = table order); -a rounds list every hit of the best stratum, the
+    # canonical pick last (the record the reference's parser keeps, manifoldAlign.py:50-56)
+    want_bam, want_trf = bool(getattr(args, "bam_out", False)), bool(getattr(args, "tRNA_frag", False))
+    if want_bam or want_trf:
+        pols = round_policies()
+        for rnd in range(10 if spike else 9):
+            fname = (_SAM_BAM.get(rnd) if want_bam else None) or (_SAM_TRF.get(rnd) if want_trf else None)
+            if fname is None:
+                continue
+            rows = np.nonzero(annot == rnd)[0]
+            if rows.size == 0:
+                continue
+            lib = libs[ROUND_LIBS[rnd]]
+            if rnd in _SAM_TRF:
+                r_idx, words = best_stratum_hits(dev, lib, pols[rnd], keys, rows, hit_d)
+                order = np.lexsort((np.iinfo(np.int64).max - words.astype(np.int64), r_idx))  # row ascending, hit descending
+                sam_rows, sam_hits = rows[r_idx[order]], words[order]
+            else:
+                sam_rows, sam_hits = rows, hit[rows].view(np.uint64)
+            write_round_sam(Path(workDir) / fname, seqs, sam_rows, sam_hits, lib, pols[rnd])
     finish = time.perf_counter()
     if not spike:
         pdDataFrame = pdDataFrame.drop(columns=["spike-in"])

@@ -816,3 +816,34 @@ def mir_counts_csv(mir_counts: Dict[str, Sequence[float]], samples: Sequence[str
     for n, v in mir_counts.items():
         out.append(n + "," + ",".join(repr(float(x)) for x in v))
     return "\n".join(out) + "\n"
+
+
+# ---------------------------------------------------------------------------------------------------
+# bowtie 1 SAM records (-S) for the per-round SAM files of -bam / -trf (manifoldAlign.py:20-62).  Field layout
+# after the bowtie manual and the example line the reference quotes (summary.py:1194): FLAG 0 (forward strand,
+# --norc), 1-based POS of the (trimmed) query, MAPQ 255, CIGAR <len>M, QUAL all 'I' (FASTA input), then
+# XA:i:<stratum> MD:Z:<mismatch string> NM:i:<mismatches>.  bowtie's XM:i tag is not reproduced (its value
+# depends on -m/-M bookkeeping the reference never reads).
+# ---------------------------------------------------------------------------------------------------
+
+def md_string(query: str, ref_seg: str) -> Tuple[str, List[int]]:
+    """MD:Z value of an ungapped alignment and the 0-based query positions of its mismatches."""
+    out, run, pos = [], 0, []
+    for j, (q, r) in enumerate(zip(query.upper(), ref_seg.upper())):
+        if q == r and q in "ACGT":
+            run += 1
+        else:
+            out.append(str(run))
+            out.append(r)
+            run = 0
+            pos.append(j)
+    out.append(str(run))
+    return "".join(out), pos
+
+
+def sam_line(qname: str, query: str, ref_name: str, ref_seq: str, off: int, pol: RoundPolicy) -> str:
+    md, pos = md_string(query, ref_seq[off : off + len(query)])
+    seed = len(query) if pol.seed_len == 0 else min(pol.seed_len, len(query))
+    stratum = sum(1 for p in pos if p < seed)
+    return "%s\t0\t%s\t%d\t255\t%dM\t*\t0\t0\t%s\t%s\tXA:i:%d\tMD:Z:%s\tNM:i:%d" % (
+        qname, ref_name, off + 1, len(query), query, "I" * len(query), stratum, md, len(pos))

@@ -101,8 +101,7 @@ for line in open(fasta):
     if "-a" not in flags:
         hs = hs[:1]
     for mm, r, off in reversed(hs):  # canonical pick (minimum) last: the reference keeps the last line
-        out.write("%%s\t0\t%%s\t%%d\t255\t%%dM\t*\t0\t0\t%%s\t%%s\tXA:i:%%d\tNM:i:%%d\n"
-                  %% (name, lib.names[r], off + 1, len(q), q, "I" * len(q), mm, mm))
+        out.write(po.sam_line(name, q, lib.names[r], lib.seqs[r], off, pol) + "\n")
 '''
 
 FAKE_INSPECT = r'''#!%(python)s
@@ -192,7 +191,7 @@ QIA_INNER = "AACTGTAGGCACCATCAAT"
 
 def reference_args(libdir=None, bindir=None, **kw):
     """The args namespace fields the reference code reads (mirge/libs/parse.py defaults unless overridden)."""
-    a = argparse.Namespace(threads=2, bowtie_path=str(bindir) if bindir else None, bowtieVersion="True", quiet=True,
+    a = argparse.Namespace(threads=1, bowtie_path=str(bindir) if bindir else None, bowtieVersion="True", quiet=True,
                            organism_name=ORG, libraries_path=str(libdir) if libdir else None, spikeIn=True, bam_out=False,
                            tRNA_frag=False, crThreshold="0.1", gff_out=False, AtoI=False, isoform_entropy=False,
                            novel_miRNA=False,
@@ -344,6 +343,17 @@ def main():
         pdUnmapped.to_csv(work / "unmapped.csv")                             # __main__.py:173
         for f in ("mapped.csv", "unmapped.csv", "annotation.report.csv", "miR.Counts.csv", "miR.RPM.csv"):
             shutil.copy(work / f, CASE / f)
+        # the per-round SAM files of -bam / -trf (manifoldAlign.py:20-62): bwtAlign alone, on a fresh table
+        work2 = Path(tmp) / "work_sam"
+        work2.mkdir()
+        args2 = reference_args(libdir, bindir, quality_cutoff="20", bam_out=True, tRNA_frag=True)
+        df2, *_ = baking(args2, files, SAMPLES, work2)
+        out2 = bwtAlign(args2, df2, work2, DB)
+        assert out2.equals(out)
+        (CASE / "sam").mkdir()
+        for f in sorted(os.listdir(work2)):
+            if f.endswith(".sam"):
+                shutil.copy(work2 / f, CASE / "sam" / f)
     n_map, n_un = len(pdMapped), len(pdUnmapped)
     (CASE / "README.txt").write_text(
         "Generated by tests/golden/make_reference_golden.py (pandas %s) from the unmodified reference's bwtAlign,\n"

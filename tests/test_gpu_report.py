@@ -93,3 +93,21 @@ def test_baking_matches_reference_baking(dev, tmp_path, name):
         tcf = os.path.join(d, s + ".trim.collapse.fa")
         if os.path.exists(tcf):
             assert tcf_pairs(str(tmp_path / (s + ".trim.collapse.fa"))) == tcf_pairs(tcf)
+
+
+def test_per_round_sam_files_match_reference(dev, tmp_path):
+    """bwtAlign with -bam and -trf writes the per-round SAM files the reference wrote (all best-stratum hits for
+    the two tRNA rounds, canonical pick last), and the table is the same as without the flags."""
+    from mirge_b200 import digest as DG
+    from mirge_b200 import manifoldAlign as MA
+
+    args = make_args(libraries_path=os.path.join(CASE, "lib"), organism_name=ORG, spikeIn=True, quality_cutoff="20",
+                     bam_out=True, tRNA_frag=True)
+    files = [os.path.join(CASE, s + ".fastq.gz") for s in SAMPLES]
+    df, *_ = DG.baking(args, files, SAMPLES, str(tmp_path), device=dev)
+    out = MA.bwtAlign(args, df, str(tmp_path), DB, device=dev)
+    out.to_csv(tmp_path / "all.csv")
+    sam_dir = os.path.join(CASE, "sam")
+    for name in sorted(os.listdir(sam_dir)):
+        assert (tmp_path / name).read_text() == open(os.path.join(sam_dir, name)).read(), name
+    assert int((out.annotFlag == 1).sum()) == len(golden("mapped.csv").splitlines()) - 1

@@ -126,3 +126,32 @@ def test_oracle_digest_matches_reference_baking(name):
             counts.setdefault(k, [0] * len(tables))[j] = c
     rows = [(k, 0, [""] * 10, counts[k]) for k in sorted(counts)]
     assert po.table_csv(rows, meta["samples"], True) == open(os.path.join(d, "complete_set.csv")).read()
+
+
+SAM_FILES = {0: "miRge3_miRNA.sam", 8: "miRge3_miRNA.sam", 1: "miRge3_hairpin_miRNA.sam", 4: "miRge3_snorna.sam",
+             5: "miRge3_rrna.sam", 6: "miRge3_ncrna_others.sam", 7: "miRge3_mrna.sam", 2: "miRge3_tRNA.sam",
+             3: "miRge3_pre_tRNA.sam"}  # manifoldAlign.py:20-45
+
+
+def test_per_round_sam_files_match_reference(oracle_run):
+    """-bam / -trf: which records the reference appends to which file, in which order (the record text itself is
+    the stand-in bowtie's, i.e. the oracle's sam_line)."""
+    counts, annot, libs, *_ = oracle_run
+    files = {}
+    for rnd in range(9):  # round 9 (spike-in) is never written (manifoldAlign.py:57-62)
+        lib, pol = libs[po.ROUND_LIBS[rnd]], po.ROUND_POLICIES[rnd]
+        for seq in sorted(counts):
+            a = annot.get(seq)
+            if a is None or a[0] != rnd:
+                continue
+            q = po.round_query(seq, rnd)
+            hs = po.hits(q, lib, pol)
+            best = min(h[0] for h in hs)
+            hs = sorted((h[0], h[1], h[2]) for h in hs if h[0] == best)
+            if rnd not in (2, 3):
+                hs = hs[:1]
+            for mm, r, off in reversed(hs):
+                files.setdefault(SAM_FILES[rnd], []).append(po.sam_line(seq, q, lib.names[r], lib.seqs[r], off, pol))
+    assert sorted(files) == sorted(set(SAM_FILES.values()))
+    for name, lines in files.items():
+        assert "\n".join(lines) + "\n" == golden(os.path.join("sam", name)), name
