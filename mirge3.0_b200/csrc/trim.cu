@@ -261,6 +261,12 @@ struct FastCtx {
 struct ByteRead {
   const uint8_t *p;
   __device__ __forceinline__ uint32_t eq(const uint32_t *eqt, int j) const { return eqt[p[j]]; }
+  // sequential access for the column loop
+  struct Cursor {
+    const uint8_t *q;
+    __device__ __forceinline__ uint32_t next(const uint32_t *eqt) { return eqt[*q++]; }
+  };
+  __device__ __forceinline__ Cursor cursor() const { return Cursor{p}; }
 };
 struct PackedRead {
   const uint32_t *ps;
@@ -268,6 +274,29 @@ struct PackedRead {
   __device__ __forceinline__ uint32_t eq(const uint32_t *eqt, int j) const {
     const int a = base + j;
     return eqt[(ps[(a >> 4) * TRIM_THREADS] >> (2 * (a & 15))) & 3u];
+  }
+  // sequential access for the column loop: the current 16-base word lives in a register and is shifted by one
+  // base per column; a new word is fetched every 16 columns
+  struct Cursor {
+    const uint32_t *row;
+    uint32_t w;
+    int left;
+    __device__ __forceinline__ uint32_t next(const uint32_t *eqt) {
+      if (left == 0) {
+        row += TRIM_THREADS;
+        w = *row;
+        left = 16;
+      }
+      const uint32_t code = w & 3u;
+      w >>= 2;
+      --left;
+      return eqt[code];
+    }
+  };
+  __device__ __forceinline__ Cursor cursor() const {
+    const uint32_t *row = ps + (base >> 4) * TRIM_THREADS;
+    const int sh = base & 15;
+    return Cursor{row, *row >> (2 * sh), 16 - sh};
   }
 };
 
@@ -483,8 +512,9 @@ __device__ __forceinline__ int locate_fast(const int a, const RV read, const int
   }
 
   uint32_t hp = 0, hn = 0;  // horizontal deltas of the column just computed
+  auto cur = read.cursor();
   for (int j = 1; j <= n; ++j) {
-    eq = read.eq(eqt, j - 1);
+    eq = cur.next(eqt);
     const int score_prev = score;
     pvp = vp;
     pvn = vn;
@@ -664,6 +694,27 @@ __device__ __noinline__ bool apply_mod(int mi, const uint8_t *seq, const uint8_t
     default: break;
   }
   return false;
+}
+
+// the modifiers that need no adapter search (everything stage 1 of the split pipeline runs before the adapter)
+__device__ __forceinline__ void apply_plain_mod(int mi, const uint8_t *seq, const uint8_t *qual, int &start, int &stop) {
+  const int len = stop - start;
+  const int kind = c_p.kind[mi];
+  if (kind == MIRGE_MOD_NEXTSEQ) {
+    stop = start + nextseq_trim_index(seq + start, qual + start, len, c_p.a[mi], c_p.b[mi]);
+  } else if (kind == MIRGE_MOD_QUALITY) {
+    int s, e;
+    quality_trim_index(qual + start, len, c_p.a[mi], c_p.b[mi], c_p.c[mi], s, e);
+    stop = start + e;
+    start = start + s;
+  } else if (kind == MIRGE_MOD_NEND) {
+    while (start < stop && seq[start] == 'N') ++start;
+    while (stop > start && seq[stop - 1] == 'N') --stop;
+  } else if (kind == MIRGE_MOD_CUT) {
+    const int c = c_p.a[mi];
+    if (c > 0) start += min(c, len);
+    else stop = start + max(len + c, 0);
+  }
 }
 
 __device__ __forceinline__ int find_sub(const uint8_t *s, int n, const uint8_t *t, int tl, int from) {
@@ -958,7 +1009,13 @@ __device__ __forceinline__ void process_record(const bool valid, const uint64_t 
     if (good) { RUN_MODS(0, n_mods) }
   } else {
     const int mi_ad = first_adapter_mod();
-    if (good) { RUN_MODS(0, mi_ad) }
+    if (good) {
+      _Pragma("unroll 1") for (int mi = 0; mi < mi_ad; ++mi) {
+        apply_plain_mod(mi, seq, qual, start, stop);
+        __syncwarp(good_lanes);
+        RECORD_SLOT(mi)
+      }
+    }
     bool to_dp = false, resolved = false;
     if (good && mi_ad < n_mods) {
       const DevAdapter &ad0 = c_p.ad[0];
