@@ -4,8 +4,8 @@
 //
 // Layout: the byte stream is cut into tiles of TOK_TILE bytes (one CTA each, 32 contiguous bytes
 // per thread, two coalesced 128-bit loads).  Pass 1 counts '\n' per tile and per group of
-// TOK_GROUP tiles; a one-CTA scan turns group totals into prefixes; pass 2 re-reads the tile
-// (L2-resident for batches below the 126 MB L2, otherwise streamed) and scatters the start offset
+// TOK_GROUP tiles and keeps every thread's 32-bit newline mask (1/8 of the data); a one-CTA scan turns group
+// totals into prefixes; pass 2 reads the masks instead of the bytes and scatters the start offset
 // of every line: line_start[g + 1] = position after the g-th '\n'.  Four consecutive entries are
 // the header / sequence / '+' / quality line of one record, so the trim kernel fetches one
 // aligned uint4 per read.
@@ -16,6 +16,8 @@
 #define TOK_GROUP 1024
 
 struct TokScratch {
+  uint32_t *masks;  // newline mask of every 32-byte piece (one per thread of pass 1)
+  uint32_t *tile_excl;  // '\n' before the tile inside its group
   uint32_t *tile_counts;
   uint32_t *group_totals;
   uint64_t *group_prefix;
@@ -29,6 +31,10 @@ static TokScratch tok_layout(void *scratch, uint64_t nbytes) {
   s.n_tiles = (nbytes + TOK_TILE - 1) / TOK_TILE;
   s.n_groups = (s.n_tiles + TOK_GROUP - 1) / TOK_GROUP;
   uint8_t *p = (uint8_t *)scratch;
+  s.masks = (uint32_t *)p;
+  p += align16(s.n_tiles * TOK_THREADS * 4);
+  s.tile_excl = (uint32_t *)p;
+  p += align16(s.n_tiles * 4 + 4);
   s.tile_counts = (uint32_t *)p;
   p += align16(s.n_tiles * 4 + 4);
   s.group_totals = (uint32_t *)p;
@@ -41,7 +47,7 @@ extern "C" uint64_t mirge_tokenise_scratch_bytes(uint64_t nbytes) {
   nbytes += 16;  // alignment skew
   uint64_t n_tiles = (nbytes + TOK_TILE - 1) / TOK_TILE;
   uint64_t n_groups = (n_tiles + TOK_GROUP - 1) / TOK_GROUP;
-  return align16(n_tiles * 4 + 4) + align16(n_groups * 4 + 4) + align16((n_groups + 1) * 8) + 64;
+  return align16(n_tiles * TOK_THREADS * 4) + 2 * align16(n_tiles * 4 + 4) + align16(n_groups * 4 + 4) + align16((n_groups + 1) * 8) + 64;
 }
 
 // 32 bytes of the stream starting at pos -> 8 words (zero filled past n)
@@ -101,19 +107,20 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
 }
 
 __global__ void __launch_bounds__(TOK_THREADS) tok_count_kernel(const uint8_t *__restrict__ fq, uint64_t n, uint32_t skew,
-                                                                 uint32_t *__restrict__ tile_counts,
+                                                                 uint32_t *__restrict__ masks, uint32_t *__restrict__ tile_counts,
                                                                  uint32_t *__restrict__ group_totals) {
   __shared__ uint32_t sm[TOK_THREADS / 32];
   const uint64_t tile = blockIdx.x;
   const uint64_t pos = tile * TOK_TILE + (uint64_t)threadIdx.x * 32;
-  uint32_t c = 0;
+  uint32_t c = 0, mk = 0;
   if (pos < n) {
     uint32_t w[8];
     load32(fq, n, pos, w);
-    uint32_t mk = newline_mask(w);
+    mk = newline_mask(w);
     if (pos == 0) mk &= ~((1u << skew) - 1u);  // bytes before the stream start are not ours
     c = __popc(mk);
   }
+  masks[tile * TOK_THREADS + threadIdx.x] = mk;
   c = __reduce_add_sync(0xffffffffu, c);
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
   __syncthreads();
@@ -139,38 +146,37 @@ __global__ void tok_scan_groups_kernel(const uint32_t *__restrict__ group_totals
   }
 }
 
-// number of '\n' before this tile
-__device__ __forceinline__ uint64_t tile_prefix(const uint32_t *tile_counts, const uint64_t *group_prefix,
-                                                uint64_t tile, uint32_t *smem) {
-  const uint64_t g = tile / TOK_GROUP, first = g * TOK_GROUP;
-  uint32_t s = 0;
-  for (uint64_t t = first + threadIdx.x; t < tile; t += TOK_THREADS) s += tile_counts[t];
-  s = __reduce_add_sync(0xffffffffu, s);
-  if ((threadIdx.x & 31) == 0) smem[threadIdx.x >> 5] = s;
-  __syncthreads();
-  uint32_t tot = 0;
+// exclusive prefix of the tile counts inside every group of TOK_GROUP tiles (one CTA per group), so that pass 2
+// finds the number of '\n' before its tile with two loads
+__global__ void __launch_bounds__(TOK_THREADS) tok_scan_tiles_kernel(const uint32_t *__restrict__ tile_counts, uint64_t n_tiles,
+                                                                      uint32_t *__restrict__ tile_excl) {
+  __shared__ uint32_t sm[TOK_THREADS / 32];
+  const uint64_t first = (uint64_t)blockIdx.x * TOK_GROUP + (uint64_t)threadIdx.x * (TOK_GROUP / TOK_THREADS);
+  uint32_t c[TOK_GROUP / TOK_THREADS], mine = 0;
 #pragma unroll
-  for (int i = 0; i < TOK_THREADS / 32; ++i) tot += smem[i];
-  __syncthreads();
-  return group_prefix[g] + tot;
+  for (int k = 0; k < TOK_GROUP / TOK_THREADS; ++k) {
+    c[k] = first + k < n_tiles ? tile_counts[first + k] : 0u;
+    mine += c[k];
+  }
+  uint32_t total;
+  uint32_t run = block_exclusive_scan(mine, sm, &total);
+#pragma unroll
+  for (int k = 0; k < TOK_GROUP / TOK_THREADS; ++k) {
+    if (first + k < n_tiles) tile_excl[first + k] = run;
+    run += c[k];
+  }
 }
 
-__global__ void __launch_bounds__(TOK_THREADS) tok_index_kernel(const uint8_t *__restrict__ fq, uint64_t n,
-                                                                 const uint32_t *__restrict__ tile_counts,
+__global__ void __launch_bounds__(TOK_THREADS) tok_index_kernel(const uint32_t *__restrict__ masks, uint64_t n,
+                                                                 const uint32_t *__restrict__ tile_excl,
                                                                  const uint64_t *__restrict__ group_prefix,
                                                                  uint32_t *__restrict__ line_start, uint64_t max_lines,
                                                                  uint32_t skew) {
   __shared__ uint32_t sm[TOK_THREADS / 32];
   const uint64_t tile = blockIdx.x;
-  const uint64_t before = tile_prefix(tile_counts, group_prefix, tile, sm);
+  const uint64_t before = group_prefix[tile / TOK_GROUP] + tile_excl[tile];
   const uint64_t pos = tile * TOK_TILE + (uint64_t)threadIdx.x * 32;
-  uint32_t mask = 0;
-  if (pos < n) {
-    uint32_t w[8];
-    load32(fq, n, pos, w);
-    mask = newline_mask(w);
-    if (pos == 0) mask &= ~((1u << skew) - 1u);
-  }
+  uint32_t mask = masks[tile * TOK_THREADS + threadIdx.x];  // written by pass 1 (zero past the end)
   uint32_t total;
   uint32_t ex = block_exclusive_scan(__popc(mask), sm, &total);
   uint64_t g = before + ex;  // ordinal (0-based) of this thread's first '\n'
@@ -188,7 +194,7 @@ __global__ void tok_fixup_kernel(uint32_t *last, uint32_t virtual_end) {
 }
 
 // position just after the target-th '\n' (1-based ordinal); 0 when target == 0
-__global__ void __launch_bounds__(TOK_THREADS) tok_find_kernel(const uint8_t *__restrict__ fq, uint64_t n,
+__global__ void __launch_bounds__(TOK_THREADS) tok_find_kernel(const uint32_t *__restrict__ masks, uint64_t n,
                                                                 const uint32_t *__restrict__ tile_counts,
                                                                 const uint64_t *__restrict__ group_prefix,
                                                                 uint64_t n_groups, uint64_t n_tiles, uint64_t target,
@@ -212,13 +218,7 @@ __global__ void __launch_bounds__(TOK_THREADS) tok_find_kernel(const uint8_t *__
   }
   __syncthreads();
   const uint64_t pos = s_tile * TOK_TILE + (uint64_t)threadIdx.x * 32;
-  uint32_t mask = 0;
-  if (pos < n) {
-    uint32_t w[8];
-    load32(fq, n, pos, w);
-    mask = newline_mask(w);
-    if (pos == 0) mask &= ~((1u << skew) - 1u);
-  }
+  uint32_t mask = masks[s_tile * TOK_THREADS + threadIdx.x];
   uint32_t total;
   uint32_t ex = block_exclusive_scan(__popc(mask), sm, &total);
   uint64_t g = s_before + ex;
@@ -246,7 +246,7 @@ extern "C" int mirge_tokenise_sync(mirge_ctx *ctx, const uint8_t *d_fastq, uint6
   const uint64_t n_al = nbytes + skew;
   TokScratch s = tok_layout(d_scratch, n_al);
   MIRGE_CUDA(ctx, cudaMemsetAsync(s.group_totals, 0, s.n_groups * 4, stream));
-  tok_count_kernel<<<(unsigned)s.n_tiles, TOK_THREADS, 0, stream>>>(fq_al, n_al, skew, s.tile_counts, s.group_totals);
+  tok_count_kernel<<<(unsigned)s.n_tiles, TOK_THREADS, 0, stream>>>(fq_al, n_al, skew, s.masks, s.tile_counts, s.group_totals);
   MIRGE_LAUNCH_CHECK(ctx, "tok_count_kernel");
   tok_scan_groups_kernel<<<1, 32, 0, stream>>>(s.group_totals, s.n_groups, s.group_prefix, ctx->d_small);
   MIRGE_LAUNCH_CHECK(ctx, "tok_scan_groups_kernel");
@@ -265,7 +265,7 @@ extern "C" int mirge_tokenise_sync(mirge_ctx *ctx, const uint8_t *d_fastq, uint6
     return MIRGE_OK;
   }
   *n_records = n_nl / 4;
-  tok_find_kernel<<<1, TOK_THREADS, 0, stream>>>(fq_al, n_al, s.tile_counts, s.group_prefix, s.n_groups, s.n_tiles,
+  tok_find_kernel<<<1, TOK_THREADS, 0, stream>>>(s.masks, n_al, s.tile_counts, s.group_prefix, s.n_groups, s.n_tiles,
                                                  4 * (*n_records), skew, ctx->d_small + 1);
   MIRGE_LAUNCH_CHECK(ctx, "tok_find_kernel");
   MIRGE_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_small + 1, 8, cudaMemcpyDeviceToHost, stream));
@@ -291,7 +291,9 @@ extern "C" int mirge_line_index(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t
   // EOF rule: when the last line has no '\n' the 4n-th line break does not exist; the entry is
   // zeroed first and a fix-up kernel turns a still-zero entry into the virtual break nbytes + 1.
   MIRGE_CUDA(ctx, cudaMemsetAsync(d_line_start + 4 * n_records, 0, 4, stream));
-  tok_index_kernel<<<(unsigned)s.n_tiles, TOK_THREADS, 0, stream>>>(fq_al, n_al, s.tile_counts, s.group_prefix,
+  tok_scan_tiles_kernel<<<(unsigned)s.n_groups, TOK_THREADS, 0, stream>>>(s.tile_counts, s.n_tiles, s.tile_excl);
+  MIRGE_LAUNCH_CHECK(ctx, "tok_scan_tiles_kernel");
+  tok_index_kernel<<<(unsigned)s.n_tiles, TOK_THREADS, 0, stream>>>(s.masks, n_al, s.tile_excl, s.group_prefix,
                                                                     d_line_start, 4 * n_records, skew);
   MIRGE_LAUNCH_CHECK(ctx, "tok_index_kernel");
   tok_fixup_kernel<<<1, 1, 0, stream>>>(d_line_start + 4 * n_records, (uint32_t)(n_al + 1));

@@ -272,7 +272,7 @@ class DigestEngine:
         # same nbytes as the census: the scratch layout depends on it
         with d.timed("line_index"):
             d.check(lib.mirge_line_index(d.ctx, _ptr(buf), nbytes, _ptr(scratch), _ptr(line_start), n, st))
-        d.launches += 2
+        d.launches += 3
         win = d.empty(n * E * 4, torch.int16)
         key_off = d.empty(n * E, torch.int32)
         slow = d.empty(lib.mirge_trim_scratch_bytes(n), torch.uint8)  # work lists of the split trim pipeline
