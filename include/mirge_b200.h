@@ -124,8 +124,9 @@ typedef struct mirge_table {
 } mirge_table;
 
 /* One annotation library resident on the device (bowtie index replacement). */
+#define MIRGE_LIB_PAD_WORDS 40 /* readable zero words after d_packed: > MIRGE_MAX_READ_LEN / 16 + 2 */
 typedef struct mirge_library {
-  const uint32_t *d_packed;  /* 2 bits/base, all references concatenated */
+  const uint32_t *d_packed;  /* 2 bits/base, all references concatenated, followed by MIRGE_LIB_PAD_WORDS zero words */
   const uint32_t *d_nmask;   /* 1 bit/base, 1 = reference base is not ACGT */
   const uint32_t *d_ref_off; /* [n_refs + 1] first base of each reference */
   uint32_t n_refs;

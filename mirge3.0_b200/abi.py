@@ -12,6 +12,7 @@ MAX_ADAPTER_LEN = 64
 MAX_MODS = 8
 MAX_READ_LEN = 512
 ANNOTATE_ORDER_BINS = 1024  # MIRGE_ANNOTATE_ORDER_BINS
+LIB_PAD_WORDS = 40  # MIRGE_LIB_PAD_WORDS
 
 MOD_NEXTSEQ, MOD_QUALITY, MOD_ADAPTER, MOD_NEND, MOD_CUT = 1, 2, 3, 4, 5
 UMI_NONE, UMI_FLANKS, UMI_QIAGEN = 0, 1, 2

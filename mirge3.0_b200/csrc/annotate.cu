@@ -21,13 +21,13 @@
 
 __device__ __forceinline__ uint32_t lib_base(const uint32_t *packed, uint32_t p) { return (packed[p >> 4] >> (2 * (p & 15))) & 3u; }
 
-// 16 bases starting at base position p as a 2-bit word (base p in bits 0..1)
-__device__ __forceinline__ uint32_t lib_word16(const uint32_t *packed, uint64_t p, uint64_t n_words) {
+// 16 bases starting at base position p as a 2-bit word (base p in bits 0..1).  The packed text is followed by
+// MIRGE_LIB_PAD_WORDS zero words (mirge_library contract), so a candidate that runs past the end of the library
+// -- rejected afterwards by its reference bounds -- reads zeros, and no bound check is needed here.
+__device__ __forceinline__ uint32_t lib_word16(const uint32_t *packed, uint64_t p) {
   const uint64_t w = p >> 4;
   const uint32_t sh = 2 * (uint32_t)(p & 15);
-  const uint32_t lo = packed[w];
-  const uint32_t hi = (w + 1 < n_words) ? packed[w + 1] : 0u;
-  return sh ? __funnelshift_r(lo, hi, sh) : lo;
+  return __funnelshift_r(packed[w], packed[w + 1], sh);
 }
 
 // reference holding base `pos`: coarse block table, then a short forward scan (largest r with ref_off[r] <= pos)
@@ -112,11 +112,10 @@ struct RoundSet {
 // count or -1 when the policy is violated.
 __device__ __forceinline__ int verify_text(const mirge_library &lib, const uint32_t *qw, const uint32_t *qnx, int L,
                                            const mirge_round_policy &pol, int R, uint64_t astart) {
-  const uint64_t n_words = ((uint64_t)lib.n_bases + 15) >> 4;
   int mm = 0, smm = 0;
   const int nw = (L + 15) >> 4;
   for (int w = 0; w < nw; ++w) {
-    const uint32_t refw = lib_word16(lib.d_packed, astart + 16 * (uint64_t)w, n_words);
+    const uint32_t refw = lib_word16(lib.d_packed, astart + 16 * (uint64_t)w);
     uint32_t x = qw[w] ^ refw;
     x = ((x | (x >> 1)) & 0x55555555u) | qnx[w];
     const int rem = L - 16 * w;
@@ -184,6 +183,12 @@ struct WarpScratch {
   unsigned long long best[32];
 };
 
+// bases [a, b) of seed piece pi: a = pi * R / np without an integer division (np = seed mismatches + 1 <= 4, R < 2^16)
+__device__ __forceinline__ int piece_bound(int pi, int R, int np) {
+  const uint32_t x = (uint32_t)(pi * R);
+  return np == 1 ? (int)x : np == 2 ? (int)(x >> 1) : np == 3 ? (int)((x * 43691u) >> 17) : (int)(x >> 2);
+}
+
 // One bowtie round for the query of this lane (active lanes only); all 32 lanes must call it together.
 // republish: this lane's query words changed since the last round (window change) and must be copied again.
 __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const mirge_round_policy &pol, bool active,
@@ -194,11 +199,11 @@ __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const
   for (int i = 0; i < MAX_PIECES; ++i) p_lo[i] = p_hi[i] = p_off[i] = 0;
   const int R = pol.seed_len == 0 ? L : min(pol.seed_len, L);
   const int np = pol.seed_mm + 1;
-  const bool degenerate = active && (R / np < MIN_SEED);
+  const bool degenerate = active && (R < MIN_SEED * np);
   const int nw = (L + 15) >> 4;
   if (active && !degenerate) {
     for (int pi = 0; pi < np; ++pi) {
-      const int a = (int)((uint32_t)(pi * R) / (uint32_t)np), b = (int)((uint32_t)((pi + 1) * R) / (uint32_t)np);
+      const int a = piece_bound(pi, R, np), b = piece_bound(pi + 1, R, np);
       const int s = min(16, b - a);
       // a piece with a non-ACGT read base cannot be exact
       if (has_exc && query_has_n(qnx, a, b)) continue;
@@ -447,7 +452,7 @@ allhits_kernel(mirge_library lib, mirge_round_policy pol, mirge_table t, const u
       if (fill) out[o0 + k] = (h_);                         \
       ++k;                                                  \
     }
-    if (R / np < MIN_SEED) {
+    if (R < MIN_SEED * np) {
       for (uint32_t r = 0; r < lib.n_refs; ++r) {
         const uint32_t lo = lib.d_ref_off[r], hi = lib.d_ref_off[r + 1];
         for (uint64_t a = lo; a + L <= hi; ++a) {
@@ -457,7 +462,7 @@ allhits_kernel(mirge_library lib, mirge_round_policy pol, mirge_table t, const u
       }
     } else {
       for (int pi = 0; pi < np; ++pi) {
-        const int a = (int)((uint32_t)(pi * R) / (uint32_t)np), b = (int)((uint32_t)((pi + 1) * R) / (uint32_t)np);
+        const int a = piece_bound(pi, R, np), b = piece_bound(pi + 1, R, np);
         const int s = min(16, b - a);
         if (kv.nexc > 0 && query_has_n(qnx, a, b)) continue;
         const uint32_t span = (s == 16) ? 0u : ((1u << (2 * (16 - s))) - 1u);

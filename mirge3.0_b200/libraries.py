@@ -119,8 +119,8 @@ class DeviceLibrary:
         text = torch.frombuffer(bytearray(b"".join(seqs)), dtype=torch.uint8).to(dev.tdev) if self.n_bases else \
             torch.zeros(0, dtype=torch.uint8, device=dev.tdev)
         self.packed, self.nmask = pack_text(text)
-        if self.packed.numel() == 0:
-            self.packed = torch.zeros(1, dtype=torch.int32, device=dev.tdev)
+        # MIRGE_LIB_PAD_WORDS zero words after the text: the verifier may read past the last reference
+        self.packed = torch.cat([self.packed, torch.zeros(abi.LIB_PAD_WORDS, dtype=torch.int32, device=dev.tdev)])
         self.idx_kmer = self.idx_pos = self.idx_bucket = self.filter = None
         self.filter_bases = 0
         self.n_idx = 0
@@ -136,7 +136,7 @@ class DeviceLibrary:
         """ASCII text of the concatenated references on the host (decoded once from the device copy; only the SAM
         writers need it, for MD:Z tags)."""
         if getattr(self, "_host_text", None) is None:
-            words = self.packed.cpu().numpy().view(np.uint32)
+            words = self.packed[: (self.n_bases + 15) // 16].cpu().numpy().view(np.uint32)
             codes = ((words[:, None] >> (2 * np.arange(16, dtype=np.uint32))) & 3).astype(np.uint8).reshape(-1)[: self.n_bases]
             text = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
             nm = self.nmask.cpu().numpy().view(np.uint32)
