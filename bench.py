@@ -223,11 +223,14 @@ def run_b200(args):
 
     def finish(tab_local):
         """collapse done on this rank -> (exchange) -> annotate; returns (table, n_keys)"""
-        ids, cnt = tab_local.drain()
+        with dev.timed("drain"):
+            ids, cnt = tab_local.drain()
         if world > 1:
-            owner.reset()
+            with dev.timed("owner_reset"):
+                owner.reset()
             MD.exchange_and_merge(dev, tab_local, ids, cnt, owner, world)
-            ids, cnt = owner.drain()
+            with dev.timed("drain"):
+                ids, cnt = owner.drain()
             tab = owner
         else:
             tab = tab_local

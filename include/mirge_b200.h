@@ -267,6 +267,17 @@ int mirge_partition_pack(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d
                          const uint32_t *d_counts, uint64_t n, const uint32_t *d_rec_off,
                          uint32_t *d_rec, void *stream);
 
+/* The same packing without sorting by destination.  mirge_partition_totals: d_totals[d] = words and
+ * d_totals[n_parts + d] = records bound for destination d (u64[2 * n_parts], zeroed here; n_parts <= 64).
+ * mirge_partition_scatter: d_cursors (u64[n_parts]) holds, per destination, (first record index of its region in
+ * d_sizes) << 32 | (first word offset of its region in d_rec), both < 2^32; every pair is written as [count][key words] at the offset
+ * its destination's cursor hands out and its size in words to d_sizes (order inside a destination: arbitrary). */
+int mirge_partition_totals(mirge_ctx *ctx, const uint32_t *d_dest, const uint32_t *d_words, uint64_t n,
+                           uint32_t n_parts, uint64_t *d_totals, void *stream);
+int mirge_partition_scatter(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_ids, const uint32_t *d_counts,
+                            const uint32_t *d_dest, const uint32_t *d_words, uint64_t n, uint32_t n_parts,
+                            uint64_t *d_cursors, uint32_t *d_rec, uint32_t *d_sizes, void *stream);
+
 /* ---- stage 3: annotation rounds (bwtAlign, manifoldAlign.py:68-146) ------------------------ */
 /* 16-mer (zero padded, truncated at reference ends / ambiguous bases) of every base position:
  * d_kmer[n_bases], d_valid[n_bases] = number of usable bases (0..16).  Input to the host-side

@@ -591,3 +591,97 @@ extern "C" int mirge_partition_pack(mirge_ctx *ctx, const mirge_table *t, const 
   MIRGE_LAUNCH_CHECK(ctx, "partition_pack_kernel");
   return MIRGE_OK;
 }
+
+// ---- exchange packing without a sort: per-destination totals, then a scatter with per-destination cursors ----
+
+#define MAX_PARTS 64
+
+__global__ void __launch_bounds__(COL_THREADS)
+partition_totals_kernel(const uint32_t *__restrict__ dest, const uint32_t *__restrict__ words, uint64_t n, uint32_t n_parts,
+                        unsigned long long *__restrict__ totals) {
+  __shared__ unsigned long long s_w[MAX_PARTS], s_r[MAX_PARTS];
+  if (threadIdx.x < MAX_PARTS) { s_w[threadIdx.x] = 0; s_r[threadIdx.x] = 0; }
+  __syncthreads();
+  for (uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * COL_THREADS) {
+    const uint32_t d = dest[i];
+    // one shared-memory atomic per group of lanes with the same destination
+    const unsigned peers = __match_any_sync(__activemask(), d);
+    const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+    uint32_t w = words[i], sum = 0;
+    for (unsigned m = peers; m; m &= m - 1) sum += __shfl_sync(peers, w, __ffs(m) - 1);
+    if (lane == leader) {
+      atomicAdd(&s_w[d], (unsigned long long)sum);
+      atomicAdd(&s_r[d], (unsigned long long)__popc(peers));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < n_parts) {
+    if (s_w[threadIdx.x]) atomicAdd(totals + threadIdx.x, s_w[threadIdx.x]);
+    if (s_r[threadIdx.x]) atomicAdd(totals + n_parts + threadIdx.x, s_r[threadIdx.x]);
+  }
+}
+
+extern "C" int mirge_partition_totals(mirge_ctx *ctx, const uint32_t *d_dest, const uint32_t *d_words, uint64_t n, uint32_t n_parts,
+                                      uint64_t *d_totals, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  if (!d_totals || n_parts == 0 || n_parts > MAX_PARTS) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "partition_totals: 1..%d destinations", MAX_PARTS);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  MIRGE_CUDA(ctx, cudaMemsetAsync(d_totals, 0, 2ull * n_parts * sizeof(uint64_t), stream));
+  if (n == 0) return MIRGE_OK;
+  if (!d_dest || !d_words) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "partition_totals: null buffer");
+  uint64_t grid = (n + COL_THREADS - 1) / COL_THREADS;
+  if (grid > (uint64_t)ctx->sm_count * 8) grid = (uint64_t)ctx->sm_count * 8;
+  partition_totals_kernel<<<(unsigned)grid, COL_THREADS, 0, stream>>>(d_dest, d_words, n, n_parts, (unsigned long long *)d_totals);
+  MIRGE_LAUNCH_CHECK(ctx, "partition_totals_kernel");
+  return MIRGE_OK;
+}
+
+// record i goes to the send buffer of its destination: [count][key words...] at the word offset its destination's
+// cursor hands out, its size to sizes[] at the record index of the second cursor.  The order inside a destination
+// is arbitrary (the owner-side merge does not depend on it).  cursors[d] = record index << 32 | word offset.
+__global__ void __launch_bounds__(COL_THREADS)
+partition_scatter_kernel(mirge_table t, const uint32_t *__restrict__ ids, const uint32_t *__restrict__ counts,
+                         const uint32_t *__restrict__ dest, const uint32_t *__restrict__ words, uint64_t n, uint32_t n_parts,
+                         unsigned long long *__restrict__ cursors, uint32_t *__restrict__ rec, uint32_t *__restrict__ sizes) {
+  const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t d = dest[i], w = words[i];
+  const unsigned peers = __match_any_sync(__activemask(), d);
+  const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
+  uint32_t before = 0, sum = 0;
+  for (unsigned m = peers; m; m &= m - 1) {
+    const int src = __ffs(m) - 1;
+    const uint32_t x = __shfl_sync(peers, w, src);
+    if (src < lane) before += x;
+    sum += x;
+  }
+  // one atomic hands out the word range and the record range together (record index in the high half), so the
+  // order of the records in the buffer and of their sizes in sizes[] is the same
+  unsigned long long both = 0;
+  if (lane == leader) both = atomicAdd(cursors + d, ((unsigned long long)__popc(peers) << 32) | (unsigned long long)sum);
+  both = __shfl_sync(peers, both, leader);
+  const unsigned long long wbase = both & 0xFFFFFFFFull, rbase = both >> 32;
+  const uint32_t *key = t.d_arena + t.d_key_ref[ids[i]];
+  uint32_t *o = rec + wbase + before;
+  o[0] = counts[i];
+  for (uint32_t k = 0; k + 1 < w; ++k) o[1 + k] = key[k];
+  sizes[rbase + __popc(peers & ((1u << lane) - 1u))] = w;
+}
+
+extern "C" int mirge_partition_scatter(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_ids, const uint32_t *d_counts,
+                                       const uint32_t *d_dest, const uint32_t *d_words, uint64_t n, uint32_t n_parts,
+                                       uint64_t *d_cursors, uint32_t *d_rec, uint32_t *d_sizes, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  int rc = check_table(ctx, t);
+  if (rc) return rc;
+  if (n == 0) return MIRGE_OK;
+  if (!d_ids || !d_counts || !d_dest || !d_words || !d_cursors || !d_rec || !d_sizes || n_parts == 0 || n_parts > MAX_PARTS)
+    MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "partition_scatter: bad argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  partition_scatter_kernel<<<(unsigned)((n + COL_THREADS - 1) / COL_THREADS), COL_THREADS, 0, stream>>>(
+      *t, d_ids, d_counts, d_dest, d_words, n, n_parts, (unsigned long long *)d_cursors, d_rec, d_sizes);
+  MIRGE_LAUNCH_CHECK(ctx, "partition_scatter_kernel");
+  return MIRGE_OK;
+}

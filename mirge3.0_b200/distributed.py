@@ -28,22 +28,26 @@ def shard_ranges(total: int, world: int):
     return out
 
 
-def exchange_records(rec: torch.Tensor, sizes: torch.Tensor, send_recs: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:
+def exchange_records(rec: torch.Tensor, sizes: torch.Tensor, send_recs: torch.Tensor, group=None,
+                     send_words: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """All-to-all of variable-size records.
 
     rec       int32 words of all records, grouped by destination rank (ascending)
     sizes     int32 [n] words of each record, same order
     send_recs int64 [world] number of records for each destination
+    send_words optional int64 [world] words for each destination (computed from sizes when absent)
     Returns (recv words, recv sizes) with records grouped by source rank.  Device-agnostic plumbing:
     NCCL on GPUs, gloo in the CPU tests."""
     world = dist.get_world_size(group)
     dev = rec.device
     send_recs = send_recs.to(torch.int64)
-    bounds = torch.zeros(world + 1, dtype=torch.int64, device=dev)
-    bounds[1:] = torch.cumsum(send_recs.to(dev), 0)
-    csum = torch.zeros(sizes.numel() + 1, dtype=torch.int64, device=dev)
-    csum[1:] = torch.cumsum(sizes.to(torch.int64), 0)
-    send_words = csum[bounds[1:]] - csum[bounds[:-1]]
+    if send_words is None:  # words per destination from the record sizes
+        bounds = torch.zeros(world + 1, dtype=torch.int64, device=dev)
+        bounds[1:] = torch.cumsum(send_recs.to(dev), 0)
+        csum = torch.zeros(sizes.numel() + 1, dtype=torch.int64, device=dev)
+        csum[1:] = torch.cumsum(sizes.to(torch.int64), 0)
+        send_words = csum[bounds[1:]] - csum[bounds[:-1]]
+    send_words = send_words.to(torch.int64).to(dev)
     meta_out = torch.stack([send_recs.to(dev), send_words]).t().contiguous()  # [world, 2]
     meta_in = torch.empty_like(meta_out)
     dist.all_to_all_single(meta_in, meta_out, group=group)
@@ -61,42 +65,47 @@ def exchange_records(rec: torch.Tensor, sizes: torch.Tensor, send_recs: torch.Te
 
 def exchange_and_merge(dev, local_table, ids: torch.Tensor, cnt: torch.Tensor, owner_table, world: int, umi=(0, 0), group=None):
     """Partition the drained (key id, count) pairs of ``local_table`` by owner, exchange, merge into
-    ``owner_table`` (GPU path; every kernel through the C ABI)."""
+    ``owner_table`` (GPU path; every kernel through the C ABI): plan (owner and record size of every pair) ->
+    totals per owner -> scatter into per-owner regions of the send buffer (cursors, no sort) -> all-to-all ->
+    merge."""
     from .device import _ptr
 
     lib = dev.lib
     n = int(ids.numel())
     dest = dev.empty(n, torch.int32)
     words = dev.empty(n, torch.int32)
-    if n:
-        dev.check(lib.mirge_partition_plan(dev.ctx, C.byref(local_table.struct), _ptr(ids), n, int(umi[0]), int(umi[1]), world,
-                                           _ptr(dest), _ptr(words), dev.stream()))
-        dev.launches += 1
-    dest, words = dest[:n], words[:n]
-    # group by destination: world <= 256, so one 8-bit radix pass (torch.sort is plumbing here; order inside a
-    # destination does not matter, the owner-side merge is order independent)
-    order = torch.sort(dest.to(torch.uint8), stable=True)[1] if world <= 256 else torch.argsort(dest.to(torch.int64), stable=True)
-    ids_s, cnt_s, words_s = ids[order].contiguous(), cnt[order].contiguous(), words[order].contiguous()
-    send_recs = torch.bincount(dest.to(torch.int64), minlength=world)[:world]
-    off64 = torch.cumsum(words_s.to(torch.int64), 0) - words_s.to(torch.int64)
-    total = int((off64[-1] + words_s[-1]).item()) if n else 0
+    totals = dev.zeros(2 * world, torch.int64)
+    with dev.timed("xchg_plan"):
+        if n:
+            dev.check(lib.mirge_partition_plan(dev.ctx, C.byref(local_table.struct), _ptr(ids), n, int(umi[0]), int(umi[1]), world,
+                                               _ptr(dest), _ptr(words), dev.stream()))
+        dev.check(lib.mirge_partition_totals(dev.ctx, _ptr(dest), _ptr(words), n, world, _ptr(totals), dev.stream()))
+        dev.launches += 2
+        tot = totals.cpu()
+    send_words, send_recs = tot[:world].clone(), tot[world:].clone()
+    total = int(send_words.sum())
     if total >= (1 << 31):
         raise RuntimeError("exchange larger than 2^31 words per rank; lower the batch size")
+    base = ((torch.cumsum(send_recs, 0) - send_recs) << 32) | (torch.cumsum(send_words, 0) - send_words)
     rec = dev.empty(total, torch.int32)
-    if n:
-        rec_off = off64.to(torch.int32)
-        dev.check(lib.mirge_partition_pack(dev.ctx, C.byref(local_table.struct), _ptr(ids_s), _ptr(cnt_s), n, _ptr(rec_off),
-                                           _ptr(rec), dev.stream()))
-        dev.launches += 1
-    r_rec, r_sizes = exchange_records(rec[:total], words_s, send_recs, group)
+    sizes = dev.empty(n, torch.int32)
+    with dev.timed("xchg_pack"):
+        cursors = base.to(dev.tdev)
+        if n:
+            dev.check(lib.mirge_partition_scatter(dev.ctx, C.byref(local_table.struct), _ptr(ids), _ptr(cnt), _ptr(dest), _ptr(words), n,
+                                                  world, _ptr(cursors), _ptr(rec), _ptr(sizes), dev.stream()))
+            dev.launches += 1
+    with dev.timed("xchg_a2a"):
+        r_rec, r_sizes = exchange_records(rec[:total], sizes[:n], send_recs, group, send_words=send_words)
     m = int(r_sizes.numel())
     if m == 0:
         return 0
-    r_off = (torch.cumsum(r_sizes.to(torch.int64), 0) - r_sizes.to(torch.int64)).to(torch.int32)
-    owner_table.check()
-    owner_table.reserve(m, int(r_rec.numel()))
-    deferred = dev.empty(m, torch.int32)
-    dev.check(lib.mirge_collapse_merge(dev.ctx, C.byref(owner_table.struct), _ptr(r_rec), _ptr(r_off), m, _ptr(deferred), dev.stream()))
-    dev.launches += 3
-    owner_table.check()
+    with dev.timed("xchg_merge"):
+        r_off = (torch.cumsum(r_sizes.to(torch.int64), 0) - r_sizes.to(torch.int64)).to(torch.int32)
+        owner_table.check()
+        owner_table.reserve(m, int(r_rec.numel()))
+        deferred = dev.empty(m, torch.int32)
+        dev.check(lib.mirge_collapse_merge(dev.ctx, C.byref(owner_table.struct), _ptr(r_rec), _ptr(r_off), m, _ptr(deferred), dev.stream()))
+        dev.launches += 3
+        owner_table.check()
     return m
