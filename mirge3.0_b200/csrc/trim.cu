@@ -731,8 +731,14 @@ __device__ __forceinline__ uint32_t key_byte(const uint8_t *seq, int start, int 
   return p < l1 ? seq[start + p] : seq[us + p - l1];
 }
 
-#define PACK_WORDS 8             // reads up to 128 bases keep their 2-bit text in shared memory
-#define PS_ROWS (PACK_WORDS + 3)  // + zero words so that 64-bit windows may start at any base
+// Reads of up to 16 * pack_words bases keep their 2-bit text in shared memory (pack_words + 3 rows of TRIM_THREADS
+// words per CTA: + zero words so that 64-bit windows may start at any base).  The host picks 8 rows for batches of
+// short reads (seven CTAs per SM fit) and MAX_PACK_WORDS for longer ones; longer reads take the whole-pipeline pass.
+#define MAX_PACK_WORDS 10
+#define PS_ROWS_OF(pw) ((pw) + 3)
+__device__ int g_pack_words = 8;  // set before every launch group (cudaMemcpyToSymbolAsync on the launch stream)
+#define PACK_WORDS g_pack_words
+#define PS_ROWS PS_ROWS_OF(g_pack_words)
 
 // ---- split pipeline ----------------------------------------------------------------------------------------
 // When every adapter qualifies for the bit-parallel search, the work of a read is cut at the first adapter
@@ -1303,11 +1309,11 @@ trim_dp_kernel(const DpEntry *__restrict__ entries, const uint32_t *__restrict__
                        ctrl, nullptr, ps_mine);
 }
 
-// scratch layout of mirge_trim: [second-pass list u32[n]][stage-3 list u32[n]][DpEntry[n]][packed text u32[PACK_WORDS][n]]
+// scratch layout of mirge_trim: [second-pass list u32[n]][stage-3 list u32[n]][DpEntry[n]][packed text u32[MAX_PACK_WORDS][n]]
 static uint64_t align16(uint64_t x) { return (x + 15) & ~15ull; }
 extern "C" uint64_t mirge_trim_scratch_bytes(uint64_t n_records) {
   const uint64_t n = n_records ? n_records : 1;
-  return 2 * align16(4 * n) + align16(sizeof(DpEntry) * n) + align16(4ull * PACK_WORDS * n) + 64;
+  return 2 * align16(4 * n) + align16(sizeof(DpEntry) * n) + align16(4ull * MAX_PACK_WORDS * n) + 64;
 }
 
 extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, const uint32_t *d_line_start, uint64_t n_records,
@@ -1351,7 +1357,10 @@ extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbyte
     so.entries = (DpEntry *)(sc + 2 * align16(4 * n_records));
     so.pk = (uint32_t *)(sc + 2 * align16(4 * n_records) + align16(sizeof(DpEntry) * n_records));
     so.cap = n_records;
-    const size_t extra = (size_t)ctx->params.n_adapters * 1024 + (size_t)PS_ROWS * TRIM_THREADS * 4;
+    // packed-read rows: 8 words cover reads of up to 128 bases (record = header + 2 x read + 6 bytes)
+    const int pack_words = avg <= 2 * 112 + 40 ? 8 : MAX_PACK_WORDS;
+    MIRGE_CUDA(ctx, cudaMemcpyToSymbolAsync(g_pack_words, &pack_words, sizeof(int), 0, cudaMemcpyHostToDevice, stream));
+    const size_t extra = (size_t)ctx->params.n_adapters * 1024 + (size_t)PS_ROWS_OF(pack_words) * TRIM_THREADS * 4;
     if (split) {
       // stage 1: every read up to the adapter modifier; exact adapter occurrences are settled here
       MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

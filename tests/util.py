@@ -88,6 +88,8 @@ CONFIGS = {
     "wild": P.TrimConfig(adapters=[("back", "TGGAATTCNNGGGTGCCAAGGRACTCCAG")], error_rate=0.2, overlap=5),
     "noq_m1": P.TrimConfig(adapters=[("back", ILL)], quality_cutoff=None, minimum_length=1, times=2),
     "long_adapter": P.TrimConfig(adapters=[("back", LONG_AD)]),
+    "reads150": P.TrimConfig(adapters=[("back", ILL)], nextseq_trim=20, quality_cutoff="20", trim_n=True, cut=[1]),
+    "reads200": P.TrimConfig(adapters=[("back", ILL)], quality_cutoff="20"),
 }
 
 # keyword arguments for random_fastq that exercise each configuration
@@ -99,6 +101,8 @@ CONFIG_DATA = {
     "wild": dict(adapter=ILL),
     "long_adapter": dict(adapter=LONG_AD, L=90),
     "noq_m1": dict(varlen=True),
+    "reads150": dict(L=150),  # still inside the packed-read fast path (PACK_WORDS * 16 = 160 bases)
+    "reads200": dict(L=200),  # beyond it: whole-pipeline kernel per read
 }
 
 
