@@ -240,6 +240,8 @@ def run_b200(args):
         return tab
 
     def step_resident():
+        # (annotating every batch's new keys on a side stream while the next batch is trimmed was measured: no
+        # gain for the resident pass -- the kernels do not share SMs usefully -- so the pass stays sequential)
         table.reset()
         n = eng.digest_device(fq, table, batch_bytes)
         finish(table)

@@ -358,8 +358,9 @@ class DigestEngine:
         d.launches += 3
         table.check()
 
-    def digest_device(self, buf: torch.Tensor, table: CollapseTable, batch_bytes: int = 256 << 20) -> int:
-        """Whole sample resident on the device: returns the number of records parsed."""
+    def digest_device(self, buf: torch.Tensor, table: CollapseTable, batch_bytes: int = 256 << 20, on_piece=None) -> int:
+        """Whole sample resident on the device: returns the number of records parsed.  ``on_piece(table)`` runs
+        after every collapsed batch (streamed annotation of the keys it created)."""
         total = int(buf.numel())
         pos = 0
         n_records = 0
@@ -372,6 +373,8 @@ class DigestEngine:
                 if end - pos >= batch_bytes and batch_bytes >= (1 << 20):
                     raise FastqFormatError("FASTQ record does not fit into a batch")
             self.collapse_batch(table, br)
+            if on_piece is not None:
+                on_piece(table)
             n_records += br.n_records
             if br.consumed == 0 and not final:
                 raise FastqFormatError("no complete FASTQ record in batch")

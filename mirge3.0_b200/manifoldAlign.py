@@ -75,12 +75,16 @@ class KeySet:
         return cls(dev, arena, key_off, n)
 
 
-def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = False, fused: bool = True, ordered: bool = False):
+def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = False, fused: bool = True, ordered: bool = False,
+                  out=None):
     """Run rounds 0..8 (0..9 with spike-ins) in miRge's order (manifoldAlign.py:86-135).
     Returns device tensors (annot_round uint8[n] with 0xFF = unannotated, hit int64[n])."""
     n = keys.n
-    annot = torch.full((max(n, 1),), 0xFF, dtype=torch.uint8, device=dev.tdev)
-    hit = torch.full((max(n, 1),), -1, dtype=torch.int64, device=dev.tdev)
+    if out is not None:  # caller-provided result arrays (initialised to 0xFF / -1 by the caller)
+        annot, hit = out
+    else:
+        annot = torch.full((max(n, 1),), 0xFF, dtype=torch.uint8, device=dev.tdev)
+        hit = torch.full((max(n, 1),), -1, dtype=torch.int64, device=dev.tdev)
     if n == 0:
         return annot[:0], hit[:0]
     pols = round_policies()
@@ -105,23 +109,26 @@ def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = 
 
 
 class StreamedAnnotator:
-    """``HostStreamer.run(on_piece=...)`` hook for single-GPU runs: after every collapsed piece the keys that
-    piece created are annotated (a key's annotation depends on nothing but its text) and the new arena
-    words, key offsets, annotation rounds and hit words are copied to pinned host buffers on a separate
-    stream, so the D2H of the result table overlaps the H2D of the following pieces.  Only the per-sample
-    counts are left for the end of the sample."""
+    """Per-piece hook (``HostStreamer.run(on_piece=...)`` / ``DigestEngine.digest_device(on_piece=...)``) for
+    single-GPU runs: after every collapsed piece the keys that piece created are annotated -- a key's annotation
+    depends on nothing but its text -- on a side stream, so the (latency-bound) annotation kernel shares the SMs
+    with the (issue-bound) trim kernels of the next piece.  With ``to_host`` the new arena words, key offsets,
+    annotation rounds and hit words are also copied to pinned host buffers on a third stream, so the D2H of the
+    result table overlaps the H2D of the following pieces; only the per-sample counts are left for the end."""
 
-    def __init__(self, dev: Device, libs: LibrarySet, spike_in: bool = False):
-        self.dev, self.libs, self.spike = dev, libs, spike_in
+    def __init__(self, dev: Device, libs: LibrarySet, spike_in: bool = False, to_host: bool = True):
+        self.dev, self.libs, self.spike, self.copy_out = dev, libs, spike_in, to_host
+        self.ann = torch.cuda.Stream(device=dev.tdev)
         self.d2h = torch.cuda.Stream(device=dev.tdev)
         self.host: Dict[str, torch.Tensor] = {}
+        self.annot_d: Optional[torch.Tensor] = None  # annotation round / hit word of every key id, on the device
+        self.hit_d: Optional[torch.Tensor] = None
         self.reset()
 
     def reset(self):
         self.n_done = 0
         self.w_done = 0
         self.d2h_bytes = 0
-        self.n_annotated = None
 
     def _host(self, name: str, dtype, need: int, used: int) -> torch.Tensor:
         buf = self.host.get(name)
@@ -143,22 +150,55 @@ class StreamedAnnotator:
         dst[at : at + n].copy_(src, non_blocking=True)
         self.d2h_bytes += n * src.element_size()
 
+    def _device_results(self, need: int):
+        """annot_d / hit_d with room for ``need`` keys (grown on the annotation stream, contents kept)."""
+        if self.annot_d is None or self.annot_d.numel() < need:
+            cap = max(int(need * 1.5), 1 << 20)
+            with torch.cuda.stream(self.ann):
+                a = torch.empty(cap, dtype=torch.uint8, device=self.dev.tdev)
+                h = torch.empty(cap, dtype=torch.int64, device=self.dev.tdev)
+                if self.annot_d is not None and self.n_done:
+                    a[: self.n_done].copy_(self.annot_d[: self.n_done])
+                    h[: self.n_done].copy_(self.hit_d[: self.n_done])
+            self.annot_d, self.hit_d = a, h
+
     def __call__(self, table: CollapseTable):
         n0, w0, n1, w1 = self.n_done, self.w_done, table.n_keys, table.arena_used
         if n1 <= n0:
             return
         dev = self.dev
-        ks = KeySet(dev, table.arena, table.key_ref[n0:n1], n1 - n0)
-        annot, hit = annotate_keys(dev, self.libs, ks, self.spike)
+        self._device_results(n1)
         ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(dev.tdev))
-        with torch.cuda.stream(self.d2h):
-            self.d2h.wait_event(ev)
-            self.to_host("arena", table.arena[w0:w1], w0, w0)
-            self.to_host("key_ref", table.key_ref[n0:n1], n0, n0)
-            self.to_host("annot", annot, n0, n0)
-            self.to_host("hit", hit, n0, n0)
+        ev.record(torch.cuda.current_stream(dev.tdev))  # the piece's keys are in the table
+        with torch.cuda.stream(self.ann):
+            self.ann.wait_event(ev)
+            # the table may re-allocate these while the side stream still reads them
+            table.arena.record_stream(self.ann)
+            table.key_ref.record_stream(self.ann)
+            annot, hit = self.annot_d[n0:n1], self.hit_d[n0:n1]
+            annot.fill_(0xFF)
+            hit.fill_(-1)
+            ks = KeySet(dev, table.arena, table.key_ref[n0:n1], n1 - n0)
+            annotate_keys(dev, self.libs, ks, self.spike, out=(annot, hit))
+            done = torch.cuda.Event()
+            done.record(self.ann)
+        if self.copy_out:
+            with torch.cuda.stream(self.d2h):
+                self.d2h.wait_event(done)
+                self.to_host("arena", table.arena[w0:w1], w0, w0)
+                self.to_host("key_ref", table.key_ref[n0:n1], n0, n0)
+                self.to_host("annot", annot, n0, n0)
+                self.to_host("hit", hit, n0, n0)
         self.n_done, self.w_done = n1, w1
+
+    def results(self):
+        """(annot uint8[n], hit int64[n]) on the device, valid on the current stream."""
+        torch.cuda.current_stream(self.dev.tdev).wait_stream(self.ann)
+        n = self.n_done
+        if self.annot_d is None:
+            e = torch.empty(0, dtype=torch.uint8, device=self.dev.tdev)
+            return e, torch.empty(0, dtype=torch.int64, device=self.dev.tdev)
+        return self.annot_d[:n], self.hit_d[:n]
 
     def finish(self, table: CollapseTable):
         """End of the sample: per-sample counts to the host; returns when every byte has arrived."""
@@ -170,6 +210,7 @@ class StreamedAnnotator:
             self.d2h.wait_event(ev)
             self.to_host("ids", ids, 0, 0)
             self.to_host("cnt", cnt, 0, 0)
+        self.ann.synchronize()
         self.d2h.synchronize()
         return int(ids.numel())
 

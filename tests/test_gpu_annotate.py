@@ -257,11 +257,15 @@ def test_streamed_annotation_matches_whole_table(dev):
     assert np.array_equal(sa.host["key_ref"][:nk].numpy(), table.key_ref[:nk].cpu().numpy())
     # arena words referenced by keys arrived intact (dead space of duplicate emissions is copied too)
     assert np.array_equal(sa.host["arena"][:nw].numpy(), table.arena[:nw].cpu().numpy())
-    # counts: same multiset as a resident pass
+    # counts: same multiset as a resident pass; the device-only variant (digest_device hook) gives the same arrays
     t2 = D.CollapseTable(dev, min_keys=1 << 10)
-    eng.digest_device(fq, t2)
+    sb = MA.StreamedAnnotator(dev, lset, True, to_host=False)
+    eng.digest_device(fq, t2, 250_000, on_piece=sb)
     ids2, cnt2 = t2.drain()
     assert sorted(sa.host["cnt"][:n_pairs].tolist()) == sorted(cnt2.cpu().tolist())
+    a2, h2 = sb.results()
+    ann2, hit2 = MA.annotate_keys(dev, lset, MA.KeySet.from_table(t2), True)
+    assert torch.equal(a2, ann2) and torch.equal(h2, hit2) and not sb.host
 
 
 def test_libraries_load_from_bowtie_index_files(dev, tmp_path):
