@@ -195,7 +195,8 @@ int mirge_line_index(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, co
  *   d_key_off[e]    = word offset of the packed key in d_keys, or 0xFFFFFFFF when the slot is not
  *                     counted (length filter, digest.py:348,362,368).
  * d_trim_ctrl (8 x u64, zeroed by the caller): [0] key words used [1] emitted keys [2] error flags
- * [3] first malformed record, [5] reads left to the whole-pipeline second pass, [6] reads whose adapter search
+ * [3] first malformed record, [4] key words of all emitted keys (a slot whose text repeats the previous slot's
+ * shares that slot's key: same d_key_off, no space of its own), [5] reads left to the whole-pipeline second pass, [6] reads whose adapter search
  * ran the bit-vector DP, [7] of those, the ones that needed cost columns.
  * d_scratch: mirge_trim_scratch_bytes(n_records) bytes, 16-byte aligned.  With 3' adapters of <= 32 nt the work
  * is split at the adapter modifier: stage 1 handles every read up to there (an exact occurrence of the whole

@@ -139,13 +139,19 @@ __device__ __forceinline__ void defer_item(unsigned long long *counter, uint32_t
 // mode 0: items are emission slots (keys/key_off, add = 1)
 // mode 1: items are exchange records [count][key...] at rec_off[i]
 // mode 2: emission slots whose keys the trim kernel wrote straight into the table's arena (keys == arena)
-__device__ __forceinline__ void item_key(int mode, const uint32_t *keys, const uint32_t *off, uint64_t i,
+// In modes 0 and 2 consecutive slots that carry the same key offset (HEAD counting emitted the same text after
+// consecutive modifiers) are one insert: the first slot of the run adds the run length, the others do nothing.
+__device__ __forceinline__ void item_key(int mode, const uint32_t *keys, const uint32_t *off, uint64_t i, uint64_t n,
                                          const uint32_t *&key, uint32_t &add, uint32_t &in_arena) {
   const uint32_t o = off[i];
   in_arena = NOT_IN_ARENA;
   if (o == 0xFFFFFFFFu) { key = nullptr; add = 0; return; }
-  if (mode == 1) { key = keys + o + 1; add = keys[o]; }
-  else { key = keys + o; add = 1; if (mode == 2) in_arena = o; }
+  if (mode == 1) { key = keys + o + 1; add = keys[o]; return; }
+  if (i > 0 && off[i - 1] == o) { key = nullptr; add = 0; return; }  // counted by the first slot of the run
+  add = 1;
+  for (uint64_t k = i + 1; k < n && k < i + MIRGE_MAX_MODS && off[k] == o; ++k) ++add;
+  key = keys + o;
+  if (mode == 2) in_arena = o;
 }
 
 __global__ void __launch_bounds__(COL_THREADS)
@@ -154,7 +160,7 @@ collapse_insert_kernel(mirge_table t, const uint32_t *__restrict__ keys, const u
   const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
   if (i >= n) return;
   const uint32_t *key; uint32_t add, in_arena;
-  item_key(mode, keys, off, i, key, add, in_arena);
+  item_key(mode, keys, off, i, n, key, add, in_arena);
   if (!key || add == 0) return;
   const uint32_t nw = key_words(key[0]);
   const uint64_t h = hash_key(key, nw);
@@ -164,7 +170,7 @@ collapse_insert_kernel(mirge_table t, const uint32_t *__restrict__ keys, const u
 
 // drains the deferred list: one lane per warp, so a waiter never shares a warp with its claimant
 __global__ void __launch_bounds__(COL_THREADS)
-collapse_retry_kernel(mirge_table t, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ off, int mode,
+collapse_retry_kernel(mirge_table t, const uint32_t *__restrict__ keys, const uint32_t *__restrict__ off, uint64_t n, int mode,
                       const uint32_t *__restrict__ deferred) {
   if (threadIdx.x & 31) return;
   const unsigned long long nd = ((unsigned long long *)t.d_ctrl)[3];
@@ -173,7 +179,7 @@ collapse_retry_kernel(mirge_table t, const uint32_t *__restrict__ keys, const ui
   for (uint64_t j = warp; j < nd; j += nwarps) {
     const uint64_t i = deferred[j];
     const uint32_t *key; uint32_t add, in_arena;
-    item_key(mode, keys, off, i, key, add, in_arena);
+    item_key(mode, keys, off, i, n, key, add, in_arena);
     if (!key) continue;
     const uint32_t nw = key_words(key[0]);
     table_insert(t, key, nw, add, hash_key(key, nw), true, in_arena);
@@ -211,7 +217,7 @@ static int run_insert(mirge_ctx *ctx, const mirge_table *t, const uint32_t *keys
   const unsigned grid = (unsigned)((n + COL_THREADS - 1) / COL_THREADS);
   collapse_insert_kernel<<<grid, COL_THREADS, 0, stream>>>(*t, keys, off, n, mode, d_deferred);
   MIRGE_LAUNCH_CHECK(ctx, "collapse_insert_kernel");
-  collapse_retry_kernel<<<ctx->sm_count, COL_THREADS, 0, stream>>>(*t, keys, off, mode, d_deferred);
+  collapse_retry_kernel<<<ctx->sm_count, COL_THREADS, 0, stream>>>(*t, keys, off, n, mode, d_deferred);
   MIRGE_LAUNCH_CHECK(ctx, "collapse_retry_kernel");
   clear_deferred_kernel<<<1, 1, 0, stream>>>((unsigned long long *)t->d_ctrl);
   MIRGE_LAUNCH_CHECK(ctx, "clear_deferred_kernel");

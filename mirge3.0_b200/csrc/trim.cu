@@ -810,12 +810,22 @@ __device__ __forceinline__ void emit_record(const bool valid, const uint64_t r, 
                                             uint64_t keys_cap, unsigned long long *__restrict__ ctrl, uint32_t *__restrict__ d_slow,
                                             const uint32_t *ps_mine) {
   const int lane = threadIdx.x & 31;
-  uint32_t my_words = 0, my_kept = 0;
+  uint32_t my_words = 0, my_kept = 0, my_alg = 0, same_as_prev = 0;
   if (valid) {
-    // size of every kept key: header + payload + exceptions
+    // size of every kept key: header + payload + exceptions.  A slot whose text is the text of the slot before
+    // it (a modifier that changed nothing: HEAD counting emits the read again) gets no space of its own -- its
+    // key offset repeats the previous one and the collapse counts the run in one insert.
 #pragma unroll 1
     for (int s = slot_lo; s < slot_hi; ++s) {
       if (!w_words[s]) continue;
+      ++my_kept;
+      if (s > slot_lo && w_words[s - 1] && w_start[s] == w_start[s - 1] && w_stop[s] == w_stop[s - 1] && w_us[s] == w_us[s - 1] &&
+          w_ue[s] == w_ue[s - 1]) {
+        w_words[s] = w_words[s - 1];
+        my_alg += w_words[s];
+        same_as_prev |= 1u << s;
+        continue;
+      }
       if (FAST && fast_emit) {
         w_words[s] = 1u + ((uint32_t)(w_stop[s] - w_start[s] + 15) >> 4);
       } else {
@@ -825,7 +835,7 @@ __device__ __forceinline__ void emit_record(const bool valid, const uint64_t r, 
         w_words[s] = 1u + ((uint32_t)(len + 15) >> 4) + nexc;
       }
       my_words += w_words[s];
-      ++my_kept;
+      my_alg += w_words[s];
     }
   }
   uint32_t inc = my_words;
@@ -836,10 +846,12 @@ __device__ __forceinline__ void emit_record(const bool valid, const uint64_t r, 
   }
   const uint32_t warp_total = __shfl_sync(0xffffffffu, inc, 31);
   const uint32_t kept_warp = __reduce_add_sync(0xffffffffu, my_kept);
+  const uint32_t alg_warp = __reduce_add_sync(0xffffffffu, my_alg);
   unsigned long long warp_base = 0;
   if (lane == 0) {
     if (warp_total) warp_base = atomicAdd(ctrl + 0, (unsigned long long)warp_total);
     if (kept_warp) atomicAdd(ctrl + 1, (unsigned long long)kept_warp);
+    if (alg_warp) atomicAdd(ctrl + 4, (unsigned long long)alg_warp);  // key words of all emitted keys (repeats included)
   }
   warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
   const bool overflow = warp_base + warp_total > keys_cap || warp_base + warp_total > 0xFFFFFFF0ull;
@@ -861,6 +873,10 @@ __device__ __forceinline__ void emit_record(const bool valid, const uint64_t r, 
     win[e] = make_ushort4((unsigned short)w_start[s], (unsigned short)w_stop[s], (unsigned short)w_us[s], (unsigned short)w_ue[s]);
     if (!w_words[s] || overflow) {
       key_off[e] = 0xFFFFFFFFu;
+      continue;
+    }
+    if ((same_as_prev >> s) & 1u) {  // same text as the previous slot: same key
+      key_off[e] = off - w_words[s];
       continue;
     }
     key_off[e] = off;

@@ -231,6 +231,7 @@ class BatchResult:
     key_off: Optional[torch.Tensor] = None
     keys: Optional[torch.Tensor] = None
     in_place: bool = False  # keys were written straight into the collapse table's arena
+    arena_words: int = 0  # words the batch's keys occupy (repeated slots share a key); key_words counts every emitted key
 
 
 class DigestEngine:
@@ -327,10 +328,10 @@ class DigestEngine:
         if table is not None:
             table.arena_used = int(c[0])
             table.ctrl[0] = table.arena_used  # the table's own counter of arena words in use
-            return BatchResult(n, used, int(c[1]), int(c[0]) - base_words, line_start if keep else None,
-                               win if keep else None, key_off, None, True)
-        return BatchResult(n, used, int(c[1]), int(c[0]), line_start if keep else None, win if keep else None,
-                           key_off, keys)
+            return BatchResult(n, used, int(c[1]), int(c[4]), line_start if keep else None,
+                               win if keep else None, key_off, None, True, int(c[0]) - base_words)
+        return BatchResult(n, used, int(c[1]), int(c[4]), line_start if keep else None, win if keep else None,
+                           key_off, keys, False, int(c[0]))
 
     def collapse_batch(self, table: CollapseTable, br: BatchResult):
         """completeDict[key] += 1 for every key the trim kernel emitted."""
@@ -351,7 +352,7 @@ class DigestEngine:
                                                           _ptr(deferred), d.stream()))
         else:
             table.check()
-            table.reserve(br.n_emitted, br.key_words)
+            table.reserve(br.n_emitted, br.arena_words)
             with d.timed("collapse"):
                 d.check(lib.mirge_collapse_insert(d.ctx, C.byref(table.struct), _ptr(br.keys), _ptr(br.key_off), n_slots,
                                                   _ptr(deferred), d.stream()))
