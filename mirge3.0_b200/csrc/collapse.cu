@@ -89,7 +89,10 @@ __device__ __forceinline__ int table_insert(const mirge_table &t, const uint32_t
         t.d_key_ref[id] = (uint32_t)aoff;
         s->id = (uint32_t)id;
         atomicAdd(&s->count, add);
-        __threadfence();  // release: key text, id and count are visible before ref
+        // release: a key text this thread just copied must be visible before ref.  A key that already sits in
+        // the arena was written by an earlier kernel, and waiters read nothing else the owner wrote (they only
+        // add to count, atomically; id and key_ref are read by later kernels), so no fence is needed then.
+        if (in_arena == NOT_IN_ARENA) __threadfence();
         atomicExch(&s->ref, (uint32_t)aoff + 1u);
         return INS_OK;
       }
