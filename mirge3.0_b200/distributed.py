@@ -109,3 +109,142 @@ def exchange_and_merge(dev, local_table, ids: torch.Tensor, cnt: torch.Tensor, o
         dev.launches += 3
         owner_table.check()
     return m
+
+
+# ---------------------------------------------------------------------------------------------------
+# The two entry points for one process per GPU (torchrun): same arguments and, on rank 0, the same return
+# values as digest.baking / manifoldAlign.bwtAlign.  Samples are dealt round-robin to the ranks (a sample's
+# reads -- and with UMIs its first-level table -- stay on one GPU), every sample's unique sequences are
+# hash-partitioned to their owners with one all-to-all, owners keep the per-sample counts of their slice and
+# annotate it against replicated libraries; rank 0 gathers (sequence, counts, annotation) for the DataFrame
+# (SURVEY.md section 8e).
+# ---------------------------------------------------------------------------------------------------
+
+_SHARD = {}
+
+
+def baking_sharded(args, inFileArray, inFileBaseArray, workDir, device=None, count_mode=None, batch_bytes=256 << 20, group=None):
+    """Call on every rank.  Returns (complete_set, sampleReadCounts, trimmedReadCounts, trimmedReadCountsUnique);
+    complete_set is the DataFrame of digest.baking on rank 0 and None elsewhere."""
+    import numpy as np
+
+    from . import digest as DG
+    from . import params as P
+    from .device import CollapseTable, Device, DigestEngine
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    cfg = P.TrimConfig.from_args(args, count_mode or DG.default_count_mode())
+    dev = device or Device(torch.cuda.current_device())
+    eng = DigestEngine(dev, cfg)
+    umi = cfg.umi()
+    local = CollapseTable(dev, min_keys=1 << 20)
+    first_level = CollapseTable(dev, min_keys=1 << 20) if umi is not None else None
+    owner = CollapseTable(dev, min_keys=1 << 20)
+    streamer = DG.HostStreamer(eng, batch_bytes)
+    names = list(inFileBaseArray)
+    counts_read = np.zeros(len(names), dtype=np.int64)
+    per_sample = []  # (owner ids, counts) of this rank's slice, per sample
+    empty = torch.zeros(0, dtype=torch.int32, device=dev.tdev)
+    for s, path in enumerate(inFileArray):
+        if s % world == rank:
+            umi_csv = None
+            if umi is not None and getattr(args, "umiDedup", False):
+                import os
+
+                umi_csv = os.path.join(str(workDir), names[s] + "_umiCounts.csv")
+            with DG._open_fastq(path) as f:
+                res = DG.digest_sample(eng, f, local, first_level, bool(getattr(args, "umiDedup", False)), batch_bytes, umi_csv, streamer)
+            counts_read[s] = res.count
+            ids = torch.from_numpy(res.ids.astype(np.int32)).to(dev.tdev)
+            cnt = torch.from_numpy(res.counts.astype(np.int32)).to(dev.tdev)
+        else:
+            ids, cnt = empty, empty
+        exchange_and_merge(dev, local, ids, cnt, owner, world, group=group)  # collective
+        o_ids, o_cnt = owner.drain()
+        per_sample.append((o_ids.cpu().numpy().astype(np.int64), o_cnt.cpu().numpy().astype(np.int64)))
+        local.reset()
+    # counters (digest.py:212-217): records parsed by the digesting rank, emitted counts and unique sequences
+    # summed over the owners
+    tot = torch.zeros((3, len(names)), dtype=torch.int64, device=dev.tdev)
+    tot[0] = torch.from_numpy(counts_read).to(dev.tdev)
+    tot[1] = torch.tensor([int(c.sum()) for _, c in per_sample], dtype=torch.int64, device=dev.tdev)
+    tot[2] = torch.tensor([int(i.size) for i, _ in per_sample], dtype=torch.int64, device=dev.tdev)
+    dist.all_reduce(tot, group=group)
+    tot_h = tot.cpu().numpy()
+    src = {n: int(tot_h[0, j]) for j, n in enumerate(names)}
+    trc = {n: int(tot_h[1, j]) for j, n in enumerate(names)}
+    tru = {n: int(tot_h[2, j]) for j, n in enumerate(names)}
+    keys = owner.export_keys()
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object((keys, per_sample), gathered, dst=0, group=group)
+    _SHARD.clear()
+    _SHARD.update(dev=dev, owner=owner, n_own=int(keys.shape[0]))
+    if rank != 0:
+        return None, src, trc, tru
+    import pandas as pd
+
+    sizes = [int(g[0].shape[0]) for g in gathered]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    width = max([g[0].dtype.itemsize for g in gathered] + [1])
+    all_keys = np.concatenate([g[0].astype("S%d" % width) for g in gathered]) if sum(sizes) else np.zeros(0, dtype="S1")
+    mat = np.zeros((all_keys.shape[0], len(names)), dtype=np.int64)
+    for r, (_, ps) in enumerate(gathered):
+        for j, (i_, c_) in enumerate(ps):
+            mat[offs[r] + i_, j] = c_
+    seen = mat.any(axis=1) if mat.size else np.zeros(0, dtype=bool)
+    order = np.argsort(all_keys, kind="stable")
+    order = order[seen[order]]
+    index = pd.Index([k.decode("latin-1") for k in all_keys[order].tolist()], name="Sequence", dtype=object)
+    df = pd.DataFrame(mat[order], index=index, columns=names)
+    df = df.assign(**dict.fromkeys(DG.INITIAL_FLAGS, ""))
+    df = df.assign(annotFlag=0)
+    df = df.reindex(columns=["annotFlag"] + DG.INITIAL_FLAGS + names)
+    df = df.astype({"annotFlag": int})
+    _SHARD.update(order=order, offs=offs, n_all=int(all_keys.shape[0]))
+    return df, src, trc, tru
+
+
+def bwtAlign_sharded(args, pdDataFrame, workDir, ref_db, libraries=None, group=None):
+    """Call on every rank after baking_sharded (pdDataFrame: its result on rank 0, None elsewhere).  Every rank
+    annotates the sequences it owns; rank 0 returns the DataFrame manifoldAlign.bwtAlign would return."""
+    import numpy as np
+
+    from . import manifoldAlign as MA
+    from .libraries import ROUND_LIBS
+
+    if getattr(args, "bam_out", False) or getattr(args, "tRNA_frag", False):
+        raise RuntimeError("-bam / -trf are written by the single-process bwtAlign only")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    dev, owner = _SHARD["dev"], _SHARD["owner"]
+    libs = libraries or MA.load_libraries(args, ref_db, dev)
+    spike = bool(getattr(args, "spikeIn", False))
+    annot_d, hit_d = MA.annotate_keys(dev, libs, MA.KeySet.from_table(owner), spike)
+    annot = annot_d.cpu().numpy()
+    _, _mm, ref, _off = MA.decode_hits(annot, hit_d.cpu().numpy())
+    names = np.full(annot.shape[0], "", dtype=object)
+    for rnd in range(10 if spike else 9):
+        rows = np.nonzero(annot == rnd)[0]
+        if rows.size:
+            names[rows] = np.asarray(libs[ROUND_LIBS[rnd]].names, dtype=object)[ref[rows]]
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object((annot, names), gathered, dst=0, group=group)
+    if rank != 0:
+        return None
+    order = _SHARD["order"]
+    annot_all = np.concatenate([g[0] for g in gathered]) if _SHARD["n_all"] else np.zeros(0, dtype=np.uint8)
+    names_all = np.concatenate([g[1] for g in gathered]) if _SHARD["n_all"] else np.zeros(0, dtype=object)
+    a, nm = annot_all[order], names_all[order]
+    colnames = list(pdDataFrame.columns)
+    for rnd in range(10 if spike else 9):
+        rows = np.nonzero(a == rnd)[0]
+        if rows.size == 0:
+            continue
+        col = pdDataFrame[colnames[1 + rnd]].to_numpy(dtype=object, copy=True)
+        col[rows] = nm[rows]
+        pdDataFrame[colnames[1 + rnd]] = col
+    flag = pdDataFrame[colnames[0]].to_numpy(copy=True)
+    flag[a != 0xFF] = 1
+    pdDataFrame[colnames[0]] = flag
+    if not spike:
+        pdDataFrame = pdDataFrame.drop(columns=["spike-in"])
+    return pdDataFrame.fillna("")

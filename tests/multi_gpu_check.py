@@ -20,10 +20,66 @@ from mirge_b200 import manifoldAlign as MA  # noqa: E402
 from mirge_b200 import synth  # noqa: E402
 
 
+def check_entry_points(rank, world, dev, umi):
+    """baking_sharded + bwtAlign_sharded (one process per GPU) against the single-process entry points."""
+    import gzip
+    import tempfile
+
+    from mirge_b200 import digest as DG
+    from tests.test_gpu_annotate import make_libs, write_lib_dir
+    from tests.util import ILL, make_args, random_fastq
+
+    box = [tempfile.mkdtemp(prefix="mirge_mg_") if rank == 0 else None]
+    dist.broadcast_object_list(box, 0)
+    tmp = box[0]
+    names = ["s%d" % i for i in range(5)]
+    files = [os.path.join(tmp, n + (".fastq.gz" if i == 1 else ".fastq")) for i, n in enumerate(names)]
+    if rank == 0:
+        rng = np.random.default_rng(3)
+        libs = make_libs(rng, scale=0.4)
+        write_lib_dir(os.path.join(tmp, "lib"), libs)
+        mir = libs["mirna"][1]
+        for i, f in enumerate(files):
+            r2 = np.random.default_rng(50 + i)
+            recs = []
+            for k in range(2500 + 300 * i):
+                ins = mir[int(r2.zipf(1.3)) % len(mir)]
+                pre = "".join(r2.choice(list("ACGT"), 4)) if umi else ""
+                suf = "".join(r2.choice(list("ACGT"), 4)) if umi else ""
+                s_ = (pre + ins + suf + ILL + "ACGTACGTACGTAC")[:60]
+                recs.append("@r%d.%d\n%s\n+\n%s\n" % (i, k, s_, "I" * len(s_)))
+            data = "".join(recs).encode()
+            if f.endswith(".gz"):
+                with gzip.open(f, "wb") as fh:
+                    fh.write(data)
+            else:
+                open(f, "wb").write(data)
+    dist.barrier()
+    args = make_args(libraries_path=os.path.join(tmp, "lib"), spikeIn=True, uniq_mol_ids="4,4" if umi else None, umiDedup=bool(umi))
+    df, src, trc, tru = MD.baking_sharded(args, files, names, tmp, device=dev, batch_bytes=200_000)
+    out = MD.bwtAlign_sharded(args, df, tmp, "miRBase")
+    ok = True
+    if rank == 0:
+        df1, src1, trc1, tru1 = DG.baking(args, files, names, tmp, device=dev, batch_bytes=200_000)
+        out1 = MA.bwtAlign(args, df1, tmp, "miRBase", device=dev)
+        ok = out.equals(out1) and list(out.columns) == list(out1.columns) and (src, trc, tru) == (src1, trc1, tru1)
+        print("sharded entry points: world=%d samples=%d rows=%d annotated=%d umi=%s ok=%s"
+              % (world, len(names), len(out), int((out.annotFlag == 1).sum()), bool(umi), ok))
+        if not ok:
+            print(src, src1, trc, trc1, tru, tru1, out.shape, out1.shape)
+    return ok
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = D.Device(local)
+    if len(sys.argv) > 1 and sys.argv[1] in ("entry", "entry_umi"):
+        ok = check_entry_points(rank, world, dev, sys.argv[1] == "entry_umi")
+        flag = torch.tensor([1 if ok else 0], device=dev.tdev)
+        dist.broadcast(flag, 0)
+        dist.destroy_process_group()
+        sys.exit(0 if int(flag.item()) == 1 else 1)
     cfg_id = int(sys.argv[1]) if len(sys.argv) > 1 else 1
     n_reads = 120_000
     libs = synth.make_libraries(scale=0.05, mrna_count=100)

@@ -21,3 +21,16 @@ def test_two_gpu_exchange_matches_oracle(cfg_id):
     p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "ok=True" in p.stdout
+
+
+@pytest.mark.parametrize("mode", ["entry", "entry_umi"])
+def test_two_gpu_entry_points_match_single_process(mode):
+    """baking_sharded / bwtAlign_sharded (samples dealt to the ranks, hash-partitioned collapse, owner-side annotation,
+    gather to rank 0) give the DataFrame and counters of the single-process baking / bwtAlign."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29611", os.path.join(ROOT, "tests", "multi_gpu_check.py"), mode]
+    p = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "ok=True" in p.stdout
