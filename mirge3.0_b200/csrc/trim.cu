@@ -471,7 +471,7 @@ __device__ __forceinline__ int locate_fast(const int a, const RV read, const int
   const uint32_t *eqt = fc.s_eq + a * 256;
   const uint32_t top = 1u << (m - 1);
   const int acc_m = ad.acc[m];
-  uint32_t vp = 0xFFFFFFFFu, vn = 0u, pvp = vp, pvn = vn, eq = 0;
+  uint32_t vp = 0xFFFFFFFFu, vn = 0u, eq = 0;
   int score = m;
   bool have = false;
   int b_m = 0, b_c = 0, b_o = 0, b_idx = 0;
@@ -515,9 +515,6 @@ __device__ __forceinline__ int locate_fast(const int a, const RV read, const int
   auto cur = read.cursor();
   for (int j = 1; j <= n; ++j) {
     eq = cur.next(eqt);
-    const int score_prev = score;
-    pvp = vp;
-    pvn = vn;
     MYERS_STEP(eq, vp, vn, hp, hn)
     score += (hp & top) ? 1 : 0;
     score -= (hn & top) ? 1 : 0;
@@ -544,15 +541,15 @@ __device__ __forceinline__ int locate_fast(const int a, const RV read, const int
         stopped = true;
         break;
       }
-      // first traceback step of cell (m, j) from the two cost columns at hand
-      bool is_del = false, is_ins = false, is_match = true;
-      if (!(eq & top)) {
-        is_match = false;
-        const int dm1_prev = score_prev - (int)((pvp >> (m - 1)) & 1u) + (int)((pvn >> (m - 1)) & 1u);  // D[m-1][j-1]
-        const int dm1_cur = score - (int)((vp >> (m - 1)) & 1u) + (int)((vn >> (m - 1)) & 1u);          // D[m-1][j]
-        const int cd = dm1_prev + 1, cdel = score_prev + 1, cins = dm1_cur + 1;
-        if (!(cd <= cdel && cd <= cins)) {
-          if (cins <= cdel) is_ins = true;
+      // first traceback step of cell (m, j) from this column's step masks (see the last-column scan below):
+      // mismatch <=> vertical delta + horizontal delta one row up == 1; else insertion <=> vertical delta +1
+      bool is_del = false, is_ins = false;
+      const bool is_match = (eq & top) != 0u;
+      if (!is_match) {
+        const uint32_t hps = hp << 1, hns = hn << 1;
+        const bool mis = (((vp & ~hps & ~hns) | (~vp & ~vn & hps)) & top) != 0u;
+        if (!mis) {
+          if (vp & top) is_ins = true;
           else is_del = true;
         }
       }
