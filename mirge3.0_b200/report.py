@@ -91,7 +91,7 @@ def canonical_filter(can: np.ndarray, iso: np.ndarray, ca_thr: float) -> np.ndar
 def build_report(base_names: Sequence[str], sums: Sequence[Tuple[np.ndarray, np.ndarray, np.ndarray]], has_exact: np.ndarray,
                  mirna_names: Sequence[str], member: Dict[str, str], merged_names: Sequence[str], sampleReadCounts: Dict[str, int],
                  trimmedReadCounts: Dict[str, int], trimmedReadCountsUnique: Dict[str, int], ca_thr: float, spike_in: bool):
-    """(annotation.report DataFrame, miR.Counts DataFrame) from the per-sample sums.  ``has_exact[ref]``: the miRNA
+    """(annotation.report, miR.Counts, miR.RPM DataFrames) from the per-sample sums.  ``has_exact[ref]``: the miRNA
     has at least one exact-miRNA row in the mapped table (the rows of cann_collapse, summary.py:741)."""
     S = len(base_names)
     out_name = [member.get(n, n) for n in mirna_names]  # summary.py:750-752
@@ -132,7 +132,14 @@ def build_report(base_names: Sequence[str], sums: Sequence[Tuple[np.ndarray, np.
     for n, i in gidx.items():
         counts[pos[n]] = grouped[i]
     mir_counts = pd.DataFrame(counts, index=pd.Index(all_names, name="miRNA"), columns=list(base_names))
-    return summary, mir_counts
+    # miR.RPM.csv (summary.py:759,795,797): reads per million of the filtered miRNA reads, 4 decimals
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rpm_g = np.round(grouped / grouped.sum(axis=0) * 1000000, 4)
+    rpm = np.zeros((len(all_names), S), dtype=np.float64)
+    for n, i in gidx.items():
+        rpm[pos[n]] = rpm_g[i]
+    mir_rpm = pd.DataFrame(np.nan_to_num(rpm, nan=0.0), index=pd.Index(all_names, name="miRNA"), columns=list(base_names))
+    return summary, mir_counts, mir_rpm
 
 
 def codes_from_dataframe(pdDataFrame: pd.DataFrame, libs: LibrarySet, spike_in: bool):
@@ -156,8 +163,8 @@ def codes_from_dataframe(pdDataFrame: pd.DataFrame, libs: LibrarySet, spike_in: 
 def annotation_report(args, workDir, ref_db, base_names: Sequence[str], pdDataFrame: pd.DataFrame, sampleReadCounts, trimmedReadCounts,
                       trimmedReadCountsUnique, libraries: Optional[LibrarySet] = None, device: Optional[Device] = None,
                       write: bool = True):
-    """annotation.report.csv and miR.Counts.csv from the DataFrame ``bwtAlign`` returned (same inputs as the
-    reference's summarize(), summary.py:677).  Returns (report DataFrame, miR.Counts DataFrame)."""
+    """annotation.report.csv, miR.Counts.csv and miR.RPM.csv from the DataFrame ``bwtAlign`` returned (same inputs
+    as the reference's summarize(), summary.py:677).  Returns the three DataFrames."""
     from .manifoldAlign import get_device, load_libraries
 
     dev = device or get_device()
@@ -181,9 +188,10 @@ def annotation_report(args, workDir, ref_db, base_names: Sequence[str], pdDataFr
     has_exact[(hit[annot == 0] >> 28) & 0xFFFFFFF] = True
     mfname = str(args.organism_name) + "_merges_" + str(ref_db) + ".csv"
     member, merged = read_merges(Path(args.libraries_path) / args.organism_name / "annotation.Libs" / mfname)
-    summary, mir_counts = build_report(base_names, sums, has_exact, mir.names, member, merged, sampleReadCounts, trimmedReadCounts,
-                                       trimmedReadCountsUnique, float(getattr(args, "crThreshold", 0.1)), spike)
+    summary, mir_counts, mir_rpm = build_report(base_names, sums, has_exact, mir.names, member, merged, sampleReadCounts,
+                                                trimmedReadCounts, trimmedReadCountsUnique, float(getattr(args, "crThreshold", 0.1)), spike)
     if write:
         summary.to_csv(Path(workDir) / "annotation.report.csv")  # summary.py:1275-1279
         mir_counts.to_csv(Path(workDir) / "miR.Counts.csv")  # summary.py:796
-    return summary, mir_counts
+        mir_rpm.to_csv(Path(workDir) / "miR.RPM.csv")  # summary.py:797
+    return summary, mir_counts, mir_rpm

@@ -847,3 +847,18 @@ def sam_line(qname: str, query: str, ref_name: str, ref_seq: str, off: int, pol:
     stratum = sum(1 for p in pos if p < seed)
     return "%s\t0\t%s\t%d\t255\t%dM\t*\t0\t0\t%s\t%s\tXA:i:%d\tMD:Z:%s\tNM:i:%d" % (
         qname, ref_name, off + 1, len(query), query, "I" * len(query), stratum, md, len(pos))
+
+
+def mir_rpm_csv(mir_counts: Dict[str, Sequence[float]], samples: Sequence[str]) -> str:
+    """miR.RPM.csv (summary.py:759,795,797): counts / column sum * 1e6 rounded to 4 decimals (numpy rounding, as
+    pandas does), names without reads stay 0.0."""
+    import numpy as np
+
+    names = list(mir_counts)
+    m = np.array([list(mir_counts[n]) for n in names], dtype=np.float64).reshape(len(names), len(samples))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rpm = np.nan_to_num(np.round(m / m.sum(axis=0) * 1000000, 4), nan=0.0)
+    out = ["miRNA," + ",".join(samples)]
+    for n, row in zip(names, rpm.tolist()):
+        out.append(n + "," + ",".join(repr(float(x)) for x in row))
+    return "\n".join(out) + "\n"

@@ -31,8 +31,8 @@ def test_pipeline_reproduces_reference_files(dev, tmp_path):
     df, src, trc, tru = DG.baking(args, files, SAMPLES, str(tmp_path), device=dev, batch_bytes=150_000)
     out = MA.bwtAlign(args, df, str(tmp_path), DB, device=dev)
     RP.write_tables(out, str(tmp_path))
-    summary, mir = RP.annotation_report(args, str(tmp_path), DB, SAMPLES, out, src, trc, tru, device=dev)
-    for name in ("mapped.csv", "unmapped.csv", "annotation.report.csv", "miR.Counts.csv"):
+    summary, mir, rpm = RP.annotation_report(args, str(tmp_path), DB, SAMPLES, out, src, trc, tru, device=dev)
+    for name in ("mapped.csv", "unmapped.csv", "annotation.report.csv", "miR.Counts.csv", "miR.RPM.csv"):
         assert (tmp_path / name).read_text() == golden(name), name
     assert summary.loc["sampleA", "Total Input Reads"] == 2500
 

@@ -63,6 +63,7 @@ def test_annotation_report_matches_reference(oracle_run):
     report, mir = po.summarize_counts(annot, counts, SAMPLES, src, trc, tru, merges, libs["mirna"].names, 0.1, True)
     assert po.report_csv(report, SAMPLES, True) == golden("annotation.report.csv")
     assert po.mir_counts_csv(mir, SAMPLES) == golden("miR.Counts.csv")
+    assert po.mir_rpm_csv(mir, SAMPLES) == golden("miR.RPM.csv")
 
 
 # ---- digest-only cases: the reference's baking() (worker, parent merge, UMI levels, matrix, counters, side files)
