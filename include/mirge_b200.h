@@ -228,6 +228,11 @@ int mirge_collapse_insert_inplace(mirge_ctx *ctx, const mirge_table *t, const ui
  * offset of record i.  Used by the owner side of the hash-partitioned exchange. */
 int mirge_collapse_merge(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_rec,
                          const uint32_t *d_rec_off, uint64_t n_rec, uint32_t *d_deferred, void *stream);
+/* The same when the records were received straight into the table's arena (the all-to-all writes them at the
+ * arena's end): d_rec_off holds arena word offsets, the key of the first record of a sequence becomes the table's
+ * copy, nothing is moved.  The caller advances the arena counter (d_ctrl[0]) past the received words. */
+int mirge_collapse_merge_inplace(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_rec_off, uint64_t n_rec,
+                                 uint32_t *d_deferred, void *stream);
 /* Growth: re-insert every slot of old_t into the larger slot array of new_t (zeroed here).  Both
  * tables must reference the same key text (new_t->d_arena holds a copy of the used arena words),
  * the same d_key_ref contents and the same d_ctrl.  Key ids, refs and counts are preserved. */

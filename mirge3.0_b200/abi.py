@@ -125,6 +125,7 @@ SYMBOLS = {
     "mirge_collapse_insert": (C.c_int, [_P, C.POINTER(Table), _P, _P, _U64, _P, _P]),
     "mirge_collapse_insert_inplace": (C.c_int, [_P, C.POINTER(Table), _P, _U64, _P, _P]),
     "mirge_collapse_merge": (C.c_int, [_P, C.POINTER(Table), _P, _P, _U64, _P, _P]),
+    "mirge_collapse_merge_inplace": (C.c_int, [_P, C.POINTER(Table), _P, _U64, _P, _P]),
     "mirge_table_rehash": (C.c_int, [_P, C.POINTER(Table), C.POINTER(Table), _P]),
     "mirge_table_check_sync":(C.c_int, [_P, C.POINTER(Table), _PU64, _PU64, _P]),
     "mirge_table_drain": (C.c_int, [_P, C.POINTER(Table), _P, _P, _U64, _P, _P]),

@@ -142,6 +142,8 @@ __device__ __forceinline__ void defer_item(unsigned long long *counter, uint32_t
 // mode 0: items are emission slots (keys/key_off, add = 1)
 // mode 1: items are exchange records [count][key...] at rec_off[i]
 // mode 2: emission slots whose keys the trim kernel wrote straight into the table's arena (keys == arena)
+// mode 3: exchange records that were received straight into the table's arena (keys == arena): the key of a
+//         record becomes the table's copy where it lies, nothing is moved
 // In modes 0 and 2 consecutive slots that carry the same key offset (HEAD counting emitted the same text after
 // consecutive modifiers) are one insert: the first slot of the run adds the run length, the others do nothing.
 __device__ __forceinline__ void item_key(int mode, const uint32_t *keys, const uint32_t *off, uint64_t i, uint64_t n,
@@ -150,6 +152,7 @@ __device__ __forceinline__ void item_key(int mode, const uint32_t *keys, const u
   in_arena = NOT_IN_ARENA;
   if (o == 0xFFFFFFFFu) { key = nullptr; add = 0; return; }
   if (mode == 1) { key = keys + o + 1; add = keys[o]; return; }
+  if (mode == 3) { key = keys + o + 1; add = keys[o]; in_arena = o + 1; return; }
   if (i > 0 && off[i - 1] == o) { key = nullptr; add = 0; return; }  // counted by the first slot of the run
   add = 1;
   for (uint64_t k = i + 1; k < n && k < i + MIRGE_MAX_MODS && off[k] == o; ++k) ++add;
@@ -244,6 +247,13 @@ extern "C" int mirge_collapse_merge(mirge_ctx *ctx, const mirge_table *t, const 
                                     uint64_t n_rec, uint32_t *d_deferred, void *stream) {
   if (!ctx) return MIRGE_ERR_ARG;
   return run_insert(ctx, t, d_rec, d_rec_off, n_rec, 1, d_deferred, (cudaStream_t)stream);
+}
+
+extern "C" int mirge_collapse_merge_inplace(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_rec_off, uint64_t n_rec,
+                                            uint32_t *d_deferred, void *stream) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  if (!t) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "collapse: null table");
+  return run_insert(ctx, t, t->d_arena, d_rec_off, n_rec, 3, d_deferred, (cudaStream_t)stream);
 }
 
 extern "C" int mirge_table_check_sync(mirge_ctx *ctx, const mirge_table *t, uint64_t *n_keys, uint64_t *arena_used, void *stream_) {

@@ -29,13 +29,14 @@ def shard_ranges(total: int, world: int):
 
 
 def exchange_records(rec: torch.Tensor, sizes: torch.Tensor, send_recs: torch.Tensor, group=None,
-                     send_words: torch.Tensor = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                     send_words: torch.Tensor = None, recv_buffer=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """All-to-all of variable-size records.
 
     rec       int32 words of all records, grouped by destination rank (ascending)
     sizes     int32 [n] words of each record, same order
     send_recs int64 [world] number of records for each destination
     send_words optional int64 [world] words for each destination (computed from sizes when absent)
+    recv_buffer optional callable (n_records, n_words) -> tensor the records are received into
     Returns (recv words, recv sizes) with records grouped by source rank.  Device-agnostic plumbing:
     NCCL on GPUs, gloo in the CPU tests."""
     world = dist.get_world_size(group)
@@ -58,7 +59,9 @@ def exchange_records(rec: torch.Tensor, sizes: torch.Tensor, send_recs: torch.Te
     s_words = [int(x) for x in send_words.cpu()]
     r_sizes = torch.empty(sum(recv_recs), dtype=sizes.dtype, device=dev)
     dist.all_to_all_single(r_sizes, sizes.contiguous(), output_split_sizes=recv_recs, input_split_sizes=s_recs, group=group)
-    r_rec = torch.empty(sum(recv_words), dtype=rec.dtype, device=dev)
+    # recv_buffer(n_records, n_words) -> tensor of n_words elements to receive into (e.g. the end of a table's arena)
+    r_rec = recv_buffer(sum(recv_recs), sum(recv_words)) if recv_buffer is not None else \
+        torch.empty(sum(recv_words), dtype=rec.dtype, device=dev)
     dist.all_to_all_single(r_rec, rec.contiguous(), output_split_sizes=recv_words, input_split_sizes=s_words, group=group)
     return r_rec, r_sizes
 
@@ -95,17 +98,30 @@ def exchange_and_merge(dev, local_table, ids: torch.Tensor, cnt: torch.Tensor, o
             dev.check(lib.mirge_partition_scatter(dev.ctx, C.byref(local_table.struct), _ptr(ids), _ptr(cnt), _ptr(dest), _ptr(words), n,
                                                   world, _ptr(cursors), _ptr(rec), _ptr(sizes), dev.stream()))
             dev.launches += 1
+    # the records are received straight into the end of the owner's arena: the first record of a sequence becomes
+    # the table's copy of its key where it lies (no copy, no publishing fence)
+    owner_table.check()
+    state = {}
+
+    def into_arena(n_rec, n_words):
+        owner_table.reserve(n_rec, n_words)
+        a0 = owner_table.arena_used
+        state["a0"] = a0
+        return owner_table.arena[a0 : a0 + n_words]
+
     with dev.timed("xchg_a2a"):
-        r_rec, r_sizes = exchange_records(rec[:total], sizes[:n], send_recs, group, send_words=send_words)
+        r_rec, r_sizes = exchange_records(rec[:total], sizes[:n], send_recs, group, send_words=send_words, recv_buffer=into_arena)
     m = int(r_sizes.numel())
     if m == 0:
         return 0
     with dev.timed("xchg_merge"):
-        r_off = (torch.cumsum(r_sizes.to(torch.int64), 0) - r_sizes.to(torch.int64)).to(torch.int32)
-        owner_table.check()
-        owner_table.reserve(m, int(r_rec.numel()))
+        a0 = state["a0"]
+        r_off = (torch.cumsum(r_sizes.to(torch.int64), 0) - r_sizes.to(torch.int64) + a0)
+        r_off = torch.where(r_off >= (1 << 31), r_off - (1 << 32), r_off).to(torch.int32)
+        owner_table.arena_used = a0 + int(r_rec.numel())
+        owner_table.ctrl[0] = owner_table.arena_used
         deferred = dev.empty(m, torch.int32)
-        dev.check(lib.mirge_collapse_merge(dev.ctx, C.byref(owner_table.struct), _ptr(r_rec), _ptr(r_off), m, _ptr(deferred), dev.stream()))
+        dev.check(lib.mirge_collapse_merge_inplace(dev.ctx, C.byref(owner_table.struct), _ptr(r_off), m, _ptr(deferred), dev.stream()))
         dev.launches += 3
         owner_table.check()
     return m
