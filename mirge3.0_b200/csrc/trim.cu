@@ -11,6 +11,13 @@
 // Data movement: a CTA owns TRIM_THREADS consecutive records, whose bytes are one contiguous span
 // of the FASTQ stream; the span is staged in shared memory with coalesced 128-bit streaming loads
 // and every thread then works on its own record out of shared memory.  All arithmetic is integer.
+//
+// Kernels (see "split pipeline" below): with 3' adapters of <= 32 nt the work is cut at the adapter modifier into
+// stage 1 (trim_kernel<32,true,1,true>: everything up to the adapter + exact adapter search), stage 2
+// (trim_dp_kernel<true>: bit-vector DP of the listed reads) and stage 3 (trim_dp_kernel<false>: the searches that
+// need cost columns); trim_kernel<32,true,2,false> runs the whole pipeline per read for the leftovers, and
+// trim_kernel<32,true,1,false> + that leftover pass is the unsplit bit-parallel path (qiagen UMIs);
+// trim_kernel<32|64,false,0,false> is the generic full-DP kernel (5' adapters, --no-indels, long adapters).
 #include "common.cuh"
 
 #define TRIM_THREADS 128
@@ -458,9 +465,10 @@ __device__ __forceinline__ bool all_deletions_possible(const uint32_t *eqt, cons
 #define INS_MASK(eq, vp, hn) (~(eq) & (vp) & ((hn) << 1))
 #define CHAIN_LEN(ins, i) (__clz((int)~((ins) << (32 - (i)))))
 
-// DEFER (first pass of the two-pass scheme): as soon as a candidate would need cost columns (recompute +
-// general traceback) the search gives up with 2 and the read is queued for the second pass, which runs
-// this function without DEFER on a compacted list, so that the rare expensive path executes with full warps.
+// DEFER: as soon as a candidate would need cost columns (recompute + general traceback) the search gives up
+// with 2 and the read is queued for a later stage (stage 3 of the split pipeline, or the leftover pass of the
+// unsplit path), which runs this function without DEFER on a compacted list, so that the rare expensive path
+// executes with full warps.
 // Returns 0 = no match, 1 = match in `out`, 2 = deferred.
 template <bool DEFER, class RV>
 __device__ __forceinline__ int locate_fast(const int a, const RV read, const int n, const FastCtx &fc, Match &out) {
