@@ -287,9 +287,22 @@ def run_b200(args):
 
     # ---- end to end from pinned host memory
     e2e = None
+    host = None
     if not args.no_e2e:
-        host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-        host.copy_(fq)
+        # the host copy of the input (pinned).  If any rank cannot pin that much memory all ranks skip the e2e leg
+        # together (it contains collectives) and the line reports e2e = null.
+        try:
+            host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+            host.copy_(fq)
+        except (RuntimeError, MemoryError) as exc:
+            sys.stderr.write("bench: e2e leg skipped on rank %d: %s\n" % (rank, exc))
+            host = None
+        okf = torch.tensor([0 if host is None else 1], device=dev.tdev)
+        if world > 1:
+            dist.all_reduce(okf, op=dist.ReduceOp.MIN)
+        if int(okf.item()) == 0:
+            host = None
+    if host is not None:
         torch.cuda.synchronize()
         streamer = DG.HostStreamer(eng, args.e2e_batch_mb << 20)
 
