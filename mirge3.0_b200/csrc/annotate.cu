@@ -367,7 +367,9 @@ __device__ __forceinline__ void build_query(const KeyView &k, int qs, int qe, ui
 // All rounds of bwtAlign for one unique sequence per thread, in order; a sequence leaves at the first round
 // that hits it (manifoldAlign.py:120,129).  The key is read once and the query words are rebuilt only when
 // a round's window differs (poly-T stripping of round 3, -5/-3 trimming of round 8).
-__global__ void __launch_bounds__(ANN_THREADS)
+// 10 CTAs per SM (48 registers): 17.5 ms per 39 M sequences; 85 registers / 6 CTAs measured 28.3 ms, 40 registers / 12
+// CTAs 17.8 ms -- the kernel lives on warps in flight, up to the point where spills eat the gain.
+__global__ void __launch_bounds__(ANN_THREADS, 10)
 annotate_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_keys, uint8_t *__restrict__ annot_round,
                 uint64_t *__restrict__ hit, const uint32_t *__restrict__ order) {
   __shared__ WarpScratch s_ws[ANN_THREADS / 32];

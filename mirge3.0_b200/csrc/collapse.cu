@@ -116,8 +116,16 @@ __device__ __forceinline__ int table_insert(const mirge_table &t, const uint32_t
       // release made it visible before ref: no fence needed on this side
       const uint32_t *k2 = t.d_arena + (ref - 1u);
       bool same = true;
-      for (uint32_t i = 0; i < nw; ++i) {
-        if (ld_cg_u32(k2 + i) != key[i]) { same = false; break; }
+      if (nw <= 8u) {  // all words in flight together: a tag match is almost always the same key, an early exit saves nothing
+        uint32_t d = 0;
+#pragma unroll
+        for (uint32_t i = 0; i < 8u; ++i)
+          if (i < nw) d |= ld_cg_u32(k2 + i) ^ key[i];
+        same = d == 0u;
+      } else {
+        for (uint32_t i = 0; i < nw; ++i) {
+          if (ld_cg_u32(k2 + i) != key[i]) { same = false; break; }
+        }
       }
       if (same) {
         atomicAdd(&s->count, add);
@@ -153,11 +161,34 @@ __device__ __forceinline__ void item_key(int mode, const uint32_t *keys, const u
   if (o == 0xFFFFFFFFu) { key = nullptr; add = 0; return; }
   if (mode == 1) { key = keys + o + 1; add = keys[o]; return; }
   if (mode == 3) { key = keys + o + 1; add = keys[o]; in_arena = o + 1; return; }
-  if (i > 0 && off[i - 1] == o) { key = nullptr; add = 0; return; }  // counted by the first slot of the run
+  // the neighbours that decide the run are loaded together (independent loads: one latency, not one per step)
+  const uint32_t o_prev = i > 0 ? off[i - 1] : 0u, o1 = i + 1 < n ? off[i + 1] : 0xFFFFFFFFu, o2 = i + 2 < n ? off[i + 2] : 0xFFFFFFFFu;
+  if (i > 0 && o_prev == o) { key = nullptr; add = 0; return; }  // counted by the first slot of the run
   add = 1;
-  for (uint64_t k = i + 1; k < n && k < i + MIRGE_MAX_MODS && off[k] == o; ++k) ++add;
+  if (o1 == o) {
+    ++add;
+    if (o2 == o) {
+      ++add;
+      for (uint64_t k = i + 3; k < n && k < i + MIRGE_MAX_MODS && off[k] == o; ++k) ++add;
+    }
+  }
   key = keys + o;
   if (mode == 2) in_arena = o;
+}
+
+// Hash of an in-arena key whose length is not known yet: the header and the next seven words are fetched together
+// (clipped to the arena), so the header -> payload dependency costs one memory latency instead of two.
+__device__ __forceinline__ uint64_t hash_key_in_arena(const mirge_table &t, const uint32_t *key, uint32_t aoff, uint32_t &nw) {
+  uint32_t kw[8];
+#pragma unroll
+  for (uint32_t j = 0; j < 8u; ++j) kw[j] = ((uint64_t)aoff + j < t.arena_words) ? key[j] : 0u;
+  nw = key_words(kw[0]);
+  uint64_t h = 0x243F6A8885A308D3ull;
+#pragma unroll
+  for (uint32_t j = 0; j < 8u; ++j)
+    if (j < nw) h = hash_step(h, kw[j]);
+  for (uint32_t j = 8u; j < nw; ++j) h = hash_step(h, key[j]);
+  return mix64(h);
 }
 
 __global__ void __launch_bounds__(COL_THREADS)
@@ -168,8 +199,14 @@ collapse_insert_kernel(mirge_table t, const uint32_t *__restrict__ keys, const u
   const uint32_t *key; uint32_t add, in_arena;
   item_key(mode, keys, off, i, n, key, add, in_arena);
   if (!key || add == 0) return;
-  const uint32_t nw = key_words(key[0]);
-  const uint64_t h = hash_key(key, nw);
+  uint32_t nw;
+  uint64_t h;
+  if (mode >= 2) {  // uniform: the keys lie in the table's arena
+    h = hash_key_in_arena(t, key, in_arena, nw);
+  } else {
+    nw = key_words(key[0]);
+    h = hash_key(key, nw);
+  }
   if (table_insert(t, key, nw, add, h, false, in_arena) == INS_DEFER)
     defer_item((unsigned long long *)t.d_ctrl + 3, deferred, (uint32_t)i);
 }

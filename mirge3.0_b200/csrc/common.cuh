@@ -88,3 +88,13 @@ __device__ __forceinline__ uint4 ld_stream_u4(const void *p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+
+// Asynchronous global -> shared copies (LDGSTS): every copy of a thread is in flight at once and no register is
+// held for the data; the thread waits for all of its own copies with cp_async_wait_all().
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }

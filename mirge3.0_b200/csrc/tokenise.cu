@@ -70,13 +70,22 @@ __device__ __forceinline__ void load32(const uint8_t *fq, uint64_t n, uint64_t p
   }
 }
 
-// bit i set <=> byte i of the 32 bytes is '\n'
+// newline_mask: bit i set <=> byte i of the 32 bytes is '\n'.
+// Exact zero-byte test of w ^ "\n\n\n\n" (bit 7 of every byte that is '\n'; no carry crosses a byte), then two words
+// at a time: the flags of the first word move to bits 8b+3, those of the second stay at 8b+7, and one multiply by
+// 2^0 + 2^7 + 2^14 + 2^21 lines all eight up in the top byte (the 32 partial products land on distinct bits, so
+// the sum has no carries).
+__device__ __forceinline__ uint32_t newline_flags(uint32_t w) {
+  const uint32_t x = w ^ 0x0A0A0A0Au;
+  const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+  return ~(t | x) & 0x80808080u;
+}
 __device__ __forceinline__ uint32_t newline_mask(const uint32_t w[8]) {
   uint32_t m = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    uint32_t eq = __vcmpeq4(w[k], 0x0A0A0A0Au) & 0x80808080u;
-    m |= ((eq * 0x00204081u) >> 28) << (4 * k);
+  for (int k = 0; k < 8; k += 2) {
+    const uint32_t q = newline_flags(w[k + 1]) | (newline_flags(w[k]) >> 4);
+    m |= ((q * 0x00204081u) >> 24) << (4 * k);
   }
   return m;
 }
@@ -106,30 +115,55 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *s
   return base + inc - v;
 }
 
+// Pass 1: one CTA per TOK_PAIR consecutive tiles; the loads of both tiles (4 x 128 bits per thread) are issued before
+// any of them is used.
+#define TOK_PAIR 2
+static_assert(TOK_GROUP % TOK_PAIR == 0, "a tile pair must not straddle two groups");
 __global__ void __launch_bounds__(TOK_THREADS) tok_count_kernel(const uint8_t *__restrict__ fq, uint64_t n, uint32_t skew,
                                                                  uint32_t *__restrict__ masks, uint32_t *__restrict__ tile_counts,
-                                                                 uint32_t *__restrict__ group_totals) {
-  __shared__ uint32_t sm[TOK_THREADS / 32];
-  const uint64_t tile = blockIdx.x;
-  const uint64_t pos = tile * TOK_TILE + (uint64_t)threadIdx.x * 32;
-  uint32_t c = 0, mk = 0;
-  if (pos < n) {
-    uint32_t w[8];
-    load32(fq, n, pos, w);
-    mk = newline_mask(w);
-    if (pos == 0) mk &= ~((1u << skew) - 1u);  // bytes before the stream start are not ours
-    c = __popc(mk);
+                                                                 uint32_t *__restrict__ group_totals, uint64_t n_tiles) {
+  __shared__ uint32_t sm[TOK_PAIR][TOK_THREADS / 32];
+  const uint64_t tile0 = (uint64_t)blockIdx.x * TOK_PAIR;
+  uint32_t w[TOK_PAIR][8], mk[TOK_PAIR], c[TOK_PAIR];
+  const uint64_t pos0 = tile0 * TOK_TILE + (uint64_t)threadIdx.x * 32;
+  if (pos0 + (TOK_PAIR - 1) * TOK_TILE + 32 <= n) {  // all pieces complete: straight-line loads
+#pragma unroll
+    for (int k = 0; k < TOK_PAIR; ++k) {
+      const uint4 a = ld_stream_u4(fq + pos0 + k * TOK_TILE), b = ld_stream_u4(fq + pos0 + k * TOK_TILE + 16);
+      w[k][0] = a.x; w[k][1] = a.y; w[k][2] = a.z; w[k][3] = a.w;
+      w[k][4] = b.x; w[k][5] = b.y; w[k][6] = b.z; w[k][7] = b.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < TOK_PAIR; ++k) {
+      const uint64_t pos = pos0 + (uint64_t)k * TOK_TILE;
+      if (pos < n) load32(fq, n, pos, w[k]);
+    }
   }
-  masks[tile * TOK_THREADS + threadIdx.x] = mk;
-  c = __reduce_add_sync(0xffffffffu, c);
-  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = c;
+#pragma unroll
+  for (int k = 0; k < TOK_PAIR; ++k) {
+    const uint64_t pos = (tile0 + k) * TOK_TILE + (uint64_t)threadIdx.x * 32;
+    mk[k] = 0;
+    if (pos < n) {
+      mk[k] = newline_mask(w[k]);
+      if (pos == 0) mk[k] &= ~((1u << skew) - 1u);  // bytes before the stream start are not ours
+    }
+    if (tile0 + k < n_tiles) masks[(tile0 + k) * TOK_THREADS + threadIdx.x] = mk[k];
+    c[k] = __reduce_add_sync(0xffffffffu, __popc(mk[k]));
+    if ((threadIdx.x & 31) == 0) sm[k][threadIdx.x >> 5] = c[k];
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t t = 0;
+    uint32_t both = 0;
 #pragma unroll
-    for (int i = 0; i < TOK_THREADS / 32; ++i) t += sm[i];
-    tile_counts[tile] = t;
-    atomicAdd(&group_totals[tile / TOK_GROUP], t);
+    for (int k = 0; k < TOK_PAIR; ++k) {
+      uint32_t t = 0;
+#pragma unroll
+      for (int i = 0; i < TOK_THREADS / 32; ++i) t += sm[k][i];
+      if (tile0 + k < n_tiles) tile_counts[tile0 + k] = t;
+      both += t;
+    }
+    atomicAdd(&group_totals[tile0 / TOK_GROUP], both);
   }
 }
 
@@ -167,26 +201,38 @@ __global__ void __launch_bounds__(TOK_THREADS) tok_scan_tiles_kernel(const uint3
   }
 }
 
+// Pass 2: one CTA per TOK_SUPER consecutive tiles (they share a group: TOK_SUPER divides TOK_GROUP), one 128-bit load of
+// four masks (128 bytes of the stream) per thread, one block scan, then the line starts of those bytes.
+#define TOK_SUPER 4
+static_assert(TOK_GROUP % TOK_SUPER == 0, "a super-tile must not straddle two groups");
 __global__ void __launch_bounds__(TOK_THREADS) tok_index_kernel(const uint32_t *__restrict__ masks, uint64_t n,
                                                                  const uint32_t *__restrict__ tile_excl,
                                                                  const uint64_t *__restrict__ group_prefix,
                                                                  uint32_t *__restrict__ line_start, uint64_t max_lines,
                                                                  uint32_t skew) {
   __shared__ uint32_t sm[TOK_THREADS / 32];
-  const uint64_t tile = blockIdx.x;
-  const uint64_t before = group_prefix[tile / TOK_GROUP] + tile_excl[tile];
-  const uint64_t pos = tile * TOK_TILE + (uint64_t)threadIdx.x * 32;
-  uint32_t mask = masks[tile * TOK_THREADS + threadIdx.x];  // written by pass 1 (zero past the end)
+  const uint64_t n_tiles = (n + TOK_TILE - 1) / TOK_TILE;
+  const uint64_t tile0 = (uint64_t)blockIdx.x * TOK_SUPER;
+  const uint64_t before = group_prefix[tile0 / TOK_GROUP] + tile_excl[tile0];
+  const uint64_t w0 = tile0 * TOK_THREADS + 4ull * threadIdx.x;  // first of this thread's four mask words
+  uint4 m4 = make_uint4(0, 0, 0, 0);
+  if (w0 < n_tiles * TOK_THREADS) m4 = *(const uint4 *)(masks + w0);  // written by pass 1 (zero past the end of the stream)
+  const uint32_t mk[4] = {m4.x, m4.y, m4.z, m4.w};
   uint32_t total;
-  uint32_t ex = block_exclusive_scan(__popc(mask), sm, &total);
+  const uint32_t ex = block_exclusive_scan(__popc(m4.x) + __popc(m4.y) + __popc(m4.z) + __popc(m4.w), sm, &total);
   uint64_t g = before + ex;  // ordinal (0-based) of this thread's first '\n'
-  while (mask) {
-    int b = __ffs(mask) - 1;
-    mask &= mask - 1;
-    if (g + 1 <= max_lines) line_start[g + 1] = (uint32_t)(pos + b + 1);
-    ++g;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint64_t pos = (w0 + k) * 32;
+    uint32_t mask = mk[k];
+    while (mask) {
+      const int b = __ffs(mask) - 1;
+      mask &= mask - 1;
+      if (g + 1 <= max_lines) line_start[g + 1] = (uint32_t)(pos + b + 1);
+      ++g;
+    }
   }
-  if (tile == 0 && threadIdx.x == 0) line_start[0] = skew;
+  if (blockIdx.x == 0 && threadIdx.x == 0) line_start[0] = skew;
 }
 
 __global__ void tok_fixup_kernel(uint32_t *last, uint32_t virtual_end) {
@@ -246,7 +292,8 @@ extern "C" int mirge_tokenise_sync(mirge_ctx *ctx, const uint8_t *d_fastq, uint6
   const uint64_t n_al = nbytes + skew;
   TokScratch s = tok_layout(d_scratch, n_al);
   MIRGE_CUDA(ctx, cudaMemsetAsync(s.group_totals, 0, s.n_groups * 4, stream));
-  tok_count_kernel<<<(unsigned)s.n_tiles, TOK_THREADS, 0, stream>>>(fq_al, n_al, skew, s.masks, s.tile_counts, s.group_totals);
+  tok_count_kernel<<<(unsigned)((s.n_tiles + TOK_PAIR - 1) / TOK_PAIR), TOK_THREADS, 0, stream>>>(fq_al, n_al, skew, s.masks, s.tile_counts,
+                                                                                              s.group_totals, s.n_tiles);
   MIRGE_LAUNCH_CHECK(ctx, "tok_count_kernel");
   tok_scan_groups_kernel<<<1, 32, 0, stream>>>(s.group_totals, s.n_groups, s.group_prefix, ctx->d_small);
   MIRGE_LAUNCH_CHECK(ctx, "tok_scan_groups_kernel");
@@ -293,7 +340,7 @@ extern "C" int mirge_line_index(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t
   MIRGE_CUDA(ctx, cudaMemsetAsync(d_line_start + 4 * n_records, 0, 4, stream));
   tok_scan_tiles_kernel<<<(unsigned)s.n_groups, TOK_THREADS, 0, stream>>>(s.tile_counts, s.n_tiles, s.tile_excl);
   MIRGE_LAUNCH_CHECK(ctx, "tok_scan_tiles_kernel");
-  tok_index_kernel<<<(unsigned)s.n_tiles, TOK_THREADS, 0, stream>>>(s.masks, n_al, s.tile_excl, s.group_prefix,
+  tok_index_kernel<<<(unsigned)((s.n_tiles + TOK_SUPER - 1) / TOK_SUPER), TOK_THREADS, 0, stream>>>(s.masks, n_al, s.tile_excl, s.group_prefix,
                                                                     d_line_start, 4 * n_records, skew);
   MIRGE_LAUNCH_CHECK(ctx, "tok_index_kernel");
   tok_fixup_kernel<<<1, 1, 0, stream>>>(d_line_start + 4 * n_records, (uint32_t)(n_al + 1));
