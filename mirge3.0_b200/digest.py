@@ -9,7 +9,6 @@ final table is exported."""
 from __future__ import annotations
 
 import ctypes as C
-import gzip
 import os
 import time
 from pathlib import Path
@@ -20,6 +19,7 @@ import pandas as pd
 import torch
 
 from . import abi
+from . import ingest
 from . import params as P
 from .device import CollapseTable, Device, DigestEngine, FastqFormatError, MirgeError, _ptr
 from .manifoldAlign import get_device
@@ -36,12 +36,18 @@ def default_count_mode() -> str:
     return os.environ.get("MIRGE_B200_COUNT_MODE", "head")
 
 
-def _open_fastq(path: str):
-    with open(path, "rb") as f:
-        magic = f.read(2)
-    if magic == b"\x1f\x8b":
-        return gzip.open(path, "rb")
-    return open(path, "rb", buffering=0)
+def _host_threads(args) -> Optional[int]:
+    """Worker threads for reading / inflating input: the reference's ``-cpu`` / args.threads (digest.py:139)."""
+    try:
+        t = int(getattr(args, "threads", 0) or 0)
+    except (TypeError, ValueError):
+        t = 0
+    return t if t > 0 else None
+
+
+def _open_fastq(path: str, threads: Optional[int] = None):
+    """One input file as a readinto() source: read / inflated on worker threads (ingest.py)."""
+    return ingest.open_fastq(path, threads)
 
 
 class HostStreamer:
@@ -275,12 +281,18 @@ def baking(args, inFileArray, inFileBaseArray, workDir, device: Optional[Device]
     runlogFile = Path(workDir) / "run.log"
     outlog = open(str(runlogFile), "a+")
     quiet = bool(getattr(args, "quiet", False))
+    # the files of the run are read (and inflated) ahead of the sample being digested, on args.threads workers
+    readahead = ingest.SampleReadahead([str(p) for p in inFileArray], threads=_host_threads(args))
     for index, FQfile in enumerate(inFileArray):
         start = time.perf_counter()
         base = inFileBaseArray[index]
         umi_csv = str(Path(workDir) / (base + "_umiCounts.csv")) if (umi is not None and getattr(args, "umiDedup", False)) else None
-        with _open_fastq(FQfile) as f:
-            res = digest_sample(eng, f, table, first_level, bool(getattr(args, "umiDedup", False)), batch_bytes, umi_csv, streamer)
+        try:
+            with readahead.open(index) as f:
+                res = digest_sample(eng, f, table, first_level, bool(getattr(args, "umiDedup", False)), batch_bytes, umi_csv, streamer)
+        except BaseException:
+            readahead.close()
+            raise
         results.append(res)
         sampleReadCounts[base] = res.count
         trimmedReadCounts[base] = res.trimmed
@@ -300,6 +312,7 @@ def baking(args, inFileArray, inFileBaseArray, workDir, device: Optional[Device]
         if not quiet:
             print(f"Collapsing finished for file {base} in {round(finish3-finish2, 4)} second(s)\n")
         outlog.write(f"Collapsing finished for file {base} in {round(finish3-finish2, 4)} second(s)\n")
+    readahead.close()
     finish3 = time.perf_counter()
     complete_set = build_matrix(table, results, list(inFileBaseArray))
     finish4 = time.perf_counter()

@@ -161,6 +161,9 @@ def baking_sharded(args, inFileArray, inFileBaseArray, workDir, device=None, cou
     counts_read = np.zeros(len(names), dtype=np.int64)
     per_sample = []  # (owner ids, counts) of this rank's slice, per sample
     empty = torch.zeros(0, dtype=torch.int32, device=dev.tdev)
+    # this rank's files are read / inflated ahead of the sample it is digesting (ingest.py)
+    mine = [s for s in range(len(inFileArray)) if s % world == rank]
+    readahead = DG.ingest.SampleReadahead([str(inFileArray[s]) for s in mine], threads=DG._host_threads(args))
     for s, path in enumerate(inFileArray):
         if s % world == rank:
             umi_csv = None
@@ -168,7 +171,7 @@ def baking_sharded(args, inFileArray, inFileBaseArray, workDir, device=None, cou
                 import os
 
                 umi_csv = os.path.join(str(workDir), names[s] + "_umiCounts.csv")
-            with DG._open_fastq(path) as f:
+            with readahead.open(mine.index(s)) as f:
                 res = DG.digest_sample(eng, f, local, first_level, bool(getattr(args, "umiDedup", False)), batch_bytes, umi_csv, streamer)
             counts_read[s] = res.count
             ids = torch.from_numpy(res.ids.astype(np.int32)).to(dev.tdev)
@@ -179,6 +182,7 @@ def baking_sharded(args, inFileArray, inFileBaseArray, workDir, device=None, cou
         o_ids, o_cnt = owner.drain()
         per_sample.append((o_ids.cpu().numpy().astype(np.int64), o_cnt.cpu().numpy().astype(np.int64)))
         local.reset()
+    readahead.close()
     # counters (digest.py:212-217): records parsed by the digesting rank, emitted counts and unique sequences
     # summed over the owners
     tot = torch.zeros((3, len(names)), dtype=torch.int64, device=dev.tdev)

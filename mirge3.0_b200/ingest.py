@@ -1,0 +1,342 @@
+"""Host-side ingest of FASTQ files for ``baking`` -- what the reference does with ``xopen(FQfile, "rb")`` and
+``dnaio.read_chunks`` in the parent process (mirge/libs/digest.py:136-140; SURVEY.md section 8, row a1 and "next" row f-3).
+
+The GPU path consumes FASTQ bytes far faster than one core inflates them, and ``mirge_tokenise_sync`` makes the
+digesting thread wait for the device once per piece, so reading and inflating must not happen on that thread:
+
+* every file is read by a worker thread into a bounded queue of chunks; the digesting thread only copies chunks
+  into its pinned staging buffers (``readinto``);
+* plain gzip is one DEFLATE stream and is inflated by that one worker (multi-member files and trailing zero
+  padding are handled like Python's ``gzip`` module does);
+* BGZF files (bgzip, many sequencing pipelines: gzip members of <= 64 KB that carry their size in a 'BC' extra field)
+  are inflated block-parallel on a thread pool (zlib releases the GIL), CRC and size of every block checked;
+* ``SampleReadahead`` keeps the readers of the next samples of a run going while the current one is digested, which
+  is where a cohort of single-stream ``.fastq.gz`` files gets its parallelism (one inflating core per sample).
+
+Nothing here touches the device; the classes are file-like sources for ``digest.HostStreamer``.  Truncated or corrupt
+input raises (EOFError / OSError / zlib.error), like the reference's reader would."""
+from __future__ import annotations
+
+import collections
+import os
+import queue
+import struct
+import threading
+import zlib
+from concurrent.futures import ThreadPoolExecutor
+from typing import Callable, Iterator, List, Optional, Sequence
+
+CHUNK = 8 << 20  # bytes per queue entry (inflated)
+RAW_READ = 1 << 20  # compressed bytes fed to zlib per call
+BGZF_BATCH = 2 << 20  # compressed bytes per pool task
+
+_pool_lock = threading.Lock()
+_pool: Optional[ThreadPoolExecutor] = None
+_pool_size = 0
+
+
+def default_threads() -> int:
+    return max(1, min(32, (os.cpu_count() or 2) - 1))
+
+
+def inflate_pool(threads: Optional[int] = None) -> ThreadPoolExecutor:
+    """Process-wide pool of inflate workers (grown, never shrunk)."""
+    global _pool, _pool_size
+    want = int(threads or default_threads())
+    with _pool_lock:
+        if _pool is None or want > _pool_size:
+            _pool = ThreadPoolExecutor(max_workers=want, thread_name_prefix="mirge-inflate")
+            _pool_size = want
+        return _pool
+
+
+def sniff(path: str) -> str:
+    """'bgzf', 'gzip' or 'plain' from the first bytes of the file (xopen decides by magic number too)."""
+    with open(path, "rb") as f:
+        head = f.read(18)
+    if len(head) < 2 or head[:2] != b"\x1f\x8b":
+        return "plain"
+    if len(head) >= 18 and head[2] == 8 and (head[3] & 4):
+        xlen = struct.unpack_from("<H", head, 10)[0]
+        if xlen >= 6 and head[12:14] == b"BC" and struct.unpack_from("<H", head, 14)[0] == 2:
+            return "bgzf"
+    return "gzip"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# producers: generators of inflated chunks, run on the reader thread
+
+
+def _plain_chunks(path: str) -> Iterator[bytes]:
+    with open(path, "rb", buffering=0) as f:
+        while True:
+            b = f.read(CHUNK)
+            if not b:
+                return
+            yield b
+
+
+def _gzip_chunks(path: str) -> Iterator[bytes]:
+    """One worker, one DEFLATE stream at a time; members are chained, zero padding after a member is skipped."""
+    with open(path, "rb", buffering=0) as f:
+        d = zlib.decompressobj(31)
+        fed = False  # the current member has received data
+        while True:
+            raw = f.read(RAW_READ)
+            if not raw:
+                if fed and not d.eof:
+                    raise EOFError("Compressed file ended before the end-of-stream marker was reached: %s" % path)
+                return
+            buf = raw
+            while buf:
+                if not fed:  # between members: zero padding may run on into this read
+                    buf = buf.lstrip(b"\x00")
+                    if not buf:
+                        break
+                out = d.decompress(buf, CHUNK)
+                fed = True
+                if out:
+                    yield out
+                if d.eof:
+                    buf = d.unused_data
+                    d = zlib.decompressobj(31)
+                    fed = False
+                else:
+                    buf = d.unconsumed_tail
+
+
+def _read_exact(f, n: int, path: str) -> bytes:
+    b = f.read(n)
+    if len(b) != n:
+        raise EOFError("Compressed file ended inside a BGZF block: %s" % path)
+    return b
+
+
+def _bgzf_blocks(f, path: str):
+    """(deflate payload, crc32, isize) of every block, in file order."""
+    while True:
+        head = f.read(12)
+        if not head:
+            return
+        if len(head) != 12 or head[:4] != b"\x1f\x8b\x08\x04":
+            raise OSError("not a BGZF block at offset %d of %s" % (f.tell() - len(head), path))
+        xlen = struct.unpack_from("<H", head, 10)[0]
+        extra = _read_exact(f, xlen, path)
+        bsize = None
+        p = 0
+        while p + 4 <= xlen:
+            slen = struct.unpack_from("<H", extra, p + 2)[0]
+            if extra[p : p + 2] == b"BC" and slen == 2:
+                bsize = struct.unpack_from("<H", extra, p + 4)[0]
+            p += 4 + slen
+        if bsize is None:
+            raise OSError("gzip member without a BGZF size field in %s" % path)
+        rest = bsize + 1 - 12 - xlen
+        if rest < 8:
+            raise OSError("corrupt BGZF block size in %s" % path)
+        body = _read_exact(f, rest, path)
+        crc, isize = struct.unpack_from("<II", body, rest - 8)
+        yield body[: rest - 8], crc, isize
+
+
+def _inflate_blocks(blocks) -> bytes:
+    out = []
+    for payload, crc, isize in blocks:
+        data = zlib.decompress(payload, -15) if isize else b""
+        if len(data) != isize or (zlib.crc32(data) & 0xFFFFFFFF) != crc:
+            raise OSError("BGZF block fails its CRC / size check")
+        out.append(data)
+    return b"".join(out)
+
+
+def _bgzf_chunks(path: str, threads: Optional[int] = None) -> Iterator[bytes]:
+    pool = inflate_pool(threads)
+    window = 2 * (threads or default_threads())
+    inflight: collections.deque = collections.deque()
+    with open(path, "rb", buffering=4 << 20) as f:
+        batch, size = [], 0
+        for blk in _bgzf_blocks(f, path):
+            batch.append(blk)
+            size += len(blk[0])
+            if size >= BGZF_BATCH:
+                inflight.append(pool.submit(_inflate_blocks, batch))
+                batch, size = [], 0
+                while len(inflight) >= window:
+                    out = inflight.popleft().result()
+                    if out:
+                        yield out
+        if batch:
+            inflight.append(pool.submit(_inflate_blocks, batch))
+        while inflight:
+            out = inflight.popleft().result()
+            if out:
+                yield out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+
+
+class ChunkReader:
+    """File-like source (``readinto`` / ``read``) over chunks produced on a worker thread.
+
+    The queue holds at most ``depth`` chunks, so a reader that is far ahead of its consumer blocks instead of
+    buffering the file.  An exception on the worker is re-raised by the next ``readinto``."""
+
+    def __init__(self, producer: Callable[[], Iterator[bytes]], depth: int = 4, name: str = ""):
+        self.name = name
+        self._q: queue.Queue = queue.Queue(maxsize=max(int(depth), 1))
+        self._stop = threading.Event()
+        self._cur = memoryview(b"")
+        self._pos = 0
+        self._done = False
+        self.bytes_out = 0
+        self._t = threading.Thread(target=self._run, args=(producer,), daemon=True, name="mirge-read")
+        self._t.start()
+
+    def _put(self, item) -> bool:
+        while not self._stop.is_set():
+            try:
+                self._q.put(item, timeout=0.05)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def _run(self, producer):
+        try:
+            for chunk in producer():
+                if not self._put(chunk):
+                    return
+            self._put(None)
+        except BaseException as e:  # noqa: BLE001 -- handed to the consumer
+            self._put(e)
+
+    def readinto(self, out) -> int:
+        out = memoryview(out).cast("B")
+        n = 0
+        while n < len(out):
+            if self._pos == len(self._cur):
+                if self._done:
+                    break
+                item = self._q.get()
+                if item is None:
+                    self._done = True
+                    break
+                if isinstance(item, BaseException):
+                    self._done = True
+                    raise item
+                self._cur = memoryview(item)
+                self._pos = 0
+                continue
+            k = min(len(out) - n, len(self._cur) - self._pos)
+            out[n : n + k] = self._cur[self._pos : self._pos + k]
+            n += k
+            self._pos += k
+        self.bytes_out += n
+        return n
+
+    def read(self, n: int = -1) -> bytes:
+        if n is None or n < 0:
+            parts = []
+            while True:
+                b = self.read(CHUNK)
+                if not b:
+                    return b"".join(parts)
+                parts.append(b)
+        buf = bytearray(n)
+        k = self.readinto(buf)
+        return bytes(buf[:k])
+
+    def close(self):
+        self._stop.set()
+        try:
+            while True:
+                self._q.get_nowait()
+        except queue.Empty:
+            pass
+        self._t.join(timeout=5)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
+def open_fastq(path: str, threads: Optional[int] = None, depth: int = 4) -> ChunkReader:
+    """Reader for one FASTQ file: plain, gzip or BGZF by magic number (not by suffix, like xopen)."""
+    kind = sniff(path)
+    if kind == "bgzf":
+        return ChunkReader(lambda: _bgzf_chunks(path, threads), depth, name=path)
+    if kind == "gzip":
+        return ChunkReader(lambda: _gzip_chunks(path), depth, name=path)
+    return ChunkReader(lambda: _plain_chunks(path), depth, name=path)
+
+
+def readahead_budget_bytes() -> int:
+    """Host memory the look-ahead readers of a run may fill together: MIRGE_B200_READAHEAD_MB, else an eighth of
+    the machine's memory, at most 16 GB."""
+    env = os.environ.get("MIRGE_B200_READAHEAD_MB")
+    if env:
+        return max(int(env), 1) << 20
+    try:
+        total = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES")
+    except (ValueError, OSError):
+        total = 8 << 30
+    return int(min(total // 8, 16 << 30))
+
+
+class SampleReadahead:
+    """The input files of a run, opened in order with the next ``ahead`` of them already being read and inflated.
+
+    ``open(i)`` must be called with increasing ``i``; it returns the reader of file ``i`` (a context manager) and
+    starts the readers of files ``i + 1 .. i + ahead``.  Each look-ahead reader may buffer ``budget / (ahead + 1)``
+    bytes, so a cohort of single-stream gzip files is inflated by ``ahead + 1`` cores at once while the device
+    digests the sample in front."""
+
+    def __init__(self, paths: Sequence[str], ahead: Optional[int] = None, threads: Optional[int] = None,
+                 budget_bytes: Optional[int] = None):
+        self.paths = list(paths)
+        self.threads = int(threads or default_threads())
+        if ahead is None:
+            ahead = min(max(self.threads - 1, 0), 8)
+        self.ahead = max(0, min(int(ahead), max(len(self.paths) - 1, 0)))
+        budget = int(budget_bytes if budget_bytes is not None else readahead_budget_bytes())
+        self.depth = max(2, budget // ((self.ahead + 1) * CHUNK))
+        self._readers: List[object] = [None] * len(self.paths)  # ChunkReader, the OSError of its open, or None
+        self._next = 0
+
+    def _start_until(self, last: int):
+        while self._next <= min(last, len(self.paths) - 1):
+            i = self._next
+            try:
+                self._readers[i] = open_fastq(self.paths[i], self.threads, self.depth)
+            except OSError as e:  # a missing / unreadable file fails when its turn comes, not while it is looked ahead
+                self._readers[i] = e
+            self._next += 1
+
+    def open(self, i: int) -> ChunkReader:
+        if i < 0 or i >= len(self.paths):
+            raise IndexError(i)
+        self._start_until(i + self.ahead)
+        r = self._readers[i]
+        if r is None:
+            raise RuntimeError("SampleReadahead.open() must be called once per file, in order")
+        self._readers[i] = None
+        if isinstance(r, BaseException):
+            raise r
+        return r
+
+    def close(self):
+        for i, r in enumerate(self._readers):
+            if isinstance(r, ChunkReader):
+                r.close()
+            self._readers[i] = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False

@@ -1,0 +1,210 @@
+"""CPU tests of the host-side ingest (mirge3.0_b200/ingest.py): the readers that stand where the reference has
+``xopen(FQfile, "rb")`` + ``dnaio.read_chunks`` (mirge/libs/digest.py:136-140).  Every reader must hand the device
+path exactly the bytes Python's gzip module (what xopen falls back to) would: plain, gzip, multi-member gzip, zero
+padding, BGZF; truncated or corrupt files must raise; the look-ahead over the samples of a run must keep the order."""
+import gzip
+import os
+import struct
+import threading
+import zlib
+
+import numpy as np
+import pytest
+
+import mirge_b200  # noqa: F401
+from mirge_b200 import ingest
+from tests.util import random_fastq
+
+
+def write_bgzf(path, data: bytes, block=60000, eof_block=True):
+    """Minimal BGZF writer (SAM spec 4.1): gzip members with a 'BC' extra field holding the block size - 1."""
+    with open(path, "wb") as f:
+        pieces = [data[i : i + block] for i in range(0, len(data), block)]
+        if eof_block:
+            pieces.append(b"")
+        for p in pieces:
+            c = zlib.compressobj(6, zlib.DEFLATED, -15)
+            payload = c.compress(p) + c.flush()
+            bsize = 12 + 6 + len(payload) + 8
+            f.write(b"\x1f\x8b\x08\x04" + b"\x00" * 4 + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1))
+            f.write(payload)
+            f.write(struct.pack("<II", zlib.crc32(p) & 0xFFFFFFFF, len(p)))
+
+
+def read_all(reader, bufsize):
+    out = bytearray()
+    buf = np.zeros(bufsize, dtype=np.uint8)
+    mv = memoryview(buf)  # what digest.HostStreamer hands to readinto()
+    while True:
+        k = reader.readinto(mv)
+        if not k:
+            return bytes(out)
+        out += buf[:k].tobytes()
+
+
+@pytest.fixture(scope="module")
+def files(tmp_path_factory):
+    d = tmp_path_factory.mktemp("ingest")
+    data = random_fastq(20000, seed=3)  # ~2.6 MB
+    paths = {}
+    p = str(d / "plain.fastq")
+    open(p, "wb").write(data)
+    paths["plain"] = p
+    p = str(d / "single.fastq.gz")
+    with gzip.open(p, "wb") as f:
+        f.write(data)
+    paths["gzip"] = p
+    p = str(d / "members.gz")
+    cut = [0, 1, 100001, len(data) // 2, len(data)]
+    with open(p, "wb") as f:
+        for a, b in zip(cut, cut[1:]):
+            f.write(gzip.compress(data[a:b]))
+        f.write(b"\x00" * 300)  # tape-style zero padding, ignored like the gzip module does
+    paths["members"] = p
+    p = str(d / "padded_between.gz")
+    with open(p, "wb") as f:
+        f.write(gzip.compress(data[:5000]) + b"\x00" * 17 + gzip.compress(data[5000:]))
+    paths["padded"] = p
+    p = str(d / "blocks.fastq.gz")  # BGZF under a .gz name: the format is taken from the bytes, not the suffix
+    write_bgzf(p, data)
+    paths["bgzf"] = p
+    p = str(d / "blocks_noeof.bgz")
+    write_bgzf(p, data, block=1000, eof_block=False)
+    paths["bgzf_small"] = p
+    p = str(d / "empty.fastq")
+    open(p, "wb").close()
+    paths["empty"] = p
+    p = str(d / "empty.fastq.gz")
+    with gzip.open(p, "wb"):
+        pass
+    paths["empty_gz"] = p
+    return d, data, paths
+
+
+def test_sniff(files):
+    _, _, paths = files
+    assert ingest.sniff(paths["plain"]) == "plain"
+    assert ingest.sniff(paths["empty"]) == "plain"
+    assert ingest.sniff(paths["gzip"]) == "gzip"
+    assert ingest.sniff(paths["members"]) == "gzip"
+    assert ingest.sniff(paths["bgzf"]) == "bgzf"
+    assert ingest.sniff(paths["bgzf_small"]) == "bgzf"
+
+
+@pytest.mark.parametrize("kind", ["plain", "gzip", "members", "padded", "bgzf", "bgzf_small"])
+@pytest.mark.parametrize("bufsize", [4096, 1 << 20, 5 << 20])
+def test_readers_return_the_stream(files, kind, bufsize):
+    _, data, paths = files
+    with ingest.open_fastq(paths[kind], threads=3, depth=2) as r:
+        got = read_all(r, bufsize)
+    assert got == data
+    if kind != "plain":
+        # what the reference's xopen / gzip would have produced
+        ref = gzip.open(paths[kind], "rb").read()
+        assert got == ref
+
+
+def test_small_chunks_all_formats(files, monkeypatch):
+    _, data, paths = files
+    monkeypatch.setattr(ingest, "CHUNK", 1 << 12)
+    monkeypatch.setattr(ingest, "RAW_READ", 777)
+    monkeypatch.setattr(ingest, "BGZF_BATCH", 2500)
+    for kind in ("plain", "gzip", "members", "padded", "bgzf", "bgzf_small"):
+        with ingest.open_fastq(paths[kind], threads=4, depth=3) as r:
+            assert read_all(r, 10007) == data, kind
+    with ingest.open_fastq(paths["bgzf_small"], threads=2, depth=1) as r:
+        head = bytearray()
+        for _ in range(3000):
+            b7 = bytearray(7)
+            k = r.readinto(b7)
+            head += b7[:k]
+        assert bytes(head) == data[: len(head)] and len(head) == 21000
+    with ingest.open_fastq(paths["gzip"], threads=2) as r:
+        assert r.read(10) == data[:10]
+        assert r.read() == data[10:]
+
+
+def test_empty_inputs(files):
+    _, _, paths = files
+    for k in ("empty", "empty_gz"):
+        with ingest.open_fastq(paths[k]) as r:
+            assert r.readinto(bytearray(100)) == 0
+            assert r.readinto(bytearray(100)) == 0
+
+
+def test_truncated_and_corrupt_inputs_raise(files):
+    d, data, paths = files
+    raw = open(paths["gzip"], "rb").read()
+    p = str(d / "trunc.gz")
+    open(p, "wb").write(raw[: len(raw) // 2])
+    with pytest.raises(EOFError):
+        with ingest.open_fastq(p) as r:
+            read_all(r, 1 << 20)
+    with pytest.raises(EOFError):  # the gzip module agrees
+        gzip.open(p, "rb").read()
+    raw = open(paths["bgzf"], "rb").read()
+    p = str(d / "trunc.bgz")
+    open(p, "wb").write(raw[: len(raw) // 2])
+    with pytest.raises(EOFError):
+        with ingest.open_fastq(p) as r:
+            read_all(r, 1 << 20)
+    bad = bytearray(raw)
+    bad[len(raw) // 3] ^= 0x55  # flips a bit inside some block's payload
+    p = str(d / "corrupt.bgz")
+    open(p, "wb").write(bytes(bad))
+    with pytest.raises((OSError, zlib.error)):
+        with ingest.open_fastq(p) as r:
+            read_all(r, 1 << 20)
+    p = str(d / "garbage_after.gz")
+    open(p, "wb").write(open(paths["gzip"], "rb").read() + b"not gzip")
+    with pytest.raises(zlib.error):
+        with ingest.open_fastq(p) as r:
+            read_all(r, 1 << 20)
+
+
+def test_sample_readahead_keeps_order_and_stops_its_threads(files):
+    _, data, paths = files
+    order = ["gzip", "plain", "bgzf", "members", "empty", "bgzf_small", "padded"]
+    before = threading.active_count()
+    with ingest.SampleReadahead([paths[k] for k in order], ahead=3, threads=4, budget_bytes=4 * ingest.CHUNK) as ra:
+        assert ra.depth == 2  # the budget bounds what the look-ahead readers may hold
+        for i, k in enumerate(order):
+            with ra.open(i) as r:
+                got = read_all(r, 1 << 19)
+            assert got == (b"" if k == "empty" else data), k
+        with pytest.raises(RuntimeError):
+            ra.open(2)  # each file once, in order
+    # a run that stops early must not leave readers behind
+    ra = ingest.SampleReadahead([paths[k] for k in order], ahead=4, threads=4, budget_bytes=2 * ingest.CHUNK)
+    r0 = ra.open(0)
+    assert r0.readinto(bytearray(1000)) == 1000
+    r0.close()
+    ra.close()
+    for t in threading.enumerate():
+        if t.name == "mirge-read":
+            t.join(timeout=5)
+    assert sum(t.name == "mirge-read" and t.is_alive() for t in threading.enumerate()) == 0
+    assert threading.active_count() <= before + ingest.default_threads() + 4  # pool workers may stay
+
+
+def test_missing_file_fails_at_its_turn(files):
+    d, data, paths = files
+    with ingest.SampleReadahead([paths["gzip"], str(d / "nope.fastq"), paths["plain"]], ahead=2, threads=2) as ra:
+        with ra.open(0) as r:
+            assert read_all(r, 1 << 20) == data  # the sample in front is not affected by the look-ahead's failure
+        with pytest.raises(FileNotFoundError):
+            ra.open(1)
+        with ra.open(2) as r:
+            assert read_all(r, 1 << 20) == data
+
+
+def test_readahead_defaults():
+    ra = ingest.SampleReadahead(["a", "b", "c"], threads=16, budget_bytes=1 << 30)
+    assert ra.ahead == 2 and ra.depth == (1 << 30) // (3 * ingest.CHUNK)
+    ra = ingest.SampleReadahead(["a"], threads=16, budget_bytes=1 << 30)
+    assert ra.ahead == 0
+    os.environ["MIRGE_B200_READAHEAD_MB"] = "64"
+    try:
+        assert ingest.readahead_budget_bytes() == 64 << 20
+    finally:
+        del os.environ["MIRGE_B200_READAHEAD_MB"]
