@@ -332,7 +332,6 @@ extern "C" int mirge_line_index(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t
     return MIRGE_OK;
   }
   const uint32_t skew = (uint32_t)((uintptr_t)d_fastq & 15);
-  const uint8_t *fq_al = d_fastq - skew;
   const uint64_t n_al = nbytes + skew;
   TokScratch s = tok_layout((void *)d_scratch, n_al);
   // EOF rule: when the last line has no '\n' the 4n-th line break does not exist; the entry is
