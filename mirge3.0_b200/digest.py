@@ -18,7 +18,6 @@ import numpy as np
 import pandas as pd
 import torch
 
-from . import abi
 from . import ingest
 from . import params as P
 from .device import CollapseTable, Device, DigestEngine, FastqFormatError, MirgeError, _ptr

@@ -9,8 +9,7 @@ import ctypes as C
 import gzip
 import math
 import os
-from dataclasses import dataclass
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
 import torch

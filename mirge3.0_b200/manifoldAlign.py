@@ -13,7 +13,7 @@ import torch
 
 from . import abi
 from .device import CollapseTable, Device, MirgeError, _ptr
-from .libraries import ROUND_COLUMNS, ROUND_LIBS, LibrarySet, round_policies
+from .libraries import ROUND_LIBS, LibrarySet, round_policies
 
 _DEVICE: Optional[Device] = None
 _LIB_CACHE: Dict[Tuple, LibrarySet] = {}

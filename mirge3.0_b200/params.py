@@ -3,7 +3,7 @@ globals ``baking`` publishes (digest.py:110-122): resolve miRge's ``args`` names
 plain ``mirge_trim_params`` structure the kernels consume."""
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
 from . import abi

@@ -9,7 +9,6 @@ host.  The reference's own ``summarize`` keeps working on the DataFrame ``bwtAli
 the same arithmetic without the pandas joins, for tables that do not fit a DataFrame comfortably."""
 from __future__ import annotations
 
-import ctypes as C
 from pathlib import Path
 from typing import Dict, List, Optional, Sequence, Tuple
 

@@ -6,8 +6,8 @@ as specified; reads are generated with torch on the target device (``torch.Gener
 data, every parity check runs the oracle on the very same bytes."""
 from __future__ import annotations
 
-from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Tuple
+from dataclasses import dataclass
+from typing import Dict, List, Optional
 
 import numpy as np
 import torch

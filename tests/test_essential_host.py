@@ -5,7 +5,6 @@ import argparse
 import gzip
 import os
 import subprocess
-import sys
 
 import numpy as np
 import pytest
