@@ -253,6 +253,17 @@ def digest_cases(rng):
             s = "N" * int(rng.integers(1, 3)) + s
         return s
 
+    FRONT = "GTTCAGAGTTCTACAGTCCGACGATC"  # the reference's "illumina" alias for -g (mirge/__main__.py:74-76)
+
+    def both(i):  # 5' adapter remnant + insert + 3' adapter: -g and -a together, two removal rounds, no indels
+        s = insert() + noisy(ILLUMINA, 0.05) + rnd(30)
+        r = rng.random()
+        if r < 0.35:
+            s = noisy(FRONT[int(rng.integers(0, 20)):], 0.04) + s
+        elif r < 0.4:
+            s = rnd(int(rng.integers(1, 4))) + FRONT + s  # 5' adapter not at the very start
+        return s
+
     return [
         ("ref_case2_umi", dict(uniq_mol_ids="4,4", umiDedup=False, tcf_out=True), [reads(1500, ill4n, tag="u%d" % k) for k in range(2)]),
         ("ref_case3_umi_dedup", dict(uniq_mol_ids="4,4", umiDedup=True), [reads(1500, ill4n, tag="d")]),
@@ -260,6 +271,9 @@ def digest_cases(rng):
          [reads(1500, qia, L=75, tag="q%d" % k) for k in range(2)]),
         ("ref_case5_nextseq_cuts", dict(nextseq_trim=20, quality_cutoff="5,15", trim_n=True, cut=[2, -3], times=2, minimum_length=14),
          [reads(1500, nxt, L=75, tag="n")]),
+        ("ref_case6_front_back_noindels", dict(adapters=[("back", ILLUMINA), ("front", FRONT)], indels=False, times=2, minimum_length=18,
+                                               tcf_out=True),
+         [reads(1200, both, L=75, tag="f%d" % k) for k in range(3)]),
     ]
 
 

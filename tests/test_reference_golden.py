@@ -68,7 +68,7 @@ def test_annotation_report_matches_reference(oracle_run):
 
 # ---- digest-only cases: the reference's baking() (worker, parent merge, UMI levels, matrix, counters, side files)
 
-DIGEST_CASES = ["ref_case2_umi", "ref_case3_umi_dedup", "ref_case4_qiagen", "ref_case5_nextseq_cuts"]
+DIGEST_CASES = ["ref_case2_umi", "ref_case3_umi_dedup", "ref_case4_qiagen", "ref_case5_nextseq_cuts", "ref_case6_front_back_noindels"]
 
 
 def load_digest_case(name):
