@@ -1,0 +1,135 @@
+"""Seeded fuzz of the two oracle implementations against each other: random trim configurations (adapter text with
+IUPAC wildcards, 3' / 5' / both, error rate, minimum overlap, indels on / off, removal rounds, NextSeq and two-sided
+quality cut-offs, -NX, cuts, minimum length, UMI flanks, both counting modes) times reads built to provoke the search
+(adapter copies with substitutions and indels, partial adapters at the 3' end, repeats, poly-G tails, N, lower case).
+The readable Python restatement (pinned on the reference-written golden files) and the C port (what the GPU path is
+held to at scale) must give the same emitted keys read by read."""
+import numpy as np
+import pytest
+
+from mirge_b200 import params as P
+from oracle import coracle, pyoracle as po
+from tests.util import py_params
+
+B = np.array(list("ACGT"))
+IUPAC = "RYSWKMBDHVN"
+
+
+def rnd_seq(rng, n):
+    return "".join(rng.choice(B, n))
+
+
+def mutate(rng, s, p_sub, p_indel):
+    out = []
+    for c in s:
+        r = rng.random()
+        if r < p_indel / 2:
+            continue
+        if r < p_indel:
+            out.append(str(rng.choice(B)))
+        out.append(str(rng.choice(B)) if rng.random() < p_sub else c)
+    return "".join(out)
+
+
+def random_config(rng):
+    n_ad = int(rng.integers(1, 3))
+    adapters = []
+    for k in range(n_ad):
+        m = int(rng.integers(6, 33))
+        s = rnd_seq(rng, m)
+        if rng.random() < 0.3:  # a few wildcard positions
+            s = list(s)
+            for _ in range(int(rng.integers(1, 4))):
+                s[int(rng.integers(m))] = IUPAC[int(rng.integers(len(IUPAC)))]
+            s = "".join(s)
+        if rng.random() < 0.15:  # low-complexity adapter: many equally good alignments, tie rules decide
+            s = (s[:3] * 12)[:m]
+        adapters.append(("back" if (k == 0 and rng.random() < 0.8) or rng.random() < 0.5 else "front", s))
+    q = None
+    r = rng.random()
+    if r < 0.4:
+        q = str(int(rng.integers(5, 31)))
+    elif r < 0.6:
+        q = "%d,%d" % (int(rng.integers(0, 25)), int(rng.integers(0, 31)))
+    umi = None
+    if rng.random() < 0.2:
+        umi = "%d,%d" % (int(rng.integers(0, 7)), int(rng.integers(0, 7)))
+    cut = []
+    if rng.random() < 0.3:
+        cut = [int(rng.integers(1, 5))] if rng.random() < 0.5 else [int(rng.integers(1, 5)), -int(rng.integers(1, 5))]
+    return P.TrimConfig(adapters=adapters, error_rate=float(rng.choice([0.0, 0.05, 0.1, 0.12, 0.2, 0.34])),
+                        overlap=int(rng.integers(1, 8)), indels=bool(rng.random() < 0.8), times=int(rng.integers(1, 3)),
+                        nextseq_trim=int(rng.integers(10, 31)) if rng.random() < 0.3 else None, quality_cutoff=q,
+                        quality_base=33, trim_n=bool(rng.random() < 0.3), cut=cut, minimum_length=int(rng.integers(0, 25)),
+                        uniq_mol_ids=umi, count_mode="head" if rng.random() < 0.7 else "release")
+
+
+def random_reads(rng, cfg, n):
+    recs = []
+    for i in range(n):
+        L = int(rng.integers(1, 101)) if rng.random() < 0.9 else int(rng.integers(101, 160))
+        ins = rnd_seq(rng, int(rng.integers(0, 45)))
+        s = ins
+        for where, ad in cfg.adapters:
+            plain = "".join(c if c in "ACGT" else str(rng.choice(B)) for c in ad)
+            r = rng.random()
+            if r < 0.55:
+                piece = mutate(rng, plain, 0.06, 0.04 if rng.random() < 0.5 else 0.0)
+                s = piece + s if where == "front" and rng.random() < 0.7 else s + piece
+            elif r < 0.7:
+                s = s + plain[: int(rng.integers(1, len(plain) + 1))]  # partial adapter (ends the read if not padded)
+            elif r < 0.8:
+                s = s + plain + rnd_seq(rng, 3) + plain  # two occurrences: leftmost-best rule
+        if rng.random() < 0.6:
+            s = s + rnd_seq(rng, int(rng.integers(0, 40)))
+        if rng.random() < 0.15:
+            s = s + "G" * int(rng.integers(1, 30))
+        s = s[:L] if s else "A"
+        s = list(s)
+        for j in range(len(s)):
+            r = rng.random()
+            if r < 0.01:
+                s[j] = "N"
+            elif r < 0.015:
+                s[j] = s[j].lower()
+        if rng.random() < 0.1:
+            s[0] = "N"
+            s[-1] = "N"
+        s = "".join(s)
+        q = np.clip(rng.integers(20, 42, len(s)) - (np.arange(len(s)) * rng.integers(0, 40) // max(len(s), 1)), 0, 41)
+        if rng.random() < 0.1:
+            q[:] = rng.integers(0, 42, len(s))
+        recs.append("@f%d some text\n%s\n+\n%s\n" % (i, s, "".join(chr(33 + int(v)) for v in q)))
+    return "".join(recs).encode()
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_c_oracle_equals_python_oracle_on_random_configurations(seed):
+    rng = np.random.default_rng(9000 + seed)
+    cfg = random_config(rng)
+    try:
+        cp = P.build_trim_params(cfg)
+    except P.UnsupportedAdapterSpec:
+        pytest.skip("configuration the product rejects")
+    pp = py_params(cfg)
+    data = random_reads(rng, cfg, 250)
+    fq = np.frombuffer(data, dtype=np.uint8)
+    E = P.trim_slots(cp)
+    n, win, kept = coracle.trim(fq, cp)
+    recs = po.parse_fastq(data)
+    assert n == len(recs) == 250
+    pydict = {}
+    for r, (_nm, seq, qual) in enumerate(recs):
+        keys_py = [k for k, _ in po.digest_read(seq, qual, pp)]
+        keys_c = [seq[win[r, s, 0] : win[r, s, 1]] + seq[win[r, s, 2] : win[r, s, 3]] for s in range(E) if kept[r, s]]
+        assert keys_c == keys_py, (seed, cfg, r, seq, qual)
+        for k in keys_py:
+            pydict[k] = pydict.get(k, 0) + 1
+    n2, tab = coracle.digest_collapse(fq, cp, nthreads=2)
+    assert n2 == n and tab.to_dict() == pydict
+    umi = cfg.umi()
+    if umi is not None:
+        for dedup in (False, True):
+            d = po.digest_sample(data, pp, umi_dedup=dedup)
+            t2 = tab.umi_collapse(umi[0], umi[1], cfg.minimum_length, dedup)
+            assert t2.to_dict() == d.table and t2.total == d.trimmed
