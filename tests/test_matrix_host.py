@@ -1,0 +1,72 @@
+"""CPU test of digest.build_matrix (the reference's matrix build, mirge/libs/digest.py:237-261) with a stand-in for
+the device table: DataFrame contract of SURVEY.md section 8b -- index name, column order, dtypes, '' fill, row order,
+keys no sample counted are left out -- and the pickle round trip of `-spl` / `-rr` (__main__.py:101,145)."""
+import pickle
+
+import numpy as np
+import pandas as pd
+
+import mirge_b200  # noqa: F401
+from mirge_b200 import digest as DG
+
+
+class FakeTable:
+    def __init__(self, keys):
+        w = max(len(k) for k in keys)
+        self._keys = np.array([k.encode() for k in keys], dtype="S%d" % w)
+
+    def export_keys(self):
+        return self._keys
+
+
+def sample(ids, counts):
+    r = DG.SampleResult()
+    r.ids = np.array(ids, dtype=np.int64)
+    r.counts = np.array(counts, dtype=np.int64)
+    r.count, r.trimmed, r.unique = int(sum(counts)), int(sum(counts)), len(ids)
+    r.hist = np.zeros(0, dtype=np.int64)
+    return r
+
+
+def test_matrix_contract_and_pickle_round_trip(tmp_path):
+    keys = ["TTGACC", "ACGTNACGT", "ACGT", "ACGTA", "acgt", "GGGGGGGGGGGGGGGGGGGGGGGGG", "CCCC"]
+    table = FakeTable(keys)
+    s1 = sample([0, 2, 3], [5, 1, 7])
+    s2 = sample([1, 2, 4, 5], [2, 2, 9, 4])  # key 6 ("CCCC") is counted by no sample (left by an earlier run of the table)
+    df = DG.build_matrix(table, [s1, s2], ["sampleA", "sampleB"])
+    assert df.index.name == "Sequence"
+    assert list(df.columns) == ["annotFlag"] + DG.INITIAL_FLAGS + ["sampleA", "sampleB"]
+    # rows: byte-wise lexicographic (what pandas' outer join of the per-sample frames gives), unseen keys dropped
+    assert list(df.index) == sorted(k for k in keys if k != "CCCC")
+    assert df.loc["ACGT", ["sampleA", "sampleB"]].tolist() == [1, 2]
+    assert df.loc["acgt", ["sampleA", "sampleB"]].tolist() == [0, 9]
+    assert df.loc["TTGACC", ["sampleA", "sampleB"]].tolist() == [5, 0]
+    assert str(df["annotFlag"].dtype) == "int64" and (df["annotFlag"] == 0).all()
+    assert all(str(df[c].dtype) == "int64" for c in ("sampleA", "sampleB"))
+    assert all((df[c] == "").all() for c in DG.INITIAL_FLAGS)
+    assert int(df["sampleA"].sum()) == 13 and int(df["sampleB"].sum()) == 17
+    # -spl / -rr: DataFrame and the accessories tuple survive pickling unchanged
+    p = tmp_path / "collapsed.pkl"
+    df.to_pickle(p)
+    back = pd.read_pickle(p)
+    assert back.equals(df) and list(back.columns) == list(df.columns) and back.index.name == "Sequence"
+    acc = ({"sampleA": 13}, {"sampleA": 13}, {"sampleA": 3}, ["/x/sampleA.fastq"], ["sampleA"])
+    with open(tmp_path / "collapsed_accessories.pkl", "wb") as f:
+        pickle.dump(acc, f)
+    assert pickle.load(open(tmp_path / "collapsed_accessories.pkl", "rb")) == acc
+    # the annotFlag split + to_csv of __main__.py:164-173 works on it
+    df.loc["ACGT", "annotFlag"] = 1
+    df.loc["ACGT", "exact miRNA"] = "hsa-miR-1"
+    mapped, unmapped = df[df.annotFlag.eq(1)], df[df.annotFlag.eq(0)]
+    mapped.to_csv(tmp_path / "mapped.csv")
+    assert (tmp_path / "mapped.csv").read_text().splitlines()[0].startswith("Sequence,annotFlag,exact miRNA,")
+    assert len(mapped) == 1 and len(unmapped) == 5
+
+
+def test_empty_run_gives_an_empty_frame_with_the_columns():
+    class Empty:
+        def export_keys(self):
+            return np.zeros(0, dtype="S1")
+
+    df = DG.build_matrix(Empty(), [sample([], [])], ["s"])
+    assert len(df) == 0 and list(df.columns) == ["annotFlag"] + DG.INITIAL_FLAGS + ["s"] and df.index.name == "Sequence"
