@@ -1,6 +1,6 @@
-// adapter_search.cuh -- the adapter search of the trim kernels (cutadapt Aligner.locate, 3P):
-// the device view of the trim parameters, the literal full-column DP (locate) and the bit-parallel search with
-// traceback on demand (locate_fast).  Included by trim.cu; tests/test_adapter_search_host.py compiles the same text
+// adapter_search.cuh -- the per-read arithmetic of the trim kernels that restates cutadapt (3P):
+// the device view of the trim parameters, the literal full-column DP (locate), the bit-parallel search with traceback
+// on demand (locate_fast) and the NextSeq / BWA quality scans.  Included by trim.cu; tests/test_adapter_search_host.py compiles the same text
 // for the host (ADAPTER_SEARCH_HOST: one thread, CUDA intrinsics replaced by the few lines below) and holds the two
 // searches against each other and against the oracle on adversarial inputs.
 #pragma once
@@ -616,4 +616,35 @@ __device__ __forceinline__ int locate_fast(const int a, const RV read, const int
   out.matches = b_m;
   out.errors = b_c;
   return 1;
+}
+
+// ------------------------------------------------------------------ quality trimming --------
+
+__device__ __forceinline__ int nextseq_trim_index(const uint8_t *seq, const uint8_t *qual, int len, int cutoff, int base) {
+  int s = 0, max_qual = 0, max_i = len;
+  for (int i = len - 1; i >= 0; --i) {
+    int q = (int)qual[i] - base;
+    if (seq[i] == 'G') q = cutoff - 1;
+    s += cutoff - q;
+    if (s < 0) break;
+    if (s > max_qual) { max_qual = s; max_i = i; }
+  }
+  return max_i;
+}
+
+__device__ __forceinline__ void quality_trim_index(const uint8_t *qual, int len, int q5, int q3, int base, int &start, int &stop) {
+  int s = 0, max_qual = 0;
+  start = 0; stop = len;
+  for (int i = 0; i < len; ++i) {
+    s += q5 - ((int)qual[i] - base);
+    if (s < 0) break;
+    if (s > max_qual) { max_qual = s; start = i + 1; }
+  }
+  max_qual = 0; s = 0;
+  for (int i = len - 1; i >= 0; --i) {
+    s += q3 - ((int)qual[i] - base);
+    if (s < 0) break;
+    if (s > max_qual) { max_qual = s; stop = i; }
+  }
+  if (start >= stop) { start = 0; stop = 0; }
 }

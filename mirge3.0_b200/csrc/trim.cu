@@ -50,37 +50,6 @@ extern "C" int mirge_set_trim_params(mirge_ctx *ctx, const mirge_trim_params *p)
   return MIRGE_OK;
 }
 
-// ------------------------------------------------------------------ quality trimming --------
-
-__device__ __forceinline__ int nextseq_trim_index(const uint8_t *seq, const uint8_t *qual, int len, int cutoff, int base) {
-  int s = 0, max_qual = 0, max_i = len;
-  for (int i = len - 1; i >= 0; --i) {
-    int q = (int)qual[i] - base;
-    if (seq[i] == 'G') q = cutoff - 1;
-    s += cutoff - q;
-    if (s < 0) break;
-    if (s > max_qual) { max_qual = s; max_i = i; }
-  }
-  return max_i;
-}
-
-__device__ __forceinline__ void quality_trim_index(const uint8_t *qual, int len, int q5, int q3, int base, int &start, int &stop) {
-  int s = 0, max_qual = 0;
-  start = 0; stop = len;
-  for (int i = 0; i < len; ++i) {
-    s += q5 - ((int)qual[i] - base);
-    if (s < 0) break;
-    if (s > max_qual) { max_qual = s; start = i + 1; }
-  }
-  max_qual = 0; s = 0;
-  for (int i = len - 1; i >= 0; --i) {
-    s += q3 - ((int)qual[i] - base);
-    if (s < 0) break;
-    if (s > max_qual) { max_qual = s; stop = i; }
-  }
-  if (start >= stop) { start = 0; stop = 0; }
-}
-
 // AdapterCutter._best_match: most matches, then fewer errors, first adapter wins ties.
 // returns the index of the winning adapter, -1 for none, -2 when the search was deferred (DEFER only)
 template <int MAXM, bool FAST, bool DEFER>

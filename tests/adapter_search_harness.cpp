@@ -62,3 +62,11 @@ extern "C" int hs_locate(int mode, int a, const uint8_t *read, int len, int star
   out[0] = mt.rstart; out[1] = mt.rstop; out[2] = mt.matches; out[3] = mt.errors;
   return rc;
 }
+
+// the two quality scans (cutadapt qualtrim.pyx), as the trim kernels call them
+extern "C" int hs_nextseq(const uint8_t *seq, const uint8_t *qual, int len, int cutoff, int base) {
+  return nextseq_trim_index(seq, qual, len, cutoff, base);
+}
+extern "C" void hs_quality(const uint8_t *qual, int len, int q5, int q3, int base, int *start, int *stop) {
+  quality_trim_index(qual, len, q5, q3, base, *start, *stop);
+}

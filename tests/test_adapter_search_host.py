@@ -162,3 +162,36 @@ def test_generic_search_with_front_adapters_wildcards_and_no_indels(hs, seed):
         reads += [mutate(rng, ad2, 0.05, 0.02, 0.02) + rnd(rng, 30) for _ in range(10)]  # 5' adapter at the start
         run_case(hs, cfg, [r for r in reads if r], stats)
     assert stats.get(("mode", 0), 0) > 100 and stats.get("matches", 0) > 20, stats
+
+
+def test_quality_scans_equal_the_oracle(hs):
+    """nextseq_trim_index / quality_trim_index of the kernels on random and adversarial
+    quality strings: ties of the running maximum, scans that never go negative, empty reads, both Phred offsets."""
+    hs.hs_nextseq.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+    hs.hs_quality.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    rng = np.random.default_rng(77)
+    n = 0
+    for it in range(6000):
+        L = int(rng.integers(0, 120))
+        base = 33 if rng.random() < 0.8 else 64
+        mode = it % 5
+        if mode == 0:
+            q = rng.integers(0, 42, L)
+        elif mode == 1:  # decaying qualities
+            q = np.clip(38 - (np.arange(L) * rng.integers(0, 50) // max(L, 1)) + rng.integers(-5, 6, L), 0, 41)
+        elif mode == 2:  # two levels around the cut-off: many ties
+            q = rng.choice([19, 20, 21], L)
+        elif mode == 3:
+            q = np.full(L, int(rng.integers(0, 42)))
+        else:
+            q = rng.integers(0, 94 - (base - 33), L)  # any printable byte
+        qual = "".join(chr(base + int(v)) for v in q)
+        seq = "".join(rng.choice(np.array(list("ACGTGGN")), L))
+        cutoff = int(rng.integers(0, 41))
+        q5 = int(rng.integers(0, 41)) if rng.random() < 0.5 else 0
+        assert hs.hs_nextseq(seq.encode(), qual.encode(), L, cutoff, base) == po.nextseq_trim_index(seq, qual, cutoff, base), (seq, qual, cutoff, base)
+        s, e = C.c_int(-1), C.c_int(-1)
+        hs.hs_quality(qual.encode(), L, q5, cutoff, base, C.byref(s), C.byref(e))
+        assert (s.value, e.value) == tuple(po.quality_trim_index(qual, q5, cutoff, base)), (qual, q5, cutoff, base)
+        n += 1
+    assert n == 6000
