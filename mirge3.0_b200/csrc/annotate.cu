@@ -183,7 +183,8 @@ struct WarpScratch {
   unsigned long long best[32];
 };
 
-// bases [a, b) of seed piece pi: a = pi * R / np without an integer division (np = seed mismatches + 1 <= 4, R < 2^16)
+// bases [a, b) of seed piece pi: a = pi * R / np without an integer division (np = seed mismatches + 1 <= 4; the
+// multiply-shift for np == 3 is exact while pi * R < 2^17, and R <= MIRGE_MAX_READ_LEN = 512)
 __device__ __forceinline__ int piece_bound(int pi, int R, int np) {
   const uint32_t x = (uint32_t)(pi * R);
   return np == 1 ? (int)x : np == 2 ? (int)(x >> 1) : np == 3 ? (int)((x * 43691u) >> 17) : (int)(x >> 2);
