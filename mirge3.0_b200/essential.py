@@ -55,7 +55,7 @@ def check_dependencies(args, runlogFile) -> None:
             print(problem)
             outlog.write(problem + "\n")
             outlog.close()
-            exit()
+            sys.exit()  # the reference's probe ends with exit() after its message (miRgeEssential.py:22, :41)
         args.bowtieVersion = "True"
         args.cutadaptVersion = CUTADAPT_SEMANTICS
         lines.append("bowtie version: %s (semantics restated on the GPU; no bowtie process is run)" % BOWTIE_SEMANTICS)
