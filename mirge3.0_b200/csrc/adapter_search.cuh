@@ -1,37 +1,11 @@
 // adapter_search.cuh -- the per-read arithmetic of the trim kernels that restates cutadapt (3P):
 // the device view of the trim parameters, the literal full-column DP (locate), the bit-parallel search with traceback
 // on demand (locate_fast) and the NextSeq / BWA quality scans.  Included by trim.cu; tests/test_adapter_search_host.py compiles the same text
-// for the host (ADAPTER_SEARCH_HOST: one thread, CUDA intrinsics replaced by the few lines below) and holds the two
+// for the host (ADAPTER_SEARCH_HOST: one thread, CUDA intrinsics replaced by host_shims.h) and holds the two
 // searches against each other and against the oracle on adversarial inputs.
 #pragma once
 #ifdef ADAPTER_SEARCH_HOST
-#include <stdint.h>
-#include <stdio.h>
-#include <string.h>
-
-#include <algorithm>
-
-#include "../../include/mirge_b200.h"
-#define __device__
-#define __host__
-#define __forceinline__ inline
-#define __noinline__
-using std::max;
-using std::min;
-static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
-static inline int __clz(int x) { return x ? __builtin_clz((uint32_t)x) : 32; }
-static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
-static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
-  sh &= 31u;
-  return sh ? (lo >> sh) | (hi << (32u - sh)) : lo;
-}
-static inline unsigned __activemask() { return 1u; }
-static inline void __syncwarp(unsigned = 0xffffffffu) {}
-static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }
-static inline uint32_t base_code_upper(uint32_t c) {  // common.cuh
-  c &= ~0x20u;
-  return (c == 'A') ? 0u : (c == 'C') ? 1u : (c == 'G') ? 2u : (c == 'T') ? 3u : 4u;
-}
+#include "host_shims.h"
 #else
 #include "common.cuh"
 #endif
