@@ -155,7 +155,7 @@ def test_hot_key_contention(dev):
     assert got["TGAGGTAGTAGGTTGTATAGTT"] >= 200000
 
 
-@pytest.mark.parametrize("cfg_id", [1, 2, 3])
+@pytest.mark.parametrize("cfg_id", [1, 2, 3, 4, 5])
 def test_synthetic_workloads_match_oracle(dev, cfg_id):
     """The benchmark's own read model at 300k reads: windows and table bit-exact."""
     from mirge_b200 import device as D

@@ -1,12 +1,7 @@
 """GPU twin of tests/test_oracle_fuzz.py: the product trim + collapse path against the C oracle on random trim
 configurations, in all three kernel modes.
 
-STATUS: written after round 1's GPU budget was spent, so it has not run on a device yet.  Until it has, it only runs
-when MIRGE_B200_GPU_FUZZ=1 is set (first GPU call of the next round: `MIRGE_B200_GPU_FUZZ=1 pytest
-tests/test_gpu_zz_fuzz.py`); once green, drop the gate.  The file name sorts it after the other GPU tests, so a device
-fault here cannot take them down with it."""
-import os
-
+The file name sorts it after the other GPU tests, so a device fault here cannot take them down with it."""
 import numpy as np
 import pytest
 
@@ -14,8 +9,7 @@ from mirge_b200 import params as P
 from oracle import coracle
 from tests.test_oracle_fuzz import random_config, random_reads
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MIRGE_B200_GPU_FUZZ") != "1", reason="not yet validated on a device (see module docstring)")]
+pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 
