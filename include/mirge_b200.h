@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MIRGE_ABI_VERSION 1
+#define MIRGE_ABI_VERSION 2
 
 #define MIRGE_OK 0
 #define MIRGE_ERR_CUDA (-1)     /* CUDA runtime error (message has the cudaError string) */
@@ -194,7 +194,14 @@ int mirge_line_index(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, co
  *   d_win[4e..4e+3] = (start, stop, ustart, ustop): emitted text = read[start:stop] + read[ustart:ustop]
  *   d_key_off[e]    = word offset of the packed key in d_keys, or 0xFFFFFFFF when the slot is not
  *                     counted (length filter, digest.py:348,362,368).
- * d_trim_ctrl (8 x u64, zeroed by the caller): [0] key words used [1] emitted keys [2] error flags
+ * d_win / d_key_off may both be NULL when only the insert list is wanted (the product path).
+ * Insert list (d_ins, u64[ins_capacity >= n_records * slots], or NULL): one entry per DISTINCT key a read emits
+ * -- low 32 bits = word offset of the key, high 32 bits = number of consecutive slots of that read that carry
+ * this text (digest.py:354-373 counts the same string once per modifier) -- in no particular order;
+ * d_trim_ctrl[0] >> 36 counts the entries.  mirge_collapse_insert_list consumes it.
+ * d_trim_ctrl (16 x u64, zeroed by the caller): [0] key words used (low 36 bits; the caller may preset them to the
+ * first free word of d_keys) | insert-list entries << 36 (records x slots must be < 2^28 per call)
+ * [1] emitted keys [2] error flags
  * [3] first malformed record, [4] key words of all emitted keys (a slot whose text repeats the previous slot's
  * shares that slot's key: same d_key_off, no space of its own), [5] reads left to the whole-pipeline second pass, [6] reads whose adapter search
  * ran the bit-vector DP, [7] of those, the ones that needed cost columns.
@@ -205,7 +212,8 @@ int mirge_line_index(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, co
 uint64_t mirge_trim_scratch_bytes(uint64_t n_records);
 int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, const uint32_t *d_line_start,
                uint64_t n_records, uint16_t *d_win, uint32_t *d_key_off, uint32_t *d_keys,
-               uint64_t keys_capacity_words, uint64_t *d_trim_ctrl, void *d_scratch, void *stream);
+               uint64_t keys_capacity_words, uint64_t *d_trim_ctrl, void *d_scratch, uint64_t *d_ins,
+               uint64_t ins_capacity, void *stream);
 
 /* Kernel selection for mirge_trim: 0 = automatic (split bit-parallel pipeline when every adapter is a 3'
  * adapter with indels and <= 32 nt, else the generic full-DP kernel), 1 = always generic, 2 = bit-parallel
@@ -215,15 +223,14 @@ int mirge_trim_mode(mirge_ctx *ctx, int mode);
 
 /* ---- stage 2: collapse (digest.py:141-163,164-205,237-245) --------------------------------- */
 int mirge_table_reset(mirge_ctx *ctx, const mirge_table *t, void *stream);
-/* completeDict[key] += 1 for every emitted key of a batch.  d_deferred: u32[2 * n_slots] scratch. */
-int mirge_collapse_insert(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_keys,
-                          const uint32_t *d_key_off, uint64_t n_slots, uint32_t *d_deferred,
-                          void *stream);
-/* The same when the trim kernel wrote the keys straight into the table's arena (mirge_trim called with
- * d_keys = t->d_arena and d_trim_ctrl[0] preset to the arena words in use): the first occurrence of a key
- * becomes the table's copy, nothing is moved.  d_key_off holds arena word offsets. */
-int mirge_collapse_insert_inplace(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_key_off,
-                                  uint64_t n_slots, uint32_t *d_deferred, void *stream);
+/* completeDict[key] += count for the n_items (offset, count) entries of a batch's insert list (mirge_trim): the parent
+ * merge of digest.py:141-163.  d_keys = the buffer the list's offsets point into; when it is the table's own arena
+ * (mirge_trim called with d_keys = t->d_arena and d_trim_ctrl[0] preset to the arena words in use) the first
+ * occurrence of a key becomes the table's copy where it lies, otherwise new keys are copied into the arena.
+ * d_scratch: u32[2 * n_items].  Dense key ids are handed out by a second, streaming kernel (no id atomic on the
+ * chain of dependent accesses of an insert). */
+int mirge_collapse_insert_list(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_keys, const uint64_t *d_ins,
+                               uint64_t n_items, uint32_t *d_scratch, void *stream);
 /* Merge (key, count) records: d_rec = [count][key words...] back to back, d_rec_off[i] = word
  * offset of record i.  Used by the owner side of the hash-partitioned exchange. */
 int mirge_collapse_merge(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_rec,
@@ -302,14 +309,14 @@ int mirge_annotate_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_r
                          const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round,
                          uint64_t *d_hit, void *stream);
 
-/* The same for several consecutive rounds in one launch (libs[i] / policies[i] = round i of the call):
- * every key is read once and leaves at the first round that hits it.  At most 10 rounds per call.
- * d_order_scratch: NULL, or u32[MIRGE_ANNOTATE_ORDER_BINS + n_keys] scratch; with it the sequences are
- * processed grouped by length (homogeneous warps), which changes the speed, never the result. */
-#define MIRGE_ANNOTATE_ORDER_BINS 1024
+/* The same for several consecutive rounds (libs[i] / policies[i] = round i of the call).  At most 10 rounds per call.
+ * form 0: one thread per sequence runs all rounds (the sequence leaves at the first round that hits it).
+ * form 1 (the product path): a CTA owns a tile of 2048 sequences; a filter phase evaluates the seed-piece prefix
+ * filters of all rounds into a round mask per sequence, then, round by round, the sequences that still need a search
+ * are compacted in shared memory and searched with full, homogeneous warps.  Same results. */
 int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, const mirge_round_policy *policies,
                           int n_rounds, const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round,
-                          uint64_t *d_hit, uint32_t *d_order_scratch, void *stream);
+                          uint64_t *d_hit, int form, void *stream);
 
 /* Every hit of the best stratum for the sequences d_ids[0..n_ids) that `policy`'s round annotated (bowtie
  * -a --best --strata, rounds 2 and 3; feeds the per-round SAM files of -trf / -bam, manifoldAlign.py:20-62).

@@ -11,7 +11,6 @@ MAX_ADAPTERS = 4
 MAX_ADAPTER_LEN = 64
 MAX_MODS = 8
 MAX_READ_LEN = 512
-ANNOTATE_ORDER_BINS = 1024  # MIRGE_ANNOTATE_ORDER_BINS
 LIB_PAD_WORDS = 40  # MIRGE_LIB_PAD_WORDS
 
 MOD_NEXTSEQ, MOD_QUALITY, MOD_ADAPTER, MOD_NEND, MOD_CUT = 1, 2, 3, 4, 5
@@ -104,6 +103,8 @@ class RoundPolicy(C.Structure):
     ]
 
 
+ABI_VERSION = 2  # MIRGE_ABI_VERSION of include/mirge_b200.h
+
 # name -> (restype, argtypes); every symbol include/mirge_b200.h declares
 _P = C.c_void_p
 _U64 = C.c_uint64
@@ -119,11 +120,10 @@ SYMBOLS = {
     "mirge_tokenise_sync": (C.c_int, [_P, _P, _U64, C.c_int, _P, _PU64, _PU64, _P]),
     "mirge_line_index": (C.c_int, [_P, _P, _U64, _P, _P, _U64, _P]),
     "mirge_trim_scratch_bytes": (_U64, [_U64]),
-    "mirge_trim": (C.c_int, [_P, _P, _U64, _P, _U64, _P, _P, _P, _U64, _P, _P, _P]),
+    "mirge_trim": (C.c_int, [_P, _P, _U64, _P, _U64, _P, _P, _P, _U64, _P, _P, _P, _U64, _P]),
     "mirge_trim_mode": (C.c_int, [_P, C.c_int]),
     "mirge_table_reset": (C.c_int, [_P, C.POINTER(Table), _P]),
-    "mirge_collapse_insert": (C.c_int, [_P, C.POINTER(Table), _P, _P, _U64, _P, _P]),
-    "mirge_collapse_insert_inplace": (C.c_int, [_P, C.POINTER(Table), _P, _U64, _P, _P]),
+    "mirge_collapse_insert_list": (C.c_int, [_P, C.POINTER(Table), _P, _P, _U64, _P, _P]),
     "mirge_collapse_merge": (C.c_int, [_P, C.POINTER(Table), _P, _P, _U64, _P, _P]),
     "mirge_collapse_merge_inplace": (C.c_int, [_P, C.POINTER(Table), _P, _U64, _P, _P]),
     "mirge_table_rehash": (C.c_int, [_P, C.POINTER(Table), C.POINTER(Table), _P]),
@@ -147,7 +147,7 @@ SYMBOLS = {
     "mirge_lib_filter": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     "mirge_annotate_rounds": (
         C.c_int,
-        [_P, C.POINTER(Library), C.POINTER(RoundPolicy), C.c_int, C.POINTER(Table), _U64, _P, _P, _P, _P],
+        [_P, C.POINTER(Library), C.POINTER(RoundPolicy), C.c_int, C.POINTER(Table), _U64, _P, _P, C.c_int, _P],
     ),
     "mirge_annotate_allhits": (
         C.c_int,
@@ -180,7 +180,7 @@ def load_library(path: str = None):
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.mirge_abi_version() != 1:
+    if lib.mirge_abi_version() != ABI_VERSION:
         raise RuntimeError("mirge_b200: ABI version mismatch")
     if path is None:
         _lib = lib

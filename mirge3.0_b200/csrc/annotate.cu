@@ -217,13 +217,12 @@ __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const
 // CTAs 17.8 ms -- the kernel lives on warps in flight, up to the point where spills eat the gain.
 __global__ void __launch_bounds__(ANN_THREADS, 10)
 annotate_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_keys, uint8_t *__restrict__ annot_round,
-                uint64_t *__restrict__ hit, const uint32_t *__restrict__ order) {
+                uint64_t *__restrict__ hit) {
   __shared__ WarpScratch s_ws[ANN_THREADS / 32];
   const uint64_t slot = (uint64_t)blockIdx.x * ANN_THREADS + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool in_range = slot < n_keys;
-  // with `order` the threads of a warp hold sequences of the same length (see order_* kernels below)
-  const uint64_t id = (in_range && order) ? order[slot] : slot;
+  const uint64_t id = slot;
   uint32_t qw[QW_MAX], qnx[QW_MAX];
   KeyView kv;
   kv.pay = kv.exc = nullptr; kv.len = kv.nexc = 0;
@@ -335,49 +334,142 @@ allhits_kernel(mirge_library lib, mirge_round_policy pol, mirge_table t, const u
   if (!fill) counts[i] = k;
 }
 
-// ---- sequences ordered by length (counting sort) -----------------------------------------------------------
-// Key ids are handed out in emission order, so a warp would hold a mix of short, library-derived sequences
-// (several verified candidates per round) and long ones that no library contains (a few look-ups per round) and
-// run at the pace of its busiest lane.  Grouping by length makes warps homogeneous: same rounds selected, same
-// query word count, similar candidate work.  order[] = key ids, shortest first; bins[] = MIRGE_MAX_READ_LEN + 2
-// cursors.  The order inside a bin is arbitrary; results do not depend on it.
-#define ORDER_BINS (MIRGE_MAX_READ_LEN + 2)
-static_assert(ORDER_BINS <= MIRGE_ANNOTATE_ORDER_BINS, "scratch layout");
+// ---- tiled rounds: per-CTA filter phase -> per-round compaction in shared memory -> full-warp search -----------
+// In the fused kernel above a warp runs nine rounds at the pace of its busiest lane, and most lanes hold sequences no
+// library contains (HEAD counting keeps the untrimmed reads): per round they evaluate their seed pieces' prefix
+// filters, find nothing and wait.  Here a CTA owns a tile of TILE_KEYS consecutive sequences.  Phase A evaluates
+// the prefix filters of ALL rounds for every sequence of the tile -- no search, no dependent index look-ups -- into a
+// per-sequence round mask in shared memory.  Then, round by round, the CTA compacts the sequences that round still
+// has to search (mask bit set, and not annotated by an earlier round) into a shared-memory list and searches them
+// with full warps: every lane holds a sequence with at least one piece the library may contain, all lanes use the
+// same library and policy.  Nothing leaves the CTA between the phases: no global lists, no global atomics, and the
+// order of the rounds is the CTA's own program order.  The masks are a superset (phase A ignores what earlier rounds
+// will find; the search re-checks everything), so results cannot differ from the fused form.
+#define TILE_KEYS 2048
+static_assert(TILE_KEYS % ANN_THREADS == 0, "tile must be a whole number of CTA sweeps");
 
-__global__ void __launch_bounds__(256) order_hist_kernel(mirge_table t, uint64_t n_keys, uint32_t *__restrict__ bins) {
-  __shared__ uint32_t s_bins[ORDER_BINS];
-  for (int b = threadIdx.x; b < ORDER_BINS; b += 256) s_bins[b] = 0;
-  __syncthreads();
-  for (uint64_t id = (uint64_t)blockIdx.x * 256 + threadIdx.x; id < n_keys; id += (uint64_t)gridDim.x * 256) {
-    const uint32_t len = min(key_len(t.d_arena[t.d_key_ref[id]]), (uint32_t)(ORDER_BINS - 1));
-    atomicAdd(&s_bins[len], 1u);
+// rounds (bit ri of the result) in which the key may have a candidate; state = annotation before this call
+__device__ __forceinline__ uint32_t round_mask(const RoundSet &rs, const KeyView &kv, uint32_t state) {
+  uint32_t qw[QW_MAX], qnx[QW_MAX];
+  int cur_qs = -1, cur_qe = -1, tlen = -1;
+  const int len = kv.len;
+  const bool has_exc = kv.nexc > 0;
+  uint32_t mask = 0;
+  for (int ri = 0; ri < rs.n; ++ri) {
+    const mirge_round_policy &pol = rs.pol[ri];
+    const mirge_library &lib = rs.lib[ri];
+    bool active;
+    if (pol.select == MIRGE_SELECT_LEN_LT26) active = len < 26;
+    else if (pol.select == MIRGE_SELECT_LEN_GT25) active = len > 25;
+    else active = state == 0xFF;  // annotated before this call: stays annotated
+    if (!active) continue;
+    int qs, qe;
+    if (!round_window(kv, pol, tlen, qs, qe)) continue;
+    const int L = qe - qs;
+    if (qs != cur_qs || qe != cur_qe) {
+      build_query(kv, qs, qe, qw, qnx);
+      cur_qs = qs;
+      cur_qe = qe;
+    }
+    const int R = pol.seed_len == 0 ? L : min(pol.seed_len, L);
+    const int np = pol.seed_mm + 1;
+    const int nw = (L + 15) >> 4;
+    bool pass = false;
+    if (R < MIN_SEED * np) {
+      pass = true;  // exhaustive scan in the search
+    } else {
+      for (int pi = 0; pi < np; ++pi) {
+        const int a = piece_bound(pi, R, np), b = piece_bound(pi + 1, R, np);
+        const int s = min(16, b - a);
+        if (has_exc && query_has_n(qnx, a, b)) continue;
+        if (lib.filter_bases && (uint32_t)s >= lib.filter_bases) {
+          const uint32_t span = (s == 16) ? 0u : ((1u << (2 * (16 - s))) - 1u);
+          const uint32_t k_lo = query_kmer16(qw, a, nw) & ~span;
+          const uint32_t fi = lib.filter_bases >= 16 ? k_lo : (k_lo >> (32 - 2 * lib.filter_bases));
+          pass |= ((lib.d_filter[fi >> 5] >> (fi & 31)) & 1u) != 0u;
+        } else {
+          pass = true;  // piece shorter than the filter prefix: look it up
+        }
+      }
+    }
+    if (pass) mask |= 1u << ri;
   }
-  __syncthreads();
-  for (int b = threadIdx.x; b < ORDER_BINS; b += 256)
-    if (s_bins[b]) atomicAdd(&bins[b], s_bins[b]);
+  return mask;
 }
 
-__global__ void order_scan_kernel(uint32_t *bins) {  // one thread: 514 bins
-  uint32_t run = 0;
-  for (int b = 0; b < ORDER_BINS; ++b) {
-    const uint32_t c = bins[b];
-    bins[b] = run;
-    run += c;
-  }
-}
+struct TileShared {
+  uint16_t mask[TILE_KEYS];
+  uint16_t list[TILE_KEYS];
+  uint8_t state[TILE_KEYS];
+  uint32_t count;
+  WarpScratch ws[ANN_THREADS / 32];
+};
 
-__global__ void __launch_bounds__(256) order_scatter_kernel(mirge_table t, uint64_t n_keys, uint32_t *__restrict__ bins,
-                                                            uint32_t *__restrict__ order) {
-  const uint64_t id = (uint64_t)blockIdx.x * 256 + threadIdx.x;
-  if (id >= n_keys) return;
-  const uint32_t len = min(key_len(t.d_arena[t.d_key_ref[id]]), (uint32_t)(ORDER_BINS - 1));
-  // one atomic per group of lanes with the same length
-  const unsigned peers = __match_any_sync(__activemask(), len);
-  const int leader = __ffs(peers) - 1, lane = threadIdx.x & 31;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(&bins[len], (uint32_t)__popc(peers));
-  base = __shfl_sync(peers, base, leader);
-  order[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)id;
+__global__ void __launch_bounds__(ANN_THREADS, 8)
+annotate_tile_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_keys, uint8_t *__restrict__ annot_round,
+                     uint64_t *__restrict__ hit) {
+  __shared__ TileShared sh;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint64_t tile0 = (uint64_t)blockIdx.x * TILE_KEYS;
+  const uint32_t n_tile = (uint32_t)min((uint64_t)TILE_KEYS, n_keys - tile0);
+  // phase A: round masks
+  for (uint32_t k = tid; k < n_tile; k += ANN_THREADS) {
+    const uint64_t id = tile0 + k;
+    const uint32_t state = annot_round[id];
+    const KeyView kv = key_view(t.d_arena + t.d_key_ref[id]);
+    sh.mask[k] = (uint16_t)round_mask(rs, kv, state);
+    sh.state[k] = (uint8_t)state;
+  }
+  if (tid == 0) sh.count = 0;
+  __syncthreads();
+  for (int ri = 0; ri < rs.n; ++ri) {
+    const mirge_round_policy &pol = rs.pol[ri];
+    // the sequences this round searches
+    for (uint32_t k0 = 0; k0 < TILE_KEYS; k0 += ANN_THREADS) {
+      const uint32_t k = k0 + tid;
+      bool p = k < n_tile && ((sh.mask[k] >> ri) & 1u);
+      if (p && pol.select == MIRGE_SELECT_UNANNOTATED) p = sh.state[k] == 0xFF;
+      const unsigned bal = __ballot_sync(0xffffffffu, p);
+      if (bal) {
+        const int leader = __ffs(bal) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&sh.count, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (p) sh.list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)k;
+      }
+    }
+    __syncthreads();
+    const uint32_t cnt = sh.count;
+    for (uint32_t base = warp * 32; base < cnt; base += ANN_THREADS) {  // uniform per warp
+      const uint32_t idx = base + lane;
+      bool active = idx < cnt;
+      const uint32_t k = active ? sh.list[idx] : 0u;
+      const uint64_t id = tile0 + k;
+      uint32_t qw[QW_MAX], qnx[QW_MAX];
+      KeyView kv;
+      kv.pay = kv.exc = nullptr; kv.len = kv.nexc = 0;
+      int L = 0, tlen = -1;
+      if (active) {
+        kv = key_view(t.d_arena + t.d_key_ref[id]);
+        int qs, qe;
+        active = round_window(kv, pol, tlen, qs, qe);  // (true: the mask bit says so)
+        if (active) {
+          L = qe - qs;
+          build_query(kv, qs, qe, qw, qnx);
+        }
+      }
+      bool republish = true;
+      const uint64_t best = search_round(rs.lib[ri], pol, active, qw, qnx, L, kv.nexc > 0, sh.ws[warp], republish, lane);
+      if (active && best != MIRGE_NO_HIT) {
+        sh.state[k] = (uint8_t)pol.round;
+        annot_round[id] = (uint8_t)pol.round;
+        hit[id] = best;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) sh.count = 0;
+    __syncthreads();
+  }
 }
 
 static int check_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_round_policy *policy) {
@@ -396,10 +488,11 @@ static int check_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_rou
 
 extern "C" int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, const mirge_round_policy *policies, int n_rounds,
                                      const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round, uint64_t *d_hit,
-                                     uint32_t *d_order_scratch, void *stream_) {
+                                     int form, void *stream_) {
   if (!ctx) return MIRGE_ERR_ARG;
   if (!libs || !policies || !t || !d_annot_round || !d_hit) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: null argument");
   if (n_keys > 0xFFFFFFFFull) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: more than 2^32 sequences in one call");
+  if (form != 0 && form != 1) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: unknown form %d", form);
   if (n_rounds < 0 || n_rounds > MAX_ROUNDS) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: at most %d rounds per call", MAX_ROUNDS);
   if (n_keys == 0 || n_rounds == 0) return MIRGE_OK;
   RoundSet rs;
@@ -415,20 +508,12 @@ extern "C" int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, 
   if (rs.n == 0) return MIRGE_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
-  const uint32_t *order = nullptr;
-  if (d_order_scratch) {
-    uint32_t *bins = d_order_scratch, *ord = d_order_scratch + MIRGE_ANNOTATE_ORDER_BINS;
-    MIRGE_CUDA(ctx, cudaMemsetAsync(bins, 0, ORDER_BINS * sizeof(uint32_t), stream));
-    uint64_t hg = (n_keys + 255) / 256;
-    if (hg > (uint64_t)ctx->sm_count * 8) hg = (uint64_t)ctx->sm_count * 8;
-    order_hist_kernel<<<(unsigned)hg, 256, 0, stream>>>(*t, n_keys, bins);
-    order_scan_kernel<<<1, 1, 0, stream>>>(bins);
-    order_scatter_kernel<<<(unsigned)((n_keys + 255) / 256), 256, 0, stream>>>(*t, n_keys, bins, ord);
-    MIRGE_LAUNCH_CHECK(ctx, "order kernels");
-    order = ord;
+  if (form == 1) {
+    annotate_tile_kernel<<<(unsigned)((n_keys + TILE_KEYS - 1) / TILE_KEYS), ANN_THREADS, 0, stream>>>(rs, *t, n_keys, d_annot_round, d_hit);
+    MIRGE_LAUNCH_CHECK(ctx, "annotate_tile_kernel");
+    return MIRGE_OK;
   }
-  annotate_kernel<<<(unsigned)((n_keys + ANN_THREADS - 1) / ANN_THREADS), ANN_THREADS, 0, stream>>>(rs, *t, n_keys, d_annot_round, d_hit,
-                                                                                                  order);
+  annotate_kernel<<<(unsigned)((n_keys + ANN_THREADS - 1) / ANN_THREADS), ANN_THREADS, 0, stream>>>(rs, *t, n_keys, d_annot_round, d_hit);
   MIRGE_LAUNCH_CHECK(ctx, "annotate_kernel");
   return MIRGE_OK;
 }
@@ -437,7 +522,7 @@ extern "C" int mirge_annotate_round(mirge_ctx *ctx, const mirge_library *lib, co
                                     uint64_t n_keys, uint8_t *d_annot_round, uint64_t *d_hit, void *stream_) {
   if (!ctx) return MIRGE_ERR_ARG;
   if (!lib || !policy) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: null argument");
-  return mirge_annotate_rounds(ctx, lib, policy, 1, t, n_keys, d_annot_round, d_hit, nullptr, stream_);
+  return mirge_annotate_rounds(ctx, lib, policy, 1, t, n_keys, d_annot_round, d_hit, 0, stream_);
 }
 
 extern "C" int mirge_annotate_allhits(mirge_ctx *ctx, const mirge_library *lib, const mirge_round_policy *policy, const mirge_table *t,

@@ -39,8 +39,11 @@ enum { INS_OK = 0, INS_DEFER = 1, INS_FAIL = 2 };
 // completeDict[key] += add.  `unbounded`: keep polling an unpublished slot (retry kernel only).
 // in_arena: word offset of the key when it already lives in the table's arena (the trim kernel wrote it
 // there): the owner then publishes that offset instead of allocating and copying.
+// DEFER_ID: the owner takes no dense id here (and touches no shared counter when the key is in place): it reports
+// the slot it created through *own_slot and a streaming kernel hands out the ids afterwards (assign_ids_kernel).
+template <bool DEFER_ID>
 __device__ __forceinline__ int table_insert(const mirge_table &t, const uint32_t *key, uint32_t nw, uint32_t add,
-                                            uint64_t h, bool unbounded, uint32_t in_arena) {
+                                            uint64_t h, bool unbounded, uint32_t in_arena, uint32_t *own_slot = nullptr) {
   unsigned long long *ctrl = (unsigned long long *)t.d_ctrl;
   const uint64_t mask = t.capacity - 1;
   uint32_t tag = (uint32_t)(h >> 32);
@@ -70,12 +73,12 @@ __device__ __forceinline__ int table_insert(const mirge_table &t, const uint32_t
           }
         }
         if ((int)lane == leader) {
-          base_id = atomicAdd(ctrl + 1, (unsigned long long)__popc(grp));
+          if (!DEFER_ID) base_id = atomicAdd(ctrl + 1, (unsigned long long)__popc(grp));
           if (in_arena == NOT_IN_ARENA) base_w = atomicAdd(ctrl + 0, (unsigned long long)total);
         }
-        base_id = __shfl_sync(grp, base_id, leader);
-        base_w = __shfl_sync(grp, base_w, leader);
-        const unsigned long long id = base_id + rank;
+        if (!DEFER_ID) base_id = __shfl_sync(grp, base_id, leader);
+        if (!DEFER_ID || in_arena == NOT_IN_ARENA) base_w = __shfl_sync(grp, base_w, leader);
+        const unsigned long long id = DEFER_ID ? 0ull : base_id + rank;
         const unsigned long long aoff = in_arena == NOT_IN_ARENA ? base_w + pre : (unsigned long long)in_arena;
         if (aoff + nw > t.arena_words || aoff + nw >= 0xFFFFFFF0ull || id >= t.max_keys) {
           atomicOr(ctrl + 2, id >= t.max_keys ? ERR_KEYS_FULL : ERR_ARENA_FULL);
@@ -86,8 +89,12 @@ __device__ __forceinline__ int table_insert(const mirge_table &t, const uint32_t
           uint32_t *dst = t.d_arena + aoff;
           for (uint32_t i = 0; i < nw; ++i) dst[i] = key[i];
         }
-        t.d_key_ref[id] = (uint32_t)aoff;
-        s->id = (uint32_t)id;
+        if (!DEFER_ID) {
+          t.d_key_ref[id] = (uint32_t)aoff;
+          s->id = (uint32_t)id;
+        } else {
+          *own_slot = (uint32_t)idx;
+        }
         atomicAdd(&s->count, add);
         // release: a key text this thread just copied must be visible before ref.  A key that already sits in
         // the arena was written by an earlier kernel, and waiters read nothing else the owner wrote (they only
@@ -147,33 +154,17 @@ __device__ __forceinline__ void defer_item(unsigned long long *counter, uint32_t
   list[base + __popc(grp & ((1u << lane) - 1u))] = item;
 }
 
-// mode 0: items are emission slots (keys/key_off, add = 1)
-// mode 1: items are exchange records [count][key...] at rec_off[i]
-// mode 2: emission slots whose keys the trim kernel wrote straight into the table's arena (keys == arena)
-// mode 3: exchange records that were received straight into the table's arena (keys == arena): the key of a
-//         record becomes the table's copy where it lies, nothing is moved
-// In modes 0 and 2 consecutive slots that carry the same key offset (HEAD counting emitted the same text after
-// consecutive modifiers) are one insert: the first slot of the run adds the run length, the others do nothing.
-__device__ __forceinline__ void item_key(int mode, const uint32_t *keys, const uint32_t *off, uint64_t i, uint64_t n,
+// Exchange records of the owner-side merge.  mode 1: records [count][key...] at rec_off[i] of `keys`;
+// mode 3: records that were received straight into the table's arena (keys == arena): the key of a record becomes
+// the table's copy where it lies, nothing is moved.
+__device__ __forceinline__ void item_key(int mode, const uint32_t *keys, const uint32_t *off, uint64_t i,
                                          const uint32_t *&key, uint32_t &add, uint32_t &in_arena) {
   const uint32_t o = off[i];
   in_arena = NOT_IN_ARENA;
   if (o == 0xFFFFFFFFu) { key = nullptr; add = 0; return; }
-  if (mode == 1) { key = keys + o + 1; add = keys[o]; return; }
-  if (mode == 3) { key = keys + o + 1; add = keys[o]; in_arena = o + 1; return; }
-  // the neighbours that decide the run are loaded together (independent loads: one latency, not one per step)
-  const uint32_t o_prev = i > 0 ? off[i - 1] : 0u, o1 = i + 1 < n ? off[i + 1] : 0xFFFFFFFFu, o2 = i + 2 < n ? off[i + 2] : 0xFFFFFFFFu;
-  if (i > 0 && o_prev == o) { key = nullptr; add = 0; return; }  // counted by the first slot of the run
-  add = 1;
-  if (o1 == o) {
-    ++add;
-    if (o2 == o) {
-      ++add;
-      for (uint64_t k = i + 3; k < n && k < i + MIRGE_MAX_MODS && off[k] == o; ++k) ++add;
-    }
-  }
-  key = keys + o;
-  if (mode == 2) in_arena = o;
+  key = keys + o + 1;
+  add = keys[o];
+  if (mode == 3) in_arena = o + 1;
 }
 
 // Hash of an in-arena key whose length is not known yet: the header and the next seven words are fetched together
@@ -197,17 +188,17 @@ collapse_insert_kernel(mirge_table t, const uint32_t *__restrict__ keys, const u
   const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
   if (i >= n) return;
   const uint32_t *key; uint32_t add, in_arena;
-  item_key(mode, keys, off, i, n, key, add, in_arena);
+  item_key(mode, keys, off, i, key, add, in_arena);
   if (!key || add == 0) return;
   uint32_t nw;
   uint64_t h;
-  if (mode >= 2) {  // uniform: the keys lie in the table's arena
+  if (mode == 3) {  // uniform: the keys lie in the table's arena
     h = hash_key_in_arena(t, key, in_arena, nw);
   } else {
     nw = key_words(key[0]);
     h = hash_key(key, nw);
   }
-  if (table_insert(t, key, nw, add, h, false, in_arena) == INS_DEFER)
+  if (table_insert<false>(t, key, nw, add, h, false, in_arena) == INS_DEFER)
     defer_item((unsigned long long *)t.d_ctrl + 3, deferred, (uint32_t)i);
 }
 
@@ -222,14 +213,96 @@ collapse_retry_kernel(mirge_table t, const uint32_t *__restrict__ keys, const ui
   for (uint64_t j = warp; j < nd; j += nwarps) {
     const uint64_t i = deferred[j];
     const uint32_t *key; uint32_t add, in_arena;
-    item_key(mode, keys, off, i, n, key, add, in_arena);
+    item_key(mode, keys, off, i, key, add, in_arena);
     if (!key) continue;
     const uint32_t nw = key_words(key[0]);
-    table_insert(t, key, nw, add, hash_key(key, nw), true, in_arena);
+    table_insert<false>(t, key, nw, add, hash_key(key, nw), true, in_arena);
   }
 }
 
 __global__ void clear_deferred_kernel(unsigned long long *ctrl) { ctrl[3] = 0; }
+
+// ---- the insert list of a batch (mirge_trim): one distinct key of a read per lane ------------------------------
+#define NO_SLOT 0xFFFFFFFFu
+
+// IN_PLACE: the keys lie in the table's arena (the trim kernels wrote them there).  own[i] = slot this item
+// created, NO_SLOT when the key existed (or the item was deferred).
+template <bool IN_PLACE>
+__global__ void __launch_bounds__(COL_THREADS)
+collapse_list_kernel(mirge_table t, const uint32_t *__restrict__ keys, const uint2 *__restrict__ ins, uint64_t n,
+                     uint32_t *__restrict__ own, uint32_t *__restrict__ deferred) {
+  const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
+  if (i >= n) return;
+  const uint2 it = ins[i];
+  const uint32_t o = it.x, add = it.y;
+  const uint32_t *key = keys + o;
+  uint32_t nw, slot = NO_SLOT;
+  uint64_t h;
+  if (IN_PLACE) {
+    h = hash_key_in_arena(t, key, o, nw);
+  } else {
+    nw = key_words(key[0]);
+    h = hash_key(key, nw);
+  }
+  const int rc = table_insert<true>(t, key, nw, add, h, false, IN_PLACE ? o : NOT_IN_ARENA, &slot);
+  own[i] = slot;
+  if (rc == INS_DEFER) defer_item((unsigned long long *)t.d_ctrl + 3, deferred, (uint32_t)i);
+}
+
+template <bool IN_PLACE>
+__global__ void __launch_bounds__(COL_THREADS)
+collapse_list_retry_kernel(mirge_table t, const uint32_t *__restrict__ keys, const uint2 *__restrict__ ins,
+                           uint32_t *__restrict__ own, const uint32_t *__restrict__ deferred) {
+  if (threadIdx.x & 31) return;
+  const unsigned long long nd = ((unsigned long long *)t.d_ctrl)[3];
+  const uint64_t warp = ((uint64_t)blockIdx.x * COL_THREADS + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * COL_THREADS) >> 5;
+  for (uint64_t j = warp; j < nd; j += nwarps) {
+    const uint64_t i = deferred[j];
+    const uint2 it = ins[i];
+    const uint32_t o = it.x;
+    const uint32_t *key = keys + o;
+    const uint32_t nw = key_words(key[0]);
+    uint32_t slot = NO_SLOT;
+    table_insert<true>(t, key, nw, it.y, hash_key(key, nw), true, IN_PLACE ? o : NOT_IN_ARENA, &slot);
+    own[i] = slot;
+  }
+}
+
+// Dense key ids for the slots a batch created: a block-wide scan of the ownership flags and ONE atomic per CTA on
+// the key counter; then id -> slot and id -> key offset.  Runs after the inserts, off their dependent chain.
+template <bool IN_PLACE>
+__global__ void __launch_bounds__(COL_THREADS)
+assign_ids_kernel(mirge_table t, const uint2 *__restrict__ ins, const uint32_t *__restrict__ own, uint64_t n) {
+  __shared__ uint32_t warp_tot[COL_THREADS / 32];
+  __shared__ unsigned long long block_base;
+  const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
+  const uint32_t slot = i < n ? own[i] : NO_SLOT;
+  const bool mine = slot != NO_SLOT;
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, mine);
+  if (lane == 0) warp_tot[warp] = __popc(bal);
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < COL_THREADS / 32; ++w) {
+    const uint32_t x = warp_tot[w];
+    if ((unsigned)w < warp) before += x;
+    total += x;
+  }
+  if (total == 0) return;
+  if (threadIdx.x == 0) block_base = atomicAdd((unsigned long long *)t.d_ctrl + 1, (unsigned long long)total);
+  __syncthreads();
+  if (!mine) return;
+  const unsigned long long id = block_base + before + __popc(bal & ((1u << lane) - 1u));
+  if (id >= t.max_keys) {
+    atomicOr((unsigned long long *)t.d_ctrl + 2, ERR_KEYS_FULL);
+    return;
+  }
+  mirge_slot *s = t.d_slots + slot;
+  s->id = (uint32_t)id;
+  t.d_key_ref[id] = IN_PLACE ? ins[i].x : s->ref - 1u;
+}
 
 static int check_table(mirge_ctx *ctx, const mirge_table *t) {
   if (!t || !t->d_slots || !t->d_arena || !t->d_key_ref || !t->d_ctrl) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "table: null buffer");
@@ -267,17 +340,33 @@ static int run_insert(mirge_ctx *ctx, const mirge_table *t, const uint32_t *keys
   return MIRGE_OK;
 }
 
-extern "C" int mirge_collapse_insert(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_keys, const uint32_t *d_key_off,
-                                     uint64_t n_slots, uint32_t *d_deferred, void *stream) {
+extern "C" int mirge_collapse_insert_list(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_keys, const uint64_t *d_ins,
+                                          uint64_t n_items, uint32_t *d_scratch, void *stream_) {
   if (!ctx) return MIRGE_ERR_ARG;
-  return run_insert(ctx, t, d_keys, d_key_off, n_slots, 0, d_deferred, (cudaStream_t)stream);
-}
-
-extern "C" int mirge_collapse_insert_inplace(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_key_off, uint64_t n_slots,
-                                             uint32_t *d_deferred, void *stream) {
-  if (!ctx) return MIRGE_ERR_ARG;
-  if (!t) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "collapse: null table");
-  return run_insert(ctx, t, t->d_arena, d_key_off, n_slots, 2, d_deferred, (cudaStream_t)stream);
+  int rc = check_table(ctx, t);
+  if (rc) return rc;
+  if (n_items == 0) return MIRGE_OK;
+  if (!d_keys || !d_ins || !d_scratch) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "collapse: null buffer");
+  const uint2 *ins = (const uint2 *)d_ins;
+  if (n_items > 0xFFFFFFFFull) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "collapse: more than 2^32 items in one batch");
+  if (t->capacity > 0xFFFFFFFFull) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "collapse: more than 2^32 - 1 slots");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint32_t *own = d_scratch, *deferred = d_scratch + n_items;
+  const unsigned grid = (unsigned)((n_items + COL_THREADS - 1) / COL_THREADS);
+  if (d_keys == t->d_arena) {
+    collapse_list_kernel<true><<<grid, COL_THREADS, 0, stream>>>(*t, d_keys, ins, n_items, own, deferred);
+    collapse_list_retry_kernel<true><<<ctx->sm_count, COL_THREADS, 0, stream>>>(*t, d_keys, ins, own, deferred);
+    assign_ids_kernel<true><<<grid, COL_THREADS, 0, stream>>>(*t, ins, own, n_items);
+  } else {
+    collapse_list_kernel<false><<<grid, COL_THREADS, 0, stream>>>(*t, d_keys, ins, n_items, own, deferred);
+    collapse_list_retry_kernel<false><<<ctx->sm_count, COL_THREADS, 0, stream>>>(*t, d_keys, ins, own, deferred);
+    assign_ids_kernel<false><<<grid, COL_THREADS, 0, stream>>>(*t, ins, own, n_items);
+  }
+  MIRGE_LAUNCH_CHECK(ctx, "collapse list kernels");
+  clear_deferred_kernel<<<1, 1, 0, stream>>>((unsigned long long *)t->d_ctrl);
+  MIRGE_LAUNCH_CHECK(ctx, "clear_deferred_kernel");
+  return MIRGE_OK;
 }
 
 extern "C" int mirge_collapse_merge(mirge_ctx *ctx, const mirge_table *t, const uint32_t *d_rec, const uint32_t *d_rec_off,
@@ -449,7 +538,7 @@ umi_collapse_kernel(mirge_table first, const uint32_t *__restrict__ ids, const u
     if (cl < min_len) continue;
     const uint32_t nw = slice_key(key, f, b, buf);
     const uint32_t add = dedup ? 1u : counts[item];
-    const int rc = table_insert(second, buf, nw, add, hash_key(buf, nw), retry != 0, NOT_IN_ARENA);
+    const int rc = table_insert<false>(second, buf, nw, add, hash_key(buf, nw), retry != 0, NOT_IN_ARENA);
     if (rc == INS_DEFER) defer_item(ctrl2 + 3, deferred, (uint32_t)item);
   }
 }

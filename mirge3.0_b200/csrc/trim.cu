@@ -213,6 +213,34 @@ __device__ __forceinline__ int exact_find(const uint32_t *ps, uint64_t a2, int m
   return -1;
 }
 
+// Insert list of the collapse: one entry per distinct key a read emits (arena / key buffer word offset, and how
+// many consecutive emission slots carry that text), so that the insert kernel runs one key per lane with no
+// filtered or repeated slots in between.  off == nullptr: no list wanted.
+struct InsList {
+  uint2 *off;  // (key word offset, count)
+  uint64_t cap;
+};
+// ctrl[0] = insert-list entries << WORD_BITS | key words.  A batch is < 4 GiB and a record of l bases has >= 2l + 6
+// bytes and <= MIRGE_MAX_MODS keys of <= 1 + l/16 + l words, so base (< 2^32) + key words of a batch < 2^36; the
+// entries (<= records x slots, checked on the host side of mirge_trim) keep the 28 bits above.
+#define WORD_BITS 36
+#define WORD_MASK ((1ull << WORD_BITS) - 1ull)
+#define MAX_LIST_ITEMS (1ull << (64 - WORD_BITS))
+
+// per-CTA statistics: [0] emitted keys, [1] key words of all emitted keys
+__shared__ unsigned int s_stats[2];
+__device__ __forceinline__ void init_stats() {
+  if (threadIdx.x < 2) s_stats[threadIdx.x] = 0;
+}
+// all threads of the CTA, after their last emit_record
+__device__ __forceinline__ void flush_stats(unsigned long long *ctrl) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_stats[0]) atomicAdd(ctrl + 1, (unsigned long long)s_stats[0]);
+    if (s_stats[1]) atomicAdd(ctrl + 4, (unsigned long long)s_stats[1]);
+  }
+}
+
 // Sizes, key space (one atomic per warp), second-pass queue and the writes of emission slots [slot_lo, slot_hi)
 // of record r.  All 32 lanes of a warp must call it together.  fast_emit: the keys are slices of the packed
 // pure-ACGT read in ps_mine; otherwise they are packed from the bytes in seq (exceptions included).
@@ -223,9 +251,9 @@ __device__ __forceinline__ void emit_record(const bool valid, const uint64_t r, 
                                             const int *w_us, const int *w_ue, uint32_t *w_words, const bool to_slow,
                                             ushort4 *__restrict__ win, uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys,
                                             uint64_t keys_cap, unsigned long long *__restrict__ ctrl, uint32_t *__restrict__ d_slow,
-                                            const uint32_t *ps_mine) {
+                                            const uint32_t *ps_mine, const InsList il) {
   const int lane = threadIdx.x & 31;
-  uint32_t my_words = 0, my_kept = 0, my_alg = 0, same_as_prev = 0;
+  uint32_t my_words = 0, my_kept = 0, my_alg = 0, same_as_prev = 0, my_items = 0;
   if (valid) {
     // size of every kept key: header + payload + exceptions.  A slot whose text is the text of the slot before
     // it (a modifier that changed nothing: HEAD counting emits the read again) gets no space of its own -- its
@@ -251,24 +279,35 @@ __device__ __forceinline__ void emit_record(const bool valid, const uint64_t r, 
       }
       my_words += w_words[s];
       my_alg += w_words[s];
+      ++my_items;
     }
   }
-  uint32_t inc = my_words;
+  // one scan for both prefixes: key words in the low 24 bits (<= 8 slots x 545 words x 32 lanes < 2^18), insert-list
+  // items (distinct keys of the read, <= 8 per lane) above
+  uint32_t inc = my_words | (my_items << 24);
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
     const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
     if (lane >= d) inc += t;
   }
-  const uint32_t warp_total = __shfl_sync(0xffffffffu, inc, 31);
+  const uint32_t both_total = __shfl_sync(0xffffffffu, inc, 31);
+  const uint32_t warp_total = both_total & 0xFFFFFFu, warp_items = both_total >> 24;
+  const uint32_t item_before = (inc >> 24) - my_items;
+  inc &= 0xFFFFFFu;
   const uint32_t kept_warp = __reduce_add_sync(0xffffffffu, my_kept);
   const uint32_t alg_warp = __reduce_add_sync(0xffffffffu, my_alg);
-  unsigned long long warp_base = 0;
+  // ONE global atomic per warp hands out the key words (low WORD_BITS bits of ctrl[0]) and the insert-list entries
+  // (bits above) together; the two statistics go through the CTA's shared-memory counters (flushed once per CTA by
+  // flush_stats): same-line atomics of every warp of the grid serialise in one L2 atomic unit, and the key-space
+  // atomic is on every warp's critical path.
+  unsigned long long both = 0;
   if (lane == 0) {
-    if (warp_total) warp_base = atomicAdd(ctrl + 0, (unsigned long long)warp_total);
-    if (kept_warp) atomicAdd(ctrl + 1, (unsigned long long)kept_warp);
-    if (alg_warp) atomicAdd(ctrl + 4, (unsigned long long)alg_warp);  // key words of all emitted keys (repeats included)
+    if (both_total) both = atomicAdd(ctrl + 0, ((unsigned long long)warp_items << WORD_BITS) | (unsigned long long)warp_total);
+    if (kept_warp) atomicAdd(&s_stats[0], kept_warp);
+    if (alg_warp) atomicAdd(&s_stats[1], alg_warp);  // key words of all emitted keys (repeats included)
   }
-  warp_base = __shfl_sync(0xffffffffu, warp_base, 0);
+  both = __shfl_sync(0xffffffffu, both, 0);
+  const unsigned long long warp_base = both & WORD_MASK, item_base = both >> WORD_BITS;
   const bool overflow = warp_base + warp_total > keys_cap || warp_base + warp_total > 0xFFFFFFF0ull;
   if (overflow && lane == 0 && warp_total) atomicOr(ctrl + 2, 2ull);
   if (PASS == 1) {  // queue the deferred reads for the second pass (one atomic per warp)
@@ -282,19 +321,25 @@ __device__ __forceinline__ void emit_record(const bool valid, const uint64_t r, 
   }
   if (!valid) return;
   uint32_t off = (uint32_t)warp_base + inc - my_words;
+  uint64_t item = item_base + item_before;
 #pragma unroll 1
   for (int s = slot_lo; s < slot_hi; ++s) {
     const uint64_t e = r * (uint64_t)E + s;
-    win[e] = make_ushort4((unsigned short)w_start[s], (unsigned short)w_stop[s], (unsigned short)w_us[s], (unsigned short)w_ue[s]);
+    if (win) win[e] = make_ushort4((unsigned short)w_start[s], (unsigned short)w_stop[s], (unsigned short)w_us[s], (unsigned short)w_ue[s]);
     if (!w_words[s] || overflow) {
-      key_off[e] = 0xFFFFFFFFu;
+      if (key_off) key_off[e] = 0xFFFFFFFFu;
       continue;
     }
     if ((same_as_prev >> s) & 1u) {  // same text as the previous slot: same key
-      key_off[e] = off - w_words[s];
+      if (key_off) key_off[e] = off - w_words[s];
       continue;
     }
-    key_off[e] = off;
+    if (key_off) key_off[e] = off;
+    if (il.off && item < il.cap) {  // one insert per distinct key: the run of slots that repeat it is its count
+      const uint32_t run = (uint32_t)__ffs((int)(~(same_as_prev >> (s + 1)) | (1u << (slot_hi - s - 1))));
+      il.off[item] = make_uint2(off, run);
+      ++item;
+    }
     const int l1 = w_stop[s] - w_start[s], len = l1 + (w_ue[s] - w_us[s]);
     const uint32_t npay = (uint32_t)(len + 15) >> 4;
     uint32_t *k = keys + off;
@@ -354,7 +399,8 @@ __device__ __forceinline__ void process_record(const bool valid, const uint64_t 
                                                const uint32_t *__restrict__ line_start, ushort4 *__restrict__ win,
                                                uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys, uint64_t keys_cap,
                                                unsigned long long *__restrict__ ctrl, uint32_t *__restrict__ d_slow, FastCtx &fc,
-                                               uint32_t *ps_mine, const SplitOut so, const uint4 ls, const uint32_t nxt) {
+                                               uint32_t *ps_mine, const SplitOut so, const uint4 ls, const uint32_t nxt,
+                                               const InsList il) {
   const int lane = threadIdx.x & 31;
   bool is_slow = false;
   const int E = c_p.slots;
@@ -532,7 +578,7 @@ __device__ __forceinline__ void process_record(const bool valid, const uint64_t 
     }
   }
   emit_record<FAST, PASS>(valid, r, E, slot_lo, slot_hi, seq, fast_emit, w_start, w_stop, w_us, w_ue, w_words, to_slow, win, key_off,
-                          keys, keys_cap, ctrl, d_slow, ps_mine);
+                          keys, keys_cap, ctrl, d_slow, ps_mine, il);
 }
 
 // FAST = bit-parallel adapter search (locate_fast) + packed-read key emission; requires the CTA's span to be
@@ -542,13 +588,15 @@ template <int MAXM, bool FAST, int PASS, bool SPLIT>
 __global__ void __launch_bounds__(TRIM_THREADS, (FAST && PASS == 1) ? 7 : 1)
 trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__restrict__ line_start, uint64_t n_records,
             ushort4 *__restrict__ win, uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys, uint64_t keys_cap,
-            unsigned long long *__restrict__ ctrl, uint32_t smem_bytes, uint32_t *__restrict__ d_slow, const SplitOut so) {
+            unsigned long long *__restrict__ ctrl, uint32_t smem_bytes, uint32_t *__restrict__ d_slow, const SplitOut so,
+            const InsList il) {
   extern __shared__ uint4 smem4[];
   uint8_t *sbuf = (uint8_t *)smem4;
   const int tid = threadIdx.x;
   FastCtx fc;
   fc.s_eq = nullptr; fc.ps = nullptr; fc.jump_ok = false; fc.rbase = 0;
   uint32_t *ps_mine = nullptr;
+  init_stats();  // (a barrier follows before any emission on every path below)
   if (FAST) {
     // smem: [staging smem_bytes][eq tables n_adapters * 256 words][packed reads PS_ROWS * T words]
     uint32_t *eq = (uint32_t *)(sbuf + smem_bytes);
@@ -574,9 +622,10 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
       uint32_t nxt = 0;
       if (valid) { ls = *(const uint4 *)(line_start + 4 * r); nxt = line_start[4 * r + 4]; }
       process_record<MAXM, FAST, 2, false>(valid, r, fq, nbytes, line_start, win, key_off, keys, keys_cap, ctrl,
-                                           d_slow, fc, ps_mine, so, ls, nxt);
+                                           d_slow, fc, ps_mine, so, ls, nxt, il);
       __syncwarp();
     }
+    flush_stats(ctrl);
     return;
   }
   const uint64_t r0 = (uint64_t)blockIdx.x * TRIM_THREADS;
@@ -620,7 +669,8 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
   uint32_t nxt = 0;
   if (valid) { ls = *(const uint4 *)(line_start + 4 * r); nxt = line_start[4 * r + 4]; }
   const uint8_t *B = staged ? (const uint8_t *)(sbuf - alo) : fq;  // B[absolute stream offset]
-  process_record<MAXM, FAST, PASS, SPLIT>(valid, r, B, nbytes, line_start, win, key_off, keys, keys_cap, ctrl, d_slow, fc, ps_mine, so, ls, nxt);
+  process_record<MAXM, FAST, PASS, SPLIT>(valid, r, B, nbytes, line_start, win, key_off, keys, keys_cap, ctrl, d_slow, fc, ps_mine, so, ls, nxt, il);
+  flush_stats(ctrl);
 }
 
 // Stages 2 and 3 of the split pipeline: the adapter search (and everything after it) of the listed reads, from
@@ -630,7 +680,7 @@ template <bool FIRST>
 __global__ void __launch_bounds__(TRIM_THREADS, FIRST ? 7 : 4)
 trim_dp_kernel(const DpEntry *__restrict__ entries, const uint32_t *__restrict__ pk, uint64_t cap, uint32_t *__restrict__ redo,
                ushort4 *__restrict__ win, uint32_t *__restrict__ key_off, uint32_t *__restrict__ keys, uint64_t keys_cap,
-               unsigned long long *__restrict__ ctrl) {
+               unsigned long long *__restrict__ ctrl, const InsList il) {
   extern __shared__ uint4 smem4[];
   // smem: [eq tables n_adapters * 256 words, entries 0..3 used][packed reads PS_ROWS * T words][entries T][hist T][order T]
   uint32_t *eq = (uint32_t *)smem4;
@@ -642,6 +692,7 @@ trim_dp_kernel(const DpEntry *__restrict__ entries, const uint32_t *__restrict__
   const unsigned long long n_items = FIRST ? ctrl[6] : ctrl[7];
   const uint64_t base = (uint64_t)blockIdx.x * TRIM_THREADS;
   if (base >= n_items) return;  // uniform per CTA
+  init_stats();
   for (int e = tid; e < c_p.n_adapters * 4; e += TRIM_THREADS) eq[(e >> 2) * 256 + (e & 3)] = (uint32_t)c_p.ad[e >> 2].peq[e & 3];
   const int n_here = (int)min((unsigned long long)TRIM_THREADS, n_items - base);
   // this CTA's entries, then a counting sort by window length (longest first): the lanes of a warp run column
@@ -748,7 +799,8 @@ trim_dp_kernel(const DpEntry *__restrict__ entries, const uint32_t *__restrict__
     if (need_redo) slot_hi = slot_lo;
   }
   emit_record<true, 0>(valid, r, E, slot_lo, slot_hi, nullptr, true, w_start, w_stop, w_us, w_ue, w_words, false, win, key_off, keys, keys_cap,
-                       ctrl, nullptr, ps_mine);
+                       ctrl, nullptr, ps_mine, il);
+  flush_stats(ctrl);
 }
 
 // scratch layout of mirge_trim: [second-pass list u32[n]][stage-3 list u32[n]][DpEntry[n]][packed text u32[MAX_PACK_WORDS][n]]
@@ -760,13 +812,19 @@ extern "C" uint64_t mirge_trim_scratch_bytes(uint64_t n_records) {
 
 extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, const uint32_t *d_line_start, uint64_t n_records,
                           uint16_t *d_win, uint32_t *d_key_off, uint32_t *d_keys, uint64_t keys_capacity_words,
-                          uint64_t *d_trim_ctrl, void *d_scratch, void *stream_) {
+                          uint64_t *d_trim_ctrl, void *d_scratch, uint64_t *d_ins, uint64_t ins_capacity, void *stream_) {
   if (!ctx) return MIRGE_ERR_ARG;
   if (!ctx->params_set) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: mirge_set_trim_params has not been called");
   if (n_records == 0) return MIRGE_OK;
-  if (!d_fastq || !d_line_start || !d_win || !d_key_off || !d_keys || !d_trim_ctrl) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: null buffer");
+  if (!d_fastq || !d_line_start || !d_keys || !d_trim_ctrl) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: null buffer");
+  if (!d_win != !d_key_off) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: d_win and d_key_off go together");
+  if (!d_key_off && !d_ins) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: neither per-slot outputs nor an insert list requested");
+  if (d_ins && (ins_capacity == 0 || ((uintptr_t)d_ins & 7))) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: bad insert list");
+  if (n_records * (uint64_t)trim_slots_of(&ctx->params) >= MAX_LIST_ITEMS)
+    MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: more than 2^28 emission slots in one batch (use smaller batches)");
   if (((uintptr_t)d_line_start & 15) || ((uintptr_t)d_win & 7) || ((uintptr_t)d_scratch & 15))
     MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: misaligned buffer");
+  const InsList il{(uint2 *)d_ins, d_ins ? ins_capacity : 0};
   if (n_records >= 0x80000000ull) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "trim: more than 2^31 records in one batch");
   // same convention as the tokeniser: line_start offsets are relative to the 16-byte aligned stream
   {
@@ -807,22 +865,22 @@ extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbyte
       // stage 1: every read up to the adapter modifier; exact adapter occurrences are settled here
       MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, true, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       trim_kernel<32, true, 1, true><<<grid, TRIM_THREADS, smem + extra, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off,
-                                                                                 d_keys, keys_capacity_words, ctrl, smem, d_slow, so);
+                                                                                 d_keys, keys_capacity_words, ctrl, smem, d_slow, so, il);
       MIRGE_LAUNCH_CHECK(ctx, "trim_kernel(stage 1)");
       // stages 2 and 3: the listed reads (counts live on the device: CTAs beyond the list exit at once)
       const size_t dp_smem = extra + (size_t)TRIM_THREADS * (sizeof(DpEntry) + 4 + 2);
       trim_dp_kernel<true><<<grid, TRIM_THREADS, dp_smem, stream>>>(so.entries, so.pk, so.cap, d_redo, win, d_key_off, d_keys,
-                                                                    keys_capacity_words, ctrl);
+                                                                    keys_capacity_words, ctrl, il);
       MIRGE_LAUNCH_CHECK(ctx, "trim_dp_kernel(stage 2)");
       trim_dp_kernel<false><<<grid, TRIM_THREADS, dp_smem, stream>>>(so.entries, so.pk, so.cap, d_redo, win, d_key_off, d_keys,
-                                                                     keys_capacity_words, ctrl);
+                                                                     keys_capacity_words, ctrl, il);
       MIRGE_LAUNCH_CHECK(ctx, "trim_dp_kernel(stage 3)");
     } else {
       MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, true, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       // pass 1: every read; adapter searches that need cost columns are deferred to the list d_slow
       trim_kernel<32, true, 1, false><<<grid, TRIM_THREADS, smem + extra, stream>>>(d_fastq, nbytes, d_line_start, n_records, win,
                                                                                   d_key_off, d_keys, keys_capacity_words, ctrl, smem,
-                                                                                  d_slow, so);
+                                                                                  d_slow, so, il);
       MIRGE_LAUNCH_CHECK(ctx, "trim_kernel(pass 1)");
     }
     // pass 2: the reads left over (whole pipeline per read, from the global stream; grid-stride over the list)
@@ -831,15 +889,15 @@ extern "C" int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbyte
     unsigned grid2 = split ? grid / 4 + 1 : grid / 16 + 1;
     if (grid2 > (unsigned)ctx->sm_count * (split ? 64u : 8u)) grid2 = (unsigned)ctx->sm_count * (split ? 64u : 8u);
     trim_kernel<32, true, 2, false><<<grid2, TRIM_THREADS, extra, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off,
-                                                                          d_keys, keys_capacity_words, ctrl, 0u, d_slow, so);
+                                                                          d_keys, keys_capacity_words, ctrl, 0u, d_slow, so, il);
   } else if (ctx->max_adapter_len <= 32) {
     MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<32, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     trim_kernel<32, false, 0, false><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off,
-                                                                           d_keys, keys_capacity_words, ctrl, smem, nullptr, so);
+                                                                           d_keys, keys_capacity_words, ctrl, smem, nullptr, so, il);
   } else {
     MIRGE_CUDA(ctx, cudaFuncSetAttribute(trim_kernel<64, false, 0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
     trim_kernel<64, false, 0, false><<<grid, TRIM_THREADS, smem, stream>>>(d_fastq, nbytes, d_line_start, n_records, win, d_key_off,
-                                                                           d_keys, keys_capacity_words, ctrl, smem, nullptr, so);
+                                                                           d_keys, keys_capacity_words, ctrl, smem, nullptr, so, il);
   }
   MIRGE_LAUNCH_CHECK(ctx, "trim_kernel");
   return MIRGE_OK;

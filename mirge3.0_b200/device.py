@@ -6,6 +6,7 @@ every byte of the hot path is touched by the kernels in ``csrc/`` through the C 
 from __future__ import annotations
 
 import contextlib
+import os
 import ctypes as C
 from dataclasses import dataclass
 from typing import Optional
@@ -131,6 +132,10 @@ class CollapseTable:
         self.ctrl = dev.zeros(8, torch.int64)
         self.n_keys = 0
         self.arena_used = 0
+        # share of a batch's insert-list items that created a key (last batch): decides whether the next batch's keys
+        # are written straight into the arena (mostly new keys: nothing is copied) or into a batch buffer from which
+        # only the new keys are copied (mostly repeats: the arena grows with unique sequences, not with reads)
+        self.new_frac = 1.0
         self._struct()
 
     def _struct(self):
@@ -143,6 +148,7 @@ class CollapseTable:
         d.check(d.lib.mirge_table_reset(d.ctx, C.byref(self.struct), d.stream()))
         self.n_keys = 0
         self.arena_used = 0
+        self.new_frac = 1.0
 
     def check(self):
         """Synchronise, raise on table errors, refresh n_keys / arena_used."""
@@ -232,6 +238,8 @@ class BatchResult:
     keys: Optional[torch.Tensor] = None
     in_place: bool = False  # keys were written straight into the collapse table's arena
     arena_words: int = 0  # words the batch's keys occupy (repeated slots share a key); key_words counts every emitted key
+    ins: Optional[torch.Tensor] = None  # insert list of the collapse: (key word offset, count) of every distinct key a read emitted
+    n_items: int = 0
 
 
 class DigestEngine:
@@ -243,6 +251,7 @@ class DigestEngine:
         self.cfg = cfg
         self.E = dev.slots
         self.trim_mode = 0  # 0 = automatic kernel choice, 1 = always the generic full-DP kernel
+        self.INPLACE_MIN_NEW = float(os.environ.get("MIRGE_B200_INPLACE_MIN_NEW", "0.25"))
         dev.check(dev.lib.mirge_trim_mode(dev.ctx, 0))
         self.stats = {"records": 0, "bytes": 0, "emitted": 0, "key_words": 0, "deferred": 0, "dp_reads": 0, "dp_redo": 0}  # running totals (bench.py rooflines)
 
@@ -274,17 +283,22 @@ class DigestEngine:
         with d.timed("line_index"):
             d.check(lib.mirge_line_index(d.ctx, _ptr(buf), nbytes, _ptr(scratch), _ptr(line_start), n, st))
         d.launches += 3
-        win = d.empty(n * E * 4, torch.int16)
-        key_off = d.empty(n * E, torch.int32)
+        # per-slot windows / key offsets are what the parity tests read; the product path (keep=False) only wants the
+        # insert list of the collapse
+        win = d.empty(n * E * 4, torch.int16) if keep else None
+        key_off = d.empty(n * E, torch.int32) if keep else None
+        ins = d.empty(n * E, torch.int64)
         slow = d.empty(lib.mirge_trim_scratch_bytes(n), torch.uint8)  # work lists of the split trim pipeline
         cap = E * (2 * n + used // 24) + 4096
         mode = self.trim_mode
         base_words = 0
+        if table is not None and table.new_frac < self.INPLACE_MIN_NEW:
+            table = None  # repeats dominate: batch key buffer + copying insert keeps the arena tight
         if table is not None:
             table.check()
             base_words = table.arena_used
         for attempt in range(4):
-            ctrl = d.zeros(8, torch.int64)
+            ctrl = d.zeros(16, torch.int64)
             if table is not None:
                 table.reserve(0, cap)  # room in the arena for this batch's keys
                 keys = table.arena
@@ -298,12 +312,14 @@ class DigestEngine:
             try:
                 with d.timed("trim"):
                     d.check(lib.mirge_trim(d.ctx, _ptr(buf), used, _ptr(line_start), n, _ptr(win), _ptr(key_off),
-                                           _ptr(keys), cap_abs, _ptr(ctrl), _ptr(slow), st))
+                                           _ptr(keys), cap_abs, _ptr(ctrl), _ptr(slow), _ptr(ins), n * E, st))
             finally:
                 if mode != self.trim_mode:
                     d.check(lib.mirge_trim_mode(d.ctx, self.trim_mode))
             d.launches += 4
             c = ctrl.cpu().numpy().view(np.uint64)
+            # ctrl[0] = insert-list entries << 36 | key words (one atomic hands out both, csrc/trim.cu)
+            words_used, n_items = int(c[0]) & ((1 << 36) - 1), int(c[0]) >> 36
             flags = int(c[2])
             self.stats["deferred"] += int(c[5])  # reads handed to the whole-pipeline second pass (diagnostics)
             self.stats["dp_reads"] += int(c[6])  # reads whose adapter search ran the bit-vector DP
@@ -326,12 +342,12 @@ class DigestEngine:
                 continue
             break
         if table is not None:
-            table.arena_used = int(c[0])
+            table.arena_used = words_used
             table.ctrl[0] = table.arena_used  # the table's own counter of arena words in use
-            return BatchResult(n, used, int(c[1]), int(c[4]), line_start if keep else None,
-                               win if keep else None, key_off, None, True, int(c[0]) - base_words)
-        return BatchResult(n, used, int(c[1]), int(c[4]), line_start if keep else None, win if keep else None,
-                           key_off, keys, False, int(c[0]))
+            return BatchResult(n, used, int(c[1]), int(c[4]), line_start if keep else None, win, key_off, None, True,
+                               words_used - base_words, ins, n_items)
+        return BatchResult(n, used, int(c[1]), int(c[4]), line_start if keep else None, win, key_off, keys, False,
+                           words_used, ins, n_items)
 
     def collapse_batch(self, table: CollapseTable, br: BatchResult):
         """completeDict[key] += 1 for every key the trim kernel emitted."""
@@ -343,21 +359,21 @@ class DigestEngine:
         if br.n_records == 0 or br.n_emitted == 0:
             return
         d, lib = self.dev, self.dev.lib
-        n_slots = br.n_records * self.E
-        deferred = d.empty(n_slots, torch.int32)
+        scratch = d.empty(2 * br.n_items, torch.int32)
         if br.in_place:
-            table.reserve(br.n_emitted, 0)
-            with d.timed("collapse"):
-                d.check(lib.mirge_collapse_insert_inplace(d.ctx, C.byref(table.struct), _ptr(br.key_off), n_slots,
-                                                          _ptr(deferred), d.stream()))
+            table.reserve(br.n_items, 0)
+            keys = table.arena
         else:
             table.check()
-            table.reserve(br.n_emitted, br.arena_words)
-            with d.timed("collapse"):
-                d.check(lib.mirge_collapse_insert(d.ctx, C.byref(table.struct), _ptr(br.keys), _ptr(br.key_off), n_slots,
-                                                  _ptr(deferred), d.stream()))
-        d.launches += 3
+            table.reserve(br.n_items, br.arena_words)
+            keys = br.keys
+        with d.timed("collapse"):
+            d.check(lib.mirge_collapse_insert_list(d.ctx, C.byref(table.struct), _ptr(keys), _ptr(br.ins), br.n_items,
+                                                   _ptr(scratch), d.stream()))
+        d.launches += 4
+        before = table.n_keys
         table.check()
+        table.new_frac = (table.n_keys - before) / max(br.n_items, 1)
 
     def digest_device(self, buf: torch.Tensor, table: CollapseTable, batch_bytes: int = 256 << 20, on_piece=None) -> int:
         """Whole sample resident on the device: returns the number of records parsed.  ``on_piece(table)`` runs

@@ -75,10 +75,13 @@ class KeySet:
         return cls(dev, arena, key_off, n)
 
 
-def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = False, fused: bool = True, ordered: bool = False,
+def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = False, fused: bool = True, split: bool = True,
                   out=None):
     """Run rounds 0..8 (0..9 with spike-ins) in miRge's order (manifoldAlign.py:86-135).
-    Returns device tensors (annot_round uint8[n] with 0xFF = unannotated, hit int64[n])."""
+    Returns device tensors (annot_round uint8[n] with 0xFF = unannotated, hit int64[n]).
+    ``split`` (default): CTA per tile of sequences, filter phase for all rounds, then per-round compaction and
+    full-warp search; ``fused`` without ``split``: one thread per sequence runs all rounds; neither: one
+    whole-table launch per round."""
     n = keys.n
     if out is not None:  # caller-provided result arrays (initialised to 0xFF / -1 by the caller)
         annot, hit = out
@@ -93,11 +96,10 @@ def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = 
         # all rounds in one launch: every key is read once and leaves at the first round that hits it
         lib_arr = (abi.Library * n_rounds)(*[libs[ROUND_LIBS[r]].struct for r in range(n_rounds)])
         pol_arr = (abi.RoundPolicy * n_rounds)(*pols[:n_rounds])
-        order = dev.empty(abi.ANNOTATE_ORDER_BINS + n, torch.int32) if ordered else None
         with dev.timed("annotate"):
             dev.check(dev.lib.mirge_annotate_rounds(dev.ctx, lib_arr, pol_arr, n_rounds, C.byref(keys.struct), n,
-                                                    _ptr(annot), _ptr(hit), _ptr(order), dev.stream()))
-        dev.launches += 4 if ordered else 1
+                                                    _ptr(annot), _ptr(hit), 1 if split else 0, dev.stream()))
+        dev.launches += 1
         return annot[:n], hit[:n]
     for rnd in range(n_rounds):
         lib = libs[ROUND_LIBS[rnd]]

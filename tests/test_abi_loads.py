@@ -18,7 +18,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(abi.SYMBOLS), declared ^ set(abi.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.mirge_abi_version() == 1
+    assert lib.mirge_abi_version() == abi.ABI_VERSION == 2
 
 
 def test_struct_sizes_match_header():

@@ -120,8 +120,10 @@ def test_rounds_match_oracle(dev):
         assert set(np.unique(a_o)) >= set(range(9)), np.unique(a_o)
         assert (a_o == 0xFF).sum() > 0
         # one launch per round (mirge_annotate_round) gives the same as the fused launch
-        a_u, h_u = MA.annotate_keys(dev, ls, ks, spike, fused=False)
-        assert np.array_equal(a_u.cpu().numpy(), a_g) and np.array_equal(h_u.cpu().numpy().view(np.uint64), h_g)
+        # (the default above is the split form: filter pre-pass + one list-driven search per round)
+        for kw in ({"fused": False}, {"fused": True, "split": False}):
+            a_u, h_u = MA.annotate_keys(dev, ls, ks, spike, **kw)
+            assert np.array_equal(a_u.cpu().numpy(), a_g) and np.array_equal(h_u.cpu().numpy().view(np.uint64), h_g), kw
 
 
 def test_python_oracle_spot_check(dev):

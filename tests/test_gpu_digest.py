@@ -229,3 +229,28 @@ def test_host_streamer_pipeline_matches_device_path(dev):
     with pytest.raises(D.FastqFormatError):
         long_rec = b"@r\n" + b"A" * 400 + b"\n+\n" + b"I" * 400 + b"\n"
         DG.HostStreamer(eng, 64, max_record=64, n_buf=2).run(io.BytesIO(long_rec * 3), table)
+
+
+def test_arena_growth_tracks_unique_keys(dev):
+    """with the trim kernels writing every emitted key into the table's arena, a cohort of samples that
+    repeat the same sequences grew the arena with the number of reads.  The engine now switches to a batch key
+    buffer + copying insert as soon as repeats dominate a batch, so the arena stops growing."""
+    from mirge_b200 import device as D
+
+    cfg = CONFIGS["default"]
+    data = random_fastq(4000, seed=5)
+    fq = np.frombuffer(data, dtype=np.uint8)
+    eng = D.DigestEngine(dev, cfg)
+    _, tab = coracle.digest_collapse(fq, dev.trim_params)
+    exp = tab.to_dict()
+    table = D.CollapseTable(dev, min_keys=1 << 10)
+    buf = to_dev(dev, data)
+    used = []
+    for sample in range(6):
+        assert eng.digest_device(buf, table, batch_bytes=200000) == 4000
+        table.check()
+        used.append(table.arena_used)
+        assert table_dict(table) == exp  # drained per sample: every sample counts the same
+    assert table.n_keys == len(exp)
+    assert used[-1] == used[1], used  # no growth once the repeats are recognised
+    assert used[1] <= 2 * used[0]

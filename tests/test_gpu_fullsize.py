@@ -75,8 +75,8 @@ def test_c2_full_size_properties():
 
     # annotation of the 39 M sequences: independent of the processing order, and every annotated key has a hit
     keys = MA.KeySet.from_table(ta)
-    a1, h1 = MA.annotate_keys(dev, lset, keys, False, ordered=False)
-    a2, h2 = MA.annotate_keys(dev, lset, keys, False, ordered=True)
+    a1, h1 = MA.annotate_keys(dev, lset, keys, False, split=True)   # several pre-pass chunks at this size
+    a2, h2 = MA.annotate_keys(dev, lset, keys, False, split=False)  # the fused single launch
     assert torch.equal(a1, a2) and torch.equal(h1, h2)
     assert torch.equal(a1 != 0xFF, h1 != -1) and int((a1 != 0xFF).sum()) > 1_000_000
     del ta, keys, a1, a2, h1, h2, ids, cnt, ids2, cnt2
