@@ -140,6 +140,10 @@ typedef struct mirge_library {
   uint32_t ref_block_shift;
   uint32_t filter_bases;        /* 0 = no prefix filter, else 4..16: d_filter has 4^filter_bases bits */
   const uint32_t *d_filter;     /* presence bitmap of the first filter_bases bases of every indexed position */
+  uint32_t filter16_bits;       /* 0 = none, else 16..30: d_filter16 has 2^filter16_bits bits */
+  uint32_t max_ref_len;         /* length of the longest reference (0 = unknown): an end-to-end alignment of a longer
+                                   query cannot exist, the round is skipped for it */
+  const uint32_t *d_filter16;   /* presence bitmap of a 32-bit mix of every complete 16-mer (mirge_lib_filter16) */
 } mirge_library;
 
 #define MIRGE_SELECT_LEN_LT26 0    /* round 0 (manifoldAlign.py:93)  */
@@ -302,6 +306,12 @@ int mirge_lib_kmers(mirge_ctx *ctx, const mirge_library *lib, uint32_t *d_kmer, 
  * mirge_library.d_filter.  A seed piece whose prefix bit is clear has no occurrence in the library. */
 int mirge_lib_filter(mirge_ctx *ctx, const uint32_t *d_kmer, const uint8_t *d_valid, uint32_t n_bases,
                      uint32_t prefix_bases, uint32_t *d_filter, void *stream);
+/* The same for complete 16-mers through a hash: bit (mix32(16-mer) >> (32 - bits)) of d_filter16 (2^bits bits, zeroed
+ * here, bits = 16..30) is set for every position with 16 usable bases.  A 16-base seed piece whose bit is clear does
+ * not occur in the library; with 64 bits per position one look-up in 64 of an absent piece passes (the prefix
+ * bitmap of a small library passes one in 16-20).  mirge_library.d_filter16 / filter16_bits. */
+int mirge_lib_filter16(mirge_ctx *ctx, const uint32_t *d_kmer, const uint8_t *d_valid, uint32_t n_bases,
+                       uint32_t bits, uint32_t *d_filter16, void *stream);
 /* One bowtie round over the keys of table t.  Keys selected by policy->select that have a valid
  * alignment get d_annot_round[id] = policy->round and d_hit[id] = canonical pick (minimum of
  * (n_mismatch, reference index, offset) over the valid hit set). */
@@ -310,13 +320,13 @@ int mirge_annotate_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_r
                          uint64_t *d_hit, void *stream);
 
 /* The same for several consecutive rounds (libs[i] / policies[i] = round i of the call).  At most 10 rounds per call.
- * form 0: one thread per sequence runs all rounds (the sequence leaves at the first round that hits it).
- * form 1 (the product path): a CTA owns a tile of 2048 sequences; a filter phase evaluates the seed-piece prefix
- * filters of all rounds into a round mask per sequence, then, round by round, the sequences that still need a search
- * are compacted in shared memory and searched with full, homogeneous warps.  Same results. */
+ * d_scratch == NULL: one thread per sequence runs all rounds (the sequence leaves at the first round that hits it).
+ * d_scratch = 2 * n_keys bytes (the product path): pass 1 evaluates the seed-piece filters of all rounds of every
+ * sequence into a round mask; pass 2 gives a warp 512 sequences, which it compacts and searches round by round
+ * with full, homogeneous lanes.  Same results. */
 int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, const mirge_round_policy *policies,
                           int n_rounds, const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round,
-                          uint64_t *d_hit, int form, void *stream);
+                          uint64_t *d_hit, void *d_scratch, void *stream);
 
 /* Every hit of the best stratum for the sequences d_ids[0..n_ids) that `policy`'s round annotated (bowtie
  * -a --best --strata, rounds 2 and 3; feeds the per-round SAM files of -trf / -bam, manifoldAlign.py:20-62).

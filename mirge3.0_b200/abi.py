@@ -87,6 +87,9 @@ class Library(C.Structure):
         ("ref_block_shift", C.c_uint32),
         ("filter_bases", C.c_uint32),
         ("d_filter", C.c_void_p),
+        ("filter16_bits", C.c_uint32),
+        ("max_ref_len", C.c_uint32),
+        ("d_filter16", C.c_void_p),
     ]
 
 
@@ -145,9 +148,10 @@ SYMBOLS = {
     "mirge_partition_scatter": (C.c_int, [_P, C.POINTER(Table), _P, _P, _P, _P, _U64, C.c_uint32, _P, _P, _P, _P]),
     "mirge_lib_kmers": (C.c_int, [_P, C.POINTER(Library), _P, _P, _P]),
     "mirge_lib_filter": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, _P, _P]),
+    "mirge_lib_filter16": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     "mirge_annotate_rounds": (
         C.c_int,
-        [_P, C.POINTER(Library), C.POINTER(RoundPolicy), C.c_int, C.POINTER(Table), _U64, _P, _P, C.c_int, _P],
+        [_P, C.POINTER(Library), C.POINTER(RoundPolicy), C.c_int, C.POINTER(Table), _U64, _P, _P, _P, _P],
     ),
     "mirge_annotate_allhits": (
         C.c_int,

@@ -77,6 +77,43 @@ extern "C" int mirge_lib_filter(mirge_ctx *ctx, const uint32_t *d_kmer, const ui
   return MIRGE_OK;
 }
 
+// Presence bitmap of complete 16-mers through a 32-bit mix (no false negatives; see mirge_lib_filter16 in the header)
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ bool filter16_pass(const mirge_library &lib, uint32_t kmer) {
+  const uint32_t fi = mix32(kmer) >> (32 - lib.filter16_bits);
+  return (lib.d_filter16[fi >> 5] >> (fi & 31)) & 1u;
+}
+
+__global__ void __launch_bounds__(256)
+lib_filter16_kernel(const uint32_t *__restrict__ kmer, const uint8_t *__restrict__ valid, uint32_t n, uint32_t bits,
+                    uint32_t *__restrict__ filter) {
+  const uint32_t p = blockIdx.x * 256u + threadIdx.x;
+  if (p >= n || valid[p] < 16) return;
+  const uint32_t fi = mix32(kmer[p]) >> (32 - bits);
+  atomicOr(filter + (fi >> 5), 1u << (fi & 31));
+}
+
+extern "C" int mirge_lib_filter16(mirge_ctx *ctx, const uint32_t *d_kmer, const uint8_t *d_valid, uint32_t n_bases, uint32_t bits,
+                                  uint32_t *d_filter16, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  if (!d_kmer || !d_valid || !d_filter16) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "lib_filter16: null buffer");
+  if (bits < 16 || bits > 30) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "lib_filter16: 16..30 bits");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  MIRGE_CUDA(ctx, cudaMemsetAsync(d_filter16, 0, (size_t)1 << (bits - 3), stream));
+  if (n_bases == 0) return MIRGE_OK;
+  lib_filter16_kernel<<<(n_bases + 255) / 256, 256, 0, stream>>>(d_kmer, d_valid, n_bases, bits, d_filter16);
+  MIRGE_LAUNCH_CHECK(ctx, "lib_filter16_kernel");
+  return MIRGE_OK;
+}
+
 // ------------------------------------------------------------------ search -------------------
 
 #define MAX_PIECES 4
@@ -108,6 +145,8 @@ __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const
   uint32_t p_lo[MAX_PIECES], p_hi[MAX_PIECES], p_off[MAX_PIECES];
 #pragma unroll
   for (int i = 0; i < MAX_PIECES; ++i) p_lo[i] = p_hi[i] = p_off[i] = 0;
+  // an end-to-end alignment lies inside one reference: a query longer than the longest reference has none
+  if (lib.max_ref_len && (uint32_t)L > lib.max_ref_len) active = false;
   const int R = pol.seed_len == 0 ? L : min(pol.seed_len, L);
   const int np = pol.seed_mm + 1;
   const bool degenerate = active && (R < MIN_SEED * np);
@@ -120,7 +159,9 @@ __device__ __forceinline__ uint64_t search_round(const mirge_library &lib, const
       if (has_exc && query_has_n(qnx, a, b)) continue;
       const uint32_t span = (s == 16) ? 0u : ((1u << (2 * (16 - s))) - 1u);
       const uint32_t k_lo = query_kmer16(qw, a, nw) & ~span, k_hi = k_lo | span;
-      if (lib.filter_bases && (uint32_t)s >= lib.filter_bases) {  // prefix absent from the library: no candidates
+      if (s == 16 && lib.filter16_bits && lib.filter_bases < 16) {  // complete 16-mer absent from the library
+        if (!filter16_pass(lib, k_lo)) continue;
+      } else if (lib.filter_bases && (uint32_t)s >= lib.filter_bases) {  // prefix absent from the library: no candidates
         const uint32_t fi = lib.filter_bases >= 16 ? k_lo : (k_lo >> (32 - 2 * lib.filter_bases));
         if (!((lib.d_filter[fi >> 5] >> (fi & 31)) & 1u)) continue;
       }
@@ -334,19 +375,17 @@ allhits_kernel(mirge_library lib, mirge_round_policy pol, mirge_table t, const u
   if (!fill) counts[i] = k;
 }
 
-// ---- tiled rounds: per-CTA filter phase -> per-round compaction in shared memory -> full-warp search -----------
+// ---- two-pass rounds: filter masks for all rounds -> per-warp compaction and search ---------------------------
 // In the fused kernel above a warp runs nine rounds at the pace of its busiest lane, and most lanes hold sequences no
-// library contains (HEAD counting keeps the untrimmed reads): per round they evaluate their seed pieces' prefix
-// filters, find nothing and wait.  Here a CTA owns a tile of TILE_KEYS consecutive sequences.  Phase A evaluates
-// the prefix filters of ALL rounds for every sequence of the tile -- no search, no dependent index look-ups -- into a
-// per-sequence round mask in shared memory.  Then, round by round, the CTA compacts the sequences that round still
-// has to search (mask bit set, and not annotated by an earlier round) into a shared-memory list and searches them
-// with full warps: every lane holds a sequence with at least one piece the library may contain, all lanes use the
-// same library and policy.  Nothing leaves the CTA between the phases: no global lists, no global atomics, and the
-// order of the rounds is the CTA's own program order.  The masks are a superset (phase A ignores what earlier rounds
-// will find; the search re-checks everything), so results cannot differ from the fused form.
-#define TILE_KEYS 2048
-static_assert(TILE_KEYS % ANN_THREADS == 0, "tile must be a whole number of CTA sweeps");
+// library contains (HEAD counting keeps the untrimmed reads): per round they evaluate their seed pieces' filters,
+// find nothing and wait.  Pass 1 (annot_mask_kernel) does that part for ALL rounds of every sequence in one
+// streaming kernel -- no search, no dependent index look-ups -- and leaves a round mask per sequence.  Pass 2
+// (annot_search_kernel) hands a warp 512 consecutive sequences: round by round the warp compacts the ones that round
+// still has to search (mask bit set, and not annotated by an earlier round) into a shared-memory list and searches
+// them 32 at a time: every lane holds a sequence with at least one piece the library may contain, all lanes use
+// the same library and policy, and the order of the rounds is the warp's own program order.  The masks are a
+// superset (pass 1 ignores what earlier rounds will find; the search re-checks everything), so results cannot
+// differ from the fused form.
 
 // rounds (bit ri of the result) in which the key may have a candidate; state = annotation before this call
 __device__ __forceinline__ uint32_t round_mask(const RoundSet &rs, const KeyView &kv, uint32_t state) {
@@ -366,6 +405,7 @@ __device__ __forceinline__ uint32_t round_mask(const RoundSet &rs, const KeyView
     int qs, qe;
     if (!round_window(kv, pol, tlen, qs, qe)) continue;
     const int L = qe - qs;
+    if (lib.max_ref_len && (uint32_t)L > lib.max_ref_len) continue;
     if (qs != cur_qs || qe != cur_qe) {
       build_query(kv, qs, qe, qw, qnx);
       cur_qs = qs;
@@ -382,7 +422,9 @@ __device__ __forceinline__ uint32_t round_mask(const RoundSet &rs, const KeyView
         const int a = piece_bound(pi, R, np), b = piece_bound(pi + 1, R, np);
         const int s = min(16, b - a);
         if (has_exc && query_has_n(qnx, a, b)) continue;
-        if (lib.filter_bases && (uint32_t)s >= lib.filter_bases) {
+        if (s == 16 && lib.filter16_bits && lib.filter_bases < 16) {
+          pass |= filter16_pass(lib, query_kmer16(qw, a, nw));
+        } else if (lib.filter_bases && (uint32_t)s >= lib.filter_bases) {
           const uint32_t span = (s == 16) ? 0u : ((1u << (2 * (16 - s))) - 1u);
           const uint32_t k_lo = query_kmer16(qw, a, nw) & ~span;
           const uint32_t fi = lib.filter_bases >= 16 ? k_lo : (k_lo >> (32 - 2 * lib.filter_bases));
@@ -397,53 +439,141 @@ __device__ __forceinline__ uint32_t round_mask(const RoundSet &rs, const KeyView
   return mask;
 }
 
-struct TileShared {
-  uint16_t mask[TILE_KEYS];
-  uint16_t list[TILE_KEYS];
-  uint8_t state[TILE_KEYS];
-  uint32_t count;
-  WarpScratch ws[ANN_THREADS / 32];
+// Lean form of round_mask for the common key (no exception words, <= LEAN_WORDS payload words): the payload sits in a
+// shared-memory column of the thread (dynamic word index without local memory), a piece's 16 bases are one funnel
+// shift of two of those words, and nothing is copied per window.  Bases of the 16-base window beyond the piece are
+// masked by the prefix span exactly as in search_round, so the look-ups are the same ones.
+#define LEAN_WORDS 8
+#define MASK_THREADS 256
+__device__ __forceinline__ uint32_t lean_kmer16(const uint32_t *col, int p) {  // 16 bases from base p, first base most significant
+  const int wi = p >> 4, sh = 2 * (p & 15);
+  const uint32_t v = __funnelshift_r(col[wi * MASK_THREADS], col[(wi + 1) * MASK_THREADS], sh);
+  const uint32_t r = __brev(v);
+  return ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+}
+
+__device__ __forceinline__ uint32_t round_mask_lean(const RoundSet &rs, const uint32_t *col, int len, uint32_t state) {
+  int tlen = -1;
+  uint32_t mask = 0;
+  for (int ri = 0; ri < rs.n; ++ri) {
+    const mirge_round_policy &pol = rs.pol[ri];
+    const mirge_library &lib = rs.lib[ri];
+    bool active;
+    if (pol.select == MIRGE_SELECT_LEN_LT26) active = len < 26;
+    else if (pol.select == MIRGE_SELECT_LEN_GT25) active = len > 25;
+    else active = state == 0xFF;
+    if (!active) continue;
+    int qs = 0, qe = len;
+    if (pol.strip_polyT) {
+      if (tlen < 0) {
+        int tpos = len;
+        while (tpos > 0 && ((col[((tpos - 1) >> 4) * MASK_THREADS] >> (2 * ((tpos - 1) & 15))) & 3u) == 3u) --tpos;
+        tlen = tpos;
+      }
+      if (len - tlen < 3) continue;
+      qe = tlen;
+    }
+    qs += pol.trim5;
+    qe -= pol.trim3;
+    if (qe <= qs) continue;
+    const int L = qe - qs;
+    if (lib.max_ref_len && (uint32_t)L > lib.max_ref_len) continue;
+    const int R = pol.seed_len == 0 ? L : min(pol.seed_len, L);
+    const int np = pol.seed_mm + 1;
+    bool pass = false;
+    if (R < MIN_SEED * np) {
+      pass = true;
+    } else {
+      int a = 0;
+      for (int pi = 0; pi < np; ++pi) {
+        const int b = piece_bound(pi + 1, R, np);
+        const int s = min(16, b - a);
+        const uint32_t k16 = lean_kmer16(col, qs + a);
+        if (s == 16 && lib.filter16_bits && lib.filter_bases < 16) {
+          pass |= filter16_pass(lib, k16);
+        } else if (lib.filter_bases && (uint32_t)s >= lib.filter_bases) {
+          const uint32_t fi = lib.filter_bases >= 16 ? k16 : (k16 >> (32 - 2 * lib.filter_bases));
+          pass |= ((lib.d_filter[fi >> 5] >> (fi & 31)) & 1u) != 0u;
+        } else {
+          pass = true;
+        }
+        a = b;
+      }
+    }
+    if (pass) mask |= 1u << ri;
+  }
+  return mask;
+}
+
+// pass 1: the round mask of every sequence (streaming: one thread per sequence, nothing but filter look-ups)
+__global__ void __launch_bounds__(MASK_THREADS)
+annot_mask_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_keys, const uint8_t *__restrict__ annot_round,
+                  uint16_t *__restrict__ masks) {
+  __shared__ uint32_t s_pay[LEAN_WORDS + 2][MASK_THREADS];
+  const uint64_t id = (uint64_t)blockIdx.x * MASK_THREADS + threadIdx.x;
+  if (id >= n_keys) return;
+  const uint32_t *key = t.d_arena + t.d_key_ref[id];
+  const uint32_t state = annot_round[id];
+  const KeyView kv = key_view(key);
+  const int npay = (kv.len + 15) >> 4;
+  uint32_t mask;
+  if (kv.nexc == 0 && npay <= LEAN_WORDS) {
+    uint32_t *col = &s_pay[0][threadIdx.x];
+#pragma unroll
+    for (int w = 0; w < LEAN_WORDS + 2; ++w) col[w * MASK_THREADS] = w < npay ? kv.pay[w] : 0u;
+    mask = round_mask_lean(rs, col, kv.len, state);
+  } else {
+    mask = round_mask(rs, kv, state);
+  }
+  masks[id] = (uint16_t)mask;
+}
+
+// pass 2: a WARP owns SUB_KEYS consecutive sequences and runs the rounds on them in order, alone: per round it
+// compacts the sequences to search (mask bit set, not annotated by an earlier round) into its shared-memory list and
+// searches them 32 at a time.  No CTA barrier: warps do not wait for each other's searches.
+#define SUB_KEYS 512
+struct WarpTile {
+  uint16_t mask[SUB_KEYS];
+  uint16_t list[SUB_KEYS];
+  uint8_t state[SUB_KEYS];
+  WarpScratch ws;
 };
 
 __global__ void __launch_bounds__(ANN_THREADS, 8)
-annotate_tile_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_keys, uint8_t *__restrict__ annot_round,
-                     uint64_t *__restrict__ hit) {
-  __shared__ TileShared sh;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint64_t tile0 = (uint64_t)blockIdx.x * TILE_KEYS;
-  const uint32_t n_tile = (uint32_t)min((uint64_t)TILE_KEYS, n_keys - tile0);
-  // phase A: round masks
-  for (uint32_t k = tid; k < n_tile; k += ANN_THREADS) {
-    const uint64_t id = tile0 + k;
-    const uint32_t state = annot_round[id];
-    const KeyView kv = key_view(t.d_arena + t.d_key_ref[id]);
-    sh.mask[k] = (uint16_t)round_mask(rs, kv, state);
-    sh.state[k] = (uint8_t)state;
+annot_search_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_keys, const uint16_t *__restrict__ masks,
+                    uint8_t *__restrict__ annot_round, uint64_t *__restrict__ hit) {
+  __shared__ WarpTile s_wt[ANN_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  WarpTile &W = s_wt[warp];
+  const uint64_t tile0 = ((uint64_t)blockIdx.x * (ANN_THREADS / 32) + warp) * SUB_KEYS;
+  if (tile0 >= n_keys) return;
+  const uint32_t n_tile = (uint32_t)min((uint64_t)SUB_KEYS, n_keys - tile0);
+  uint32_t any = 0;
+  for (uint32_t k = lane; k < SUB_KEYS; k += 32) {
+    const uint32_t m = k < n_tile ? masks[tile0 + k] : 0u;
+    W.mask[k] = (uint16_t)m;
+    W.state[k] = k < n_tile ? annot_round[tile0 + k] : (uint8_t)0;
+    any |= m;
   }
-  if (tid == 0) sh.count = 0;
-  __syncthreads();
+  any = __reduce_or_sync(0xffffffffu, any);
+  __syncwarp();
   for (int ri = 0; ri < rs.n; ++ri) {
+    if (!((any >> ri) & 1u)) continue;
     const mirge_round_policy &pol = rs.pol[ri];
-    // the sequences this round searches
-    for (uint32_t k0 = 0; k0 < TILE_KEYS; k0 += ANN_THREADS) {
-      const uint32_t k = k0 + tid;
-      bool p = k < n_tile && ((sh.mask[k] >> ri) & 1u);
-      if (p && pol.select == MIRGE_SELECT_UNANNOTATED) p = sh.state[k] == 0xFF;
+    uint32_t cnt = 0;
+    for (uint32_t k0 = 0; k0 < SUB_KEYS; k0 += 32) {
+      const uint32_t k = k0 + lane;
+      bool p = (W.mask[k] >> ri) & 1u;
+      if (p && pol.select == MIRGE_SELECT_UNANNOTATED) p = W.state[k] == 0xFF;
       const unsigned bal = __ballot_sync(0xffffffffu, p);
-      if (bal) {
-        const int leader = __ffs(bal) - 1;
-        uint32_t base = 0;
-        if (lane == leader) base = atomicAdd(&sh.count, (uint32_t)__popc(bal));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (p) sh.list[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)k;
-      }
+      if (p) W.list[cnt + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)k;
+      cnt += __popc(bal);
     }
-    __syncthreads();
-    const uint32_t cnt = sh.count;
-    for (uint32_t base = warp * 32; base < cnt; base += ANN_THREADS) {  // uniform per warp
+    __syncwarp();
+    for (uint32_t base = 0; base < cnt; base += 32) {
       const uint32_t idx = base + lane;
       bool active = idx < cnt;
-      const uint32_t k = active ? sh.list[idx] : 0u;
+      const uint32_t k = active ? W.list[idx] : 0u;
       const uint64_t id = tile0 + k;
       uint32_t qw[QW_MAX], qnx[QW_MAX];
       KeyView kv;
@@ -452,23 +582,21 @@ annotate_tile_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_
       if (active) {
         kv = key_view(t.d_arena + t.d_key_ref[id]);
         int qs, qe;
-        active = round_window(kv, pol, tlen, qs, qe);  // (true: the mask bit says so)
+        active = round_window(kv, pol, tlen, qs, qe);
         if (active) {
           L = qe - qs;
           build_query(kv, qs, qe, qw, qnx);
         }
       }
       bool republish = true;
-      const uint64_t best = search_round(rs.lib[ri], pol, active, qw, qnx, L, kv.nexc > 0, sh.ws[warp], republish, lane);
+      const uint64_t best = search_round(rs.lib[ri], pol, active, qw, qnx, L, kv.nexc > 0, W.ws, republish, lane);
       if (active && best != MIRGE_NO_HIT) {
-        sh.state[k] = (uint8_t)pol.round;
+        W.state[k] = (uint8_t)pol.round;
         annot_round[id] = (uint8_t)pol.round;
         hit[id] = best;
       }
     }
-    __syncthreads();
-    if (tid == 0) sh.count = 0;
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -479,6 +607,8 @@ static int check_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_rou
   if (lib->ref_block_shift > 20) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: ref_block_shift out of range");
   if (lib->filter_bases && (!lib->d_filter || lib->filter_bases < 4 || lib->filter_bases > 16))
     MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: bad prefix filter");
+  if (lib->filter16_bits && (!lib->d_filter16 || lib->filter16_bits < 16 || lib->filter16_bits > 30))
+    MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: bad 16-mer filter");
   if (lib->bucket_bits < 1 || lib->bucket_bits > 28) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: bucket_bits out of range");
   if (policy->seed_mm < 0 || policy->seed_mm > 3 || policy->total_mm < policy->seed_mm || policy->trim5 < 0 || policy->trim3 < 0)
     MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: unsupported policy");
@@ -488,11 +618,10 @@ static int check_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_rou
 
 extern "C" int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, const mirge_round_policy *policies, int n_rounds,
                                      const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round, uint64_t *d_hit,
-                                     int form, void *stream_) {
+                                     void *d_scratch, void *stream_) {
   if (!ctx) return MIRGE_ERR_ARG;
   if (!libs || !policies || !t || !d_annot_round || !d_hit) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: null argument");
   if (n_keys > 0xFFFFFFFFull) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: more than 2^32 sequences in one call");
-  if (form != 0 && form != 1) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: unknown form %d", form);
   if (n_rounds < 0 || n_rounds > MAX_ROUNDS) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: at most %d rounds per call", MAX_ROUNDS);
   if (n_keys == 0 || n_rounds == 0) return MIRGE_OK;
   RoundSet rs;
@@ -508,9 +637,14 @@ extern "C" int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, 
   if (rs.n == 0) return MIRGE_OK;
   cudaStream_t stream = (cudaStream_t)stream_;
   MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (form == 1) {
-    annotate_tile_kernel<<<(unsigned)((n_keys + TILE_KEYS - 1) / TILE_KEYS), ANN_THREADS, 0, stream>>>(rs, *t, n_keys, d_annot_round, d_hit);
-    MIRGE_LAUNCH_CHECK(ctx, "annotate_tile_kernel");
+  if (d_scratch) {
+    if ((uintptr_t)d_scratch & 1) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: misaligned scratch");
+    uint16_t *masks = (uint16_t *)d_scratch;
+    annot_mask_kernel<<<(unsigned)((n_keys + MASK_THREADS - 1) / MASK_THREADS), MASK_THREADS, 0, stream>>>(rs, *t, n_keys, d_annot_round, masks);
+    MIRGE_LAUNCH_CHECK(ctx, "annot_mask_kernel");
+    const uint64_t per_cta = (uint64_t)SUB_KEYS * (ANN_THREADS / 32);
+    annot_search_kernel<<<(unsigned)((n_keys + per_cta - 1) / per_cta), ANN_THREADS, 0, stream>>>(rs, *t, n_keys, masks, d_annot_round, d_hit);
+    MIRGE_LAUNCH_CHECK(ctx, "annot_search_kernel");
     return MIRGE_OK;
   }
   annotate_kernel<<<(unsigned)((n_keys + ANN_THREADS - 1) / ANN_THREADS), ANN_THREADS, 0, stream>>>(rs, *t, n_keys, d_annot_round, d_hit);
@@ -522,7 +656,7 @@ extern "C" int mirge_annotate_round(mirge_ctx *ctx, const mirge_library *lib, co
                                     uint64_t n_keys, uint8_t *d_annot_round, uint64_t *d_hit, void *stream_) {
   if (!ctx) return MIRGE_ERR_ARG;
   if (!lib || !policy) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: null argument");
-  return mirge_annotate_rounds(ctx, lib, policy, 1, t, n_keys, d_annot_round, d_hit, 0, stream_);
+  return mirge_annotate_rounds(ctx, lib, policy, 1, t, n_keys, d_annot_round, d_hit, nullptr, stream_);
 }
 
 extern "C" int mirge_annotate_allhits(mirge_ctx *ctx, const mirge_library *lib, const mirge_round_policy *policy, const mirge_table *t,

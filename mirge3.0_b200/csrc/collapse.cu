@@ -12,6 +12,8 @@
 // so the insert path cannot dead-lock.
 #include <cooperative_groups.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 namespace cg = cooperative_groups;
 
@@ -43,7 +45,8 @@ enum { INS_OK = 0, INS_DEFER = 1, INS_FAIL = 2 };
 // the slot it created through *own_slot and a streaming kernel hands out the ids afterwards (assign_ids_kernel).
 template <bool DEFER_ID>
 __device__ __forceinline__ int table_insert(const mirge_table &t, const uint32_t *key, uint32_t nw, uint32_t add,
-                                            uint64_t h, bool unbounded, uint32_t in_arena, uint32_t *own_slot = nullptr) {
+                                            uint64_t h, bool unbounded, uint32_t in_arena, uint32_t *own_slot = nullptr,
+                                            uint32_t *dup_slot = nullptr) {
   unsigned long long *ctrl = (unsigned long long *)t.d_ctrl;
   const uint64_t mask = t.capacity - 1;
   uint32_t tag = (uint32_t)(h >> 32);
@@ -136,6 +139,7 @@ __device__ __forceinline__ int table_insert(const mirge_table &t, const uint32_t
       }
       if (same) {
         atomicAdd(&s->count, add);
+        if (dup_slot) *dup_slot = (uint32_t)idx;
         return INS_OK;
       }
     }
@@ -169,8 +173,8 @@ __device__ __forceinline__ void item_key(int mode, const uint32_t *keys, const u
 
 // Hash of an in-arena key whose length is not known yet: the header and the next seven words are fetched together
 // (clipped to the arena), so the header -> payload dependency costs one memory latency instead of two.
-__device__ __forceinline__ uint64_t hash_key_in_arena(const mirge_table &t, const uint32_t *key, uint32_t aoff, uint32_t &nw) {
-  uint32_t kw[8];
+__device__ __forceinline__ uint64_t hash_key_in_arena(const mirge_table &t, const uint32_t *key, uint32_t aoff, uint32_t &nw,
+                                                   uint32_t kw[8]) {
 #pragma unroll
   for (uint32_t j = 0; j < 8u; ++j) kw[j] = ((uint64_t)aoff + j < t.arena_words) ? key[j] : 0u;
   nw = key_words(kw[0]);
@@ -193,7 +197,8 @@ collapse_insert_kernel(mirge_table t, const uint32_t *__restrict__ keys, const u
   uint32_t nw;
   uint64_t h;
   if (mode == 3) {  // uniform: the keys lie in the table's arena
-    h = hash_key_in_arena(t, key, in_arena, nw);
+    uint32_t kw[8];
+    h = hash_key_in_arena(t, key, in_arena, nw, kw);
   } else {
     nw = key_words(key[0]);
     h = hash_key(key, nw);
@@ -225,28 +230,86 @@ __global__ void clear_deferred_kernel(unsigned long long *ctrl) { ctrl[3] = 0; }
 // ---- the insert list of a batch (mirge_trim): one distinct key of a read per lane ------------------------------
 #define NO_SLOT 0xFFFFFFFFu
 
+// Hot keys.  Small-RNA samples are dominated by a few hundred sequences (the top miRNA alone is several per cent of
+// the reads), and every repeat of such a key costs three transactions at ONE L2 slice -- the slot, the owner's key
+// text, the count atomic -- so that slice sets the pace of the whole kernel (ncu: busiest slice 49 % busy, average
+// 17 %).  A CTA therefore walks a contiguous chunk of the list and remembers the repeated keys it meets in a
+// direct-mapped shared-memory cache (hash -> slot, key text, pending count): later repeats inside the chunk are
+// decided against the cached text (exact comparison, not the hash) and counted in shared memory; the pending counts
+// go to the slots with one atomic per entry when the CTA is done.  Only keys of <= 8 words are cached (reads of up
+// to 112 bases without exceptions); longer ones take the global path.
+#define HK_ENT 512
+#define HK_ITEMS 4  // list items per thread (default; MIRGE_B200_HK_ITEMS overrides for experiments)
+struct HotCache {
+  unsigned long long hash[HK_ENT];
+  uint32_t state[HK_ENT];  // 0 empty, 1 being filled, 2 valid
+  uint32_t slot[HK_ENT];
+  uint32_t pend[HK_ENT];
+  uint32_t key[8][HK_ENT];
+};
+
 // IN_PLACE: the keys lie in the table's arena (the trim kernels wrote them there).  own[i] = slot this item
 // created, NO_SLOT when the key existed (or the item was deferred).
 template <bool IN_PLACE>
 __global__ void __launch_bounds__(COL_THREADS)
 collapse_list_kernel(mirge_table t, const uint32_t *__restrict__ keys, const uint2 *__restrict__ ins, uint64_t n,
-                     uint32_t *__restrict__ own, uint32_t *__restrict__ deferred) {
-  const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
-  if (i >= n) return;
-  const uint2 it = ins[i];
-  const uint32_t o = it.x, add = it.y;
-  const uint32_t *key = keys + o;
-  uint32_t nw, slot = NO_SLOT;
-  uint64_t h;
-  if (IN_PLACE) {
-    h = hash_key_in_arena(t, key, o, nw);
-  } else {
-    nw = key_words(key[0]);
-    h = hash_key(key, nw);
+                     uint32_t *__restrict__ own, uint32_t *__restrict__ deferred, const int per_thread) {
+  __shared__ HotCache hc;
+  for (int e = threadIdx.x; e < HK_ENT; e += COL_THREADS) { hc.state[e] = 0; hc.pend[e] = 0; }
+  __syncthreads();
+  const uint64_t chunk0 = (uint64_t)blockIdx.x * COL_THREADS * per_thread;
+  for (int it = 0; it < per_thread; ++it) {
+    const uint64_t i = chunk0 + (uint64_t)it * COL_THREADS + threadIdx.x;
+    if (i >= n) break;
+    const uint2 item = ins[i];
+    const uint32_t o = item.x, add = item.y;
+    const uint32_t *key = keys + o;
+    uint32_t nw, slot = NO_SLOT, dslot = NO_SLOT, kw[8];
+    uint64_t h;
+    if (IN_PLACE) {
+      h = hash_key_in_arena(t, key, o, nw, kw);
+    } else {
+      nw = key_words(key[0]);
+#pragma unroll
+      for (uint32_t j = 0; j < 8u; ++j) kw[j] = j < nw ? key[j] : 0u;
+      h = hash_key(key, nw);
+    }
+    const uint32_t e = (uint32_t)(h >> 23) & (HK_ENT - 1);
+    bool counted = false;
+    if (nw <= 8u && *(volatile uint32_t *)&hc.state[e] == 2u) {
+      __threadfence_block();
+      if (*(volatile unsigned long long *)&hc.hash[e] == h) {
+        uint32_t d = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < 8u; ++j)
+          if (j < nw) d |= *(volatile uint32_t *)&hc.key[j][e] ^ kw[j];
+        if (d == 0u) {
+          atomicAdd(&hc.pend[e], add);
+          counted = true;
+        }
+      }
+    }
+    if (counted) {
+      own[i] = NO_SLOT;
+      continue;
+    }
+    const int rc = table_insert<true>(t, key, nw, add, h, false, IN_PLACE ? o : NOT_IN_ARENA, &slot, &dslot);
+    own[i] = slot;
+    if (rc == INS_DEFER) {
+      defer_item((unsigned long long *)t.d_ctrl + 3, deferred, (uint32_t)i);
+    } else if (dslot != NO_SLOT && nw <= 8u && atomicCAS(&hc.state[e], 0u, 1u) == 0u) {
+      // a key that repeats: remember it (first come; the head of the distribution gets there first)
+      hc.hash[e] = h;
+      hc.slot[e] = dslot;
+#pragma unroll
+      for (uint32_t j = 0; j < 8u; ++j) hc.key[j][e] = kw[j];
+      __threadfence_block();
+      atomicExch(&hc.state[e], 2u);
+    }
   }
-  const int rc = table_insert<true>(t, key, nw, add, h, false, IN_PLACE ? o : NOT_IN_ARENA, &slot);
-  own[i] = slot;
-  if (rc == INS_DEFER) defer_item((unsigned long long *)t.d_ctrl + 3, deferred, (uint32_t)i);
+  __syncthreads();
+  for (int e = threadIdx.x; e < HK_ENT; e += COL_THREADS)
+    if (hc.state[e] == 2u && hc.pend[e]) atomicAdd(&t.d_slots[hc.slot[e]].count, hc.pend[e]);
 }
 
 template <bool IN_PLACE>
@@ -354,12 +417,19 @@ extern "C" int mirge_collapse_insert_list(mirge_ctx *ctx, const mirge_table *t, 
   MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
   uint32_t *own = d_scratch, *deferred = d_scratch + n_items;
   const unsigned grid = (unsigned)((n_items + COL_THREADS - 1) / COL_THREADS);
+  static int per_thread = 0;
+  if (!per_thread) {
+    const char *e = getenv("MIRGE_B200_HK_ITEMS");
+    per_thread = e ? atoi(e) : HK_ITEMS;
+    if (per_thread < 1 || per_thread > 4096) per_thread = HK_ITEMS;
+  }
+  const unsigned lgrid = (unsigned)((n_items + (uint64_t)COL_THREADS * per_thread - 1) / ((uint64_t)COL_THREADS * per_thread));
   if (d_keys == t->d_arena) {
-    collapse_list_kernel<true><<<grid, COL_THREADS, 0, stream>>>(*t, d_keys, ins, n_items, own, deferred);
+    collapse_list_kernel<true><<<lgrid, COL_THREADS, 0, stream>>>(*t, d_keys, ins, n_items, own, deferred, per_thread);
     collapse_list_retry_kernel<true><<<ctx->sm_count, COL_THREADS, 0, stream>>>(*t, d_keys, ins, own, deferred);
     assign_ids_kernel<true><<<grid, COL_THREADS, 0, stream>>>(*t, ins, own, n_items);
   } else {
-    collapse_list_kernel<false><<<grid, COL_THREADS, 0, stream>>>(*t, d_keys, ins, n_items, own, deferred);
+    collapse_list_kernel<false><<<lgrid, COL_THREADS, 0, stream>>>(*t, d_keys, ins, n_items, own, deferred, per_thread);
     collapse_list_retry_kernel<false><<<ctx->sm_count, COL_THREADS, 0, stream>>>(*t, d_keys, ins, own, deferred);
     assign_ids_kernel<false><<<grid, COL_THREADS, 0, stream>>>(*t, ins, own, n_items);
   }

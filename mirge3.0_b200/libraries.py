@@ -114,14 +114,16 @@ class DeviceLibrary:
         if len(lens) and int(lens.max()) >= (1 << 28):
             raise MirgeError("library %s has a reference longer than 2^28 bases" % key)
         self.ref_off_host = off
+        self.max_ref_len = int(lens.max()) if len(lens) else 0
         self.ref_off = torch.from_numpy(off.astype(np.uint32).view(np.int32)).to(dev.tdev)
         text = torch.frombuffer(bytearray(b"".join(seqs)), dtype=torch.uint8).to(dev.tdev) if self.n_bases else \
             torch.zeros(0, dtype=torch.uint8, device=dev.tdev)
         self.packed, self.nmask = pack_text(text)
         # MIRGE_LIB_PAD_WORDS zero words after the text: the verifier may read past the last reference
         self.packed = torch.cat([self.packed, torch.zeros(abi.LIB_PAD_WORDS, dtype=torch.int32, device=dev.tdev)])
-        self.idx_kmer = self.idx_pos = self.idx_bucket = self.filter = None
+        self.idx_kmer = self.idx_pos = self.idx_bucket = self.filter = self.filter16 = None
         self.filter_bases = 0
+        self.filter16_bits = 0
         self.n_idx = 0
         self.bucket_bits = 4
         # coarse position -> reference map (one entry per 64 bases) replacing a binary search over ref_off
@@ -150,7 +152,8 @@ class DeviceLibrary:
                            0 if self.idx_pos is None else self.idx_pos.data_ptr(), self.n_idx, self.bucket_bits,
                            0 if self.idx_bucket is None else self.idx_bucket.data_ptr(),
                            self.ref_block.data_ptr(), self.ref_block_shift, self.filter_bases,
-                           0 if self.filter is None else self.filter.data_ptr())
+                           0 if self.filter is None else self.filter.data_ptr(), self.filter16_bits, self.max_ref_len,
+                           0 if self.filter16 is None else self.filter16.data_ptr())
 
     def _build_index(self):
         d = self.dev
@@ -169,6 +172,15 @@ class DeviceLibrary:
         d.check(d.lib.mirge_lib_filter(d.ctx, _ptr(kmer), _ptr(valid), self.n_bases, fb, _ptr(self.filter), d.stream()))
         d.launches += 1
         self.filter_bases = fb
+        # complete 16-mers through a hash, 64 bits per position (at most 64 MB: it has to stay in L2); a library whose
+        # prefix bitmap already addresses whole 16-mers (mRNA) needs none
+        n16 = int((valid >= 16).sum().item())
+        if fb < 16 and n16 > 0:
+            bits = int(min(29, max(16, math.ceil(math.log2(64 * n16)))))
+            self.filter16 = d.empty(1 << (bits - 5), torch.int32)
+            d.check(d.lib.mirge_lib_filter16(d.ctx, _ptr(kmer), _ptr(valid), self.n_bases, bits, _ptr(self.filter16), d.stream()))
+            d.launches += 1
+            self.filter16_bits = bits
         pos = torch.nonzero(valid >= MIN_INDEX_K).squeeze(1)
         k64 = kmer[pos].to(torch.int64) & 0xFFFFFFFF
         del kmer, valid

@@ -79,9 +79,9 @@ def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = 
                   out=None):
     """Run rounds 0..8 (0..9 with spike-ins) in miRge's order (manifoldAlign.py:86-135).
     Returns device tensors (annot_round uint8[n] with 0xFF = unannotated, hit int64[n]).
-    ``split`` (default): CTA per tile of sequences, filter phase for all rounds, then per-round compaction and
-    full-warp search; ``fused`` without ``split``: one thread per sequence runs all rounds; neither: one
-    whole-table launch per round."""
+    ``split`` (default): a streaming pass leaves a round mask per sequence (seed-piece filters of all rounds), then
+    warps compact and search their sequences round by round; ``fused`` without ``split``: one thread per sequence
+    runs all rounds; neither: one whole-table launch per round."""
     n = keys.n
     if out is not None:  # caller-provided result arrays (initialised to 0xFF / -1 by the caller)
         annot, hit = out
@@ -96,10 +96,11 @@ def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = 
         # all rounds in one launch: every key is read once and leaves at the first round that hits it
         lib_arr = (abi.Library * n_rounds)(*[libs[ROUND_LIBS[r]].struct for r in range(n_rounds)])
         pol_arr = (abi.RoundPolicy * n_rounds)(*pols[:n_rounds])
+        scratch = dev.empty(n, torch.int16) if split else None
         with dev.timed("annotate"):
             dev.check(dev.lib.mirge_annotate_rounds(dev.ctx, lib_arr, pol_arr, n_rounds, C.byref(keys.struct), n,
-                                                    _ptr(annot), _ptr(hit), 1 if split else 0, dev.stream()))
-        dev.launches += 1
+                                                    _ptr(annot), _ptr(hit), _ptr(scratch), dev.stream()))
+        dev.launches += 2 if split else 1
         return annot[:n], hit[:n]
     for rnd in range(n_rounds):
         lib = libs[ROUND_LIBS[rnd]]
