@@ -321,9 +321,11 @@ int mirge_annotate_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_r
 
 /* The same for several consecutive rounds (libs[i] / policies[i] = round i of the call).  At most 10 rounds per call.
  * d_scratch == NULL: one thread per sequence runs all rounds (the sequence leaves at the first round that hits it).
- * d_scratch = 2 * n_keys bytes (the product path): pass 1 evaluates the seed-piece filters of all rounds of every
- * sequence into a round mask; pass 2 gives a warp 512 sequences, which it compacts and searches round by round
- * with full, homogeneous lanes.  Same results. */
+ * d_scratch = mirge_annotate_scratch_bytes(n_keys) bytes, 8-byte aligned (the product path): pass 1 evaluates the
+ * seed-piece filters of all rounds of every sequence into a round mask; pass 2 gives a warp 256 sequences, which it
+ * compacts and searches round by round from a shared-memory copy of each key; sequences that search does not take
+ * (exception words, > 128 bases, many candidates) are listed and finished by pass 3 with the general code.  Same results. */
+uint64_t mirge_annotate_scratch_bytes(uint64_t n_keys);
 int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, const mirge_round_policy *policies,
                           int n_rounds, const mirge_table *t, uint64_t n_keys, uint8_t *d_annot_round,
                           uint64_t *d_hit, void *d_scratch, void *stream);

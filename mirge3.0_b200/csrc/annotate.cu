@@ -445,11 +445,35 @@ __device__ __forceinline__ uint32_t round_mask(const RoundSet &rs, const KeyView
 // masked by the prefix span exactly as in search_round, so the look-ups are the same ones.
 #define LEAN_WORDS 8
 #define MASK_THREADS 256
-__device__ __forceinline__ uint32_t lean_kmer16(const uint32_t *col, int p) {  // 16 bases from base p, first base most significant
+template <int S>
+__device__ __forceinline__ uint32_t lean_word16(const uint32_t *col, int p) {  // 16 bases from base p, base p in bits 0..1
   const int wi = p >> 4, sh = 2 * (p & 15);
-  const uint32_t v = __funnelshift_r(col[wi * MASK_THREADS], col[(wi + 1) * MASK_THREADS], sh);
+  return __funnelshift_r(col[wi * S], col[(wi + 1) * S], sh);
+}
+template <int S>
+__device__ __forceinline__ uint32_t lean_kmer16(const uint32_t *col, int p) {  // the same, first base most significant
+  const uint32_t v = lean_word16<S>(col, p);
   const uint32_t r = __brev(v);
   return ((r >> 1) & 0x55555555u) | ((r & 0x55555555u) << 1);
+}
+
+// query window of a round for a key without exception words whose payload is the column `col` (round_window)
+template <int S>
+__device__ __forceinline__ bool lean_window(const uint32_t *col, int len, const mirge_round_policy &pol, int &tlen, int &qs, int &qe) {
+  qs = 0;
+  qe = len;
+  if (pol.strip_polyT) {
+    if (tlen < 0) {
+      int tpos = len;
+      while (tpos > 0 && ((col[((tpos - 1) >> 4) * S] >> (2 * ((tpos - 1) & 15))) & 3u) == 3u) --tpos;
+      tlen = tpos;
+    }
+    if (len - tlen < 3) return false;
+    qe = tlen;
+  }
+  qs += pol.trim5;
+  qe -= pol.trim3;
+  return qe > qs;
 }
 
 __device__ __forceinline__ uint32_t round_mask_lean(const RoundSet &rs, const uint32_t *col, int len, uint32_t state) {
@@ -463,19 +487,8 @@ __device__ __forceinline__ uint32_t round_mask_lean(const RoundSet &rs, const ui
     else if (pol.select == MIRGE_SELECT_LEN_GT25) active = len > 25;
     else active = state == 0xFF;
     if (!active) continue;
-    int qs = 0, qe = len;
-    if (pol.strip_polyT) {
-      if (tlen < 0) {
-        int tpos = len;
-        while (tpos > 0 && ((col[((tpos - 1) >> 4) * MASK_THREADS] >> (2 * ((tpos - 1) & 15))) & 3u) == 3u) --tpos;
-        tlen = tpos;
-      }
-      if (len - tlen < 3) continue;
-      qe = tlen;
-    }
-    qs += pol.trim5;
-    qe -= pol.trim3;
-    if (qe <= qs) continue;
+    int qs, qe;
+    if (!lean_window<MASK_THREADS>(col, len, pol, tlen, qs, qe)) continue;
     const int L = qe - qs;
     if (lib.max_ref_len && (uint32_t)L > lib.max_ref_len) continue;
     const int R = pol.seed_len == 0 ? L : min(pol.seed_len, L);
@@ -488,7 +501,7 @@ __device__ __forceinline__ uint32_t round_mask_lean(const RoundSet &rs, const ui
       for (int pi = 0; pi < np; ++pi) {
         const int b = piece_bound(pi + 1, R, np);
         const int s = min(16, b - a);
-        const uint32_t k16 = lean_kmer16(col, qs + a);
+        const uint32_t k16 = lean_kmer16<MASK_THREADS>(col, qs + a);
         if (s == 16 && lib.filter16_bits && lib.filter_bases < 16) {
           pass |= filter16_pass(lib, k16);
         } else if (lib.filter_bases && (uint32_t)s >= lib.filter_bases) {
@@ -528,20 +541,113 @@ annot_mask_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n
   masks[id] = (uint16_t)mask;
 }
 
+// One round for one sequence from its shared-memory column: the same pieces, index ranges, candidates and checks as
+// search_round + verify, without the query copies in local memory and without the warp-level candidate sharing --
+// for the common sequence (no exception words, <= LEAN_WORDS payload words, a handful of candidates).  Returns
+// false when the sequence needs the general path (degenerate seed, many candidates); `best` is then untouched.
+#define LEAN_MAX_CAND 12
+template <int S>
+__device__ __forceinline__ bool search_lean(const mirge_library &lib, const mirge_round_policy &pol, const uint32_t *col, int qs,
+                                            int L, uint64_t &best) {
+  if (lib.max_ref_len && (uint32_t)L > lib.max_ref_len) return true;  // longer than every reference: no alignment
+  const int R = pol.seed_len == 0 ? L : min(pol.seed_len, L);
+  const int np = pol.seed_mm + 1;
+  if (R < MIN_SEED * np) return false;
+  uint32_t p_lo[MAX_PIECES], p_hi[MAX_PIECES];
+  uint32_t total = 0;
+  int a = 0;
+#pragma unroll
+  for (int pi = 0; pi < MAX_PIECES; ++pi) {
+    p_lo[pi] = p_hi[pi] = 0;
+    if (pi < np) {
+      const int b = piece_bound(pi + 1, R, np);
+      const int s = min(16, b - a);
+      const uint32_t k16 = lean_kmer16<S>(col, qs + a);
+      const uint32_t span = (s == 16) ? 0u : ((1u << (2 * (16 - s))) - 1u);
+      const uint32_t k_lo = k16 & ~span, k_hi = k_lo | span;
+      bool look = true;
+      if (s == 16 && lib.filter16_bits && lib.filter_bases < 16) {
+        look = filter16_pass(lib, k_lo);
+      } else if (lib.filter_bases && (uint32_t)s >= lib.filter_bases) {
+        const uint32_t fi = lib.filter_bases >= 16 ? k_lo : (k_lo >> (32 - 2 * lib.filter_bases));
+        look = (lib.d_filter[fi >> 5] >> (fi & 31)) & 1u;
+      }
+      if (look) {
+        const uint32_t bsh = 32 - lib.bucket_bits;
+        uint32_t l = lib.d_idx_bucket[k_lo >> bsh], h = lib.d_idx_bucket[(k_hi >> bsh) + 1];
+        const uint32_t hi0 = h;
+        while (l < h) { const uint32_t mid = (l + h) >> 1; if (lib.d_idx_kmer[mid] < k_lo) l = mid + 1; else h = mid; }
+        p_lo[pi] = l;
+        h = hi0;
+        while (l < h) { const uint32_t mid = (l + h) >> 1; if (lib.d_idx_kmer[mid] <= k_hi) l = mid + 1; else h = mid; }
+        p_hi[pi] = l;
+        total += p_hi[pi] - p_lo[pi];
+      }
+      a = b;
+    }
+  }
+  if (total > LEAN_MAX_CAND) return false;
+  const int nw = (L + 15) >> 4;
+  a = 0;
+#pragma unroll
+  for (int pi = 0; pi < MAX_PIECES; ++pi) {
+    if (pi < np) {
+      for (uint32_t e = p_lo[pi]; e < p_hi[pi]; ++e) {
+        const uint32_t pos = lib.d_idx_pos[e];
+        if (pos < (uint32_t)a) continue;
+        const uint64_t astart = pos - (uint32_t)a;
+        // text under the round policy (verify_text on the column)
+        int mm = 0, smm = 0;
+        for (int w = 0; w < nw && mm >= 0; ++w) {
+          uint32_t x = lean_word16<S>(col, qs + 16 * w) ^ lib_word16(lib.d_packed, astart + 16 * (uint64_t)w);
+          x = (x | (x >> 1)) & 0x55555555u;
+          const int rem = L - 16 * w;
+          if (rem < 16) x &= (1u << (2 * rem)) - 1u;
+          if (x) {
+            mm += __popc(x);
+            const int srem = R - 16 * w;
+            if (srem >= 16) smm += __popc(x);
+            else if (srem > 0) smm += __popc(x & ((1u << (2 * srem)) - 1u));
+            if (mm > pol.total_mm || smm > pol.seed_mm) mm = -1;
+          }
+        }
+        if (mm < 0) continue;
+        const uint32_t r = find_ref(lib, pos);
+        const uint32_t rlo = lib.d_ref_off[r], rhi = lib.d_ref_off[r + 1];
+        if (astart < rlo || astart + (uint64_t)L > rhi) continue;
+        if (ref_has_n(lib, astart, astart + L)) continue;
+        const uint64_t hword = ((uint64_t)mm << 56) | ((uint64_t)r << 28) | (uint64_t)(astart - rlo);
+        if (hword < best) best = hword;
+      }
+      a = piece_bound(pi + 1, R, np);
+    }
+  }
+  return true;
+}
+
 // pass 2: a WARP owns SUB_KEYS consecutive sequences and runs the rounds on them in order, alone: per round it
 // compacts the sequences to search (mask bit set, not annotated by an earlier round) into its shared-memory list and
 // searches them 32 at a time.  No CTA barrier: warps do not wait for each other's searches.
-#define SUB_KEYS 512
+#define SUB_KEYS 256
 struct WarpTile {
   uint16_t mask[SUB_KEYS];
   uint16_t list[SUB_KEYS];
   uint8_t state[SUB_KEYS];
-  WarpScratch ws;
+  uint32_t pay[LEAN_WORDS + 2][32];  // payload column of the sequence a lane is searching
 };
 
-__global__ void __launch_bounds__(ANN_THREADS, 8)
+// Sequences the lean search does not take (exception words, > 128 bases, a degenerate seed, many candidates) leave
+// pass 2 at the round that meets them: (id, round index) goes to a list and pass 3 (annot_general_kernel) runs that
+// round and every later one for them with the general code, thread per sequence, candidates shared across the warp.
+struct GeneralList {
+  unsigned long long *count;
+  uint32_t *id;
+  uint8_t *round;
+};
+
+__global__ void __launch_bounds__(ANN_THREADS, 10)
 annot_search_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n_keys, const uint16_t *__restrict__ masks,
-                    uint8_t *__restrict__ annot_round, uint64_t *__restrict__ hit) {
+                    uint8_t *__restrict__ annot_round, uint64_t *__restrict__ hit, const GeneralList gl) {
   __shared__ WarpTile s_wt[ANN_THREADS / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WarpTile &W = s_wt[warp];
@@ -572,24 +678,37 @@ annot_search_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t
     __syncwarp();
     for (uint32_t base = 0; base < cnt; base += 32) {
       const uint32_t idx = base + lane;
-      bool active = idx < cnt;
+      const bool active = idx < cnt;
       const uint32_t k = active ? W.list[idx] : 0u;
       const uint64_t id = tile0 + k;
-      uint32_t qw[QW_MAX], qnx[QW_MAX];
-      KeyView kv;
-      kv.pay = kv.exc = nullptr; kv.len = kv.nexc = 0;
-      int L = 0, tlen = -1;
+      uint64_t best = MIRGE_NO_HIT;
+      bool general = false;
       if (active) {
-        kv = key_view(t.d_arena + t.d_key_ref[id]);
-        int qs, qe;
-        active = round_window(kv, pol, tlen, qs, qe);
-        if (active) {
-          L = qe - qs;
-          build_query(kv, qs, qe, qw, qnx);
+        const KeyView kv = key_view(t.d_arena + t.d_key_ref[id]);
+        const int npay = (kv.len + 15) >> 4;
+        general = true;
+        if (kv.nexc == 0 && npay <= LEAN_WORDS) {
+          uint32_t *col = &W.pay[0][lane];
+#pragma unroll
+          for (int w = 0; w < LEAN_WORDS + 2; ++w) col[w * 32] = w < npay ? kv.pay[w] : 0u;
+          int qs, qe, tlen = -1;
+          if (!lean_window<32>(col, kv.len, pol, tlen, qs, qe)) general = false;  // (cannot happen: the mask bit says the round searches it)
+          else general = !search_lean<32>(rs.lib[ri], pol, col, qs, qe - qs, best);
         }
       }
-      bool republish = true;
-      const uint64_t best = search_round(rs.lib[ri], pol, active, qw, qnx, L, kv.nexc > 0, W.ws, republish, lane);
+      const unsigned gm = __ballot_sync(0xffffffffu, general);
+      if (gm) {  // hand these sequences to pass 3 from this round on; no later round of this pass looks at them
+        const int leader = __ffs(gm) - 1;
+        unsigned long long gb = 0;
+        if (lane == leader) gb = atomicAdd(gl.count, (unsigned long long)__popc(gm));
+        gb = __shfl_sync(0xffffffffu, gb, leader);
+        if (general) {
+          const unsigned long long e = gb + __popc(gm & ((1u << lane) - 1u));
+          gl.id[e] = (uint32_t)id;
+          gl.round[e] = (uint8_t)ri;
+          W.mask[k] = 0;
+        }
+      }
       if (active && best != MIRGE_NO_HIT) {
         W.state[k] = (uint8_t)pol.round;
         annot_round[id] = (uint8_t)pol.round;
@@ -598,6 +717,72 @@ annot_search_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t
     }
     __syncwarp();
   }
+}
+
+// pass 3: the listed sequences, rounds from the listed one on (entries beyond *count: CTAs exit at once)
+__global__ void __launch_bounds__(ANN_THREADS, 10)
+annot_general_kernel(const __grid_constant__ RoundSet rs, mirge_table t, const GeneralList gl, uint8_t *__restrict__ annot_round,
+                     uint64_t *__restrict__ hit) {
+  __shared__ WarpScratch s_ws[ANN_THREADS / 32];
+  const unsigned long long n = *gl.count;
+  if ((uint64_t)blockIdx.x * ANN_THREADS >= n) return;  // uniform per CTA
+  const uint64_t i = (uint64_t)blockIdx.x * ANN_THREADS + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool in_range = i < n;
+  const uint64_t id = in_range ? gl.id[i] : 0;
+  const int first = in_range ? gl.round[i] : rs.n;
+  uint32_t qw[QW_MAX], qnx[QW_MAX];
+  KeyView kv;
+  kv.pay = kv.exc = nullptr; kv.len = kv.nexc = 0;
+  int cur_qs = -1, cur_qe = -1, tlen = -1;
+  uint32_t state = 0xFF;
+  if (in_range) {
+    kv = key_view(t.d_arena + t.d_key_ref[id]);
+    state = annot_round[id];
+  }
+  const int len = kv.len, nexc = kv.nexc;
+  uint64_t my_hit = MIRGE_NO_HIT;
+  int my_round = -1;
+  bool republish = true;
+  const int lo = __reduce_min_sync(0xffffffffu, first);
+  for (int ri = lo; ri < rs.n; ++ri) {
+    const mirge_round_policy &pol = rs.pol[ri];
+    bool active = in_range && ri >= first;
+    if (active) {
+      if (pol.select == MIRGE_SELECT_LEN_LT26) active = len < 26;
+      else if (pol.select == MIRGE_SELECT_LEN_GT25) active = len > 25;
+      else active = state == 0xFF;
+    }
+    int L = 0;
+    if (active) {
+      int qs, qe;
+      active = round_window(kv, pol, tlen, qs, qe);
+      if (active) {
+        L = qe - qs;
+        if (qs != cur_qs || qe != cur_qe) {
+          build_query(kv, qs, qe, qw, qnx);
+          cur_qs = qs;
+          cur_qe = qe;
+          republish = true;
+        }
+      }
+    }
+    const uint64_t best = search_round(rs.lib[ri], pol, active, qw, qnx, L, nexc > 0, s_ws[warp], republish, lane);
+    if (active && best != MIRGE_NO_HIT) {
+      state = (uint32_t)pol.round;
+      my_round = pol.round;
+      my_hit = best;
+    }
+  }
+  if (my_round >= 0) {
+    annot_round[id] = (uint8_t)my_round;
+    hit[id] = my_hit;
+  }
+}
+
+extern "C" uint64_t mirge_annotate_scratch_bytes(uint64_t n_keys) {
+  const uint64_t n = (n_keys + 7) & ~7ull;
+  return 16 + 2 * n + 4 * n + n;  // counter, round masks, list of (id, round) for the general pass
 }
 
 static int check_round(mirge_ctx *ctx, const mirge_library *lib, const mirge_round_policy *policy) {
@@ -638,13 +823,21 @@ extern "C" int mirge_annotate_rounds(mirge_ctx *ctx, const mirge_library *libs, 
   cudaStream_t stream = (cudaStream_t)stream_;
   MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
   if (d_scratch) {
-    if ((uintptr_t)d_scratch & 1) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: misaligned scratch");
-    uint16_t *masks = (uint16_t *)d_scratch;
+    if ((uintptr_t)d_scratch & 7) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "annotate: misaligned scratch");
+    const uint64_t n8 = (n_keys + 7) & ~7ull;
+    GeneralList gl;
+    gl.count = (unsigned long long *)d_scratch;
+    uint16_t *masks = (uint16_t *)((uint8_t *)d_scratch + 16);
+    gl.id = (uint32_t *)((uint8_t *)d_scratch + 16 + 2 * n8);
+    gl.round = (uint8_t *)d_scratch + 16 + 6 * n8;
+    MIRGE_CUDA(ctx, cudaMemsetAsync(gl.count, 0, 16, stream));
     annot_mask_kernel<<<(unsigned)((n_keys + MASK_THREADS - 1) / MASK_THREADS), MASK_THREADS, 0, stream>>>(rs, *t, n_keys, d_annot_round, masks);
     MIRGE_LAUNCH_CHECK(ctx, "annot_mask_kernel");
     const uint64_t per_cta = (uint64_t)SUB_KEYS * (ANN_THREADS / 32);
-    annot_search_kernel<<<(unsigned)((n_keys + per_cta - 1) / per_cta), ANN_THREADS, 0, stream>>>(rs, *t, n_keys, masks, d_annot_round, d_hit);
+    annot_search_kernel<<<(unsigned)((n_keys + per_cta - 1) / per_cta), ANN_THREADS, 0, stream>>>(rs, *t, n_keys, masks, d_annot_round, d_hit, gl);
     MIRGE_LAUNCH_CHECK(ctx, "annot_search_kernel");
+    annot_general_kernel<<<(unsigned)((n_keys + ANN_THREADS - 1) / ANN_THREADS), ANN_THREADS, 0, stream>>>(rs, *t, gl, d_annot_round, d_hit);
+    MIRGE_LAUNCH_CHECK(ctx, "annot_general_kernel");
     return MIRGE_OK;
   }
   annotate_kernel<<<(unsigned)((n_keys + ANN_THREADS - 1) / ANN_THREADS), ANN_THREADS, 0, stream>>>(rs, *t, n_keys, d_annot_round, d_hit);

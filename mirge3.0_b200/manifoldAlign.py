@@ -96,11 +96,11 @@ def annotate_keys(dev: Device, libs: LibrarySet, keys: KeySet, spike_in: bool = 
         # all rounds in one launch: every key is read once and leaves at the first round that hits it
         lib_arr = (abi.Library * n_rounds)(*[libs[ROUND_LIBS[r]].struct for r in range(n_rounds)])
         pol_arr = (abi.RoundPolicy * n_rounds)(*pols[:n_rounds])
-        scratch = dev.empty(n, torch.int16) if split else None
+        scratch = dev.empty(dev.lib.mirge_annotate_scratch_bytes(n) // 8 + 1, torch.int64) if split else None
         with dev.timed("annotate"):
             dev.check(dev.lib.mirge_annotate_rounds(dev.ctx, lib_arr, pol_arr, n_rounds, C.byref(keys.struct), n,
                                                     _ptr(annot), _ptr(hit), _ptr(scratch), dev.stream()))
-        dev.launches += 2 if split else 1
+        dev.launches += 3 if split else 1
         return annot[:n], hit[:n]
     for rnd in range(n_rounds):
         lib = libs[ROUND_LIBS[rnd]]
