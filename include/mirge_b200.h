@@ -219,6 +219,27 @@ int mirge_trim(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, const ui
                uint64_t keys_capacity_words, uint64_t *d_trim_ctrl, void *d_scratch, uint64_t *d_ins,
                uint64_t ins_capacity, void *stream);
 
+/* ---- stages 1a + 1b in one pass: fused tokeniser + trim (the product path) -------------------------------------
+ * The same result as mirge_tokenise_sync + mirge_line_index + mirge_trim without a separate pass over the bytes: a
+ * persistent kernel takes the stream tile by tile through the bulk-copy engine (cp.async.bulk + mbarrier), finds the
+ * line breaks of each tile in shared memory, numbers the records by a single-pass look-back over the tiles in front
+ * and runs stage 1 of the split pipeline on the bytes where they lie; stages 2 / 3 and the whole-pipeline pass follow
+ * as in mirge_trim.  Applies when mirge_digest_fused_ok() (3' adapters of <= 32 nt with indels, no qiagen UMIs,
+ * automatic kernel choice); otherwise use the three calls above.
+ * The number of records is not known beforehand: n_cap is the caller's bound (outputs and lists are sized by it:
+ * d_line_start u32[4 n_cap + 4] or NULL, d_win / d_key_off for n_cap x slots or NULL, d_ins >= n_cap x slots
+ * entries, d_scratch = mirge_digest_scratch_bytes(nbytes, n_cap)).  d_trim_ctrl (16 x u64, zeroed by the caller) as
+ * for mirge_trim, plus [9] line breaks of the batch (with is_final, a last line without '\n' counts as complete),
+ * [10] offset just behind the last complete record, relative to d_fastq rounded down to 16 bytes,
+ * [2] bit 16: more than n_cap records -- repeat with n_cap >= [9] / 4; [2] bit 8: too many records for the
+ * whole-pipeline list -- use the three-call path for this batch. */
+int mirge_digest_fused_ok(const mirge_ctx *ctx);
+uint64_t mirge_digest_scratch_bytes(uint64_t nbytes, uint64_t n_cap);
+int mirge_digest_tiles(mirge_ctx *ctx, const uint8_t *d_fastq, uint64_t nbytes, int is_final, uint64_t n_cap,
+                       uint32_t *d_line_start, uint16_t *d_win, uint32_t *d_key_off, uint32_t *d_keys,
+                       uint64_t keys_capacity_words, uint64_t *d_trim_ctrl, void *d_scratch, uint64_t *d_ins,
+                       uint64_t ins_capacity, void *stream);
+
 /* Kernel selection for mirge_trim: 0 = automatic (split bit-parallel pipeline when every adapter is a 3'
  * adapter with indels and <= 32 nt, else the generic full-DP kernel), 1 = always generic, 2 = bit-parallel
  * kernel without the split (one kernel + second pass; kept for the parity tests).  When the generic-free

@@ -125,6 +125,9 @@ SYMBOLS = {
     "mirge_trim_scratch_bytes": (_U64, [_U64]),
     "mirge_trim": (C.c_int, [_P, _P, _U64, _P, _U64, _P, _P, _P, _U64, _P, _P, _P, _U64, _P]),
     "mirge_trim_mode": (C.c_int, [_P, C.c_int]),
+    "mirge_digest_fused_ok": (C.c_int, [_P]),
+    "mirge_digest_scratch_bytes": (_U64, [_U64, _U64]),
+    "mirge_digest_tiles": (C.c_int, [_P, _P, _U64, C.c_int, _U64, _P, _P, _P, _P, _U64, _P, _P, _P, _U64, _P]),
     "mirge_table_reset": (C.c_int, [_P, C.POINTER(Table), _P]),
     "mirge_collapse_insert_list": (C.c_int, [_P, C.POINTER(Table), _P, _P, _U64, _P, _P]),
     "mirge_collapse_merge": (C.c_int, [_P, C.POINTER(Table), _P, _P, _U64, _P, _P]),

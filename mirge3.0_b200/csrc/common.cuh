@@ -98,3 +98,51 @@ __device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gmem_src)
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// newline_mask: bit i set <=> byte i of the 32 bytes is '\n'.
+// Exact zero-byte test of w ^ "\n\n\n\n" (bit 7 of every byte that is '\n'; no carry crosses a byte), then two words
+// at a time: the flags of the first word move to bits 8b+3, those of the second stay at 8b+7, and one multiply by
+// 2^0 + 2^7 + 2^14 + 2^21 lines all eight up in the top byte (the 32 partial products land on distinct bits, so
+// the sum has no carries).
+__device__ __forceinline__ uint32_t newline_flags(uint32_t w) {
+  const uint32_t x = w ^ 0x0A0A0A0Au;
+  const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+  return ~(t | x) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t newline_mask(const uint32_t w[8]) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    const uint32_t q = newline_flags(w[k + 1]) | (newline_flags(w[k]) >> 4);
+    m |= ((q * 0x00204081u) >> 24) << (4 * k);
+  }
+  return m;
+}
+
+// ---------------------------------------------------------------- mbarrier / bulk copy (TMA) ----
+// Shared-memory barriers with transaction counts and the 1-D bulk copy engine (cp.async.bulk): one elected thread
+// arms the barrier with the byte count and issues the copy; waiters poll the phase parity.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+// global -> shared bulk copy of `bytes` (multiple of 16; both addresses 16-byte aligned), completion counted on `bar`
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}

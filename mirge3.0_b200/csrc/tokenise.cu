@@ -70,26 +70,6 @@ __device__ __forceinline__ void load32(const uint8_t *fq, uint64_t n, uint64_t p
   }
 }
 
-// newline_mask: bit i set <=> byte i of the 32 bytes is '\n'.
-// Exact zero-byte test of w ^ "\n\n\n\n" (bit 7 of every byte that is '\n'; no carry crosses a byte), then two words
-// at a time: the flags of the first word move to bits 8b+3, those of the second stay at 8b+7, and one multiply by
-// 2^0 + 2^7 + 2^14 + 2^21 lines all eight up in the top byte (the 32 partial products land on distinct bits, so
-// the sum has no carries).
-__device__ __forceinline__ uint32_t newline_flags(uint32_t w) {
-  const uint32_t x = w ^ 0x0A0A0A0Au;
-  const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-  return ~(t | x) & 0x80808080u;
-}
-__device__ __forceinline__ uint32_t newline_mask(const uint32_t w[8]) {
-  uint32_t m = 0;
-#pragma unroll
-  for (int k = 0; k < 8; k += 2) {
-    const uint32_t q = newline_flags(w[k + 1]) | (newline_flags(w[k]) >> 4);
-    m |= ((q * 0x00204081u) >> 24) << (4 * k);
-  }
-  return m;
-}
-
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *smem, uint32_t *total) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t inc = v;

@@ -27,7 +27,7 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(abi.TrimParams) == 4 * (1 + 8 * 4 + 8) + 4 * ctypes.sizeof(abi.Adapter)
     assert ctypes.sizeof(abi.Table) == 56
     assert ctypes.sizeof(abi.RoundPolicy) == 32
-    assert ctypes.sizeof(abi.Library) == 88
+    assert ctypes.sizeof(abi.Library) == 104  # + filter16_bits, max_ref_len, d_filter16 (ABI v2)
 
 
 def test_no_device_fails_loudly():
