@@ -252,7 +252,9 @@ class DigestEngine:
         self.E = dev.slots
         self.trim_mode = 0  # 0 = automatic kernel choice, 1 = always the generic full-DP kernel
         self.INPLACE_MIN_NEW = float(os.environ.get("MIRGE_B200_INPLACE_MIN_NEW", "0.25"))
-        self.fused = os.environ.get("MIRGE_B200_FUSED", "1") != "0"  # single-pass tokenise + stage 1 where it applies
+        # single-pass tokenise + stage 1 (bulk-copy fed persistent kernel) where it applies; off by default: measured
+        # slower than tokenise -> line index -> stage 1 on the B200 (profiles/README.md), kept selectable
+        self.fused = os.environ.get("MIRGE_B200_FUSED", "0") == "1"
         self._avg_record = None  # bytes per record of the last batch (record bound of the fused kernel)
         dev.check(dev.lib.mirge_trim_mode(dev.ctx, 0))
         self.stats = {"records": 0, "bytes": 0, "emitted": 0, "key_words": 0, "deferred": 0, "dp_reads": 0, "dp_redo": 0}  # running totals (bench.py rooflines)

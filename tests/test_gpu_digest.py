@@ -254,3 +254,75 @@ def test_arena_growth_tracks_unique_keys(dev):
     assert table.n_keys == len(exp)
     assert used[-1] == used[1], used  # no growth once the repeats are recognised
     assert used[1] <= 2 * used[0]
+
+
+@pytest.mark.parametrize("case", ["synthetic2", "synthetic1", "batches", "crlf_noeol", "far_records", "tiny", "truncated"])
+def test_fused_single_pass_kernel_matches_oracle(dev, case):
+    """mirge_digest_tiles (bulk-copy fed persistent tokenise + stage 1 kernel, opt-in) against the oracle: record
+    numbering by the look-back scan, tile / overhang edges, EOF rule, records beyond the overhang, batching."""
+    from mirge_b200 import device as D
+    from mirge_b200 import synth
+
+    def engine(cfg):
+        eng = D.DigestEngine(dev, cfg)
+        eng.fused = True
+        assert dev.lib.mirge_digest_fused_ok(dev.ctx) == 1
+        return eng
+
+    if case.startswith("synthetic"):
+        cfg_id = int(case[-1])
+        libs = synth.make_libraries(scale=0.1, mrna_count=200)
+        buf = synth.ReadGenerator(libs, synth.CONFIGS[cfg_id], dev.tdev).fastq(200_000)
+        eng = engine(synth.trim_config_for(cfg_id))
+        fq = buf.cpu().numpy()
+        n, win_o, kept_o = coracle.trim(fq, dev.trim_params, nthreads=8)
+        br = eng.trim_batch(buf, buf.numel(), True)
+        assert br.n_records == n == 200_000
+        win_g, kept_g = gpu_windows(eng, br)
+        assert np.array_equal(kept_g, kept_o) and np.array_equal(win_g, win_o)
+        # the line index it writes on request is the tokeniser's
+        eng.fused = False
+        br2 = eng.trim_batch(buf, buf.numel(), True)
+        assert torch.equal(br.line_start[: 4 * n + 1], br2.line_start[: 4 * n + 1])
+        table = D.CollapseTable(dev, min_keys=1 << 12)
+        eng.collapse_batch(table, br)
+        _, tab = coracle.digest_collapse(fq, dev.trim_params, nthreads=8)
+        assert table_dict(table) == tab.to_dict()
+        return
+    cfg = CONFIGS["default"]
+    eng = engine(cfg)
+    if case == "batches":
+        data = random_fastq(20000, seed=12, n_rate=0.0005)
+        variants = [(data, pad, batch) for pad, batch in ((0, 1 << 30), (0, 16384), (3, 16384 * 3 + 1), (13, 50001), (7, 18432))]
+    elif case == "crlf_noeol":
+        base = random_fastq(9000, seed=13, n_rate=0.0005)
+        variants = [(random_fastq(9000, seed=13, n_rate=0.0005, crlf=True), 5, 1 << 30), (base[:-1], 0, 1 << 30), (base[:-1], 9, 40000)]
+        data = base
+    elif case == "far_records":
+        rng = np.random.default_rng(8)
+        recs = []
+        for i in range(400):
+            L = int(rng.integers(20, 60))
+            s = "".join(rng.choice(list("ACGT"), L))
+            hdr = "r%d" % i + ("x" * int(rng.integers(1500, 4000)) if i % 7 == 0 else "")  # some records exceed the 2 KB overhang
+            seq = (s[:15] + ILL + s)[:L] if i % 2 else s
+            recs.append("@%s\n%s\n+\n%s\n" % (hdr, seq, "I" * L))
+        data = "".join(recs).encode()
+        variants = [(data, 0, 1 << 30), (data, 11, 30000)]
+    elif case == "tiny":
+        data = b"@a\nTGAGGTAGTAGGTTGTATAGTT\n+\nIIIIIIIIIIIIIIIIIIIIII\n"
+        variants = [(data, 0, 1 << 30), (data[:-1], 1, 1 << 30), (data * 3, 2, 1 << 30)]
+    else:  # truncated final record: a format error, as with the tokeniser
+        data = random_fastq(3000, seed=14, n_rate=0.0005)
+        cut = data[: len(data) - 30]
+        table = D.CollapseTable(dev, min_keys=1 << 10)
+        with pytest.raises(D.FastqFormatError):
+            eng.digest_device(to_dev(dev, cut), table)
+        return
+    for blob, pad, batch in variants:
+        ref = data if case != "tiny" else blob + (b"\n" if not blob.endswith(b"\n") else b"")
+        _, tab = coracle.digest_collapse(np.frombuffer(ref, dtype=np.uint8), dev.trim_params)
+        table = D.CollapseTable(dev, min_keys=1 << 10)
+        n = eng.digest_device(to_dev(dev, blob, pad), table, batch_bytes=batch)
+        assert n == ref.count(b"\n") // 4, (case, pad, batch)
+        assert table_dict(table) == tab.to_dict(), (case, pad, batch)
