@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--batch-mb", type=int, default=2048)
     ap.add_argument("--e2e-batch-mb", type=int, default=256, help="piece size of the host-fed (e2e) pipeline")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--overlap-exchange", action="store_true", help="N > 1: per-batch exchange on a worker thread / side stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -218,7 +219,14 @@ def run_b200(args):
     setup_s = time.perf_counter() - t_setup
 
     table = D.CollapseTable(dev, min_keys=1 << 22)
-    owner = D.CollapseTable(dev, min_keys=1 << 22) if world > 1 else None
+    # N > 1: one exchange per pass after the local collapse.  (--overlap-exchange: the exchange of every batch on a worker
+    # thread / side stream while the next batch is trimmed into a second local table, distributed.ExchangeWorker --
+    # measured slower at N = 2 (61.6 vs 52 ms per pass): five drains / resets of GB-sized tables and two streams of
+    # latency-bound kernels that take each other's SM slots cost more than the 12 ms they hide.)
+    overlap = world > 1 and args.overlap_exchange
+    table_b = D.CollapseTable(dev, min_keys=1 << 22) if overlap else None
+    worker = MD.ExchangeWorker(local, world, owner_min_keys=1 << 22) if overlap else None
+    owner = worker.owner if worker else (D.CollapseTable(dev, min_keys=1 << 22) if world > 1 else None)
     state = {}
 
     def finish(tab_local):
@@ -242,6 +250,17 @@ def run_b200(args):
     def step_resident():
         # (annotating every batch's new keys on a side stream while the next batch is trimmed was measured: no
         # gain for the resident pass -- the kernels do not share SMs usefully -- so the pass stays sequential)
+        if overlap:
+            # per-batch exchange behind the next batch's trim; the same number of batches on every rank (equal shards)
+            worker.reset_owner()
+            n = eng.digest_device_exchange(fq, (table, table_b), worker, batch_bytes, n_batches=state["n_batches"])
+            worker.finish()
+            with dev.timed("drain"):
+                ids, cnt = owner.drain()
+            keys = MA.KeySet.from_table(owner)
+            annot, hit = MA.annotate_keys(dev, lset, keys, False)
+            state.update(ids=ids, cnt=cnt, annot=annot, hit=hit, tab=owner)
+            return n
         table.reset()
         n = eng.digest_device(fq, table, batch_bytes)
         finish(table)
@@ -252,6 +271,11 @@ def run_b200(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if world > 1:  # every rank submits the same number of per-batch exchanges
+        nb = torch.tensor([D.DigestEngine.max_batches(nbytes, batch_bytes)], device=dev.tdev)
+        dist.all_reduce(nb, op=dist.ReduceOp.MAX)
+        state["n_batches"] = int(nb.item())
 
     # ---- device-resident throughput ("value")
     for _ in range(args.warmup):

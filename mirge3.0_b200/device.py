@@ -495,3 +495,45 @@ class DigestEngine:
                 raise FastqFormatError("no complete FASTQ record in batch")
             pos += br.consumed if not final else (end - pos)
         return n_records
+
+    @staticmethod
+    def max_batches(total_bytes: int, batch_bytes: int, max_record: int = 1 << 16) -> int:
+        """Upper bound of the batches digest_device* cuts ``total_bytes`` into (a batch ends at a record boundary)."""
+        step = max(batch_bytes - max_record, 1)
+        return (int(total_bytes) + step - 1) // step
+
+    def digest_device_exchange(self, buf: torch.Tensor, locals2, worker, batch_bytes: int = 256 << 20, n_batches: int = 0) -> int:
+        """Multi-GPU form of digest_device (one process per GPU): every batch is collapsed into one of two local tables
+        and its (key, count) pairs are handed to ``worker`` (distributed.ExchangeWorker), which partitions them by
+        owner, runs the all-to-all and merges into the owner table on its own stream while the next batch is trimmed
+        here into the other local table.  Collective: every rank must submit the same number of exchanges -- pass
+        ``n_batches`` = the maximum over the ranks of ``max_batches(...)`` and a rank that runs out of input keeps
+        submitting empty exchanges."""
+        total = int(buf.numel())
+        pos, k, n_records = 0, 0, 0
+        handles = [None, None]
+        for t in locals2:
+            t.reset()
+        while pos < total:
+            tab = locals2[k % 2]
+            if handles[k % 2] is not None:
+                handles[k % 2].wait()  # the exchange that read this table is done
+                tab.reset()
+            end = min(total, pos + batch_bytes)
+            final = end == total
+            br = self.trim_batch(buf[pos:end], end - pos, final, keep=False, table=tab)
+            self.collapse_batch(tab, br)
+            with self.dev.timed("drain"):
+                ids, cnt = tab.drain()
+            handles[k % 2] = worker.submit(tab, ids, cnt)
+            n_records += br.n_records
+            if br.consumed == 0 and not final:
+                raise FastqFormatError("no complete FASTQ record in batch")
+            pos += br.consumed if not final else (end - pos)
+            k += 1
+        empty = torch.zeros(0, dtype=torch.int32, device=self.dev.tdev)
+        while k < n_batches:  # keep the collectives of all ranks in step
+            worker.submit(locals2[0], empty, empty)
+            k += 1
+        return n_records
+

@@ -66,11 +66,11 @@ def exchange_records(rec: torch.Tensor, sizes: torch.Tensor, send_recs: torch.Te
     return r_rec, r_sizes
 
 
-def exchange_and_merge(dev, local_table, ids: torch.Tensor, cnt: torch.Tensor, owner_table, world: int, umi=(0, 0), group=None):
-    """Partition the drained (key id, count) pairs of ``local_table`` by owner, exchange, merge into
-    ``owner_table`` (GPU path; every kernel through the C ABI): plan (owner and record size of every pair) ->
-    totals per owner -> scatter into per-owner regions of the send buffer (cursors, no sort) -> all-to-all ->
-    merge."""
+def plan_and_pack(dev, local_table, ids: torch.Tensor, cnt: torch.Tensor, world: int, umi=(0, 0)):
+    """Sender side of the exchange (every kernel through the C ABI): owner and record size of every drained
+    (key id, count) pair -> totals per owner -> scatter into per-owner regions of one send buffer (cursors, no sort).
+    Returns (rec int32 words grouped by owner, sizes int32 [n] in the same order, send_recs int64 [world],
+    send_words int64 [world])."""
     from .device import _ptr
 
     lib = dev.lib
@@ -98,8 +98,12 @@ def exchange_and_merge(dev, local_table, ids: torch.Tensor, cnt: torch.Tensor, o
             dev.check(lib.mirge_partition_scatter(dev.ctx, C.byref(local_table.struct), _ptr(ids), _ptr(cnt), _ptr(dest), _ptr(words), n,
                                                   world, _ptr(cursors), _ptr(rec), _ptr(sizes), dev.stream()))
             dev.launches += 1
-    # the records are received straight into the end of the owner's arena: the first record of a sequence becomes
-    # the table's copy of its key where it lies (no copy, no publishing fence)
+    return rec[:total], sizes[:n], send_recs, send_words
+
+
+def arena_receiver(owner_table):
+    """(callable for exchange_records' recv_buffer, state): the records are received straight into the end of the
+    owner's arena, where the first record of a sequence becomes the table's copy of its key (no copy, no fence)."""
     owner_table.check()
     state = {}
 
@@ -109,22 +113,156 @@ def exchange_and_merge(dev, local_table, ids: torch.Tensor, cnt: torch.Tensor, o
         state["a0"] = a0
         return owner_table.arena[a0 : a0 + n_words]
 
-    with dev.timed("xchg_a2a"):
-        r_rec, r_sizes = exchange_records(rec[:total], sizes[:n], send_recs, group, send_words=send_words, recv_buffer=into_arena)
+    return into_arena, state
+
+
+def merge_received(dev, owner_table, r_rec: torch.Tensor, r_sizes: torch.Tensor, a0: int) -> int:
+    """Owner side: the received records lie at arena word a0; merge them in place (mirge_collapse_merge_inplace)."""
+    from .device import _ptr
+
     m = int(r_sizes.numel())
     if m == 0:
         return 0
     with dev.timed("xchg_merge"):
-        a0 = state["a0"]
         r_off = (torch.cumsum(r_sizes.to(torch.int64), 0) - r_sizes.to(torch.int64) + a0)
         r_off = torch.where(r_off >= (1 << 31), r_off - (1 << 32), r_off).to(torch.int32)
         owner_table.arena_used = a0 + int(r_rec.numel())
         owner_table.ctrl[0] = owner_table.arena_used
         deferred = dev.empty(m, torch.int32)
-        dev.check(lib.mirge_collapse_merge_inplace(dev.ctx, C.byref(owner_table.struct), _ptr(r_off), m, _ptr(deferred), dev.stream()))
+        dev.check(dev.lib.mirge_collapse_merge_inplace(dev.ctx, C.byref(owner_table.struct), _ptr(r_off), m, _ptr(deferred), dev.stream()))
         dev.launches += 3
         owner_table.check()
     return m
+
+
+def exchange_and_merge(dev, local_table, ids: torch.Tensor, cnt: torch.Tensor, owner_table, world: int, umi=(0, 0), group=None):
+    """Partition the drained (key id, count) pairs of ``local_table`` by owner, exchange, merge into
+    ``owner_table``: plan_and_pack -> all-to-all (received into the owner's arena) -> merge_received."""
+    rec, sizes, send_recs, send_words = plan_and_pack(dev, local_table, ids, cnt, world, umi)
+    into_arena, state = arena_receiver(owner_table)
+    with dev.timed("xchg_a2a"):
+        r_rec, r_sizes = exchange_records(rec, sizes, send_recs, group, send_words=send_words, recv_buffer=into_arena)
+    return merge_received(dev, owner_table, r_rec, r_sizes, state.get("a0", 0))
+
+
+def loopback_exchange(devs, local_tables, pairs, owner_tables, umi=(0, 0)):
+    """The same exchange for ``world`` = len(local_tables) ranks that live in ONE process (tests on a single GPU, and
+    single-process multi-table runs): every rank's send buffer is cut by owner and the pieces are copied into the
+    owners' arenas in source-rank order -- what the all-to-all does -- then merged in place.  ``pairs[r]`` = (ids, cnt)
+    drained from local_tables[r]; devs[r] = Device used for rank r's kernels."""
+    world = len(local_tables)
+    sent = [plan_and_pack(devs[r], local_tables[r], pairs[r][0], pairs[r][1], world, umi) for r in range(world)]
+    merged = []
+    for o in range(world):
+        dev = devs[o]
+        rec_parts, size_parts = [], []
+        for r in range(world):
+            rec, sizes, send_recs, send_words = sent[r]
+            w0, r0 = int(send_words[:o].sum()), int(send_recs[:o].sum())
+            rec_parts.append(rec[w0 : w0 + int(send_words[o])])
+            size_parts.append(sizes[r0 : r0 + int(send_recs[o])])
+        r_sizes = torch.cat(size_parts)
+        n_words = sum(int(p.numel()) for p in rec_parts)
+        into_arena, state = arena_receiver(owner_tables[o])
+        dst = into_arena(int(r_sizes.numel()), n_words)
+        at = 0
+        for part in rec_parts:
+            dst[at : at + part.numel()].copy_(part)
+            at += int(part.numel())
+        merged.append(merge_received(dev, owner_tables[o], dst, r_sizes, state["a0"]))
+    return merged
+
+
+class ExchangeWorker:
+    """The exchange off the critical path.  ``exchange_and_merge`` is a chain of small kernels, three collectives and
+    host round trips for their split sizes (about 12 ms per 50 M-read pass, during which the trim kernels of the next
+    batch could run).  A worker thread drives it on its own CUDA stream -- and with its own library context, whose
+    pinned staging words the *_sync calls of the main thread must not share -- in submission order, which is the same
+    on every rank, so the collectives line up.  The caller digests batch k + 1 into a second local table meanwhile and
+    waits for the hand-over of batch k before it reuses that table.
+
+        w = ExchangeWorker(device_index, owner_min_keys, world)
+        h = w.submit(local_table, ids, cnt)        # after local_table.drain() on the main stream
+        ...                                        # next batch, other local table
+        h.wait()                                   # before local_table.reset()
+        owner = w.finish()                         # all merges done; the owner table belongs to the caller again
+    """
+
+    class Handle:
+        def __init__(self):
+            import threading
+
+            self._ev = threading.Event()
+            self.result = None
+            self.error = None
+
+        def wait(self):
+            self._ev.wait()
+            if self.error is not None:
+                raise self.error
+            return self.result
+
+    def __init__(self, index: int, world: int, owner_min_keys: int = 1 << 22, umi=(0, 0), group=None):
+        import queue
+        import threading
+
+        from .device import CollapseTable, Device
+
+        self.dev = Device(index)  # own context: own pinned staging for the synchronising calls
+        self.owner = CollapseTable(self.dev, min_keys=owner_min_keys)
+        self.world, self.umi, self.group = world, umi, group
+        self.stream = torch.cuda.Stream(device=self.dev.tdev)
+        self.q = queue.Queue()
+        self.thread = threading.Thread(target=self._run, name="mirge-exchange", daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        torch.cuda.set_device(self.dev.tdev)
+        with torch.cuda.stream(self.stream):
+            while True:
+                item = self.q.get()
+                if item is None:
+                    return
+                kind, h, args = item
+                try:
+                    if kind == "xchg":
+                        table, ids, cnt, ev, drain = args
+                        self.stream.wait_event(ev)
+                        ids.record_stream(self.stream)
+                        cnt.record_stream(self.stream)
+                        exchange_and_merge(self.dev, table, ids, cnt, self.owner, self.world, self.umi, self.group)
+                        h.result = self.owner.drain() if drain else None
+                    elif kind == "reset":
+                        self.owner.reset()
+                    self.stream.synchronize()
+                except BaseException as exc:  # surfaces in wait()
+                    h.error = exc
+                h._ev.set()
+
+    def submit(self, local_table, ids: torch.Tensor, cnt: torch.Tensor, drain_owner: bool = False) -> "ExchangeWorker.Handle":
+        """Queue the exchange of the pairs drained from ``local_table`` (collective: every rank submits the same
+        sequence of calls).  With ``drain_owner`` the handle's result is ``owner.drain()`` after the merge."""
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev.tdev))
+        h = ExchangeWorker.Handle()
+        self.q.put(("xchg", h, (local_table, ids, cnt, ev, drain_owner)))
+        return h
+
+    def reset_owner(self) -> "ExchangeWorker.Handle":
+        h = ExchangeWorker.Handle()
+        self.q.put(("reset", h, None))
+        return h
+
+    def finish(self):
+        """Block until everything queued has run; the current stream then sees the owner table's final state."""
+        h = ExchangeWorker.Handle()
+        self.q.put(("noop", h, None))
+        h.wait()
+        return self.owner
+
+    def close(self):
+        self.q.put(None)
+        self.thread.join()
 
 
 # ---------------------------------------------------------------------------------------------------

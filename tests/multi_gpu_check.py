@@ -94,12 +94,15 @@ def main():
     b0 = 0 if lo == 0 else int(nl[4 * lo - 1]) + 1
     b1 = int(nl[4 * hi - 1]) + 1
     shard = torch.from_numpy(fq[b0:b1].copy()).to(dev.tdev)
+    # per-batch exchange on the worker thread / side stream behind the next batch's trim (two local tables)
     local_t = D.CollapseTable(dev, min_keys=1 << 12)
-    owner_t = D.CollapseTable(dev, min_keys=1 << 12)
-    n = eng.digest_device(shard, local_t, batch_bytes=3 << 20)
+    local_b = D.CollapseTable(dev, min_keys=1 << 12)
+    nb = torch.tensor([D.DigestEngine.max_batches(shard.numel(), 3 << 20)], device=dev.tdev)
+    dist.all_reduce(nb, op=dist.ReduceOp.MAX)
+    worker = MD.ExchangeWorker(local, world, owner_min_keys=1 << 12, umi=umi)
+    n = eng.digest_device_exchange(shard, (local_t, local_b), worker, batch_bytes=3 << 20, n_batches=int(nb.item()))
     assert n == hi - lo
-    ids, cnt = local_t.drain()
-    MD.exchange_and_merge(dev, local_t, ids, cnt, owner_t, world, umi=umi)
+    owner_t = worker.finish()
     ids, cnt = owner_t.drain()
     keys = owner_t.export_keys()
     annot, hit = MA.annotate_keys(dev, lset, MA.KeySet.from_table(owner_t), True)

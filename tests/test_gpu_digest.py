@@ -326,3 +326,52 @@ def test_fused_single_pass_kernel_matches_oracle(dev, case):
         n = eng.digest_device(to_dev(dev, blob, pad), table, batch_bytes=batch)
         assert n == ref.count(b"\n") // 4, (case, pad, batch)
         assert table_dict(table) == tab.to_dict(), (case, pad, batch)
+
+
+@pytest.mark.parametrize("cfg_id", [1, 3])
+def test_exchange_world2_on_one_device_matches_oracle(dev, cfg_id):
+    """The multi-GPU exchange with world = 2 on ONE device (two local tables, two owner tables, loop-back transport):
+    partition plan / totals / scatter, records received into the owners' arenas, mirge_collapse_merge_inplace --
+    everything of the N > 1 path except NCCL -- against the single-process oracle.  (tests/test_gpu_multi.py runs the
+    same with NCCL on two GPUs.)"""
+    from mirge_b200 import device as D
+    from mirge_b200 import distributed as MD
+    from mirge_b200 import synth
+
+    n_reads = 60_000
+    libs = synth.make_libraries(scale=0.05, mrna_count=100)
+    cfg = synth.trim_config_for(cfg_id)
+    eng = D.DigestEngine(dev, cfg)
+    umi = cfg.umi() or (0, 0)
+    fq = synth.ReadGenerator(libs, synth.CONFIGS[cfg_id], "cpu").fastq(n_reads).numpy()
+    nl = np.flatnonzero(fq == 10)
+    locals_, pairs = [], []
+    for lo, hi in MD.shard_ranges(n_reads, 2):
+        b0 = 0 if lo == 0 else int(nl[4 * lo - 1]) + 1
+        b1 = int(nl[4 * hi - 1]) + 1
+        t = D.CollapseTable(dev, min_keys=1 << 12)
+        assert eng.digest_device(torch.from_numpy(fq[b0:b1].copy()).to(dev.tdev), t, batch_bytes=3 << 20) == hi - lo
+        locals_.append(t)
+        pairs.append(t.drain())
+    owners = [D.CollapseTable(dev, min_keys=1 << 12) for _ in range(2)]
+    # two rounds of the same exchange: the second one meets every key again (merge into existing slots)
+    for _ in range(2):
+        MD.loopback_exchange([dev, dev], locals_, pairs, owners, umi=umi)
+    union = {}
+    for o in owners:
+        d = table_dict(o)
+        assert not (set(d) & set(union)), "a sequence is owned by two ranks"
+        union.update(d)
+    _, tab = coracle.digest_collapse(fq, dev.trim_params, nthreads=8)
+    exp = tab.to_dict()
+    if cfg.umi() is None:
+        assert union == {k: 2 * v for k, v in exp.items()}
+    else:
+        # UMI mode partitions by the centre (flanks removed): both levels stay owner-local; first-level keys as such
+        assert union == {k: 2 * v for k, v in exp.items()}
+        centres = {}
+        for i, o in enumerate(owners):
+            keys = o.export_keys()
+            for k in keys.tolist():
+                c = k.decode()[umi[0] : len(k) - umi[1]] if umi[1] else k.decode()[umi[0] :]
+                assert centres.setdefault(c, i) == i, "a centre sequence is split across owners"
