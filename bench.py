@@ -28,8 +28,23 @@ import torch  # noqa: E402
 
 METRIC = "M reads/s trim+collapse+annotate"
 UNIT = "M reads/s"
+# BASELINE.json configs: reads per sample, samples per GPU, mRNA entries, spike-in round, label.
+# C2 is the configuration the metric is quoted on and the default; C4 / C5 are per-GPU shares of the multi-GPU
+# configurations (48 samples = 6 per GPU x 8, 1 B reads = 125 M per GPU x 8).
+CONFIG_TABLE = {
+    1: dict(reads=1_000_000, samples=1, mrna=5_000, spike=False,
+            label="C1: 1M-read synthetic Illumina small-RNA sample, L=50, -a illumina (default -q 10), 9 rounds (mRNA 5k entries)"),
+    2: dict(reads=50_000_000, samples=1, mrna=100_000, spike=False,
+            label="C2: 50M-read single sample, L=75, -a illumina -nxt 20 -q 20, full ordered library annotation (mRNA 100k entries)"),
+    3: dict(reads=100_000_000, samples=1, mrna=100_000, spike=False,
+            label="C3: 100M-read QIAseq-style UMI library, L=75, -a AACTGTAGGCACCATCAAT --qiagenumi -umi 0,12 -udd, UMI-aware collapse"),
+    4: dict(reads=20_000_000, samples=6, mrna=100_000, spike=False,
+            label="C4 share: 6 samples x 20M reads per GPU (48 samples at 8 GPUs), L=50, -a illumina, per-sample counts"),
+    5: dict(reads=125_000_000, samples=1, mrna=100_000, spike=True,
+            label="C5 share: 125M reads per GPU (1B pooled at 8 GPUs), L=75, -a illumina -spk, 10 rounds incl. mRNA and spike-ins"),
+}
 CFG_ID = 2
-WORKLOAD = "C2: 50M-read single sample, L=75, -a illumina -nxt 20 -q 20, full ordered library annotation (mRNA 100k entries)"
+WORKLOAD = CONFIG_TABLE[2]["label"]
 
 
 def parse_args():
@@ -38,8 +53,12 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--reads", type=int, default=50_000_000, help="reads per GPU (default: the C2 sample size)")
-    ap.add_argument("--mrna", type=int, default=100_000, help="mRNA library entries")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIG_TABLE), help="BASELINE.json config (default 2: the metric's)")
+    ap.add_argument("--reads", type=int, default=0, help="reads per sample and GPU (default: the config's)")
+    ap.add_argument("--samples", type=int, default=0, help="samples per GPU (default: the config's)")
+    ap.add_argument("--mrna", type=int, default=0, help="mRNA library entries (default: the config's)")
+    ap.add_argument("--dropin", action="store_true",
+                    help="also time baking(args, [file on /dev/shm]) + bwtAlign(args, df) -- the reference's entry points -- on one sample")
     ap.add_argument("--count-mode", default="head", choices=["head", "release"])
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="reads of the bounded CPU sample (0 = 12 M for the cpu_baseline leg, 4 M per step for --impl reference)")
@@ -48,7 +67,15 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--overlap-exchange", action="store_true", help="N > 1: per-batch exchange on a worker thread / side stream")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    c = CONFIG_TABLE[a.config]
+    a.reads = a.reads or c["reads"]
+    a.samples = a.samples or c["samples"]
+    a.mrna = a.mrna or c["mrna"]
+    a.spike = c["spike"]
+    a.workload = c["label"] if (a.reads, a.samples, a.mrna) == (c["reads"], c["samples"], c["mrna"]) else \
+        c["label"] + " [reduced: %d reads x %d samples, mRNA %d]" % (a.reads, a.samples, a.mrna)
+    return a
 
 
 # ------------------------------------------------------------------------------------------------
@@ -68,6 +95,7 @@ class CpuPath:
 
         self.co = coracle
         self.threads = threads
+        self.cfg = cfg
         self.cp = P.build_trim_params(cfg)
         self.pols = round_policies()
         self.round_libs = ROUND_LIBS
@@ -79,6 +107,9 @@ class CpuPath:
     def step(self, fq: np.ndarray, spike=False):
         co = self.co
         n, tab = co.digest_collapse(fq, self.cp, nthreads=self.threads)
+        umi = self.cfg.umi()
+        if umi is not None:  # second level (digest.py:164-205), -udd
+            tab = tab.umi_collapse(umi[0], umi[1], self.cfg.minimum_length, True)
         keys, off, cnt = tab.export()
         ar = np.full(len(cnt), 0xFF, dtype=np.uint8)
         hit = np.full(len(cnt), 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
@@ -103,26 +134,26 @@ def run_reference(args):
 
     threads = host_threads()
     libs = synth.make_libraries(mrna_count=args.mrna)
-    cfg = synth.trim_config_for(CFG_ID, args.count_mode)
+    cfg = synth.trim_config_for(args.config, args.count_mode)
     cpu = CpuPath(libs, cfg, threads)
-    gen = synth.ReadGenerator(libs, synth.CONFIGS[CFG_ID], "cpu")
-    sample = args.cpu_sample or 4_000_000
+    gen = synth.ReadGenerator(libs, synth.CONFIGS[args.config], "cpu")
+    sample = min(args.cpu_sample or 4_000_000, args.reads * args.samples)
     fq = gen.fastq(sample).numpy()
     for _ in range(args.warmup):
-        cpu.step(fq)
+        cpu.step(fq, args.spike)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        n, nu, na = cpu.step(fq)
+        n, nu, na = cpu.step(fq, args.spike)
     dt = (time.perf_counter() - t0) / max(args.steps, 1)
     v = sample / dt / 1e6
     line = {
         "impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "count_mode": args.count_mode, "reads_per_step": sample,
+        "config": {"workload": args.workload, "count_mode": args.count_mode, "reads_per_step": sample,
                    "note": "bounded sample of the workload per step; CPU only"},
         "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": "%d reads of the C2 workload per step (oracle port: cutadapt/bowtie not installable)" % sample},
+                         "sample": "%d reads of the workload per step (oracle port: cutadapt/bowtie not installable)" % sample},
         "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -180,6 +211,67 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Run this process on the CPUs next to its GPU (NVML's affinity mask) where the container's CPU set allows it, so
+    that pinned host buffers are first touched on the GPU's own NUMA node and the copy threads stay there."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        near = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        pick = near & allowed
+        if pick and pick != allowed:
+            os.sched_setaffinity(0, pick)
+        return sorted(pick)
+    except Exception:
+        return None
+
+
+def run_dropin(args, dev, lset, libs, fq_dev, cfg_id):
+    """The drop-in boundary itself: baking(args, [file], [name], workDir) then bwtAlign(args, df, workDir, ref_db) -- the two
+    calls miRge3.0's main() makes -- on one sample of the workload written to /dev/shm (FASTQ file in, pandas DataFrame
+    out, run.log written).  Wall clock; reported beside e2e, which feeds the same kernels from a pinned buffer."""
+    import shutil
+    import tempfile
+
+    from mirge_b200 import digest as DG
+    from mirge_b200 import manifoldAlign as MA
+    from tests.util import make_args
+
+    tmp = tempfile.mkdtemp(prefix="mirge_dropin_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        path = os.path.join(tmp, "sample.fastq")
+        with open(path, "wb") as fh:
+            step = 1 << 30
+            for lo in range(0, int(fq_dev.numel()), step):
+                fh.write(fq_dev[lo : lo + step].cpu().numpy().tobytes())
+        kw = dict(quiet=True, spikeIn=bool(args.spike), threads=host_threads())
+        if cfg_id == 2:
+            kw.update(nextseq_trim=20, quality_cutoff="20")
+        if cfg_id == 3:
+            from mirge_b200 import synth
+
+            kw.update(adapters=[("back", synth.QIA_INNER)], uniq_mol_ids="0,12", qiagenumi=True, umiDedup=True)
+        a = make_args(**kw)
+        out = {}
+        for rep in range(2):  # the second pass is the timed one (first: allocator warm-up, page cache)
+            t0 = time.perf_counter()
+            df, src, trc, tru = DG.baking(a, [path], ["sample"], tmp, device=dev, count_mode=args.count_mode)
+            t1 = time.perf_counter()
+            df = MA.bwtAlign(a, df, tmp, "miRBase", libraries=lset, device=dev)
+            t2 = time.perf_counter()
+            out = {"value": round(args.reads / (t2 - t0) / 1e6, 3), "unit": UNIT, "baking_s": round(t1 - t0, 2),
+                   "bwtAlign_s": round(t2 - t1, 2), "rows": int(len(df)), "annotated_rows": int((df["annotFlag"] == 1).sum()),
+                   "reads": int(src["sample"]), "input": "FASTQ file on /dev/shm", "output": "pandas DataFrame (reference contract)"}
+            del df
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_b200(args):
     import torch.distributed as dist
 
@@ -201,50 +293,64 @@ def run_b200(args):
     batch_bytes = args.batch_mb << 20
 
     t_setup = time.perf_counter()
+    cfg_id = args.config
     libs = synth.make_libraries(mrna_count=args.mrna)
     lset = LB.LibrarySet.from_fasta_dict(dev, libs.fasta_dict())
-    cfg = synth.trim_config_for(CFG_ID, args.count_mode)
+    cfg = synth.trim_config_for(cfg_id, args.count_mode)
     eng = D.DigestEngine(dev, cfg)
-    rc = synth.CONFIGS[CFG_ID]
-    if world > 1:
-        import dataclasses
+    umi = cfg.umi()
+    import dataclasses
 
-        rc = dataclasses.replace(rc, sample_seed=0)
-    gen = synth.ReadGenerator(libs, rc, dev.tdev)
-    gen.gen.manual_seed(2000 + CFG_ID + 7919 * rank)
-    fq = gen.fastq(args.reads, first_index=rank * args.reads)
-    del gen
+    # this GPU's samples (C4: per-sample abundance perturbation, synth.ReadConfig.sample_seed); resident in HBM
+    fqs = []
+    for s_i in range(args.samples):
+        gs = rank * args.samples + s_i  # global sample index
+        rc = dataclasses.replace(synth.CONFIGS[cfg_id], sample_seed=gs if args.samples > 1 else 0)
+        gen = synth.ReadGenerator(libs, rc, dev.tdev)
+        gen.gen.manual_seed(2000 + cfg_id + 7919 * gs)
+        fqs.append(gen.fastq(args.reads, first_index=gs * args.reads))
+        del gen
+    rc = synth.CONFIGS[cfg_id]
     torch.cuda.synchronize()
-    nbytes = int(fq.numel())
+    nbytes = int(sum(f.numel() for f in fqs))
+    reads_per_gpu = args.reads * args.samples
     setup_s = time.perf_counter() - t_setup
 
     table = D.CollapseTable(dev, min_keys=1 << 22)
-    # N > 1: one exchange per pass after the local collapse.  (--overlap-exchange: the exchange of every batch on a worker
-    # thread / side stream while the next batch is trimmed into a second local table, distributed.ExchangeWorker --
-    # measured slower at N = 2 (61.6 vs 52 ms per pass): five drains / resets of GB-sized tables and two streams of
-    # latency-bound kernels that take each other's SM slots cost more than the 12 ms they hide.)
-    overlap = world > 1 and args.overlap_exchange
+    first_level = D.CollapseTable(dev, min_keys=1 << 22) if umi is not None else None
+    # N > 1: one exchange per sample after its local collapse.  (--overlap-exchange, single-sample configs: the exchange of
+    # every batch on a worker thread / side stream while the next batch is trimmed into a second local table,
+    # distributed.ExchangeWorker -- measured slower at N = 2 (61.6 vs 52 ms per pass): five drains / resets of GB-sized
+    # tables and two streams of latency-bound kernels that take each other's SM slots cost more than the 12 ms they hide.)
+    overlap = world > 1 and args.overlap_exchange and args.samples == 1 and umi is None
     table_b = D.CollapseTable(dev, min_keys=1 << 22) if overlap else None
     worker = MD.ExchangeWorker(local, world, owner_min_keys=1 << 22) if overlap else None
     owner = worker.owner if worker else (D.CollapseTable(dev, min_keys=1 << 22) if world > 1 else None)
     state = {}
+    xumi = umi if umi is not None else (0, 0)
 
-    def finish(tab_local):
-        """collapse done on this rank -> (exchange) -> annotate; returns (table, n_keys)"""
+    def sample_done(columns):
+        """the sample's reads are collapsed into `table` (or the first-level table): UMI level, per-sample column,
+        exchange to the owners"""
+        if umi is not None:
+            with dev.timed("drain"):
+                ids1, cnt1 = first_level.drain()
+            with dev.timed("umi_collapse"):
+                DG.umi_collapse(dev, first_level, ids1, cnt1, table, umi, cfg.minimum_length, True)
+            first_level.reset()
         with dev.timed("drain"):
-            ids, cnt = tab_local.drain()
+            ids, cnt = table.drain()
         if world > 1:
-            with dev.timed("owner_reset"):
-                owner.reset()
-            MD.exchange_and_merge(dev, tab_local, ids, cnt, owner, world)
+            MD.exchange_and_merge(dev, table, ids, cnt, owner, world, umi=(0, 0))  # (second-level keys carry no UMI)
             with dev.timed("drain"):
                 ids, cnt = owner.drain()
-            tab = owner
-        else:
-            tab = tab_local
+        columns.append((ids, cnt))
+
+    def annotate_final(columns):
+        tab = owner if world > 1 else table
         keys = MA.KeySet.from_table(tab)
-        annot, hit = MA.annotate_keys(dev, lset, keys, False)
-        state.update(ids=ids, cnt=cnt, annot=annot, hit=hit, tab=tab)
+        annot, hit = MA.annotate_keys(dev, lset, keys, args.spike)
+        state.update(columns=columns, annot=annot, hit=hit, tab=tab)
         return tab
 
     def step_resident():
@@ -253,17 +359,21 @@ def run_b200(args):
         if overlap:
             # per-batch exchange behind the next batch's trim; the same number of batches on every rank (equal shards)
             worker.reset_owner()
-            n = eng.digest_device_exchange(fq, (table, table_b), worker, batch_bytes, n_batches=state["n_batches"])
+            n = eng.digest_device_exchange(fqs[0], (table, table_b), worker, batch_bytes, n_batches=state["n_batches"])
             worker.finish()
             with dev.timed("drain"):
                 ids, cnt = owner.drain()
-            keys = MA.KeySet.from_table(owner)
-            annot, hit = MA.annotate_keys(dev, lset, keys, False)
-            state.update(ids=ids, cnt=cnt, annot=annot, hit=hit, tab=owner)
+            annotate_final([(ids, cnt)])
             return n
         table.reset()
-        n = eng.digest_device(fq, table, batch_bytes)
-        finish(table)
+        if owner is not None:
+            with dev.timed("owner_reset"):
+                owner.reset()
+        n, columns = 0, []
+        for fq_s in fqs:
+            n += eng.digest_device(fq_s, first_level if umi is not None else table, batch_bytes)
+            sample_done(columns)
+        annotate_final(columns)
         return n
 
     def barrier():
@@ -272,7 +382,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    if world > 1:  # every rank submits the same number of per-batch exchanges
+    if overlap:  # every rank submits the same number of per-batch exchanges
         nb = torch.tensor([D.DigestEngine.max_batches(nbytes, batch_bytes)], device=dev.tdev)
         dist.all_reduce(nb, op=dist.ReduceOp.MAX)
         state["n_batches"] = int(nb.item())
@@ -305,28 +415,32 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
     ms_max = float(tms.item())
+    assert n_rec == reads_per_gpu, (n_rec, reads_per_gpu)
     n_unique = int(state["tab"].n_keys)
     n_annot = int((state["annot"] != 0xFF).sum().item())
-    emitted_words = None
 
     # ---- end to end from pinned host memory
     e2e = None
-    host = None
+    hosts = None
     if not args.no_e2e:
         # the host copy of the input (pinned).  If any rank cannot pin that much memory all ranks skip the e2e leg
         # together (it contains collectives) and the line reports e2e = null.
         try:
-            host = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
-            host.copy_(fq)
+            bind_to_gpu_numa_node(local)  # pinned pages and the copy threads on the GPU's own NUMA node where allowed
+            hosts = []
+            for f in fqs:
+                h = torch.empty(int(f.numel()), dtype=torch.uint8).pin_memory()
+                h.copy_(f)
+                hosts.append(h)
         except (RuntimeError, MemoryError) as exc:
             sys.stderr.write("bench: e2e leg skipped on rank %d: %s\n" % (rank, exc))
-            host = None
-        okf = torch.tensor([0 if host is None else 1], device=dev.tdev)
+            hosts = None
+        okf = torch.tensor([0 if hosts is None else 1], device=dev.tdev)
         if world > 1:
             dist.all_reduce(okf, op=dist.ReduceOp.MIN)
         if int(okf.item()) == 0:
-            host = None
-    if host is not None:
+            hosts = None
+    if hosts is not None:
         torch.cuda.synchronize()
         streamer = DG.HostStreamer(eng, args.e2e_batch_mb << 20)
 
@@ -342,24 +456,40 @@ def run_b200(args):
             buf[:n_el].copy_(t, non_blocking=True)
             return n_el * t.element_size()
 
-        sa = MA.StreamedAnnotator(dev, lset, False) if world == 1 else None
+        # single GPU, no UMI level: annotation and the D2H of the result table are streamed piece by piece behind the H2D
+        # of the following pieces (the keys of a piece are final as soon as it is collapsed)
+        sa = MA.StreamedAnnotator(dev, lset, args.spike) if (world == 1 and umi is None) else None
 
         def step_e2e():
             table.reset()
+            if owner is not None:
+                owner.reset()
+            n, columns, d2h = 0, [], 0
             if sa is not None:
-                # single GPU: annotation and the D2H of the result table are streamed piece by piece behind
-                # the H2D of the following pieces; only the per-sample counts remain for the end
                 sa.reset()
-                n = streamer.run(host, table, on_piece=sa)
+            for h in hosts:
+                if sa is not None:
+                    n += streamer.run(h, table, on_piece=sa)
+                    with dev.timed("drain"):
+                        ids, cnt = table.drain()
+                    columns.append((ids, cnt))
+                else:
+                    n += streamer.run(h, first_level if umi is not None else table)
+                    sample_done(columns)
+            if sa is not None:
                 sa.finish(table)
-                return n, sa.d2h_bytes
-            n = streamer.run(host, table)
-            tab = finish(table)
-            # result table -> host: packed unique sequences, per-key counts and annotation
+                d2h += sa.d2h_bytes
+                for j, (ids, cnt) in enumerate(columns):
+                    d2h += to_host("ids%d" % j, ids) + to_host("cnt%d" % j, cnt)
+                torch.cuda.current_stream().synchronize()
+                return n, d2h
+            tab = annotate_final(columns)
+            # result table -> host: packed unique sequences, per-sample (key id, count) columns and annotation
             nk = tab.n_keys
             d2h = to_host("arena", tab.arena[: tab.arena_used]) + to_host("key_ref", tab.key_ref[:nk]) + \
-                to_host("ids", state["ids"]) + to_host("cnt", state["cnt"]) + to_host("annot", state["annot"]) + \
-                to_host("hit", state["hit"])
+                to_host("annot", state["annot"]) + to_host("hit", state["hit"])
+            for j, (ids, cnt) in enumerate(columns):
+                d2h += to_host("ids%d" % j, ids) + to_host("cnt%d" % j, cnt)
             torch.cuda.current_stream().synchronize()
             return n, d2h
 
@@ -367,20 +497,23 @@ def run_b200(args):
             step_e2e()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t0 = time.perf_counter()
         f0.record()
         for _ in range(args.steps):
             _, d2h = step_e2e()
         f1.record()
         barrier()
-        wall = (time.perf_counter() - t0) / max(args.steps, 1) * 1e3
-        ems = max(f0.elapsed_time(f1) / max(args.steps, 1), wall * 0.0)
+        ems = f0.elapsed_time(f1) / max(args.steps, 1)
         tme = torch.tensor([ems], device=dev.tdev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tme, op=dist.ReduceOp.MAX)
-        e2e = {"value": round(args.reads * world / (float(tme.item()) / 1e3) / 1e6, 3), "unit": UNIT,
+        e2e = {"value": round(reads_per_gpu * world / (float(tme.item()) / 1e3) / 1e6, 3), "unit": UNIT,
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h), "ms_per_step": round(float(tme.item()), 3)}
-        del host, streamer
+        del hosts, streamer
+
+    # ---- the reference's own entry points on one sample: baking(args, [file]) + bwtAlign(args, df)  (rank 0, N = 1)
+    dropin = None
+    if args.dropin and world == 1:
+        dropin = run_dropin(args, dev, lset, libs, fqs[0], cfg_id)
 
     if rank != 0:
         if world > 1:
@@ -396,7 +529,7 @@ def run_b200(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     E = eng.E
-    rec_bytes = nbytes / args.reads
+    rec_bytes = nbytes / reads_per_gpu
     steps = max(args.steps, 1)
     kinfo = {}
     for name, (cnt_l, tot_ms) in timers.items():
@@ -408,7 +541,7 @@ def run_b200(args):
     ann_ms = sum(v[1] for k, v in timers.items() if k.startswith("annotate")) / steps
     kinfo["annotate"] = {"launches_per_step": sum(v[0] for k, v in timers.items() if k.startswith("annotate")) // steps,
                          "ms_per_step": round(ann_ms, 3)}
-    trim_gbs = args.reads * b_trim / (trim_ms / 1e3) / 1e9 if trim_ms else 0.0
+    trim_gbs = reads_per_gpu * b_trim / (trim_ms / 1e3) / 1e9 if trim_ms else 0.0
     kinfo.setdefault("trim", {})["achieved_gbs"] = round(trim_gbs, 1)
     kinfo["trim"]["frac_hbm"] = round(trim_gbs / peak, 4)
     # collapse: every emitted key is read once and probes/updates one slot: sum over keys of (2K + 16) bytes
@@ -416,20 +549,21 @@ def run_b200(args):
     col_gbs = b_col_total / (col_ms / 1e3) / 1e9 if col_ms else 0.0
     kinfo.setdefault("collapse", {})["achieved_gbs"] = round(col_gbs, 1)
     kinfo["collapse"]["frac_hbm"] = round(col_gbs / peak, 4)
-    kinfo["collapse"]["algorithmic_bytes_per_read"] = round(b_col_total / args.reads, 1)
+    kinfo["collapse"]["algorithmic_bytes_per_read"] = round(b_col_total / reads_per_gpu, 1)
     kinfo["trim"]["dp_search_frac"] = round(stats.get("dp_reads", 0) / max(stats["records"], 1), 4)
     kinfo["trim"]["cost_column_frac"] = round(stats.get("dp_redo", 0) / max(stats["records"], 1), 4)
     kinfo["trim"]["second_pass_frac"] = round(stats.get("deferred", 0) / max(stats["records"], 1), 4)
     dom = max((("trim", trim_ms), ("collapse", col_ms), ("annotate", ann_ms)), key=lambda kv: kv[1])[0]
     traffic = None
+    traffic_file = "r2_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r2_traffic.json")) else "r1_traffic.json"
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["trim_kernel"]
-        traffic = int(tr["bytes_per_read"] * args.reads / max(kinfo["trim"].get("launches_per_step", 1), 1))
+        tr = json.load(open(os.path.join(ROOT, "profiles", traffic_file)))["trim_kernel"]
+        traffic = int(tr["bytes_per_read"] * reads_per_gpu / max(kinfo["trim"].get("launches_per_step", 1), 1))
     except Exception:
         pass
     roofline = {"kernel": "trim_kernel", "bound": "hbm", "achieved": round(trim_gbs, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(trim_gbs / peak, 4), "traffic": traffic,
-                "traffic_source": "ncu dram bytes per read (profiles/r1_traffic.json) x reads per launch",
+                "traffic_source": "ncu dram bytes per read (profiles/%s) x reads per launch" % traffic_file,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_read": round(b_trim, 1), "dominant_by_time": dom,
                 "launches_per_step": kinfo["trim"].get("launches_per_step")}
@@ -440,30 +574,32 @@ def run_b200(args):
         threads = host_threads()
         sample = min(args.cpu_sample or 12_000_000, args.reads)
         sb = int(sample * rec_bytes * 1.02) + 4096
-        raw = fq[: min(sb, nbytes)].cpu().numpy()
+        raw = fqs[0][: min(sb, int(fqs[0].numel()))].cpu().numpy()
         # cut at the end of read `sample`
         nl = np.flatnonzero(raw == 10)
         raw = raw[: int(nl[4 * sample - 1]) + 1] if nl.size >= 4 * sample else raw[: int(nl[(nl.size // 4) * 4 - 1]) + 1]
         sample = min(sample, nl.size // 4)
         cpu = CpuPath(libs, cfg, threads)
-        cpu.step(raw[: int(nl[4 * max(sample // 8, 1) - 1]) + 1])  # warm-up on a record-aligned prefix
+        cpu.step(raw[: int(nl[4 * max(sample // 8, 1) - 1]) + 1], args.spike)  # warm-up on a record-aligned prefix
         t0 = time.perf_counter()
-        cpu.step(raw)
+        cpu.step(raw, args.spike)
         dt = time.perf_counter() - t0
         cpu_baseline = {"value": round(sample / dt / 1e6, 4), "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": "first %d reads of the same synthetic workload, oracle port of cutadapt+bowtie semantics, %d threads, %.1f s"
                                   % (sample, threads, dt)}
 
-    value = args.reads * world / (ms_max / 1e3) / 1e6
+    value = reads_per_gpu * world / (ms_max / 1e3) / 1e6
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_max, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "reads_per_gpu": args.reads, "read_len": rc.L, "count_mode": args.count_mode,
+        "config": {"workload": args.workload, "reads_per_gpu": reads_per_gpu, "samples_per_gpu": args.samples, "read_len": rc.L,
+                   "count_mode": args.count_mode,
                    "fastq_bytes_per_gpu": nbytes, "l2": "inputs (%.1f GB per pass) larger than L2" % (nbytes / 1e9),
                    "batch_mb": args.batch_mb, "unique_sequences": n_unique, "annotated_sequences": n_annot,
                    "emission_slots_per_read": E, "setup_s": round(setup_s, 1)},
-        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline, "kernels": kinfo,
+        "e2e": e2e, "dropin": dropin, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "kernels": kinfo,
         "clocks": clk, "bit_exact": "tests/ -m gpu (oracle parity); bench does not re-check",
     }
     print(json.dumps(line))

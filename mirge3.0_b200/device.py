@@ -204,13 +204,15 @@ class CollapseTable:
         self.check()
         return ids[:n], cnt[:n]
 
-    def export_keys(self, id0: int = 0, n: Optional[int] = None) -> np.ndarray:
-        """Keys [id0, id0+n) decoded to a numpy 'S<maxlen>' array (exact original read text)."""
+    def export_keys(self, id0: int = 0, n: Optional[int] = None, order: bool = False):
+        """Keys [id0, id0+n) decoded to a numpy 'S<maxlen>' array (exact original read text).  With ``order`` also the
+        permutation that sorts them bytewise (numpy's order for 'S' arrays), computed on the device: an LSD radix sort
+        over 8-byte chunks of the zero-padded rows -- argsort of tens of millions of strings on the host takes minutes."""
         d = self.dev
         if n is None:
             n = self.n_keys - id0
         if n <= 0:
-            return np.zeros(0, dtype="S1")
+            return (np.zeros(0, dtype="S1"), np.zeros(0, dtype=np.int64)) if order else np.zeros(0, dtype="S1")
         # first pass with a narrow stride to learn the lengths, second pass only if needed
         stride = 64
         while True:
@@ -223,7 +225,17 @@ class CollapseTable:
                 break
             stride = (mx + 15) // 16 * 16
         host = asc.cpu().numpy().reshape(n, stride)
-        return np.ascontiguousarray(host).view("S%d" % stride).reshape(n)
+        keys = np.ascontiguousarray(host).view("S%d" % stride).reshape(n)
+        if not order:
+            return keys
+        if int((asc >= 128).any().item()):  # a byte >= 0x80 would flip the sign of its chunk: let numpy do it
+            return keys, np.argsort(keys, kind="stable")
+        # big-endian 8-byte chunks (bytes reversed inside every chunk, then read as int64): integer order = byte order
+        chunks = asc.view(n, stride // 8, 8).flip(2).contiguous().view(torch.int64).view(n, stride // 8)
+        perm = torch.arange(n, device=d.tdev, dtype=torch.int64)
+        for c in range(stride // 8 - 1, -1, -1):
+            perm = perm[torch.sort(chunks[perm, c], stable=True).indices]
+        return keys, perm.cpu().numpy()
 
 
 @dataclass

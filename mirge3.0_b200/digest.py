@@ -241,23 +241,72 @@ def _write_umi_csv(path: str, first: CollapseTable, ids: np.ndarray, counts: np.
                 fh.write(s[:f_] + s[-b_:] + "," + center + "," + str(c) + "\n")  # UMIParser incl. the b == 0 quirk
 
 
+def _no_keys():
+    return None
+
+
+class DeviceKeys:
+    """What build_matrix leaves in DataFrame.attrs for bwtAlign: the table whose arena holds the packed keys and the
+    key id of every row.  Not data: pickling the DataFrame (-spl / -rr, __main__.py:101,145) drops it."""
+
+    def __init__(self, table, order):
+        self.table, self.order = table, order
+
+    def __reduce__(self):
+        return (_no_keys, ())
+
+    def __deepcopy__(self, memo):
+        return self
+
+    def __eq__(self, other):  # DataFrame.equals / comparisons of attrs never differ because of the cache
+        return True
+
+    def __hash__(self):
+        return 0
+
+
+ARROW_INDEX_MIN = int(os.environ.get("MIRGE_B200_ARROW_INDEX_MIN", str(2_000_000)))
+
+
+def sequence_index(keys: np.ndarray) -> pd.Index:
+    """The 'Sequence' index of the matrix from an 'S' array of sequences.  Up to ARROW_INDEX_MIN rows: Python strings
+    (object dtype, as the reference builds it).  Beyond: an Arrow-backed string index built from offsets + bytes without
+    creating a Python object per row -- tens of millions of str objects cost more than the whole device pipeline;
+    element access, .str methods, to_csv and joins behave the same."""
+    n = int(keys.shape[0])
+    if n < ARROW_INDEX_MIN:
+        return pd.Index([k.decode("latin-1") for k in keys.tolist()], name="Sequence", dtype=object)
+    import pyarrow as pa
+
+    width = keys.dtype.itemsize
+    mat = keys.view(np.uint8).reshape(n, width)
+    lens = (mat != 0).sum(axis=1).astype(np.int64)  # sequences hold no NUL: the padding is the only zero
+    offsets = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    data = mat[np.arange(width, dtype=np.int64)[None, :] < lens[:, None]]
+    arr = pa.LargeStringArray.from_buffers(n, pa.py_buffer(offsets), pa.py_buffer(data))
+    return pd.Index(pd.arrays.ArrowStringArray(arr), name="Sequence")
+
+
 def build_matrix(table: CollapseTable, samples: List[SampleResult], names: List[str]) -> pd.DataFrame:
     """digest.py:237-261: unique sequences x samples, rows in lexicographic order (what pandas' outer
     join produces for > 1 sample; the single-sample order of the reference is not deterministic)."""
-    keys = table.export_keys()
+    keys, order = table.export_keys(order=True)  # (the bytewise order is computed on the device)
     n = keys.shape[0]
     mat = np.zeros((n, len(samples)), dtype=np.int64)
     for j, s in enumerate(samples):
         mat[s.ids, j] = s.counts
     seen = mat.any(axis=1) if n else np.zeros(0, dtype=bool)
-    order = np.argsort(keys, kind="stable")
     order = order[seen[order]]
-    index = pd.Index([k.decode("latin-1") for k in keys[order].tolist()], name="Sequence", dtype=object)
+    index = sequence_index(keys[order])
     df = pd.DataFrame(mat[order], index=index, columns=list(names))
     df = df.assign(**dict.fromkeys(INITIAL_FLAGS, ""))
     df = df.assign(annotFlag=0)
     df = df.reindex(columns=["annotFlag"] + INITIAL_FLAGS + list(names))
     df = df.astype({"annotFlag": int})
+    # the packed keys stay on the device: bwtAlign finds them here instead of re-encoding every index string
+    # (row i of the DataFrame = key id order[i] of the table)
+    df.attrs["_mirge_b200_keys"] = DeviceKeys(table, order)
     return df
 
 

@@ -75,6 +75,14 @@ def plan_and_pack(dev, local_table, ids: torch.Tensor, cnt: torch.Tensor, world:
 
     lib = dev.lib
     n = int(ids.numel())
+    if n > (1 << 16):
+        # the drain lists the pairs in slot order, i.e. at random with respect to the arena; in key-id order (= creation
+        # order = arena order) the two passes below stream the key text instead of chasing it (2.4 + 3.7 ms -> about a
+        # third for 39 M keys)
+        with dev.timed("xchg_order"):
+            ids, order = torch.sort(ids)
+            cnt = cnt[order]
+            del order
     dest = dev.empty(n, torch.int32)
     words = dev.empty(n, torch.int32)
     totals = dev.zeros(2 * world, torch.int64)

@@ -308,6 +308,21 @@ def write_round_sam(path, seqs, rows: np.ndarray, hits: np.ndarray, lib, pol):
                      % (name, lib.names[ref], off + 1, len(q), q, "I" * len(q), xa, md, nm))
 
 
+def _rows_match(cached, seqs, probes: int = 64) -> bool:
+    """The key cache of a DataFrame is only used while its rows are still the ones baking() returned: first, last and a
+    seeded sample of rows are decoded from the device table and compared with the index."""
+    table, order = cached.table, cached.order
+    n = len(seqs)
+    if n == 0:
+        return True
+    rng = np.random.default_rng(12345)
+    rows = np.unique(np.concatenate([[0, n - 1], rng.integers(0, n, size=min(probes, n))]))
+    for i in rows.tolist():
+        if table.export_keys(int(order[i]), 1)[0].decode("latin-1") != str(seqs[i]):
+            return False
+    return True
+
+
 def bwtAlign(args, pdDataFrame, workDir, ref_db, libraries: Optional[LibrarySet] = None, device: Optional[Device] = None):
     """Same contract as the reference ``bwtAlign(args, pdDataFrame, workDir, ref_db)``
     (manifoldAlign.py:68-146): fills the annotation column of the first round that hits each
@@ -323,10 +338,21 @@ def bwtAlign(args, pdDataFrame, workDir, ref_db, libraries: Optional[LibrarySet]
     libs = libraries or load_libraries(args, ref_db, dev)
     spike = bool(getattr(args, "spikeIn", False))
     seqs = pdDataFrame.index.to_numpy()
-    keys = KeySet.from_strings(dev, list(seqs))
-    annot_d, hit_d = annotate_keys(dev, libs, keys, spike)
-    annot = annot_d.cpu().numpy()
-    hit = hit_d.cpu().numpy()
+    cached = pdDataFrame.attrs.get("_mirge_b200_keys")
+    if cached is not None and getattr(cached.table, "dev", None) is dev and len(cached.order) == len(pdDataFrame) and \
+            not (getattr(args, "bam_out", False) or getattr(args, "tRNA_frag", False)) and _rows_match(cached, seqs):
+        # the DataFrame comes straight from baking(): its packed keys are still on the device (row i = key id order[i])
+        table, order = cached.table, cached.order
+        keys = KeySet.from_table(table)
+        annot_all, hit_all = annotate_keys(dev, libs, keys, spike)
+        sel = torch.from_numpy(np.ascontiguousarray(order)).to(dev.tdev)
+        annot = annot_all[sel].cpu().numpy()
+        hit = hit_all[sel].cpu().numpy()
+    else:
+        keys = KeySet.from_strings(dev, list(seqs))
+        annot_d, hit_d = annotate_keys(dev, libs, keys, spike)
+        annot = annot_d.cpu().numpy()
+        hit = hit_d.cpu().numpy()
     _, _mm, ref, _off = decode_hits(annot, hit)
     colnames = list(pdDataFrame.columns)
     for rnd in range(10 if spike else 9):

@@ -15,8 +15,8 @@ class FakeTable:
         w = max(len(k) for k in keys)
         self._keys = np.array([k.encode() for k in keys], dtype="S%d" % w)
 
-    def export_keys(self):
-        return self._keys
+    def export_keys(self, order=False):
+        return (self._keys, np.argsort(self._keys, kind="stable")) if order else self._keys
 
 
 def sample(ids, counts):
@@ -65,8 +65,31 @@ def test_matrix_contract_and_pickle_round_trip(tmp_path):
 
 def test_empty_run_gives_an_empty_frame_with_the_columns():
     class Empty:
-        def export_keys(self):
-            return np.zeros(0, dtype="S1")
+        def export_keys(self, order=False):
+            k = np.zeros(0, dtype="S1")
+            return (k, np.zeros(0, dtype=np.int64)) if order else k
 
     df = DG.build_matrix(Empty(), [sample([], [])], ["s"])
     assert len(df) == 0 and list(df.columns) == ["annotFlag"] + DG.INITIAL_FLAGS + ["s"] and df.index.name == "Sequence"
+
+
+def test_large_tables_get_an_arrow_index_without_python_strings():
+    """Beyond ARROW_INDEX_MIN rows the 'Sequence' index is Arrow-backed (no Python object per row); it holds the same
+    strings, in the same order, and writes the same CSV."""
+    rng = np.random.default_rng(0)
+    keys = sorted({"".join(rng.choice(list("ACGTN"), int(rng.integers(1, 40)))) for _ in range(500)})
+    arr = np.array([k.encode() for k in keys], dtype="S48")
+    old = DG.ARROW_INDEX_MIN
+    try:
+        DG.ARROW_INDEX_MIN = 10
+        big = DG.sequence_index(arr)
+        DG.ARROW_INDEX_MIN = 10 ** 9
+        small = DG.sequence_index(arr)
+    finally:
+        DG.ARROW_INDEX_MIN = old
+    assert small.dtype == object and "string" in str(big.dtype)
+    assert big.tolist() == small.tolist() == keys and big.name == small.name == "Sequence"
+    a = pd.DataFrame({"x": np.arange(len(keys))}, index=big)
+    b = pd.DataFrame({"x": np.arange(len(keys))}, index=small)
+    assert a.to_csv() == b.to_csv() and a.loc[keys[7], "x"] == 7
+    assert (a.index.str.len().to_numpy() == np.array([len(k) for k in keys])).all()
