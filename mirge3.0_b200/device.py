@@ -204,15 +204,9 @@ class CollapseTable:
         self.check()
         return ids[:n], cnt[:n]
 
-    def export_keys(self, id0: int = 0, n: Optional[int] = None, order: bool = False):
-        """Keys [id0, id0+n) decoded to a numpy 'S<maxlen>' array (exact original read text).  With ``order`` also the
-        permutation that sorts them bytewise (numpy's order for 'S' arrays), computed on the device: an LSD radix sort
-        over 8-byte chunks of the zero-padded rows -- argsort of tens of millions of strings on the host takes minutes."""
+    def _export_device(self, id0: int, n: int):
+        """(asc uint8[n * stride] on the device, stride, lens int32[n]): zero-padded ASCII rows of keys [id0, id0 + n)."""
         d = self.dev
-        if n is None:
-            n = self.n_keys - id0
-        if n <= 0:
-            return (np.zeros(0, dtype="S1"), np.zeros(0, dtype=np.int64)) if order else np.zeros(0, dtype="S1")
         # first pass with a narrow stride to learn the lengths, second pass only if needed
         stride = 64
         while True:
@@ -222,20 +216,50 @@ class CollapseTable:
             d.launches += 1
             mx = int(lens.max().item())
             if mx <= stride:
-                break
+                return asc, stride, lens
             stride = (mx + 15) // 16 * 16
+
+    def export_keys(self, id0: int = 0, n: Optional[int] = None) -> np.ndarray:
+        """Keys [id0, id0+n) decoded to a numpy 'S<maxlen>' array (exact original read text)."""
+        if n is None:
+            n = self.n_keys - id0
+        if n <= 0:
+            return np.zeros(0, dtype="S1")
+        asc, stride, _ = self._export_device(id0, n)
         host = asc.cpu().numpy().reshape(n, stride)
-        keys = np.ascontiguousarray(host).view("S%d" % stride).reshape(n)
-        if not order:
-            return keys
-        if int((asc >= 128).any().item()):  # a byte >= 0x80 would flip the sign of its chunk: let numpy do it
-            return keys, np.argsort(keys, kind="stable")
-        # big-endian 8-byte chunks (bytes reversed inside every chunk, then read as int64): integer order = byte order
-        chunks = asc.view(n, stride // 8, 8).flip(2).contiguous().view(torch.int64).view(n, stride // 8)
-        perm = torch.arange(n, device=d.tdev, dtype=torch.int64)
-        for c in range(stride // 8 - 1, -1, -1):
-            perm = perm[torch.sort(chunks[perm, c], stable=True).indices]
-        return keys, perm.cpu().numpy()
+        return np.ascontiguousarray(host).view("S%d" % stride).reshape(n)
+
+    def export_sorted(self, seen: Optional[np.ndarray] = None):
+        """(order int64[m], offsets int64[m + 1], data uint8[...]) on the host: the key ids in bytewise order of their text
+        (numpy's order for 'S' arrays; only ids with seen[id] when given) and the texts back to back in that order.
+        Sorting (LSD radix over big-endian 8-byte chunks of the zero-padded rows), selection and compaction run on
+        the device: argsort and slicing of tens of millions of strings on the host take minutes."""
+        d = self.dev
+        n = self.n_keys
+        if n <= 0:
+            return np.zeros(0, dtype=np.int64), np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.uint8)
+        asc, stride, lens = self._export_device(0, n)
+        rows = asc.view(n, stride)
+        if int((asc >= 128).any().item()):
+            # a byte >= 0x80 would flip the sign of its chunk: order on the host (does not happen with FASTQ text)
+            keys = np.ascontiguousarray(rows.cpu().numpy()).view("S%d" % stride).reshape(n)
+            perm = torch.from_numpy(np.argsort(keys, kind="stable")).to(d.tdev)
+        else:
+            chunks = rows.view(n, stride // 8, 8).flip(2).contiguous().view(torch.int64).view(n, stride // 8)
+            perm = torch.arange(n, device=d.tdev, dtype=torch.int64)
+            for c in range(stride // 8 - 1, -1, -1):
+                perm = perm[torch.sort(chunks[perm, c], stable=True).indices]
+            del chunks
+        if seen is not None:
+            keep = torch.from_numpy(np.ascontiguousarray(seen.astype(bool))).to(d.tdev)
+            perm = perm[keep[perm]]
+        lens_s = lens[perm].to(torch.int64)
+        srt = rows[perm]
+        inside = torch.arange(stride, device=d.tdev).unsqueeze(0) < lens_s.unsqueeze(1)
+        data = srt[inside]
+        offsets = torch.zeros(perm.numel() + 1, dtype=torch.int64, device=d.tdev)
+        torch.cumsum(lens_s, 0, out=offsets[1:])
+        return perm.cpu().numpy(), offsets.cpu().numpy(), data.cpu().numpy()
 
 
 @dataclass

@@ -269,36 +269,45 @@ ARROW_INDEX_MIN = int(os.environ.get("MIRGE_B200_ARROW_INDEX_MIN", str(2_000_000
 
 
 def sequence_index(keys: np.ndarray) -> pd.Index:
-    """The 'Sequence' index of the matrix from an 'S' array of sequences.  Up to ARROW_INDEX_MIN rows: Python strings
-    (object dtype, as the reference builds it).  Beyond: an Arrow-backed string index built from offsets + bytes without
-    creating a Python object per row -- tens of millions of str objects cost more than the whole device pipeline;
-    element access, .str methods, to_csv and joins behave the same."""
+    """The 'Sequence' index from an 'S' array of sequences (see sequence_index_packed)."""
     n = int(keys.shape[0])
-    if n < ARROW_INDEX_MIN:
-        return pd.Index([k.decode("latin-1") for k in keys.tolist()], name="Sequence", dtype=object)
-    import pyarrow as pa
-
     width = keys.dtype.itemsize
     mat = keys.view(np.uint8).reshape(n, width)
     lens = (mat != 0).sum(axis=1).astype(np.int64)  # sequences hold no NUL: the padding is the only zero
     offsets = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(lens, out=offsets[1:])
     data = mat[np.arange(width, dtype=np.int64)[None, :] < lens[:, None]]
-    arr = pa.LargeStringArray.from_buffers(n, pa.py_buffer(offsets), pa.py_buffer(data))
+    return sequence_index_packed(offsets, data)
+
+
+def sequence_index_packed(offsets: np.ndarray, data: np.ndarray) -> pd.Index:
+    """The 'Sequence' index of the matrix from texts stored back to back.  Up to ARROW_INDEX_MIN rows: Python strings
+    (object dtype, as the reference builds it).  Beyond: an Arrow-backed string index wrapped around the two buffers
+    without creating a Python object per row -- tens of millions of str objects cost more than the whole device
+    pipeline; element access, .str methods, to_csv and joins behave the same."""
+    n = int(offsets.shape[0]) - 1
+    if n < ARROW_INDEX_MIN or (data.size and int(data.max()) >= 128):
+        blob = data.tobytes()
+        off = offsets.tolist()
+        return pd.Index([blob[off[i] : off[i + 1]].decode("latin-1") for i in range(n)], name="Sequence", dtype=object)
+    import pyarrow as pa
+
+    arr = pa.LargeStringArray.from_buffers(n, pa.py_buffer(np.ascontiguousarray(offsets, dtype=np.int64)),
+                                           pa.py_buffer(np.ascontiguousarray(data)))
     return pd.Index(pd.arrays.ArrowStringArray(arr), name="Sequence")
 
 
 def build_matrix(table: CollapseTable, samples: List[SampleResult], names: List[str]) -> pd.DataFrame:
     """digest.py:237-261: unique sequences x samples, rows in lexicographic order (what pandas' outer
     join produces for > 1 sample; the single-sample order of the reference is not deterministic)."""
-    keys, order = table.export_keys(order=True)  # (the bytewise order is computed on the device)
-    n = keys.shape[0]
+    n = int(table.n_keys)
     mat = np.zeros((n, len(samples)), dtype=np.int64)
     for j, s in enumerate(samples):
         mat[s.ids, j] = s.counts
     seen = mat.any(axis=1) if n else np.zeros(0, dtype=bool)
-    order = order[seen[order]]
-    index = sequence_index(keys[order])
+    # order, selection and the packed texts come from the device (CollapseTable.export_sorted)
+    order, offsets, data = table.export_sorted(seen)
+    index = sequence_index_packed(offsets, data)
     df = pd.DataFrame(mat[order], index=index, columns=list(names))
     df = df.assign(**dict.fromkeys(INITIAL_FLAGS, ""))
     df = df.assign(annotFlag=0)

@@ -308,6 +308,29 @@ def write_round_sam(path, seqs, rows: np.ndarray, hits: np.ndarray, lib, pol):
                      % (name, lib.names[ref], off + 1, len(q), q, "I" * len(q), xa, md, nm))
 
 
+def _filled_column(old: "pd.Series", rows: np.ndarray, names: np.ndarray, ref: np.ndarray):
+    """The annotation column of a round: names[ref] at ``rows``, the old values elsewhere (manifoldAlign.py:17-18,55).
+    A column that is still all '' -- what baking() hands over -- is built from codes + dictionary (Arrow dictionary
+    decode for pandas' string dtype, one object take otherwise) instead of turning every cell into a Python object
+    and back: the difference is seconds per round on tens of millions of rows."""
+    n = len(old)
+    fresh = n > 100_000 and not bool((old != "").any())
+    if not fresh:
+        col = old.to_numpy(dtype=object, copy=True)
+        col[rows] = names[ref]
+        return col
+    codes = np.zeros(n, dtype=np.int32)
+    codes[rows] = 1 + ref.astype(np.int32)
+    ext = np.concatenate([np.array([""], dtype=object), names])
+    if old.dtype == object:
+        return ext[codes]
+    import pandas as pd
+    import pyarrow as pa
+
+    arr = pa.DictionaryArray.from_arrays(pa.array(codes), pa.array(ext.tolist(), type=pa.large_string())).dictionary_decode()
+    return pd.array(arr, dtype=old.dtype)
+
+
 def _rows_match(cached, seqs, probes: int = 64) -> bool:
     """The key cache of a DataFrame is only used while its rows are still the ones baking() returned: first, last and a
     seeded sample of rows are decoded from the device table and compared with the index."""
@@ -361,9 +384,7 @@ def bwtAlign(args, pdDataFrame, workDir, ref_db, libraries: Optional[LibrarySet]
             continue
         names = np.asarray(libs[ROUND_LIBS[rnd]].names, dtype=object)
         ci = 1 + rnd
-        col = pdDataFrame[colnames[ci]].to_numpy(dtype=object, copy=True)
-        col[rows] = names[ref[rows]]
-        pdDataFrame[colnames[ci]] = col
+        pdDataFrame[colnames[ci]] = _filled_column(pdDataFrame[colnames[ci]], rows, names, ref[rows])
     flag = pdDataFrame[colnames[0]].to_numpy(copy=True)
     flag[annot != 0xFF] = 1
     pdDataFrame[colnames[0]] = flag

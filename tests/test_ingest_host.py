@@ -208,3 +208,31 @@ def test_readahead_defaults():
         assert ingest.readahead_budget_bytes() == 64 << 20
     finally:
         del os.environ["MIRGE_B200_READAHEAD_MB"]
+
+
+def test_plain_reader_parallel_positional_reads(tmp_path):
+    """Uncompressed files: readinto() fills the caller's buffer with striped positional reads from the pool."""
+    from mirge_b200 import ingest
+
+    rng = np.random.default_rng(3)
+    data = rng.integers(0, 256, size=3 * ingest.PlainReader.STRIPE + 12345, dtype=np.uint8).tobytes()
+    p = tmp_path / "plain.fastq"
+    p.write_bytes(b"@" + data[1:])  # not a gzip magic number
+    data = b"@" + data[1:]
+    r = ingest.open_fastq(str(p), threads=4)
+    assert isinstance(r, ingest.PlainReader)
+    with r:
+        out = bytearray()
+        buf = bytearray(2 * ingest.PlainReader.STRIPE + 77)  # spans several stripes, not a multiple of the stripe
+        while True:
+            k = r.readinto(buf)
+            if not k:
+                break
+            out += buf[:k]
+        assert bytes(out) == data and r.bytes_out == len(data)
+    with ingest.open_fastq(str(p), threads=1) as r1:
+        assert r1.read(10) == data[:10] and r1.read() == data[10:] and r1.read(5) == b""
+    empty = tmp_path / "empty.fastq"
+    empty.write_bytes(b"")
+    with ingest.open_fastq(str(empty)) as r0:
+        assert r0.read() == b""

@@ -15,8 +15,22 @@ class FakeTable:
         w = max(len(k) for k in keys)
         self._keys = np.array([k.encode() for k in keys], dtype="S%d" % w)
 
-    def export_keys(self, order=False):
-        return (self._keys, np.argsort(self._keys, kind="stable")) if order else self._keys
+    @property
+    def n_keys(self):
+        return int(self._keys.shape[0])
+
+    def export_keys(self):
+        return self._keys
+
+    def export_sorted(self, seen=None):
+        """host stand-in of CollapseTable.export_sorted: order, offsets, packed texts"""
+        order = np.argsort(self._keys, kind="stable")
+        if seen is not None:
+            order = order[seen[order]]
+        texts = [bytes(k) for k in self._keys[order].tolist()]
+        offsets = np.zeros(len(texts) + 1, dtype=np.int64)
+        offsets[1:] = np.cumsum([len(t) for t in texts])
+        return order, offsets, np.frombuffer(b"".join(texts), dtype=np.uint8)
 
 
 def sample(ids, counts):
@@ -65,9 +79,10 @@ def test_matrix_contract_and_pickle_round_trip(tmp_path):
 
 def test_empty_run_gives_an_empty_frame_with_the_columns():
     class Empty:
-        def export_keys(self, order=False):
-            k = np.zeros(0, dtype="S1")
-            return (k, np.zeros(0, dtype=np.int64)) if order else k
+        n_keys = 0
+
+        def export_sorted(self, seen=None):
+            return np.zeros(0, dtype=np.int64), np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.uint8)
 
     df = DG.build_matrix(Empty(), [sample([], [])], ["s"])
     assert len(df) == 0 and list(df.columns) == ["annotFlag"] + DG.INITIAL_FLAGS + ["s"] and df.index.name == "Sequence"
