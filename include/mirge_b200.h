@@ -62,6 +62,14 @@ extern "C" {
 #define MIRGE_UMI_FLANKS 1 /* -umi f,b            (digest.py:359-366) */
 #define MIRGE_UMI_QIAGEN 2 /* --qiagenumi -umi 0,U (digest.py:332-352) */
 
+/* cutadapt's Aligner.locate picks, among the accepted alignments, the one with ...
+ *   2.x - 3.x ("ADOPTED FROM CUTADAPT 2.7", digest.py:3): most matches, then lowest cost;
+ *   >= 4.0: the highest score (match +1, mismatch -1, insertion / deletion -2), then lowest cost -- restated from the
+ *   published description, not yet held against an install (tests/test_tier3_real_tools.py does when one is there).
+ * MIRGE_COMPAT_CUTADAPT4 runs on the full-DP kernel (the bit-parallel search is built on the matches objective). */
+#define MIRGE_COMPAT_CUTADAPT23 0
+#define MIRGE_COMPAT_CUTADAPT4 1
+
 #define MIRGE_COUNT_HEAD 0    /* count after every modifier, as digest.py:354-373 is written */
 #define MIRGE_COUNT_RELEASE 1 /* count once after the pipeline (released 0.1.x behaviour)   */
 
@@ -95,6 +103,7 @@ typedef struct mirge_trim_params {
   int32_t umi5, umi3; /* -umi f,b */
   int32_t qia_adapter_len; /* len(args.adapters[0][1]) (digest.py:121,343) */
   int32_t count_mode; /* MIRGE_COUNT_* */
+  int32_t compat;     /* MIRGE_COMPAT_*: which cutadapt's alignment objective Aligner.locate follows */
   mirge_adapter adapters[MIRGE_MAX_ADAPTERS];
 } mirge_trim_params;
 

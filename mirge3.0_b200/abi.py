@@ -15,6 +15,7 @@ LIB_PAD_WORDS = 40  # MIRGE_LIB_PAD_WORDS
 
 MOD_NEXTSEQ, MOD_QUALITY, MOD_ADAPTER, MOD_NEND, MOD_CUT = 1, 2, 3, 4, 5
 UMI_NONE, UMI_FLANKS, UMI_QIAGEN = 0, 1, 2
+COMPAT_CUTADAPT23, COMPAT_CUTADAPT4 = 0, 1
 COUNT_HEAD, COUNT_RELEASE = 0, 1
 SELECT_LEN_LT26, SELECT_LEN_GT25, SELECT_UNANNOTATED = 0, 1, 2
 
@@ -55,6 +56,7 @@ class TrimParams(C.Structure):
         ("umi3", C.c_int32),
         ("qia_adapter_len", C.c_int32),
         ("count_mode", C.c_int32),
+        ("compat", C.c_int32),
         ("adapters", Adapter * MAX_ADAPTERS),
     ]
 

@@ -24,6 +24,7 @@ struct DevAdapter {
 struct DevParams {
   int n_mods, kind[MIRGE_MAX_MODS], a[MIRGE_MAX_MODS], b[MIRGE_MAX_MODS], c[MIRGE_MAX_MODS];
   int n_adapters, times, min_len, umi_mode, umi5, umi3, qia_len, slots;
+  int w_mis, w_indel;  // what a mismatch / an indel adds to the merit a DP cell carries: 0, 0 (matches) or -1, -2 (cutadapt >= 4 score)
   DevAdapter ad[MIRGE_MAX_ADAPTERS];
 };
 #ifdef ADAPTER_SEARCH_HOST
@@ -64,6 +65,9 @@ static int fill_dev_params(const mirge_trim_params *p, DevParams &d, int &maxm, 
   d.umi3 = p->umi3;
   d.qia_len = p->qia_adapter_len;
   d.slots = trim_slots_of(p);
+  if (p->compat != MIRGE_COMPAT_CUTADAPT23 && p->compat != MIRGE_COMPAT_CUTADAPT4) FILL_FAIL("unknown cutadapt compat %d", p->compat);
+  d.w_mis = p->compat == MIRGE_COMPAT_CUTADAPT4 ? -1 : 0;
+  d.w_indel = p->compat == MIRGE_COMPAT_CUTADAPT4 ? -2 : 0;
   if (p->umi_mode < MIRGE_UMI_NONE || p->umi_mode > MIRGE_UMI_QIAGEN) FILL_FAIL("bad umi_mode");
   if (p->umi_mode != MIRGE_UMI_NONE && (p->umi5 < 0 || p->umi3 < 0)) FILL_FAIL("negative UMI length");
   if (p->umi_mode == MIRGE_UMI_QIAGEN && p->n_adapters < 1) FILL_FAIL("qiagen UMI mode needs an adapter");
@@ -96,6 +100,7 @@ static int fill_dev_params(const mirge_trim_params *p, DevParams &d, int &maxm, 
         o->a2 |= code << (2 * i);
       }
     if (s->where != 0 || s->indel_cost != 1 || s->m > 32 || s->min_overlap < 1 || s->m + 2 * s->k + 3 > 48) fast_ok = 0;
+    if (p->compat != MIRGE_COMPAT_CUTADAPT23) fast_ok = 0;  // the bit-parallel search is built on the matches objective
     if (s->m > maxm) maxm = s->m;
   }
   return MIRGE_OK;
@@ -106,26 +111,32 @@ static int fill_dev_params(const mirge_trim_params *p, DevParams &d, int &maxm, 
 
 struct Match { int rstart, rstop, matches, errors; };
 
-// cutadapt Aligner.locate: full-column DP in registers, one column per read base.
+// cutadapt Aligner.locate: full-column DP in registers, one column per read base.  A cell's origin and merit -- its
+// matches, or with MIRGE_COMPAT_CUTADAPT4 its score (match +1, mismatch -1, indel -2; biased by SB so that the field
+// stays positive: a path has at most MIRGE_MAX_READ_LEN + MAXM steps of -2) -- travel in one word.
+#define MS 12
+#define MM 0xFFF
 template <int MAXM>
 __device__ __noinline__ bool locate(const int a, const uint8_t *read, const int n, Match &out) {
   const DevAdapter &ad = c_p.ad[a];
   const int m = ad.m, ic = ad.indel_cost, k = ad.k;
   const bool back = ad.where == 0;
+  const int w_mis = c_p.w_mis, w_indel = c_p.w_indel;
+  const int SB = w_indel ? 2048 : 0;
   const uint64_t p0 = ad.peq[0], p1 = ad.peq[1], p2 = ad.peq[2], p3 = ad.peq[3];
   int cost[MAXM + 1], om[MAXM + 1];
 #pragma unroll
   for (int i = 0; i <= MAXM; ++i) {
     cost[i] = back ? i * ic : 0;
-    om[i] = ((back ? 0 : -i) + OB) << 8;
+    om[i] = (((back ? 0 : -i) + OB) << MS) + SB + (back ? i * w_indel : 0);
   }
-  int best_cost = m + n, best_om = OB << 8, best_ref_stop = m, best_query_stop = n;
+  int best_cost = m + n, best_om = (OB << MS) + (w_indel ? 0 : SB), best_ref_stop = m, best_query_stop = n;
   bool stopped = false;
   for (int j = 1; j <= n; ++j) {
     const uint32_t rc = base_code_upper(read[j - 1]);
     const uint64_t eq = rc == 0 ? p0 : rc == 1 ? p1 : rc == 2 ? p2 : rc == 3 ? p3 : 0ull;
     int dc = cost[0], dom = om[0];
-    om[0] = (j + OB) << 8;
+    om[0] = ((j + OB) << MS) + SB;
     int cm = 0, omm = 0;
 #pragma unroll
     for (int i = 1; i <= MAXM; ++i) {
@@ -135,9 +146,9 @@ __device__ __noinline__ bool locate(const int a, const uint8_t *read, const int 
           c = dc; o = dom + 1;
         } else {
           const int cd = dc + 1, cdel = cost[i] + ic, cins = cost[i - 1] + ic;
-          if (cd <= cdel && cd <= cins) { c = cd; o = dom; }
-          else if (cins <= cdel) { c = cins; o = om[i - 1]; }
-          else { c = cdel; o = om[i]; }
+          if (cd <= cdel && cd <= cins) { c = cd; o = dom + w_mis; }
+          else if (cins <= cdel) { c = cins; o = om[i - 1] + w_indel; }
+          else { c = cdel; o = om[i] + w_indel; }
         }
         dc = cost[i]; dom = om[i];
         cost[i] = c; om[i] = o;
@@ -145,14 +156,14 @@ __device__ __noinline__ bool locate(const int a, const uint8_t *read, const int 
       }
     }
     if (cm <= k) {
-      const int origin = (omm >> 8) - OB, mt = omm & 0xFF;
+      const int origin = (omm >> MS) - OB, mt = omm & MM;
       const int length = m + min(origin, 0);
       int eff = length;
       if (ad.wildcard_ref) eff = (length < m) ? length - (ad.n_counts[m] - ad.n_counts[m - length]) : ad.effective_length;
-      const int bm = best_om & 0xFF;
+      const int bm = best_om & MM;
       if (length >= ad.min_overlap && cm <= ad.max_err[eff] && (mt > bm || (mt == bm && cm < best_cost))) {
         best_cost = cm; best_om = omm; best_ref_stop = m; best_query_stop = j;
-        if (cm == 0 && mt == m) { stopped = true; break; }
+        if (cm == 0 && mt - SB == m) { stopped = true; break; }
       }
     }
   }
@@ -161,14 +172,14 @@ __device__ __noinline__ bool locate(const int a, const uint8_t *read, const int 
 #pragma unroll
     for (int i = 0; i <= MAXM; ++i) {
       if (i >= first_i && i <= m) {
-        const int origin = (om[i] >> 8) - OB, mt = om[i] & 0xFF, c = cost[i];
+        const int origin = (om[i] >> MS) - OB, mt = om[i] & MM, c = cost[i];
         const int length = i + min(origin, 0);
         int eff = length;
         if (ad.wildcard_ref) {
           if (length < m) { const int ref_start = origin < 0 ? -origin : 0; eff = length - (ad.n_counts[i] - ad.n_counts[ref_start]); }
           else eff = ad.effective_length;
         }
-        const int bm = best_om & 0xFF;
+        const int bm = best_om & MM;
         if (length >= ad.min_overlap && eff >= 0 && c <= ad.max_err[eff] && (mt > bm || (mt == bm && c < best_cost))) {
           best_cost = c; best_om = om[i]; best_ref_stop = i; best_query_stop = n;
         }
@@ -177,10 +188,10 @@ __device__ __noinline__ bool locate(const int a, const uint8_t *read, const int 
   }
   (void)best_ref_stop;
   if (best_cost == m + n) return false;
-  const int origin = (best_om >> 8) - OB;
+  const int origin = (best_om >> MS) - OB;
   out.rstart = origin >= 0 ? origin : 0;
   out.rstop = best_query_stop;
-  out.matches = best_om & 0xFF;
+  out.matches = (best_om & MM) - SB;
   out.errors = best_cost;
   return true;
 }

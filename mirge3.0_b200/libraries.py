@@ -211,6 +211,43 @@ class DeviceLibrary:
         return cls(dev, names, seqs, key=key or os.path.basename(path))
 
 
+def _sequences_of_index(index_base: str, ebwt):
+    """(names, sequences) of a library that ships as a bowtie index only.  A real ``bowtie-inspect`` on PATH is asked
+    first (what the reference itself does, summary.py:776-788).  The built-in decoder (ebwt.py) is written from the
+    published index layout and has never met an index built by a real bowtie-build -- a wrong base order there would
+    give silently wrong annotation in every round -- so it is only used on request (MIRGE_B200_TRUST_EBWT=1), and says
+    so; tests/test_tier3_real_tools.py pins it wherever bowtie-build exists."""
+    import shutil
+    import subprocess
+    import warnings
+
+    tool = shutil.which("bowtie-inspect")
+    if tool and "mirge_b200" not in os.path.realpath(tool):  # (not the shim this package installs for summarize())
+        p = subprocess.run([tool, index_base], capture_output=True, check=False)
+        if p.returncode == 0 and p.stdout.startswith(b">"):
+            names, seqs, cur = [], [], []
+            for line in p.stdout.splitlines():
+                if line.startswith(b">"):
+                    if names:
+                        seqs.append(b"".join(cur))
+                    hdr = line[1:].split()
+                    names.append(hdr[0].decode("latin-1") if hdr else "")
+                    cur = []
+                else:
+                    cur.append(line.strip())
+            seqs.append(b"".join(cur))
+            return names, seqs
+    if os.environ.get("MIRGE_B200_TRUST_EBWT", "0") != "1":
+        raise MirgeError(
+            "library %s ships as a bowtie index only and no bowtie-inspect is on PATH.  Provide the sequences as FASTA next "
+            "to it (`bowtie-inspect %s > %s.fa`, on any machine that has bowtie), or set MIRGE_B200_TRUST_EBWT=1 to use the "
+            "built-in .ebwt decoder, which has not been validated against an index built by a real bowtie-build."
+            % (os.path.basename(index_base), index_base, index_base))
+    warnings.warn("mirge_b200: decoding %s.*.ebwt with the built-in, not yet bowtie-validated decoder (MIRGE_B200_TRUST_EBWT=1); "
+                  "annotation depends on it" % index_base, RuntimeWarning, stacklevel=3)
+    return ebwt.decode_index(index_base)
+
+
 class LibrarySet:
     """The libraries of one organism keyed by round library name (ROUND_LIBS)."""
 
@@ -255,7 +292,7 @@ class LibrarySet:
                 continue
             eb = os.path.join(base, "index.Libs", name)
             if os.path.exists(eb + ".1.ebwt"):
-                names, seqs = ebwt.decode_index(eb)
+                names, seqs = _sequences_of_index(eb, ebwt)
                 out[key] = DeviceLibrary(dev, names, seqs, key=key)
                 continue
             raise MirgeError("library %s not found under %s (no FASTA, no .ebwt index)" % (name, base))

@@ -3,6 +3,8 @@ globals ``baking`` publishes (digest.py:110-122): resolve miRge's ``args`` names
 plain ``mirge_trim_params`` structure the kernels consume."""
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import List, Optional, Sequence, Tuple
 
@@ -93,6 +95,7 @@ class TrimConfig:
     uniq_mol_ids: Optional[str] = None
     qiagenumi: bool = False
     count_mode: str = "head"
+    cutadapt_compat: str = ""  # "2-3" | "4" ("" = MIRGE_B200_CUTADAPT_COMPAT, default "2-3"); see include/mirge_b200.h
 
     @classmethod
     def from_args(cls, args, count_mode: str = "head") -> "TrimConfig":
@@ -210,6 +213,10 @@ def build_trim_params(cfg: TrimConfig) -> abi.TrimParams:
     if cfg.count_mode not in ("head", "release"):
         raise RuntimeError("count_mode must be 'head' or 'release'")
     p.count_mode = abi.COUNT_HEAD if cfg.count_mode == "head" else abi.COUNT_RELEASE
+    compat = cfg.cutadapt_compat or os.environ.get("MIRGE_B200_CUTADAPT_COMPAT", "2-3")
+    if compat not in ("2-3", "4"):
+        raise RuntimeError("cutadapt_compat must be '2-3' or '4'")
+    p.compat = abi.COMPAT_CUTADAPT4 if compat == "4" else abi.COMPAT_CUTADAPT23
     return p
 
 

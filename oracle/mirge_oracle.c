@@ -82,17 +82,20 @@ static inline int acgt_mask(int c) {
 typedef struct { int astart, astop, rstart, rstop, matches, errors; } match_t;
 
 /* cutadapt Aligner.locate (pyoracle.locate). Returns 1 if a match was found. */
-static int locate(const mirge_adapter *ad, const uint8_t *read, int n, match_t *out) {
+static int locate(const mirge_adapter *ad, const uint8_t *read, int n, match_t *out, int compat) {
+  /* merit carried by a cell: matches (cutadapt 2.x-3.x) or the score of cutadapt >= 4 (match +1, mismatch -1, indel -2) */
+  const int w_mis = compat == MIRGE_COMPAT_CUTADAPT4 ? -1 : 0, w_indel = compat == MIRGE_COMPAT_CUTADAPT4 ? -2 : 0;
   int m = ad->m;
   int cost[MAXM + 1], origin[MAXM + 1], matches[MAXM + 1];
   int back = ad->where == 0;
   int ic = ad->indel_cost;
   for (int i = 0; i <= m; ++i) {
-    matches[i] = 0;
+    matches[i] = back ? i * w_indel : 0;
     if (back) { cost[i] = i * ic; origin[i] = 0; } else { cost[i] = 0; origin[i] = -i; }
   }
   int k = ad->k;
-  int best_cost = m + n, best_origin = 0, best_matches = 0, best_ref_stop = m, best_query_stop = n;
+  int best_cost = m + n, best_origin = 0, best_matches = compat == MIRGE_COMPAT_CUTADAPT4 ? -(1 << 30) : 0, best_ref_stop = m,
+      best_query_stop = n;
   int stopped = 0;
   for (int j = 1; j <= n; ++j) {
     int dc = cost[0], dor = origin[0], dm = matches[0];
@@ -103,9 +106,9 @@ static int locate(const mirge_adapter *ad, const uint8_t *read, int n, match_t *
       if (ad->mask[i - 1] & rc) { c = dc; o = dor; mt = dm + 1; }
       else {
         int cd = dc + 1, cdel = cost[i] + ic, cins = cost[i - 1] + ic;
-        if (cd <= cdel && cd <= cins) { c = cd; o = dor; mt = dm; }
-        else if (cins <= cdel) { c = cins; o = origin[i - 1]; mt = matches[i - 1]; }
-        else { c = cdel; o = origin[i]; mt = matches[i]; }
+        if (cd <= cdel && cd <= cins) { c = cd; o = dor; mt = dm + w_mis; }
+        else if (cins <= cdel) { c = cins; o = origin[i - 1]; mt = matches[i - 1] + w_indel; }
+        else { c = cdel; o = origin[i]; mt = matches[i] + w_indel; }
       }
       dc = cost[i]; dor = origin[i]; dm = matches[i];
       cost[i] = c; origin[i] = o; matches[i] = mt;
@@ -143,7 +146,7 @@ static int locate(const mirge_adapter *ad, const uint8_t *read, int n, match_t *
 }
 
 /* Adapter.match_to: exact find on upper(read) first when the adapter has no wildcards. */
-static int match_to(const mirge_adapter *ad, const uint8_t *read, int n, match_t *out) {
+static int match_to(const mirge_adapter *ad, const uint8_t *read, int n, match_t *out, int compat) {
   int m = ad->m;
   if (!ad->wildcard_ref) {
     for (int p = 0; p + m <= n; ++p) {
@@ -152,14 +155,14 @@ static int match_to(const mirge_adapter *ad, const uint8_t *read, int n, match_t
       if (j == m) { out->astart = 0; out->astop = m; out->rstart = p; out->rstop = p + m; out->matches = m; out->errors = 0; return 1; }
     }
   }
-  return locate(ad, read, n, out);
+  return locate(ad, read, n, out, compat);
 }
 
 static int best_match(const mirge_trim_params *p, const uint8_t *read, int n, match_t *best) {
   int have = 0, which = -1;
   for (int a = 0; a < p->n_adapters; ++a) {
     match_t mt;
-    if (!match_to(&p->adapters[a], read, n, &mt)) continue;
+    if (!match_to(&p->adapters[a], read, n, &mt, p->compat)) continue;
     if (!have || mt.matches > best->matches || (mt.matches == best->matches && mt.errors < best->errors)) { *best = mt; have = 1; which = a; }
   }
   return which;

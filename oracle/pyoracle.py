@@ -168,7 +168,7 @@ class Adapter:
     """One parsed adapter (subset of cutadapt's spec language that miRge's CLI can produce from
     ``-a SEQ`` / ``-g SEQ``, parse.py:74-77: plain 3' ("back") and 5' ("front") adapters)."""
 
-    where: str  # "back" | "front"
+    where: str  # "back" | "front" | "prefix" (anchored 5', ^SEQ) | "suffix" (anchored 3', SEQ$)
     sequence: str
     max_error_rate: float = 0.12  # parse.py:91
     min_overlap: int = 3  # parse.py:90
@@ -194,14 +194,40 @@ class Adapter:
         if self.effective_length == 0:
             raise ValueError("Cannot have only N wildcards in the sequence")
         self.masks = [IUPAC[ch] for ch in self.sequence]
+        if self.where not in ("back", "front", "prefix", "suffix"):
+            raise ValueError("unknown adapter type %r" % (self.where,))
+        if self.where in ("prefix", "suffix"):
+            self.min_overlap = m  # cutadapt adapters.py: anchored adapters must occur in full
+
+
+@dataclass
+class LinkedAdapter:
+    """cutadapt ``LinkedAdapter`` ("ADAPTER1...ADAPTER2", quick_start.md:208-220): a 5' adapter, then a 3' adapter
+    searched in what the 5' match leaves.  ``-g A...B``: both required, A not anchored; ``-a A...B``: A anchored and
+    required, B optional (cutadapt parser.py ``_parse_linked``); ``^`` / ``$`` anchor explicitly."""
+
+    front: Adapter
+    back: Adapter
+    front_required: bool = True
+    back_required: bool = True
+
+    @property
+    def where(self):
+        return "linked"
 
 
 def _allowed(length: int, rate: float) -> float:
     return length * rate  # evaluated in double exactly as cutadapt's "cost <= length * max_error_rate"
 
 
-def locate(ad: Adapter, read: str) -> Optional[Tuple[int, int, int, int, int, int]]:
-    """cutadapt 2.x-3.x ``Aligner.locate(query)`` for back (3') and front (5') adapters.
+def locate(ad: Adapter, read: str, compat: str = "2-3") -> Optional[Tuple[int, int, int, int, int, int]]:
+    """cutadapt ``Aligner.locate(query)`` for back (3') and front (5') adapters.
+
+    ``compat`` "2-3" (the versions the reference names): every cell carries its number of matches and a candidate
+    wins with more matches, then lower cost.  "4": cutadapt >= 4.0 carries a score instead -- match +1, mismatch -1,
+    insertion / deletion -2, the first column of a 3' adapter starts at -2 i -- and a candidate wins with a higher
+    score, then lower cost; the fifth field of the result is then the score.  (Restated from the published
+    description; parity with an install is what tests/test_tier3_real_tools.py checks when one is there.)
 
     Returns (astart, astop, rstart, rstop, matches, errors) or None.  Unit-cost semi-global DP,
     adapter = rows, read = columns, one column kept; each cell carries (cost, origin, matches).
@@ -219,25 +245,39 @@ def locate(ad: Adapter, read: str) -> Optional[Tuple[int, int, int, int, int, in
     up = read.upper()
     # read characters -> 4-bit class (non-ACGT never matches; match_read_wildcards=False, parse.py:97)
     rmask = [ACGT.get(ch, 0) for ch in up]
+    # cutadapt's Where flags: BACK = start/stop anywhere in the read, adapter end may be skipped; FRONT = adapter start
+    # may be skipped instead; PREFIX (anchored 5') = read and adapter start together; SUFFIX (anchored 3') = end together
+    start_in_ref = ad.where == "front"
+    stop_in_ref = ad.where == "back"
+    start_in_query = ad.where in ("back", "front", "suffix")
+    stop_in_query = ad.where in ("back", "front", "prefix")
     back = ad.where == "back"
-    start_in_ref = not back  # FRONT: adapter start may be skipped
-    stop_in_ref = back  # BACK: adapter end may be skipped (overhang at the read's 3' end)
-    # start_in_query = stop_in_query = True for both  =>  min_n = 0, max_n = n
+    if compat not in ("2-3", "4"):
+        raise ValueError("compat must be '2-3' or '4'")
+    # what a step adds to the merit a cell carries (matches, or the score of cutadapt >= 4)
+    w_mis, w_indel = (-1, -2) if compat == "4" else (0, 0)
+    k = int(rate * m)
+    # columns that matter (Aligner.locate): an anchored start cannot use more than m + k read bases, an anchored end
+    # only the last m + k
+    max_n = n if start_in_query else min(n, m + k)
+    min_n = 0 if stop_in_query else max(0, n - m - k)
     cost = [0] * (m + 1)
     origin = [0] * (m + 1)
     matches = [0] * (m + 1)
-    if start_in_ref:
-        for i in range(m + 1):
-            cost[i] = 0
-            origin[i] = -i
-    else:
-        for i in range(m + 1):
-            cost[i] = i * ins_cost
-            origin[i] = 0
-    k = int(rate * m)
+    for i in range(m + 1):
+        if not start_in_ref and not start_in_query:
+            cost[i], origin[i] = max(i, min_n) * ins_cost, 0
+        elif start_in_ref and not start_in_query:
+            cost[i], origin[i] = min_n * ins_cost, min(0, min_n - i)
+        elif not start_in_ref and start_in_query:
+            cost[i], origin[i] = i * ins_cost, max(0, min_n - i)
+        else:
+            cost[i], origin[i] = min(i, min_n) * ins_cost, min_n - i
+        if not start_in_ref:
+            matches[i] = i * w_indel
     best_cost = m + n
     best_origin = 0
-    best_matches = 0
+    best_matches = 0 if compat != "4" else -(1 << 30)
     best_ref_stop = m
     best_query_stop = n
     stopped_early = False
@@ -249,9 +289,13 @@ def locate(ad: Adapter, read: str) -> Optional[Tuple[int, int, int, int, int, in
             return ad.effective_length
         return length
 
-    for j in range(1, n + 1):
+    for j in range(min_n + 1, max_n + 1):
         diag_c, diag_o, diag_m = cost[0], origin[0], matches[0]
-        origin[0] = j  # start_in_query
+        if start_in_query:
+            origin[0] = j
+        else:
+            cost[0] = j * ins_cost
+            matches[0] = j * w_indel
         rc = rmask[j - 1]
         for i in range(1, m + 1):
             if ad.masks[i - 1] & rc:
@@ -261,15 +305,15 @@ def locate(ad: Adapter, read: str) -> Optional[Tuple[int, int, int, int, int, in
                 cdel = cost[i] + del_cost
                 cins = cost[i - 1] + ins_cost
                 if cd <= cdel and cd <= cins:
-                    c, o, mt = cd, diag_o, diag_m
+                    c, o, mt = cd, diag_o, diag_m + w_mis
                 elif cins <= cdel:
-                    c, o, mt = cins, origin[i - 1], matches[i - 1]
+                    c, o, mt = cins, origin[i - 1], matches[i - 1] + w_indel
                 else:
-                    c, o, mt = cdel, origin[i], matches[i]
+                    c, o, mt = cdel, origin[i], matches[i] + w_indel
             diag_c, diag_o, diag_m = cost[i], origin[i], matches[i]
             cost[i], origin[i], matches[i] = c, o, mt
-        # row m is examined only when column[m].cost <= k ("last == m")
-        if cost[m] <= k:
+        # row m is examined only when column[m].cost <= k ("last == m"), and only if the match may end inside the read
+        if cost[m] <= k and stop_in_query:
             length = m + min(origin[m], 0)
             c = cost[m]
             mt = matches[m]
@@ -283,7 +327,7 @@ def locate(ad: Adapter, read: str) -> Optional[Tuple[int, int, int, int, int, in
                 if c == 0 and mt == m:
                     stopped_early = True
                     break
-    if not stopped_early:  # max_n == n always here
+    if not stopped_early and max_n == n:
         first_i = 0 if stop_in_ref else m
         for i in range(first_i, m + 1):
             length = i + min(origin[i], 0)
@@ -313,7 +357,7 @@ def locate(ad: Adapter, read: str) -> Optional[Tuple[int, int, int, int, int, in
     return (start1, best_ref_stop, start2, best_query_stop, best_matches, best_cost)
 
 
-def match_to(ad: Adapter, read: str) -> Optional[Tuple[int, int, int, int, int, int]]:
+def match_to(ad: Adapter, read: str, compat: str = "2-3") -> Optional[Tuple[int, int, int, int, int, int]]:
     """cutadapt ``Adapter.match_to``: exact ``str.find`` on the upper-cased read first (only when
     the adapter has no wildcards), otherwise ``Aligner.locate``.  The fast path returns what the
     DP would (leftmost exact occurrence: the DP stops at the first column with cost 0, matches m).
@@ -323,17 +367,17 @@ def match_to(ad: Adapter, read: str) -> Optional[Tuple[int, int, int, int, int, 
         pos = up.find(ad.sequence)
         if pos >= 0:
             m = len(ad.sequence)
-            return (0, m, pos, pos + m, m, 0)
-    return locate(ad, read)
+            return (0, m, pos, pos + m, m, 0)  # (m matches; also the score of m matches)
+    return locate(ad, read, compat)
 
 
-def best_match(adapters: Sequence[Adapter], read: str):
-    """cutadapt ``AdapterCutter._best_match``: most matches wins, then fewer errors; first adapter
-    wins remaining ties."""
+def best_match(adapters: Sequence[Adapter], read: str, compat: str = "2-3"):
+    """cutadapt ``AdapterCutter._best_match``: most matches (cutadapt >= 4: the highest score) wins, then fewer
+    errors; first adapter wins remaining ties."""
     best = None
     best_ad = None
     for ad in adapters:
-        mt = match_to(ad, read)
+        mt = match_to(ad, read, compat)
         if mt is None:
             continue
         if best is None or mt[4] > best[4] or (mt[4] == best[4] and mt[5] < best[5]):
@@ -371,6 +415,7 @@ class TrimParams:
     umi: Optional[Tuple[int, int]] = None  # parse.py:84 "-umi f,b"
     qiagenumi: bool = False  # parse.py:85
     count_mode: str = "head"  # "head": digest.py:354-373 as written; "release": dist/ 0.1.x
+    compat: str = "2-3"  # cutadapt's alignment objective: "2-3" (matches, then cost) or "4" (score, then cost)
 
     def modifiers(self) -> List[Tuple[str, tuple]]:
         """Ordered modifier list exactly as stipulate() builds it (digest.py:87-99):
@@ -409,7 +454,7 @@ def apply_modifier(mod, seq: str, qual: str, start: int, stop: int, p: TrimParam
         return start + s, start + e
     if kind == "adapter":
         for _ in range(p.times):
-            ad, mt = best_match(p.adapters, seq[start:stop])
+            ad, mt = best_match(p.adapters, seq[start:stop], p.compat)
             if mt is None:
                 break
             if ad.where == "back":

@@ -270,8 +270,11 @@ def test_streamed_annotation_matches_whole_table(dev):
     assert torch.equal(a2, ann2) and torch.equal(h2, hit2) and not sb.host
 
 
-def test_libraries_load_from_bowtie_index_files(dev, tmp_path):
-    """A library directory that ships only .ebwt files (stock miRge3_Lib) gives the same annotation as FASTA."""
+def test_libraries_load_from_bowtie_index_files(dev, tmp_path, monkeypatch):
+    """A library directory that ships only .ebwt files (stock miRge3_Lib) gives the same annotation as FASTA -- once the
+    built-in decoder is asked for: without MIRGE_B200_TRUST_EBWT=1 (and without a bowtie-inspect) the loader refuses."""
+    monkeypatch.setenv("PATH", str(tmp_path))  # no bowtie-inspect
+    monkeypatch.delenv("MIRGE_B200_TRUST_EBWT", raising=False)
     from mirge_b200 import libraries as LB
     from mirge_b200 import manifoldAlign as MA
     from mirge_b200.libraries import INDEX_SUFFIX, ROUND_LIBS
@@ -287,7 +290,13 @@ def test_libraries_load_from_bowtie_index_files(dev, tmp_path):
         write_ebwt(str(d / ("human" + INDEX_SUFFIX[rnd] + ("miRBase" if rnd in (0, 1, 8) else ""))),
                    ["%s some description" % n for n in names], seqs)
     a = LB.LibrarySet.from_mirge_lib(dev, str(tmp_path / "fa"), "human", "miRBase", True)
-    b = LB.LibrarySet.from_mirge_lib(dev, str(tmp_path / "eb"), "human", "miRBase", True)
+    from mirge_b200.device import MirgeError
+
+    with pytest.raises(MirgeError, match="MIRGE_B200_TRUST_EBWT"):
+        LB.LibrarySet.from_mirge_lib(dev, str(tmp_path / "eb"), "human", "miRBase", True)
+    monkeypatch.setenv("MIRGE_B200_TRUST_EBWT", "1")
+    with pytest.warns(RuntimeWarning, match="not yet bowtie-validated"):
+        b = LB.LibrarySet.from_mirge_lib(dev, str(tmp_path / "eb"), "human", "miRBase", True)
     seqs = make_queries(rng, libs, 1500)
     ks = MA.KeySet.from_strings(dev, seqs)
     ra, ha = MA.annotate_keys(dev, a, ks, True)

@@ -61,7 +61,8 @@ def random_config(rng):
                         overlap=int(rng.integers(1, 8)), indels=bool(rng.random() < 0.8), times=int(rng.integers(1, 3)),
                         nextseq_trim=int(rng.integers(10, 31)) if rng.random() < 0.3 else None, quality_cutoff=q,
                         quality_base=33, trim_n=bool(rng.random() < 0.3), cut=cut, minimum_length=int(rng.integers(0, 25)),
-                        uniq_mol_ids=umi, count_mode="head" if rng.random() < 0.7 else "release")
+                        uniq_mol_ids=umi, count_mode="head" if rng.random() < 0.7 else "release",
+                        cutadapt_compat="4" if rng.random() < 0.25 else "2-3")
 
 
 def random_reads(rng, cfg, n):

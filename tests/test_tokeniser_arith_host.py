@@ -1,4 +1,4 @@
-"""Host check of the tokeniser's newline-mask arithmetic (csrc/tokenise.cu::newline_mask; the kernel replaces the
+"""Host check of the tokeniser's newline-mask arithmetic (csrc/common.cuh::newline_mask, shared by tokenise.cu and the fused kernel of trim.cu; the kernel replaces the
 line splitting of dnaio's FastqIter, reference call site mirge/libs/digest.py:324) against a plain byte compare.
 It is a pure integer trick, so it is restated with numpy and swept over random words: any byte values, dense
 newlines, bytes >= 128."""
@@ -13,7 +13,7 @@ CSRC = os.path.join(mirge_b200.PACKAGE_DIR, "csrc")
 
 def test_newline_mask_arithmetic():
     """newline_mask(): exact zero-byte flags of w ^ '\\n' x 4, two words per multiply by 0x00204081."""
-    src = open(os.path.join(CSRC, "tokenise.cu")).read()
+    src = open(os.path.join(CSRC, "common.cuh")).read()
     assert "0x00204081u" in src and "0x7F7F7F7Fu" in src  # the constants restated below are the kernel's
     rng = np.random.default_rng(1)
     n = 200000

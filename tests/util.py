@@ -21,7 +21,7 @@ def py_params(cfg: P.TrimConfig) -> po.TrimParams:
     return po.TrimParams(adapters=ads, times=cfg.times, nextseq_trim=cfg.nextseq_trim,
                          quality_cutoff=cfg.quality_cutoff, quality_base=cfg.quality_base, trim_n=cfg.trim_n,
                          cut=list(cfg.cut), minimum_length=cfg.minimum_length, umi=cfg.umi(),
-                         qiagenumi=cfg.qiagenumi, count_mode=cfg.count_mode)
+                         qiagenumi=cfg.qiagenumi, count_mode=cfg.count_mode, compat=cfg.cutadapt_compat or "2-3")
 
 
 def random_fastq(n, seed=0, L=50, adapter=ILL, umi3=0, n_rate=0.01, lower_rate=0.0, err=0.03, indel=0.01,
@@ -90,6 +90,9 @@ CONFIGS = {
     "long_adapter": P.TrimConfig(adapters=[("back", LONG_AD)]),
     "reads150": P.TrimConfig(adapters=[("back", ILL)], nextseq_trim=20, quality_cutoff="20", trim_n=True, cut=[1]),
     "reads200": P.TrimConfig(adapters=[("back", ILL)], quality_cutoff="20"),
+    # cutadapt >= 4 objective (score instead of matches): full-DP kernel
+    "compat4": P.TrimConfig(adapters=[("back", ILL)], cutadapt_compat="4"),
+    "compat4_fb": P.TrimConfig(adapters=[("back", ILL), ("front", "GTTCAGAGTTCTACAGTCCGACGATC")], cutadapt_compat="4", times=2),
 }
 
 # keyword arguments for random_fastq that exercise each configuration
@@ -103,6 +106,8 @@ CONFIG_DATA = {
     "noq_m1": dict(varlen=True),
     "reads150": dict(L=150),  # still inside the packed-read fast path (PACK_WORDS * 16 = 160 bases)
     "reads200": dict(L=200),  # beyond it: whole-pipeline kernel per read
+    "compat4": dict(err=0.06, indel=0.04),
+    "compat4_fb": dict(front="CAGTCCGACGATC", err=0.06, indel=0.04),
 }
 
 
