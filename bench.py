@@ -9,8 +9,9 @@ tails, ``-a illumina -nxt 20 -q 20``, all ordered libraries incl. a 100 000-entr
 one whole pass of the hot path over that sample: tokenise -> trim -> collapse -> 9 annotation rounds.
 ``value``: inputs resident in HBM.  ``e2e``: the same pass fed from pinned HOST memory through the
 streaming entry point (H2D of every input byte and D2H of the result table inside the timed region).
-Multi-GPU (weak scaling): every rank digests its own 50 M-read shard, unique sequences are hash-
-partitioned to their owner rank with one all-to-all, owners merge and annotate their slice.
+Multi-GPU (weak scaling): every rank trims its own 50 M-read shard; the keys of every batch are hash-
+partitioned to their owner rank (all-to-all under the next batch's trim), owners collapse and annotate
+their slice.  Multi-sample / UMI configurations collapse locally and exchange unique sequences per sample.
 """
 import argparse
 import json
@@ -66,6 +67,8 @@ def parse_args():
     ap.add_argument("--e2e-batch-mb", type=int, default=256, help="piece size of the host-fed (e2e) pipeline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--overlap-exchange", action="store_true", help="N > 1: per-batch exchange on a worker thread / side stream")
+    ap.add_argument("--exchange-unique", action="store_true",
+                    help="N > 1, single-sample configs: local collapse + exchange of the unique sequences instead of sharding before the collapse")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     c = CONFIG_TABLE[a.config]
@@ -266,6 +269,11 @@ def run_dropin(args, dev, lset, libs, fq_dev, cfg_id):
             out = {"value": round(args.reads / (t2 - t0) / 1e6, 3), "unit": UNIT, "baking_s": round(t1 - t0, 2),
                    "bwtAlign_s": round(t2 - t1, 2), "rows": int(len(df)), "annotated_rows": int((df["annotFlag"] == 1).sum()),
                    "reads": int(src["sample"]), "input": "FASTQ file on /dev/shm", "output": "pandas DataFrame (reference contract)"}
+            try:  # the reference's own stage lines (run.log is appended to: the last pass's are the last ones)
+                lines = [ln.strip() for ln in open(os.path.join(tmp, "run.log")) if "second(s)" in ln]
+                out["run_log"] = lines[-5:]
+            except OSError:
+                pass
             del df
         return out
     finally:
@@ -323,9 +331,14 @@ def run_b200(args):
     # distributed.ExchangeWorker -- measured slower at N = 2 (61.6 vs 52 ms per pass): five drains / resets of GB-sized
     # tables and two streams of latency-bound kernels that take each other's SM slots cost more than the 12 ms they hide.)
     overlap = world > 1 and args.overlap_exchange and args.samples == 1 and umi is None
+    # N > 1, one sample whose reads are spread over the ranks (C2, C5): sharding before the collapse -- every batch's keys go
+    # to their owner ranks and are inserted once, there (distributed.ShardedCollapse); --exchange-unique keeps the
+    # local-collapse + exchange-of-unique-sequences path that multi-sample and UMI flows use
+    sharded = world > 1 and args.samples == 1 and umi is None and not overlap and not args.exchange_unique
+    sc = MD.ShardedCollapse(eng, world) if sharded else None
     table_b = D.CollapseTable(dev, min_keys=1 << 22) if overlap else None
     worker = MD.ExchangeWorker(local, world, owner_min_keys=1 << 22) if overlap else None
-    owner = worker.owner if worker else (D.CollapseTable(dev, min_keys=1 << 22) if world > 1 else None)
+    owner = worker.owner if worker else (D.CollapseTable(dev, min_keys=1 << 22) if (world > 1 and not sharded) else None)
     state = {}
     xumi = umi if umi is not None else (0, 0)
 
@@ -347,7 +360,7 @@ def run_b200(args):
         columns.append((ids, cnt))
 
     def annotate_final(columns):
-        tab = owner if world > 1 else table
+        tab = owner if owner is not None else table
         keys = MA.KeySet.from_table(tab)
         annot, hit = MA.annotate_keys(dev, lset, keys, args.spike)
         state.update(columns=columns, annot=annot, hit=hit, tab=tab)
@@ -366,6 +379,12 @@ def run_b200(args):
             annotate_final([(ids, cnt)])
             return n
         table.reset()
+        if sharded:
+            n = sc.digest_device(fqs[0], table, batch_bytes)
+            with dev.timed("drain"):
+                ids, cnt = table.drain()
+            annotate_final([(ids, cnt)])
+            return n
         if owner is not None:
             with dev.timed("owner_reset"):
                 owner.reset()
@@ -405,6 +424,24 @@ def run_b200(args):
     e1.record()
     barrier()
     torch.cuda.profiler.stop()
+    trace_to = os.environ.get("MIRGE_B200_TRACE")
+    if trace_to and rank == 0:
+        # diagnostics, outside the timed region: one more step under torch.profiler, kernels / copies per stream in time order
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            step_resident()
+            torch.cuda.synchronize()
+        evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+        evs.sort(key=lambda e: e.time_range.start)
+        t0 = evs[0].time_range.start if evs else 0
+        with open(trace_to, "w") as fh:
+            for e in evs:
+                fh.write("%10.3f %9.3f ms  stream %-4s %s\n" % ((e.time_range.start - t0) / 1e3, (e.time_range.end - e.time_range.start) / 1e3,
+                                                               getattr(e, "device_resource_id", getattr(e, "device_index", "?")), e.name[:90]))
+    elif trace_to and world > 1:
+        step_resident()  # (the step is collective)
+        torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / max(args.steps, 1)
     timers = dev.timer_totals()
     dev.timing = False
@@ -458,7 +495,7 @@ def run_b200(args):
 
         # single GPU, no UMI level: annotation and the D2H of the result table are streamed piece by piece behind the H2D
         # of the following pieces (the keys of a piece are final as soon as it is collapsed)
-        sa = MA.StreamedAnnotator(dev, lset, args.spike) if (world == 1 and umi is None) else None
+        sa = MA.StreamedAnnotator(dev, lset, args.spike) if ((world == 1 or sharded) and umi is None) else None
 
         def step_e2e():
             table.reset()
@@ -469,7 +506,7 @@ def run_b200(args):
                 sa.reset()
             for h in hosts:
                 if sa is not None:
-                    n += streamer.run(h, table, on_piece=sa)
+                    n += streamer.run(h, table, on_piece=sa, sharded=sc)
                     with dev.timed("drain"):
                         ids, cnt = table.drain()
                     columns.append((ids, cnt))

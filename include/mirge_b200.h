@@ -325,6 +325,21 @@ int mirge_partition_scatter(mirge_ctx *ctx, const mirge_table *t, const uint32_t
                             const uint32_t *d_dest, const uint32_t *d_words, uint64_t n, uint32_t n_parts,
                             uint64_t *d_cursors, uint32_t *d_rec, uint32_t *d_sizes, void *stream);
 
+/* Sharding BEFORE the collapse (reads of one sample spread over the ranks; the reference's counterpart is the
+ * parent loop that merges the workers' dictionaries, digest.py:141-163): the insert list of a batch (d_keys, d_ins as
+ * mirge_trim / mirge_digest_tiles wrote them) is cut by owner = hash(key) mod n_parts into n_parts regions of
+ * d_out_items (u64 = {u32 word offset of the key inside the region's keys, u32 count}; region d starts at d * cap_items)
+ * and d_out_keys (region d starts at word d * cap_words).  d_cursors[d] (u64[n_parts], zeroed here) = items << 32 | key
+ * words bound for d -- it keeps counting when a region is full; the caller then repeats with regions that large.
+ * mirge_shard_rebase: after the all-to-all the items of source s (item_counts[s] of them, back to back in d_items)
+ * get the word offset key_bases[s] of that source's keys (host arrays of n_parts values) added to their key offsets,
+ * which makes d_items an insert list for mirge_collapse_insert_list. */
+int mirge_shard_scatter(mirge_ctx *ctx, const uint32_t *d_keys, const uint64_t *d_ins, uint64_t n_items, uint32_t n_parts,
+                        uint32_t cap_items, uint32_t cap_words, uint64_t *d_cursors, uint64_t *d_out_items,
+                        uint32_t *d_out_keys, void *stream);
+int mirge_shard_rebase(mirge_ctx *ctx, uint64_t *d_items, uint32_t n_parts, const uint64_t *item_counts,
+                       const uint64_t *key_bases, void *stream);
+
 /* ---- stage 3: annotation rounds (bwtAlign, manifoldAlign.py:68-146) ------------------------ */
 /* 16-mer (zero padded, truncated at reference ends / ambiguous bases) of every base position:
  * d_kmer[n_bases], d_valid[n_bases] = number of usable bases (0..16).  Input to the host-side

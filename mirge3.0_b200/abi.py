@@ -151,6 +151,8 @@ SYMBOLS = {
     "mirge_partition_pack": (C.c_int, [_P, C.POINTER(Table), _P, _P, _U64, _P, _P, _P]),
     "mirge_partition_totals": (C.c_int, [_P, _P, _P, _U64, C.c_uint32, _P, _P]),
     "mirge_partition_scatter": (C.c_int, [_P, C.POINTER(Table), _P, _P, _P, _P, _U64, C.c_uint32, _P, _P, _P, _P]),
+    "mirge_shard_scatter": (C.c_int, [_P, _P, _P, _U64, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
+    "mirge_shard_rebase": (C.c_int, [_P, _P, C.c_uint32, _PU64, _PU64, _P]),
     "mirge_lib_kmers": (C.c_int, [_P, C.POINTER(Library), _P, _P, _P]),
     "mirge_lib_filter": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, _P, _P]),
     "mirge_lib_filter16": (C.c_int, [_P, _P, _P, C.c_uint32, C.c_uint32, _P, _P]),

@@ -874,3 +874,138 @@ extern "C" int mirge_partition_scatter(mirge_ctx *ctx, const mirge_table *t, con
   MIRGE_LAUNCH_CHECK(ctx, "partition_scatter_kernel");
   return MIRGE_OK;
 }
+
+// ------------------------------------------------------------------ sharding before the collapse -----------
+// One process per GPU, reads of ONE sample sharded over the ranks: the insert list of a batch
+// -- (key offset, count) of every distinct key a read emitted -- is cut by owner = hash(key) mod ranks BEFORE any
+// table sees it, the pieces travel with one all-to-all, and every rank collapses what it owns.  Nothing is inserted
+// twice (a local collapse followed by a merge of the unique sequences inserts nearly every read twice when most emitted
+// keys are unique, as the pre-adapter texts of HEAD counting are), and the owner's table, ids and annotation are the
+// single-GPU ones.
+//
+// Send side: n_parts regions of fixed capacity, region d = items[cap_items] (uint2: word offset of the key inside the
+// region's keys, count) and keys[cap_words].  A CTA counts its items per owner in shared memory, reserves its ranges
+// with ONE global atomic per owner and then copies; the order inside a region is arbitrary (counts do not depend on
+// it).  cursors[d] = items << 32 | words bound for d: it keeps counting when a region is full, so the host learns the
+// exact sizes from it and repeats with larger regions.
+
+#define XS_ITEMS 4
+
+__device__ __forceinline__ uint32_t owner_of(uint64_t h, uint32_t n_parts) {
+  return (uint32_t)(mix64(h ^ 0x5851F42D4C957F2Dull) % n_parts);
+}
+
+__global__ void __launch_bounds__(COL_THREADS)
+shard_scatter_kernel(const uint32_t *__restrict__ keys, const uint2 *__restrict__ ins, uint64_t n, uint32_t n_parts,
+                     uint32_t cap_items, uint32_t cap_words, unsigned long long *__restrict__ cursors,
+                     uint2 *__restrict__ out_items, uint32_t *__restrict__ out_keys) {
+  // (two 32-bit counters per owner: item slot and key space of an item are handed out independently -- the item
+  // carries its key's offset -- and 32-bit shared-memory atomics are native, 64-bit ones a compare-and-swap loop)
+  __shared__ uint32_t s_items[MAX_PARTS], s_words[MAX_PARTS], s_bi[MAX_PARTS], s_bw[MAX_PARTS], s_ok[MAX_PARTS];
+  if (threadIdx.x < MAX_PARTS) { s_items[threadIdx.x] = 0; s_words[threadIdx.x] = 0; }
+  __syncthreads();
+  const uint64_t chunk0 = (uint64_t)blockIdx.x * COL_THREADS * XS_ITEMS;
+  const unsigned lane = threadIdx.x & 31;
+  uint32_t off[XS_ITEMS], add[XS_ITEMS], nw[XS_ITEMS], dst[XS_ITEMS], l_item[XS_ITEMS], l_word[XS_ITEMS];
+#pragma unroll
+  for (int it = 0; it < XS_ITEMS; ++it) {
+    const uint64_t i = chunk0 + (uint64_t)it * COL_THREADS + threadIdx.x;
+    nw[it] = 0;
+    if (i >= n) continue;
+    const uint2 item = ins[i];
+    const uint32_t *key = keys + item.x;
+    const uint32_t w = key_words(key[0]);
+    off[it] = item.x;
+    add[it] = item.y;
+    nw[it] = w;
+    const uint32_t d = owner_of(hash_key(key, w), n_parts);
+    dst[it] = d;
+    // item slots: one atomic per group of lanes with the same owner
+    const unsigned peers = __match_any_sync(__activemask(), d);
+    uint32_t base = 0;
+    if (lane == (unsigned)(__ffs(peers) - 1)) base = atomicAdd(&s_items[d], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, __ffs(peers) - 1);
+    l_item[it] = base + __popc(peers & ((1u << lane) - 1u));
+    l_word[it] = atomicAdd(&s_words[d], w);
+  }
+  __syncthreads();
+  if (threadIdx.x < n_parts) {
+    const uint32_t ci = s_items[threadIdx.x], cw = s_words[threadIdx.x];
+    uint32_t ok = 1;
+    if (ci) {
+      const unsigned long long g = atomicAdd(cursors + threadIdx.x, ((unsigned long long)ci << 32) | cw);
+      s_bi[threadIdx.x] = (uint32_t)(g >> 32);
+      s_bw[threadIdx.x] = (uint32_t)g;
+      if ((g >> 32) + ci > cap_items || (g & 0xFFFFFFFFull) + cw > cap_words) ok = 0;
+    }
+    s_ok[threadIdx.x] = ok;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < XS_ITEMS; ++it) {
+    if (nw[it] == 0) continue;
+    const uint32_t d = dst[it];
+    if (!s_ok[d]) continue;  // region full: the host sees it in the cursors and repeats with larger regions
+    const uint32_t wo = s_bw[d] + l_word[it];
+    out_items[(uint64_t)d * cap_items + s_bi[d] + l_item[it]] = make_uint2(wo, add[it]);
+    const uint32_t *key = keys + off[it];
+    uint32_t *o = out_keys + (uint64_t)d * cap_words + wo;
+    for (uint32_t k = 0; k < nw[it]; ++k) o[k] = key[k];
+  }
+}
+
+extern "C" int mirge_shard_scatter(mirge_ctx *ctx, const uint32_t *d_keys, const uint64_t *d_ins, uint64_t n_items, uint32_t n_parts,
+                                   uint32_t cap_items, uint32_t cap_words, uint64_t *d_cursors, uint64_t *d_out_items,
+                                   uint32_t *d_out_keys, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  if (!d_cursors || n_parts == 0 || n_parts > MAX_PARTS) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "shard_scatter: 1..%d owners", MAX_PARTS);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  MIRGE_CUDA(ctx, cudaMemsetAsync(d_cursors, 0, n_parts * sizeof(uint64_t), stream));
+  if (n_items == 0) return MIRGE_OK;
+  if (!d_keys || !d_ins || !d_out_items || !d_out_keys) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "shard_scatter: null buffer");
+  const uint64_t per_cta = (uint64_t)COL_THREADS * XS_ITEMS;
+  shard_scatter_kernel<<<(unsigned)((n_items + per_cta - 1) / per_cta), COL_THREADS, 0, stream>>>(
+      d_keys, (const uint2 *)d_ins, n_items, n_parts, cap_items, cap_words, (unsigned long long *)d_cursors, (uint2 *)d_out_items,
+      d_out_keys);
+  MIRGE_LAUNCH_CHECK(ctx, "shard_scatter_kernel");
+  return MIRGE_OK;
+}
+
+// Receive side: the items of the n_parts sources lie back to back (source s = items [item_end[s-1], item_end[s])) and
+// their key offsets count from the start of their source's keys; the keys of source s rest at word key_base[s] of the
+// buffer the collapse reads (the table's arena): make the offsets absolute.
+struct ShardSources {
+  uint32_t item_end[MAX_PARTS];
+  uint32_t key_base[MAX_PARTS];
+};
+
+__global__ void __launch_bounds__(COL_THREADS)
+shard_rebase_kernel(uint2 *__restrict__ items, uint64_t n, uint32_t n_parts, const ShardSources src) {
+  const uint64_t i = (uint64_t)blockIdx.x * COL_THREADS + threadIdx.x;
+  if (i >= n) return;
+  uint32_t s = 0;
+  while (s + 1 < n_parts && i >= src.item_end[s]) ++s;
+  items[i].x += src.key_base[s];
+}
+
+extern "C" int mirge_shard_rebase(mirge_ctx *ctx, uint64_t *d_items, uint32_t n_parts, const uint64_t *item_counts,
+                                  const uint64_t *key_bases, void *stream_) {
+  if (!ctx) return MIRGE_ERR_ARG;
+  if (!item_counts || !key_bases || n_parts == 0 || n_parts > MAX_PARTS) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "shard_rebase: 1..%d sources", MAX_PARTS);
+  ShardSources src;
+  uint64_t n = 0;
+  for (uint32_t s = 0; s < n_parts; ++s) {
+    n += item_counts[s];
+    if (n > 0xFFFFFFFFull || key_bases[s] >= 0xFFFFFFF0ull) MIRGE_FAIL(ctx, MIRGE_ERR_CAPACITY, "shard_rebase: offsets beyond 2^32");
+    src.item_end[s] = (uint32_t)n;
+    src.key_base[s] = (uint32_t)key_bases[s];
+  }
+  if (n == 0) return MIRGE_OK;
+  if (!d_items) MIRGE_FAIL(ctx, MIRGE_ERR_ARG, "shard_rebase: null buffer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  MIRGE_CUDA(ctx, cudaSetDevice(ctx->device));
+  shard_rebase_kernel<<<(unsigned)((n + COL_THREADS - 1) / COL_THREADS), COL_THREADS, 0, stream>>>((uint2 *)d_items, n, n_parts, src);
+  MIRGE_LAUNCH_CHECK(ctx, "shard_rebase_kernel");
+  return MIRGE_OK;
+}

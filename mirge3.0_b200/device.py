@@ -344,7 +344,7 @@ class DigestEngine:
             if table is not None:
                 table.reserve(0, cap)
                 keys = table.arena
-                ctrl[0] = base_words
+                ctrl[0:1].fill_(base_words)
                 cap_abs = int(table.arena.numel())
             else:
                 keys = d.empty(cap, torch.int32)
@@ -391,7 +391,7 @@ class DigestEngine:
             line_start, win, key_off = line_start[: 4 * n + 4], win[: n * E * 4], key_off[: n * E]
         if table is not None:
             table.arena_used = words_used
-            table.ctrl[0] = table.arena_used
+            table.ctrl[0:1].fill_(table.arena_used)
             return BatchResult(n, used, int(c[1]), int(c[4]), line_start, win, key_off, None, True, words_used - base_words, ins, n_items)
         return BatchResult(n, used, int(c[1]), int(c[4]), line_start, win, key_off, keys, False, words_used, ins, n_items)
 
@@ -436,7 +436,7 @@ class DigestEngine:
             if table is not None:
                 table.reserve(0, cap)  # room in the arena for this batch's keys
                 keys = table.arena
-                ctrl[0] = base_words
+                ctrl[0:1].fill_(base_words)
                 cap_abs = int(table.arena.numel())
             else:
                 keys = d.empty(cap, torch.int32)
@@ -477,7 +477,7 @@ class DigestEngine:
             break
         if table is not None:
             table.arena_used = words_used
-            table.ctrl[0] = table.arena_used  # the table's own counter of arena words in use
+            table.ctrl[0:1].fill_(table.arena_used)  # the table's own counter of arena words in use
             return BatchResult(n, used, int(c[1]), int(c[4]), line_start if keep else None, win, key_off, None, True,
                                words_used - base_words, ins, n_items)
         return BatchResult(n, used, int(c[1]), int(c[4]), line_start if keep else None, win, key_off, keys, False,

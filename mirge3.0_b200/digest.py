@@ -101,8 +101,10 @@ class HostStreamer:
                 return
             cur = (cur + 1) % self.n_buf
 
-    def run(self, src, table: CollapseTable, on_piece=None) -> int:
-        """Digest the whole stream into ``table``; returns the number of records parsed."""
+    def run(self, src, table: CollapseTable, on_piece=None, sharded=None) -> int:
+        """Digest the whole stream into ``table``; returns the number of records parsed.  ``sharded``
+        (distributed.ShardedCollapse, one process per GPU): the stream is this rank's share of the sample's reads; every
+        piece's keys go to their owner ranks before the collapse, and ``table`` receives the keys this rank owns."""
         eng, dev, H = self.eng, self.dev, self.headroom
         main = torch.cuda.current_stream(dev.tdev)
         it = self._pieces(src)
@@ -135,6 +137,7 @@ class HostStreamer:
         for _ in range(self.n_buf - 1):
             enqueue()
         n_records = 0
+        more_any = True  # sharded: whether any rank has announced more input (unknown before this rank's first round)
         tail = 0  # bytes of the previous piece's incomplete last record, sitting just below the headroom mark
         while pending:
             b, n, ev = pending.pop(0)
@@ -143,7 +146,7 @@ class HostStreamer:
             main.wait_event(ev)
             nbytes = tail + n
             view = self.d[b][H - tail : H + n]
-            br = eng.trim_batch(view, nbytes, final, keep=False, table=table)
+            br = eng.trim_batch(view, nbytes, final, keep=False, table=None if sharded is not None else table)
             if not final:
                 new_tail = nbytes - br.consumed
                 if new_tail > H:
@@ -153,13 +156,18 @@ class HostStreamer:
                 if new_tail:
                     self.d[pending[0][0]][H - new_tail : H].copy_(view[br.consumed : nbytes])
                 tail = new_tail
-            eng.collapse_batch(table, br)
+            if sharded is not None:
+                more_any = sharded.round(table, br, not final, on_piece)
+            else:
+                eng.collapse_batch(table, br)
             fe = torch.cuda.Event()
             fe.record(main)
             free_ev[b] = fe
             n_records += br.n_records
-            if on_piece is not None:
+            if sharded is None and on_piece is not None:
                 on_piece(table)
+        if sharded is not None:
+            sharded.drain_rounds(table, more_any, on_piece)
         return n_records
 
 
@@ -249,8 +257,8 @@ class DeviceKeys:
     """What build_matrix leaves in DataFrame.attrs for bwtAlign: the table whose arena holds the packed keys and the
     key id of every row.  Not data: pickling the DataFrame (-spl / -rr, __main__.py:101,145) drops it."""
 
-    def __init__(self, table, order):
-        self.table, self.order = table, order
+    def __init__(self, table, order, lens=None):
+        self.table, self.order, self.lens = table, order, lens
 
     def __reduce__(self):
         return (_no_keys, ())
@@ -297,25 +305,43 @@ def sequence_index_packed(offsets: np.ndarray, data: np.ndarray) -> pd.Index:
     return pd.Index(pd.arrays.ArrowStringArray(arr), name="Sequence")
 
 
+def empty_flag_column(n: int):
+    """A column of n empty strings with the dtype ``df.assign(col="")`` gives under the installed pandas (object before
+    3.0, the Arrow-backed ``str`` dtype from 3.0 on) -- for the Arrow dtype one shared all-zero offsets buffer instead of
+    n Python objects (``assign`` of ten such columns took 8 s for 39 M rows)."""
+    dt = pd.DataFrame(index=[0]).assign(x="")["x"].dtype
+    if dt == object:
+        return np.full(n, "", dtype=object)
+    import pyarrow as pa
+
+    arr = pa.LargeStringArray.from_buffers(n, pa.py_buffer(np.zeros(n + 1, dtype=np.int64)), pa.py_buffer(b""))
+    return pd.array(arr, dtype=dt)
+
+
 def build_matrix(table: CollapseTable, samples: List[SampleResult], names: List[str]) -> pd.DataFrame:
     """digest.py:237-261: unique sequences x samples, rows in lexicographic order (what pandas' outer
-    join produces for > 1 sample; the single-sample order of the reference is not deterministic)."""
+    join produces for > 1 sample; the single-sample order of the reference is not deterministic).  Columns as the
+    reference leaves them (digest.py:253-256): annotFlag (int), the ten annotation columns (''), the samples."""
     n = int(table.n_keys)
-    mat = np.zeros((n, len(samples)), dtype=np.int64)
+    cols = np.zeros((len(samples), n), dtype=np.int64)  # one contiguous row per sample
     for j, s in enumerate(samples):
-        mat[s.ids, j] = s.counts
-    seen = mat.any(axis=1) if n else np.zeros(0, dtype=bool)
+        cols[j, s.ids] = s.counts
+    seen = cols.any(axis=0) if n else np.zeros(0, dtype=bool)
     # order, selection and the packed texts come from the device (CollapseTable.export_sorted)
     order, offsets, data = table.export_sorted(seen)
     index = sequence_index_packed(offsets, data)
-    df = pd.DataFrame(mat[order], index=index, columns=list(names))
-    df = df.assign(**dict.fromkeys(INITIAL_FLAGS, ""))
-    df = df.assign(annotFlag=0)
-    df = df.reindex(columns=["annotFlag"] + INITIAL_FLAGS + list(names))
-    df = df.astype({"annotFlag": int})
+    m = int(order.shape[0])
+    empty = empty_flag_column(m)
+    frame = {"annotFlag": np.zeros(m, dtype=np.dtype(int))}
+    frame.update((f, empty) for f in INITIAL_FLAGS)
+    df = pd.DataFrame(frame, index=index, copy=False)
+    for j, name in enumerate(names):
+        df[name] = cols[j][order]
+    if not len(names):
+        df = df.reindex(columns=["annotFlag"] + INITIAL_FLAGS)
     # the packed keys stay on the device: bwtAlign finds them here instead of re-encoding every index string
-    # (row i of the DataFrame = key id order[i] of the table)
-    df.attrs["_mirge_b200_keys"] = DeviceKeys(table, order)
+    # (row i of the DataFrame = key id order[i] of the table); the text lengths serve the read-length histogram
+    df.attrs["_mirge_b200_keys"] = DeviceKeys(table, order, np.diff(offsets))
     return df
 
 
@@ -397,7 +423,8 @@ def _write_histograms(workDir, df: pd.DataFrame, results: List[SampleResult], na
     except Exception:
         return
     histData = FormatJS(workDir)
-    lens = df.index.str.len().to_numpy()
+    cached = df.attrs.get("_mirge_b200_keys")
+    lens = cached.lens if cached is not None and cached.lens is not None and len(cached.lens) == len(df) else df.index.str.len().to_numpy()
     for div_idnum, (name, res) in enumerate(zip(names, results), 1):
         val = lens[df[name].to_numpy() > 0]
         if val.size == 0:

@@ -135,7 +135,7 @@ def merge_received(dev, owner_table, r_rec: torch.Tensor, r_sizes: torch.Tensor,
         r_off = (torch.cumsum(r_sizes.to(torch.int64), 0) - r_sizes.to(torch.int64) + a0)
         r_off = torch.where(r_off >= (1 << 31), r_off - (1 << 32), r_off).to(torch.int32)
         owner_table.arena_used = a0 + int(r_rec.numel())
-        owner_table.ctrl[0] = owner_table.arena_used
+        owner_table.ctrl[0:1].fill_(owner_table.arena_used)
         deferred = dev.empty(m, torch.int32)
         dev.check(dev.lib.mirge_collapse_merge_inplace(dev.ctx, C.byref(owner_table.struct), _ptr(r_off), m, _ptr(deferred), dev.stream()))
         dev.launches += 3
@@ -179,6 +179,254 @@ def loopback_exchange(devs, local_tables, pairs, owner_tables, umi=(0, 0)):
             at += int(part.numel())
         merged.append(merge_received(dev, owner_tables[o], dst, r_sizes, state["a0"]))
     return merged
+
+
+class ShardedCollapse:
+    """Collapse of ONE sample whose reads are spread over the ranks (bench.py weak scaling, a large sample cut by reads):
+    sharding BEFORE the collapse.  Per batch of a rank's reads:
+
+        pack      the batch's insert list (what the trim kernels wrote: packed keys + (key offset, count) items) is cut
+                  by owner = hash(key) mod world into fixed-capacity regions (mirge_shard_scatter);
+        sizes     one all-gather of the per-owner (items, words) tells every rank what it will receive; the flag that
+                  rides along says whether the rank has more input, so ranks with fewer batches keep joining rounds;
+        exchange  two all-to-alls with exact sizes (items; key words straight into the end of the owner's arena);
+        insert    key offsets made absolute (mirge_shard_rebase), then the single-GPU collapse
+                  (mirge_collapse_insert_list, keys in place).
+
+    The rounds are software-pipelined: while round k is packed, round k - 1 is on the wire and round k - 2 is inserted.
+    Collectives run on a side stream (under the next batch's trim kernels) and their sizes come back through pinned
+    memory, so the launch stream never waits for the host or the network.  Every emitted key is inserted exactly once,
+    into the table of the rank that owns it: there is no local table and no drain / sort / merge of unique sequences
+    (exchange_and_merge above, still the path for samples dealt whole to ranks: baking_sharded).  Owner tables, key ids
+    and the annotation that follows are the single-GPU ones.
+
+        more = True
+        for every local batch:  more = sc.round(table, br, has_more_input)
+        sc.drain_rounds(table, more)          # join the other ranks' remaining rounds, insert the last arrivals
+    """
+
+    def __init__(self, eng, world: int, group=None, overlap: bool = True, slack: float = 1.2):
+        self.eng, self.dev = eng, eng.dev
+        self.world, self.group = int(world), group
+        self.slack = float(slack)
+        self.overlap = bool(overlap)
+        if group is None and dist.is_initialized() and dist.get_backend() == "nccl" and self.overlap:
+            # the collectives run under the trim / collapse kernels of other rounds: NCCL's kernels must not queue behind
+            # the CTAs of those grids, so this path gets its own communicator on a high-priority stream (collective: every
+            # rank constructs its ShardedCollapse at the same point)
+            try:
+                opts = dist.ProcessGroupNCCL.Options()
+                opts.is_high_priority_stream = True
+                self.group = dist.new_group(backend="nccl", pg_options=opts)
+            except Exception:
+                self.group = None
+        self.comm = torch.cuda.Stream(device=self.dev.tdev, priority=-1)
+        self.q = []  # rounds in flight, oldest first
+        self.rounds = 0
+        self._pinned = []
+
+    # -- sender ------------------------------------------------------------------------------------------------
+    def pack(self, br, cap_items: int = 0, cap_words: int = 0):
+        """Cut the batch's insert list by owner.  Returns a dict with the regions and their capacities."""
+        from .device import _ptr
+
+        d, W = self.dev, self.world
+        n_items = int(br.n_items) if br is not None else 0
+        words = int(br.arena_words) if br is not None else 0
+        cap_items = max(int(cap_items), int(n_items / W * self.slack) + 1024)
+        cap_words = max(int(cap_words), int(words / W * self.slack) + 8192)
+        items = d.empty(W * cap_items, torch.int64)
+        keys = d.empty(W * cap_words, torch.int32)
+        cursors = d.empty(W, torch.int64)
+        src_keys = None
+        if n_items:
+            if br.in_place:
+                raise RuntimeError("ShardedCollapse.pack: the batch must be trimmed into a batch buffer (table=None)")
+            src_keys = br.keys
+        with d.timed("shard_pack"):
+            d.check(d.lib.mirge_shard_scatter(d.ctx, _ptr(src_keys), _ptr(br.ins if n_items else None), n_items, W, cap_items, cap_words,
+                                              _ptr(cursors), _ptr(items), _ptr(keys), d.stream()))
+        d.launches += 1
+        return {"items": items, "keys": keys, "cursors": cursors, "cap_items": cap_items, "cap_words": cap_words, "br": br}
+
+    @staticmethod
+    def split_cursors(cur):
+        """(items[world], words[world]) from the packed cursors (host ints)."""
+        return [int(c) >> 32 for c in cur], [int(c) & 0xFFFFFFFF for c in cur]
+
+    def settle(self, packed, cur):
+        """Repeat the scatter with exact capacities when a region was too small (skewed owners).  ``cur`` = this rank's
+        cursors on the host; they are exact either way."""
+        n_it, n_w = self.split_cursors(cur)
+        if max(n_it) <= packed["cap_items"] and max(n_w) <= packed["cap_words"]:
+            return packed
+        return self.pack(packed["br"], max(n_it) + 1, max(n_w) + 1)
+
+    def _gather_sizes(self, packed, more: bool):
+        """All-gather of the cursors (+ the 'more input' flag) on the side stream, result on its way to pinned memory."""
+        W = self.world
+        main = torch.cuda.current_stream(self.dev.tdev)
+        host = self._pinned.pop() if self._pinned else torch.empty((W, W + 1), dtype=torch.int64).pin_memory()
+        self.comm.wait_stream(main)
+        packed["cursors"].record_stream(self.comm)
+        with torch.cuda.stream(self.comm):
+            mine = torch.empty(W + 1, dtype=torch.int64, device=self.dev.tdev)
+            mine[:W] = packed["cursors"]
+            mine[W:].fill_(1 if more else 0)  # (a kernel argument; ``mine[W] = ...`` is a pageable copy that blocks the host)
+            allc = torch.empty((W, W + 1), dtype=torch.int64, device=self.dev.tdev)
+            dist.all_gather_into_tensor(allc.view(-1), mine, group=self.group)
+            host.copy_(allc, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.comm)
+        return host, ev
+
+    # -- receiver ----------------------------------------------------------------------------------------------
+    def place(self, table, recv_items, recv_words):
+        """Room for the received keys at the end of the owner's arena: (items buffer, arena slice, key bases)."""
+        d = self.dev
+        n_it, n_w = int(sum(recv_items)), int(sum(recv_words))
+        if table.arena_used + n_w > table.arena.numel():
+            self.comm.synchronize()  # the arena is about to move: nothing may still be arriving in the old one
+        table.reserve(n_it, n_w)
+        a0 = table.arena_used
+        bases, at = [], a0
+        for w in recv_words:
+            bases.append(at)
+            at += int(w)
+        table.arena_used = at
+        table.ctrl[0:1].fill_(at)
+        return d.empty(n_it, torch.int64), table.arena[a0:at], bases
+
+    def insert(self, table, items, recv_items, bases, local_br=None):
+        """The received items into the owner's table (keys already in its arena)."""
+        import ctypes as C
+
+        from .device import _ptr
+
+        d, W = self.dev, self.world
+        st_ = self.eng.stats
+        if local_br is not None:  # the rank's own reads: what bench.py's rooflines are quoted on
+            st_["records"] += local_br.n_records
+            st_["bytes"] += local_br.consumed
+            st_["emitted"] += local_br.n_emitted
+            st_["key_words"] += local_br.key_words
+        n = int(sum(recv_items))
+        if n == 0:
+            return
+        cnt = (C.c_uint64 * W)(*[int(x) for x in recv_items])
+        kb = (C.c_uint64 * W)(*[int(x) for x in bases])
+        with d.timed("shard_rebase"):
+            d.check(d.lib.mirge_shard_rebase(d.ctx, _ptr(items), W, cnt, kb, d.stream()))
+        table.reserve(n, 0)
+        scratch = d.empty(2 * n, torch.int32)
+        with d.timed("collapse"):
+            d.check(d.lib.mirge_collapse_insert_list(d.ctx, C.byref(table.struct), _ptr(table.arena), _ptr(items), n, _ptr(scratch), d.stream()))
+        d.launches += 5
+        before = table.n_keys
+        table.check()
+        table.new_frac = (table.n_keys - before) / max(n, 1)
+
+    # -- the pipeline (collective) -----------------------------------------------------------------------------------
+    def _exchange(self, table, r) -> bool:
+        """Stage 2 of round r: its sizes have arrived -> room in the arena, the two all-to-alls on the side stream.
+        Returns whether any rank announced more input in that round."""
+        W = self.world
+        rank = dist.get_rank(self.group)
+        main = torch.cuda.current_stream(self.dev.tdev)
+        r["ev_sizes"].synchronize()
+        allc = r["host"].numpy().copy()
+        self._pinned.append(r.pop("host"))
+        packed = r["packed"]
+        again = self.settle(packed, allc[rank, :W])
+        if again is not packed:
+            packed = r["packed"] = again
+            self.comm.wait_stream(main)  # (the repeated scatter runs on the launch stream)
+        send_it, send_w = self.split_cursors(allc[rank, :W])
+        recv_it, recv_w = [int(allc[s, rank]) >> 32 for s in range(W)], [int(allc[s, rank]) & 0xFFFFFFFF for s in range(W)]
+        r_items, r_keys, bases = self.place(table, recv_it, recv_w)
+        ci, cw = packed["cap_items"], packed["cap_words"]
+        s_items = [packed["items"][d * ci : d * ci + send_it[d]] for d in range(W)]
+        s_keys = [packed["keys"][d * cw : d * cw + send_w[d]] for d in range(W)]
+        o_items = list(torch.split(r_items, recv_it)) if r_items.numel() else [r_items[:0]] * W
+        o_keys = list(torch.split(r_keys, recv_w)) if r_keys.numel() else [r_keys[:0]] * W
+        for t in (packed["items"], packed["keys"], r_items, table.arena):
+            t.record_stream(self.comm)
+        with torch.cuda.stream(self.comm):
+            with self.dev.timed("shard_a2a"):
+                # what this rank owns itself does not go through the communicator: a device-to-device copy
+                o_items[rank].copy_(s_items[rank], non_blocking=True)
+                o_keys[rank].copy_(s_keys[rank], non_blocking=True)
+                o_items[rank], s_items[rank] = r_items[:0], packed["items"][:0]
+                o_keys[rank], s_keys[rank] = r_keys[:0], packed["keys"][:0]
+                if W > 1:
+                    dist.all_to_all(o_items, s_items, group=self.group)
+                    dist.all_to_all(o_keys, s_keys, group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.comm)
+        r.update(items=r_items, recv_items=recv_it, bases=bases, ev_data=ev, stage=2)
+        return bool(allc[:, W].any())
+
+    def _insert_round(self, table, r, on_piece=None):
+        torch.cuda.current_stream(self.dev.tdev).wait_event(r["ev_data"])
+        self.insert(table, r["items"], r["recv_items"], r["bases"], r["packed"]["br"])
+        if on_piece is not None:
+            on_piece(table)
+
+    def round(self, table, br, more: bool, on_piece=None) -> bool:
+        """One collective round: this rank's batch ``br`` (None: no input left; ``more``: whether input remains after it)
+        is packed and its sizes announced; the previous round goes on the wire; the one before is inserted
+        (``on_piece(table)`` after it).  Returns False once every rank's input is known to be exhausted -- nothing was
+        started then and the caller must stop calling (drain_rounds does the rest); True otherwise."""
+        packed = self.pack(br)  # (first: the scatter follows the trim kernels without waiting for the host work below)
+        any_more = True
+        if self.q and self.q[-1]["stage"] == 1:
+            any_more = self._exchange(table, self.q[-1])
+        if not any_more:
+            if br is not None and br.n_records:
+                raise RuntimeError("ShardedCollapse: a batch arrived after every rank had announced the end of its input")
+            return False
+        host, ev = self._gather_sizes(packed, more)
+        self.q.append({"stage": 1, "packed": packed, "host": host, "ev_sizes": ev})
+        self.rounds += 1
+        depth = 2 if self.overlap else 0
+        while len(self.q) > depth and self.q[0]["stage"] == 2:
+            self._insert_round(table, self.q.pop(0), on_piece)
+        if not self.overlap:  # in line: exchange and insert this round now
+            any_more = self._exchange(table, self.q[-1])
+            self._insert_round(table, self.q.pop(0), on_piece)
+            return any_more
+        return True
+
+    def drain_rounds(self, table, more_any: bool = True, on_piece=None):
+        """After a rank's last batch: keep joining rounds while another rank may have input, then insert what is still
+        on its way.  Leaves the object ready for the next sample."""
+        while more_any:
+            more_any = self.round(table, None, False, on_piece)
+        while self.q:
+            r = self.q.pop(0)
+            if r["stage"] == 1:  # (cannot happen after a False round; kept for symmetry)
+                self._exchange(table, r)
+            self._insert_round(table, r, on_piece)
+
+    def digest_device(self, buf: torch.Tensor, table, batch_bytes: int = 256 << 20, on_piece=None) -> int:
+        """DigestEngine.digest_device for a rank's shard of the sample: returns the records this rank parsed; ``table``
+        ends up holding the keys this rank owns with their counts over ALL ranks' reads."""
+        from .device import FastqFormatError
+
+        eng = self.eng
+        total, pos, n_records = int(buf.numel()), 0, 0
+        more_any = True
+        while pos < total:
+            end = min(total, pos + batch_bytes)
+            final = end == total
+            br = eng.trim_batch(buf[pos:end], end - pos, final, keep=False, table=None)
+            if br.consumed == 0 and not final:
+                raise FastqFormatError("no complete FASTQ record in batch")
+            pos += br.consumed if not final else (end - pos)
+            n_records += br.n_records
+            more_any = self.round(table, br, pos < total, on_piece)
+        self.drain_rounds(table, more_any, on_piece)
+        return n_records
 
 
 class ExchangeWorker:

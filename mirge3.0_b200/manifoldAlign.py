@@ -4,6 +4,7 @@ bowtie ten times and parsing SAM text (manifoldAlign.py:12-64)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 import time
 from pathlib import Path
 from typing import Dict, Optional, Sequence, Tuple
@@ -331,17 +332,89 @@ def _filled_column(old: "pd.Series", rows: np.ndarray, names: np.ndarray, ref: n
     return pd.array(arr, dtype=old.dtype)
 
 
-def _rows_match(cached, seqs, probes: int = 64) -> bool:
+def _round_column_device(dev: Device, annot_d: torch.Tensor, ref_d: torch.Tensor, rnd: int, names, dtype):
+    """The same column for pandas' Arrow-backed string dtype, assembled on the device: per-row name lengths -> running
+    sum = the Arrow offsets buffer, name bytes gathered into the data buffer; two device-to-host copies and no pass over
+    the rows on the host.  None when the round annotated nothing."""
+    import pandas as pd
+    import pyarrow as pa
+
+    rows = torch.nonzero(annot_d == rnd).squeeze(1)
+    if rows.numel() == 0:
+        return None
+    n = int(annot_d.numel())
+    enc = [nm.encode("utf-8") for nm in names]
+    name_len = torch.from_numpy(np.fromiter((len(b) for b in enc), dtype=np.int64, count=len(enc))).to(dev.tdev)
+    name_off = torch.cumsum(name_len, 0) - name_len
+    blob = torch.from_numpy(np.frombuffer(b"".join(enc) or b"\0", dtype=np.uint8).copy()).to(dev.tdev)
+    ref_r = ref_d[rows].to(torch.int64)
+    lens_r = name_len[ref_r]
+    offsets = torch.zeros(n + 1, dtype=torch.int64, device=dev.tdev)
+    offsets[rows + 1] = lens_r
+    torch.cumsum(offsets, 0, out=offsets)
+    total = int(offsets[-1].item())
+    out_start = offsets[rows]
+    src = torch.arange(total, device=dev.tdev, dtype=torch.int64) - torch.repeat_interleave(out_start - name_off[ref_r], lens_r)
+    data = blob[src] if total else blob[:0]
+    arr = pa.LargeStringArray.from_buffers(n, pa.py_buffer(offsets.cpu().numpy()), pa.py_buffer(data.cpu().numpy()))
+    return pd.array(arr, dtype=dtype)
+
+
+def _fill_rounds_device(pdDataFrame, dev: Device, annot_d: torch.Tensor, ref_d: torch.Tensor, libs, n_rounds: int) -> bool:
+    """_fill_rounds with the columns built on the device; False (nothing done) unless the table is large and every
+    annotation column is still the all-'' Arrow string column baking() hands over."""
+    colnames = list(pdDataFrame.columns)
+    n = len(pdDataFrame)
+    if n < 1_000_000:
+        return False
+    for rnd in range(n_rounds):
+        col = pdDataFrame[colnames[1 + rnd]]
+        if col.dtype == object or not hasattr(col.array, "_pa_array") or bool((col != "").any()):
+            return False
+    for rnd in range(n_rounds):
+        col = _round_column_device(dev, annot_d, ref_d, rnd, libs[ROUND_LIBS[rnd]].names, pdDataFrame[colnames[1 + rnd]].dtype)
+        if col is not None:
+            pdDataFrame[colnames[1 + rnd]] = col
+    return True
+
+
+def _fill_rounds(pdDataFrame, annot: np.ndarray, ref: np.ndarray, libs, n_rounds: int, threads: int = 0):
+    """Columns 1 + round of every round that annotated something (manifoldAlign.py:17-18,55).  The rounds are independent
+    (a sequence is annotated by one round), so large tables build their columns on a few threads: numpy and Arrow
+    release the GIL for the passes over tens of millions of rows."""
+    colnames = list(pdDataFrame.columns)
+
+    def one(rnd):
+        rows = np.nonzero(annot == rnd)[0]
+        if rows.size == 0:
+            return rnd, None
+        names = np.asarray(libs[ROUND_LIBS[rnd]].names, dtype=object)
+        return rnd, _filled_column(pdDataFrame[colnames[1 + rnd]], rows, names, ref[rows])
+
+    rounds = list(range(n_rounds))
+    if len(annot) > 1_000_000:
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=max(1, min(len(rounds), threads or (os.cpu_count() or 4)))) as ex:
+            built = list(ex.map(one, rounds))
+    else:
+        built = [one(r) for r in rounds]
+    for rnd, col in built:
+        if col is not None:
+            pdDataFrame[colnames[1 + rnd]] = col
+
+
+def _rows_match(cached, index, probes: int = 64) -> bool:
     """The key cache of a DataFrame is only used while its rows are still the ones baking() returned: first, last and a
     seeded sample of rows are decoded from the device table and compared with the index."""
     table, order = cached.table, cached.order
-    n = len(seqs)
+    n = len(index)
     if n == 0:
         return True
     rng = np.random.default_rng(12345)
     rows = np.unique(np.concatenate([[0, n - 1], rng.integers(0, n, size=min(probes, n))]))
     for i in rows.tolist():
-        if table.export_keys(int(order[i]), 1)[0].decode("latin-1") != str(seqs[i]):
+        if table.export_keys(int(order[i]), 1)[0].decode("latin-1") != str(index[i]):
             return False
     return True
 
@@ -360,31 +433,33 @@ def bwtAlign(args, pdDataFrame, workDir, ref_db, libraries: Optional[LibrarySet]
     dev = device or get_device()
     libs = libraries or load_libraries(args, ref_db, dev)
     spike = bool(getattr(args, "spikeIn", False))
-    seqs = pdDataFrame.index.to_numpy()
+    annot_dv = hit_dv = None
+    seqs = None  # the index as Python strings: only where needed (a frame that did not come from baking(), SAM files)
     cached = pdDataFrame.attrs.get("_mirge_b200_keys")
     if cached is not None and getattr(cached.table, "dev", None) is dev and len(cached.order) == len(pdDataFrame) and \
-            not (getattr(args, "bam_out", False) or getattr(args, "tRNA_frag", False)) and _rows_match(cached, seqs):
+            not (getattr(args, "bam_out", False) or getattr(args, "tRNA_frag", False)) and _rows_match(cached, pdDataFrame.index):
         # the DataFrame comes straight from baking(): its packed keys are still on the device (row i = key id order[i])
         table, order = cached.table, cached.order
         keys = KeySet.from_table(table)
         annot_all, hit_all = annotate_keys(dev, libs, keys, spike)
         sel = torch.from_numpy(np.ascontiguousarray(order)).to(dev.tdev)
-        annot = annot_all[sel].cpu().numpy()
-        hit = hit_all[sel].cpu().numpy()
+        annot_dv, hit_dv = annot_all[sel], hit_all[sel]
+        annot = annot_dv.cpu().numpy()
+        hit = hit_dv.cpu().numpy()
     else:
+        seqs = pdDataFrame.index.to_numpy()
         keys = KeySet.from_strings(dev, list(seqs))
         annot_d, hit_d = annotate_keys(dev, libs, keys, spike)
         annot = annot_d.cpu().numpy()
         hit = hit_d.cpu().numpy()
-    _, _mm, ref, _off = decode_hits(annot, hit)
+    ref = ((hit.view(np.uint64) >> np.uint64(28)) & np.uint64(0xFFFFFFF)).astype(np.int64)  # decode_hits()[2]
     colnames = list(pdDataFrame.columns)
-    for rnd in range(10 if spike else 9):
-        rows = np.nonzero(annot == rnd)[0]
-        if rows.size == 0:
-            continue
-        names = np.asarray(libs[ROUND_LIBS[rnd]].names, dtype=object)
-        ci = 1 + rnd
-        pdDataFrame[colnames[ci]] = _filled_column(pdDataFrame[colnames[ci]], rows, names, ref[rows])
+    n_rounds = 10 if spike else 9
+    on_device = False
+    if annot_dv is not None:
+        on_device = _fill_rounds_device(pdDataFrame, dev, annot_dv, (hit_dv >> 28) & 0xFFFFFFF, libs, n_rounds)
+    if not on_device:
+        _fill_rounds(pdDataFrame, annot, ref, libs, n_rounds, int(getattr(args, "threads", 0) or 0))
     flag = pdDataFrame[colnames[0]].to_numpy(copy=True)
     flag[annot != 0xFF] = 1
     pdDataFrame[colnames[0]] = flag
@@ -394,6 +469,8 @@ def bwtAlign(args, pdDataFrame, workDir, ref_db, libraries: Optional[LibrarySet]
     want_bam, want_trf = bool(getattr(args, "bam_out", False)), bool(getattr(args, "tRNA_frag", False))
     if want_bam or want_trf:
         pols = round_policies()
+        if seqs is None:
+            seqs = pdDataFrame.index.to_numpy()
         for rnd in range(10 if spike else 9):
             fname = (_SAM_BAM.get(rnd) if want_bam else None) or (_SAM_TRF.get(rnd) if want_trf else None)
             if fname is None:

@@ -70,6 +70,19 @@ def check_entry_points(rank, world, dev, umi):
     return ok
 
 
+def exchange_unique(dev, eng, shard, local, world, umi, n_expected):
+    """per-batch exchange of unique sequences on the worker thread / side stream behind the next batch's trim (two local
+    tables, distributed.ExchangeWorker)"""
+    local_t = D.CollapseTable(dev, min_keys=1 << 12)
+    local_b = D.CollapseTable(dev, min_keys=1 << 12)
+    nb = torch.tensor([D.DigestEngine.max_batches(shard.numel(), 3 << 20)], device=dev.tdev)
+    dist.all_reduce(nb, op=dist.ReduceOp.MAX)
+    worker = MD.ExchangeWorker(local, world, owner_min_keys=1 << 12, umi=umi)
+    n = eng.digest_device_exchange(shard, (local_t, local_b), worker, batch_bytes=3 << 20, n_batches=int(nb.item()))
+    assert n == n_expected
+    return worker.finish()
+
+
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -80,8 +93,10 @@ def main():
         dist.broadcast(flag, 0)
         dist.destroy_process_group()
         sys.exit(0 if int(flag.item()) == 1 else 1)
+    mode = sys.argv[2] if len(sys.argv) > 2 else "unique"  # unique | sharded | sharded_sync
+    sharded = mode.startswith("sharded")
     cfg_id = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-    n_reads = 120_000
+    n_reads = 60_000 if sharded else 120_000
     libs = synth.make_libraries(scale=0.05, mrna_count=100)
     lset = LB.LibrarySet.from_fasta_dict(dev, libs.fasta_dict())
     cfg = synth.trim_config_for(cfg_id)
@@ -94,15 +109,19 @@ def main():
     b0 = 0 if lo == 0 else int(nl[4 * lo - 1]) + 1
     b1 = int(nl[4 * hi - 1]) + 1
     shard = torch.from_numpy(fq[b0:b1].copy()).to(dev.tdev)
-    # per-batch exchange on the worker thread / side stream behind the next batch's trim (two local tables)
-    local_t = D.CollapseTable(dev, min_keys=1 << 12)
-    local_b = D.CollapseTable(dev, min_keys=1 << 12)
-    nb = torch.tensor([D.DigestEngine.max_batches(shard.numel(), 3 << 20)], device=dev.tdev)
-    dist.all_reduce(nb, op=dist.ReduceOp.MAX)
-    worker = MD.ExchangeWorker(local, world, owner_min_keys=1 << 12, umi=umi)
-    n = eng.digest_device_exchange(shard, (local_t, local_b), worker, batch_bytes=3 << 20, n_batches=int(nb.item()))
-    assert n == hi - lo
-    owner_t = worker.finish()
+    if sharded:
+        # sharding before the collapse: unequal shards (rank 0 has more batches than the others), small batches
+        cut = [0] + [int(n_reads * (0.55 + 0.45 * r / (world - 1))) for r in range(world - 1)] + [n_reads] if world > 1 else [0, n_reads]
+        lo, hi = cut[rank], cut[rank + 1]
+        b0 = 0 if lo == 0 else int(nl[4 * lo - 1]) + 1
+        shard = torch.from_numpy(fq[b0 : int(nl[4 * hi - 1]) + 1].copy()).to(dev.tdev)
+        owner_t = D.CollapseTable(dev, min_keys=1 << 12)
+        sc = MD.ShardedCollapse(eng, world, overlap=(mode == "sharded"))
+        n = sc.digest_device(shard, owner_t, batch_bytes=2 << 20)
+        assert n == hi - lo, (n, lo, hi)
+        assert sc.rounds >= 2
+    else:
+        owner_t = exchange_unique(dev, eng, shard, local, world, umi, hi - lo)
     ids, cnt = owner_t.drain()
     keys = owner_t.export_keys()
     annot, hit = MA.annotate_keys(dev, lset, MA.KeySet.from_table(owner_t), True)

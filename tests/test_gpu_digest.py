@@ -328,6 +328,76 @@ def test_fused_single_pass_kernel_matches_oracle(dev, case):
         assert table_dict(table) == tab.to_dict(), (case, pad, batch)
 
 
+@pytest.mark.parametrize("world,cfg_id,tight", [(2, 1, False), (3, 2, False), (2, 2, True)])
+def test_sharding_before_collapse_on_one_device_matches_oracle(dev, world, cfg_id, tight):
+    """distributed.ShardedCollapse with ``world`` ranks on ONE device (loop-back instead of the all-to-all): every batch's
+    insert list cut by owner (mirge_shard_scatter), the pieces placed at the end of the owners' arenas in source-rank
+    order, key offsets rebased (mirge_shard_rebase), in-place insert -- everything of that path except NCCL -- against
+    the single-process oracle.  ``tight``: regions far too small on the first try (the exact-size repeat of the scatter).
+    (tests/test_gpu_multi.py runs the same with NCCL on two GPUs.)"""
+    from mirge_b200 import device as D
+    from mirge_b200 import distributed as MD
+    from mirge_b200 import synth
+
+    n_reads = 50_000
+    libs = synth.make_libraries(scale=0.05, mrna_count=100)
+    cfg = synth.trim_config_for(cfg_id)
+    eng = D.DigestEngine(dev, cfg)
+    fq = synth.ReadGenerator(libs, synth.CONFIGS[cfg_id], "cpu").fastq(n_reads).numpy()
+    nl = np.flatnonzero(fq == 10)
+    scs = [MD.ShardedCollapse(eng, world, overlap=False, slack=0.01 if tight else 1.2) for _ in range(world)]
+    owners = [D.CollapseTable(dev, min_keys=1 << 12) for _ in range(world)]
+    # unequal shards: rank 0 has several batches, the last rank a single one
+    cuts = [0] + [int(n_reads * f) for f in ((0.6,) if world == 2 else (0.5, 0.85))] + [n_reads]
+    shards = []
+    for r in range(world):
+        lo, hi = cuts[r], cuts[r + 1]
+        b0 = 0 if lo == 0 else int(nl[4 * lo - 1]) + 1
+        shards.append(torch.from_numpy(fq[b0 : int(nl[4 * hi - 1]) + 1].copy()).to(dev.tdev))
+    pos = [0] * world
+    batch = 2 << 20
+    n_rec = 0
+    while any(pos[r] < shards[r].numel() for r in range(world)):
+        packed, sizes = [], []
+        for r in range(world):
+            br = None
+            if pos[r] < shards[r].numel():
+                end = min(int(shards[r].numel()), pos[r] + batch)
+                final = end == shards[r].numel()
+                br = eng.trim_batch(shards[r][pos[r] : end], end - pos[r], final, keep=False, table=None)
+                pos[r] += br.consumed if not final else end - pos[r]
+                n_rec += br.n_records
+            p = scs[r].pack(br)
+            cur = p["cursors"].cpu().numpy()
+            if tight and br is not None and br.n_items > 5000:
+                assert max(MD.ShardedCollapse.split_cursors(cur)[0]) > p["cap_items"]  # the first try did overflow
+            p = scs[r].settle(p, cur)
+            packed.append(p)
+            sizes.append(MD.ShardedCollapse.split_cursors(p["cursors"].cpu().numpy()))
+        for o in range(world):  # what the two all-to-alls deliver to owner o
+            recv_it = [sizes[s][0][o] for s in range(world)]
+            recv_w = [sizes[s][1][o] for s in range(world)]
+            items, arena, bases = scs[o].place(owners[o], recv_it, recv_w)
+            ai = aw = 0
+            for s in range(world):
+                ci, cw = packed[s]["cap_items"], packed[s]["cap_words"]
+                items[ai : ai + recv_it[s]].copy_(packed[s]["items"][o * ci : o * ci + recv_it[s]])
+                arena[aw : aw + recv_w[s]].copy_(packed[s]["keys"][o * cw : o * cw + recv_w[s]])
+                ai += recv_it[s]
+                aw += recv_w[s]
+            scs[o].insert(owners[o], items, recv_it, bases)
+    assert n_rec == n_reads
+    union = {}
+    for o in owners:
+        d = table_dict(o)
+        assert not (set(d) & set(union)), "a sequence is owned by two ranks"
+        union.update(d)
+    _, tab = coracle.digest_collapse(fq, dev.trim_params, nthreads=8)
+    assert union == tab.to_dict()
+    sizes = [o.n_keys for o in owners]
+    assert min(sizes) > 0.6 * max(sizes), sizes  # the owner hash spreads the sequences evenly
+
+
 @pytest.mark.parametrize("cfg_id", [1, 3])
 def test_exchange_world2_on_one_device_matches_oracle(dev, cfg_id):
     """The multi-GPU exchange with world = 2 on ONE device (two local tables, two owner tables, loop-back transport):

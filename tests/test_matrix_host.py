@@ -108,3 +108,40 @@ def test_large_tables_get_an_arrow_index_without_python_strings():
     b = pd.DataFrame({"x": np.arange(len(keys))}, index=small)
     assert a.to_csv() == b.to_csv() and a.loc[keys[7], "x"] == 7
     assert (a.index.str.len().to_numpy() == np.array([len(k) for k in keys])).all()
+
+
+def test_flag_columns_match_what_assign_gives():
+    """empty_flag_column: the dtype and content of ``df.assign(col='')`` (digest.py:254) without n Python objects."""
+    n = 1000
+    ref = pd.DataFrame({"s": np.arange(n)}).assign(x="")["x"]
+    col = pd.Series(DG.empty_flag_column(n), name="x")
+    assert col.dtype == ref.dtype and col.equals(ref) and bool((col == "").all())
+
+
+def test_device_built_annotation_column_equals_the_host_one():
+    """manifoldAlign._round_column_device (Arrow offsets / data assembled with tensor ops; here on the CPU device)
+    against _filled_column, incl. multi-byte names and a round without hits."""
+    import torch
+
+    from mirge_b200 import manifoldAlign as MA
+
+    class Dev:
+        tdev = torch.device("cpu")
+
+    n = 300_000
+    rng = np.random.default_rng(0)
+    annot = np.full(n, 0xFF, dtype=np.uint8)
+    sel = rng.random(n) < 0.2
+    annot[sel] = rng.integers(0, 3, int(sel.sum()))
+    annot[-1] = 1  # the last row annotated: the running sum ends inside a name
+    ref = rng.integers(0, 500, n)
+    names = ["hsa-miR-%d-5p/é" % i if i % 7 == 0 else "n%d" % i for i in range(500)]
+    old = pd.Series(DG.empty_flag_column(n))
+    for rnd in range(3):
+        got = MA._round_column_device(Dev, torch.from_numpy(annot), torch.from_numpy(ref), rnd, names, old.dtype)
+        rows = np.nonzero(annot == rnd)[0]
+        exp = MA._filled_column(old, rows, np.asarray(names, dtype=object), ref[rows])
+        if old.dtype == object:
+            continue  # (pandas < 3: the device path is not used)
+        assert pd.Series(got).equals(pd.Series(exp))
+    assert MA._round_column_device(Dev, torch.from_numpy(annot), torch.from_numpy(ref), 5, names, old.dtype) is None
