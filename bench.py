@@ -545,6 +545,29 @@ def run_b200(args):
             dist.all_reduce(tme, op=dist.ReduceOp.MAX)
         e2e = {"value": round(reads_per_gpu * world / (float(tme.item()) / 1e3) / 1e6, 3), "unit": UNIT,
                "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": int(d2h), "ms_per_step": round(float(tme.item()), 3)}
+        # what the box gives all N ranks at once: the same pinned input copied to the device with no kernel in the way
+        # (all ranks start together, max over ranks) -- e2e is bounded by max(this, the device-resident pass)
+        try:
+            probe = torch.empty(min(int(hosts[0].numel()), 2 << 30), dtype=torch.uint8, device=dev.tdev)
+            reps = max(1, min(4, int(nbytes // max(probe.numel(), 1))))
+            for timed_pass in (False, True):
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(reps):
+                    probe.copy_(hosts[0][: probe.numel()], non_blocking=True)
+                g1.record()
+                barrier()
+            tp = torch.tensor([g0.elapsed_time(g1)], device=dev.tdev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+            gbs = reps * probe.numel() / (float(tp.item()) / 1e3) / 1e9
+            e2e["h2d_ceiling_gbs_per_gpu"] = round(gbs, 2)
+            e2e["h2d_floor_ms_per_step"] = round(nbytes / gbs / 1e6, 3)
+            e2e["frac_of_h2d_ceiling"] = round(e2e["h2d_floor_ms_per_step"] / e2e["ms_per_step"], 3)
+            del probe
+        except RuntimeError as exc:
+            sys.stderr.write("bench: H2D ceiling probe skipped: %s\n" % exc)
         del hosts, streamer
 
     # ---- the reference's own entry points on one sample: baking(args, [file]) + bwtAlign(args, df)  (rank 0, N = 1)

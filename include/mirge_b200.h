@@ -73,6 +73,8 @@ extern "C" {
 #define MIRGE_COUNT_HEAD 0    /* count after every modifier, as digest.py:354-373 is written */
 #define MIRGE_COUNT_RELEASE 1 /* count once after the pipeline (released 0.1.x behaviour)   */
 
+#define MIRGE_LINK_BACK_HALF 0x100
+
 /* One adapter in cutadapt's Aligner terms (restated in oracle/pyoracle.py::locate). */
 typedef struct mirge_adapter {
   int32_t where;        /* 0 = back (3', -a), 1 = front (5', -g) */
@@ -82,7 +84,9 @@ typedef struct mirge_adapter {
   int32_t wildcard_ref; /* adapter contains IUPAC wildcards and -N was not given */
   int32_t k;            /* int(error_rate * m) */
   int32_t effective_length;
-  int32_t reserved;
+  int32_t link;         /* 0 = plain adapter; 1 + index of the 3' half = the 5' half of a linked pair (-g "A...B": both
+                         * halves non-anchored and required, cutadapt parser/LinkedAdapter); MIRGE_LINK_BACK_HALF = the 3'
+                         * half of a pair, never searched on its own */
   uint8_t mask[MIRGE_MAX_ADAPTER_LEN];  /* 4-bit IUPAC set per adapter base (A=1,C=2,G=4,T=8) */
   uint8_t ascii[MIRGE_MAX_ADAPTER_LEN]; /* upper-cased adapter text */
   int32_t n_counts[MIRGE_MAX_ADAPTER_LEN + 1]; /* number of 'N' before position i */

@@ -16,6 +16,7 @@ LIB_PAD_WORDS = 40  # MIRGE_LIB_PAD_WORDS
 MOD_NEXTSEQ, MOD_QUALITY, MOD_ADAPTER, MOD_NEND, MOD_CUT = 1, 2, 3, 4, 5
 UMI_NONE, UMI_FLANKS, UMI_QIAGEN = 0, 1, 2
 COMPAT_CUTADAPT23, COMPAT_CUTADAPT4 = 0, 1
+LINK_BACK_HALF = 0x100  # MIRGE_LINK_BACK_HALF
 COUNT_HEAD, COUNT_RELEASE = 0, 1
 SELECT_LEN_LT26, SELECT_LEN_GT25, SELECT_UNANNOTATED = 0, 1, 2
 
@@ -33,7 +34,7 @@ class Adapter(C.Structure):
         ("wildcard_ref", C.c_int32),
         ("k", C.c_int32),
         ("effective_length", C.c_int32),
-        ("reserved", C.c_int32),
+        ("link", C.c_int32),
         ("mask", C.c_uint8 * MAX_ADAPTER_LEN),
         ("ascii", C.c_uint8 * MAX_ADAPTER_LEN),
         ("n_counts", C.c_int32 * (MAX_ADAPTER_LEN + 1)),

@@ -14,7 +14,8 @@
 #define OB 64  // origin bias inside the packed (origin, matches) word
 
 struct DevAdapter {
-  int where, m, min_overlap, indel_cost, wildcard_ref, k, effective_length, pad;
+  int where, m, min_overlap, indel_cost, wildcard_ref, k, effective_length;
+  int link;  // mirge_adapter.link: 0 plain, 1 + index of the 3' half (5' half of a linked pair), MIRGE_LINK_BACK_HALF
   uint64_t peq[5];  // bit i-1 set <=> adapter row i matches read class c (A,C,G,T,other)
   int n_counts[MIRGE_MAX_ADAPTER_LEN + 1];
   int max_err[MIRGE_MAX_ADAPTER_LEN + 1];
@@ -80,6 +81,14 @@ static int fill_dev_params(const mirge_trim_params *p, DevParams &d, int &maxm, 
     DevAdapter *o = &d.ad[a];
     o->where = s->where; o->m = s->m; o->min_overlap = s->min_overlap; o->indel_cost = s->indel_cost;
     o->wildcard_ref = s->wildcard_ref; o->k = s->k; o->effective_length = s->effective_length;
+    o->link = s->link;
+    if (s->link != 0 && s->link != MIRGE_LINK_BACK_HALF) {
+      const int b = s->link - 1;
+      if (s->where != 1 || b <= a || b >= p->n_adapters || p->adapters[b].where != 0 || p->adapters[b].link != MIRGE_LINK_BACK_HALF)
+        FILL_FAIL("adapter %d: a linked pair is a 5' adapter followed by its 3' half", a);
+      if (p->umi_mode == MIRGE_UMI_QIAGEN) FILL_FAIL("linked adapters are not supported with qiagen UMIs");
+    }
+    if (s->link != 0) fast_ok = 0;  // linked pairs run on the full-DP kernel
     for (int c = 0; c < 4; ++c) {
       uint64_t bits = 0;
       for (int i = 0; i < s->m; ++i)

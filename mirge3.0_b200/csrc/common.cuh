@@ -138,8 +138,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
+#ifndef MBAR_SLEEP
+#define MBAR_SLEEP 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {}
+  while (!mbar_try_wait(bar, parity)) {
+    if (MBAR_SLEEP) __nanosleep(MBAR_SLEEP);  // a waiting warp leaves the issue slots to the warps that work
+  }
 }
 // global -> shared bulk copy of `bytes` (multiple of 16; both addresses 16-byte aligned), completion counted on `bar`
 __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {

@@ -57,10 +57,23 @@ __device__ __noinline__ int best_match(const uint8_t *read, int n, Match &best, 
   int which = -1;
   for (int a = 0; a < c_p.n_adapters; ++a) {
     Match mt;
+    const int link = c_p.ad[a].link;
+    if (link == MIRGE_LINK_BACK_HALF) continue;  // searched through its 5' half only
     if (FAST) {
       const int rc = locate_fast<DEFER>(a, ByteRead{read}, n, fc, mt);
       if (rc == 2) return -2;
       if (rc == 0) continue;
+    } else if (link != 0) {
+      // cutadapt LinkedAdapter.match_to for -g "A...B": the 5' half must match; the 3' half is searched in what the
+      // 5' match leaves and must match too; matches and errors of the pair are the sums.  The Match of a pair carries
+      // the two cut points: rstart = first base kept, rstop = end of what is kept (both relative to `read`).
+      Match f, b;
+      if (!locate<MAXM>(a, read, n, f)) continue;
+      if (!locate<MAXM>(link - 1, read + f.rstop, n - f.rstop, b)) continue;
+      mt.rstart = f.rstop;
+      mt.rstop = f.rstop + b.rstart;
+      mt.matches = f.matches + b.matches;
+      mt.errors = f.errors + b.errors;
     } else if (!locate<MAXM>(a, read, n, mt)) continue;
     if (which < 0 || mt.matches > best.matches || (mt.matches == best.matches && mt.errors < best.errors)) {
       best = mt;
@@ -92,7 +105,8 @@ __device__ __noinline__ bool apply_mod(int mi, const uint8_t *seq, const uint8_t
         const int a = best_match<MAXM, FAST, DEFER>(seq + start, stop - start, mt, fc);
         if (a == -2) return true;
         if (a < 0) break;
-        if (c_p.ad[a].where == 0) stop = start + mt.rstart;
+        if (c_p.ad[a].link != 0) { stop = start + mt.rstop; start = start + mt.rstart; }  // a linked pair cuts both ends
+        else if (c_p.ad[a].where == 0) stop = start + mt.rstart;
         else start = start + mt.rstop;
       }
       break;
@@ -752,12 +766,18 @@ trim_kernel(const uint8_t *__restrict__ fq, uint64_t nbytes, const uint32_t *__r
 // that stage 1 hands on anyway: non-ACGT characters, long reads) goes to the whole-pipeline pass with its line
 // starts.  Buffers cycle through full (bulk copy done) -> ready (scanned) -> empty (all consumer warps done)
 // mbarriers; nothing in the loop is a CTA-wide barrier.
+#ifndef DT_TILE
 #define DT_TILE 16384
+#endif
 #define DT_OVH 2048
 #define DT_LOAD (DT_TILE + DT_OVH)
 #define DT_WORDS (DT_LOAD / 32)
+#ifndef DT_NBUF
 #define DT_NBUF 2
-#define DT_GROUPS 2
+#endif
+#ifndef DT_GROUPS
+#define DT_GROUPS 1
+#endif
 #define DT_CWARPS (DT_GROUPS * TRIM_THREADS / 32)
 #define DT_THREADS (32 + DT_GROUPS * TRIM_THREADS)
 #define DT_FLAG_AGG (1ull << 62)

@@ -41,17 +41,31 @@ def parse_cutoffs(s) -> List[int]:
 
 @dataclass
 class AdapterSpec:
-    where: str  # "back" | "front"
+    where: str  # "back" | "front" | "linked" (sequence = the 5' half, sequence2 = the 3' half)
     sequence: str
+    sequence2: str = ""
 
 
 def parse_adapter_spec(kind: str, spec: str) -> AdapterSpec:
     """The subset of cutadapt's adapter specification language reachable from miRge's ``-a``/``-g``
-    (parse.py:74-77) that this path implements: a plain (non-anchored, non-linked) 3' or 5' adapter,
-    optionally ``name=SEQ``.  Everything else raises instead of silently diverging."""
+    (parse.py:74-77) that this path implements: a plain (non-anchored) 3' or 5' adapter, optionally ``name=SEQ``,
+    and the linked form the reference documents, ``-g "ADAPTER5...ADAPTER3"`` (docs/source/quick_start.md:208-220;
+    cutadapt: both halves non-anchored, both required).  ``-a "A...B"`` anchors its 5' half and is, like everything else,
+    rejected instead of silently diverging."""
     if kind not in ("back", "front"):
         raise UnsupportedAdapterSpec("adapter type %r is not supported" % (kind,))
     s = spec.strip()
+    if "..." in s and kind == "front":
+        body = s.split("=", 1)[1] if "=" in s else s
+        halves = body.split("...")
+        if len(halves) != 2 or not halves[0] or not halves[1]:
+            raise UnsupportedAdapterSpec("linked adapter specification %r: expected ADAPTER5...ADAPTER3" % spec)
+        if any(x.lower() == "illumina" for x in halves):
+            # quick_start.md:219-221: the alias is not decoded inside a linked specification (cutadapt would take the
+            # letters as bases)
+            raise UnsupportedAdapterSpec("linked adapter specification %r: give the complete adapter sequences" % spec)
+        five, three = (parse_adapter_spec("front", halves[0]), parse_adapter_spec("back", halves[1]))
+        return AdapterSpec("linked", five.sequence, three.sequence)
     if s.lower() == "illumina":
         s = ILLUMINA_BACK if kind == "back" else ILLUMINA_FRONT
     if "=" in s:
@@ -136,8 +150,9 @@ def build_adapter(spec: AdapterSpec, cfg: TrimConfig) -> abi.Adapter:
     if not wildcard_ref and not set(seq) <= set("ACGT"):
         raise UnsupportedAdapterSpec("IUPAC adapter characters with -N (no adapter wildcards) are not supported")
     a.where = 0 if spec.where == "back" else 1
+    a.link = 0
     a.m = m
-    a.min_overlap = int(cfg.overlap)
+    a.min_overlap = min(int(cfg.overlap), m)  # cutadapt adapters.py: min_overlap = min(min_overlap, len(sequence))
     a.indel_cost = 1 if cfg.indels else 100000
     a.wildcard_ref = 1 if wildcard_ref else 0
     a.k = int(cfg.error_rate * m)
@@ -164,7 +179,18 @@ def build_trim_params(cfg: TrimConfig) -> abi.TrimParams:
     if cfg.match_read_wildcards:
         raise RuntimeError("--match-read-wildcards is not supported")
     p = abi.TrimParams()
-    specs = [parse_adapter_spec(k, s) for (k, s) in cfg.adapters]
+    specs = []
+    links = []  # per flattened adapter: mirge_adapter.link
+    for (k, s) in cfg.adapters:
+        sp = parse_adapter_spec(k, s)
+        if sp.where == "linked":  # two consecutive entries: the 5' half points at the 3' half
+            specs += [AdapterSpec("front", sp.sequence), AdapterSpec("back", sp.sequence2)]
+            links += [len(specs), abi.LINK_BACK_HALF]  # (1 + index of the 3' half) = len(specs) after both were appended
+        else:
+            specs.append(sp)
+            links.append(0)
+    if any(links) and cfg.qiagenumi:
+        raise UnsupportedAdapterSpec("linked adapters together with --qiagenumi are not supported")
     if len(specs) > abi.MAX_ADAPTERS:
         raise RuntimeError("at most %d adapters are supported" % abi.MAX_ADAPTERS)
     mods = []
@@ -194,6 +220,7 @@ def build_trim_params(cfg: TrimConfig) -> abi.TrimParams:
     p.n_adapters = len(specs)
     for i, s in enumerate(specs):
         p.adapters[i] = build_adapter(s, cfg)
+        p.adapters[i].link = links[i]
     p.times = int(cfg.times)
     p.min_len = int(cfg.minimum_length)
     umi = cfg.umi()

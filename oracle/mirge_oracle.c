@@ -162,7 +162,17 @@ static int best_match(const mirge_trim_params *p, const uint8_t *read, int n, ma
   int have = 0, which = -1;
   for (int a = 0; a < p->n_adapters; ++a) {
     match_t mt;
-    if (!match_to(&p->adapters[a], read, n, &mt, p->compat)) continue;
+    int link = p->adapters[a].link;
+    if (link == MIRGE_LINK_BACK_HALF) continue;
+    if (link != 0) {
+      /* cutadapt LinkedAdapter.match_to, -g "A...B": both halves required; the 3' half is searched in read[front.rstop:].
+       * The match of a pair: rstart = first base kept, rstop = end of what is kept, matches / errors = sums. */
+      match_t f, b;
+      if (!match_to(&p->adapters[a], read, n, &f, p->compat)) continue;
+      if (!match_to(&p->adapters[link - 1], read + f.rstop, n - f.rstop, &b, p->compat)) continue;
+      mt = f;
+      mt.rstart = f.rstop; mt.rstop = f.rstop + b.rstart; mt.matches = f.matches + b.matches; mt.errors = f.errors + b.errors;
+    } else if (!match_to(&p->adapters[a], read, n, &mt, p->compat)) continue;
     if (!have || mt.matches > best->matches || (mt.matches == best->matches && mt.errors < best->errors)) { *best = mt; have = 1; which = a; }
   }
   return which;
@@ -183,7 +193,8 @@ static void apply_mod(const mirge_trim_params *p, int mi, const uint8_t *seq, co
       for (int t = 0; t < p->times; ++t) {
         match_t mt; int a = best_match(p, seq + start, stop - start, &mt);
         if (a < 0) break;
-        if (p->adapters[a].where == 0) stop = start + mt.rstart; else start = start + mt.rstop;
+        if (p->adapters[a].link != 0) { stop = start + mt.rstop; start = start + mt.rstart; }
+        else if (p->adapters[a].where == 0) stop = start + mt.rstart; else start = start + mt.rstop;
       }
       break;
     case MIRGE_MOD_NEND:

@@ -183,6 +183,7 @@ class Adapter:
         if not self.wildcard_ref and not set(self.sequence) <= set("ACGT"):
             raise ValueError("non-ACGT adapter characters need adapter wildcards (unsupported combination)")
         m = len(self.sequence)
+        self.min_overlap = min(int(self.min_overlap), m)  # cutadapt adapters.py: an adapter shorter than -O lowers it
         self.n_counts = [0] * (m + 1)
         c = 0
         for i, ch in enumerate(self.sequence):
@@ -362,6 +363,8 @@ def match_to(ad: Adapter, read: str, compat: str = "2-3") -> Optional[Tuple[int,
     the adapter has no wildcards), otherwise ``Aligner.locate``.  The fast path returns what the
     DP would (leftmost exact occurrence: the DP stops at the first column with cost 0, matches m).
     """
+    if isinstance(ad, LinkedAdapter):
+        return match_linked(ad, read, compat)
     up = read.upper()
     if not ad.wildcard_ref:
         pos = up.find(ad.sequence)
@@ -369,6 +372,23 @@ def match_to(ad: Adapter, read: str, compat: str = "2-3") -> Optional[Tuple[int,
             m = len(ad.sequence)
             return (0, m, pos, pos + m, m, 0)  # (m matches; also the score of m matches)
     return locate(ad, read, compat)
+
+
+def match_linked(ad: LinkedAdapter, read: str, compat: str = "2-3") -> Optional[Tuple[int, int, int, int, int, int]]:
+    """cutadapt ``LinkedAdapter.match_to``: the 5' adapter on the read, the 3' adapter on what the 5' match leaves
+    (``read[front.rstop:]``); a missing half ends the search when that half is required (and a pair needs at least its
+    5' half).  ``LinkedMatch``: matches and errors are the sums over the halves that matched.  Returned in the shape of
+    the other matches, with the two cut points in the read fields: (0, 0, first base kept, end of what is kept,
+    matches, errors)."""
+    f = match_to(ad.front, read, compat)
+    if f is None and ad.front_required:
+        return None
+    rest = f[3] if f is not None else 0
+    b = match_to(ad.back, read[rest:], compat)
+    if b is None and (ad.back_required or f is None):
+        return None
+    keep_stop = rest + b[2] if b is not None else len(read)
+    return (0, 0, rest, keep_stop, (f[4] if f else 0) + (b[4] if b else 0), (f[5] if f else 0) + (b[5] if b else 0))
 
 
 def best_match(adapters: Sequence[Adapter], read: str, compat: str = "2-3"):
@@ -457,7 +477,9 @@ def apply_modifier(mod, seq: str, qual: str, start: int, stop: int, p: TrimParam
             ad, mt = best_match(p.adapters, seq[start:stop], p.compat)
             if mt is None:
                 break
-            if ad.where == "back":
+            if ad.where == "linked":
+                start, stop = start + mt[2], start + mt[3]  # LinkedMatch.trimmed(): both ends cut
+            elif ad.where == "back":
                 stop = start + mt[2]  # read[:rstart]
             else:
                 start = start + mt[3]  # read[rstop:]

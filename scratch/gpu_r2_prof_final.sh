@@ -18,3 +18,10 @@ d = json.loads([l for l in open("gpurun_out/ncu_$TAG.log") if l.startswith("{")]
 print("reads", d["config"]["reads_per_gpu"], "unique", d["config"]["unique_sequences"])
 open("gpurun_out/prof_${TAG}_counts.json", "w").write(json.dumps({"reads": d["config"]["reads_per_gpu"], "unique": d["config"]["unique_sequences"]}))
 PY
+# the bulk-copy fed fused kernel (opt-in): one capture of it on the same reduced run
+MIRGE_B200_FUSED=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'digest_tiles' -c 2 -f -o gpurun_out/prof_${TAG}_fused \
+  python bench.py --reads 2500000 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline > gpurun_out/ncu_${TAG}_fused.log 2>&1
+python profiles/ncu_summary.py gpurun_out/prof_${TAG}_fused.ncu-rep > gpurun_out/prof_${TAG}_fused_summary.txt 2>&1
+python profiles/ncu_lines_id.py gpurun_out/prof_${TAG}_fused.ncu-rep 0 40 >> gpurun_out/prof_${TAG}_fused_summary.txt 2>&1
+python profiles/ncu_lines_id.py gpurun_out/prof_${TAG}_fused.ncu-rep 0 30 inst >> gpurun_out/prof_${TAG}_fused_summary.txt 2>&1
+tail -5 gpurun_out/prof_${TAG}_fused_summary.txt

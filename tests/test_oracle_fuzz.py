@@ -57,6 +57,9 @@ def random_config(rng):
     cut = []
     if rng.random() < 0.3:
         cut = [int(rng.integers(1, 5))] if rng.random() < 0.5 else [int(rng.integers(1, 5)), -int(rng.integers(1, 5))]
+    backs = [k for k, (w, _) in enumerate(adapters) if w == "back"]
+    if backs and rng.random() < 0.2:  # a linked pair -g "A...B": a random 5' half in front of one of the 3' adapters
+        adapters[backs[0]] = ("front", rnd_seq(rng, int(rng.integers(5, 14))) + "..." + adapters[backs[0]][1])
     return P.TrimConfig(adapters=adapters, error_rate=float(rng.choice([0.0, 0.05, 0.1, 0.12, 0.2, 0.34])),
                         overlap=int(rng.integers(1, 8)), indels=bool(rng.random() < 0.8), times=int(rng.integers(1, 3)),
                         nextseq_trim=int(rng.integers(10, 31)) if rng.random() < 0.3 else None, quality_cutoff=q,
@@ -71,7 +74,13 @@ def random_reads(rng, cfg, n):
         L = int(rng.integers(1, 101)) if rng.random() < 0.9 else int(rng.integers(101, 160))
         ins = rnd_seq(rng, int(rng.integers(0, 45)))
         s = ins
+        flat = []
         for where, ad in cfg.adapters:
+            if "..." in ad:
+                flat += [("front", ad.split("...")[0]), ("back", ad.split("...")[1])]
+            else:
+                flat.append((where, ad))
+        for where, ad in flat:
             plain = "".join(c if c in "ACGT" else str(rng.choice(B)) for c in ad)
             r = rng.random()
             if r < 0.55:

@@ -28,6 +28,23 @@ def test_adapter_specification_subset():
             P.parse_adapter_spec(kind, spec)
 
 
+def test_linked_adapter_specification():
+    """-g "ADAPTER5...ADAPTER3" (docs/source/quick_start.md:208-220): a 5' half pointing at its 3' half in the flat adapter
+    list; the forms that anchor a half, and the alias inside a linked specification, stay rejected."""
+    sp = P.parse_adapter_spec("front", "TTAGGC...TGGAATTCTCGGGTGCCAAGGAACTCCAGT")
+    assert (sp.where, sp.sequence, sp.sequence2) == ("linked", "TTAGGC", "TGGAATTCTCGGGTGCCAAGGAACTCCAGT")
+    p = P.build_trim_params(P.TrimConfig(adapters=[("back", "ACGTACGTAC"), ("front", "name=TTAGGC...ACGTTGCA")]))
+    assert p.n_adapters == 3
+    assert [p.adapters[i].where for i in range(3)] == [0, 1, 0]
+    assert [p.adapters[i].link for i in range(3)] == [0, 3, abi.LINK_BACK_HALF]
+    for kind, spec in (("front", "TTAGGC...illumina"), ("front", "^TTAGGC...ACGT"), ("front", "TTAGGC...ACGT$"), ("front", "A...C...G"),
+                       ("front", "...ACGT"), ("back", "TTAGGC...ACGT")):
+        with pytest.raises(P.UnsupportedAdapterSpec):
+            P.parse_adapter_spec(kind, spec)
+    with pytest.raises(P.UnsupportedAdapterSpec):
+        P.build_trim_params(P.TrimConfig(adapters=[("front", "TTAGGC...AACTGTAGGCACCATCAAT")], qiagenumi=True, uniq_mol_ids="0,12"))
+
+
 def test_parse_cutoffs_doctests():  # digest.py:19-35
     assert P.parse_cutoffs("5") == [0, 5] or tuple(P.parse_cutoffs("5")) == (0, 5)
     assert tuple(P.parse_cutoffs("6,7")) == (6, 7)

@@ -16,8 +16,11 @@ def py_params(cfg: P.TrimConfig) -> po.TrimParams:
     ads = []
     for k, s in cfg.adapters:
         sp = P.parse_adapter_spec(k, s)
-        ads.append(po.Adapter(sp.where, sp.sequence, cfg.error_rate, cfg.overlap, cfg.indels,
-                              cfg.match_adapter_wildcards))
+        mk = lambda where, seq: po.Adapter(where, seq, cfg.error_rate, cfg.overlap, cfg.indels, cfg.match_adapter_wildcards)
+        if sp.where == "linked":  # -g "A...B": both halves required (cutadapt parser)
+            ads.append(po.LinkedAdapter(mk("front", sp.sequence), mk("back", sp.sequence2), True, True))
+            continue
+        ads.append(mk(sp.where, sp.sequence))
     return po.TrimParams(adapters=ads, times=cfg.times, nextseq_trim=cfg.nextseq_trim,
                          quality_cutoff=cfg.quality_cutoff, quality_base=cfg.quality_base, trim_n=cfg.trim_n,
                          cut=list(cfg.cut), minimum_length=cfg.minimum_length, umi=cfg.umi(),
@@ -90,6 +93,10 @@ CONFIGS = {
     "long_adapter": P.TrimConfig(adapters=[("back", LONG_AD)]),
     "reads150": P.TrimConfig(adapters=[("back", ILL)], nextseq_trim=20, quality_cutoff="20", trim_n=True, cut=[1]),
     "reads200": P.TrimConfig(adapters=[("back", ILL)], quality_cutoff="20"),
+    # linked adapters -g "A...B" (quick_start.md:208-220): both halves required, 3' half searched behind the 5' match
+    "linked": P.TrimConfig(adapters=[("front", "TTAGGC...TGGAATTCTCGGGTGCCAAGGAACTCCAGT")]),
+    "linked_x2": P.TrimConfig(adapters=[("front", "CAGTCCGACGATC..." + ILL), ("back", "AAAAAAAAAA")], times=2, indels=False,
+                              uniq_mol_ids="2,2"),
     # cutadapt >= 4 objective (score instead of matches): full-DP kernel
     "compat4": P.TrimConfig(adapters=[("back", ILL)], cutadapt_compat="4"),
     "compat4_fb": P.TrimConfig(adapters=[("back", ILL), ("front", "GTTCAGAGTTCTACAGTCCGACGATC")], cutadapt_compat="4", times=2),
@@ -106,6 +113,8 @@ CONFIG_DATA = {
     "noq_m1": dict(varlen=True),
     "reads150": dict(L=150),  # still inside the packed-read fast path (PACK_WORDS * 16 = 160 bases)
     "reads200": dict(L=200),  # beyond it: whole-pipeline kernel per read
+    "linked": dict(front="TTAGGC", err=0.05),
+    "linked_x2": dict(front="CAGTCCGACGATC", L=70),
     "compat4": dict(err=0.06, indel=0.04),
     "compat4_fb": dict(front="CAGTCCGACGATC", err=0.06, indel=0.04),
 }
