@@ -234,10 +234,19 @@ class CollapseTable:
         (numpy's order for 'S' arrays; only ids with seen[id] when given) and the texts back to back in that order.
         Sorting (LSD radix over big-endian 8-byte chunks of the zero-padded rows), selection and compaction run on
         the device: argsort and slicing of tens of millions of strings on the host take minutes."""
+        if self.n_keys <= 0:
+            return np.zeros(0, dtype=np.int64), np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.uint8)
+        keep = None if seen is None else torch.from_numpy(np.ascontiguousarray(seen.astype(bool))).to(self.dev.tdev)
+        perm, offsets, data = self.export_sorted_device(keep)
+        return perm.cpu().numpy(), offsets.cpu().numpy(), data.cpu().numpy()
+
+    def export_sorted_device(self, keep: Optional[torch.Tensor] = None):
+        """export_sorted with the three results left on the device (``keep``: bool tensor over the key ids)."""
         d = self.dev
         n = self.n_keys
         if n <= 0:
-            return np.zeros(0, dtype=np.int64), np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.uint8)
+            z = torch.zeros(0, dtype=torch.int64, device=d.tdev)
+            return z, torch.zeros(1, dtype=torch.int64, device=d.tdev), torch.zeros(0, dtype=torch.uint8, device=d.tdev)
         asc, stride, lens = self._export_device(0, n)
         rows = asc.view(n, stride)
         if int((asc >= 128).any().item()):
@@ -250,8 +259,7 @@ class CollapseTable:
             for c in range(stride // 8 - 1, -1, -1):
                 perm = perm[torch.sort(chunks[perm, c], stable=True).indices]
             del chunks
-        if seen is not None:
-            keep = torch.from_numpy(np.ascontiguousarray(seen.astype(bool))).to(d.tdev)
+        if keep is not None:
             perm = perm[keep[perm]]
         lens_s = lens[perm].to(torch.int64)
         srt = rows[perm]
@@ -259,7 +267,7 @@ class CollapseTable:
         data = srt[inside]
         offsets = torch.zeros(perm.numel() + 1, dtype=torch.int64, device=d.tdev)
         torch.cumsum(lens_s, 0, out=offsets[1:])
-        return perm.cpu().numpy(), offsets.cpu().numpy(), data.cpu().numpy()
+        return perm, offsets, data
 
 
 @dataclass

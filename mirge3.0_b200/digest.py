@@ -199,7 +199,33 @@ def umi_collapse(dev: Device, first: CollapseTable, ids: torch.Tensor, cnt: torc
 
 
 class SampleResult:
-    __slots__ = ("count", "trimmed", "unique", "ids", "counts", "rlen", "hist")
+    """One sample's column of the matrix: (key id, count) pairs.  They stay on the device (``ids_d`` / ``counts_d``); the
+    numpy views ``ids`` / ``counts`` are materialised on first use (the -tcf writer, the multi-GPU gather, tests)."""
+
+    __slots__ = ("count", "trimmed", "unique", "_ids", "_counts", "ids_d", "counts_d", "rlen", "hist")
+
+    def __init__(self):
+        self._ids = self._counts = self.ids_d = self.counts_d = None
+
+    @property
+    def ids(self):
+        if self._ids is None and self.ids_d is not None:
+            self._ids = self.ids_d.cpu().numpy().astype(np.int64)
+        return self._ids
+
+    @ids.setter
+    def ids(self, v):
+        self._ids = v
+
+    @property
+    def counts(self):
+        if self._counts is None and self.counts_d is not None:
+            self._counts = self.counts_d.cpu().numpy().astype(np.int64)
+        return self._counts
+
+    @counts.setter
+    def counts(self, v):
+        self._counts = v
 
 
 def digest_sample(eng: DigestEngine, source, table: CollapseTable, first_level: Optional[CollapseTable], umi_dedup: bool,
@@ -228,10 +254,9 @@ def digest_sample(eng: DigestEngine, source, table: CollapseTable, first_level: 
             _write_umi_csv(umi_csv, first_level, ids1.cpu().numpy(), res.hist, umi, cfg.minimum_length)
         first_level.reset()
     ids, cnt = table.drain()
-    res.ids = ids.cpu().numpy().astype(np.int64)
-    res.counts = cnt.cpu().numpy().astype(np.int64)
-    res.trimmed = int(res.counts.sum())  # digest.py:160-163 / 178-181 / 199-202
-    res.unique = int(res.ids.size)  # len(completeDict), digest.py:212
+    res.ids_d, res.counts_d = ids, cnt
+    res.trimmed = int(cnt.sum(dtype=torch.int64).item())  # digest.py:160-163 / 178-181 / 199-202
+    res.unique = int(ids.numel())  # len(completeDict), digest.py:212
     return res
 
 
@@ -257,8 +282,13 @@ class DeviceKeys:
     """What build_matrix leaves in DataFrame.attrs for bwtAlign: the table whose arena holds the packed keys and the
     key id of every row.  Not data: pickling the DataFrame (-spl / -rr, __main__.py:101,145) drops it."""
 
-    def __init__(self, table, order, lens=None):
-        self.table, self.order, self.lens = table, order, lens
+    def __init__(self, table, order, offsets=None, order_d=None):
+        self.table, self.order, self.offsets, self.order_d = table, order, offsets, order_d
+
+    @property
+    def lens(self):
+        """text length of every row (from the export's offsets; only the read-length histogram asks)"""
+        return None if self.offsets is None else np.diff(self.offsets)
 
     def __reduce__(self):
         return (_no_keys, ())
@@ -274,6 +304,7 @@ class DeviceKeys:
 
 
 ARROW_INDEX_MIN = int(os.environ.get("MIRGE_B200_ARROW_INDEX_MIN", str(2_000_000)))
+MATRIX_DEVICE_BYTES = int(os.environ.get("MIRGE_B200_MATRIX_DEVICE_BYTES", str(16 << 30)))  # sample x sequence counts kept in HBM
 
 
 def sequence_index(keys: np.ndarray) -> pd.Index:
@@ -323,12 +354,28 @@ def build_matrix(table: CollapseTable, samples: List[SampleResult], names: List[
     join produces for > 1 sample; the single-sample order of the reference is not deterministic).  Columns as the
     reference leaves them (digest.py:253-256): annotFlag (int), the ten annotation columns (''), the samples."""
     n = int(table.n_keys)
-    cols = np.zeros((len(samples), n), dtype=np.int64)  # one contiguous row per sample
-    for j, s in enumerate(samples):
-        cols[j, s.ids] = s.counts
-    seen = cols.any(axis=0) if n else np.zeros(0, dtype=bool)
-    # order, selection and the packed texts come from the device (CollapseTable.export_sorted)
-    order, offsets, data = table.export_sorted(seen)
+    on_device = n > 0 and all(s.ids_d is not None for s in samples) and hasattr(table, "export_sorted_device") and \
+        8 * n * max(len(samples), 1) <= MATRIX_DEVICE_BYTES
+    if on_device:
+        # the columns are scattered, selected and ordered on the device; the host sees each of them once, finished
+        tdev = table.dev.tdev
+        cols_d = torch.zeros((len(samples), n), dtype=torch.int64, device=tdev)  # one contiguous row per sample
+        for j, s in enumerate(samples):
+            cols_d[j, s.ids_d.long()] = s.counts_d.long()
+        seen_d = (cols_d != 0).any(dim=0)
+        perm_d, offsets_d, data_d = table.export_sorted_device(seen_d)
+        order, offsets, data = perm_d.cpu().numpy(), offsets_d.cpu().numpy(), data_d.cpu().numpy()
+        del offsets_d, data_d
+        column = lambda j: cols_d[j][perm_d].cpu().numpy()
+    else:
+        perm_d = None
+        cols = np.zeros((len(samples), n), dtype=np.int64)
+        for j, s in enumerate(samples):
+            cols[j, s.ids] = s.counts
+        seen = cols.any(axis=0) if n else np.zeros(0, dtype=bool)
+        # order, selection and the packed texts come from the device (CollapseTable.export_sorted)
+        order, offsets, data = table.export_sorted(seen)
+        column = lambda j: cols[j][order]
     index = sequence_index_packed(offsets, data)
     m = int(order.shape[0])
     empty = empty_flag_column(m)
@@ -336,12 +383,12 @@ def build_matrix(table: CollapseTable, samples: List[SampleResult], names: List[
     frame.update((f, empty) for f in INITIAL_FLAGS)
     df = pd.DataFrame(frame, index=index, copy=False)
     for j, name in enumerate(names):
-        df[name] = cols[j][order]
+        df[name] = column(j)
     if not len(names):
         df = df.reindex(columns=["annotFlag"] + INITIAL_FLAGS)
     # the packed keys stay on the device: bwtAlign finds them here instead of re-encoding every index string
     # (row i of the DataFrame = key id order[i] of the table); the text lengths serve the read-length histogram
-    df.attrs["_mirge_b200_keys"] = DeviceKeys(table, order, np.diff(offsets))
+    df.attrs["_mirge_b200_keys"] = DeviceKeys(table, order, offsets, perm_d)
     return df
 
 
@@ -424,7 +471,8 @@ def _write_histograms(workDir, df: pd.DataFrame, results: List[SampleResult], na
         return
     histData = FormatJS(workDir)
     cached = df.attrs.get("_mirge_b200_keys")
-    lens = cached.lens if cached is not None and cached.lens is not None and len(cached.lens) == len(df) else df.index.str.len().to_numpy()
+    lens = cached.lens if cached is not None and cached.offsets is not None and len(cached.offsets) == len(df) + 1 else \
+        df.index.str.len().to_numpy()
     for div_idnum, (name, res) in enumerate(zip(names, results), 1):
         val = lens[df[name].to_numpy() > 0]
         if val.size == 0:

@@ -442,23 +442,27 @@ def bwtAlign(args, pdDataFrame, workDir, ref_db, libraries: Optional[LibrarySet]
         table, order = cached.table, cached.order
         keys = KeySet.from_table(table)
         annot_all, hit_all = annotate_keys(dev, libs, keys, spike)
-        sel = torch.from_numpy(np.ascontiguousarray(order)).to(dev.tdev)
+        sel = getattr(cached, "order_d", None)
+        if sel is None:
+            sel = torch.from_numpy(np.ascontiguousarray(order)).to(dev.tdev)
         annot_dv, hit_dv = annot_all[sel], hit_all[sel]
         annot = annot_dv.cpu().numpy()
-        hit = hit_dv.cpu().numpy()
+        hit = None  # (copied only if the columns have to be built on the host)
     else:
         seqs = pdDataFrame.index.to_numpy()
         keys = KeySet.from_strings(dev, list(seqs))
         annot_d, hit_d = annotate_keys(dev, libs, keys, spike)
         annot = annot_d.cpu().numpy()
         hit = hit_d.cpu().numpy()
-    ref = ((hit.view(np.uint64) >> np.uint64(28)) & np.uint64(0xFFFFFFF)).astype(np.int64)  # decode_hits()[2]
     colnames = list(pdDataFrame.columns)
     n_rounds = 10 if spike else 9
     on_device = False
     if annot_dv is not None:
         on_device = _fill_rounds_device(pdDataFrame, dev, annot_dv, (hit_dv >> 28) & 0xFFFFFFF, libs, n_rounds)
     if not on_device:
+        if hit is None:
+            hit = hit_dv.cpu().numpy()
+        ref = ((hit.view(np.uint64) >> np.uint64(28)) & np.uint64(0xFFFFFFF)).astype(np.int64)  # decode_hits()[2]
         _fill_rounds(pdDataFrame, annot, ref, libs, n_rounds, int(getattr(args, "threads", 0) or 0))
     flag = pdDataFrame[colnames[0]].to_numpy(copy=True)
     flag[annot != 0xFF] = 1
