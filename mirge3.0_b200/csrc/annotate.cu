@@ -545,7 +545,9 @@ annot_mask_kernel(const __grid_constant__ RoundSet rs, mirge_table t, uint64_t n
 // search_round + verify, without the query copies in local memory and without the warp-level candidate sharing --
 // for the common sequence (no exception words, <= LEAN_WORDS payload words, a handful of candidates).  Returns
 // false when the sequence needs the general path (degenerate seed, many candidates); `best` is then untouched.
+#ifndef LEAN_MAX_CAND
 #define LEAN_MAX_CAND 12
+#endif
 template <int S>
 __device__ __forceinline__ bool search_lean(const mirge_library &lib, const mirge_round_policy &pol, const uint32_t *col, int qs,
                                             int L, uint64_t &best) {
