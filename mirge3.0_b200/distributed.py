@@ -194,8 +194,9 @@ class ShardedCollapse:
                   (mirge_collapse_insert_list, keys in place).
 
     The rounds are software-pipelined: while round k is packed, round k - 1 is on the wire and round k - 2 is inserted.
-    Collectives run on a side stream (under the next batch's trim kernels) and their sizes come back through pinned
-    memory, so the launch stream never waits for the host or the network.  Every emitted key is inserted exactly once,
+    Collectives run on side streams (under the next batch's trim kernels; sizes and data on separate communicators, so
+    a round's few bytes of sizes never queue behind the previous round's data) and the sizes come back through pinned
+    memory: the launch stream never waits for the host or the network.  Every emitted key is inserted exactly once,
     into the table of the rank that owns it: there is no local table and no drain / sort / merge of unique sequences
     (exchange_and_merge above, still the path for samples dealt whole to ranks: baking_sharded).  Owner tables, key ids
     and the annotation that follows are the single-GPU ones.
@@ -210,17 +211,24 @@ class ShardedCollapse:
         self.world, self.group = int(world), group
         self.slack = float(slack)
         self.overlap = bool(overlap)
+        self.size_group = group
         if group is None and dist.is_initialized() and dist.get_backend() == "nccl" and self.overlap:
-            # the collectives run under the trim / collapse kernels of other rounds: NCCL's kernels must not queue behind
-            # the CTAs of those grids, so this path gets its own communicator on a high-priority stream (collective: every
-            # rank constructs its ShardedCollapse at the same point)
+            # The collectives run under the trim / collapse kernels of other rounds: NCCL's kernels must not queue behind
+            # the CTAs of those grids, so this path gets its own communicators on high-priority streams -- two of them,
+            # because a communicator runs its operations in order and the few bytes of a round's sizes must not wait for
+            # the previous round's data (at 8 ranks that wait stalled the host once per round).  Collective: every rank
+            # constructs its ShardedCollapse at the same point.
             try:
                 opts = dist.ProcessGroupNCCL.Options()
                 opts.is_high_priority_stream = True
                 self.group = dist.new_group(backend="nccl", pg_options=opts)
+                opts2 = dist.ProcessGroupNCCL.Options()
+                opts2.is_high_priority_stream = True
+                self.size_group = dist.new_group(backend="nccl", pg_options=opts2)
             except Exception:
-                self.group = None
-        self.comm = torch.cuda.Stream(device=self.dev.tdev, priority=-1)
+                self.group = self.size_group = None
+        self.comm = torch.cuda.Stream(device=self.dev.tdev, priority=-1)       # data: the two all-to-alls
+        self.comm_sizes = torch.cuda.Stream(device=self.dev.tdev, priority=-1)  # sizes: the all-gather and its copy to the host
         self.q = []  # rounds in flight, oldest first
         self.rounds = 0
         self._pinned = []
@@ -267,17 +275,18 @@ class ShardedCollapse:
         W = self.world
         main = torch.cuda.current_stream(self.dev.tdev)
         host = self._pinned.pop() if self._pinned else torch.empty((W, W + 1), dtype=torch.int64).pin_memory()
-        self.comm.wait_stream(main)
-        packed["cursors"].record_stream(self.comm)
-        with torch.cuda.stream(self.comm):
+        cs = self.comm_sizes
+        cs.wait_stream(main)
+        packed["cursors"].record_stream(cs)
+        with torch.cuda.stream(cs):
             mine = torch.empty(W + 1, dtype=torch.int64, device=self.dev.tdev)
             mine[:W] = packed["cursors"]
             mine[W:].fill_(1 if more else 0)  # (a kernel argument; ``mine[W] = ...`` is a pageable copy that blocks the host)
             allc = torch.empty((W, W + 1), dtype=torch.int64, device=self.dev.tdev)
-            dist.all_gather_into_tensor(allc.view(-1), mine, group=self.group)
+            dist.all_gather_into_tensor(allc.view(-1), mine, group=self.size_group)
             host.copy_(allc, non_blocking=True)
             ev = torch.cuda.Event()
-            ev.record(self.comm)
+            ev.record(cs)
         return host, ev
 
     # -- receiver ----------------------------------------------------------------------------------------------
@@ -376,7 +385,12 @@ class ShardedCollapse:
         """One collective round: this rank's batch ``br`` (None: no input left; ``more``: whether input remains after it)
         is packed and its sizes announced; the previous round goes on the wire; the one before is inserted
         (``on_piece(table)`` after it).  Returns False once every rank's input is known to be exhausted -- nothing was
-        started then and the caller must stop calling (drain_rounds does the rest); True otherwise."""
+        announced then and the caller must stop calling (drain_rounds does the rest); True otherwise.
+
+        Every hand-over has a round of slack: the sizes announced in round k are read in round k + 1 (after that batch's
+        trim), the data put on the wire in round k + 1 is waited for -- by the launch stream, not the host -- in round
+        k + 2.  (Reading the sizes in the round that announces them would make every round a barrier between the
+        ranks.)"""
         packed = self.pack(br)  # (first: the scatter follows the trim kernels without waiting for the host work below)
         any_more = True
         if self.q and self.q[-1]["stage"] == 1:
