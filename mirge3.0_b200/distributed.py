@@ -227,8 +227,11 @@ class ShardedCollapse:
                 self.size_group = dist.new_group(backend="nccl", pg_options=opts2)
             except Exception:
                 self.group = self.size_group = None
-        self.comm = torch.cuda.Stream(device=self.dev.tdev, priority=-1)       # data: the two all-to-alls
-        self.comm_sizes = torch.cuda.Stream(device=self.dev.tdev, priority=-1)  # sizes: the all-gather and its copy to the host
+        # (the plumbing below also runs on a CPU device with the gloo backend -- no streams, events or pinned memory --
+        # which is how tests/test_distributed_cpu.py drives the round protocol with stand-ins for the three kernels)
+        self._cuda = self.dev.tdev.type == "cuda"
+        self.comm = torch.cuda.Stream(device=self.dev.tdev, priority=-1) if self._cuda else None        # data: the two all-to-alls
+        self.comm_sizes = torch.cuda.Stream(device=self.dev.tdev, priority=-1) if self._cuda else None  # sizes: all-gather + copy to the host
         self.q = []  # rounds in flight, oldest first
         self.rounds = 0
         self._pinned = []
@@ -273,6 +276,13 @@ class ShardedCollapse:
     def _gather_sizes(self, packed, more: bool):
         """All-gather of the cursors (+ the 'more input' flag) on the side stream, result on its way to pinned memory."""
         W = self.world
+        if not self._cuda:
+            mine = torch.empty(W + 1, dtype=torch.int64)
+            mine[:W] = packed["cursors"]
+            mine[W] = 1 if more else 0
+            parts = [torch.empty(W + 1, dtype=torch.int64) for _ in range(W)]
+            dist.all_gather(parts, mine, group=self.size_group)
+            return torch.stack(parts), None
         main = torch.cuda.current_stream(self.dev.tdev)
         host = self._pinned.pop() if self._pinned else torch.empty((W, W + 1), dtype=torch.int64).pin_memory()
         cs = self.comm_sizes
@@ -294,7 +304,7 @@ class ShardedCollapse:
         """Room for the received keys at the end of the owner's arena: (items buffer, arena slice, key bases)."""
         d = self.dev
         n_it, n_w = int(sum(recv_items)), int(sum(recv_words))
-        if table.arena_used + n_w > table.arena.numel():
+        if table.arena_used + n_w > table.arena.numel() and self.comm is not None:
             self.comm.synchronize()  # the arena is about to move: nothing may still be arriving in the old one
         table.reserve(n_it, n_w)
         a0 = table.arena_used
@@ -341,15 +351,19 @@ class ShardedCollapse:
         Returns whether any rank announced more input in that round."""
         W = self.world
         rank = dist.get_rank(self.group)
-        main = torch.cuda.current_stream(self.dev.tdev)
-        r["ev_sizes"].synchronize()
+        main = torch.cuda.current_stream(self.dev.tdev) if self._cuda else None
+        if r["ev_sizes"] is not None:
+            r["ev_sizes"].synchronize()
         allc = r["host"].numpy().copy()
-        self._pinned.append(r.pop("host"))
+        if self._cuda:
+            self._pinned.append(r["host"])
+        r.pop("host")
         packed = r["packed"]
         again = self.settle(packed, allc[rank, :W])
         if again is not packed:
             packed = r["packed"] = again
-            self.comm.wait_stream(main)  # (the repeated scatter runs on the launch stream)
+            if self._cuda:
+                self.comm.wait_stream(main)  # (the repeated scatter runs on the launch stream)
         send_it, send_w = self.split_cursors(allc[rank, :W])
         recv_it, recv_w = [int(allc[s, rank]) >> 32 for s in range(W)], [int(allc[s, rank]) & 0xFFFFFFFF for s in range(W)]
         r_items, r_keys, bases = self.place(table, recv_it, recv_w)
@@ -358,25 +372,51 @@ class ShardedCollapse:
         s_keys = [packed["keys"][d * cw : d * cw + send_w[d]] for d in range(W)]
         o_items = list(torch.split(r_items, recv_it)) if r_items.numel() else [r_items[:0]] * W
         o_keys = list(torch.split(r_keys, recv_w)) if r_keys.numel() else [r_keys[:0]] * W
-        for t in (packed["items"], packed["keys"], r_items, table.arena):
-            t.record_stream(self.comm)
-        with torch.cuda.stream(self.comm):
-            with self.dev.timed("shard_a2a"):
-                # what this rank owns itself does not go through the communicator: a device-to-device copy
-                o_items[rank].copy_(s_items[rank], non_blocking=True)
-                o_keys[rank].copy_(s_keys[rank], non_blocking=True)
-                o_items[rank], s_items[rank] = r_items[:0], packed["items"][:0]
-                o_keys[rank], s_keys[rank] = r_keys[:0], packed["keys"][:0]
-                if W > 1:
-                    dist.all_to_all(o_items, s_items, group=self.group)
-                    dist.all_to_all(o_keys, s_keys, group=self.group)
-            ev = torch.cuda.Event()
-            ev.record(self.comm)
+        def wire():
+            # what this rank owns itself does not go through the communicator: a device-to-device copy
+            o_items[rank].copy_(s_items[rank], non_blocking=True)
+            o_keys[rank].copy_(s_keys[rank], non_blocking=True)
+            o_items[rank], s_items[rank] = r_items[:0], packed["items"][:0]
+            o_keys[rank], s_keys[rank] = r_keys[:0], packed["keys"][:0]
+            if W > 1:
+                self._all_to_all(o_items, s_items)
+                self._all_to_all(o_keys, s_keys)
+
+        ev = None
+        if self._cuda:
+            for t in (packed["items"], packed["keys"], r_items, table.arena):
+                t.record_stream(self.comm)
+            with torch.cuda.stream(self.comm):
+                with self.dev.timed("shard_a2a"):
+                    wire()
+                ev = torch.cuda.Event()
+                ev.record(self.comm)
+        else:
+            wire()
         r.update(items=r_items, recv_items=recv_it, bases=bases, ev_data=ev, stage=2)
         return bool(allc[:, W].any())
 
+    def _all_to_all(self, outs, ins):
+        """Exact-size all-to-all of per-peer tensors (NCCL: grouped send / receive; gloo has no list form, the CPU tests
+        go through point-to-point operations)."""
+        if self._cuda:
+            dist.all_to_all(outs, ins, group=self.group)
+            return
+        rank = dist.get_rank(self.group)
+        reqs = []
+        for peer in range(self.world):
+            if peer == rank:
+                continue
+            if ins[peer].numel():
+                reqs.append(dist.isend(ins[peer].contiguous(), peer, group=self.group))
+            if outs[peer].numel():
+                reqs.append(dist.irecv(outs[peer], peer, group=self.group))
+        for q in reqs:
+            q.wait()
+
     def _insert_round(self, table, r, on_piece=None):
-        torch.cuda.current_stream(self.dev.tdev).wait_event(r["ev_data"])
+        if r["ev_data"] is not None:
+            torch.cuda.current_stream(self.dev.tdev).wait_event(r["ev_data"])
         self.insert(table, r["items"], r["recv_items"], r["bases"], r["packed"]["br"])
         if on_piece is not None:
             on_piece(table)

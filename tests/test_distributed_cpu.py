@@ -109,3 +109,150 @@ def test_hash_partitioned_exchange_world2():
     union = {**results[0], **results[1]}
     assert union == exp
     assert len(results[0]) > 0 and len(results[1]) > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# distributed.ShardedCollapse (sharding before the collapse): the round protocol on CPU / gloo.  The three kernels
+# (mirge_shard_scatter, the arena placement + mirge_shard_rebase, mirge_collapse_insert_list) are replaced by numpy
+# stand-ins with the same buffer layouts; everything else -- pack-first ordering, all-gathered sizes and "more
+# input" flags, the exact-size exchange with the rank's own part bypassing it, undersized regions repeated with
+# exact sizes, ranks that run out of batches early, the three-stage pipeline and its drain -- is the product code.
+# ---------------------------------------------------------------------------------------------------------------
+
+
+def key_words(header: int) -> int:
+    """words of a packed key from its header word (len | n_exc << 16): csrc/key_format.cuh"""
+    ln, exc = header & 0xFFFF, header >> 16
+    return 1 + (ln + 15) // 16 + exc
+
+
+def sim_owner(words, world):
+    return zlib.crc32(np.asarray(words, dtype=np.int32).tobytes()) % world
+
+
+class SimSharded(MD.ShardedCollapse):
+    def pack(self, br, cap_items=0, cap_words=0):
+        W = self.world
+        items = [] if br is None else br["items"]
+        n_items = len(items)
+        n_words = sum(key_words(int(br["keys"][o])) for o, _ in items) if n_items else 0
+        cap_items = max(int(cap_items), int(n_items / W * self.slack) + 2)
+        cap_words = max(int(cap_words), int(n_words / W * self.slack) + 4)
+        out_items = torch.zeros(W * cap_items, dtype=torch.int64)
+        out_keys = torch.zeros(W * cap_words, dtype=torch.int32)
+        cur_i, cur_w = [0] * W, [0] * W
+        for o, c in items:
+            nw = key_words(int(br["keys"][o]))
+            kw = br["keys"][o : o + nw]
+            d = sim_owner(kw, W)
+            if cur_i[d] + 1 <= cap_items and cur_w[d] + nw <= cap_words:  # (a full region keeps counting, as the kernel does)
+                out_items[d * cap_items + cur_i[d]] = cur_w[d] | (c << 32)
+                out_keys[d * cap_words + cur_w[d] : d * cap_words + cur_w[d] + nw] = torch.from_numpy(np.asarray(kw, dtype=np.int32))
+            cur_i[d] += 1
+            cur_w[d] += nw
+        cursors = torch.tensor([(i << 32) | w for i, w in zip(cur_i, cur_w)], dtype=torch.int64)
+        return {"items": out_items, "keys": out_keys, "cursors": cursors, "cap_items": cap_items, "cap_words": cap_words, "br": br}
+
+    def place(self, table, recv_items, recv_words):
+        n_it, n_w = int(sum(recv_items)), int(sum(recv_words))
+        a0 = table["used"]
+        if a0 + n_w > table["arena"].numel():
+            grown = torch.zeros(2 * (a0 + n_w) + 16, dtype=torch.int32)
+            grown[:a0] = table["arena"][:a0]
+            table["arena"] = grown
+        bases, at = [], a0
+        for w in recv_words:
+            bases.append(at)
+            at += int(w)
+        table["used"] = at
+        return torch.empty(n_it, dtype=torch.int64), table["arena"][a0:at], bases
+
+    def insert(self, table, items, recv_items, bases, local_br=None):
+        arena = table["arena"].numpy()
+        lo = 0
+        for n, base in zip(recv_items, bases):
+            for v in items[lo : lo + n].tolist():
+                off, cnt = (v & 0xFFFFFFFF) + base, v >> 32
+                kw = tuple(int(x) for x in arena[off : off + key_words(int(arena[off]))])
+                table["counts"][kw] = table["counts"].get(kw, 0) + cnt
+            lo += n
+        table["inserts"] = table.get("inserts", 0) + 1
+
+
+def sim_batches(rank, n_batches, seed):
+    """[{keys: int32 words, items: [(offset, count)]}] of a rank + the (key words -> count) it contributes"""
+    rng = np.random.default_rng(seed + 17 * rank)
+    pool = [tuple([int(ln)] + [int(x) for x in rng.integers(-2**31, 2**31 - 1, (ln + 15) // 16)]) for ln in rng.integers(16, 60, 40)]
+    out, total = [], {}
+    for _ in range(n_batches):
+        words, items = [], []
+        for _ in range(int(rng.integers(1, 60))):
+            k = pool[int(rng.integers(len(pool)))] if rng.random() < 0.7 else \
+                tuple([33] + [int(x) for x in np.random.default_rng(int(rng.integers(1 << 30))).integers(0, 1 << 20, 3)])
+            c = int(rng.integers(1, 4))
+            items.append((len(words), c))
+            words.extend(k)
+            total[k] = total.get(k, 0) + c
+        out.append({"keys": np.asarray(words, dtype=np.int64).astype(np.int32), "items": items, "n_records": len(items)})
+    return out, total
+
+
+class _Br(dict):
+    n_records = property(lambda self: self["n_records"])
+
+
+def sharded_worker(rank, world, port, overlap, slack, n_batches, q):
+    import types
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        eng = types.SimpleNamespace(dev=types.SimpleNamespace(tdev=torch.device("cpu")), stats={})
+        sc = SimSharded(eng, world, overlap=overlap, slack=slack)
+        table = {"arena": torch.zeros(64, dtype=torch.int32), "used": 0, "counts": {}}
+        pieces = []
+        for sample in range(2):  # two samples in a row: the object must come back clean from drain_rounds
+            batches, _ = sim_batches(rank, n_batches[rank], 100 * sample)
+            more_any = True
+            for i, b in enumerate(batches):
+                more_any = sc.round(table, _Br(b), i + 1 < len(batches), on_piece=lambda t: pieces.append(len(t["counts"])))
+            sc.drain_rounds(table, more_any, on_piece=lambda t: pieces.append(len(t["counts"])))
+            assert not sc.q
+        q.put((rank, table["counts"], sc.rounds, len(pieces)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("overlap,slack,n_batches", [(True, 1.2, (5, 2)), (False, 1.2, (1, 4)), (True, 0.3, (3, 3)), (True, 1.2, (0, 3))])
+def test_sharding_before_collapse_round_protocol_world2(overlap, slack, n_batches):
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=sharded_worker, args=(r, world, port, overlap, slack, n_batches, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = {}
+    for _ in range(world):
+        rank, counts, rounds, n_pieces = q.get(timeout=120)
+        results[rank] = (counts, rounds, n_pieces)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    exp = {}
+    for rank in range(world):
+        for sample in range(2):
+            _, tot = sim_batches(rank, n_batches[rank], 100 * sample)
+            for k, c in tot.items():
+                exp[k] = exp.get(k, 0) + c
+    got0, got1 = results[0][0], results[1][0]
+    assert set(got0).isdisjoint(got1)
+    assert all(sim_owner(k, world) == 0 for k in got0) and all(sim_owner(k, world) == 1 for k in got1)
+    assert {**got0, **got1} == exp
+    # both ranks ran the same number of rounds: max(batches) per sample (+ the closing round of the pipelined form,
+    # which learns one round late that everybody is done), and every round's arrivals were handed to on_piece
+    assert results[0][1] == results[1][1]
+    per_sample = max(max(n_batches), 1)
+    assert results[0][1] == 2 * per_sample
+    assert results[0][2] == results[0][1]
