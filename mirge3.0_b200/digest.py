@@ -432,12 +432,7 @@ def baking(args, inFileArray, inFileBaseArray, workDir, device: Optional[Device]
             print(f"Cutadapt finished for file {base} in {round(finish2-start, 4)} second(s)")
         outlog.write(f"Cutadapt finished for file {base} in {round(finish2-start, 4)} second(s)\n")
         if getattr(args, "tcf_out", False):
-            keys = table.export_keys()
-            order = np.argsort(-res.counts, kind="stable")
-            with open(Path(workDir) / (str(base) + ".trim.collapse.fa"), "w") as fo:  # digest.py:226-235
-                for hc, j in enumerate(order.tolist(), 1):
-                    fo.write(">seq" + str(hc) + "_" + str(int(res.counts[j])) + "\n")
-                    fo.write(keys[res.ids[j]].decode("latin-1") + "\n")
+            write_tcf(workDir, base, table, res)
         finish3 = time.perf_counter()
         if not quiet:
             print(f"Collapsing finished for file {base} in {round(finish3-finish2, 4)} second(s)\n")
@@ -458,6 +453,16 @@ def baking(args, inFileArray, inFileBaseArray, workDir, device: Optional[Device]
     if keep_table:
         return complete_set, sampleReadCounts, trimmedReadCounts, trimmedReadCountsUnique, table
     return (complete_set, sampleReadCounts, trimmedReadCounts, trimmedReadCountsUnique)
+
+
+def write_tcf(workDir, base, table: CollapseTable, res: SampleResult):
+    """``<sample>.trim.collapse.fa`` (digest.py:226-235): the sample's sequences by descending count (stable)."""
+    keys = table.export_keys()
+    order = np.argsort(-res.counts, kind="stable")
+    with open(Path(workDir) / (str(base) + ".trim.collapse.fa"), "w") as fo:
+        for hc, j in enumerate(order.tolist(), 1):
+            fo.write(">seq" + str(hc) + "_" + str(int(res.counts[j])) + "\n")
+            fo.write(keys[res.ids[j]].decode("latin-1") + "\n")
 
 
 def _write_histograms(workDir, df: pd.DataFrame, results: List[SampleResult], names: List[str], umi):

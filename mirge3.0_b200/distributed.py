@@ -622,8 +622,11 @@ def baking_sharded(args, inFileArray, inFileBaseArray, workDir, device=None, cou
             with readahead.open(mine.index(s)) as f:
                 res = DG.digest_sample(eng, f, local, first_level, bool(getattr(args, "umiDedup", False)), batch_bytes, umi_csv, streamer)
             counts_read[s] = res.count
-            ids = torch.from_numpy(res.ids.astype(np.int32)).to(dev.tdev)
-            cnt = torch.from_numpy(res.counts.astype(np.int32)).to(dev.tdev)
+            if getattr(args, "tcf_out", False):
+                # <sample>.trim.collapse.fa (digest.py:226-235) by the rank that digested the sample: its local table
+                # holds exactly the sample's completeDict
+                DG.write_tcf(workDir, names[s], local, res)
+            ids, cnt = res.ids_d, res.counts_d
         else:
             ids, cnt = empty, empty
         exchange_and_merge(dev, local, ids, cnt, owner, world, group=group)  # collective
@@ -669,6 +672,12 @@ def baking_sharded(args, inFileArray, inFileBaseArray, workDir, device=None, cou
     df = df.reindex(columns=["annotFlag"] + DG.INITIAL_FLAGS + names)
     df = df.astype({"annotFlag": int})
     _SHARD.update(order=order, offs=offs, n_all=int(all_keys.shape[0]))
+    # index_data.js read-length histograms (digest.py:270-295) from the gathered matrix; the UMI count histograms stay
+    # with the single-process baking (their per-sample lists live on the digesting ranks)
+    class _NoHist:
+        hist = np.zeros(0, dtype=np.int64)
+
+    DG._write_histograms(workDir, df, [_NoHist()] * len(names), names, None)
     return df, src, trc, tru
 
 

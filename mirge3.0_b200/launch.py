@@ -28,19 +28,54 @@ def _bakingEC_unsupported(*_a, **_k):
              "run without -mEC")
 
 
+def _tool(args, path_attr: str, name: str):
+    """the executable the reference would run for ``name`` (its ``-pbwt`` / ``-psam`` / ``-prf`` directory, else PATH)"""
+    d = getattr(args, path_attr, None)
+    if d:
+        cand = os.path.join(str(d), name)
+        return cand if os.access(cand, os.X_OK) else None
+    return shutil.which(name)
+
+
+def downstream_tools(args):
+    """[(tool, option that needs it)] the reference will shell out to AFTER the hot path, for the options of this run:
+    -nmir: bowtie / bowtie-build / samtools / RNAfold (novel_mir.py:224-225,318-323); -ai and -trf: bowtie
+    (mirge2_tRF_a2i.py:1056,1291); -bam: samtools (bamFmt.py:116,174).  The B200 path replaces none of these."""
+    need = []
+    if getattr(args, "novel_miRNA", False):
+        need += [("bowtie_path", "bowtie", "-nmir"), ("bowtie_path", "bowtie-build", "-nmir"), ("samtools_path", "samtools", "-nmir"),
+                 ("RNAfold_path", "RNAfold", "-nmir")]
+    if getattr(args, "AtoI", False):
+        need.append(("bowtie_path", "bowtie", "-ai"))
+    if getattr(args, "tRNA_frag", False):
+        need.append(("bowtie_path", "bowtie", "-trf"))
+    if getattr(args, "bam_out", False):
+        need.append(("samtools_path", "samtools", "-bam"))
+    return need
+
+
 def _check_dependencies(args, runlogFile):
     from . import essential
 
     essential.check_dependencies(args, runlogFile)
-    have = None
-    if getattr(args, "bowtie_path", None):
-        cand = os.path.join(str(args.bowtie_path), "bowtie-inspect")
-        have = cand if os.access(cand, os.X_OK) else None
-    else:
-        have = shutil.which("bowtie-inspect")
+    # the probes of the reference's check_dependencies that still matter: tools its downstream modules run.  Missing
+    # ones stop the run here, before the digest, instead of in the middle of summarize().
+    missing = sorted({"%s (needed by %s)" % (name, opt) for attr, name, opt in downstream_tools(args) if _tool(args, attr, name) is None})
+    if missing:
+        sys.exit("mirge_b200: the requested options run tools that were not found: " + ", ".join(missing) +
+                 ". Install them or point -pbwt / -psam / -prf at them; the B200 path only replaces cutadapt and the "
+                 "annotation rounds' bowtie calls.")
+    have = _tool(args, "bowtie_path", "bowtie-inspect")
     if have is None:  # summarize() / bamFmt shell out to it (summary.py:776, bamFmt.py:10)
         shim_dir = os.path.join(os.path.dirname(os.path.abspath(str(runlogFile))), ".mirge_b200_bin")
         essential.write_inspect_shim(shim_dir)
+        # args.bowtie_path is also where the reference looks for bowtie / bowtie-build (novel_mir.py:318-321,
+        # mirge2_tRF_a2i.py:1056): the shim directory must not hide real ones
+        for name in ("bowtie", "bowtie-build"):
+            real = _tool(args, "bowtie_path", name)
+            link = os.path.join(shim_dir, name)
+            if real is not None and not os.path.lexists(link):
+                os.symlink(os.path.realpath(real), link)
         args.bowtie_path = shim_dir
 
 

@@ -55,14 +55,31 @@ def check_entry_points(rank, world, dev, umi):
             else:
                 open(f, "wb").write(data)
     dist.barrier()
-    args = make_args(libraries_path=os.path.join(tmp, "lib"), spikeIn=True, uniq_mol_ids="4,4" if umi else None, umiDedup=bool(umi))
+    args = make_args(libraries_path=os.path.join(tmp, "lib"), spikeIn=True, uniq_mol_ids="4,4" if umi else None, umiDedup=bool(umi),
+                     tcf_out=True)
     df, src, trc, tru = MD.baking_sharded(args, files, names, tmp, device=dev, batch_bytes=200_000)
     out = MD.bwtAlign_sharded(args, df, tmp, "miRBase")
+    dist.barrier()
+
+    def tcf_files():
+        """{sample: [(count, sequence)]} of the <sample>.trim.collapse.fa files (-tcf): counts must descend; ties may come in
+        any order (they follow the table's slot order)"""
+        got = {}
+        for n in names:
+            lines = open(os.path.join(tmp, n + ".trim.collapse.fa")).read().split("\n")
+            recs = [(int(h.rsplit("_", 1)[1]), s_) for h, s_ in zip(lines[0::2], lines[1::2]) if h]
+            assert all(recs[i][0] >= recs[i + 1][0] for i in range(len(recs) - 1))
+            assert [h for h in lines[0::2] if h] == [">seq%d_%d" % (i + 1, c) for i, (c, _) in enumerate(recs)]
+            got[n] = sorted(recs)
+        return got
+
     ok = True
     if rank == 0:
+        tcf_sharded = tcf_files()  # written by the ranks that digested the samples
         df1, src1, trc1, tru1 = DG.baking(args, files, names, tmp, device=dev, batch_bytes=200_000)
         out1 = MA.bwtAlign(args, df1, tmp, "miRBase", device=dev)
         ok = out.equals(out1) and list(out.columns) == list(out1.columns) and (src, trc, tru) == (src1, trc1, tru1)
+        ok = ok and tcf_sharded == tcf_files()
         print("sharded entry points: world=%d samples=%d rows=%d annotated=%d umi=%s ok=%s"
               % (world, len(names), len(out), int((out.annotFlag == 1).sum()), bool(umi), ok))
         if not ok:

@@ -155,3 +155,44 @@ def test_unmodified_reference_summarize_runs_on_the_shim(tmp_path):
         os.chdir(cwd)
     for name in ("annotation.report.csv", "miR.Counts.csv", "miR.RPM.csv"):
         assert (work / name).read_text() == golden(name), name
+
+
+def test_downstream_tools_are_probed_before_the_digest(tmp_path, monkeypatch):
+    """launch._check_dependencies: the tools the reference's downstream modules shell out to (novel_mir.py:224-225,318-323,
+    mirge2_tRF_a2i.py:1056,1291, bamFmt.py:116,174) are looked for up front, and the bowtie-inspect shim directory does not
+    hide a real bowtie / bowtie-build behind args.bowtie_path."""
+    import argparse
+    import stat
+
+    from mirge_b200 import launch
+
+    a = argparse.Namespace(novel_miRNA=True, AtoI=False, tRNA_frag=True, bam_out=True, bowtie_path=None, samtools_path=None, RNAfold_path=None)
+    need = launch.downstream_tools(a)
+    assert {(n, o) for _, n, o in need} == {("bowtie", "-nmir"), ("bowtie-build", "-nmir"), ("samtools", "-nmir"), ("RNAfold", "-nmir"),
+                                          ("bowtie", "-trf"), ("samtools", "-bam")}
+    assert launch.downstream_tools(argparse.Namespace()) == []
+    # a directory with fake tools: found through -pbwt, not through PATH
+    bindir = tmp_path / "bin"
+    bindir.mkdir()
+    for name in ("bowtie", "bowtie-build"):
+        p = bindir / name
+        p.write_text("#!/bin/sh\nexit 0\n")
+        p.chmod(p.stat().st_mode | stat.S_IXUSR)
+    monkeypatch.setenv("PATH", str(tmp_path / "nothing"))
+    a.bowtie_path = str(bindir)
+    assert launch._tool(a, "bowtie_path", "bowtie") == str(bindir / "bowtie")
+    assert launch._tool(a, "bowtie_path", "bowtie-inspect") is None
+    assert launch._tool(a, "samtools_path", "samtools") is None
+    # the full probe: samtools / RNAfold missing -> early exit naming them and the options
+    monkeypatch.setattr("mirge_b200.essential.check_dependencies", lambda args, log: None)
+    with pytest.raises(SystemExit) as e:
+        launch._check_dependencies(a, str(tmp_path / "run.log"))
+    assert "samtools (needed by -bam)" in str(e.value) and "RNAfold (needed by -nmir)" in str(e.value) and "bowtie (" not in str(e.value)
+    # nothing missing: the shim directory becomes args.bowtie_path and carries links to the real bowtie / bowtie-build
+    b = argparse.Namespace(novel_miRNA=False, AtoI=True, tRNA_frag=False, bam_out=False, bowtie_path=str(bindir), samtools_path=None,
+                           RNAfold_path=None)
+    launch._check_dependencies(b, str(tmp_path / "run.log"))
+    assert b.bowtie_path.endswith(".mirge_b200_bin")
+    for name in ("bowtie-inspect", "bowtie", "bowtie-build"):
+        assert os.access(os.path.join(b.bowtie_path, name), os.X_OK)
+    assert os.path.realpath(os.path.join(b.bowtie_path, "bowtie")) == os.path.realpath(str(bindir / "bowtie"))
