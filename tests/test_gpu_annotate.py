@@ -270,6 +270,46 @@ def test_streamed_annotation_matches_whole_table(dev):
     assert torch.equal(a2, ann2) and torch.equal(h2, hit2) and not sb.host
 
 
+def test_annotation_with_the_full_size_libraries_matches_oracle(dev):
+    """The nine rounds on > 1 M unique sequences of the C2 workload against the libraries at the size bench.py uses --
+    all of them at full scale, the mRNA library with its 100 000 entries (150 M bases: index, bucket table and presence
+    filters at the sizes the timed kernels see) -- hit by hit against the oracle's indexed CPU search."""
+    from mirge_b200 import device as D
+    from mirge_b200 import libraries as LB
+    from mirge_b200 import manifoldAlign as MA
+    from mirge_b200 import synth
+
+    libs = synth.make_libraries(mrna_count=100_000)
+    lset = LB.LibrarySet.from_fasta_dict(dev, libs.fasta_dict())
+    eng = D.DigestEngine(dev, synth.trim_config_for(2, "head"))
+    fq = synth.ReadGenerator(libs, synth.CONFIGS[2], dev.tdev).fastq(1_300_000)
+    table = D.CollapseTable(dev, min_keys=1 << 21)
+    assert eng.digest_device(fq, table, 128 << 20) == 1_300_000
+    nk = table.n_keys
+    assert nk > 1_000_000
+    annot, hit = MA.annotate_keys(dev, lset, MA.KeySet.from_table(table), False)
+    annot, hit = annot.cpu().numpy(), hit.cpu().numpy().view(np.uint64)
+    kk = table.export_keys()
+    blob = np.frombuffer(b"".join(kk.tolist()), dtype=np.uint8)
+    off = np.zeros(len(kk) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(np.char.str_len(kk))
+    a_o = np.full(nk, 0xFF, dtype=np.uint8)
+    h_o = np.full(nk, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)
+    lut = np.frombuffer(b"ACGTN", dtype=np.uint8)
+    pols = LB.round_policies()
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 4)
+    for rnd in range(9):
+        L = libs.libs[LB.ROUND_LIBS[rnd]]
+        index = coracle.Index(lut[L.codes], L.off.astype(np.uint32))
+        coracle.annotate_round_indexed(blob, off, index, pols[rnd], a_o, h_o, threads)
+        del index
+    bad = np.flatnonzero((annot != a_o) | (hit != h_o))
+    assert bad.size == 0, "first differing sequence %r: gpu round %d hit %x, oracle round %d hit %x (%d differ)" % (
+        kk[bad[0]], annot[bad[0]], hit[bad[0]], a_o[bad[0]], h_o[bad[0]], bad.size)
+    per_round = np.bincount(a_o[a_o != 0xFF], minlength=9)
+    assert (per_round > 1000).all(), per_round  # every round, the mRNA round included, annotated thousands of sequences
+
+
 def test_libraries_load_from_bowtie_index_files(dev, tmp_path, monkeypatch):
     """A library directory that ships only .ebwt files (stock miRge3_Lib) gives the same annotation as FASTA -- once the
     built-in decoder is asked for: without MIRGE_B200_TRUST_EBWT=1 (and without a bowtie-inspect) the loader refuses."""
