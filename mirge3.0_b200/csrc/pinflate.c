@@ -1,0 +1,762 @@
+/* pinflate.c -- chunk-parallel inflate of ONE gzip stream on the host cores ("next" row f-3:
+ * "parallel gz inflate").  What the reference does here is `xopen(FQfile, "rb")` (mirge/libs/digest.py:136), i.e. one
+ * gzip stream inflated by one core (or by an external pigz / igzip process, which also inflate serially); a single
+ * sample's .fastq.gz therefore reaches the device path at ~0.1-0.2 GB/s.  DEFLATE is serial by construction -- block
+ * boundaries are only known after decoding what precedes them and every block may refer to the 32 KB before it -- so
+ * this decoder does what pugz / rapidgzip published:
+ *
+ *   1. the compressed stream is cut every `chunk` bytes; near every cut a thread looks for a bit position at which a
+ *      dynamic-Huffman block header parses (complete code-length code, complete literal/length code, end-of-block
+ *      symbol present);
+ *   2. from there it decodes into 16-bit symbols with an UNKNOWN window: a back-reference that reaches before the
+ *      chunk yields markers (256 + position in the 32 KB window) that are copied like any other symbol;
+ *   3. a chunk stops exactly when its bit position equals the next chunk's start at a block boundary -- which proves
+ *      that start to be a real boundary; a start the chain never lands on is discarded and the previous chunk decodes
+ *      on, so a false positive of step 1 costs time, never correctness;
+ *   4. the windows are chained (only the last 32 KB of each chunk are resolved serially), then all chunks replace
+ *      their markers in parallel; CRC-32 is computed per chunk and combined, and checked with ISIZE against the gzip
+ *      trailer of every member.
+ *
+ * Multi-member files and zero padding between members are handled as Python's gzip module does.  Host-only code (no
+ * CUDA): built by __graft_entry__.build() with gcc -fopenmp into libmirge_inflate.so and bound by ingest.py; when the
+ * library is missing ingest.py keeps its serial zlib reader (same bytes, slower).  */
+#include <omp.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define WIN 32768
+#define MAXBITS 15
+#define LIT_PB 10 /* primary table bits, literal/length code */
+#define DST_PB 8  /* primary table bits, distance code */
+#define POOL_MAX 512
+
+/* ------------------------------------------------------------------ bit reader ------- */
+typedef struct {
+  const uint8_t *p;
+  uint64_t n;   /* bytes */
+  uint64_t pos; /* next byte to load */
+  uint64_t buf;
+  int cnt; /* valid bits in buf */
+} bitr;
+
+static inline void br_init(bitr *b, const uint8_t *p, uint64_t n, uint64_t bitpos) {
+  b->p = p; b->n = n; b->pos = bitpos >> 3; b->buf = 0; b->cnt = 0;
+  int skip = (int)(bitpos & 7);
+  if (skip) {
+    if (b->pos < n) b->buf = (uint64_t)p[b->pos] >> skip;
+    b->pos++;
+    b->cnt = 8 - skip;
+  }
+}
+static inline void br_refill(bitr *b) {
+  if (b->pos + 8 <= b->n) { /* one unaligned load tops the buffer up to >= 56 bits */
+    uint64_t v;
+    memcpy(&v, b->p + b->pos, 8);
+    b->buf |= v << b->cnt;
+    const int adv = (63 - b->cnt) >> 3;
+    b->pos += (uint64_t)adv;
+    b->cnt += adv << 3;
+    return;
+  }
+  while (b->cnt <= 56) {
+    uint64_t byte = b->pos < b->n ? b->p[b->pos] : 0; /* zeros beyond the end; br_overrun() tells */
+    b->buf |= byte << b->cnt;
+    b->pos++;
+    b->cnt += 8;
+  }
+}
+static inline uint64_t br_bitpos(const bitr *b) { return b->pos * 8 - (uint64_t)b->cnt; }
+static inline int br_overrun(const bitr *b) { return br_bitpos(b) > b->n * 8; }
+static inline uint32_t br_peek(const bitr *b, int k) { return (uint32_t)(b->buf & ((1ull << k) - 1ull)); }
+static inline void br_drop(bitr *b, int k) { b->buf >>= k; b->cnt -= k; }
+static inline uint32_t br_bits(bitr *b, int k) { uint32_t v = br_peek(b, k); br_drop(b, k); return v; }
+
+/* ------------------------------------------------------------------ Huffman tables ------- */
+typedef struct {
+  uint16_t count[MAXBITS + 1];
+  uint16_t symbol[288];
+  uint16_t fast[1 << LIT_PB]; /* (symbol << 4) | length, 0 = longer than the primary table */
+  int pb;
+} huff;
+
+/* returns 0 complete, > 0 incomplete (left over), < 0 over-subscribed */
+static int huff_build(huff *h, const uint8_t *len, int n, int pb) {
+  uint16_t offs[MAXBITS + 1];
+  h->pb = pb;
+  memset(h->count, 0, sizeof(h->count));
+  for (int s = 0; s < n; ++s) h->count[len[s]]++;
+  int left = 1;
+  for (int l = 1; l <= MAXBITS; ++l) {
+    left <<= 1;
+    left -= h->count[l];
+    if (left < 0) return left;
+  }
+  offs[1] = 0;
+  for (int l = 1; l < MAXBITS; ++l) offs[l + 1] = offs[l] + h->count[l];
+  for (int s = 0; s < n; ++s)
+    if (len[s]) h->symbol[offs[len[s]]++] = (uint16_t)s;
+  /* primary table: canonical codes, bit-reversed (DEFLATE packs codes MSB first into an LSB-first stream) */
+  memset(h->fast, 0, sizeof(uint16_t) << pb);
+  uint32_t code = 0;
+  int idx = 0;
+  for (int l = 1; l <= pb; ++l) {
+    for (int k = 0; k < h->count[l]; ++k, ++idx, ++code) {
+      uint32_t rev = 0;
+      for (int b = 0; b < l; ++b) rev |= ((code >> b) & 1u) << (l - 1 - b);
+      const uint16_t e = (uint16_t)((h->symbol[idx] << 4) | l);
+      for (uint32_t j = rev; j < (1u << pb); j += 1u << l) h->fast[j] = e;
+    }
+    code <<= 1;
+  }
+  return left;
+}
+
+/* decode one symbol; -1 = invalid code.  The caller has >= 15 bits in the buffer. */
+static inline int huff_decode(const huff *h, bitr *b) {
+  const uint16_t e = h->fast[br_peek(b, h->pb)];
+  if (e) { br_drop(b, e & 15); return e >> 4; }
+  /* canonical, bit by bit (codes longer than the primary table, or an incomplete code's unused pattern) */
+  int code = 0, first = 0, index = 0;
+  uint64_t bits = b->buf;
+  for (int l = 1; l <= MAXBITS; ++l) {
+    code |= (int)(bits & 1u);
+    bits >>= 1;
+    const int c = h->count[l];
+    if (code - c < first) { br_drop(b, l); return h->symbol[index + (code - first)]; }
+    index += c;
+    first += c;
+    first <<= 1;
+    code <<= 1;
+  }
+  return -1;
+}
+
+static const uint16_t LBASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+static const uint8_t LEXT[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+static const uint16_t DBASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+static const uint8_t DEXT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+static const uint8_t CLORD[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+/* Header of a dynamic block (the 3 block bits already consumed).  strict: what the block finder demands of a
+ * candidate (complete codes; zlib never writes anything else); otherwise what inflate accepts.  0 = ok. */
+static int dynamic_header(bitr *b, huff *lit, huff *dst, int strict) {
+  br_refill(b);
+  const int nlen = (int)br_bits(b, 5) + 257, ndist = (int)br_bits(b, 5) + 1, ncode = (int)br_bits(b, 4) + 4;
+  if (nlen > 286 || ndist > 30) return -1;
+  uint8_t lens[320];
+  uint8_t cl[19];
+  memset(cl, 0, sizeof(cl));
+  for (int i = 0; i < ncode; ++i) {
+    if ((i & 7) == 0) br_refill(b);
+    cl[CLORD[i]] = (uint8_t)br_bits(b, 3);
+  }
+  huff clh;
+  int err = huff_build(&clh, cl, 19, 7);
+  if (err < 0 || (err > 0 && strict)) return -2;
+  int idx = 0;
+  while (idx < nlen + ndist) {
+    br_refill(b);
+    int sym = huff_decode(&clh, b);
+    if (sym < 0) return -3;
+    if (sym < 16) { lens[idx++] = (uint8_t)sym; continue; }
+    int rep, val = 0;
+    if (sym == 16) {
+      if (idx == 0) return -4;
+      val = lens[idx - 1];
+      rep = 3 + (int)br_bits(b, 2);
+    } else if (sym == 17) rep = 3 + (int)br_bits(b, 3);
+    else rep = 11 + (int)br_bits(b, 7);
+    if (idx + rep > nlen + ndist) return -5;
+    while (rep--) lens[idx++] = (uint8_t)val;
+  }
+  if (br_overrun(b)) return -6;
+  if (lens[256] == 0) return -7; /* no end-of-block code */
+  err = huff_build(lit, lens, nlen, LIT_PB);
+  if (err < 0) return -8;
+  if (err > 0 && (strict || nlen != lit->count[0] + lit->count[1])) return -8; /* incomplete: only a single 1-bit code */
+  err = huff_build(dst, lens + nlen, ndist, DST_PB);
+  if (err < 0) return -9;
+  if (err > 0 && ndist != dst->count[0] + dst->count[1]) return -9;
+  return 0;
+}
+
+static huff g_fixed_lit, g_fixed_dst;
+static int g_fixed_ready = 0;
+static void fixed_tables(void) {
+  uint8_t l[288];
+  int s = 0;
+  for (; s < 144; ++s) l[s] = 8;
+  for (; s < 256; ++s) l[s] = 9;
+  for (; s < 280; ++s) l[s] = 7;
+  for (; s < 288; ++s) l[s] = 8;
+  huff_build(&g_fixed_lit, l, 288, LIT_PB);
+  for (s = 0; s < 30; ++s) l[s] = 5;
+  huff_build(&g_fixed_dst, l, 30, DST_PB);
+  g_fixed_ready = 1;
+}
+
+/* ------------------------------------------------------------------ chunk decoder ------- */
+enum { END_HIT = 1, END_FINAL = 2, END_LIMIT = 3, END_ERROR = 4 };
+
+typedef struct {
+  uint16_t *sym;  /* [WIN prefix][output] */
+  uint64_t cap;   /* symbols allocated */
+  uint64_t n;     /* output symbols (after the prefix) */
+  uint64_t start_bit, end_bit;
+  int end_kind;
+  int hit;        /* END_HIT: index of the candidate the chunk stopped at */
+  int err;
+  int known;      /* 1: the prefix holds the real window (no markers can occur), 2: empty window (start of a member) */
+  uint64_t max_out; /* speculative chunks: give up beyond this many symbols (0 = no limit) */
+  uint8_t *bytes; /* resolved output */
+  uint64_t bytes_cap;
+  uint32_t crc;
+} chunk;
+
+static int chunk_reserve(chunk *c, uint64_t need_total) {
+  if (need_total <= c->cap) return 0;
+  uint64_t nc = c->cap + c->cap / 2;
+  if (nc < need_total) nc = need_total;
+  uint16_t *p = (uint16_t *)realloc(c->sym, nc * sizeof(uint16_t));
+  if (!p) return -1;
+  c->sym = p;
+  c->cap = nc;
+  return 0;
+}
+
+/* Decode from c->start_bit.  Stops at a block boundary whose bit position equals cand[j] for some j >= first_cand
+ * (END_HIT), or is >= limit_bit once no candidate is left (END_LIMIT), or after the final block (END_FINAL).
+ * max_out: give up (END_ERROR) when a speculative chunk produced that much without getting anywhere (0 = no limit). */
+static void chunk_decode(chunk *c, const uint8_t *data, uint64_t nbytes, const uint64_t *cand, int n_cand, int first_cand,
+                         uint64_t limit_bit) {
+  bitr b;
+  br_init(&b, data, nbytes, c->start_bit);
+  uint64_t o = WIN; /* write index into c->sym */
+  int j = first_cand;
+  huff lit, dst;
+  c->end_kind = END_ERROR;
+  c->err = 0;
+  c->hit = -1;
+  int first_block = 1;
+  for (;;) {
+    const uint64_t bp = br_bitpos(&b);
+    if (!first_block) {
+      while (j < n_cand && cand[j] < bp) ++j; /* starts the chain did not land on: not real boundaries */
+      if (j < n_cand && cand[j] == bp) { c->end_kind = END_HIT; c->hit = j; break; }
+      if (j >= n_cand && bp >= limit_bit) { c->end_kind = END_LIMIT; break; }
+    }
+    first_block = 0;
+    br_refill(&b);
+    const int final = (int)br_bits(&b, 1);
+    const int type = (int)br_bits(&b, 2);
+    if (type == 3) { c->err = -10; break; }
+    if (type == 0) {
+      br_drop(&b, b.cnt & 7); /* to the byte boundary */
+      br_refill(&b);
+      const uint32_t len = br_bits(&b, 16), nlen = br_bits(&b, 16);
+      if ((len ^ 0xFFFFu) != nlen) { c->err = -11; break; }
+      if (chunk_reserve(c, o + len + 16)) { c->err = -12; break; }
+      /* the bit buffer holds whole bytes now: hand them back and copy from the stream */
+      uint64_t at = br_bitpos(&b) >> 3;
+      if (at + len > nbytes) { c->err = -13; break; }
+      for (uint32_t i = 0; i < len; ++i) c->sym[o + i] = data[at + i];
+      o += len;
+      br_init(&b, data, nbytes, (at + len) * 8);
+    } else {
+      const huff *L, *D;
+      if (type == 1) {
+        L = &g_fixed_lit; D = &g_fixed_dst;
+      } else {
+        if ((c->err = dynamic_header(&b, &lit, &dst, 0)) != 0) break;
+        L = &lit; D = &dst;
+      }
+      int bad = 0;
+      for (;;) {
+        if (o + 300 > c->cap) {
+          if (c->max_out && o - WIN > c->max_out) { bad = -20; break; } /* a speculative chunk that runs away */
+          if (chunk_reserve(c, o + 300 + c->cap / 2)) { bad = -12; break; }
+        }
+        br_refill(&b);
+        if (b.pos > nbytes + 16) { bad = -18; break; } /* reading zeros beyond the end of the file */
+        {
+          /* runs of literals: up to four primary-table codes (<= 10 bits each) per refill */
+          uint16_t e = L->fast[br_peek(&b, LIT_PB)];
+          if (e && e < (256u << 4)) {
+            br_drop(&b, e & 15); c->sym[o++] = (uint16_t)(e >> 4);
+            e = L->fast[br_peek(&b, LIT_PB)];
+            if (e && e < (256u << 4)) {
+              br_drop(&b, e & 15); c->sym[o++] = (uint16_t)(e >> 4);
+              e = L->fast[br_peek(&b, LIT_PB)];
+              if (e && e < (256u << 4)) {
+                br_drop(&b, e & 15); c->sym[o++] = (uint16_t)(e >> 4);
+                e = L->fast[br_peek(&b, LIT_PB)];
+                if (e && e < (256u << 4)) { br_drop(&b, e & 15); c->sym[o++] = (uint16_t)(e >> 4); }
+              }
+            }
+            continue;
+          }
+        }
+        int s = huff_decode(L, &b);
+        if (s < 256) {
+          if (s < 0) { bad = -14; break; }
+          c->sym[o++] = (uint16_t)s;
+          continue;
+        }
+        if (s == 256) break;
+        s -= 257;
+        if (s >= 29) { bad = -15; break; }
+        const uint32_t len = LBASE[s] + br_bits(&b, LEXT[s]);
+        const int ds = huff_decode(D, &b);
+        if (ds < 0 || ds >= 30) { bad = -16; break; }
+        const uint32_t dist = DBASE[ds] + br_bits(&b, DEXT[ds]);
+        if (c->known == 2 && dist > o - WIN) { bad = -17; break; } /* before the start of the member */
+        uint16_t *w = c->sym + o;
+        const uint16_t *r = w - dist;
+        if (dist >= len) memcpy(w, r, len * sizeof(uint16_t));
+        else for (uint32_t i = 0; i < len; ++i) w[i] = r[i];
+        o += len;
+      }
+      if (bad) { c->err = bad; break; }
+      if (br_overrun(&b)) { c->err = -18; break; }
+    }
+    if (final) { c->end_kind = END_FINAL; break; }
+  }
+  c->n = o - WIN;
+  c->end_bit = br_bitpos(&b);
+}
+
+/* first bit position in [from, to) at which a non-final dynamic block header parses strictly; UINT64_MAX: none */
+static uint64_t find_block(const uint8_t *data, uint64_t nbytes, uint64_t from, uint64_t to) {
+  huff lit, dst;
+  for (uint64_t bp = from; bp < to; ++bp) {
+    const uint64_t byte = bp >> 3;
+    if (byte + 8 >= nbytes) break;
+    uint64_t v;
+    memcpy(&v, data + byte, 8);
+    v >>= (bp & 7);
+    if ((v & 7) != 4) continue;                    /* BFINAL = 0, BTYPE = 2 */
+    if (((v >> 3) & 31) > 29 || ((v >> 8) & 31) > 29) continue; /* HLIT, HDIST */
+    bitr b;
+    br_init(&b, data, nbytes, bp + 3);
+    if (dynamic_header(&b, &lit, &dst, 1) == 0) return bp;
+  }
+  return UINT64_MAX;
+}
+
+/* ------------------------------------------------------------------ CRC-32 (slice by 8) + combine ------- */
+static uint32_t g_crc[8][256];
+static void crc_tables(void) {
+  for (uint32_t i = 0; i < 256; ++i) {
+    uint32_t c = i;
+    for (int k = 0; k < 8; ++k) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+    g_crc[0][i] = c;
+  }
+  for (uint32_t i = 0; i < 256; ++i)
+    for (int t = 1; t < 8; ++t) g_crc[t][i] = (g_crc[t - 1][i] >> 8) ^ g_crc[0][g_crc[t - 1][i] & 0xFF];
+}
+static uint32_t crc32_buf(uint32_t crc, const uint8_t *p, uint64_t n) {
+  crc = ~crc;
+  while (n && ((uintptr_t)p & 7)) { crc = g_crc[0][(crc ^ *p++) & 0xFF] ^ (crc >> 8); --n; }
+  while (n >= 8) {
+    uint64_t v;
+    memcpy(&v, p, 8);
+    v ^= crc;
+    crc = g_crc[7][v & 0xFF] ^ g_crc[6][(v >> 8) & 0xFF] ^ g_crc[5][(v >> 16) & 0xFF] ^ g_crc[4][(v >> 24) & 0xFF] ^
+          g_crc[3][(v >> 32) & 0xFF] ^ g_crc[2][(v >> 40) & 0xFF] ^ g_crc[1][(v >> 48) & 0xFF] ^ g_crc[0][v >> 56];
+    p += 8;
+    n -= 8;
+  }
+  while (n--) crc = g_crc[0][(crc ^ *p++) & 0xFF] ^ (crc >> 8);
+  return ~crc;
+}
+/* crc of A ++ B from crc(A), crc(B), len(B): multiplication by x^(8 len) in GF(2)[x] mod the CRC polynomial */
+static uint32_t gf2_times(const uint32_t *mat, uint32_t vec) {
+  uint32_t s = 0;
+  for (int i = 0; vec; vec >>= 1, ++i)
+    if (vec & 1) s ^= mat[i];
+  return s;
+}
+static void gf2_square(uint32_t *sq, const uint32_t *mat) {
+  for (int i = 0; i < 32; ++i) sq[i] = gf2_times(mat, mat[i]);
+}
+static uint32_t crc32_comb(uint32_t crc1, uint32_t crc2, uint64_t len2) {
+  if (len2 == 0) return crc1;
+  uint32_t even[32], odd[32];
+  odd[0] = 0xEDB88320u;
+  uint32_t row = 1;
+  for (int i = 1; i < 32; ++i) { odd[i] = row; row <<= 1; }
+  gf2_square(even, odd);
+  gf2_square(odd, even);
+  do {
+    gf2_square(even, odd);
+    if (len2 & 1) crc1 = gf2_times(even, crc1);
+    len2 >>= 1;
+    if (!len2) break;
+    gf2_square(odd, even);
+    if (len2 & 1) crc1 = gf2_times(odd, crc1);
+    len2 >>= 1;
+  } while (len2);
+  return crc1 ^ crc2;
+}
+
+/* ------------------------------------------------------------------ the stream ------- */
+typedef struct {
+  const uint8_t *data;
+  uint64_t n;
+  int threads;
+  uint64_t chunk_bytes;
+  /* position: next wave starts at bit `pos` inside a member (in_member) or at byte `pos / 8` between members */
+  uint64_t pos;
+  int in_member;
+  int eof;
+  uint8_t window[WIN]; /* last WIN bytes of the output so far (zero-padded at the front while shorter) */
+  uint64_t member_len; /* bytes of the current member so far */
+  uint32_t member_crc;
+  /* output of the last wave */
+  chunk *out;
+  int n_out, cur_out;
+  uint64_t cur_off;
+  uint64_t total_out;
+  /* buffers kept between waves (fresh allocations of this size are page faults, several per output page) */
+  void *pool[2][POOL_MAX];
+  uint64_t pool_cap[2][POOL_MAX];
+  int pool_n[2];
+  /* statistics */
+  uint64_t waves, chunks_used, chunks_wasted, serial_repairs;
+  double t_find, t_decode, t_chain, t_resolve;
+  char err[256];
+} pgz;
+
+static int fail(pgz *z, const char *msg, uint64_t at) {
+  snprintf(z->err, sizeof(z->err), "%s (compressed byte %llu)", msg, (unsigned long long)at);
+  return -1;
+}
+
+/* which: 0 = symbol buffers (cap in symbols), 1 = byte buffers.  Returns a buffer of at least `need` units or NULL. */
+static void *pool_take(pgz *z, int which, uint64_t need, uint64_t *cap) {
+  const uint64_t unit = which == 0 ? sizeof(uint16_t) : 1;
+  if (z->pool_n[which] > 0) {
+    const int i = --z->pool_n[which];
+    void *p = z->pool[which][i];
+    uint64_t c = z->pool_cap[which][i];
+    if (c < need) {
+      void *q = realloc(p, need * unit);
+      if (!q) { free(p); return NULL; }
+      p = q;
+      c = need;
+    }
+    *cap = c;
+    return p;
+  }
+  *cap = need;
+  return malloc(need ? need * unit : 1);
+}
+static void pool_give(pgz *z, int which, void *p, uint64_t cap) {
+  if (!p) return;
+  if (z->pool_n[which] < POOL_MAX) {
+    z->pool[which][z->pool_n[which]] = p;
+    z->pool_cap[which][z->pool_n[which]] = cap;
+    z->pool_n[which]++;
+  } else {
+    free(p);
+  }
+}
+
+/* gzip member header at byte `at` (RFC 1952); returns the byte after it, 0 on error */
+static uint64_t gzip_header(pgz *z, uint64_t at) {
+  const uint8_t *d = z->data;
+  const uint64_t n = z->n;
+  if (at + 10 > n) { fail(z, "truncated gzip header", at); return 0; }
+  if (d[at] != 0x1f || d[at + 1] != 0x8b) { fail(z, "not a gzip member (bad magic number)", at); return 0; }
+  if (d[at + 2] != 8) { fail(z, "unknown compression method", at); return 0; }
+  const int flg = d[at + 3];
+  uint64_t p = at + 10;
+  if (flg & 4) {
+    if (p + 2 > n) { fail(z, "truncated gzip header", at); return 0; }
+    p += 2 + (uint64_t)(d[p] | (d[p + 1] << 8));
+  }
+  if (flg & 8) { while (p < n && d[p]) ++p; ++p; }
+  if (flg & 16) { while (p < n && d[p]) ++p; ++p; }
+  if (flg & 2) p += 2;
+  if (p > n) { fail(z, "truncated gzip header", at); return 0; }
+  return p;
+}
+
+static void chunk_release(pgz *z, chunk *c) { /* buffers back to the pools */
+  pool_give(z, 0, c->sym, c->cap);
+  pool_give(z, 1, c->bytes, c->bytes_cap);
+  c->sym = NULL;
+  c->bytes = NULL;
+}
+
+static void prefix_unknown(chunk *c) {
+  for (int i = 0; i < WIN; ++i) c->sym[i] = (uint16_t)(256 + i);
+  c->known = 0;
+}
+static void prefix_known(chunk *c, const uint8_t *win, int empty) {
+  for (int i = 0; i < WIN; ++i) c->sym[i] = win[i];
+  c->known = empty ? 2 : 1;
+}
+
+static int chunk_alloc(pgz *z, chunk *c, uint64_t est_out) {
+  memset(c, 0, sizeof(*c));
+  c->sym = (uint16_t *)pool_take(z, 0, WIN + est_out + 1024, &c->cap);
+  return c->sym ? 0 : -1;
+}
+
+/* One wave: up to `threads` chunks decoded in parallel from z->pos on.  Fills z->out. */
+static int run_wave(pgz *z) {
+  const uint8_t *data = z->data;
+  const uint64_t n = z->n;
+  for (int i = 0; i < z->n_out; ++i) chunk_release(z, &z->out[i]);
+  free(z->out);
+  z->out = NULL;
+  z->n_out = z->cur_out = 0;
+  z->cur_off = 0;
+  if (!z->in_member) {
+    uint64_t at = z->pos >> 3;
+    while (at < n && data[at] == 0) ++at; /* zero padding between / after members */
+    if (at >= n) { z->eof = 1; return 0; }
+    const uint64_t body = gzip_header(z, at);
+    if (!body) return -1;
+    z->pos = body * 8;
+    z->in_member = 1;
+    z->member_len = 0;
+    z->member_crc = 0;
+    memset(z->window, 0, WIN);
+    /* (the window of a new member is empty: marked by known = 2 on its first chunk) */
+  }
+  const int new_member = z->member_len == 0;
+  const int T = z->threads;
+  const uint64_t S = z->chunk_bytes;
+  const uint64_t w0 = z->pos >> 3;
+  uint64_t w1 = w0 + (uint64_t)T * S;
+  if (w1 > n) w1 = n;
+  const uint64_t est = S * 8;
+  /* 1. candidate starts near every cut */
+  uint64_t *cand = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(T + 1));
+  chunk *ch = (chunk *)calloc((size_t)T + 1, sizeof(chunk));
+  if (!cand || !ch) { free(cand); free(ch); return fail(z, "out of memory", w0); }
+  int n_cut = 0;
+  for (int k = 1; k < T; ++k)
+    if (w0 + (uint64_t)k * S + 64 < w1) n_cut = k;
+  uint64_t *found = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(n_cut + 1));
+  if (!found) { free(cand); free(ch); return fail(z, "out of memory", w0); }
+  double t0 = omp_get_wtime();
+#pragma omp parallel for schedule(dynamic, 1) num_threads(T)
+  for (int k = 1; k <= n_cut; ++k) {
+    const uint64_t from = (w0 + (uint64_t)k * S) * 8;
+    uint64_t to = from + S * 8;
+    if (to > w1 * 8) to = w1 * 8;
+    found[k] = find_block(data, n, from, to);
+  }
+  int n_cand = 0;
+  for (int k = 1; k <= n_cut; ++k)
+    if (found[k] != UINT64_MAX && (n_cand == 0 || found[k] > cand[n_cand - 1])) cand[n_cand++] = found[k];
+  free(found);
+  z->t_find += omp_get_wtime() - t0; t0 = omp_get_wtime();
+  /* 2. decode: chunk 0 from the known position with the known window, chunk j + 1 from candidate j, unknown window */
+  const uint64_t limit_bit = w1 < n ? w1 * 8 : UINT64_MAX; /* the last wave runs to the final block */
+  int alloc_fail = 0;
+  for (int k = 0; k <= n_cand; ++k)
+    if (chunk_alloc(z, &ch[k], est)) alloc_fail = 1;
+  if (alloc_fail) {
+    for (int k = 0; k <= n_cand; ++k) chunk_release(z, &ch[k]);
+    free(cand); free(ch);
+    return fail(z, "out of memory", w0);
+  }
+#pragma omp parallel for schedule(dynamic, 1) num_threads(T)
+  for (int k = 0; k <= n_cand; ++k) {
+    chunk *c = &ch[k];
+    if (k == 0) {
+      c->start_bit = z->pos;
+      prefix_known(c, z->window, new_member);
+      chunk_decode(c, data, n, cand, n_cand, 0, limit_bit);
+    } else {
+      c->start_bit = cand[k - 1];
+      c->max_out = 64 * S + (64u << 20);
+      prefix_unknown(c);
+      chunk_decode(c, data, n, cand, n_cand, k, limit_bit);
+    }
+  }
+  z->t_decode += omp_get_wtime() - t0; t0 = omp_get_wtime();
+  /* 3. the chain: which chunks are real; a speculative chunk that failed is re-decoded here from where the chain
+   *    stands (its candidate was a real boundary, the chain landed on it, so the failure is the stream's) */
+  chunk *acc = (chunk *)calloc((size_t)n_cand + 2, sizeof(chunk));
+  if (!acc) { for (int k = 0; k <= n_cand; ++k) chunk_release(z, &ch[k]); free(cand); free(ch); return fail(z, "out of memory", w0); }
+  int n_acc = 0, k = 0, rc = 0, ended_final = 0;
+  uint64_t next_pos = z->pos;
+  for (;;) {
+    chunk *c = &ch[k];
+    if (c->end_kind == END_ERROR && c->err == -20) {
+      /* the chain landed on this start, so it is real: decode it again without the speculative output limit */
+      c->max_out = 0;
+      prefix_unknown(c);
+      chunk_decode(c, data, n, cand, n_cand, k, limit_bit);
+      z->serial_repairs++;
+    }
+    if (c->end_kind == END_ERROR) {
+      /* everything before this chunk is accepted and its start is a real block boundary: the error is the stream's
+       * (decoding with an unknown window fails exactly where decoding with the real one would) */
+      rc = fail(z, c->err == -18 || c->err == -13 ? "compressed file ended before the end-of-stream marker was reached"
+                                                  : "invalid deflate data", c->end_bit >> 3);
+      break;
+    }
+    acc[n_acc++] = *c;
+    memset(c, 0, sizeof(*c)); /* ownership moved */
+    chunk *a = &acc[n_acc - 1];
+    next_pos = a->end_bit;
+    if (a->end_kind == END_HIT) { z->chunks_wasted += (uint64_t)(a->hit - k); k = a->hit + 1; continue; } /* chunks k+1..hit: bogus starts */
+    if (a->end_kind == END_FINAL) ended_final = 1;
+    break;
+  }
+  for (int s = 0; s <= n_cand; ++s)
+    if (ch[s].sym) { chunk_release(z, &ch[s]); }
+  free(ch);
+  free(cand);
+  if (rc) { for (int s = 0; s < n_acc; ++s) chunk_release(z, &acc[s]); free(acc); return rc; }
+  /* 4. windows (serial over the tails), then markers -> bytes and CRC in parallel */
+  uint8_t *wins = (uint8_t *)malloc((size_t)WIN * (size_t)(n_acc + 1));
+  if (!wins) { for (int s = 0; s < n_acc; ++s) chunk_release(z, &acc[s]); free(acc); return fail(z, "out of memory", w0); }
+  memcpy(wins, z->window, WIN);
+  for (int s = 0; s < n_acc; ++s) {
+    const uint8_t *win = wins + (size_t)WIN * s;
+    uint8_t *nw = wins + (size_t)WIN * (s + 1);
+    const chunk *a = &acc[s];
+    if (a->n >= WIN) {
+      const uint16_t *t = a->sym + WIN + (a->n - WIN);
+      for (int i = 0; i < WIN; ++i) nw[i] = t[i] < 256 ? (uint8_t)t[i] : win[t[i] - 256];
+    } else {
+      const uint64_t keep = WIN - a->n;
+      memcpy(nw, win + a->n, keep);
+      const uint16_t *t = a->sym + WIN;
+      for (uint64_t i = 0; i < a->n; ++i) nw[keep + i] = t[i] < 256 ? (uint8_t)t[i] : win[t[i] - 256];
+    }
+  }
+  z->t_chain += omp_get_wtime() - t0; t0 = omp_get_wtime();
+  int oom = 0;
+  for (int s = 0; s < n_acc; ++s) {
+    acc[s].bytes = (uint8_t *)pool_take(z, 1, acc[s].n + 8, &acc[s].bytes_cap);
+    if (!acc[s].bytes) oom = 1;
+  }
+#pragma omp parallel for schedule(dynamic, 1) num_threads(T)
+  for (int s = 0; s < n_acc; ++s) {
+    chunk *a = &acc[s];
+    if (oom) continue;
+    const uint8_t *win = wins + (size_t)WIN * s;
+    const uint16_t *t = a->sym + WIN;
+    uint8_t *o = a->bytes;
+    uint64_t i = 0;
+    for (; i + 8 <= a->n; i += 8) { /* eight symbols at a time; markers are rare beyond a chunk's first 32 KB */
+      uint64_t lo, hi;
+      memcpy(&lo, t + i, 8);
+      memcpy(&hi, t + i + 4, 8);
+      if (((lo | hi) & 0xFF00FF00FF00FF00ull) == 0) {
+        lo = (lo | (lo >> 8)) & 0x0000FFFF0000FFFFull;
+        lo = (lo | (lo >> 16)) & 0x00000000FFFFFFFFull;
+        hi = (hi | (hi >> 8)) & 0x0000FFFF0000FFFFull;
+        hi = (hi | (hi >> 16)) & 0x00000000FFFFFFFFull;
+        const uint64_t v = lo | (hi << 32);
+        memcpy(o + i, &v, 8);
+      } else {
+        for (int q = 0; q < 8; ++q) o[i + q] = t[i + q] < 256 ? (uint8_t)t[i + q] : win[t[i + q] - 256];
+      }
+    }
+    for (; i < a->n; ++i) o[i] = t[i] < 256 ? (uint8_t)t[i] : win[t[i] - 256];
+    a->crc = crc32_buf(0, a->bytes, a->n);
+  }
+  for (int s = 0; s < n_acc; ++s) { pool_give(z, 0, acc[s].sym, acc[s].cap); acc[s].sym = NULL; }
+  memcpy(z->window, wins + (size_t)WIN * n_acc, WIN);
+  free(wins);
+  z->t_resolve += omp_get_wtime() - t0;
+  if (oom) { for (int s = 0; s < n_acc; ++s) chunk_release(z, &acc[s]); free(acc); return fail(z, "out of memory", w0); }
+  for (int s = 0; s < n_acc; ++s) {
+    z->member_crc = crc32_comb(z->member_crc, acc[s].crc, acc[s].n);
+    z->member_len += acc[s].n;
+  }
+  z->chunks_used += (uint64_t)n_acc;
+  z->waves++;
+  z->out = acc;
+  z->n_out = n_acc;
+  z->pos = next_pos;
+  if (ended_final) {
+    /* gzip trailer: CRC-32 and ISIZE, little endian, at the next byte boundary */
+    const uint64_t at = (next_pos + 7) >> 3;
+    if (at + 8 > n) return fail(z, "compressed file ended before the end-of-stream marker was reached", at);
+    uint32_t crc, isz;
+    memcpy(&crc, data + at, 4);
+    memcpy(&isz, data + at + 4, 4);
+    if (crc != z->member_crc) return fail(z, "CRC check failed", at);
+    if (isz != (uint32_t)(z->member_len & 0xFFFFFFFFu)) return fail(z, "incorrect length of data produced", at);
+    z->pos = (at + 8) * 8;
+    z->in_member = 0;
+  } else if (w1 >= n) {
+    return fail(z, "compressed file ended before the end-of-stream marker was reached", n);
+  }
+  return 0;
+}
+
+/* ------------------------------------------------------------------ C ABI (ctypes: ingest.py) ------- */
+__attribute__((constructor)) static void pgz_init_tables(void) {
+  crc_tables();
+  fixed_tables();
+}
+
+void *pgz_open(const uint8_t *data, uint64_t n, int threads, uint64_t chunk_bytes) {
+  if (!g_fixed_ready) return NULL;
+  pgz *z = (pgz *)calloc(1, sizeof(pgz));
+  if (!z) return NULL;
+  z->data = data;
+  z->n = n;
+  z->threads = threads < 1 ? 1 : threads;
+  z->chunk_bytes = chunk_bytes < 65536 ? 65536 : chunk_bytes;
+  return z;
+}
+
+/* next decompressed bytes into dst (at most cap): > 0 bytes written, 0 end of file, < 0 error (pgz_error) */
+int64_t pgz_read(void *h, uint8_t *dst, uint64_t cap) {
+  pgz *z = (pgz *)h;
+  uint64_t got = 0;
+  while (got < cap) {
+    if (z->cur_out < z->n_out) {
+      chunk *a = &z->out[z->cur_out];
+      uint64_t k = a->n - z->cur_off;
+      if (k > cap - got) k = cap - got;
+      memcpy(dst + got, a->bytes + z->cur_off, k);
+      got += k;
+      z->cur_off += k;
+      if (z->cur_off == a->n) { pool_give(z, 1, a->bytes, a->bytes_cap); a->bytes = NULL; z->cur_out++; z->cur_off = 0; }
+      continue;
+    }
+    if (z->eof) break;
+    if (got) break; /* hand over what is there before the next wave blocks */
+    if (run_wave(z)) return -1;
+  }
+  z->total_out += got;
+  return (int64_t)got;
+}
+
+const char *pgz_error(void *h) { return ((pgz *)h)->err; }
+
+void pgz_stats(void *h, uint64_t *out4) {
+  pgz *z = (pgz *)h;
+  out4[0] = z->waves; out4[1] = z->chunks_used; out4[2] = z->chunks_wasted; out4[3] = z->total_out;
+}
+
+/* seconds spent looking for block starts, decoding, chaining windows, resolving markers + CRC */
+void pgz_times(void *h, double *out4) {
+  pgz *z = (pgz *)h;
+  out4[0] = z->t_find; out4[1] = z->t_decode; out4[2] = z->t_chain; out4[3] = z->t_resolve;
+}
+
+void pgz_close(void *h) {
+  pgz *z = (pgz *)h;
+  if (!z) return;
+  for (int i = 0; i < z->n_out; ++i) chunk_release(z, &z->out[i]);
+  free(z->out);
+  for (int w = 0; w < 2; ++w)
+    for (int i = 0; i < z->pool_n[w]; ++i) free(z->pool[w][i]);
+  free(z);
+}

@@ -6,8 +6,10 @@ digesting thread wait for the device once per piece, so reading and inflating mu
 
 * every file is read by a worker thread into a bounded queue of chunks; the digesting thread only copies chunks
   into its pinned staging buffers (``readinto``);
-* plain gzip is one DEFLATE stream and is inflated by that one worker (multi-member files and trailing zero
-  padding are handled like Python's ``gzip`` module does);
+* plain gzip is one DEFLATE stream: large files are inflated chunk-parallel by the native decoder of csrc/pinflate.c
+  (block starts searched near every cut, speculative decoding with an unknown window, chained and CRC-checked:
+  libmirge_inflate.so), small ones -- or any file when that library has not been built -- by one worker with zlib
+  (multi-member files and trailing zero padding are handled like Python's ``gzip`` module does either way);
 * BGZF files (bgzip, many sequencing pipelines: gzip members of <= 64 KB that carry their size in a 'BC' extra field)
   are inflated block-parallel on a thread pool (zlib releases the GIL), CRC and size of every block checked;
 * ``SampleReadahead`` keeps the readers of the next samples of a run going while the current one is digested, which
@@ -18,6 +20,8 @@ input raises (EOFError / OSError / zlib.error), like the reference's reader woul
 from __future__ import annotations
 
 import collections
+import ctypes
+import mmap
 import os
 import queue
 import struct
@@ -29,6 +33,9 @@ from typing import Callable, Iterator, List, Optional, Sequence
 CHUNK = 8 << 20  # bytes per queue entry (inflated)
 RAW_READ = 1 << 20  # compressed bytes fed to zlib per call
 BGZF_BATCH = 2 << 20  # compressed bytes per pool task
+PGZ_MIN_BYTES = int(os.environ.get("MIRGE_B200_PARALLEL_GZIP_MIN_MB", "32")) << 20  # smaller gzip files: one zlib worker
+PGZ_CHUNK = int(os.environ.get("MIRGE_B200_PARALLEL_GZIP_CHUNK_KB", "2048")) << 10  # compressed bytes per speculative chunk
+PGZ_LIB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libmirge_inflate.so")
 
 _pool_lock = threading.Lock()
 _pool: Optional[ThreadPoolExecutor] = None
@@ -103,6 +110,76 @@ def _gzip_chunks(path: str) -> Iterator[bytes]:
                     fed = False
                 else:
                     buf = d.unconsumed_tail
+
+
+_pgz = None
+
+
+def parallel_gzip_library():
+    """libmirge_inflate.so (csrc/pinflate.c, built by __graft_entry__.build()) or None when it has not been built or
+    MIRGE_B200_PARALLEL_GZIP=0.  Host-only code: the serial zlib reader gives the same bytes without it."""
+    global _pgz
+    if os.environ.get("MIRGE_B200_PARALLEL_GZIP", "1") == "0":
+        return None
+    if _pgz is None:
+        if not os.path.exists(PGZ_LIB):
+            return None
+        lib = ctypes.CDLL(PGZ_LIB)
+        lib.pgz_open.restype = ctypes.c_void_p
+        lib.pgz_open.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int, ctypes.c_uint64]
+        lib.pgz_read.restype = ctypes.c_int64
+        lib.pgz_read.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        lib.pgz_error.restype = ctypes.c_char_p
+        lib.pgz_error.argtypes = [ctypes.c_void_p]
+        lib.pgz_close.argtypes = [ctypes.c_void_p]
+        lib.pgz_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64)]
+        _pgz = lib
+    return _pgz
+
+
+def _pgzip_chunks(path: str, threads: Optional[int] = None, chunk_bytes: Optional[int] = None) -> Iterator[bytes]:
+    """One gzip stream inflated on ``threads`` cores (csrc/pinflate.c); same bytes and the same kinds of errors as
+    _gzip_chunks: EOFError for a truncated file, OSError for CRC / length / header problems, zlib.error for bad data."""
+    lib = parallel_gzip_library()
+    with open(path, "rb") as f:
+        size = os.fstat(f.fileno()).st_size
+        if size == 0:
+            return
+        mm = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)
+    try:
+        if hasattr(mm, "madvise") and hasattr(mmap, "MADV_SEQUENTIAL"):
+            mm.madvise(mmap.MADV_SEQUENTIAL)
+        addr = _address_of(mm)  # (no copy: the decoder reads the mapping)
+        h = lib.pgz_open(addr, size, int(threads or default_threads()), int(chunk_bytes or PGZ_CHUNK))
+        if not h:
+            raise MemoryError("parallel gzip reader: out of memory")
+        try:
+            while True:
+                out = bytearray(CHUNK)
+                dst = (ctypes.c_ubyte * CHUNK).from_buffer(out)
+                k = lib.pgz_read(h, dst, CHUNK)
+                del dst
+                if k < 0:
+                    msg = lib.pgz_error(h).decode("latin-1") + ": " + path
+                    if "ended before" in msg:
+                        raise EOFError(msg)
+                    if "invalid deflate" in msg:
+                        raise zlib.error(msg)
+                    raise OSError(msg)
+                if k == 0:
+                    return
+                yield memoryview(out)[:k]
+        finally:
+            lib.pgz_close(h)
+    finally:
+        mm.close()
+
+
+def _address_of(mm: "mmap.mmap") -> int:
+    """address of a read-only mapping (ctypes' from_buffer wants a writable buffer; numpy takes any)"""
+    import numpy as np
+
+    return int(np.frombuffer(mm, dtype=np.uint8).ctypes.data)
 
 
 def _read_exact(f, n: int, path: str) -> bytes:
@@ -337,6 +414,13 @@ def open_fastq(path: str, threads: Optional[int] = None, depth: int = 4):
     if kind == "bgzf":
         return ChunkReader(lambda: _bgzf_chunks(path, threads), depth, name=path)
     if kind == "gzip":
+        big = os.path.isfile(path) and os.path.getsize(path) >= PGZ_MIN_BYTES
+        if big and int(threads or default_threads()) > 1 and parallel_gzip_library() is not None:
+            # the decoder works in waves of threads x PGZ_CHUNK compressed bytes and only starts the next wave when the
+            # previous one has been handed over: the queue must hold a wave's output (about 4x its input for FASTQ) for
+            # decoding and consumption to overlap
+            wave_out = 4 * int(threads or default_threads()) * PGZ_CHUNK
+            return ChunkReader(lambda: _pgzip_chunks(path, threads), max(depth, -(-2 * wave_out // CHUNK)), name=path)
         return ChunkReader(lambda: _gzip_chunks(path), depth, name=path)
     return ChunkReader(lambda: _plain_chunks(path), depth, name=path)
 

@@ -236,3 +236,121 @@ def test_plain_reader_parallel_positional_reads(tmp_path):
     empty.write_bytes(b"")
     with ingest.open_fastq(str(empty)) as r0:
         assert r0.read() == b""
+
+
+# ---- chunk-parallel inflate of single-stream gzip (csrc/pinflate.c -> libmirge_inflate.so) ---------------------------
+
+
+def _parallel(monkeypatch, chunk_kb=64):
+    if ingest.parallel_gzip_library() is None:
+        pytest.skip("libmirge_inflate.so not built (run __graft_entry__.build())")
+    monkeypatch.setattr(ingest, "PGZ_MIN_BYTES", 0)
+    monkeypatch.setattr(ingest, "PGZ_CHUNK", chunk_kb << 10)
+
+
+@pytest.mark.parametrize("kind", ["gzip", "members", "padded", "empty_gz"])
+@pytest.mark.parametrize("threads,chunk_kb", [(2, 64), (5, 64), (8, 256)])
+def test_parallel_gzip_reader_returns_the_stream(files, monkeypatch, kind, threads, chunk_kb):
+    """The native chunk-parallel decoder gives exactly what Python's gzip module (the reference's xopen fallback) gives,
+    for single streams, concatenated members (incl. 1-byte and empty ones) and zero padding."""
+    d, data, paths = files
+    _parallel(monkeypatch, chunk_kb)
+    r = ingest.open_fastq(paths[kind], threads=threads)
+    with r:
+        got = read_all(r, 777_777)
+    assert got == gzip.open(paths[kind], "rb").read()
+
+
+def test_parallel_gzip_reader_on_every_block_type(tmp_path, monkeypatch):
+    """Stored, fixed-Huffman and dynamic blocks, sync / full flush points, tiny blocks (memLevel 1), runs with distance 1,
+    incompressible bytes, a gzip header with a file name: many speculative chunks per file, every one chained and
+    CRC-checked against the trailer."""
+    _parallel(monkeypatch, 64)
+    rng = np.random.default_rng(5)
+    fq = random_fastq(60000, seed=8)
+
+    def gz(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, memlevel=8):
+        c = zlib.compressobj(level, zlib.DEFLATED, 31, memlevel, strategy)
+        return c.compress(data) + c.flush()
+
+    def flushed(data, step=300_000):
+        c = zlib.compressobj(6, zlib.DEFLATED, 31)
+        out = []
+        for i in range(0, len(data), step):
+            out.append(c.compress(data[i : i + step]))
+            out.append(c.flush(zlib.Z_FULL_FLUSH if (i // step) % 2 else zlib.Z_SYNC_FLUSH))
+        return b"".join(out) + c.flush()
+
+    import io
+
+    named = io.BytesIO()
+    with gzip.GzipFile(filename="sample_R1.fastq", mode="wb", fileobj=named, mtime=0) as f:
+        f.write(fq[:2_000_000])
+    cases = {
+        "level1": gz(fq, 1), "level9": gz(fq, 9), "fixed": gz(fq[:3_000_000], strategy=zlib.Z_FIXED),
+        "huffman_only": gz(fq[:3_000_000], strategy=zlib.Z_HUFFMAN_ONLY), "rle": gz(fq[:3_000_000], strategy=zlib.Z_RLE),
+        "stored": gz(fq[:3_000_000], 0), "small_blocks": gz(fq[:4_000_000], memlevel=1), "zeros": gz(bytes(20_000_000)),
+        "random": gz(rng.integers(0, 256, 2_000_000, dtype=np.uint8).tobytes()), "repeats": gz(b"ACGTACGTTTGACCA\n" * 500_000, 9),
+        "flushes": flushed(fq[:4_000_000]), "named": named.getvalue(),
+        "mixed_members": gz(fq[:2_000_000]) + gz(fq[2_000_000:2_000_001]) + gz(b"") + gz(fq[2_000_001:5_000_000], 1) + bytes(99),
+    }
+    for name, comp in cases.items():
+        p = tmp_path / (name + ".gz")
+        p.write_bytes(comp)
+        with ingest.open_fastq(str(p), threads=6) as r:
+            got = read_all(r, 1 << 20)
+        assert got == gzip.decompress(comp), name
+
+
+def test_parallel_gzip_reader_errors(files, monkeypatch):
+    d, data, paths = files
+    _parallel(monkeypatch, 64)
+    raw = open(paths["gzip"], "rb").read()
+
+    def reading(blob, name):
+        p = str(d / name)
+        open(p, "wb").write(blob)
+        with ingest.open_fastq(p, threads=4) as r:
+            return read_all(r, 1 << 20)
+
+    with pytest.raises(EOFError):
+        reading(raw[: len(raw) // 2], "p_trunc.gz")
+    with pytest.raises(EOFError):
+        reading(raw[:-3], "p_trunc_trailer.gz")
+    bad = bytearray(raw)
+    bad[len(raw) // 2] ^= 0x10
+    with pytest.raises((OSError, zlib.error)):  # invalid code, or the CRC at the end
+        reading(bytes(bad), "p_flip.gz")
+    bad = bytearray(raw)
+    bad[-6] ^= 1
+    with pytest.raises(OSError):
+        reading(bytes(bad), "p_crc.gz")
+    bad = bytearray(raw)
+    bad[-1] ^= 1
+    with pytest.raises(OSError):
+        reading(bytes(bad), "p_isize.gz")
+    with pytest.raises((OSError, zlib.error)):
+        reading(raw + b"not gzip", "p_garbage.gz")
+
+
+def test_parallel_gzip_is_only_used_for_large_files(files, monkeypatch):
+    d, data, paths = files
+    if ingest.parallel_gzip_library() is None:
+        pytest.skip("libmirge_inflate.so not built")
+    calls = []
+    real = ingest._pgzip_chunks
+    monkeypatch.setattr(ingest, "_pgzip_chunks", lambda *a, **k: (calls.append(a), real(*a, **k))[1])
+    with ingest.open_fastq(paths["gzip"], threads=4) as r:  # 1 MB: below PGZ_MIN_BYTES
+        read_all(r, 1 << 20)
+    assert not calls
+    monkeypatch.setattr(ingest, "PGZ_MIN_BYTES", 0)
+    with ingest.open_fastq(paths["gzip"], threads=1) as r:  # one thread: nothing to parallelise
+        read_all(r, 1 << 20)
+    assert not calls
+    with ingest.open_fastq(paths["gzip"], threads=4) as r:
+        assert read_all(r, 1 << 20) == data
+    assert len(calls) == 1
+    monkeypatch.setenv("MIRGE_B200_PARALLEL_GZIP", "0")
+    with ingest.open_fastq(paths["gzip"], threads=4) as r:
+        assert read_all(r, 1 << 20) == data
+    assert len(calls) == 1
