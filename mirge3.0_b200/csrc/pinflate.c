@@ -20,7 +20,16 @@
  * Multi-member files and zero padding between members are handled as Python's gzip module does.  Host-only code (no
  * CUDA): built by __graft_entry__.build() with gcc -fopenmp into libmirge_inflate.so and bound by ingest.py; when the
  * library is missing ingest.py keeps its serial zlib reader (same bytes, slower).  */
+#ifdef _OPENMP
 #include <omp.h>
+#else /* built without OpenMP: the same decoder on one core (the pragmas are ignored) */
+#include <time.h>
+static double omp_get_wtime(void) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
+}
+#endif
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -28,8 +37,8 @@
 
 #define WIN 32768
 #define MAXBITS 15
-#define LIT_PB 10 /* primary table bits, literal/length code */
-#define DST_PB 8  /* primary table bits, distance code */
+#define LIT_PB 11 /* primary table bits, literal/length code */
+#define DST_PB 9  /* primary table bits, distance code */
 #define POOL_MAX 512
 
 /* ------------------------------------------------------------------ bit reader ------- */
@@ -281,7 +290,7 @@ static void chunk_decode(chunk *c, const uint8_t *data, uint64_t nbytes, const u
         br_refill(&b);
         if (b.pos > nbytes + 16) { bad = -18; break; } /* reading zeros beyond the end of the file */
         {
-          /* runs of literals: up to four primary-table codes (<= 10 bits each) per refill */
+          /* runs of literals: up to four primary-table codes (<= LIT_PB = 11 bits each) per refill of >= 56 bits */
           uint16_t e = L->fast[br_peek(&b, LIT_PB)];
           if (e && e < (256u << 4)) {
             br_drop(&b, e & 15); c->sym[o++] = (uint16_t)(e >> 4);
