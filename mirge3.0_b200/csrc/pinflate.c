@@ -415,6 +415,7 @@ typedef struct {
   const uint8_t *data;
   uint64_t n;
   int threads;
+  int wave_factor;
   uint64_t chunk_bytes;
   /* position: next wave starts at bit `pos` inside a member (in_member) or at byte `pos / 8` between members */
   uint64_t pos;
@@ -539,17 +540,18 @@ static int run_wave(pgz *z) {
   }
   const int new_member = z->member_len == 0;
   const int T = z->threads;
+  const int K = T == 1 ? 1 : T * z->wave_factor; /* chunks per wave: more than threads, so that unequal chunks even out */
   const uint64_t S = z->chunk_bytes;
   const uint64_t w0 = z->pos >> 3;
-  uint64_t w1 = w0 + (uint64_t)T * S;
+  uint64_t w1 = w0 + (uint64_t)K * S;
   if (w1 > n) w1 = n;
   const uint64_t est = S * 8;
   /* 1. candidate starts near every cut */
-  uint64_t *cand = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(T + 1));
-  chunk *ch = (chunk *)calloc((size_t)T + 1, sizeof(chunk));
+  uint64_t *cand = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(K + 1));
+  chunk *ch = (chunk *)calloc((size_t)K + 1, sizeof(chunk));
   if (!cand || !ch) { free(cand); free(ch); return fail(z, "out of memory", w0); }
   int n_cut = 0;
-  for (int k = 1; k < T; ++k)
+  for (int k = 1; k < K; ++k)
     if (w0 + (uint64_t)k * S + 64 < w1) n_cut = k;
   uint64_t *found = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(n_cut + 1));
   if (!found) { free(cand); free(ch); return fail(z, "out of memory", w0); }
@@ -657,8 +659,11 @@ static int run_wave(pgz *z) {
     const uint8_t *win = wins + (size_t)WIN * s;
     const uint16_t *t = a->sym + WIN;
     uint8_t *o = a->bytes;
-    uint64_t i = 0;
-    for (; i + 8 <= a->n; i += 8) { /* eight symbols at a time; markers are rare beyond a chunk's first 32 KB */
+    uint32_t crc = 0;
+    for (uint64_t blk = 0; blk < a->n; blk += 32768) { /* block-wise: the CRC reads the bytes while they are in cache */
+    const uint64_t blk_end = blk + 32768 < a->n ? blk + 32768 : a->n;
+    uint64_t i = blk;
+    for (; i + 8 <= blk_end; i += 8) { /* eight symbols at a time; markers are rare beyond a chunk's first 32 KB */
       uint64_t lo, hi;
       memcpy(&lo, t + i, 8);
       memcpy(&hi, t + i + 4, 8);
@@ -673,8 +678,10 @@ static int run_wave(pgz *z) {
         for (int q = 0; q < 8; ++q) o[i + q] = t[i + q] < 256 ? (uint8_t)t[i + q] : win[t[i + q] - 256];
       }
     }
-    for (; i < a->n; ++i) o[i] = t[i] < 256 ? (uint8_t)t[i] : win[t[i] - 256];
-    a->crc = crc32_buf(0, a->bytes, a->n);
+    for (; i < blk_end; ++i) o[i] = t[i] < 256 ? (uint8_t)t[i] : win[t[i] - 256];
+    crc = crc32_buf(crc, o + blk, blk_end - blk);
+    }
+    a->crc = crc;
   }
   for (int s = 0; s < n_acc; ++s) { pool_give(z, 0, acc[s].sym, acc[s].cap); acc[s].sym = NULL; }
   memcpy(z->window, wins + (size_t)WIN * n_acc, WIN);
@@ -720,6 +727,11 @@ void *pgz_open(const uint8_t *data, uint64_t n, int threads, uint64_t chunk_byte
   z->data = data;
   z->n = n;
   z->threads = threads < 1 ? 1 : threads;
+  {
+    const char *e = getenv("MIRGE_B200_PGZ_WAVE_FACTOR");
+    z->wave_factor = e ? atoi(e) : 1; /* (2 and 4 measured: no gain on 8 threads, twice / four times the buffers) */
+    if (z->wave_factor < 1 || z->wave_factor > 16) z->wave_factor = 1;
+  }
   z->chunk_bytes = chunk_bytes < 65536 ? 65536 : chunk_bytes;
   return z;
 }
