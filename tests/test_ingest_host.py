@@ -354,3 +354,55 @@ def test_parallel_gzip_is_only_used_for_large_files(files, monkeypatch):
     with ingest.open_fastq(paths["gzip"], threads=4) as r:
         assert read_all(r, 1 << 20) == data
     assert len(calls) == 1
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_parallel_gzip_reader_fuzz(tmp_path, monkeypatch, seed):
+    """Random data (text, low entropy, periodic, incompressible, mixtures), random members / levels / strategies / window
+    memory / flush points, random thread counts and cut sizes: the parallel decoder returns what zlib returns."""
+    _parallel(monkeypatch, 64)
+    rng = np.random.default_rng(700 + seed)
+
+    def rand_data(n, depth=0):
+        kind = int(rng.integers(0, 5 if depth == 0 else 4))
+        if kind == 0:
+            return random_fastq(n // 150 + 1, seed=int(rng.integers(1 << 30)))[:n]
+        if kind == 1:
+            return rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        if kind == 2:
+            return rng.integers(0, 4, n, dtype=np.uint8).tobytes()
+        if kind == 3:
+            unit = rng.integers(65, 91, int(rng.integers(1, 5000)), dtype=np.uint8).tobytes()
+            return (unit * (n // len(unit) + 1))[:n]
+        parts, tot = [], 0
+        while tot < n:
+            k = int(rng.integers(1, 150_000))
+            parts.append(rand_data(k, 1))
+            tot += k
+        return b"".join(parts)[:n]
+
+    for case in range(3):
+        data = rand_data(int(rng.integers(1, 2_500_000)))
+        cuts = sorted({0, len(data)} | {int(x) for x in rng.integers(0, len(data) + 1, int(rng.integers(0, 3)))})
+        blob = []
+        for a, b in zip(cuts, cuts[1:]):
+            c = zlib.compressobj(int(rng.integers(0, 10)), zlib.DEFLATED, 31, int(rng.integers(1, 10)),
+                                 int(rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED])))
+            p = a
+            while p < b:
+                k = int(rng.integers(1, 300_000))
+                blob.append(c.compress(data[p : min(p + k, b)]))
+                p += k
+                if rng.random() < 0.2:
+                    blob.append(c.flush(int(rng.choice([zlib.Z_SYNC_FLUSH, zlib.Z_FULL_FLUSH]))))
+            blob.append(c.flush())
+            if rng.random() < 0.3:
+                blob.append(bytes(int(rng.integers(1, 40))))
+        comp = b"".join(blob)
+        assert gzip.decompress(comp) == data
+        p = tmp_path / ("f%d_%d.gz" % (seed, case))
+        p.write_bytes(comp)
+        monkeypatch.setattr(ingest, "PGZ_CHUNK", int(rng.choice([64, 128, 512])) << 10)
+        with ingest.open_fastq(str(p), threads=int(rng.integers(2, 9))) as r:
+            got = read_all(r, int(rng.integers(1, 1 << 21)))
+        assert got == data, (seed, case)
