@@ -210,18 +210,25 @@ static void fixed_tables(void) {
 enum { END_HIT = 1, END_FINAL = 2, END_LIMIT = 3, END_ERROR = 4 };
 
 typedef struct {
-  uint16_t *sym;  /* [WIN prefix][output] */
+  /* A speculative chunk is decoded in symbol mode: 16-bit symbols behind a prefix of WIN markers, resolved into bytes
+   * once its window is known.  A chunk whose window is known (the first of every wave) is decoded straight into bytes.
+   * (Changing a speculative chunk to byte mode once WIN marker-free symbols lie behind it was built and measured: on
+   * FASTQ it almost never happens -- the markers of header and separator bytes are copied forward from record to record
+   * for the whole chunk -- and tracking it cost more than it saved.) */
+  uint16_t *sym;  /* [WIN prefix][symbols] */
   uint64_t cap;   /* symbols allocated */
-  uint64_t n;     /* output symbols (after the prefix) */
+  uint64_t n_sym; /* output symbols still to be resolved (0: byte mode) */
+  uint8_t *bytes; /* known window: [WIN window bytes][output]; speculative: filled when the symbols are resolved */
+  uint64_t bytes_cap;
+  uint64_t boff;  /* where the output starts in bytes (WIN or 0) */
+  uint64_t n;     /* output bytes */
   uint64_t start_bit, end_bit;
   int end_kind;
   int hit;        /* END_HIT: index of the candidate the chunk stopped at */
   int err;
-  int known;      /* 1: the prefix holds the real window (no markers can occur), 2: empty window (start of a member) */
-  uint64_t max_out; /* speculative chunks: give up beyond this many symbols (0 = no limit) */
-  uint8_t *bytes; /* resolved output */
-  uint64_t bytes_cap;
-  uint32_t crc;
+  int known;      /* 1: the real window is known (no markers can occur), 2: empty window (start of a member) */
+  uint64_t max_out; /* speculative chunks: give up beyond this much output (0 = no limit) */
+  uint32_t crc; /* of the whole output (computed when the head is resolved; inside the decode loop it cost 3x as much) */
 } chunk;
 
 static int chunk_reserve(chunk *c, uint64_t need_total) {
@@ -234,15 +241,133 @@ static int chunk_reserve(chunk *c, uint64_t need_total) {
   c->cap = nc;
   return 0;
 }
+static int bytes_reserve(chunk *c, uint64_t need_total) {
+  if (need_total <= c->bytes_cap) return 0;
+  uint64_t nc = c->bytes_cap + c->bytes_cap / 2;
+  if (nc < need_total) nc = need_total;
+  uint8_t *p = (uint8_t *)realloc(c->bytes, nc);
+  if (!p) return -1;
+  c->bytes = p;
+  c->bytes_cap = nc;
+  return 0;
+}
+
+/* The symbols of one Huffman block, symbol mode.  *po: write index into c->sym.  0 = end of block reached, < 0 error. */
+static int block_symbols(chunk *c, bitr *b, const huff *L, const huff *D, uint64_t nbytes, uint64_t *po) {
+  uint64_t o = *po;
+  int bad = 0;
+  for (;;) {
+    if (o + 300 > c->cap) {
+      if (c->max_out && o - WIN > c->max_out) { bad = -20; break; } /* a speculative chunk that runs away */
+      if (chunk_reserve(c, o + 300 + c->cap / 2)) { bad = -12; break; }
+    }
+    br_refill(b);
+    if (b->pos > nbytes + 16) { bad = -18; break; } /* reading zeros beyond the end of the file */
+    {
+      /* runs of literals: up to four primary-table codes (<= LIT_PB = 11 bits each) per refill of >= 56 bits */
+      uint16_t e = L->fast[br_peek(b, LIT_PB)];
+      if (e && e < (256u << 4)) {
+        br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 4);
+        e = L->fast[br_peek(b, LIT_PB)];
+        if (e && e < (256u << 4)) {
+          br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 4);
+          e = L->fast[br_peek(b, LIT_PB)];
+          if (e && e < (256u << 4)) {
+            br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 4);
+            e = L->fast[br_peek(b, LIT_PB)];
+            if (e && e < (256u << 4)) { br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 4); }
+          }
+        }
+        continue;
+      }
+    }
+    int s = huff_decode(L, b);
+    if (s < 256) {
+      if (s < 0) { bad = -14; break; }
+      c->sym[o++] = (uint16_t)s;
+      continue;
+    }
+    if (s == 256) break;
+    s -= 257;
+    if (s >= 29) { bad = -15; break; }
+    const uint32_t len = LBASE[s] + br_bits(b, LEXT[s]);
+    const int ds = huff_decode(D, b);
+    if (ds < 0 || ds >= 30) { bad = -16; break; }
+    const uint32_t dist = DBASE[ds] + br_bits(b, DEXT[ds]);
+    uint16_t *w = c->sym + o;
+    const uint16_t *r = w - dist;
+    if (dist >= len) memcpy(w, r, len * sizeof(uint16_t));
+    else for (uint32_t i = 0; i < len; ++i) w[i] = r[i];
+    o += len;
+  }
+  *po = o;
+  return bad;
+}
+
+/* The same in byte mode: *po is the write index into c->bytes (at least WIN bytes of history lie in front of it). */
+static int block_bytes(chunk *c, bitr *b, const huff *L, const huff *D, uint64_t nbytes, uint64_t *po) {
+  uint64_t o = *po;
+  int bad = 0;
+  for (;;) {
+    if (o + 300 > c->bytes_cap) {
+      if (c->max_out && o - c->boff > c->max_out) { bad = -20; break; }
+      if (bytes_reserve(c, o + 300 + c->bytes_cap / 2)) { bad = -12; break; }
+    }
+    br_refill(b);
+    if (b->pos > nbytes + 16) { bad = -18; break; }
+    {
+      uint16_t e = L->fast[br_peek(b, LIT_PB)];
+      if (e && e < (256u << 4)) {
+        br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 4);
+        e = L->fast[br_peek(b, LIT_PB)];
+        if (e && e < (256u << 4)) {
+          br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 4);
+          e = L->fast[br_peek(b, LIT_PB)];
+          if (e && e < (256u << 4)) {
+            br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 4);
+            e = L->fast[br_peek(b, LIT_PB)];
+            if (e && e < (256u << 4)) { br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 4); }
+          }
+        }
+        continue;
+      }
+    }
+    int s = huff_decode(L, b);
+    if (s < 256) {
+      if (s < 0) { bad = -14; break; }
+      c->bytes[o++] = (uint8_t)s;
+      continue;
+    }
+    if (s == 256) break;
+    s -= 257;
+    if (s >= 29) { bad = -15; break; }
+    const uint32_t len = LBASE[s] + br_bits(b, LEXT[s]);
+    const int ds = huff_decode(D, b);
+    if (ds < 0 || ds >= 30) { bad = -16; break; }
+    const uint32_t dist = DBASE[ds] + br_bits(b, DEXT[ds]);
+    if (c->known == 2 && dist > o - c->boff) { bad = -17; break; } /* before the start of the member */
+    uint8_t *w = c->bytes + o;
+    const uint8_t *r = w - dist;
+    if (dist >= len) memcpy(w, r, len);
+    else if (dist == 1) memset(w, r[0], len);
+    else for (uint32_t i = 0; i < len; ++i) w[i] = r[i];
+    o += len;
+  }
+  *po = o;
+  return bad;
+}
 
 /* Decode from c->start_bit.  Stops at a block boundary whose bit position equals cand[j] for some j >= first_cand
  * (END_HIT), or is >= limit_bit once no candidate is left (END_LIMIT), or after the final block (END_FINAL).
- * max_out: give up (END_ERROR) when a speculative chunk produced that much without getting anywhere (0 = no limit). */
+ * c->known != 0: c->bytes[0 .. WIN) holds the window and the output follows it; else c->sym[0 .. WIN) holds markers. */
 static void chunk_decode(chunk *c, const uint8_t *data, uint64_t nbytes, const uint64_t *cand, int n_cand, int first_cand,
                          uint64_t limit_bit) {
   bitr b;
   br_init(&b, data, nbytes, c->start_bit);
-  uint64_t o = WIN; /* write index into c->sym */
+  int byte_mode = c->known != 0;
+  uint64_t o = WIN;  /* write index: into c->sym (symbol mode) or c->bytes (byte mode) */
+  c->boff = byte_mode ? WIN : 0;
+  c->n_sym = 0;
   int j = first_cand;
   huff lit, dst;
   c->end_kind = END_ERROR;
@@ -266,11 +391,16 @@ static void chunk_decode(chunk *c, const uint8_t *data, uint64_t nbytes, const u
       br_refill(&b);
       const uint32_t len = br_bits(&b, 16), nlen = br_bits(&b, 16);
       if ((len ^ 0xFFFFu) != nlen) { c->err = -11; break; }
-      if (chunk_reserve(c, o + len + 16)) { c->err = -12; break; }
       /* the bit buffer holds whole bytes now: hand them back and copy from the stream */
       uint64_t at = br_bitpos(&b) >> 3;
       if (at + len > nbytes) { c->err = -13; break; }
-      for (uint32_t i = 0; i < len; ++i) c->sym[o + i] = data[at + i];
+      if (byte_mode) {
+        if (bytes_reserve(c, o + len + 16)) { c->err = -12; break; }
+        memcpy(c->bytes + o, data + at, len);
+      } else {
+        if (chunk_reserve(c, o + len + 16)) { c->err = -12; break; }
+        for (uint32_t i = 0; i < len; ++i) c->sym[o + i] = data[at + i];
+      }
       o += len;
       br_init(&b, data, nbytes, (at + len) * 8);
     } else {
@@ -281,58 +411,18 @@ static void chunk_decode(chunk *c, const uint8_t *data, uint64_t nbytes, const u
         if ((c->err = dynamic_header(&b, &lit, &dst, 0)) != 0) break;
         L = &lit; D = &dst;
       }
-      int bad = 0;
-      for (;;) {
-        if (o + 300 > c->cap) {
-          if (c->max_out && o - WIN > c->max_out) { bad = -20; break; } /* a speculative chunk that runs away */
-          if (chunk_reserve(c, o + 300 + c->cap / 2)) { bad = -12; break; }
-        }
-        br_refill(&b);
-        if (b.pos > nbytes + 16) { bad = -18; break; } /* reading zeros beyond the end of the file */
-        {
-          /* runs of literals: up to four primary-table codes (<= LIT_PB = 11 bits each) per refill of >= 56 bits */
-          uint16_t e = L->fast[br_peek(&b, LIT_PB)];
-          if (e && e < (256u << 4)) {
-            br_drop(&b, e & 15); c->sym[o++] = (uint16_t)(e >> 4);
-            e = L->fast[br_peek(&b, LIT_PB)];
-            if (e && e < (256u << 4)) {
-              br_drop(&b, e & 15); c->sym[o++] = (uint16_t)(e >> 4);
-              e = L->fast[br_peek(&b, LIT_PB)];
-              if (e && e < (256u << 4)) {
-                br_drop(&b, e & 15); c->sym[o++] = (uint16_t)(e >> 4);
-                e = L->fast[br_peek(&b, LIT_PB)];
-                if (e && e < (256u << 4)) { br_drop(&b, e & 15); c->sym[o++] = (uint16_t)(e >> 4); }
-              }
-            }
-            continue;
-          }
-        }
-        int s = huff_decode(L, &b);
-        if (s < 256) {
-          if (s < 0) { bad = -14; break; }
-          c->sym[o++] = (uint16_t)s;
-          continue;
-        }
-        if (s == 256) break;
-        s -= 257;
-        if (s >= 29) { bad = -15; break; }
-        const uint32_t len = LBASE[s] + br_bits(&b, LEXT[s]);
-        const int ds = huff_decode(D, &b);
-        if (ds < 0 || ds >= 30) { bad = -16; break; }
-        const uint32_t dist = DBASE[ds] + br_bits(&b, DEXT[ds]);
-        if (c->known == 2 && dist > o - WIN) { bad = -17; break; } /* before the start of the member */
-        uint16_t *w = c->sym + o;
-        const uint16_t *r = w - dist;
-        if (dist >= len) memcpy(w, r, len * sizeof(uint16_t));
-        else for (uint32_t i = 0; i < len; ++i) w[i] = r[i];
-        o += len;
-      }
+      const int bad = byte_mode ? block_bytes(c, &b, L, D, nbytes, &o) : block_symbols(c, &b, L, D, nbytes, &o);
       if (bad) { c->err = bad; break; }
       if (br_overrun(&b)) { c->err = -18; break; }
     }
     if (final) { c->end_kind = END_FINAL; break; }
   }
-  c->n = o - WIN;
+  if (byte_mode) {
+    c->n = o - c->boff;
+  } else {
+    c->n = o - WIN;
+    c->n_sym = c->n; /* never left symbol mode: everything is resolved later */
+  }
   c->end_bit = br_bitpos(&b);
 }
 
@@ -506,14 +596,27 @@ static void prefix_unknown(chunk *c) {
   c->known = 0;
 }
 static void prefix_known(chunk *c, const uint8_t *win, int empty) {
-  for (int i = 0; i < WIN; ++i) c->sym[i] = win[i];
+  memcpy(c->bytes, win, WIN);
   c->known = empty ? 2 : 1;
 }
 
-static int chunk_alloc(pgz *z, chunk *c, uint64_t est_out) {
+/* speculative: a symbol buffer for the head (grown on demand: a chunk that never gets marker-free stays in it) and the
+ * byte buffer; known window: the byte buffer only */
+static int chunk_alloc(pgz *z, chunk *c, uint64_t est_out, int speculative) {
   memset(c, 0, sizeof(*c));
-  c->sym = (uint16_t *)pool_take(z, 0, WIN + est_out + 1024, &c->cap);
-  return c->sym ? 0 : -1;
+  if (speculative) {
+    c->sym = (uint16_t *)pool_take(z, 0, WIN + (est_out < (1u << 20) ? est_out : (1u << 20)) + 1024, &c->cap);
+    if (!c->sym) return -1;
+  }
+  c->bytes = (uint8_t *)pool_take(z, 1, WIN + est_out + 1024, &c->bytes_cap);
+  return c->bytes ? 0 : -1;
+}
+
+/* byte i of a chunk's output before / after its head has been resolved */
+static inline uint8_t chunk_byte(const chunk *a, const uint8_t *win, uint64_t i) {
+  if (i >= a->n_sym) return a->bytes[a->boff + i];
+  const uint16_t t = a->sym[WIN + i];
+  return t < 256 ? (uint8_t)t : win[t - 256];
 }
 
 /* One wave: up to `threads` chunks decoded in parallel from z->pos on.  Fills z->out. */
@@ -572,7 +675,7 @@ static int run_wave(pgz *z) {
   const uint64_t limit_bit = w1 < n ? w1 * 8 : UINT64_MAX; /* the last wave runs to the final block */
   int alloc_fail = 0;
   for (int k = 0; k <= n_cand; ++k)
-    if (chunk_alloc(z, &ch[k], est)) alloc_fail = 1;
+    if (chunk_alloc(z, &ch[k], est, k != 0)) alloc_fail = 1;
   if (alloc_fail) {
     for (int k = 0; k <= n_cand; ++k) chunk_release(z, &ch[k]);
     free(cand); free(ch);
@@ -637,49 +740,47 @@ static int run_wave(pgz *z) {
     uint8_t *nw = wins + (size_t)WIN * (s + 1);
     const chunk *a = &acc[s];
     if (a->n >= WIN) {
-      const uint16_t *t = a->sym + WIN + (a->n - WIN);
-      for (int i = 0; i < WIN; ++i) nw[i] = t[i] < 256 ? (uint8_t)t[i] : win[t[i] - 256];
+      if (a->n - a->n_sym >= WIN) memcpy(nw, a->bytes + a->boff + (a->n - WIN), WIN); /* the tail is final already */
+      else for (uint64_t i = 0; i < WIN; ++i) nw[i] = chunk_byte(a, win, a->n - WIN + i);
     } else {
       const uint64_t keep = WIN - a->n;
       memcpy(nw, win + a->n, keep);
-      const uint16_t *t = a->sym + WIN;
-      for (uint64_t i = 0; i < a->n; ++i) nw[keep + i] = t[i] < 256 ? (uint8_t)t[i] : win[t[i] - 256];
+      for (uint64_t i = 0; i < a->n; ++i) nw[keep + i] = chunk_byte(a, win, i);
     }
   }
   z->t_chain += omp_get_wtime() - t0; t0 = omp_get_wtime();
   int oom = 0;
-  for (int s = 0; s < n_acc; ++s) {
-    acc[s].bytes = (uint8_t *)pool_take(z, 1, acc[s].n + 8, &acc[s].bytes_cap);
-    if (!acc[s].bytes) oom = 1;
-  }
+  for (int s = 0; s < n_acc; ++s) /* (a chunk that stayed in symbol mode needs its whole output resolved into bytes) */
+    if (acc[s].n_sym && bytes_reserve(&acc[s], acc[s].boff + acc[s].n + 8)) oom = 1;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(T)
   for (int s = 0; s < n_acc; ++s) {
     chunk *a = &acc[s];
     if (oom) continue;
     const uint8_t *win = wins + (size_t)WIN * s;
-    const uint16_t *t = a->sym + WIN;
-    uint8_t *o = a->bytes;
+    const uint16_t *t = a->sym ? a->sym + WIN : NULL;
+    uint8_t *o = a->bytes + a->boff;
     uint32_t crc = 0;
     for (uint64_t blk = 0; blk < a->n; blk += 32768) { /* block-wise: the CRC reads the bytes while they are in cache */
-    const uint64_t blk_end = blk + 32768 < a->n ? blk + 32768 : a->n;
-    uint64_t i = blk;
-    for (; i + 8 <= blk_end; i += 8) { /* eight symbols at a time; markers are rare beyond a chunk's first 32 KB */
-      uint64_t lo, hi;
-      memcpy(&lo, t + i, 8);
-      memcpy(&hi, t + i + 4, 8);
-      if (((lo | hi) & 0xFF00FF00FF00FF00ull) == 0) {
-        lo = (lo | (lo >> 8)) & 0x0000FFFF0000FFFFull;
-        lo = (lo | (lo >> 16)) & 0x00000000FFFFFFFFull;
-        hi = (hi | (hi >> 8)) & 0x0000FFFF0000FFFFull;
-        hi = (hi | (hi >> 16)) & 0x00000000FFFFFFFFull;
-        const uint64_t v = lo | (hi << 32);
-        memcpy(o + i, &v, 8);
-      } else {
-        for (int q = 0; q < 8; ++q) o[i + q] = t[i + q] < 256 ? (uint8_t)t[i + q] : win[t[i + q] - 256];
+      const uint64_t blk_end = blk + 32768 < a->n ? blk + 32768 : a->n;
+      const uint64_t head_end = blk_end < a->n_sym ? blk_end : a->n_sym; /* symbols of this block still to resolve */
+      uint64_t i = blk;
+      for (; i + 8 <= head_end; i += 8) { /* eight symbols at a time; markers are rare beyond a chunk's first 32 KB */
+        uint64_t lo, hi;
+        memcpy(&lo, t + i, 8);
+        memcpy(&hi, t + i + 4, 8);
+        if (((lo | hi) & 0xFF00FF00FF00FF00ull) == 0) {
+          lo = (lo | (lo >> 8)) & 0x0000FFFF0000FFFFull;
+          lo = (lo | (lo >> 16)) & 0x00000000FFFFFFFFull;
+          hi = (hi | (hi >> 8)) & 0x0000FFFF0000FFFFull;
+          hi = (hi | (hi >> 16)) & 0x00000000FFFFFFFFull;
+          const uint64_t v = lo | (hi << 32);
+          memcpy(o + i, &v, 8);
+        } else {
+          for (int q = 0; q < 8; ++q) o[i + q] = t[i + q] < 256 ? (uint8_t)t[i + q] : win[t[i + q] - 256];
+        }
       }
-    }
-    for (; i < blk_end; ++i) o[i] = t[i] < 256 ? (uint8_t)t[i] : win[t[i] - 256];
-    crc = crc32_buf(crc, o + blk, blk_end - blk);
+      for (; i < head_end; ++i) o[i] = t[i] < 256 ? (uint8_t)t[i] : win[t[i] - 256];
+      crc = crc32_buf(crc, o + blk, blk_end - blk);
     }
     a->crc = crc;
   }
@@ -745,7 +846,7 @@ int64_t pgz_read(void *h, uint8_t *dst, uint64_t cap) {
       chunk *a = &z->out[z->cur_out];
       uint64_t k = a->n - z->cur_off;
       if (k > cap - got) k = cap - got;
-      memcpy(dst + got, a->bytes + z->cur_off, k);
+      memcpy(dst + got, a->bytes + a->boff + z->cur_off, k);
       got += k;
       z->cur_off += k;
       if (z->cur_off == a->n) { pool_give(z, 1, a->bytes, a->bytes_cap); a->bytes = NULL; z->cur_out++; z->cur_off = 0; }
