@@ -406,3 +406,14 @@ def test_parallel_gzip_reader_fuzz(tmp_path, monkeypatch, seed):
         with ingest.open_fastq(str(p), threads=int(rng.integers(2, 9))) as r:
             got = read_all(r, int(rng.integers(1, 1 << 21)))
         assert got == data, (seed, case)
+
+
+def test_inflate_library_is_built_and_exports_its_entry_points():
+    """libmirge_inflate.so (csrc/pinflate.c) is built by __graft_entry__.build(): the five entry points ingest.py binds."""
+    import ctypes
+
+    if not os.path.exists(ingest.PGZ_LIB):
+        pytest.skip("libmirge_inflate.so not built (run __graft_entry__.build())")
+    lib = ctypes.CDLL(ingest.PGZ_LIB)
+    for name in ("pgz_open", "pgz_read", "pgz_error", "pgz_stats", "pgz_times", "pgz_close"):
+        assert hasattr(lib, name), name
