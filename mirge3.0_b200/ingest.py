@@ -462,7 +462,8 @@ class SampleReadahead:
         while self._next <= min(last, len(self.paths) - 1):
             i = self._next
             try:
-                self._readers[i] = open_fastq(self.paths[i], self.threads, self.depth)
+                # the readers of a run share the cores: ahead + 1 of them are at work at once
+                self._readers[i] = open_fastq(self.paths[i], max(1, -(-self.threads // (self.ahead + 1))), self.depth)
             except OSError as e:  # a missing / unreadable file fails when its turn comes, not while it is looked ahead
                 self._readers[i] = e
             self._next += 1
