@@ -409,11 +409,16 @@ def test_parallel_gzip_reader_fuzz(tmp_path, monkeypatch, seed):
 
 
 def test_inflate_library_is_built_and_exports_its_entry_points():
-    """libmirge_inflate.so (csrc/pinflate.c) is built by __graft_entry__.build(): the five entry points ingest.py binds."""
+    """libmirge_inflate.so (csrc/pinflate.c) is built by __graft_entry__.build() and exports what include/mirge_inflate.h declares."""
     import ctypes
 
     if not os.path.exists(ingest.PGZ_LIB):
         pytest.skip("libmirge_inflate.so not built (run __graft_entry__.build())")
+    import re
+
     lib = ctypes.CDLL(ingest.PGZ_LIB)
-    for name in ("pgz_open", "pgz_read", "pgz_error", "pgz_stats", "pgz_times", "pgz_close"):
+    header = open(os.path.join(os.path.dirname(ingest.__file__), "..", "include", "mirge_inflate.h")).read()
+    declared = set(re.findall(r"\b(pgz_[a-z]+)\s*\(", header))
+    assert declared == {"pgz_open", "pgz_read", "pgz_error", "pgz_stats", "pgz_times", "pgz_close"}
+    for name in declared:  # every entry point include/mirge_inflate.h declares
         assert hasattr(lib, name), name
