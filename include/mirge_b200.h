@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define MIRGE_ABI_VERSION 2
+#define MIRGE_ABI_VERSION 3
 
 #define MIRGE_OK 0
 #define MIRGE_ERR_CUDA (-1)     /* CUDA runtime error (message has the cudaError string) */
@@ -73,20 +73,36 @@ extern "C" {
 #define MIRGE_COUNT_HEAD 0    /* count after every modifier, as digest.py:354-373 is written */
 #define MIRGE_COUNT_RELEASE 1 /* count once after the pipeline (released 0.1.x behaviour)   */
 
+/* mirge_adapter.where: cutadapt's Where of the placement (adapters.py; which ends of the alignment are free).
+ * Odd values are the 5' forms (the match and what precedes it are removed), even ones the 3' forms. */
+#define MIRGE_WHERE_BACK 0               /* -a SEQ   anywhere in the read, may hang over its 3' end; read[:start] is kept  */
+#define MIRGE_WHERE_FRONT 1              /* -g SEQ   anywhere, may hang over the 5' end; read[stop:] is kept               */
+#define MIRGE_WHERE_SUFFIX 2             /* -a SEQ$  anchored 3': read and adapter end together                            */
+#define MIRGE_WHERE_PREFIX 3             /* -g ^SEQ  anchored 5': read and adapter start together                          */
+#define MIRGE_WHERE_BACK_NOT_INTERNAL 4  /* -a SEQX  as BACK, but never inside the read                                    */
+#define MIRGE_WHERE_FRONT_NOT_INTERNAL 5 /* -g XSEQ  as FRONT, but never inside the read                                   */
+#define MIRGE_WHERE_IS_FRONT(w) ((w) & 1)
+
+/* mirge_adapter.link of the 5' half of a linked pair = (1 + index of its 3' half) | flags */
 #define MIRGE_LINK_BACK_HALF 0x100
+#define MIRGE_LINK_INDEX_MASK 0xFF
+#define MIRGE_LINK_FRONT_OPTIONAL 0x1000 /* the pair still matches when its 5' half is missing (";optional")               */
+#define MIRGE_LINK_BACK_OPTIONAL 0x2000  /* ... when its 3' half is missing (the default of -a "A...B")                    */
 
 /* One adapter in cutadapt's Aligner terms (restated in oracle/pyoracle.py::locate). */
 typedef struct mirge_adapter {
-  int32_t where;        /* 0 = back (3', -a), 1 = front (5', -g) */
+  int32_t where;        /* MIRGE_WHERE_* */
   int32_t m;            /* adapter length, <= MIRGE_MAX_ADAPTER_LEN */
   int32_t min_overlap;  /* args.overlap, parse.py:90 */
   int32_t indel_cost;   /* 1, or 100000 when --no-indels (cutadapt adapters.py) */
   int32_t wildcard_ref; /* adapter contains IUPAC wildcards and -N was not given */
+  int32_t wildcard_read; /* --match-read-wildcards (parse.py:97): IUPAC characters of the read match as sets */
   int32_t k;            /* int(error_rate * m) */
   int32_t effective_length;
-  int32_t link;         /* 0 = plain adapter; 1 + index of the 3' half = the 5' half of a linked pair (-g "A...B": both
-                         * halves non-anchored and required, cutadapt parser/LinkedAdapter); MIRGE_LINK_BACK_HALF = the 3'
-                         * half of a pair, never searched on its own */
+  int32_t link;         /* 0 = plain adapter; (1 + index of the 3' half) | MIRGE_LINK_*_OPTIONAL = the 5' half of a linked
+                         * pair (cutadapt parser / LinkedAdapter: -g "A...B" both halves non-anchored and required,
+                         * -a "A...B" the 5' half anchored and required, the 3' half optional);
+                         * MIRGE_LINK_BACK_HALF = the 3' half of a pair, never searched on its own */
   uint8_t mask[MIRGE_MAX_ADAPTER_LEN];  /* 4-bit IUPAC set per adapter base (A=1,C=2,G=4,T=8) */
   uint8_t ascii[MIRGE_MAX_ADAPTER_LEN]; /* upper-cased adapter text */
   int32_t n_counts[MIRGE_MAX_ADAPTER_LEN + 1]; /* number of 'N' before position i */

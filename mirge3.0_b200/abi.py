@@ -17,6 +17,9 @@ MOD_NEXTSEQ, MOD_QUALITY, MOD_ADAPTER, MOD_NEND, MOD_CUT = 1, 2, 3, 4, 5
 UMI_NONE, UMI_FLANKS, UMI_QIAGEN = 0, 1, 2
 COMPAT_CUTADAPT23, COMPAT_CUTADAPT4 = 0, 1
 LINK_BACK_HALF = 0x100  # MIRGE_LINK_BACK_HALF
+LINK_INDEX_MASK, LINK_FRONT_OPTIONAL, LINK_BACK_OPTIONAL = 0xFF, 0x1000, 0x2000  # MIRGE_LINK_*
+# MIRGE_WHERE_*
+WHERE = {"back": 0, "front": 1, "suffix": 2, "prefix": 3, "back_not_internal": 4, "front_not_internal": 5}
 COUNT_HEAD, COUNT_RELEASE = 0, 1
 SELECT_LEN_LT26, SELECT_LEN_GT25, SELECT_UNANNOTATED = 0, 1, 2
 
@@ -32,6 +35,7 @@ class Adapter(C.Structure):
         ("min_overlap", C.c_int32),
         ("indel_cost", C.c_int32),
         ("wildcard_ref", C.c_int32),
+        ("wildcard_read", C.c_int32),
         ("k", C.c_int32),
         ("effective_length", C.c_int32),
         ("link", C.c_int32),
@@ -109,7 +113,7 @@ class RoundPolicy(C.Structure):
     ]
 
 
-ABI_VERSION = 2  # MIRGE_ABI_VERSION of include/mirge_b200.h
+ABI_VERSION = 3  # MIRGE_ABI_VERSION of include/mirge_b200.h
 
 # name -> (restype, argtypes); every symbol include/mirge_b200.h declares
 _P = C.c_void_p

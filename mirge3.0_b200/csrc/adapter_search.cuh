@@ -15,12 +15,14 @@
 
 struct DevAdapter {
   int where, m, min_overlap, indel_cost, wildcard_ref, k, effective_length;
-  int link;  // mirge_adapter.link: 0 plain, 1 + index of the 3' half (5' half of a linked pair), MIRGE_LINK_BACK_HALF
+  int link;  // mirge_adapter.link: 0 plain, (1 + index of the 3' half) | MIRGE_LINK_*_OPTIONAL (5' half of a linked pair), MIRGE_LINK_BACK_HALF
   uint64_t peq[5];  // bit i-1 set <=> adapter row i matches read class c (A,C,G,T,other)
   int n_counts[MIRGE_MAX_ADAPTER_LEN + 1];
   int max_err[MIRGE_MAX_ADAPTER_LEN + 1];
   int acc[MIRGE_MAX_ADAPTER_LEN + 1];  // 3' adapters: max errors of a candidate ending in adapter row i, -1 = never
   uint64_t a2;                         // 2-bit text of the adapter (row t at bits 2(t-1)); plain ACGT adapters <= 32 nt
+  int wildcard_read;                   // --match-read-wildcards
+  int general;  // placement other than plain 3' / 5', or read wildcards: searched by locate<MAXM, true>
 };
 struct DevParams {
   int n_mods, kind[MIRGE_MAX_MODS], a[MIRGE_MAX_MODS], b[MIRGE_MAX_MODS], c[MIRGE_MAX_MODS];
@@ -77,14 +79,17 @@ static int fill_dev_params(const mirge_trim_params *p, DevParams &d, int &maxm, 
   for (int a = 0; a < p->n_adapters; ++a) {
     const mirge_adapter *s = &p->adapters[a];
     if (s->m < 1 || s->m > MIRGE_MAX_ADAPTER_LEN) FILL_FAIL("adapter %d length %d unsupported", a, s->m);
-    if (s->where != 0 && s->where != 1) FILL_FAIL("adapter %d: unknown type", a);
+    if (s->where < MIRGE_WHERE_BACK || s->where > MIRGE_WHERE_FRONT_NOT_INTERNAL) FILL_FAIL("adapter %d: unknown type", a);
     DevAdapter *o = &d.ad[a];
     o->where = s->where; o->m = s->m; o->min_overlap = s->min_overlap; o->indel_cost = s->indel_cost;
     o->wildcard_ref = s->wildcard_ref; o->k = s->k; o->effective_length = s->effective_length;
     o->link = s->link;
+    o->wildcard_read = s->wildcard_read ? 1 : 0;
+    o->general = (s->where > MIRGE_WHERE_FRONT || s->wildcard_read) ? 1 : 0;
     if (s->link != 0 && s->link != MIRGE_LINK_BACK_HALF) {
-      const int b = s->link - 1;
-      if (s->where != 1 || b <= a || b >= p->n_adapters || p->adapters[b].where != 0 || p->adapters[b].link != MIRGE_LINK_BACK_HALF)
+      const int b = (s->link & MIRGE_LINK_INDEX_MASK) - 1;
+      if ((s->link & ~(MIRGE_LINK_INDEX_MASK | MIRGE_LINK_FRONT_OPTIONAL | MIRGE_LINK_BACK_OPTIONAL)) || !MIRGE_WHERE_IS_FRONT(s->where) ||
+          b <= a || b >= p->n_adapters || MIRGE_WHERE_IS_FRONT(p->adapters[b].where) || p->adapters[b].link != MIRGE_LINK_BACK_HALF)
         FILL_FAIL("adapter %d: a linked pair is a 5' adapter followed by its 3' half", a);
       if (p->umi_mode == MIRGE_UMI_QIAGEN) FILL_FAIL("linked adapters are not supported with qiagen UMIs");
     }
@@ -108,7 +113,7 @@ static int fill_dev_params(const mirge_trim_params *p, DevParams &d, int &maxm, 
         const uint64_t code = s->ascii[i] == 'A' ? 0 : s->ascii[i] == 'C' ? 1 : s->ascii[i] == 'G' ? 2 : 3;
         o->a2 |= code << (2 * i);
       }
-    if (s->where != 0 || s->indel_cost != 1 || s->m > 32 || s->min_overlap < 1 || s->m + 2 * s->k + 3 > 48) fast_ok = 0;
+    if (s->where != MIRGE_WHERE_BACK || s->wildcard_read || s->indel_cost != 1 || s->m > 32 || s->min_overlap < 1 || s->m + 2 * s->k + 3 > 48) fast_ok = 0;
     if (p->compat != MIRGE_COMPAT_CUTADAPT23) fast_ok = 0;  // the bit-parallel search is built on the matches objective
     if (s->m > maxm) maxm = s->m;
   }
@@ -125,27 +130,66 @@ struct Match { int rstart, rstop, matches, errors; };
 // stays positive: a path has at most MIRGE_MAX_READ_LEN + MAXM steps of -2) -- travel in one word.
 #define MS 12
 #define MM 0xFFF
-template <int MAXM>
+// GEN = false: plain 3' / 5' adapters (-a SEQ / -g SEQ), read characters outside ACGT never match.  GEN = true: every
+// placement cutadapt's Where flags describe (anchored ^SEQ / SEQ$, non-internal XSEQ / SEQX: which ends of the alignment
+// are free decides the first column, the columns that matter and the rows that are candidates) and --match-read-wildcards
+// (the read's IUPAC characters match as sets).  With GEN = false every flag below is a constant of the two plain forms.
+__host__ __device__ __forceinline__ uint32_t iupac_set_upper(uint32_t c) {
+  c &= 0xDFu;  // upper case
+  switch (c) {
+    case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': case 'U': return 8;
+    case 'R': return 5; case 'Y': return 10; case 'S': return 6; case 'W': return 9; case 'K': return 12; case 'M': return 3;
+    case 'B': return 14; case 'D': return 13; case 'H': return 11; case 'V': return 7; case 'N': return 15; default: return 0;
+  }
+}
+
+template <int MAXM, bool GEN>
 __device__ __noinline__ bool locate(const int a, const uint8_t *read, const int n, Match &out) {
   const DevAdapter &ad = c_p.ad[a];
   const int m = ad.m, ic = ad.indel_cost, k = ad.k;
   const bool back = ad.where == 0;
+  const int w = ad.where;
+  const bool start_in_ref = GEN ? (w == MIRGE_WHERE_FRONT || w == MIRGE_WHERE_FRONT_NOT_INTERNAL) : !back;
+  const bool stop_in_ref = GEN ? (w == MIRGE_WHERE_BACK || w == MIRGE_WHERE_BACK_NOT_INTERNAL) : back;
+  const bool start_in_query = GEN ? (w != MIRGE_WHERE_PREFIX && w != MIRGE_WHERE_FRONT_NOT_INTERNAL) : true;
+  const bool stop_in_query = GEN ? (w != MIRGE_WHERE_SUFFIX && w != MIRGE_WHERE_BACK_NOT_INTERNAL) : true;
+  const bool wild_read = GEN && ad.wildcard_read;
+  // an anchored start cannot use more than m + k read bases, an anchored end only the last m + k (Aligner.locate)
+  const int max_n = (!GEN || start_in_query) ? n : min(n, m + k);
+  const int min_n = (!GEN || stop_in_query) ? 0 : max(0, n - m - k);
   const int w_mis = c_p.w_mis, w_indel = c_p.w_indel;
   const int SB = w_indel ? 2048 : 0;
   const uint64_t p0 = ad.peq[0], p1 = ad.peq[1], p2 = ad.peq[2], p3 = ad.peq[3];
   int cost[MAXM + 1], om[MAXM + 1];
 #pragma unroll
   for (int i = 0; i <= MAXM; ++i) {
-    cost[i] = back ? i * ic : 0;
-    om[i] = (((back ? 0 : -i) + OB) << MS) + SB + (back ? i * w_indel : 0);
+    if (!GEN) {
+      cost[i] = back ? i * ic : 0;
+      om[i] = (((back ? 0 : -i) + OB) << MS) + SB + (back ? i * w_indel : 0);
+    } else {
+      int c, o;  // the four cases of the first column (column min_n) in _align.pyx
+      if (!start_in_ref && !start_in_query) { c = max(i, min_n) * ic; o = 0; }
+      else if (start_in_ref && !start_in_query) { c = min_n * ic; o = min(0, min_n - i); }
+      else if (!start_in_ref && start_in_query) { c = i * ic; o = max(0, min_n - i); }
+      else { c = min(i, min_n) * ic; o = min_n - i; }
+      cost[i] = c;
+      om[i] = ((o + OB) << MS) + SB + (start_in_ref ? 0 : i * w_indel);
+    }
   }
   int best_cost = m + n, best_om = (OB << MS) + (w_indel ? 0 : SB), best_ref_stop = m, best_query_stop = n;
   bool stopped = false;
-  for (int j = 1; j <= n; ++j) {
-    const uint32_t rc = base_code_upper(read[j - 1]);
-    const uint64_t eq = rc == 0 ? p0 : rc == 1 ? p1 : rc == 2 ? p2 : rc == 3 ? p3 : 0ull;
+  for (int j = min_n + 1; j <= max_n; ++j) {
+    uint64_t eq;
+    if (wild_read) {
+      const uint32_t rs = iupac_set_upper(read[j - 1]);
+      eq = ((rs & 1u) ? p0 : 0ull) | ((rs & 2u) ? p1 : 0ull) | ((rs & 4u) ? p2 : 0ull) | ((rs & 8u) ? p3 : 0ull);
+    } else {
+      const uint32_t rc = base_code_upper(read[j - 1]);
+      eq = rc == 0 ? p0 : rc == 1 ? p1 : rc == 2 ? p2 : rc == 3 ? p3 : 0ull;
+    }
     int dc = cost[0], dom = om[0];
-    om[0] = ((j + OB) << MS) + SB;
+    if (!GEN || start_in_query) om[0] = ((j + OB) << MS) + SB;
+    else { cost[0] = j * ic; om[0] = (OB << MS) + SB + j * w_indel; }
     int cm = 0, omm = 0;
 #pragma unroll
     for (int i = 1; i <= MAXM; ++i) {
@@ -164,7 +208,7 @@ __device__ __noinline__ bool locate(const int a, const uint8_t *read, const int 
         if (i == m) { cm = c; omm = o; }
       }
     }
-    if (cm <= k) {
+    if (cm <= k && (!GEN || stop_in_query)) {
       const int origin = (omm >> MS) - OB, mt = omm & MM;
       const int length = m + min(origin, 0);
       int eff = length;
@@ -176,8 +220,8 @@ __device__ __noinline__ bool locate(const int a, const uint8_t *read, const int 
       }
     }
   }
-  if (!stopped) {
-    const int first_i = back ? 0 : m;
+  if (!stopped && (!GEN || max_n == n)) {
+    const int first_i = stop_in_ref ? 0 : m;
 #pragma unroll
     for (int i = 0; i <= MAXM; ++i) {
       if (i >= first_i && i <= m) {
@@ -203,6 +247,38 @@ __device__ __noinline__ bool locate(const int a, const uint8_t *read, const int 
   out.matches = (best_om & MM) - SB;
   out.errors = best_cost;
   return true;
+}
+
+// Adapter.match_to's shortcut: an adapter without wildcards is first looked for literally (str.find on the upper-cased
+// read).  For the alignment above that changes nothing -- the leftmost literal occurrence is where the DP stops -- except
+// with --match-read-wildcards, where the DP also accepts occurrences through the read's N and would find one of those
+// first; cutadapt returns the literal one.  Shift-and over the read bytes (adapter rows as bits, <= 64).
+__device__ __noinline__ bool find_literal(const int a, const uint8_t *read, const int n, Match &out) {
+  const DevAdapter &ad = c_p.ad[a];
+  const int m = ad.m;
+  const uint64_t top = 1ull << (m - 1);
+  uint64_t state = 0;
+  for (int j = 0; j < n; ++j) {
+    const uint32_t rc = base_code_upper(read[j]);
+    state = ((state << 1) | 1ull) & (rc < 4u ? ad.peq[rc] : 0ull);
+    if (state & top) {
+      out.rstart = j + 1 - m;
+      out.rstop = j + 1;
+      out.matches = m;
+      out.errors = 0;
+      return true;
+    }
+  }
+  return false;
+}
+
+// the search of one adapter on the full-DP path: the plain forms keep their own instantiation
+template <int MAXM>
+__device__ __forceinline__ bool locate_any(const int a, const uint8_t *read, const int n, Match &out) {
+  const DevAdapter &ad = c_p.ad[a];
+  if (!ad.general) return locate<MAXM, false>(a, read, n, out);
+  if (ad.wildcard_read && !ad.wildcard_ref && ad.where <= MIRGE_WHERE_FRONT && find_literal(a, read, n, out)) return true;
+  return locate<MAXM, true>(a, read, n, out);
 }
 
 // ------------------------------------------------------------------ bit-parallel locate ------
@@ -641,4 +717,85 @@ __device__ __forceinline__ void quality_trim_index(const uint8_t *qual, int len,
     if (s > max_qual) { max_qual = s; stop = i; }
   }
   if (start >= stop) { start = 0; stop = 0; }
+}
+
+// ------------------------------------------------------------------ modifiers ---------------
+
+// AdapterCutter._best_match: most matches, then fewer errors, first adapter wins ties.
+// returns the index of the winning adapter, -1 for none, -2 when the search was deferred (DEFER only)
+template <int MAXM, bool FAST, bool DEFER>
+__device__ __noinline__ int best_match(const uint8_t *read, int n, Match &best, const FastCtx &fc) {
+  int which = -1;
+  for (int a = 0; a < c_p.n_adapters; ++a) {
+    Match mt;
+    const int link = c_p.ad[a].link;
+    if (link == MIRGE_LINK_BACK_HALF) continue;  // searched through its 5' half only
+    if (FAST) {
+      const int rc = locate_fast<DEFER>(a, ByteRead{read}, n, fc, mt);
+      if (rc == 2) return -2;
+      if (rc == 0) continue;
+    } else if (link != 0) {
+      // cutadapt LinkedAdapter.match_to: the 3' half is searched in what the 5' match leaves; a missing half ends the
+      // search unless it is optional (-g "A...B": both required; -a "A...B": a half is required when it is anchored),
+      // and a pair without its 5' half needs its 3' half; matches and errors of the pair are the sums.  The Match of a
+      // pair carries the two cut points: rstart = first base kept, rstop = end of what is kept (both relative to `read`).
+      Match f, b;
+      const bool have_f = locate_any<MAXM>(a, read, n, f);
+      if (!have_f && !(link & MIRGE_LINK_FRONT_OPTIONAL)) continue;
+      const int rest = have_f ? f.rstop : 0;
+      const bool have_b = locate_any<MAXM>((link & MIRGE_LINK_INDEX_MASK) - 1, read + rest, n - rest, b);
+      if (!have_b && (!(link & MIRGE_LINK_BACK_OPTIONAL) || !have_f)) continue;
+      mt.rstart = rest;
+      mt.rstop = have_b ? rest + b.rstart : n;
+      mt.matches = (have_f ? f.matches : 0) + (have_b ? b.matches : 0);
+      mt.errors = (have_f ? f.errors : 0) + (have_b ? b.errors : 0);
+    } else if (!locate_any<MAXM>(a, read, n, mt)) continue;
+    if (which < 0 || mt.matches > best.matches || (mt.matches == best.matches && mt.errors < best.errors)) {
+      best = mt;
+      which = a;
+    }
+  }
+  return which;
+}
+
+// returns true when the adapter search was deferred to the second pass (DEFER only)
+template <int MAXM, bool FAST, bool DEFER>
+__device__ __noinline__ bool apply_mod(int mi, const uint8_t *seq, const uint8_t *qual, int &start, int &stop, FastCtx &fc) {
+  const int len = stop - start;
+  switch (c_p.kind[mi]) {
+    case MIRGE_MOD_NEXTSEQ:
+      stop = start + nextseq_trim_index(seq + start, qual + start, len, c_p.a[mi], c_p.b[mi]);
+      break;
+    case MIRGE_MOD_QUALITY: {
+      int s, e;
+      quality_trim_index(qual + start, len, c_p.a[mi], c_p.b[mi], c_p.c[mi], s, e);
+      stop = start + e;
+      start = start + s;
+      break;
+    }
+    case MIRGE_MOD_ADAPTER:
+      for (int t = 0; t < c_p.times; ++t) {
+        Match mt;
+        fc.rbase = start;
+        const int a = best_match<MAXM, FAST, DEFER>(seq + start, stop - start, mt, fc);
+        if (a == -2) return true;
+        if (a < 0) break;
+        if (c_p.ad[a].link != 0) { stop = start + mt.rstop; start = start + mt.rstart; }  // a linked pair cuts both ends
+        else if (!MIRGE_WHERE_IS_FRONT(c_p.ad[a].where)) stop = start + mt.rstart;  // 3' forms: read[:rstart]
+        else start = start + mt.rstop;                                              // 5' forms: read[rstop:]
+      }
+      break;
+    case MIRGE_MOD_NEND:
+      while (start < stop && seq[start] == 'N') ++start;
+      while (stop > start && seq[stop - 1] == 'N') --stop;
+      break;
+    case MIRGE_MOD_CUT: {
+      const int c = c_p.a[mi];
+      if (c > 0) start += min(c, len);
+      else stop = start + max(len + c, 0);
+      break;
+    }
+    default: break;
+  }
+  return false;
 }

@@ -19,7 +19,7 @@
 // trim_kernel<32,true,1,false> + that leftover pass is the unsplit bit-parallel path (qiagen UMIs);
 // trim_kernel<32|64,false,0,false> is the generic full-DP kernel (5' adapters, --no-indels, long adapters).
 #include "common.cuh"
-// DevParams / c_p, fill_dev_params, locate, locate_fast
+// DevParams / c_p, fill_dev_params, locate, locate_fast, the quality scans, best_match, apply_mod
 #include "adapter_search.cuh"
 
 extern "C" int mirge_trim_slots(const mirge_ctx *ctx) {
@@ -48,81 +48,6 @@ extern "C" int mirge_set_trim_params(mirge_ctx *ctx, const mirge_trim_params *p)
   }
   ctx->split_ok = split_ok && seen_ad;
   return MIRGE_OK;
-}
-
-// AdapterCutter._best_match: most matches, then fewer errors, first adapter wins ties.
-// returns the index of the winning adapter, -1 for none, -2 when the search was deferred (DEFER only)
-template <int MAXM, bool FAST, bool DEFER>
-__device__ __noinline__ int best_match(const uint8_t *read, int n, Match &best, const FastCtx &fc) {
-  int which = -1;
-  for (int a = 0; a < c_p.n_adapters; ++a) {
-    Match mt;
-    const int link = c_p.ad[a].link;
-    if (link == MIRGE_LINK_BACK_HALF) continue;  // searched through its 5' half only
-    if (FAST) {
-      const int rc = locate_fast<DEFER>(a, ByteRead{read}, n, fc, mt);
-      if (rc == 2) return -2;
-      if (rc == 0) continue;
-    } else if (link != 0) {
-      // cutadapt LinkedAdapter.match_to for -g "A...B": the 5' half must match; the 3' half is searched in what the
-      // 5' match leaves and must match too; matches and errors of the pair are the sums.  The Match of a pair carries
-      // the two cut points: rstart = first base kept, rstop = end of what is kept (both relative to `read`).
-      Match f, b;
-      if (!locate<MAXM>(a, read, n, f)) continue;
-      if (!locate<MAXM>(link - 1, read + f.rstop, n - f.rstop, b)) continue;
-      mt.rstart = f.rstop;
-      mt.rstop = f.rstop + b.rstart;
-      mt.matches = f.matches + b.matches;
-      mt.errors = f.errors + b.errors;
-    } else if (!locate<MAXM>(a, read, n, mt)) continue;
-    if (which < 0 || mt.matches > best.matches || (mt.matches == best.matches && mt.errors < best.errors)) {
-      best = mt;
-      which = a;
-    }
-  }
-  return which;
-}
-
-// returns true when the adapter search was deferred to the second pass (DEFER only)
-template <int MAXM, bool FAST, bool DEFER>
-__device__ __noinline__ bool apply_mod(int mi, const uint8_t *seq, const uint8_t *qual, int &start, int &stop, FastCtx &fc) {
-  const int len = stop - start;
-  switch (c_p.kind[mi]) {
-    case MIRGE_MOD_NEXTSEQ:
-      stop = start + nextseq_trim_index(seq + start, qual + start, len, c_p.a[mi], c_p.b[mi]);
-      break;
-    case MIRGE_MOD_QUALITY: {
-      int s, e;
-      quality_trim_index(qual + start, len, c_p.a[mi], c_p.b[mi], c_p.c[mi], s, e);
-      stop = start + e;
-      start = start + s;
-      break;
-    }
-    case MIRGE_MOD_ADAPTER:
-      for (int t = 0; t < c_p.times; ++t) {
-        Match mt;
-        fc.rbase = start;
-        const int a = best_match<MAXM, FAST, DEFER>(seq + start, stop - start, mt, fc);
-        if (a == -2) return true;
-        if (a < 0) break;
-        if (c_p.ad[a].link != 0) { stop = start + mt.rstop; start = start + mt.rstart; }  // a linked pair cuts both ends
-        else if (c_p.ad[a].where == 0) stop = start + mt.rstart;
-        else start = start + mt.rstop;
-      }
-      break;
-    case MIRGE_MOD_NEND:
-      while (start < stop && seq[start] == 'N') ++start;
-      while (stop > start && seq[stop - 1] == 'N') --stop;
-      break;
-    case MIRGE_MOD_CUT: {
-      const int c = c_p.a[mi];
-      if (c > 0) start += min(c, len);
-      else stop = start + max(len + c, 0);
-      break;
-    }
-    default: break;
-  }
-  return false;
 }
 
 // the modifiers that need no adapter search (everything stage 1 of the split pipeline runs before the adapter)

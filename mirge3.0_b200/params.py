@@ -5,7 +5,7 @@ from __future__ import annotations
 
 import os
 
-from dataclasses import dataclass
+from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
 from . import abi
@@ -41,51 +41,219 @@ def parse_cutoffs(s) -> List[int]:
 
 @dataclass
 class AdapterSpec:
-    where: str  # "back" | "front" | "linked" (sequence = the 5' half, sequence2 = the 3' half)
+    """One parsed ``-a`` / ``-g`` specification.  ``where`` is a key of ``abi.WHERE`` (cutadapt's ``Where`` of the placement)
+    or "linked" (sequence / where5 / params = the 5' half, sequence2 / where2 / params2 = the 3' half)."""
+
+    where: str
     sequence: str
     sequence2: str = ""
+    params: dict = field(default_factory=dict)  # per-adapter search parameters: max_error_rate, min_overlap, indels
+    where5: str = "front"  # linked pairs: placement of the halves
+    where2: str = "back"
+    params2: dict = field(default_factory=dict)
+    front_required: bool = True
+    back_required: bool = True
+
+
+# cutadapt parser.py AdapterSpecification.allowed_parameters (abbreviation -> parameter); "indels" / "noindels" are the
+# per-adapter switches later releases added
+_PARAMETERS = {"e": "max_error_rate", "error_rate": "max_error_rate", "max_errors": "max_error_rate", "o": "min_overlap",
+               "max_error_rate": None, "min_overlap": None, "anywhere": None, "required": None, "optional": None,
+               "indels": None, "noindels": None}
+
+
+def expand_braces(seq: str) -> str:
+    """cutadapt ``AdapterSpecification.expand_braces``: ``x{n}`` stands for n times the character x."""
+    out = []
+    i = 0
+    while i < len(seq):
+        c = seq[i]
+        if c == "}":
+            raise UnsupportedAdapterSpec('adapter %r: "}" cannot be used here' % seq)
+        if c == "{":
+            j = seq.find("}", i)
+            if not out or j < 0 or not seq[i + 1 : j].isdigit() or not 0 <= int(seq[i + 1 : j]) <= 10000:
+                raise UnsupportedAdapterSpec('adapter %r: "{n}" must follow a character and hold a number' % seq)
+            last = out.pop()
+            out.append(last * int(seq[i + 1 : j]))
+            i = j + 1
+            continue
+        out.append(c)
+        i += 1
+    return "".join(out)
+
+
+def _parse_parameters(text: str, spec: str) -> dict:
+    """``key=value;key;...`` behind the first ';' of a specification (cutadapt ``_parse_parameters``)."""
+    out = {}
+    for fld in text.split(";"):
+        fld = fld.strip()
+        if not fld:
+            continue
+        key, eq, value = fld.partition("=")
+        key, value = key.strip(), value.strip()
+        if eq and not value:
+            raise UnsupportedAdapterSpec("adapter specification %r: no value given for %r" % (spec, key))
+        if key not in _PARAMETERS:
+            raise UnsupportedAdapterSpec("adapter specification %r: unknown parameter %r" % (spec, key))
+        key = _PARAMETERS[key] or key
+        if not eq:
+            val = True
+        else:
+            try:
+                val = int(value)
+            except ValueError:
+                try:
+                    val = float(value)
+                except ValueError:
+                    raise UnsupportedAdapterSpec("adapter specification %r: %r is not a number" % (spec, value))
+        if key in out:
+            raise UnsupportedAdapterSpec("adapter specification %r: parameter %r given twice" % (spec, key))
+        out[key] = val
+    if "optional" in out and "required" in out:
+        raise UnsupportedAdapterSpec("adapter specification %r: 'optional' and 'required' cannot be specified at the same time" % spec)
+    if "indels" in out and "noindels" in out:
+        raise UnsupportedAdapterSpec("adapter specification %r: 'indels' and 'noindels' cannot be specified at the same time" % spec)
+    if "optional" in out:
+        out["required"] = False
+        del out["optional"]
+    if "noindels" in out:
+        out["indels"] = False
+        del out["noindels"]
+    if out.get("anywhere"):
+        raise UnsupportedAdapterSpec("adapter specification %r: ;anywhere (an adapter on either end) is not supported" % spec)
+    out.pop("anywhere", None)
+    e = out.get("max_error_rate")
+    if e is not None and not 0 <= e < 1:
+        raise UnsupportedAdapterSpec("adapter specification %r: the error rate must be in [0, 1)" % spec)
+    if "min_overlap" in out and (out["min_overlap"] is True or int(out["min_overlap"]) < 1):
+        raise UnsupportedAdapterSpec("adapter specification %r: min_overlap must be at least 1" % spec)
+    return out
+
+
+def _parse_half(spec: str, kind: str):
+    """cutadapt ``AdapterSpecification.parse``: ``[name=][^|X]SEQ[$|X][;parameters]`` -> (where, sequence, parameters)."""
+    body, _, ptext = spec.partition(";")
+    if "=" in body:
+        body = body.split("=", 1)[1]
+    body = body.strip()
+    params = _parse_parameters(ptext, spec)
+    if body.lower() == "illumina":  # __main__.py:65-83 expands the alias before baking() is called; accepted here too
+        body = ILLUMINA_BACK if kind == "back" else ILLUMINA_FRONT
+    body = expand_braces(body)
+    if body and not body.strip("Xx"):
+        raise UnsupportedAdapterSpec("adapter specification %r consists of X only" % spec)
+    front = back = None
+    if body.startswith("^"):
+        front, body = "anchored", body[1:]
+    if body.upper().startswith("X"):
+        if front:
+            raise UnsupportedAdapterSpec('adapter specification %r: either "^" or "X" must be used, not both' % spec)
+        front, body = "noninternal", body.lstrip("xX")
+    if body.endswith("$"):
+        back, body = "anchored", body[:-1]
+    if body.upper().endswith("X"):
+        if back:
+            raise UnsupportedAdapterSpec('adapter specification %r: either "$" or "X" must be used, not both' % spec)
+        back, body = "noninternal", body.rstrip("xX")
+    if front and back:
+        raise UnsupportedAdapterSpec("adapter specification %r: only one placement restriction is possible" % spec)
+    if kind == "front" and back:
+        raise UnsupportedAdapterSpec("adapter specification %r: a 5' adapter takes XADAPTER or ^ADAPTER" % spec)
+    if kind == "back" and front:
+        raise UnsupportedAdapterSpec("adapter specification %r: a 3' adapter takes ADAPTERX or ADAPTER$" % spec)
+    restriction = front or back
+    where = {None: kind, "anchored": "prefix" if kind == "front" else "suffix",
+             "noninternal": kind + "_not_internal"}[restriction]
+    seq = body.upper().replace("U", "T")
+    if not seq:
+        raise UnsupportedAdapterSpec("empty adapter")
+    if len(seq) > abi.MAX_ADAPTER_LEN:
+        raise UnsupportedAdapterSpec("adapter longer than %d nt" % abi.MAX_ADAPTER_LEN)
+    bad = set(seq) - set(IUPAC)
+    if bad:
+        raise UnsupportedAdapterSpec("adapter %r has non-IUPAC characters %s" % (spec, sorted(bad)))
+    return where, seq, params, restriction
 
 
 def parse_adapter_spec(kind: str, spec: str) -> AdapterSpec:
-    """The subset of cutadapt's adapter specification language reachable from miRge's ``-a``/``-g``
-    (parse.py:74-77) that this path implements: a plain (non-anchored) 3' or 5' adapter, optionally ``name=SEQ``,
-    and the linked form the reference documents, ``-g "ADAPTER5...ADAPTER3"`` (docs/source/quick_start.md:208-220;
-    cutadapt: both halves non-anchored, both required).  ``-a "A...B"`` anchors its 5' half and is, like everything else,
-    rejected instead of silently diverging."""
+    """One specification of cutadapt's adapter language as it reaches ``stipulate`` through miRge's ``-a`` / ``-g``
+    (parse.py:74-77; cutadapt parser.py ``AdapterParser._parse``): plain, anchored (``^SEQ``, ``SEQ$``) and non-internal
+    (``XSEQ``, ``SEQX``) adapters, ``name=``, ``x{n}`` repeats, per-adapter ``;parameters`` and the linked form
+    ``ADAPTER5...ADAPTER3`` the reference documents (docs/source/quick_start.md:208-220) -- with ``-g`` both halves are
+    required, with ``-a`` a half is required only when it is anchored, ``;required`` / ``;optional`` override both.
+    ``file:`` specifications hold several adapters: ``parse_adapter_specs``.  What the kernels have no form for
+    (``;anywhere``, adapters on either end) raises instead of silently diverging."""
     if kind not in ("back", "front"):
         raise UnsupportedAdapterSpec("adapter type %r is not supported" % (kind,))
     s = spec.strip()
-    if "..." in s and kind == "front":
-        body = s.split("=", 1)[1] if "=" in s else s
-        halves = body.split("...")
-        if len(halves) != 2 or not halves[0] or not halves[1]:
+    if s.startswith("file:"):
+        raise UnsupportedAdapterSpec("adapter specification %r names a file of adapters: use parse_adapter_specs" % spec)
+    one, dots, two = s.partition("...")
+    if dots and one and two:
+        if "..." in two:
             raise UnsupportedAdapterSpec("linked adapter specification %r: expected ADAPTER5...ADAPTER3" % spec)
-        if any(x.lower() == "illumina" for x in halves):
+        if any(x.partition(";")[0].split("=")[-1].strip().lower() == "illumina" for x in (one, two)):
             # quick_start.md:219-221: the alias is not decoded inside a linked specification (cutadapt would take the
             # letters as bases)
             raise UnsupportedAdapterSpec("linked adapter specification %r: give the complete adapter sequences" % spec)
-        five, three = (parse_adapter_spec("front", halves[0]), parse_adapter_spec("back", halves[1]))
-        return AdapterSpec("linked", five.sequence, three.sequence)
-    if s.lower() == "illumina":
-        s = ILLUMINA_BACK if kind == "back" else ILLUMINA_FRONT
-    if "=" in s:
-        s = s.split("=", 1)[1]
-    if s.startswith("file:") or "..." in s or ";" in s or s.startswith("^") or s.endswith("$"):
-        raise UnsupportedAdapterSpec(
-            "adapter specification %r (linked / anchored / file: / ;parameters) is not supported "
-            "by the B200 path" % spec
-        )
-    s = s.upper().replace("U", "T")
-    if s.endswith("X") or s.startswith("X"):
-        raise UnsupportedAdapterSpec("non-internal adapter specification %r is not supported" % spec)
-    if not s:
-        raise UnsupportedAdapterSpec("empty adapter")
-    if len(s) > abi.MAX_ADAPTER_LEN:
-        raise UnsupportedAdapterSpec("adapter longer than %d nt" % abi.MAX_ADAPTER_LEN)
-    bad = set(s) - set(IUPAC)
-    if bad:
-        raise UnsupportedAdapterSpec("adapter %r has non-IUPAC characters %s" % (spec, sorted(bad)))
-    return AdapterSpec(kind, s)
+        w5, s5, p5, r5 = _parse_half(one, "front")
+        w3, s3, p3, r3 = _parse_half(two, "back")
+        # cutadapt _parse_linked: -g needs both halves, -a only the anchored ones; ;required / ;optional decide otherwise
+        req5 = True if kind == "front" else r5 == "anchored"
+        req3 = True if kind == "front" else r3 == "anchored"
+        req5 = bool(p5.pop("required", req5))
+        req3 = bool(p3.pop("required", req3))
+        return AdapterSpec("linked", s5, s3, p5, w5, w3, p3, req5, req3)
+    if dots:
+        if not one and kind == "back":  # -a ...ADAPTER: a plain 3' adapter
+            s = two
+        elif not two:  # -a ADAPTER... / -g ADAPTER...: a plain 5' adapter
+            s, kind = one, "front"
+        else:
+            raise UnsupportedAdapterSpec("invalid adapter specification %r" % spec)
+    where, seq, params, _ = _parse_half(s, kind)
+    if "required" in params:
+        raise UnsupportedAdapterSpec("adapter specification %r: 'optional' and 'required' belong to linked adapters" % spec)
+    return AdapterSpec(where, seq, params=params)
+
+
+def read_adapter_fasta(path: str) -> List[str]:
+    """The sequences of a FASTA file of adapters (``-a file:adapters.fa``; cutadapt reads it with dnaio's FastaReader:
+    '>' header lines, sequences possibly over several lines, '#' comment lines and blank lines skipped)."""
+    seqs: List[str] = []
+    cur: Optional[List[str]] = None
+    with open(path, "r") as f:
+        for line in f:
+            line = line.strip()
+            if not line or (line.startswith("#") and cur is None):
+                continue
+            if line.startswith(">"):
+                if cur is not None:
+                    seqs.append("".join(cur))
+                cur = []
+            elif cur is None:
+                raise UnsupportedAdapterSpec("%s: not a FASTA file (no '>' before the first sequence)" % path)
+            else:
+                cur.append(line)
+    if cur is not None:
+        seqs.append("".join(cur))
+    return seqs
+
+
+def parse_adapter_specs(kind: str, spec: str) -> List[AdapterSpec]:
+    """``parse_adapter_spec`` for every adapter a ``-a`` / ``-g`` argument stands for: one, or with ``file:PATH`` one per
+    FASTA record (cutadapt parser.py ``AdapterParser.parse``: each record's sequence is a specification of its own)."""
+    s = spec.strip()
+    if s.startswith("file:"):
+        try:
+            seqs = read_adapter_fasta(s[5:])
+        except OSError as e:
+            raise UnsupportedAdapterSpec("adapter specification %r: %s" % (spec, e))
+        if not seqs:
+            raise UnsupportedAdapterSpec("adapter specification %r: the file holds no adapter" % spec)
+        return [parse_adapter_spec(kind, q) for q in seqs]
+    return [parse_adapter_spec(kind, s)]
 
 
 @dataclass
@@ -142,20 +310,28 @@ class TrimConfig:
         return int(parts[0]), int(parts[1])
 
 
-def build_adapter(spec: AdapterSpec, cfg: TrimConfig) -> abi.Adapter:
+def build_adapter(spec: AdapterSpec, cfg: TrimConfig, half: int = 0) -> abi.Adapter:
+    """One plain adapter, or with ``half`` 1 / 2 the 5' / 3' half of a linked pair, in the Aligner terms the kernels take."""
     a = abi.Adapter()
-    seq = spec.sequence
+    seq, where, prm = ((spec.sequence, spec.where, spec.params) if half == 0 else
+                       (spec.sequence, spec.where5, spec.params) if half == 1 else (spec.sequence2, spec.where2, spec.params2))
     m = len(seq)
+    rate = float(prm.get("max_error_rate", cfg.error_rate))
+    overlap = int(prm.get("min_overlap", cfg.overlap))
+    indels = bool(prm.get("indels", cfg.indels))
     wildcard_ref = cfg.match_adapter_wildcards and not set(seq) <= set("ACGT")
     if not wildcard_ref and not set(seq) <= set("ACGT"):
         raise UnsupportedAdapterSpec("IUPAC adapter characters with -N (no adapter wildcards) are not supported")
-    a.where = 0 if spec.where == "back" else 1
+    a.where = abi.WHERE[where]
     a.link = 0
     a.m = m
-    a.min_overlap = min(int(cfg.overlap), m)  # cutadapt adapters.py: min_overlap = min(min_overlap, len(sequence))
-    a.indel_cost = 1 if cfg.indels else 100000
+    a.min_overlap = min(overlap, m)  # cutadapt adapters.py: min_overlap = min(min_overlap, len(sequence))
+    if where in ("prefix", "suffix"):
+        a.min_overlap = m  # anchored adapters occur in full (every alignment the placement admits spans the adapter)
+    a.indel_cost = 1 if indels else 100000
     a.wildcard_ref = 1 if wildcard_ref else 0
-    a.k = int(cfg.error_rate * m)
+    a.wildcard_read = 1 if cfg.match_read_wildcards else 0
+    a.k = int(rate * m)
     c = 0
     for i, ch in enumerate(seq):
         a.n_counts[i] = c
@@ -168,27 +344,36 @@ def build_adapter(spec: AdapterSpec, cfg: TrimConfig) -> abi.Adapter:
     if a.effective_length == 0:
         raise UnsupportedAdapterSpec("Cannot have only N wildcards in the sequence")
     for L in range(abi.MAX_ADAPTER_LEN + 1):
-        a.max_err[L] = int(L * cfg.error_rate)  # floor of the double product, as cutadapt compares
+        a.max_err[L] = int(L * rate)  # floor of the double product, as cutadapt compares
     return a
+
+
+def flatten_adapters(cfg: TrimConfig):
+    """``args.adapters`` as the flat list the kernels walk: [(AdapterSpec, half)] plus ``mirge_adapter.link`` per entry.
+    A linked pair takes two consecutive entries, its 5' half pointing at its 3' half."""
+    flat, links = [], []
+    for (k, s) in cfg.adapters:
+        for sp in parse_adapter_specs(k, s):
+            if sp.where == "linked":
+                flat += [(sp, 1), (sp, 2)]
+                link = len(flat)  # 1 + index of the 3' half
+                if not sp.front_required:
+                    link |= abi.LINK_FRONT_OPTIONAL
+                if not sp.back_required:
+                    link |= abi.LINK_BACK_OPTIONAL
+                links += [link, abi.LINK_BACK_HALF]
+            else:
+                flat.append((sp, 0))
+                links.append(0)
+    return flat, links
 
 
 def build_trim_params(cfg: TrimConfig) -> abi.TrimParams:
     """``stipulate`` + the worker globals, flattened (modifier order: digest.py:87-99)."""
     if cfg.action != "trim":
         raise RuntimeError("action=%r is not supported (miRge always uses 'trim', parse.py:95)" % cfg.action)
-    if cfg.match_read_wildcards:
-        raise RuntimeError("--match-read-wildcards is not supported")
     p = abi.TrimParams()
-    specs = []
-    links = []  # per flattened adapter: mirge_adapter.link
-    for (k, s) in cfg.adapters:
-        sp = parse_adapter_spec(k, s)
-        if sp.where == "linked":  # two consecutive entries: the 5' half points at the 3' half
-            specs += [AdapterSpec("front", sp.sequence), AdapterSpec("back", sp.sequence2)]
-            links += [len(specs), abi.LINK_BACK_HALF]  # (1 + index of the 3' half) = len(specs) after both were appended
-        else:
-            specs.append(sp)
-            links.append(0)
+    specs, links = flatten_adapters(cfg)
     if any(links) and cfg.qiagenumi:
         raise UnsupportedAdapterSpec("linked adapters together with --qiagenumi are not supported")
     if len(specs) > abi.MAX_ADAPTERS:
@@ -218,8 +403,8 @@ def build_trim_params(cfg: TrimConfig) -> abi.TrimParams:
     for i, (k, a, b, c) in enumerate(mods):
         p.mod_kind[i], p.mod_a[i], p.mod_b[i], p.mod_c[i] = k, a, b, c
     p.n_adapters = len(specs)
-    for i, s in enumerate(specs):
-        p.adapters[i] = build_adapter(s, cfg)
+    for i, (sp, half) in enumerate(specs):
+        p.adapters[i] = build_adapter(sp, cfg, half)
         p.adapters[i].link = links[i]
     p.times = int(cfg.times)
     p.min_len = int(cfg.minimum_length)
@@ -230,7 +415,7 @@ def build_trim_params(cfg: TrimConfig) -> abi.TrimParams:
         if not specs:
             raise RuntimeError("--qiagenumi requires the internal adapter (-a)")
         p.umi_mode = abi.UMI_QIAGEN
-        p.qia_adapter_len = len(str(cfg.adapters[0][1])) if str(cfg.adapters[0][1]).lower() != "illumina" else specs[0].sequence.__len__()
+        p.qia_adapter_len = len(str(cfg.adapters[0][1])) if str(cfg.adapters[0][1]).lower() != "illumina" else len(specs[0][0].sequence)
     elif umi is not None:
         p.umi_mode = abi.UMI_FLANKS
     else:

@@ -78,8 +78,19 @@ static inline int upper(int c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
 static inline int acgt_mask(int c) {
   switch (upper(c)) { case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': case 'U': return 8; default: return 0; }
 }
+/* the read's characters as IUPAC sets (--match-read-wildcards; _align.pyx IUPAC_TABLE) */
+static inline int iupac_mask(int c) {
+  switch (upper(c)) {
+    case 'A': return 1; case 'C': return 2; case 'G': return 4; case 'T': case 'U': return 8;
+    case 'R': return 5; case 'Y': return 10; case 'S': return 6; case 'W': return 9; case 'K': return 12; case 'M': return 3;
+    case 'B': return 14; case 'D': return 13; case 'H': return 11; case 'V': return 7; case 'N': return 15; default: return 0;
+  }
+}
 
 typedef struct { int astart, astop, rstart, rstop, matches, errors; } match_t;
+
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
 
 /* cutadapt Aligner.locate (pyoracle.locate). Returns 1 if a match was found. */
 static int locate(const mirge_adapter *ad, const uint8_t *read, int n, match_t *out, int compat) {
@@ -87,20 +98,32 @@ static int locate(const mirge_adapter *ad, const uint8_t *read, int n, match_t *
   const int w_mis = compat == MIRGE_COMPAT_CUTADAPT4 ? -1 : 0, w_indel = compat == MIRGE_COMPAT_CUTADAPT4 ? -2 : 0;
   int m = ad->m;
   int cost[MAXM + 1], origin[MAXM + 1], matches[MAXM + 1];
-  int back = ad->where == 0;
+  /* cutadapt's Where flags (pyoracle.WHERE_FLAGS): which ends of the alignment are free */
+  const int w = ad->where;
+  const int start_in_ref = w == MIRGE_WHERE_FRONT || w == MIRGE_WHERE_FRONT_NOT_INTERNAL;
+  const int stop_in_ref = w == MIRGE_WHERE_BACK || w == MIRGE_WHERE_BACK_NOT_INTERNAL;
+  const int start_in_query = w == MIRGE_WHERE_BACK || w == MIRGE_WHERE_FRONT || w == MIRGE_WHERE_SUFFIX || w == MIRGE_WHERE_BACK_NOT_INTERNAL;
+  const int stop_in_query = w == MIRGE_WHERE_BACK || w == MIRGE_WHERE_FRONT || w == MIRGE_WHERE_PREFIX || w == MIRGE_WHERE_FRONT_NOT_INTERNAL;
   int ic = ad->indel_cost;
-  for (int i = 0; i <= m; ++i) {
-    matches[i] = back ? i * w_indel : 0;
-    if (back) { cost[i] = i * ic; origin[i] = 0; } else { cost[i] = 0; origin[i] = -i; }
-  }
   int k = ad->k;
+  /* an anchored start cannot use more than m + k read bases, an anchored end only the last m + k */
+  const int max_n = start_in_query ? n : imin(n, m + k);
+  const int min_n = stop_in_query ? 0 : imax(0, n - m - k);
+  for (int i = 0; i <= m; ++i) {
+    if (!start_in_ref && !start_in_query) { cost[i] = imax(i, min_n) * ic; origin[i] = 0; }
+    else if (start_in_ref && !start_in_query) { cost[i] = min_n * ic; origin[i] = imin(0, min_n - i); }
+    else if (!start_in_ref && start_in_query) { cost[i] = i * ic; origin[i] = imax(0, min_n - i); }
+    else { cost[i] = imin(i, min_n) * ic; origin[i] = min_n - i; }
+    matches[i] = start_in_ref ? 0 : i * w_indel;
+  }
   int best_cost = m + n, best_origin = 0, best_matches = compat == MIRGE_COMPAT_CUTADAPT4 ? -(1 << 30) : 0, best_ref_stop = m,
       best_query_stop = n;
   int stopped = 0;
-  for (int j = 1; j <= n; ++j) {
+  for (int j = min_n + 1; j <= max_n; ++j) {
     int dc = cost[0], dor = origin[0], dm = matches[0];
-    origin[0] = j;
-    int rc = acgt_mask(read[j - 1]);
+    if (start_in_query) origin[0] = j;
+    else { cost[0] = j * ic; matches[0] = j * w_indel; }
+    int rc = ad->wildcard_read ? iupac_mask(read[j - 1]) : acgt_mask(read[j - 1]);
     for (int i = 1; i <= m; ++i) {
       int c, o, mt;
       if (ad->mask[i - 1] & rc) { c = dc; o = dor; mt = dm + 1; }
@@ -113,7 +136,7 @@ static int locate(const mirge_adapter *ad, const uint8_t *read, int n, match_t *
       dc = cost[i]; dor = origin[i]; dm = matches[i];
       cost[i] = c; origin[i] = o; matches[i] = mt;
     }
-    if (cost[m] <= k) {
+    if (cost[m] <= k && stop_in_query) {
       int length = m + (origin[m] < 0 ? origin[m] : 0);
       int eff = length;
       if (ad->wildcard_ref) eff = (length < m) ? length - (ad->n_counts[m] - ad->n_counts[m - length]) : ad->effective_length;
@@ -124,8 +147,8 @@ static int locate(const mirge_adapter *ad, const uint8_t *read, int n, match_t *
       }
     }
   }
-  if (!stopped) {
-    int first_i = back ? 0 : m;
+  if (!stopped && max_n == n) {
+    int first_i = stop_in_ref ? 0 : m;
     for (int i = first_i; i <= m; ++i) {
       int length = i + (origin[i] < 0 ? origin[i] : 0);
       int c = cost[i], mt = matches[i], eff = length;
@@ -145,11 +168,15 @@ static int locate(const mirge_adapter *ad, const uint8_t *read, int n, match_t *
   return 1;
 }
 
-/* Adapter.match_to: exact find on upper(read) first when the adapter has no wildcards. */
+/* Adapter.match_to: when the adapter has no wildcards, an exact comparison on upper(read) first -- str.find for the
+ * plain forms, startswith / endswith for the anchored ones, none for the non-internal ones. */
 static int match_to(const mirge_adapter *ad, const uint8_t *read, int n, match_t *out, int compat) {
   int m = ad->m;
-  if (!ad->wildcard_ref) {
-    for (int p = 0; p + m <= n; ++p) {
+  if (!ad->wildcard_ref && ad->where <= MIRGE_WHERE_PREFIX) {
+    int lo = 0, hi = n - m;
+    if (ad->where == MIRGE_WHERE_PREFIX) hi = imin(hi, 0);
+    if (ad->where == MIRGE_WHERE_SUFFIX) lo = imax(n - m, 0);
+    for (int p = lo; p <= hi; ++p) {
       int j = 0;
       while (j < m && upper(read[p + j]) == ad->ascii[j]) ++j;
       if (j == m) { out->astart = 0; out->astop = m; out->rstart = p; out->rstop = p + m; out->matches = m; out->errors = 0; return 1; }
@@ -165,13 +192,19 @@ static int best_match(const mirge_trim_params *p, const uint8_t *read, int n, ma
     int link = p->adapters[a].link;
     if (link == MIRGE_LINK_BACK_HALF) continue;
     if (link != 0) {
-      /* cutadapt LinkedAdapter.match_to, -g "A...B": both halves required; the 3' half is searched in read[front.rstop:].
+      /* cutadapt LinkedAdapter.match_to: the 3' half is searched in read[front.rstop:]; a missing half ends the search
+       * unless it is optional (-g "A...B": both required; -a "A...B": the 3' half optional), and a pair needs its 5' half
+       * or, failing that, its 3' half.
        * The match of a pair: rstart = first base kept, rstop = end of what is kept, matches / errors = sums. */
       match_t f, b;
-      if (!match_to(&p->adapters[a], read, n, &f, p->compat)) continue;
-      if (!match_to(&p->adapters[link - 1], read + f.rstop, n - f.rstop, &b, p->compat)) continue;
-      mt = f;
-      mt.rstart = f.rstop; mt.rstop = f.rstop + b.rstart; mt.matches = f.matches + b.matches; mt.errors = f.errors + b.errors;
+      const int have_f = match_to(&p->adapters[a], read, n, &f, p->compat);
+      if (!have_f && !(link & MIRGE_LINK_FRONT_OPTIONAL)) continue;
+      const int rest = have_f ? f.rstop : 0;
+      const int have_b = match_to(&p->adapters[(link & MIRGE_LINK_INDEX_MASK) - 1], read + rest, n - rest, &b, p->compat);
+      if (!have_b && (!(link & MIRGE_LINK_BACK_OPTIONAL) || !have_f)) continue;
+      memset(&mt, 0, sizeof(mt));
+      mt.rstart = rest; mt.rstop = have_b ? rest + b.rstart : n;
+      mt.matches = (have_f ? f.matches : 0) + (have_b ? b.matches : 0); mt.errors = (have_f ? f.errors : 0) + (have_b ? b.errors : 0);
     } else if (!match_to(&p->adapters[a], read, n, &mt, p->compat)) continue;
     if (!have || mt.matches > best->matches || (mt.matches == best->matches && mt.errors < best->errors)) { *best = mt; have = 1; which = a; }
   }
@@ -194,7 +227,8 @@ static void apply_mod(const mirge_trim_params *p, int mi, const uint8_t *seq, co
         match_t mt; int a = best_match(p, seq + start, stop - start, &mt);
         if (a < 0) break;
         if (p->adapters[a].link != 0) { stop = start + mt.rstop; start = start + mt.rstart; }
-        else if (p->adapters[a].where == 0) stop = start + mt.rstart; else start = start + mt.rstop;
+        else if (!MIRGE_WHERE_IS_FRONT(p->adapters[a].where)) stop = start + mt.rstart; /* 3' forms */
+        else start = start + mt.rstop;                                 /* 5' forms */
       }
       break;
     case MIRGE_MOD_NEND:

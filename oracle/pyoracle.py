@@ -162,18 +162,32 @@ ACGT = {"A": 1, "C": 2, "G": 4, "T": 8, "U": 8}
 
 INDEL_OFF_COST = 100000  # cutadapt adapters.py: "indel_cost = 1 if self.indels else 100000"
 
+# cutadapt adapters.py ``Where``: which ends of the alignment are free -- (start within the adapter, stop within the
+# adapter, start within the read, stop within the read); "within the adapter" = the adapter's start / end may be skipped
+WHERE_FLAGS = {
+    "back": (False, True, True, True),  # -a SEQ: anywhere in the read, the adapter may hang over the 3' end
+    "front": (True, False, True, True),  # -g SEQ: anywhere, may hang over the 5' end
+    "prefix": (False, False, False, True),  # -g ^SEQ (anchored 5'): read and adapter start together
+    "suffix": (False, False, True, False),  # -a SEQ$ (anchored 3'): read and adapter end together
+    "front_not_internal": (True, False, False, True),  # -g XSEQ: as front, but never inside the read
+    "back_not_internal": (False, True, True, False),  # -a SEQX
+}
+REMOVE_BEFORE = ("front", "prefix", "front_not_internal")  # 5' forms: what precedes the match goes too
+
 
 @dataclass
 class Adapter:
-    """One parsed adapter (subset of cutadapt's spec language that miRge's CLI can produce from
-    ``-a SEQ`` / ``-g SEQ``, parse.py:74-77: plain 3' ("back") and 5' ("front") adapters)."""
+    """One parsed adapter of cutadapt's specification language as miRge's CLI hands it over (``-a SPEC`` / ``-g SPEC``,
+    parse.py:74-77): ``where`` is cutadapt's ``Where`` of the placement -- plain 3' / 5' adapters, the anchored forms
+    ``^SEQ`` / ``SEQ$`` and the non-internal forms ``XSEQ`` / ``SEQX``."""
 
-    where: str  # "back" | "front" | "prefix" (anchored 5', ^SEQ) | "suffix" (anchored 3', SEQ$)
+    where: str  # one of WHERE_FLAGS
     sequence: str
     max_error_rate: float = 0.12  # parse.py:91
     min_overlap: int = 3  # parse.py:90
     indels: bool = True  # parse.py:101
     adapter_wildcards: bool = True  # parse.py:98 (only effective if sequence has non-ACGT)
+    read_wildcards: bool = False  # parse.py:97 (--match-read-wildcards: IUPAC characters of the READ match as sets)
 
     def __post_init__(self):
         self.sequence = self.sequence.upper().replace("U", "T")
@@ -195,7 +209,7 @@ class Adapter:
         if self.effective_length == 0:
             raise ValueError("Cannot have only N wildcards in the sequence")
         self.masks = [IUPAC[ch] for ch in self.sequence]
-        if self.where not in ("back", "front", "prefix", "suffix"):
+        if self.where not in WHERE_FLAGS:
             raise ValueError("unknown adapter type %r" % (self.where,))
         if self.where in ("prefix", "suffix"):
             self.min_overlap = m  # cutadapt adapters.py: anchored adapters must occur in full
@@ -244,15 +258,10 @@ def locate(ad: Adapter, read: str, compat: str = "2-3") -> Optional[Tuple[int, i
     rate = ad.max_error_rate
     ins_cost = del_cost = 1 if ad.indels else INDEL_OFF_COST
     up = read.upper()
-    # read characters -> 4-bit class (non-ACGT never matches; match_read_wildcards=False, parse.py:97)
-    rmask = [ACGT.get(ch, 0) for ch in up]
-    # cutadapt's Where flags: BACK = start/stop anywhere in the read, adapter end may be skipped; FRONT = adapter start
-    # may be skipped instead; PREFIX (anchored 5') = read and adapter start together; SUFFIX (anchored 3') = end together
-    start_in_ref = ad.where == "front"
-    stop_in_ref = ad.where == "back"
-    start_in_query = ad.where in ("back", "front", "suffix")
-    stop_in_query = ad.where in ("back", "front", "prefix")
-    back = ad.where == "back"
+    # read characters -> 4-bit class: a character outside ACGT never matches, unless --match-read-wildcards
+    # (parse.py:97) turns the read's IUPAC characters into sets as well (_align.pyx: query translated with IUPAC_TABLE)
+    rmask = [(IUPAC if ad.read_wildcards else ACGT).get(ch, 0) for ch in up]
+    start_in_ref, stop_in_ref, start_in_query, stop_in_query = WHERE_FLAGS[ad.where]
     if compat not in ("2-3", "4"):
         raise ValueError("compat must be '2-3' or '4'")
     # what a step adds to the merit a cell carries (matches, or the score of cutadapt >= 4)
@@ -367,9 +376,16 @@ def match_to(ad: Adapter, read: str, compat: str = "2-3") -> Optional[Tuple[int,
         return match_linked(ad, read, compat)
     up = read.upper()
     if not ad.wildcard_ref:
-        pos = up.find(ad.sequence)
+        m = len(ad.sequence)
+        pos = -1
+        if ad.where == "prefix":
+            pos = 0 if up.startswith(ad.sequence) else -1
+        elif ad.where == "suffix":
+            pos = len(up) - m if up.endswith(ad.sequence) else -1
+        elif ad.where in ("back", "front"):
+            pos = up.find(ad.sequence)
+        # (the non-internal forms have no shortcut in cutadapt: an occurrence inside the read is not a match for them)
         if pos >= 0:
-            m = len(ad.sequence)
             return (0, m, pos, pos + m, m, 0)  # (m matches; also the score of m matches)
     return locate(ad, read, compat)
 
@@ -479,10 +495,10 @@ def apply_modifier(mod, seq: str, qual: str, start: int, stop: int, p: TrimParam
                 break
             if ad.where == "linked":
                 start, stop = start + mt[2], start + mt[3]  # LinkedMatch.trimmed(): both ends cut
-            elif ad.where == "back":
-                stop = start + mt[2]  # read[:rstart]
-            else:
+            elif ad.where in REMOVE_BEFORE:
                 start = start + mt[3]  # read[rstop:]
+            else:
+                stop = start + mt[2]  # read[:rstart]
         return start, stop
     if kind == "nend":
         # NEndTrimmer: regex ^N+ and N+$ (uppercase N only)

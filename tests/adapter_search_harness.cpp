@@ -32,7 +32,7 @@ extern "C" int hs_locate(int mode, int a, const uint8_t *read, int len, int star
   const int n = stop - start;
   int rc;
   if (mode == 0) {
-    rc = g_maxm <= 32 ? (int)locate<32>(a, read + start, n, mt) : (int)locate<64>(a, read + start, n, mt);
+    rc = g_maxm <= 32 ? (int)locate_any<32>(a, read + start, n, mt) : (int)locate_any<64>(a, read + start, n, mt);
   } else {
     if (!g_fast_ok) return -1;
     bool pure = true;
@@ -61,6 +61,21 @@ extern "C" int hs_locate(int mode, int a, const uint8_t *read, int len, int star
   }
   out[0] = mt.rstart; out[1] = mt.rstop; out[2] = mt.matches; out[3] = mt.errors;
   return rc;
+}
+
+// the whole modifier pipeline of one read on the full-DP path (apply_mod<MAXM, false, false>: what trim_kernel<MAXM, false, 0, false>
+// runs per read, linked pairs and every adapter placement included): windows[2 * mi] / [2 * mi + 1] = the read's window after modifier mi
+extern "C" int hs_pipeline(const uint8_t *seq, const uint8_t *qual, int len, int32_t *windows) {
+  FastCtx fc;
+  memset(&fc, 0, sizeof(fc));
+  int start = 0, stop = len;
+  for (int mi = 0; mi < c_p.n_mods; ++mi) {
+    if (g_maxm <= 32) apply_mod<32, false, false>(mi, seq, qual, start, stop, fc);
+    else apply_mod<64, false, false>(mi, seq, qual, start, stop, fc);
+    windows[2 * mi] = start;
+    windows[2 * mi + 1] = stop;
+  }
+  return c_p.n_mods;
 }
 
 // the two quality scans (cutadapt qualtrim.pyx), as the trim kernels call them

@@ -113,12 +113,11 @@ class UnconditionalCutter:
 
 
 def _make_adapters_from_specifications(specs, search_parameters):
-    out = []
-    for kind, spec in specs:
-        sp = P.parse_adapter_spec(kind, spec)
-        out.append(po.Adapter(sp.where, sp.sequence, search_parameters["max_errors"], search_parameters["min_overlap"],
-                              search_parameters["indels"], search_parameters["adapter_wildcards"]))
-    return out
+    from tests.util import py_adapters
+
+    return py_adapters(P.TrimConfig(adapters=list(specs), error_rate=search_parameters["max_errors"], overlap=search_parameters["min_overlap"],
+                                    indels=search_parameters["indels"], match_adapter_wildcards=search_parameters["adapter_wildcards"],
+                                    match_read_wildcards=search_parameters["read_wildcards"]))
 
 
 def install(reference_root):

@@ -18,12 +18,12 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(abi.SYMBOLS), declared ^ set(abi.SYMBOLS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.mirge_abi_version() == abi.ABI_VERSION == 2
+    assert lib.mirge_abi_version() == abi.ABI_VERSION == 3
 
 
 def test_struct_sizes_match_header():
     # sizes derived from the header's field lists
-    assert ctypes.sizeof(abi.Adapter) == 8 * 4 + 64 + 64 + 65 * 4 + 65 * 4
+    assert ctypes.sizeof(abi.Adapter) == 9 * 4 + 64 + 64 + 65 * 4 + 65 * 4  # + wildcard_read (ABI v3)
     assert ctypes.sizeof(abi.TrimParams) == 4 * (1 + 8 * 4 + 9) + 4 * ctypes.sizeof(abi.Adapter)  # + compat (ABI v2)
     assert ctypes.sizeof(abi.Table) == 56
     assert ctypes.sizeof(abi.RoundPolicy) == 32

@@ -164,6 +164,169 @@ def test_generic_search_with_front_adapters_wildcards_and_no_indels(hs, seed):
     assert stats.get(("mode", 0), 0) > 100 and stats.get("matches", 0) > 20, stats
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_per_adapter_parameters_on_the_bit_parallel_search(hs, seed):
+    """Two 3' adapters whose ;e= / ;o= differ from each other and from -e / -O: every adapter's own error table and
+    minimum overlap must reach the bit-parallel search (they stay on the fast path) as they reach the literal DP."""
+    rng = np.random.default_rng(4600 + seed)
+    stats = {}
+    for rep in range(5):
+        ad1, ad2 = make_adapter(rng, "random"), make_adapter(rng, ["repeat", "two_blocks", "random"][rep % 3])
+        spec1 = ad1 + ";e=%s" % rng.choice(["0", "0.05", "0.2", "0.25"]) + (";o=%d" % int(rng.integers(1, 9)) if rng.random() < 0.7 else "")
+        spec2 = ad2 + (";o=%d" % int(rng.integers(1, 9))) + (";e=%s" % rng.choice(["0.1", "0.3"]) if rng.random() < 0.5 else "")
+        cfg = P.TrimConfig(adapters=[("back", spec1), ("back", spec2)], error_rate=0.12, overlap=3, indels=True)
+        reads = [make_read(rng, ad1 if rng.random() < 0.5 else ad2, int(rng.integers(0, 6))) for _ in range(60)]
+        run_case(hs, cfg, [r for r in reads if r], stats)
+    assert stats.get(("mode", 1), 0) > 100 and stats.get(("mode", 3), 0) > 50 and stats.get("matches", 0) > 100, stats
+
+
+WHERE_SPECS = {  # cutadapt's notation of every placement (params.parse_adapter_spec)
+    "back": ("back", "%s"), "front": ("front", "%s"), "suffix": ("back", "%s$"), "prefix": ("front", "^%s"),
+    "back_not_internal": ("back", "%sX"), "front_not_internal": ("front", "X%s"),
+}
+
+
+def placed_read(rng, ad, where):
+    """A read that carries (a damaged / partial copy of) the adapter where the placement looks for it -- or elsewhere."""
+    r = rng.random()
+    body = mutate(rng, ad, 0.06, 0.03, 0.03) if r < 0.7 else ad
+    if rng.random() < 0.3:  # partial adapter: its start (3' forms) or its end (5' forms)
+        cut = int(rng.integers(1, len(ad) + 1))
+        body = body[:cut] if where in ("back", "suffix", "back_not_internal") else body[-cut:]
+    ins = rnd(rng, int(rng.integers(0, 40)))
+    pos = rng.random()
+    if pos < 0.45:  # at the end the placement anchors
+        s = ins + body if where in ("back", "suffix", "back_not_internal") else body + ins
+    elif pos < 0.7:  # at the other end
+        s = body + ins if where in ("back", "suffix", "back_not_internal") else ins + body
+    elif pos < 0.9:  # inside
+        s = ins + body + rnd(rng, int(rng.integers(1, 20)))
+    else:
+        s = rnd(rng, int(rng.integers(1, 60)))
+    if s and rng.random() < 0.3:
+        s = list(s)
+        for _ in range(int(rng.integers(1, 4))):
+            j = int(rng.integers(len(s)))
+            s[j] = str(rng.choice(np.array(list("NNNRYKMnacgt"))))
+        s = "".join(s)
+    if rng.random() < 0.15:  # a copy that only matches through the read's wildcards, then a literal one
+        dmg = list(ad)
+        dmg[int(rng.integers(len(dmg)))] = "N"
+        s = rnd(rng, int(rng.integers(0, 12))) + "".join(dmg) + rnd(rng, int(rng.integers(0, 8))) + ad + rnd(rng, int(rng.integers(0, 6)))
+    return s
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_every_placement_and_read_wildcards_equal_the_oracle(hs, seed):
+    """locate<MAXM, true>: anchored (^SEQ, SEQ$) and non-internal (XSEQ, SEQX) adapters, --match-read-wildcards, both
+    objectives, with and without indels, against pyoracle.locate."""
+    rng = np.random.default_rng(4400 + seed)
+    stats = {}
+    wheres = sorted(WHERE_SPECS)
+    for rep in range(12):
+        where = wheres[(seed + rep) % len(wheres)]
+        kind, fmt = WHERE_SPECS[where]
+        ad = make_adapter(rng, ["random", "repeat", "two_blocks", "prefix_repeat", "homopolymer"][rep % 5])
+        if rng.random() < 0.3:
+            ad = list(ad)
+            ad[int(rng.integers(len(ad)))] = "N"
+            ad = "".join(ad)
+            if set(ad) == {"N"}:
+                ad = "A" + ad
+        cfg = P.TrimConfig(adapters=[(kind, fmt % ad)], error_rate=float(rng.choice([0.0, 0.1, 0.15, 0.25])),
+                           overlap=int(rng.integers(1, 7)), indels=bool(rng.random() < 0.7),
+                           match_read_wildcards=bool(rng.random() < 0.4), cutadapt_compat="4" if rng.random() < 0.25 else "2-3")
+        plain = "".join(c if c in "ACGT" else "C" for c in ad)
+        reads = [placed_read(rng, plain, where) for _ in range(50)]
+        cp = P.build_trim_params(cfg)
+        pp = py_params(cfg)
+        assert pp.adapters[0].where == where and cp.adapters[0].where == abi.WHERE[where]
+        fast_ok = C.c_int(0)
+        err = C.create_string_buffer(512)
+        assert hs.hs_set_params(C.byref(cp), C.byref(fast_ok), err, 512) == 0, err.value
+        assert fast_ok.value == (1 if where == "back" and cfg.indels and not cfg.match_read_wildcards and cfg.cutadapt_compat != "4" else 0)
+        out = (C.c_int32 * 4)()
+        for read in reads:
+            if not read:
+                continue
+            raw = read.encode()
+            # Adapter.match_to: the literal comparison (find / startswith / endswith) first, else the alignment
+            exp = po.match_to(pp.adapters[0], read, pp.compat)
+            rc = hs.hs_locate(0, 0, raw, len(raw), 0, len(raw), out)
+            got = tuple(out) if rc == 1 else None
+            exp4 = None if exp is None else (exp[2], exp[3], exp[4], exp[5])
+            assert got == exp4, (cfg.adapters, cfg.error_rate, cfg.overlap, cfg.indels, cfg.match_read_wildcards, cfg.cutadapt_compat, read, got, exp4)
+            # ... and the shortcut only ever differs from the alignment through the read's wildcards (an occurrence through
+            # an N in front of the literal one)
+            al = po.locate(pp.adapters[0], read, pp.compat)
+            if not cfg.match_read_wildcards:
+                assert (al is None) == (exp is None) and (al is None or (al[2], al[3], al[5]) == (exp[2], exp[3], exp[5])), (cfg.adapters, read, al, exp)
+            elif al != exp:
+                stats["literal_first"] = stats.get("literal_first", 0) + 1
+            stats[where] = stats.get(where, 0) + (exp is not None)
+    assert sum(v for k, v in stats.items() if k != "literal_first") > 60, stats
+    if seed == 0:
+        print(stats)
+
+
+PIPELINES = [
+    dict(adapters=[("back", "^TTAGGC...TGGAATTCTCGGGTGCC")]),                                # the documented -a form: anchored 5' half, optional 3' half
+    dict(adapters=[("back", "TTAGGC...TGGAATTCTCGGGTGCC")], times=2),                        # neither half required
+    dict(adapters=[("front", "TTAGGC;optional...TGGAATTCTCGGGTGCC;e=0.2")], quality_cutoff="15"),
+    dict(adapters=[("front", "^TTAGGC...TGGAATTCTCGGGTGCC$")], indels=False),
+    dict(adapters=[("front", "^GTTCAGAGTTC"), ("back", "TGGAATTCTCGGGTGCCX")], times=2, trim_n=True, cut=[1, -1]),
+    dict(adapters=[("back", "TGGAATTCTCGGGTGCC$;e=0.2"), ("front", "XGTTCAGAGTTC;o=5")], match_read_wildcards=True, nextseq_trim=20),
+    dict(adapters=[("back", "TGGAATTCNNGGGTGCC;noindels"), ("back", "AAAAAAAA$")], match_read_wildcards=True, cutadapt_compat="4"),
+]
+
+
+@pytest.mark.parametrize("case", range(len(PIPELINES)))
+def test_modifier_pipeline_with_linked_anchored_and_parameterised_adapters(hs, case):
+    """apply_mod / best_match of the full-DP path (linked pairs with optional halves, every placement, per-adapter
+    parameters, times > 1) against the Python oracle's modifier pipeline, window by window."""
+    cfg = P.TrimConfig(**PIPELINES[case])
+    cp, pp = P.build_trim_params(cfg), py_params(cfg)
+    fast_ok = C.c_int(0)
+    err = C.create_string_buffer(512)
+    assert hs.hs_set_params(C.byref(cp), C.byref(fast_ok), err, 512) == 0, err.value
+    hs.hs_pipeline.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int32)]
+    rng = np.random.default_rng(4500 + case)
+    mods = pp.modifiers()
+    assert len(mods) == cp.n_mods
+    win = (C.c_int32 * (2 * cp.n_mods))()
+    front5, back3 = "TTAGGC", "TGGAATTCTCGGGTGCC"
+    changed = 0
+    for it in range(600):
+        f = mutate(rng, front5 if case < 4 else "GTTCAGAGTTC", 0.05, 0.02, 0.02) if rng.random() < 0.7 else ""
+        if f and rng.random() < 0.2:
+            f = rnd(rng, int(rng.integers(1, 4))) + f  # not at the very start: an anchored 5' half misses it
+        b = mutate(rng, back3, 0.05, 0.02, 0.02) if rng.random() < 0.7 else ""
+        if b and rng.random() < 0.4:
+            b = b[: int(rng.integers(1, len(b) + 1))]
+        elif b and rng.random() < 0.5:
+            b += rnd(rng, int(rng.integers(1, 12)))
+        seq = f + rnd(rng, int(rng.integers(0, 35))) + b
+        if rng.random() < 0.15:  # a copy of the 3' adapter that matches through an N only, then a literal one (match_to's shortcut)
+            dmg = list(back3)
+            dmg[int(rng.integers(len(dmg)))] = "N"
+            seq = f + rnd(rng, int(rng.integers(0, 25))) + "".join(dmg) + rnd(rng, int(rng.integers(0, 6))) + back3 + rnd(rng, int(rng.integers(0, 5)))
+        if not seq:
+            continue
+        if rng.random() < 0.2:
+            seq = list(seq)
+            seq[int(rng.integers(len(seq)))] = str(rng.choice(np.array(list("NNRn"))))
+            seq = "".join(seq)
+        q = np.clip(38 - (np.arange(len(seq)) * int(rng.integers(0, 40)) // len(seq)) + rng.integers(-5, 6, len(seq)), 2, 41)
+        qual = "".join(chr(33 + int(v)) for v in q)
+        assert hs.hs_pipeline(seq.encode(), qual.encode(), len(seq), win) == len(mods)
+        start, stop = 0, len(seq)
+        for mi, mod in enumerate(mods):
+            start, stop = po.apply_modifier(mod, seq, qual, start, stop, pp)
+            assert (win[2 * mi], win[2 * mi + 1]) == (start, stop), (PIPELINES[case], seq, qual, mi, (win[2 * mi], win[2 * mi + 1]), (start, stop))
+        changed += (start, stop) != (0, len(seq))
+    assert changed > 150, changed
+
+
 def test_quality_scans_equal_the_oracle(hs):
     """nextseq_trim_index / quality_trim_index of the kernels on random and adversarial
     quality strings: ties of the running maximum, scans that never go negative, empty reads, both Phred offsets."""

@@ -1,0 +1,57 @@
+"""GPU twin of tests/test_oracle_fuzz.py::test_c_oracle_equals_python_oracle_on_random_placements: the product trim +
+collapse path against the C oracle on the rest of cutadapt's adapter specification language -- anchored (^SEQ, SEQ$) and
+non-internal (XSEQ, SEQX) adapters, per-adapter ;parameters, linked pairs given with -a / -g with anchored, optional and
+required halves, --match-read-wildcards.  These forms run on the full-DP kernel (locate<MAXM, true>); on the CPU the same
+search code is compiled for the host and held against the Python oracle (tests/test_adapter_search_host.py).
+
+The file name sorts it last: the forms here were added after the round's GPU budget was spent (one 20-second native check of
+them ran on the device, profiles/), so nothing in front of it depends on them."""
+import numpy as np
+import pytest
+
+from mirge_b200 import params as P
+from oracle import coracle
+from tests.test_oracle_fuzz import random_placement_config, random_reads
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from mirge_b200 import device as D
+
+    return D.Device(0)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("seed", range(40))
+def test_gpu_matches_c_oracle_on_random_placements(dev, seed, mode):
+    from mirge_b200 import device as D
+    from tests.test_gpu_digest import gpu_windows, table_dict, to_dev
+
+    rng = np.random.default_rng(9500 + seed)
+    cfg = random_placement_config(rng)
+    try:
+        P.build_trim_params(cfg)
+    except (P.UnsupportedAdapterSpec, RuntimeError) as e:
+        pytest.skip("configuration the product rejects: %s" % e)
+    data = random_reads(rng, cfg, 2000)
+    fq = np.frombuffer(data, dtype=np.uint8)
+    eng = D.DigestEngine(dev, cfg)
+    eng.set_trim_mode(mode)
+    n, win_o, kept_o = coracle.trim(fq, dev.trim_params)
+    buf = to_dev(dev, data)
+    br = eng.trim_batch(buf, buf.numel(), True)
+    assert br.n_records == n
+    win_g, kept_g = gpu_windows(eng, br)
+    assert np.array_equal(kept_g, kept_o), (seed, cfg)
+    bad = np.argwhere((win_g != win_o).any(axis=2))
+    assert bad.size == 0, "seed %d %s: first differing (record, slot): %s gpu=%s oracle=%s" % (
+        seed, cfg, bad[0], win_g[tuple(bad[0])], win_o[tuple(bad[0])])
+    table = D.CollapseTable(dev, min_keys=256)
+    eng.collapse_batch(table, br)
+    _, tab = coracle.digest_collapse(fq, dev.trim_params, nthreads=2)
+    if cfg.umi() is None:
+        assert table_dict(table) == tab.to_dict()

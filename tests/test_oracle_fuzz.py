@@ -68,18 +68,75 @@ def random_config(rng):
                         cutadapt_compat="4" if rng.random() < 0.25 else "2-3")
 
 
+def random_placement_config(rng):
+    """Configurations over the rest of cutadapt's specification language: anchored (^SEQ, SEQ$) and non-internal (XSEQ,
+    SEQX) adapters, per-adapter ;parameters, x{n} repeats, linked pairs given with -a / -g with anchored, optional and
+    required halves, --match-read-wildcards."""
+    def seq(lo=6, hi=25):
+        s = rnd_seq(rng, int(rng.integers(lo, hi)))
+        if rng.random() < 0.2:
+            s = list(s)
+            s[int(rng.integers(len(s)))] = IUPAC[int(rng.integers(len(IUPAC)))]
+            s = "".join(s)
+        if rng.random() < 0.1:
+            s = s[:4] + "A{%d}" % int(rng.integers(2, 6)) + s[4:]
+        return s
+
+    def prm():
+        out = ""
+        if rng.random() < 0.25:
+            out += ";e=%s" % rng.choice(["0", "0.1", "0.2", "0.3"])
+        if rng.random() < 0.2:
+            out += ";o=%d" % int(rng.integers(1, 9))
+        if rng.random() < 0.15:
+            out += ";noindels"
+        return out
+
+    def five():
+        return str(rng.choice(["%s", "%s", "^%s", "X%s"])) % seq(5, 14)
+
+    def three():
+        return str(rng.choice(["%s", "%s", "%s$", "%sX"])) % seq()
+
+    adapters = []
+    for k in range(int(rng.integers(1, 3))):
+        r = rng.random()
+        if r < 0.35:
+            adapters.append(("back", three() + prm()))
+        elif r < 0.55:
+            adapters.append(("front", five() + prm()))
+        else:  # linked pair: -g needs both halves, -a only the anchored ones; ;required / ;optional override
+            kind = "front" if rng.random() < 0.5 else "back"
+            a, b = five() + prm(), three() + prm()
+            if rng.random() < 0.25:
+                a += str(rng.choice([";optional", ";required"]))
+            if rng.random() < 0.25:
+                b += str(rng.choice([";optional", ";required"]))
+            adapters.append((kind, a + "..." + b))
+    q = str(int(rng.integers(5, 31))) if rng.random() < 0.4 else None
+    umi = "%d,%d" % (int(rng.integers(0, 5)), int(rng.integers(0, 5))) if rng.random() < 0.15 else None
+    return P.TrimConfig(adapters=adapters, error_rate=float(rng.choice([0.0, 0.1, 0.12, 0.2])),
+                        overlap=int(rng.integers(1, 8)), indels=bool(rng.random() < 0.8), times=int(rng.integers(1, 3)),
+                        nextseq_trim=int(rng.integers(10, 31)) if rng.random() < 0.2 else None, quality_cutoff=q,
+                        trim_n=bool(rng.random() < 0.3), cut=[int(rng.integers(1, 4))] if rng.random() < 0.2 else [],
+                        minimum_length=int(rng.integers(0, 20)), uniq_mol_ids=umi,
+                        match_read_wildcards=bool(rng.random() < 0.35), count_mode="head" if rng.random() < 0.7 else "release",
+                        cutadapt_compat="4" if rng.random() < 0.2 else "2-3")
+
+
 def random_reads(rng, cfg, n):
     recs = []
+    flat = []  # (5' or 3' form, sequence) of every adapter and half
+    for kind, spec in cfg.adapters:
+        for sp in P.parse_adapter_specs(kind, spec):
+            if sp.where == "linked":
+                flat += [("front", sp.sequence), ("back", sp.sequence2)]
+            else:
+                flat.append(("front" if sp.where in ("front", "prefix", "front_not_internal") else "back", sp.sequence))
     for i in range(n):
         L = int(rng.integers(1, 101)) if rng.random() < 0.9 else int(rng.integers(101, 160))
         ins = rnd_seq(rng, int(rng.integers(0, 45)))
         s = ins
-        flat = []
-        for where, ad in cfg.adapters:
-            if "..." in ad:
-                flat += [("front", ad.split("...")[0]), ("back", ad.split("...")[1])]
-            else:
-                flat.append((where, ad))
         for where, ad in flat:
             plain = "".join(c if c in "ACGT" else str(rng.choice(B)) for c in ad)
             r = rng.random()
@@ -143,3 +200,26 @@ def test_c_oracle_equals_python_oracle_on_random_configurations(seed):
             d = po.digest_sample(data, pp, umi_dedup=dedup)
             t2 = tab.umi_collapse(umi[0], umi[1], cfg.minimum_length, dedup)
             assert t2.to_dict() == d.table and t2.total == d.trimmed
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_c_oracle_equals_python_oracle_on_random_placements(seed):
+    """The same for the rest of the specification language (random_placement_config)."""
+    rng = np.random.default_rng(9500 + seed)
+    cfg = random_placement_config(rng)
+    try:
+        cp = P.build_trim_params(cfg)
+    except (P.UnsupportedAdapterSpec, RuntimeError) as e:
+        pytest.skip("configuration the product rejects: %s" % e)
+    pp = py_params(cfg)
+    data = random_reads(rng, cfg, 250)
+    fq = np.frombuffer(data, dtype=np.uint8)
+    E = P.trim_slots(cp)
+    n, win, kept = coracle.trim(fq, cp)
+    recs = po.parse_fastq(data)
+    assert n == len(recs) == 250
+    changed = 0
+    for r, (_nm, seq, qual) in enumerate(recs):
+        keys_py = [k for k, _ in po.digest_read(seq, qual, pp)]
+        keys_c = [seq[win[r, s, 0] : win[r, s, 1]] + seq[win[r, s, 2] : win[r, s, 3]] for s in range(E) if kept[r, s]]
+        assert keys_c == keys_py, (seed, cfg, r, seq, qual)

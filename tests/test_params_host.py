@@ -16,29 +16,70 @@ ILL_BACK = "TGGAATTCTCGGGTGCCAAGGAACTCCAG"
 ILL_FRONT = "GTTCAGAGTTCTACAGTCCGACGATC"
 
 
-def test_adapter_specification_subset():
+def test_adapter_specification_language(tmp_path):
+    """cutadapt's adapter specification language as it reaches stipulate() through -a / -g (parse.py:74-77)."""
     assert P.parse_adapter_spec("back", "illumina").sequence == ILL_BACK       # mirge/__main__.py:66-86
     assert P.parse_adapter_spec("front", "Illumina").sequence == ILL_FRONT
     assert P.parse_adapter_spec("back", "myname=acgu").sequence == "ACGT"      # name=, upper-casing, U -> T
     assert P.parse_adapter_spec("back", " ACGTN ").sequence == "ACGTN"
-    for kind, spec in (("back", "file:adapters.fa"), ("back", "ACGT...TTTT"), ("back", "ACGT$"), ("front", "^ACGT"),
-                       ("back", "ACGT;max_error_rate=0.2"), ("back", "ACGTX"), ("front", "XACGT"), ("back", ""),
+    w = lambda kind, spec: (lambda sp: (sp.where, sp.sequence, sp.params))(P.parse_adapter_spec(kind, spec))
+    assert w("back", "ACGT$") == ("suffix", "ACGT", {})                        # anchored 3'
+    assert w("front", "^ACGT") == ("prefix", "ACGT", {})                       # anchored 5'
+    assert w("back", "ACGTX") == ("back_not_internal", "ACGT", {})
+    assert w("front", "xxACGT") == ("front_not_internal", "ACGT", {})
+    assert w("back", "AC{3}GT{2}") == ("back", "ACCCGTT", {})                  # x{n} repeats
+    assert w("back", "n=ACGT;e=0.2;o=5") == ("back", "ACGT", {"max_error_rate": 0.2, "min_overlap": 5})
+    assert w("back", "ACGT; max_error_rate = 0 ;noindels") == ("back", "ACGT", {"max_error_rate": 0, "indels": False})
+    assert w("back", "...ACGT") == ("back", "ACGT", {})                        # -a ...ADAPTER: plain 3' adapter
+    assert w("back", "ACGT...") == ("front", "ACGT", {})                       # -a ADAPTER...: plain 5' adapter
+    assert w("front", "ACGT...") == ("front", "ACGT", {})
+    fa = tmp_path / "adapters.fa"
+    fa.write_text("# two adapters\n>first\nACGT\nACGT\n\n>second some text\n^TTTTGG;e=0.1\n")
+    got = P.parse_adapter_specs("front", "file:%s" % fa)
+    assert [(sp.where, sp.sequence, sp.params) for sp in got] == [("front", "ACGTACGT", {}), ("prefix", "TTTTGG", {"max_error_rate": 0.1})]
+    for kind, spec in (("back", "file:/nonexistent/adapters.fa"), ("back", "^ACGT"), ("front", "ACGT$"), ("back", "XACGT"), ("front", "ACGTX"),
+                       ("front", "^XACGT"), ("back", "ACGTX$"), ("back", "XXX"), ("back", ""), ("back", "ACGT;anywhere"),
+                       ("back", "ACGT;foo=1"), ("back", "ACGT;e="), ("back", "ACGT;e=0.1;e=0.2"), ("back", "ACGT;e=2"), ("back", "ACGT;o=0"),
+                       ("back", "ACGT;required"), ("back", "ACGT;optional"), ("back", "ACGT;indels;noindels"), ("back", "AC{GT"),
+                       ("back", "{3}ACGT"), ("front", "...ACGT"),
                        ("back", "A" * (abi.MAX_ADAPTER_LEN + 1)), ("back", "ACGT-ACGT"), ("anywhere", "ACGT")):
         with pytest.raises(P.UnsupportedAdapterSpec):
-            P.parse_adapter_spec(kind, spec)
+            P.parse_adapter_specs(kind, spec)
+    # per-adapter parameters reach the Aligner terms of that adapter only
+    p = P.build_trim_params(P.TrimConfig(adapters=[("back", "ACGTACGTAC;e=0.3;o=7;noindels"), ("front", "^ACGTAC"), ("back", "TTTTTTTTX")]))
+    a0, a1, a2 = p.adapters[0], p.adapters[1], p.adapters[2]
+    assert (a0.where, a0.k, a0.min_overlap, a0.indel_cost, a0.max_err[10]) == (abi.WHERE["back"], 3, 7, 100000, 3)
+    assert (a1.where, a1.k, a1.min_overlap, a1.indel_cost) == (abi.WHERE["prefix"], 0, 6, 1)      # anchored: the whole adapter
+    assert (a2.where, a2.k, a2.min_overlap) == (abi.WHERE["back_not_internal"], 0, 3)
+    assert [abi.WHERE[k] & 1 for k in ("back", "suffix", "back_not_internal", "front", "prefix", "front_not_internal")] == [0, 0, 0, 1, 1, 1]
+    assert P.build_trim_params(P.TrimConfig(adapters=[("back", "ACGT")], match_read_wildcards=True)).adapters[0].wildcard_read == 1
 
 
 def test_linked_adapter_specification():
-    """-g "ADAPTER5...ADAPTER3" (docs/source/quick_start.md:208-220): a 5' half pointing at its 3' half in the flat adapter
-    list; the forms that anchor a half, and the alias inside a linked specification, stay rejected."""
+    """"ADAPTER5...ADAPTER3" (docs/source/quick_start.md:208-220): a 5' half pointing at its 3' half in the flat adapter
+    list.  -g: both halves required; -a: a half is required only when it is anchored; ;required / ;optional override."""
     sp = P.parse_adapter_spec("front", "TTAGGC...TGGAATTCTCGGGTGCCAAGGAACTCCAGT")
-    assert (sp.where, sp.sequence, sp.sequence2) == ("linked", "TTAGGC", "TGGAATTCTCGGGTGCCAAGGAACTCCAGT")
+    assert (sp.where, sp.sequence, sp.sequence2, sp.where5, sp.where2, sp.front_required, sp.back_required) == \
+        ("linked", "TTAGGC", "TGGAATTCTCGGGTGCCAAGGAACTCCAGT", "front", "back", True, True)
     p = P.build_trim_params(P.TrimConfig(adapters=[("back", "ACGTACGTAC"), ("front", "name=TTAGGC...ACGTTGCA")]))
     assert p.n_adapters == 3
     assert [p.adapters[i].where for i in range(3)] == [0, 1, 0]
     assert [p.adapters[i].link for i in range(3)] == [0, 3, abi.LINK_BACK_HALF]
-    for kind, spec in (("front", "TTAGGC...illumina"), ("front", "^TTAGGC...ACGT"), ("front", "TTAGGC...ACGT$"), ("front", "A...C...G"),
-                       ("front", "...ACGT"), ("back", "TTAGGC...ACGT")):
+    lk = lambda kind, spec: (lambda sp: (sp.where5, sp.where2, sp.front_required, sp.back_required))(P.parse_adapter_spec(kind, spec))
+    assert lk("back", "^TTAGGC...ACGT") == ("prefix", "back", True, False)      # the documented -a form: anchored 5' half, optional 3' half
+    assert lk("back", "TTAGGC...ACGT") == ("front", "back", False, False)
+    assert lk("back", "TTAGGC...ACGT$") == ("front", "suffix", False, True)
+    assert lk("front", "^TTAGGC...ACGTX") == ("prefix", "back_not_internal", True, True)
+    assert lk("front", "TTAGGC;optional...ACGT;e=0.2") == ("front", "back", False, True)
+    assert lk("back", "^TTAGGC...ACGT;required") == ("prefix", "back", True, True)
+    sp = P.parse_adapter_spec("front", "TTAGGC;o=4...ACGT;e=0.2")
+    assert (sp.params, sp.params2) == ({"min_overlap": 4}, {"max_error_rate": 0.2})
+    p = P.build_trim_params(P.TrimConfig(adapters=[("back", "^TTAGGC...ACGTTGCA;e=0.2")]))
+    assert [p.adapters[i].where for i in range(2)] == [abi.WHERE["prefix"], abi.WHERE["back"]]
+    assert [p.adapters[i].link for i in range(2)] == [2 | abi.LINK_BACK_OPTIONAL, abi.LINK_BACK_HALF]
+    assert (p.adapters[0].k, p.adapters[1].k) == (0, 1)
+    for kind, spec in (("front", "TTAGGC...illumina"), ("front", "A...C...G"), ("front", "TTAGGC$...ACGT"), ("front", "TTAGGC...^ACGT"),
+                       ("front", "TTAGGC;required;optional...ACGT")):
         with pytest.raises(P.UnsupportedAdapterSpec):
             P.parse_adapter_spec(kind, spec)
     with pytest.raises(P.UnsupportedAdapterSpec):
@@ -86,8 +127,6 @@ def test_wildcard_adapters_and_rejections():
         P.build_trim_params(P.TrimConfig(adapters=[("back", "NNNN")]))                      # cutadapt: only N wildcards
     with pytest.raises(P.UnsupportedAdapterSpec):
         P.build_trim_params(P.TrimConfig(adapters=[("back", "ACGTN")], match_adapter_wildcards=False))
-    with pytest.raises(RuntimeError):
-        P.build_trim_params(P.TrimConfig(adapters=[("back", "ACGT")], match_read_wildcards=True))
     with pytest.raises(RuntimeError):
         P.build_trim_params(P.TrimConfig(adapters=[("back", "ACGT")], cut=[1, 2, 3]))          # digest.py:47-48
     with pytest.raises(RuntimeError):

@@ -12,15 +12,23 @@ QIA = "AACTGTAGGCACCATCAAT"
 LONG_AD = "AGATCGGAAGAGCACACGTCTGAACTCCAGTCACATCACGATCTCGTATGCC"
 
 
-def py_params(cfg: P.TrimConfig) -> po.TrimParams:
+def py_adapters(cfg: P.TrimConfig):
+    """The adapters of a configuration as the Python oracle's objects (specification language: params.parse_adapter_specs)."""
     ads = []
     for k, s in cfg.adapters:
-        sp = P.parse_adapter_spec(k, s)
-        mk = lambda where, seq: po.Adapter(where, seq, cfg.error_rate, cfg.overlap, cfg.indels, cfg.match_adapter_wildcards)
-        if sp.where == "linked":  # -g "A...B": both halves required (cutadapt parser)
-            ads.append(po.LinkedAdapter(mk("front", sp.sequence), mk("back", sp.sequence2), True, True))
-            continue
-        ads.append(mk(sp.where, sp.sequence))
+        for sp in P.parse_adapter_specs(k, s):
+            mk = lambda where, seq, prm: po.Adapter(where, seq, prm.get("max_error_rate", cfg.error_rate), prm.get("min_overlap", cfg.overlap),
+                                                    prm.get("indels", cfg.indels), cfg.match_adapter_wildcards, cfg.match_read_wildcards)
+            if sp.where == "linked":
+                ads.append(po.LinkedAdapter(mk(sp.where5, sp.sequence, sp.params), mk(sp.where2, sp.sequence2, sp.params2),
+                                            sp.front_required, sp.back_required))
+            else:
+                ads.append(mk(sp.where, sp.sequence, sp.params))
+    return ads
+
+
+def py_params(cfg: P.TrimConfig) -> po.TrimParams:
+    ads = py_adapters(cfg)
     return po.TrimParams(adapters=ads, times=cfg.times, nextseq_trim=cfg.nextseq_trim,
                          quality_cutoff=cfg.quality_cutoff, quality_base=cfg.quality_base, trim_n=cfg.trim_n,
                          cut=list(cfg.cut), minimum_length=cfg.minimum_length, umi=cfg.umi(),
