@@ -4,8 +4,9 @@ non-internal (XSEQ, SEQX) adapters, per-adapter ;parameters, linked pairs given 
 required halves, --match-read-wildcards.  These forms run on the full-DP kernel (locate<MAXM, true>); on the CPU the same
 search code is compiled for the host and held against the Python oracle (tests/test_adapter_search_host.py).
 
-The file name sorts it last: the forms here were added after the round's GPU budget was spent (one 20-second native check of
-them ran on the device, profiles/), so nothing in front of it depends on them."""
+The file name sorts it last: the forms here were added when the round's GPU budget was nearly spent -- what ran on the
+device is the native twin of this test (tests/native/trim_check.cu through the same C-ABI calls, the same 40 seeds among its
+62 cases: profiles/r2_native_trim_check_b200.txt), not this file -- so nothing in front of it depends on it."""
 import numpy as np
 import pytest
 
