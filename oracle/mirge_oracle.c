@@ -123,7 +123,10 @@ static int locate(const mirge_adapter *ad, const uint8_t *read, int n, match_t *
     int dc = cost[0], dor = origin[0], dm = matches[0];
     if (start_in_query) origin[0] = j;
     else { cost[0] = j * ic; matches[0] = j * w_indel; }
+    /* without any wildcards _align.pyx compares the characters themselves: a U in the read is a T only through its
+     * translation tables (adapter or read wildcards active) */
     int rc = ad->wildcard_read ? iupac_mask(read[j - 1]) : acgt_mask(read[j - 1]);
+    if (!ad->wildcard_read && !ad->wildcard_ref && upper(read[j - 1]) == 'U') rc = 0;
     for (int i = 1; i <= m; ++i) {
       int c, o, mt;
       if (ad->mask[i - 1] & rc) { c = dc; o = dor; mt = dm + 1; }

@@ -159,6 +159,7 @@ IUPAC = {
     "B": 2 | 4 | 8, "D": 1 | 4 | 8, "H": 1 | 2 | 8, "V": 1 | 2 | 4, "N": 15, "X": 0,
 }
 ACGT = {"A": 1, "C": 2, "G": 4, "T": 8, "U": 8}
+ACGT_ASCII = {"A": 1, "C": 2, "G": 4, "T": 8}  # plain character comparison: a U in the read is not a T
 
 INDEL_OFF_COST = 100000  # cutadapt adapters.py: "indel_cost = 1 if self.indels else 100000"
 
@@ -260,7 +261,10 @@ def locate(ad: Adapter, read: str, compat: str = "2-3") -> Optional[Tuple[int, i
     up = read.upper()
     # read characters -> 4-bit class: a character outside ACGT never matches, unless --match-read-wildcards
     # (parse.py:97) turns the read's IUPAC characters into sets as well (_align.pyx: query translated with IUPAC_TABLE)
-    rmask = [(IUPAC if ad.read_wildcards else ACGT).get(ch, 0) for ch in up]
+    # Without any wildcards _align.pyx compares the ASCII characters themselves; its translation tables -- in which a U
+    # stands for T -- are only in use when adapter or read wildcards are active.
+    table = IUPAC if ad.read_wildcards else (ACGT if ad.wildcard_ref else ACGT_ASCII)
+    rmask = [table.get(ch, 0) for ch in up]
     start_in_ref, stop_in_ref, start_in_query, stop_in_query = WHERE_FLAGS[ad.where]
     if compat not in ("2-3", "4"):
         raise ValueError("compat must be '2-3' or '4'")

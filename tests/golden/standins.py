@@ -90,7 +90,10 @@ class AdapterCutter:
             ad, mt = po.best_match(self.adapters, read.sequence)
             if mt is None:
                 break
-            read = read[: mt[2]] if ad.where == "back" else read[mt[3]:]
+            if ad.where == "linked":
+                read = read[mt[2] : mt[3]]
+            else:
+                read = read[mt[3]:] if ad.where in po.REMOVE_BEFORE else read[: mt[2]]
         return read
 
 

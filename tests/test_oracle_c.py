@@ -40,6 +40,33 @@ def test_c_matches_python(name):
             assert t2.to_dict() == d.table and t2.total == d.trimmed
 
 
+def test_u_in_reads_is_t_only_through_the_wildcard_tables():
+    """cutadapt compares characters when no wildcard is active (a U in the read is not a T) and translated sets when the
+    adapter or the read may hold wildcards (U = T): both oracles, on reads that carry the adapter with U for T."""
+    rng = np.random.default_rng(5)
+    B = np.array(list("ACGT"))
+    for name in ("default", "wild"):
+        cfg = CONFIGS[name]
+        ad = cfg.adapters[0][1].replace("N", "A").replace("R", "G")
+        recs, n_u = [], 0
+        for i in range(300):
+            s = "".join(rng.choice(B, int(rng.integers(16, 30)))) + ad
+            if i % 2:
+                s = s.replace("T", "U")
+                n_u += 1
+            recs.append("@r%d\n%s\n+\n%s\n" % (i, s, "I" * len(s)))
+        data = "".join(recs).encode()
+        cp, pp = P.build_trim_params(cfg), py_params(cfg)
+        n, win, kept = coracle.trim(np.frombuffer(data, dtype=np.uint8), cp)
+        trimmed_u = 0
+        for r, (_nm, seq, qual) in enumerate(po.parse_fastq(data)):
+            w_py = po.digest_read(seq, qual, pp)[-1][1]
+            assert tuple(int(x) for x in win[r, -1]) == tuple(w_py), (name, seq)
+            trimmed_u += "U" in seq and w_py[1] < len(seq)
+        # plain adapter: the U reads keep their adapter (apart from chance partial matches); wildcard adapter: all are trimmed
+        assert (trimmed_u == n_u) if name == "wild" else (trimmed_u < n_u // 4), (name, trimmed_u, n_u)
+
+
 def test_crlf_and_no_final_newline():
     cfg = CONFIGS["default"]
     cp = P.build_trim_params(cfg)

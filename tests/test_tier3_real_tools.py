@@ -104,6 +104,64 @@ def test_adapter_trim_points_match_cutadapt(where, indels):
                 assert merit == o[4], (cutadapt.__version__, read, merit, o)
 
 
+SPEC_CASES = [  # (-a / -g arguments, --match-read-wildcards): the specification language beyond plain adapters
+    ([("back", ILL + "$")], False), ([("front", "^GTTCAGAGTTCTAC")], False), ([("back", ILL + "X")], False),
+    ([("front", "XGTTCAGAGTTCTAC")], False), ([("back", ILL + ";e=0.2;o=6")], False), ([("back", "TGGAA{3}TTCTCGG")], False),
+    ([("front", "GTTCAGAGTTCTAC..." + ILL)], False), ([("back", "GTTCAGAGTTCTAC..." + ILL)], False),
+    ([("back", "^GTTCAGAGTTCTAC..." + ILL)], False), ([("front", "GTTCAGAGTTCTAC;optional..." + ILL + ";e=0.2")], False),
+    ([("back", "GTTCAGAGTTCTAC;required..." + ILL + "$")], False), ([("back", ILL)], True), ([("front", "GTTCAGAGTTCTAC"), ("back", ILL + "X")], True),
+]
+
+
+@pytest.mark.parametrize("case", range(len(SPEC_CASES)))
+def test_specification_language_matches_cutadapt(case):
+    """The adapters exactly as the reference's stipulate() makes them (digest.py:66-85: cutadapt's own parser on
+    args.adapters) and cutadapt's AdapterCutter on reads, against params.parse_adapter_specs + the oracle's modifier:
+    placements, per-adapter parameters, linked pairs with required / optional halves, read wildcards."""
+    cutadapt = _real_cutadapt()
+    from cutadapt.modifiers import AdapterCutter
+
+    from mirge_b200 import params as P
+    from tests.util import py_params
+
+    specs, read_wild = SPEC_CASES[case]
+    search = dict(max_errors=0.12, min_overlap=3, read_wildcards=read_wild, adapter_wildcards=True, indels=True)
+    try:
+        from cutadapt.parser import make_adapters_from_specifications
+
+        adapters = make_adapters_from_specifications(specs, search)
+    except ImportError:
+        from cutadapt.parser import AdapterParser
+
+        search["max_error_rate"] = search.pop("max_errors")
+        adapters = AdapterParser(**search).parse_multi(specs)
+    cutter = AdapterCutter(adapters, 2, "trim")
+    major = int(str(cutadapt.__version__).split(".")[0])
+    cfg = P.TrimConfig(adapters=specs, times=2, quality_cutoff=None, match_read_wildcards=read_wild,
+                       cutadapt_compat="4" if major >= 4 else "2-3")
+    pp = py_params(cfg)
+    mod = [m for m in pp.modifiers() if m[0] == "adapter"][0]
+    from dnaio import Sequence
+
+    rng = np.random.default_rng(100 + case)
+    front = "GTTCAGAGTTCTAC"
+    for read in _reads(rng, ILL, 1500):
+        if rng.random() < 0.5:  # a 5' adapter (damaged, sometimes not at the very start) in front
+            f = "".join(str(rng.choice(B)) if rng.random() < 0.05 else c for c in front)
+            read = ("".join(rng.choice(B, int(rng.integers(1, 4)))) if rng.random() < 0.2 else "") + f + read
+        if not read:
+            continue
+        rec = Sequence("r", read, "I" * len(read))
+        try:
+            out = cutter(rec, [])
+        except TypeError:
+            from cutadapt.info import ModificationInfo
+
+            out = cutter(rec, ModificationInfo(rec))
+        start, stop = po.apply_modifier(mod, read, "I" * len(read), 0, len(read), pp)
+        assert out.sequence == read[start:stop], (cutadapt.__version__, specs, read_wild, read, out.sequence, read[start:stop])
+
+
 def test_quality_trimmers_match_cutadapt():
     _real_cutadapt()
     from cutadapt.qualtrim import nextseq_trim_index, quality_trim_index
