@@ -28,6 +28,49 @@ def shard_ranges(total: int, world: int):
     return out
 
 
+def gather_arrays(arrays, dst: int = 0, group=None, device=None):
+    """Every rank's list of numpy arrays at rank ``dst``: returns [[arrays of rank 0], [arrays of rank 1], ...] there, None
+    elsewhere.  The ranks pass the same number of arrays with the same dtype kinds; lengths (and, for byte strings, the
+    item size) may differ.  One all-gather of the sizes, then one exact-size point-to-point transfer of raw bytes per
+    rank -- no pickling of row objects (``gather_object``), which is what a cohort-sized table cannot afford.
+    ``device``: where the transport wants its tensors (the rank's GPU for NCCL, None / cpu for gloo)."""
+    import numpy as np
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    tdev = torch.device("cpu") if device is None else torch.device(device)
+    glob = (lambda r: dist.get_global_rank(group, r)) if group is not None else (lambda r: r)
+    arrs = [np.ascontiguousarray(a) for a in arrays]
+    meta = torch.tensor([[a.size, a.dtype.itemsize] for a in arrs], dtype=torch.int64).reshape(-1).to(tdev)
+    metas = [torch.empty_like(meta) for _ in range(world)]
+    dist.all_gather(metas, meta, group=group)
+    flat = np.concatenate([a.reshape(-1).view(np.uint8) for a in arrs]) if arrs else np.zeros(0, dtype=np.uint8)
+    payload = torch.from_numpy(flat).to(tdev)
+    if rank != dst:
+        if payload.numel():
+            dist.send(payload, glob(dst), group=group)
+        return None
+    out = []
+    for r in range(world):
+        sizes = metas[r].cpu().numpy().reshape(-1, 2)
+        total = int((sizes[:, 0] * sizes[:, 1]).sum())
+        if r == rank:
+            raw = flat
+        else:
+            buf = torch.empty(total, dtype=torch.uint8, device=tdev)
+            if total:
+                dist.recv(buf, glob(r), group=group)
+            raw = buf.cpu().numpy()
+        got, o = [], 0
+        for a, (n, item) in zip(arrs, sizes.tolist()):
+            dt = np.dtype("S%d" % item) if a.dtype.kind == "S" else a.dtype
+            if dt.itemsize != item:
+                raise RuntimeError("gather_arrays: rank %d sent items of %d bytes where this rank has %s" % (r, item, a.dtype))
+            got.append(raw[o : o + n * item].view(dt).reshape(n))
+            o += n * item
+        out.append(got)
+    return out
+
+
 def exchange_records(rec: torch.Tensor, sizes: torch.Tensor, send_recs: torch.Tensor, group=None,
                      send_words: torch.Tensor = None, recv_buffer=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """All-to-all of variable-size records.
@@ -646,8 +689,9 @@ def baking_sharded(args, inFileArray, inFileBaseArray, workDir, device=None, cou
     trc = {n: int(tot_h[1, j]) for j, n in enumerate(names)}
     tru = {n: int(tot_h[2, j]) for j, n in enumerate(names)}
     keys = owner.export_keys()
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object((keys, per_sample), gathered, dst=0, group=group)
+    # the owners' keys and per-sample (id, count) columns at rank 0 as raw arrays (no pickled rows)
+    flat = gather_arrays([keys] + [a for pair in per_sample for a in pair], 0, group, dev.tdev if dist.get_backend(group) == "nccl" else None)
+    gathered = None if flat is None else [(g[0], [(g[1 + 2 * j], g[2 + 2 * j]) for j in range(len(names))]) for g in flat]
     _SHARD.clear()
     _SHARD.update(dev=dev, owner=owner, n_own=int(keys.shape[0]))
     if rank != 0:
@@ -698,18 +742,18 @@ def bwtAlign_sharded(args, pdDataFrame, workDir, ref_db, libraries=None, group=N
     annot_d, hit_d = MA.annotate_keys(dev, libs, MA.KeySet.from_table(owner), spike)
     annot = annot_d.cpu().numpy()
     _, _mm, ref, _off = MA.decode_hits(annot, hit_d.cpu().numpy())
-    names = np.full(annot.shape[0], "", dtype=object)
-    for rnd in range(10 if spike else 9):
-        rows = np.nonzero(annot == rnd)[0]
-        if rows.size:
-            names[rows] = np.asarray(libs[ROUND_LIBS[rnd]].names, dtype=object)[ref[rows]]
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object((annot, names), gathered, dst=0, group=group)
+    # round and reference index of every owned sequence at rank 0; the names are looked up there (libraries are replicated)
+    gathered = gather_arrays([annot.astype(np.uint8), ref.astype(np.int64)], 0, group, dev.tdev if dist.get_backend(group) == "nccl" else None)
     if rank != 0:
         return None
     order = _SHARD["order"]
     annot_all = np.concatenate([g[0] for g in gathered]) if _SHARD["n_all"] else np.zeros(0, dtype=np.uint8)
-    names_all = np.concatenate([g[1] for g in gathered]) if _SHARD["n_all"] else np.zeros(0, dtype=object)
+    ref_all = np.concatenate([g[1] for g in gathered]) if _SHARD["n_all"] else np.zeros(0, dtype=np.int64)
+    names_all = np.full(annot_all.shape[0], "", dtype=object)
+    for rnd in range(10 if spike else 9):
+        rows = np.nonzero(annot_all == rnd)[0]
+        if rows.size:
+            names_all[rows] = np.asarray(libs[ROUND_LIBS[rnd]].names, dtype=object)[ref_all[rows]]
     a, nm = annot_all[order], names_all[order]
     colnames = list(pdDataFrame.columns)
     for rnd in range(10 if spike else 9):

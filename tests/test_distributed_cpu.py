@@ -111,6 +111,54 @@ def test_hash_partitioned_exchange_world2():
     assert len(results[0]) > 0 and len(results[1]) > 0
 
 
+def gather_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(50 + rank)
+        n = [700, 0, 1300][rank]  # one rank owns nothing
+        width = [30, 1, 75][rank]  # the key columns of the ranks differ in width
+        keys = np.array(["".join(rng.choice(list("ACGT"), int(rng.integers(1, width + 1)))) for _ in range(n)], dtype="S%d" % width) \
+            if n else np.zeros(0, dtype="S1")
+        cols = []
+        for j in range(3):  # three samples: (ids, counts) of unequal lengths
+            m = int(rng.integers(0, n + 1)) if n else 0
+            cols += [rng.integers(0, max(n, 1), m).astype(np.int64), rng.integers(1, 1000, m).astype(np.int64)]
+        annot = rng.integers(0, 256, n).astype(np.uint8)
+        got = MD.gather_arrays([keys] + cols + [annot], 0)
+        assert (got is None) == (rank != 0)
+        q.put((rank, [keys] + cols + [annot], got))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_arrays_world3():
+    """The row gather of baking_sharded / bwtAlign_sharded: raw arrays of unequal length (byte-string columns of unequal
+    width, an empty rank) arrive at rank 0 as every rank sent them."""
+    world = 3
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=gather_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        rank, sent, got = q.get(timeout=120)
+        res[rank] = (sent, got)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    got = res[0][1]
+    assert len(got) == world
+    for r in range(world):
+        sent = res[r][0]
+        assert len(got[r]) == len(sent)
+        for a, b in zip(sent, got[r]):
+            assert a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b), (r, a.dtype, b.dtype)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # distributed.ShardedCollapse (sharding before the collapse): the round protocol on CPU / gloo.  The three kernels
 # (mirge_shard_scatter, the arena placement + mirge_shard_rebase, mirge_collapse_insert_list) are replaced by numpy
