@@ -690,7 +690,7 @@ def baking_sharded(args, inFileArray, inFileBaseArray, workDir, device=None, cou
     tru = {n: int(tot_h[2, j]) for j, n in enumerate(names)}
     keys = owner.export_keys()
     # the owners' keys and per-sample (id, count) columns at rank 0 as raw arrays (no pickled rows)
-    flat = gather_arrays([keys] + [a for pair in per_sample for a in pair], 0, group, dev.tdev if dist.get_backend(group) == "nccl" else None)
+    flat = gather_arrays([keys] + [a for pair in per_sample for a in pair], 0, group, dev.tdev if "nccl" in str(dist.get_backend(group)) else None)
     gathered = None if flat is None else [(g[0], [(g[1 + 2 * j], g[2 + 2 * j]) for j in range(len(names))]) for g in flat]
     _SHARD.clear()
     _SHARD.update(dev=dev, owner=owner, n_own=int(keys.shape[0]))
@@ -743,7 +743,7 @@ def bwtAlign_sharded(args, pdDataFrame, workDir, ref_db, libraries=None, group=N
     annot = annot_d.cpu().numpy()
     _, _mm, ref, _off = MA.decode_hits(annot, hit_d.cpu().numpy())
     # round and reference index of every owned sequence at rank 0; the names are looked up there (libraries are replicated)
-    gathered = gather_arrays([annot.astype(np.uint8), ref.astype(np.int64)], 0, group, dev.tdev if dist.get_backend(group) == "nccl" else None)
+    gathered = gather_arrays([annot.astype(np.uint8), ref.astype(np.int64)], 0, group, dev.tdev if "nccl" in str(dist.get_backend(group)) else None)
     if rank != 0:
         return None
     order = _SHARD["order"]
