@@ -58,9 +58,13 @@ def inflate_pool(threads: Optional[int] = None) -> ThreadPoolExecutor:
 
 
 def sniff(path: str) -> str:
-    """'bgzf', 'gzip' or 'plain' from the first bytes of the file (xopen decides by magic number too)."""
+    """'bgzf', 'gzip', 'bz2', 'xz' or 'plain' from the first bytes of the file (xopen decides by magic number too)."""
     with open(path, "rb") as f:
         head = f.read(18)
+    if head[:3] == b"BZh":
+        return "bz2"
+    if head[:6] == b"\xfd7zXZ\x00":
+        return "xz"
     if len(head) < 2 or head[:2] != b"\x1f\x8b":
         return "plain"
     if len(head) >= 18 and head[2] == 8 and (head[3] & 4):
@@ -110,6 +114,16 @@ def _gzip_chunks(path: str) -> Iterator[bytes]:
                     fed = False
                 else:
                     buf = d.unconsumed_tail
+
+
+def _module_chunks(opener, path: str) -> Iterator[bytes]:
+    """bzip2 / xz input (xopen takes both): the standard library's reader, multi-stream files included, one core."""
+    with opener(path, "rb") as f:
+        while True:
+            b = f.read(CHUNK)
+            if not b:
+                return
+            yield b
 
 
 _pgz = None
@@ -407,7 +421,7 @@ class PlainReader:
 
 
 def open_fastq(path: str, threads: Optional[int] = None, depth: int = 4):
-    """Reader for one FASTQ file: plain, gzip or BGZF by magic number (not by suffix, like xopen)."""
+    """Reader for one FASTQ file: plain, gzip, BGZF, bzip2 or xz by magic number (what xopen(path, "rb") takes, digest.py:136)."""
     kind = sniff(path)
     if kind == "plain" and os.path.isfile(path):
         return PlainReader(path, threads)
@@ -422,6 +436,14 @@ def open_fastq(path: str, threads: Optional[int] = None, depth: int = 4):
             wave_out = 4 * int(threads or default_threads()) * PGZ_CHUNK
             return ChunkReader(lambda: _pgzip_chunks(path, threads), max(depth, -(-2 * wave_out // CHUNK)), name=path)
         return ChunkReader(lambda: _gzip_chunks(path), depth, name=path)
+    if kind == "bz2":
+        import bz2
+
+        return ChunkReader(lambda: _module_chunks(bz2.open, path), depth, name=path)
+    if kind == "xz":
+        import lzma
+
+        return ChunkReader(lambda: _module_chunks(lzma.open, path), depth, name=path)
     return ChunkReader(lambda: _plain_chunks(path), depth, name=path)
 
 

@@ -124,6 +124,28 @@ def test_small_chunks_all_formats(files, monkeypatch):
         assert r.read() == data[10:]
 
 
+def test_bzip2_and_xz_inputs(files, tmp_path):
+    """xopen(path, "rb") also takes bzip2 and xz files (by magic number): same bytes, multi-stream files included, a
+    truncated file raises."""
+    import bz2
+    import lzma
+
+    _, data, _ = files
+    half = len(data) // 2
+    for name, mod in (("reads.fastq.bz2", bz2), ("reads.fastq.xz", lzma), ("reads_without_suffix", bz2)):
+        p = str(tmp_path / name)
+        with open(p, "wb") as f:
+            f.write(mod.compress(data[:half]) + mod.compress(data[half:]))  # two streams
+        assert ingest.sniff(p) == ("bz2" if mod is bz2 else "xz")
+        with ingest.open_fastq(p, threads=2) as r:
+            assert read_all(r, 1 << 20) == data
+        raw = open(p, "rb").read()
+        open(p, "wb").write(raw[: len(raw) // 3])
+        with pytest.raises(Exception):
+            with ingest.open_fastq(p, threads=2) as r:
+                read_all(r, 1 << 20)
+
+
 def test_empty_inputs(files):
     _, _, paths = files
     for k in ("empty", "empty_gz"):
