@@ -32,6 +32,10 @@ void pgz_times(void *h, double *out4);
 
 void pgz_close(void *h);
 
+/* The decoder's CRC-32 (zlib's polynomial and conventions: crc of the bytes so far in, new crc out; 0 to start).
+ * Carry-less multiplication where the CPU has PCLMULQDQ (MIRGE_B200_PGZ_NO_CLMUL=1 turns it off), slice-by-8 otherwise. */
+uint32_t pgz_crc(uint32_t crc, const uint8_t *p, uint64_t n);
+
 #ifdef __cplusplus
 }
 #endif

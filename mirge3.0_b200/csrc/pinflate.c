@@ -88,7 +88,13 @@ typedef struct {
   uint16_t symbol[288];
   uint16_t fast[1 << LIT_PB]; /* (symbol << 4) | length, 0 = longer than the primary table */
   int pb;
+  /* the primary table once more, with what the symbol means folded in (huff_pack): base << 16 | extra bits << 8 | kind |
+   * code length; 0 = not in the primary table (longer code, unused pattern, symbol out of range): huff_decode decides */
+  uint32_t pk[1 << LIT_PB];
 } huff;
+#define PK_LIT 0x10u /* base = the literal */
+#define PK_EOB 0x20u
+#define PK_LEN 0x40u /* base = length base; distance tables: always a distance */
 
 /* returns 0 complete, > 0 incomplete (left over), < 0 over-subscribed */
 static int huff_build(huff *h, const uint8_t *len, int n, int pb) {
@@ -148,6 +154,23 @@ static const uint16_t DBASE[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 
 static const uint8_t DEXT[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 static const uint8_t CLORD[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
+/* fold base values and extra-bit counts into the primary table of a literal/length (is_dist = 0) or distance code */
+static void huff_pack(huff *h, int is_dist) {
+  const uint32_t n = 1u << h->pb;
+  for (uint32_t j = 0; j < n; ++j) {
+    const uint32_t e = h->fast[j], l = e & 15u, sym = e >> 4;
+    uint32_t v = 0;
+    if (e) {
+      if (is_dist) {
+        if (sym < 30) v = ((uint32_t)DBASE[sym] << 16) | ((uint32_t)DEXT[sym] << 8) | PK_LEN | l;
+      } else if (sym < 256) v = (sym << 16) | PK_LIT | l;
+      else if (sym == 256) v = PK_EOB | l;
+      else if (sym < 286) v = ((uint32_t)LBASE[sym - 257] << 16) | ((uint32_t)LEXT[sym - 257] << 8) | PK_LEN | l;
+    }
+    h->pk[j] = v;
+  }
+}
+
 /* Header of a dynamic block (the 3 block bits already consumed).  strict: what the block finder demands of a
  * candidate (complete codes; zlib never writes anything else); otherwise what inflate accepts.  0 = ok. */
 static int dynamic_header(bitr *b, huff *lit, huff *dst, int strict) {
@@ -201,8 +224,10 @@ static void fixed_tables(void) {
   for (; s < 280; ++s) l[s] = 7;
   for (; s < 288; ++s) l[s] = 8;
   huff_build(&g_fixed_lit, l, 288, LIT_PB);
+  huff_pack(&g_fixed_lit, 0);
   for (s = 0; s < 30; ++s) l[s] = 5;
   huff_build(&g_fixed_dst, l, 30, DST_PB);
+  huff_pack(&g_fixed_dst, 1);
   g_fixed_ready = 1;
 }
 
@@ -252,6 +277,41 @@ static int bytes_reserve(chunk *c, uint64_t need_total) {
   return 0;
 }
 
+/* One length / distance pair after the literal fast path has declined: `e` is the packed entry of the next
+ * literal/length code (0: not in the primary table).  Sets *plen / *pdist; returns 0 = a match to copy, 1 = a literal in
+ * *plen, 2 = end of block, < 0 error.  The caller refilled (>= 56 bits) before looking `e` up and has consumed nothing
+ * since: code (<= 15) + length extra (<= 5) + distance code (<= 15) + distance extra (<= 13) = 48 bits. */
+static inline int lenpair(bitr *b, const huff *L, const huff *D, uint32_t e, uint32_t *plen, uint32_t *pdist) {
+  uint32_t len;
+  if (e) {
+    br_drop(b, e & 15);
+    if (e & PK_EOB) return 2;
+    len = (e >> 16) + br_bits(b, (e >> 8) & 15);
+  } else {
+    int s = huff_decode(L, b);
+    if (s < 256) {
+      if (s < 0) return -14;
+      *plen = (uint32_t)s;
+      return 1;
+    }
+    if (s == 256) return 2;
+    s -= 257;
+    if (s >= 29) return -15;
+    len = LBASE[s] + br_bits(b, LEXT[s]);
+  }
+  const uint32_t d = D->pk[br_peek(b, DST_PB)];
+  if (d) {
+    br_drop(b, d & 15);
+    *pdist = (d >> 16) + br_bits(b, (d >> 8) & 15);
+  } else {
+    const int ds = huff_decode(D, b);
+    if (ds < 0 || ds >= 30) return -16;
+    *pdist = DBASE[ds] + br_bits(b, DEXT[ds]);
+  }
+  *plen = len;
+  return 0;
+}
+
 /* The symbols of one Huffman block, symbol mode.  *po: write index into c->sym.  0 = end of block reached, < 0 error. */
 static int block_symbols(chunk *c, bitr *b, const huff *L, const huff *D, uint64_t nbytes, uint64_t *po) {
   uint64_t o = *po;
@@ -263,42 +323,38 @@ static int block_symbols(chunk *c, bitr *b, const huff *L, const huff *D, uint64
     }
     br_refill(b);
     if (b->pos > nbytes + 16) { bad = -18; break; } /* reading zeros beyond the end of the file */
-    {
-      /* runs of literals: up to four primary-table codes (<= LIT_PB = 11 bits each) per refill of >= 56 bits */
-      uint16_t e = L->fast[br_peek(b, LIT_PB)];
-      if (e && e < (256u << 4)) {
-        br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 4);
-        e = L->fast[br_peek(b, LIT_PB)];
-        if (e && e < (256u << 4)) {
-          br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 4);
-          e = L->fast[br_peek(b, LIT_PB)];
-          if (e && e < (256u << 4)) {
-            br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 4);
-            e = L->fast[br_peek(b, LIT_PB)];
-            if (e && e < (256u << 4)) { br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 4); }
-          }
+    /* runs of literals: up to four primary-table codes (<= LIT_PB = 11 bits each) per refill of >= 56 bits */
+    uint32_t e = L->pk[br_peek(b, LIT_PB)];
+    if (e & PK_LIT) {
+      br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 16);
+      e = L->pk[br_peek(b, LIT_PB)];
+      if (e & PK_LIT) {
+        br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 16);
+        e = L->pk[br_peek(b, LIT_PB)];
+        if (e & PK_LIT) {
+          br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 16);
+          e = L->pk[br_peek(b, LIT_PB)];
+          if (e & PK_LIT) { br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 16); }
         }
-        continue;
       }
-    }
-    int s = huff_decode(L, b);
-    if (s < 256) {
-      if (s < 0) { bad = -14; break; }
-      c->sym[o++] = (uint16_t)s;
       continue;
     }
-    if (s == 256) break;
-    s -= 257;
-    if (s >= 29) { bad = -15; break; }
-    const uint32_t len = LBASE[s] + br_bits(b, LEXT[s]);
-    const int ds = huff_decode(D, b);
-    if (ds < 0 || ds >= 30) { bad = -16; break; }
-    const uint32_t dist = DBASE[ds] + br_bits(b, DEXT[ds]);
+    uint32_t len, dist;
+    const int k = lenpair(b, L, D, e, &len, &dist);
+    if (k) {
+      if (k == 1) { c->sym[o++] = (uint16_t)len; continue; }
+      if (k < 0) bad = k;
+      break;
+    }
     uint16_t *w = c->sym + o;
     const uint16_t *r = w - dist;
-    if (dist >= len) memcpy(w, r, len * sizeof(uint16_t));
-    else for (uint32_t i = 0; i < len; ++i) w[i] = r[i];
     o += len;
+    if (dist >= 4) { /* four symbols (8 bytes) at a time; the 300 symbols of slack take the overshoot */
+      uint16_t *const end = w + len;
+      do { memcpy(w, r, 8); w += 4; r += 4; } while (w < end);
+    } else {
+      for (uint32_t i = 0; i < len; ++i) w[i] = r[i];
+    }
   }
   *po = o;
   return bad;
@@ -315,43 +371,40 @@ static int block_bytes(chunk *c, bitr *b, const huff *L, const huff *D, uint64_t
     }
     br_refill(b);
     if (b->pos > nbytes + 16) { bad = -18; break; }
-    {
-      uint16_t e = L->fast[br_peek(b, LIT_PB)];
-      if (e && e < (256u << 4)) {
-        br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 4);
-        e = L->fast[br_peek(b, LIT_PB)];
-        if (e && e < (256u << 4)) {
-          br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 4);
-          e = L->fast[br_peek(b, LIT_PB)];
-          if (e && e < (256u << 4)) {
-            br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 4);
-            e = L->fast[br_peek(b, LIT_PB)];
-            if (e && e < (256u << 4)) { br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 4); }
-          }
+    uint32_t e = L->pk[br_peek(b, LIT_PB)];
+    if (e & PK_LIT) {
+      br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 16);
+      e = L->pk[br_peek(b, LIT_PB)];
+      if (e & PK_LIT) {
+        br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 16);
+        e = L->pk[br_peek(b, LIT_PB)];
+        if (e & PK_LIT) {
+          br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 16);
+          e = L->pk[br_peek(b, LIT_PB)];
+          if (e & PK_LIT) { br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 16); }
         }
-        continue;
       }
-    }
-    int s = huff_decode(L, b);
-    if (s < 256) {
-      if (s < 0) { bad = -14; break; }
-      c->bytes[o++] = (uint8_t)s;
       continue;
     }
-    if (s == 256) break;
-    s -= 257;
-    if (s >= 29) { bad = -15; break; }
-    const uint32_t len = LBASE[s] + br_bits(b, LEXT[s]);
-    const int ds = huff_decode(D, b);
-    if (ds < 0 || ds >= 30) { bad = -16; break; }
-    const uint32_t dist = DBASE[ds] + br_bits(b, DEXT[ds]);
+    uint32_t len, dist;
+    const int k = lenpair(b, L, D, e, &len, &dist);
+    if (k) {
+      if (k == 1) { c->bytes[o++] = (uint8_t)len; continue; }
+      if (k < 0) bad = k;
+      break;
+    }
     if (c->known == 2 && dist > o - c->boff) { bad = -17; break; } /* before the start of the member */
     uint8_t *w = c->bytes + o;
     const uint8_t *r = w - dist;
-    if (dist >= len) memcpy(w, r, len);
-    else if (dist == 1) memset(w, r[0], len);
-    else for (uint32_t i = 0; i < len; ++i) w[i] = r[i];
     o += len;
+    if (dist >= 8) { /* eight bytes at a time; the 300 bytes of slack take the overshoot */
+      uint8_t *const end = w + len;
+      do { memcpy(w, r, 8); w += 8; r += 8; } while (w < end);
+    } else if (dist == 1) {
+      memset(w, r[0], len);
+    } else {
+      for (uint32_t i = 0; i < len; ++i) w[i] = r[i];
+    }
   }
   *po = o;
   return bad;
@@ -409,6 +462,8 @@ static void chunk_decode(chunk *c, const uint8_t *data, uint64_t nbytes, const u
         L = &g_fixed_lit; D = &g_fixed_dst;
       } else {
         if ((c->err = dynamic_header(&b, &lit, &dst, 0)) != 0) break;
+        huff_pack(&lit, 0);
+        huff_pack(&dst, 1);
         L = &lit; D = &dst;
       }
       const int bad = byte_mode ? block_bytes(c, &b, L, D, nbytes, &o) : block_symbols(c, &b, L, D, nbytes, &o);
@@ -455,8 +510,103 @@ static void crc_tables(void) {
   for (uint32_t i = 0; i < 256; ++i)
     for (int t = 1; t < 8; ++t) g_crc[t][i] = (g_crc[t - 1][i] >> 8) ^ g_crc[0][g_crc[t - 1][i] & 0xFF];
 }
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+/* CRC-32 by carry-less multiplication (folding four 128-bit lanes over 64-byte blocks, then Barrett reduction; the
+ * constants are x^n mod P for the reflected gzip polynomial, as in Intel's "Fast CRC computation using PCLMULQDQ").
+ * crc in / out in the register form (already inverted); n >= 64, a multiple of 16.  Used when the CPU has PCLMULQDQ;
+ * tests/test_ingest_host.py holds every path against zlib. */
+__attribute__((target("pclmul,sse4.1"))) static uint32_t crc32_clmul(uint32_t crc, const uint8_t *buf, uint64_t len) {
+  const __m128i k1k2 = _mm_set_epi64x(0x01c6e41596ll, 0x0154442bd4ll);
+  const __m128i k3k4 = _mm_set_epi64x(0x00ccaa009ell, 0x01751997d0ll);
+  const __m128i k5k0 = _mm_set_epi64x(0, 0x0163cd6124ll);
+  const __m128i poly = _mm_set_epi64x(0x01f7011641ll, 0x01db710641ll);
+  __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
+  x1 = _mm_loadu_si128((const __m128i *)(buf + 0x00));
+  x2 = _mm_loadu_si128((const __m128i *)(buf + 0x10));
+  x3 = _mm_loadu_si128((const __m128i *)(buf + 0x20));
+  x4 = _mm_loadu_si128((const __m128i *)(buf + 0x30));
+  x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)crc));
+  x0 = k1k2;
+  buf += 64;
+  len -= 64;
+  while (len >= 64) {
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
+    x7 = _mm_clmulepi64_si128(x3, x0, 0x00);
+    x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
+    x3 = _mm_clmulepi64_si128(x3, x0, 0x11);
+    x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
+    y5 = _mm_loadu_si128((const __m128i *)(buf + 0x00));
+    y6 = _mm_loadu_si128((const __m128i *)(buf + 0x10));
+    y7 = _mm_loadu_si128((const __m128i *)(buf + 0x20));
+    y8 = _mm_loadu_si128((const __m128i *)(buf + 0x30));
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5);
+    x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
+    x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7);
+    x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
+    buf += 64;
+    len -= 64;
+  }
+  x0 = k3k4; /* four lanes -> one */
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
+  x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+  x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
+  while (len >= 16) { /* single 16-byte blocks */
+    x2 = _mm_loadu_si128((const __m128i *)buf);
+    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
+    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
+    x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
+    buf += 16;
+    len -= 16;
+  }
+  x2 = _mm_clmulepi64_si128(x1, x0, 0x10); /* 128 -> 64 bits */
+  x3 = _mm_setr_epi32(~0, 0, ~0, 0);
+  x1 = _mm_srli_si128(x1, 8);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = k5k0;
+  x2 = _mm_srli_si128(x1, 4);
+  x1 = _mm_and_si128(x1, x3);
+  x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  x0 = poly; /* Barrett reduction to 32 bits */
+  x2 = _mm_and_si128(x1, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
+  x2 = _mm_and_si128(x2, x3);
+  x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
+  x1 = _mm_xor_si128(x1, x2);
+  return (uint32_t)_mm_extract_epi32(x1, 1);
+}
+static int g_have_clmul = -1;
+static int have_clmul(void) {
+  if (g_have_clmul < 0) {
+    const char *off = getenv("MIRGE_B200_PGZ_NO_CLMUL");
+    __builtin_cpu_init();
+    g_have_clmul = (__builtin_cpu_supports("pclmul") && __builtin_cpu_supports("sse4.1") && !(off && off[0] == '1')) ? 1 : 0;
+  }
+  return g_have_clmul;
+}
+#else
+static int have_clmul(void) { return 0; }
+static uint32_t crc32_clmul(uint32_t crc, const uint8_t *buf, uint64_t len) { (void)buf; (void)len; return crc; }
+#endif
+
 static uint32_t crc32_buf(uint32_t crc, const uint8_t *p, uint64_t n) {
   crc = ~crc;
+  if (n >= 64 && have_clmul()) {
+    const uint64_t k = n & ~15ull;
+    crc = crc32_clmul(crc, p, k);
+    p += k;
+    n -= k;
+  }
   while (n && ((uintptr_t)p & 7)) { crc = g_crc[0][(crc ^ *p++) & 0xFF] ^ (crc >> 8); --n; }
   while (n >= 8) {
     uint64_t v;
@@ -760,6 +910,13 @@ static int run_wave(pgz *z) {
     const uint16_t *t = a->sym ? a->sym + WIN : NULL;
     uint8_t *o = a->bytes + a->boff;
     uint32_t crc = 0;
+    /* symbol -> byte as one table (literals map to themselves, markers to the window): groups that hold markers are
+     * translated without a branch per symbol -- on FASTQ the markers of header and separator bytes never die out */
+    uint8_t lut[256 + WIN];
+    if (a->n_sym) {
+      for (int q = 0; q < 256; ++q) lut[q] = (uint8_t)q;
+      memcpy(lut + 256, win, WIN);
+    }
     for (uint64_t blk = 0; blk < a->n; blk += 32768) { /* block-wise: the CRC reads the bytes while they are in cache */
       const uint64_t blk_end = blk + 32768 < a->n ? blk + 32768 : a->n;
       const uint64_t head_end = blk_end < a->n_sym ? blk_end : a->n_sym; /* symbols of this block still to resolve */
@@ -776,10 +933,10 @@ static int run_wave(pgz *z) {
           const uint64_t v = lo | (hi << 32);
           memcpy(o + i, &v, 8);
         } else {
-          for (int q = 0; q < 8; ++q) o[i + q] = t[i + q] < 256 ? (uint8_t)t[i + q] : win[t[i + q] - 256];
+          for (int q = 0; q < 8; ++q) o[i + q] = lut[t[i + q]];
         }
       }
-      for (; i < head_end; ++i) o[i] = t[i] < 256 ? (uint8_t)t[i] : win[t[i] - 256];
+      for (; i < head_end; ++i) o[i] = lut[t[i]];
       crc = crc32_buf(crc, o + blk, blk_end - blk);
     }
     a->crc = crc;
@@ -871,6 +1028,10 @@ void pgz_stats(void *h, uint64_t *out4) {
 void pgz_times(void *h, double *out4) {
   pgz *z = (pgz *)h;
   out4[0] = z->t_find; out4[1] = z->t_decode; out4[2] = z->t_chain; out4[3] = z->t_resolve;
+}
+
+uint32_t pgz_crc(uint32_t crc, const uint8_t *p, uint64_t n) {
+  return crc32_buf(crc, p, n); /* (the tables are filled when the library is loaded) */
 }
 
 void pgz_close(void *h) {

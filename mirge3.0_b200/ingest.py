@@ -151,9 +151,12 @@ def parallel_gzip_library():
     return _pgz
 
 
-def _pgzip_chunks(path: str, threads: Optional[int] = None, chunk_bytes: Optional[int] = None) -> Iterator[bytes]:
+def _pgzip_chunks(path: str, threads: Optional[int] = None, chunk_bytes: Optional[int] = None,
+                  spare: Optional[Callable[[], Optional[bytearray]]] = None) -> Iterator[bytes]:
     """One gzip stream inflated on ``threads`` cores (csrc/pinflate.c); same bytes and the same kinds of errors as
-    _gzip_chunks: EOFError for a truncated file, OSError for CRC / length / header problems, zlib.error for bad data."""
+    _gzip_chunks: EOFError for a truncated file, OSError for CRC / length / header problems, zlib.error for bad data.
+    ``spare()`` hands back a chunk buffer the consumer is done with (ChunkReader.spare), so that the steady state
+    allocates, zero-fills and page-faults nothing."""
     lib = parallel_gzip_library()
     with open(path, "rb") as f:
         size = os.fstat(f.fileno()).st_size
@@ -169,7 +172,9 @@ def _pgzip_chunks(path: str, threads: Optional[int] = None, chunk_bytes: Optiona
             raise MemoryError("parallel gzip reader: out of memory")
         try:
             while True:
-                out = bytearray(CHUNK)
+                out = spare() if spare is not None else None
+                if out is None or len(out) != CHUNK:
+                    out = bytearray(CHUNK)
                 dst = (ctypes.c_ubyte * CHUNK).from_buffer(out)
                 k = lib.pgz_read(h, dst, CHUNK)
                 del dst
@@ -281,8 +286,16 @@ class ChunkReader:
         self._pos = 0
         self._done = False
         self.bytes_out = 0
+        self._spare: "queue.SimpleQueue" = queue.SimpleQueue()  # chunk buffers the consumer has emptied
         self._t = threading.Thread(target=self._run, args=(producer,), daemon=True, name="mirge-read")
         self._t.start()
+
+    def spare(self) -> Optional[bytearray]:
+        """A chunk buffer (bytearray) the consumer is done with, or None: for producers that fill their own buffers."""
+        try:
+            return self._spare.get_nowait()
+        except queue.Empty:
+            return None
 
     def _put(self, item) -> bool:
         while not self._stop.is_set():
@@ -309,6 +322,11 @@ class ChunkReader:
             if self._pos == len(self._cur):
                 if self._done:
                     break
+                done_with = self._cur.obj
+                self._cur = memoryview(b"")
+                self._pos = 0
+                if isinstance(done_with, bytearray):
+                    self._spare.put(done_with)  # (the view above was the last reference the consumer held)
                 item = self._q.get()
                 if item is None:
                     self._done = True
@@ -434,7 +452,11 @@ def open_fastq(path: str, threads: Optional[int] = None, depth: int = 4):
             # previous one has been handed over: the queue must hold a wave's output (about 4x its input for FASTQ) for
             # decoding and consumption to overlap
             wave_out = 4 * int(threads or default_threads()) * PGZ_CHUNK
-            return ChunkReader(lambda: _pgzip_chunks(path, threads), max(depth, -(-2 * wave_out // CHUNK)), name=path)
+            holder = []
+            r = ChunkReader(lambda: _pgzip_chunks(path, threads, spare=lambda: holder[0].spare() if holder else None),
+                            max(depth, -(-2 * wave_out // CHUNK)), name=path)
+            holder.append(r)
+            return r
         return ChunkReader(lambda: _gzip_chunks(path), depth, name=path)
     if kind == "bz2":
         import bz2

@@ -441,6 +441,44 @@ def test_inflate_library_is_built_and_exports_its_entry_points():
     lib = ctypes.CDLL(ingest.PGZ_LIB)
     header = open(os.path.join(os.path.dirname(ingest.__file__), "..", "include", "mirge_inflate.h")).read()
     declared = set(re.findall(r"\b(pgz_[a-z]+)\s*\(", header))
-    assert declared == {"pgz_open", "pgz_read", "pgz_error", "pgz_stats", "pgz_times", "pgz_close"}
+    assert declared == {"pgz_open", "pgz_read", "pgz_error", "pgz_stats", "pgz_times", "pgz_close", "pgz_crc"}
     for name in declared:  # every entry point include/mirge_inflate.h declares
         assert hasattr(lib, name), name
+
+
+def test_crc_paths_equal_zlib():
+    """pgz_crc (carry-less multiplication for the bulk, slice-by-8 for the rest and on CPUs without PCLMULQDQ) against
+    zlib.crc32: every length around the 16- and 64-byte steps, odd alignments, running CRCs over pieces."""
+    import ctypes
+    import subprocess
+    import sys
+
+    if not os.path.exists(ingest.PGZ_LIB):
+        pytest.skip("libmirge_inflate.so not built (run __graft_entry__.build())")
+    code = r"""
+import ctypes, sys, zlib, numpy as np
+lib = ctypes.CDLL(sys.argv[1])
+lib.pgz_crc.restype = ctypes.c_uint32
+lib.pgz_crc.argtypes = [ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint64]
+rng = np.random.default_rng(1)
+buf = rng.integers(0, 256, 70000, dtype=np.uint8)
+base = buf.ctypes.data
+n = 0
+for off in (0, 1, 3, 8, 13):
+    for ln in list(range(0, 300)) + [1000, 4095, 4096, 4097, 32768, 65519]:
+        assert lib.pgz_crc(0, base + off, ln) == zlib.crc32(buf[off:off + ln].tobytes()), (off, ln)
+        n += 1
+crc_a = crc_b = 0
+pos = 0
+while pos < buf.size:
+    k = int(rng.integers(0, 500))
+    crc_a = lib.pgz_crc(crc_a, base + pos, min(k, buf.size - pos))
+    crc_b = zlib.crc32(buf[pos:pos + k].tobytes(), crc_b)
+    pos += k
+assert crc_a == crc_b
+print("ok", n)
+"""
+    for no_clmul in ("0", "1"):  # the switch is read once per process
+        env = dict(os.environ, MIRGE_B200_PGZ_NO_CLMUL=no_clmul)
+        out = subprocess.run([sys.executable, "-c", code, ingest.PGZ_LIB], env=env, capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0 and out.stdout.startswith("ok"), (no_clmul, out.stdout, out.stderr)
