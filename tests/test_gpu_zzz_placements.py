@@ -26,10 +26,11 @@ def dev():
     return D.Device(0)
 
 
-@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("seed", range(40))
-def test_gpu_matches_c_oracle_on_random_placements(dev, seed, mode):
+def test_gpu_matches_c_oracle_on_random_placements(dev, seed):
     from mirge_b200 import device as D
+
+    mode = seed & 1  # automatic kernel choice / generic kernel forced, alternating (as in the native check)
     from tests.test_gpu_digest import gpu_windows, table_dict, to_dev
 
     rng = np.random.default_rng(9500 + seed)
