@@ -93,6 +93,8 @@ typedef struct {
   uint32_t pk[1 << LIT_PB];
 } huff;
 #define PK_LIT 0x10u /* base = the literal */
+#define PK_LIT2 0x80u /* (with PK_LIT) two literals whose codes fit the primary table together: bits 16-23 the first,
+                       * bits 24-31 the second, code length = both codes */
 #define PK_EOB 0x20u
 #define PK_LEN 0x40u /* base = length base; distance tables: always a distance */
 
@@ -163,7 +165,13 @@ static void huff_pack(huff *h, int is_dist) {
     if (e) {
       if (is_dist) {
         if (sym < 30) v = ((uint32_t)DBASE[sym] << 16) | ((uint32_t)DEXT[sym] << 8) | PK_LEN | l;
-      } else if (sym < 256) v = (sym << 16) | PK_LIT | l;
+      } else if (sym < 256) {
+        v = (sym << 16) | PK_LIT | l;
+        /* what follows the code inside this index, zero-extended, decodes by itself iff its code needs no more than
+         * the bits that are left */
+        const uint32_t e2 = h->fast[j >> l], l2 = e2 & 15u, sym2 = e2 >> 4;
+        if (e2 && sym2 < 256 && l + l2 <= (uint32_t)h->pb) v = (sym2 << 24) | (sym << 16) | PK_LIT | PK_LIT2 | (l + l2);
+      }
       else if (sym == 256) v = PK_EOB | l;
       else if (sym < 286) v = ((uint32_t)LBASE[sym - 257] << 16) | ((uint32_t)LEXT[sym - 257] << 8) | PK_LEN | l;
     }
@@ -323,20 +331,27 @@ static int block_symbols(chunk *c, bitr *b, const huff *L, const huff *D, uint64
     }
     br_refill(b);
     if (b->pos > nbytes + 16) { bad = -18; break; } /* reading zeros beyond the end of the file */
-    /* runs of literals: up to four primary-table codes (<= LIT_PB = 11 bits each) per refill of >= 56 bits */
     uint32_t e = L->pk[br_peek(b, LIT_PB)];
-    if (e & PK_LIT) {
-      br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 16);
+    if (e & PK_LIT) { /* runs of literals as in block_bytes, two 16-bit symbols stored per entry */
+#define PUT_LITS(e_)                                          \
+  do {                                                        \
+    br_drop(b, (e_) & 15);                                    \
+    c->sym[o] = (uint16_t)(((e_) >> 16) & 0xFFu);             \
+    c->sym[o + 1] = (uint16_t)((e_) >> 24);                   \
+    o += 1 + (((e_) >> 7) & 1u);                              \
+  } while (0)
+      PUT_LITS(e);
       e = L->pk[br_peek(b, LIT_PB)];
       if (e & PK_LIT) {
-        br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 16);
+        PUT_LITS(e);
         e = L->pk[br_peek(b, LIT_PB)];
         if (e & PK_LIT) {
-          br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 16);
+          PUT_LITS(e);
           e = L->pk[br_peek(b, LIT_PB)];
-          if (e & PK_LIT) { br_drop(b, e & 15); c->sym[o++] = (uint16_t)(e >> 16); }
+          if (e & PK_LIT) PUT_LITS(e);
         }
       }
+#undef PUT_LITS
       continue;
     }
     uint32_t len, dist;
@@ -373,17 +388,27 @@ static int block_bytes(chunk *c, bitr *b, const huff *L, const huff *D, uint64_t
     if (b->pos > nbytes + 16) { bad = -18; break; }
     uint32_t e = L->pk[br_peek(b, LIT_PB)];
     if (e & PK_LIT) {
-      br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 16);
+      /* runs of literals: up to four primary-table entries (<= LIT_PB = 11 bits each, one or two literals) per refill
+       * of >= 56 bits; both bytes of an entry are stored, the write index moves by one or two */
+#define PUT_LITS(e_)                                          \
+  do {                                                        \
+    const uint16_t two_ = (uint16_t)((e_) >> 16);             \
+    br_drop(b, (e_) & 15);                                    \
+    memcpy(c->bytes + o, &two_, 2);                           \
+    o += 1 + (((e_) >> 7) & 1u);                              \
+  } while (0)
+      PUT_LITS(e);
       e = L->pk[br_peek(b, LIT_PB)];
       if (e & PK_LIT) {
-        br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 16);
+        PUT_LITS(e);
         e = L->pk[br_peek(b, LIT_PB)];
         if (e & PK_LIT) {
-          br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 16);
+          PUT_LITS(e);
           e = L->pk[br_peek(b, LIT_PB)];
-          if (e & PK_LIT) { br_drop(b, e & 15); c->bytes[o++] = (uint8_t)(e >> 16); }
+          if (e & PK_LIT) PUT_LITS(e);
         }
       }
+#undef PUT_LITS
       continue;
     }
     uint32_t len, dist;
