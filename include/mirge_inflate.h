@@ -21,7 +21,9 @@ void *pgz_open(const uint8_t *data, uint64_t n, int threads, uint64_t chunk_byte
 
 /* The next decompressed bytes into dst (at most cap): > 0 = bytes written, 0 = end of file, < 0 = error, text in
  * pgz_error (truncated file: "... ended before the end-of-stream marker ..."; bad data: "invalid deflate data";
- * trailer: "CRC check failed" / "incorrect length of data produced"; header problems).  Blocks while a wave is decoded. */
+ * trailer: "CRC check failed" / "incorrect length of data produced"; header problems).  With more than one thread the
+ * waves are decoded by a producer thread one wave ahead of the reader (MIRGE_B200_PGZ_PREFETCH=0: on demand), so the
+ * call blocks only when the reader has caught up.  After an error every later call fails as well. */
 int64_t pgz_read(void *h, uint8_t *dst, uint64_t cap);
 const char *pgz_error(void *h);
 

@@ -30,6 +30,7 @@ static double omp_get_wtime(void) {
   return (double)t.tv_sec + 1e-9 * (double)t.tv_nsec;
 }
 #endif
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -702,6 +703,19 @@ typedef struct {
   uint64_t waves, chunks_used, chunks_wasted, serial_repairs;
   double t_find, t_decode, t_chain, t_resolve;
   char err[256];
+  /* The reader's side.  With more than one thread the waves are decoded by a producer thread one wave ahead of the
+   * reader: while pgz_read copies wave k out (a serial memcpy during which the decoding threads would idle), wave k + 1
+   * is being decoded; `ready` is the hand-over slot between the two.  Everything above belongs to whoever runs
+   * run_wave (the producer thread, or the reader itself when there is none); the pools are shared under `mu`. */
+  chunk *c_out;
+  int c_n, c_cur, c_eof;
+  uint64_t c_off;
+  int async, started, stop, failed;
+  pthread_t producer;
+  pthread_mutex_t mu;
+  pthread_cond_t cv_data, cv_space;
+  chunk *ready_out;
+  int ready_n, ready_rc, ready_eof, ready_full;
 } pgz;
 
 static int fail(pgz *z, const char *msg, uint64_t at) {
@@ -712,10 +726,12 @@ static int fail(pgz *z, const char *msg, uint64_t at) {
 /* which: 0 = symbol buffers (cap in symbols), 1 = byte buffers.  Returns a buffer of at least `need` units or NULL. */
 static void *pool_take(pgz *z, int which, uint64_t need, uint64_t *cap) {
   const uint64_t unit = which == 0 ? sizeof(uint16_t) : 1;
+  pthread_mutex_lock(&z->mu);
   if (z->pool_n[which] > 0) {
     const int i = --z->pool_n[which];
     void *p = z->pool[which][i];
     uint64_t c = z->pool_cap[which][i];
+    pthread_mutex_unlock(&z->mu);
     if (c < need) {
       void *q = realloc(p, need * unit);
       if (!q) { free(p); return NULL; }
@@ -725,18 +741,21 @@ static void *pool_take(pgz *z, int which, uint64_t need, uint64_t *cap) {
     *cap = c;
     return p;
   }
+  pthread_mutex_unlock(&z->mu);
   *cap = need;
   return malloc(need ? need * unit : 1);
 }
 static void pool_give(pgz *z, int which, void *p, uint64_t cap) {
   if (!p) return;
+  pthread_mutex_lock(&z->mu);
   if (z->pool_n[which] < POOL_MAX) {
     z->pool[which][z->pool_n[which]] = p;
     z->pool_cap[which][z->pool_n[which]] = cap;
     z->pool_n[which]++;
-  } else {
-    free(p);
+    p = NULL;
   }
+  pthread_mutex_unlock(&z->mu);
+  free(p);
 }
 
 /* gzip member header at byte `at` (RFC 1952); returns the byte after it, 0 on error */
@@ -1016,27 +1035,107 @@ void *pgz_open(const uint8_t *data, uint64_t n, int threads, uint64_t chunk_byte
     if (z->wave_factor < 1 || z->wave_factor > 16) z->wave_factor = 1;
   }
   z->chunk_bytes = chunk_bytes < 65536 ? 65536 : chunk_bytes;
+  pthread_mutex_init(&z->mu, NULL);
+  pthread_cond_init(&z->cv_data, NULL);
+  pthread_cond_init(&z->cv_space, NULL);
+  {
+    const char *e = getenv("MIRGE_B200_PGZ_PREFETCH"); /* 0: decode a wave only when the reader asks for it */
+    z->async = z->threads > 1 && !(e && e[0] == '0');
+  }
   return z;
+}
+
+/* the producer thread: one wave ahead of the reader, never more (two waves of buffers exist at a time) */
+static void *producer_main(void *arg) {
+  pgz *z = (pgz *)arg;
+  for (;;) {
+    pthread_mutex_lock(&z->mu);
+    while (z->ready_full && !z->stop) pthread_cond_wait(&z->cv_space, &z->mu);
+    const int stop = z->stop;
+    pthread_mutex_unlock(&z->mu);
+    if (stop) break;
+    const int rc = run_wave(z);
+    pthread_mutex_lock(&z->mu);
+    z->ready_out = z->out;
+    z->ready_n = z->n_out;
+    z->ready_rc = rc;
+    z->ready_eof = z->eof;
+    z->out = NULL;
+    z->n_out = 0;
+    z->ready_full = 1;
+    pthread_cond_signal(&z->cv_data);
+    pthread_mutex_unlock(&z->mu);
+    if (rc || z->eof) break;
+  }
+  return NULL;
+}
+
+/* the next wave into the reader's hands; < 0: the wave failed (z->err) */
+static int next_wave(pgz *z) {
+  int rc;
+  if (!z->async) {
+    rc = run_wave(z);
+    z->c_out = z->out;
+    z->c_n = z->n_out;
+    z->c_eof = z->eof;
+    z->out = NULL;
+    z->n_out = 0;
+    return rc;
+  }
+  if (!z->started) {
+    if (pthread_create(&z->producer, NULL, producer_main, z) != 0) { /* no thread to be had: decode on demand */
+      z->async = 0;
+      return next_wave(z);
+    }
+    z->started = 1;
+  }
+  pthread_mutex_lock(&z->mu);
+  while (!z->ready_full) pthread_cond_wait(&z->cv_data, &z->mu);
+  z->c_out = z->ready_out;
+  z->c_n = z->ready_n;
+  z->c_eof = z->ready_eof;
+  rc = z->ready_rc;
+  z->ready_out = NULL;
+  z->ready_n = 0;
+  z->ready_full = 0;
+  pthread_cond_signal(&z->cv_space);
+  pthread_mutex_unlock(&z->mu);
+  return rc;
 }
 
 /* next decompressed bytes into dst (at most cap): > 0 bytes written, 0 end of file, < 0 error (pgz_error) */
 int64_t pgz_read(void *h, uint8_t *dst, uint64_t cap) {
   pgz *z = (pgz *)h;
   uint64_t got = 0;
+  if (z->failed) return -1;
   while (got < cap) {
-    if (z->cur_out < z->n_out) {
-      chunk *a = &z->out[z->cur_out];
-      uint64_t k = a->n - z->cur_off;
+    if (z->c_cur < z->c_n) {
+      chunk *a = &z->c_out[z->c_cur];
+      uint64_t k = a->n - z->c_off;
       if (k > cap - got) k = cap - got;
-      memcpy(dst + got, a->bytes + a->boff + z->cur_off, k);
+      memcpy(dst + got, a->bytes + a->boff + z->c_off, k);
       got += k;
-      z->cur_off += k;
-      if (z->cur_off == a->n) { pool_give(z, 1, a->bytes, a->bytes_cap); a->bytes = NULL; z->cur_out++; z->cur_off = 0; }
+      z->c_off += k;
+      if (z->c_off == a->n) { chunk_release(z, a); z->c_cur++; z->c_off = 0; }
       continue;
     }
-    if (z->eof) break;
+    if (z->c_out) { /* the wave is drained */
+      for (int i = 0; i < z->c_n; ++i) chunk_release(z, &z->c_out[i]);
+      free(z->c_out);
+      z->c_out = NULL;
+      z->c_n = z->c_cur = 0;
+      z->c_off = 0;
+    }
+    if (z->c_eof) break;
     if (got) break; /* hand over what is there before the next wave blocks */
-    if (run_wave(z)) return -1;
+    if (next_wave(z)) { /* the wave failed: nothing of it is handed out, and every later call fails as well */
+      for (int i = 0; i < z->c_n; ++i) chunk_release(z, &z->c_out[i]);
+      free(z->c_out);
+      z->c_out = NULL;
+      z->c_n = z->c_cur = 0;
+      z->failed = 1;
+      return -1;
+    }
   }
   z->total_out += got;
   return (int64_t)got;
@@ -1062,9 +1161,23 @@ uint32_t pgz_crc(uint32_t crc, const uint8_t *p, uint64_t n) {
 void pgz_close(void *h) {
   pgz *z = (pgz *)h;
   if (!z) return;
+  if (z->started) {
+    pthread_mutex_lock(&z->mu);
+    z->stop = 1;
+    pthread_cond_signal(&z->cv_space);
+    pthread_mutex_unlock(&z->mu);
+    pthread_join(z->producer, NULL);
+  }
   for (int i = 0; i < z->n_out; ++i) chunk_release(z, &z->out[i]);
   free(z->out);
+  for (int i = 0; i < z->ready_n; ++i) chunk_release(z, &z->ready_out[i]);
+  free(z->ready_out);
+  for (int i = 0; i < z->c_n; ++i) chunk_release(z, &z->c_out[i]);
+  free(z->c_out);
   for (int w = 0; w < 2; ++w)
     for (int i = 0; i < z->pool_n[w]; ++i) free(z->pool[w][i]);
+  pthread_mutex_destroy(&z->mu);
+  pthread_cond_destroy(&z->cv_data);
+  pthread_cond_destroy(&z->cv_space);
   free(z);
 }

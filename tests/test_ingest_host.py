@@ -446,6 +446,26 @@ def test_inflate_library_is_built_and_exports_its_entry_points():
         assert hasattr(lib, name), name
 
 
+def test_parallel_gzip_reader_closed_early_and_without_prefetch(files, monkeypatch):
+    """The decoder's producer thread works one wave ahead of the reader: closing a reader that has only taken a few bytes
+    (or nothing) must stop and join it; MIRGE_B200_PGZ_PREFETCH=0 (waves decoded on demand) returns the same bytes."""
+    _, data, paths = files
+    _parallel(monkeypatch, 64)
+    for take in (0, 1, 70000):
+        r = ingest.open_fastq(paths["gzip"], threads=4)
+        assert r.read(take) == data[:take]
+        r.close()
+    before = threading.active_count()
+    for _ in range(5):
+        with ingest.open_fastq(paths["members"], threads=3) as r:
+            assert r.read(1000) == data[:1000]
+    assert threading.active_count() <= before
+    monkeypatch.setenv("MIRGE_B200_PGZ_PREFETCH", "0")
+    for kind in ("gzip", "members", "padded"):
+        with ingest.open_fastq(paths[kind], threads=4) as r:
+            assert read_all(r, 1 << 20) == data
+
+
 def test_crc_paths_equal_zlib():
     """pgz_crc (carry-less multiplication for the bulk, slice-by-8 for the rest and on CPUs without PCLMULQDQ) against
     zlib.crc32: every length around the 16- and 64-byte steps, odd alignments, running CRCs over pieces."""
