@@ -29,3 +29,24 @@ def test_other_ranks_of_the_reference_arm_do_nothing():
     p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
                        text=True, timeout=300, cwd=ROOT, env=env)
     assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_ingest_gz_leg_of_the_bench_line():
+    """The host-side `ingest_gz` leg: its input really is ONE gzip member holding ONE DEFLATE stream (what makes the
+    parallel decoder necessary), and the leg reports both readers on it."""
+    import gzip
+    import zlib
+
+    import numpy as np
+
+    sys.path.insert(0, ROOT)
+    import bench
+    from tests.util import random_fastq
+
+    unit = random_fastq(3000, seed=2)
+    blob = bench.single_stream_gzip(unit, 4)
+    assert gzip.decompress(blob) == unit * 4
+    d = zlib.decompressobj(31)
+    assert d.decompress(blob) == unit * 4 and d.eof and d.unused_data == b""  # one member, nothing behind it
+    res = bench.run_ingest_gz(np.frombuffer(unit, dtype=np.uint8), 2, target_mb=3)
+    assert res["value"] > 0 and res["serial_zlib_mb_s"] > 0 and res["threads"] == 2 and res["fastq_mb"] > 2
