@@ -8,6 +8,7 @@ pipelines on realistic reads; here it is the matcher alone, tens of thousands of
 import ctypes as C
 import os
 import subprocess
+import zlib
 
 import numpy as np
 import pytest
@@ -16,7 +17,7 @@ import mirge_b200
 from mirge_b200 import abi
 from mirge_b200 import params as P
 from oracle import pyoracle as po
-from tests.util import py_params
+from tests.util import CONFIG_DATA, CONFIGS, py_params, random_fastq
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 B = np.array(list("ACGT"))
@@ -325,6 +326,34 @@ def test_modifier_pipeline_with_linked_anchored_and_parameterised_adapters(hs, c
             assert (win[2 * mi], win[2 * mi + 1]) == (start, stop), (PIPELINES[case], seq, qual, mi, (win[2 * mi], win[2 * mi + 1]), (start, stop))
         changed += (start, stop) != (0, len(seq))
     assert changed > 150, changed
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_modifier_pipeline_of_every_named_configuration(hs, name):
+    """The configurations the GPU suite runs (tests/util.py CONFIGS), through the kernels' full-DP modifier pipeline
+    compiled for the host, window by window against the Python oracle: what the GPU tests establish on a device for the
+    generic kernel, established for its per-read code on every CPU run."""
+    cfg = CONFIGS[name]
+    cp, pp = P.build_trim_params(cfg), py_params(cfg)
+    fast_ok = C.c_int(0)
+    err = C.create_string_buffer(512)
+    assert hs.hs_set_params(C.byref(cp), C.byref(fast_ok), err, 512) == 0, err.value
+    hs.hs_pipeline.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int32)]
+    mods = pp.modifiers()
+    assert len(mods) == cp.n_mods
+    win = (C.c_int32 * (2 * max(cp.n_mods, 1)))()
+    data = random_fastq(1500, seed=zlib.crc32(name.encode()) % 1000 + 3, n_rate=0.02, lower_rate=0.01, **CONFIG_DATA.get(name, {}))
+    changed = 0
+    for _nm, seq, qual in po.parse_fastq(data):
+        if not seq:
+            continue
+        assert hs.hs_pipeline(seq.encode(), qual.encode(), len(seq), win) == len(mods)
+        start, stop = 0, len(seq)
+        for mi, mod in enumerate(mods):
+            start, stop = po.apply_modifier(mod, seq, qual, start, stop, pp)
+            assert (win[2 * mi], win[2 * mi + 1]) == (start, stop), (name, seq, qual, mi, (win[2 * mi], win[2 * mi + 1]), (start, stop))
+        changed += (start, stop) != (0, len(seq))
+    assert changed > 300, changed
 
 
 def test_quality_scans_equal_the_oracle(hs):
