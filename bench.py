@@ -305,6 +305,27 @@ def run_ingest_gz(fastq: np.ndarray, threads: int, target_mb: int = 512):
         shutil.rmtree(tmpdir, ignore_errors=True)
 
 
+def run_ingest_gz_guarded(fastq: np.ndarray, threads: int, timeout_s: int = 240):
+    """run_ingest_gz in a process of its own with a time limit: the leg starts threads (decoder, reader) and is an extra --
+    whatever happens to it, the bench line is printed."""
+    tmpdir = tempfile.mkdtemp(prefix="mirge_gzu_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    unit = os.path.join(tmpdir, "unit.fastq")
+    try:
+        fastq.tofile(unit)
+        code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import bench; "
+                "print('INGEST_GZ ' + json.dumps(bench.run_ingest_gz(np.fromfile(sys.argv[1], dtype=np.uint8), int(sys.argv[2]))))" % ROOT)
+        try:
+            p = subprocess.run([sys.executable, "-c", code, unit, str(int(threads))], capture_output=True, text=True, timeout=timeout_s)
+        except subprocess.TimeoutExpired:
+            return {"error": "timed out after %d s" % timeout_s}
+        for ln in p.stdout.splitlines():
+            if ln.startswith("INGEST_GZ "):
+                return json.loads(ln[len("INGEST_GZ "):])
+        return {"error": "exit code %d: %s" % (p.returncode, p.stderr.strip()[-300:])}
+    finally:
+        shutil.rmtree(tmpdir, ignore_errors=True)
+
+
 def run_dropin(args, dev, lset, libs, fq_dev, cfg_id):
     """The drop-in boundary itself: baking(args, [file], [name], workDir) then bwtAlign(args, df, workDir, ref_db) -- the two
     calls miRge3.0's main() makes -- on one sample of the workload written to /dev/shm (FASTQ file in, pandas DataFrame
@@ -733,7 +754,7 @@ def run_b200(args):
             head = fqs[0][: min(48 << 20, int(fqs[0].numel()))].cpu().numpy()
             nl_h = np.flatnonzero(head == 10)
             head = head[: int(nl_h[(nl_h.size // 4) * 4 - 1]) + 1]
-            ingest_gz = run_ingest_gz(head, host_threads())
+            ingest_gz = run_ingest_gz_guarded(head, host_threads())
         except Exception as exc:  # a host-side extra must never cost the bench line
             ingest_gz = {"error": "%s: %s" % (type(exc).__name__, exc)}
 
