@@ -162,6 +162,58 @@ def test_specification_language_matches_cutadapt(case):
         assert out.sequence == read[start:stop], (cutadapt.__version__, specs, read_wild, read, out.sequence, read[start:stop])
 
 
+def _reference_baking():
+    """The unmodified reference's baking() running on the REAL cutadapt / dnaio / xopen: from the read-only checkout or an
+    installed ``mirge`` package.  Skips unless all of them are there."""
+    import sys
+
+    _real_cutadapt()
+    for mod in ("dnaio", "xopen"):
+        m = pytest.importorskip(mod)
+        if not getattr(m, "__file__", None):
+            pytest.skip("%s in sys.modules is a stand-in" % mod)
+    ref = "/root/reference"
+    if os.path.isdir(os.path.join(ref, "mirge")) and ref not in sys.path:
+        sys.path.append(ref)
+    try:
+        from mirge.libs.digest import baking  # noqa: the reference's own code
+    except Exception as e:  # not installed / its other imports are missing
+        pytest.skip("the reference's mirge.libs.digest is not importable here: %s" % e)
+    return baking
+
+
+@pytest.mark.parametrize("name", ["ref_case2_umi", "ref_case3_umi_dedup", "ref_case4_qiagen", "ref_case5_nextseq_cuts",
+                                  "ref_case6_front_back_noindels"])
+def test_reference_baking_with_the_real_tools_reproduces_the_golden_files(name, tmp_path):
+    """The committed golden files were written by the reference's code with stand-ins answering for cutadapt / dnaio
+    (tests/golden/standins.py), so for the third-party arithmetic they are circular.  Here the same reference code runs
+    on the same inputs with the REAL packages: equal files turn those goldens -- and with them the oracle and the GPU
+    path, which reproduce them byte for byte -- into pinned ones."""
+    import json
+    from pathlib import Path
+
+    from tests.golden.make_reference_golden import reference_args
+
+    baking = _reference_baking()
+    import cutadapt
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)
+    meta = json.load(open(os.path.join(d, "counters.json")))
+    ov = dict(meta["args"])
+    if "adapters" in ov:
+        ov["adapters"] = [tuple(a) for a in ov["adapters"]]
+    ver = tuple(str(cutadapt.__version__).split(".")[:2])
+    args = reference_args(cutadaptVersion=ver, **ov)  # (digest.py:111-113 switches on the installed version)
+    files = [os.path.join(d, s + ".fastq") for s in meta["samples"]]
+    df, src, trc, tru = baking(args, files, meta["samples"], Path(tmp_path))
+    got = df.sort_index(kind="stable").to_csv()
+    assert src == meta["sampleReadCounts"], (cutadapt.__version__, src)
+    assert trc == meta["trimmedReadCounts"] and tru == meta["trimmedReadCountsUnique"], (cutadapt.__version__, trc, tru)
+    assert got == open(os.path.join(d, "complete_set.csv")).read(), "complete_set.csv differs with cutadapt %s" % cutadapt.__version__
+    for extra in sorted(os.listdir(d)):
+        if extra.endswith("_umiCounts.csv"):
+            assert sorted(open(os.path.join(str(tmp_path), extra)).read().splitlines()) == sorted(open(os.path.join(d, extra)).read().splitlines()), extra
+
+
 def test_quality_trimmers_match_cutadapt():
     _real_cutadapt()
     from cutadapt.qualtrim import nextseq_trim_index, quality_trim_index
