@@ -630,6 +630,37 @@ class ExchangeWorker:
 _SHARD = {}
 
 
+def assemble_table(gathered, names):
+    """The sample x sequence DataFrame of ``baking`` (digest.py:237-261: outer join = sorted union of the sequences, 0
+    where a sample lacks one, annotation columns empty, annotFlag 0) from what the owners sent: per rank
+    (keys 'S' array, [(ids, counts) per sample]) with ids indexing that rank's keys.  Returns (df, order, offs, n_all):
+    ``order`` = rows of the concatenated key list in table order (keys no sample counted are dropped), ``offs`` = first
+    row of every rank in that list."""
+    import numpy as np
+    import pandas as pd
+
+    from . import digest as DG
+
+    sizes = [int(g[0].shape[0]) for g in gathered]
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    width = max([g[0].dtype.itemsize for g in gathered] + [1])
+    all_keys = np.concatenate([g[0].astype("S%d" % width) for g in gathered]) if sum(sizes) else np.zeros(0, dtype="S1")
+    mat = np.zeros((all_keys.shape[0], len(names)), dtype=np.int64)
+    for r, (_, ps) in enumerate(gathered):
+        for j, (i_, c_) in enumerate(ps):
+            mat[offs[r] + i_, j] = c_
+    seen = mat.any(axis=1) if mat.size else np.zeros(0, dtype=bool)
+    order = np.argsort(all_keys, kind="stable")
+    order = order[seen[order]]
+    index = pd.Index([k.decode("latin-1") for k in all_keys[order].tolist()], name="Sequence", dtype=object)
+    df = pd.DataFrame(mat[order], index=index, columns=names)
+    df = df.assign(**dict.fromkeys(DG.INITIAL_FLAGS, ""))
+    df = df.assign(annotFlag=0)
+    df = df.reindex(columns=["annotFlag"] + DG.INITIAL_FLAGS + names)
+    df = df.astype({"annotFlag": int})
+    return df, order, offs, int(all_keys.shape[0])
+
+
 def baking_sharded(args, inFileArray, inFileBaseArray, workDir, device=None, count_mode=None, batch_bytes=256 << 20, group=None):
     """Call on every rank.  Returns (complete_set, sampleReadCounts, trimmedReadCounts, trimmedReadCountsUnique);
     complete_set is the DataFrame of digest.baking on rank 0 and None elsewhere."""
@@ -696,26 +727,8 @@ def baking_sharded(args, inFileArray, inFileBaseArray, workDir, device=None, cou
     _SHARD.update(dev=dev, owner=owner, n_own=int(keys.shape[0]))
     if rank != 0:
         return None, src, trc, tru
-    import pandas as pd
-
-    sizes = [int(g[0].shape[0]) for g in gathered]
-    offs = np.concatenate([[0], np.cumsum(sizes)])
-    width = max([g[0].dtype.itemsize for g in gathered] + [1])
-    all_keys = np.concatenate([g[0].astype("S%d" % width) for g in gathered]) if sum(sizes) else np.zeros(0, dtype="S1")
-    mat = np.zeros((all_keys.shape[0], len(names)), dtype=np.int64)
-    for r, (_, ps) in enumerate(gathered):
-        for j, (i_, c_) in enumerate(ps):
-            mat[offs[r] + i_, j] = c_
-    seen = mat.any(axis=1) if mat.size else np.zeros(0, dtype=bool)
-    order = np.argsort(all_keys, kind="stable")
-    order = order[seen[order]]
-    index = pd.Index([k.decode("latin-1") for k in all_keys[order].tolist()], name="Sequence", dtype=object)
-    df = pd.DataFrame(mat[order], index=index, columns=names)
-    df = df.assign(**dict.fromkeys(DG.INITIAL_FLAGS, ""))
-    df = df.assign(annotFlag=0)
-    df = df.reindex(columns=["annotFlag"] + DG.INITIAL_FLAGS + names)
-    df = df.astype({"annotFlag": int})
-    _SHARD.update(order=order, offs=offs, n_all=int(all_keys.shape[0]))
+    df, order, offs, n_all = assemble_table(gathered, names)
+    _SHARD.update(order=order, offs=offs, n_all=n_all)
     # index_data.js read-length histograms (digest.py:270-295) from the gathered matrix; the UMI count histograms stay
     # with the single-process baking (their per-sample lists live on the digesting ranks)
     class _NoHist:

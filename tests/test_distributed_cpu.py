@@ -304,3 +304,45 @@ def test_sharding_before_collapse_round_protocol_world2(overlap, slack, n_batche
     per_sample = max(max(n_batches), 1)
     assert results[0][1] == 2 * per_sample
     assert results[0][2] == results[0][1]
+
+
+def test_assemble_table_equals_the_reference_join():
+    """Rank 0's assembly of the owners' slices (distributed.assemble_table) against the reference's matrix build
+    (digest.py:237-261: one column per sample, successive outer joins, fillna(0), flag columns): random per-sample
+    tables cut by owner over three ranks, one rank owning nothing, a key no sample counted."""
+    import pandas as pd
+
+    from mirge_b200 import digest as DG
+
+    rng = np.random.default_rng(12)
+    names = ["a", "b", "c"]
+    pool = ["".join(rng.choice(list("ACGT"), int(rng.integers(16, 40)))) for _ in range(400)]
+    tables = [{k: int(rng.integers(1, 50)) for k in rng.choice(pool, int(rng.integers(50, 300)), replace=False)} for _ in names]
+    world = 3
+    owner = lambda k: 0 if zlib.crc32(k.encode()) % 2 == 0 else 2  # rank 1 owns nothing
+    gathered = []
+    for r in range(world):
+        keys = sorted({k for t in tables for k in t if owner(k) == r})
+        if r == 0:
+            keys.append("TTTTTTTTTTTTTTTTTTTT")  # in the owner's table (an earlier sample of the run), counted by none of these
+        rng.shuffle(keys)
+        kid = {k: i for i, k in enumerate(keys)}
+        width = max([len(k) for k in keys] + [1])
+        karr = np.array([k.encode() for k in keys], dtype="S%d" % width) if keys else np.zeros(0, dtype="S1")
+        ps = []
+        for t in tables:
+            mine = [(kid[k], c) for k, c in t.items() if owner(k) == r]
+            ps.append((np.array([i for i, _ in mine], dtype=np.int64), np.array([c for _, c in mine], dtype=np.int64)))
+        gathered.append((karr, ps))
+    df, order, offs, n_all = MD.assemble_table(gathered, names)
+    # the reference's way
+    ref = None
+    for n, t in zip(names, tables):
+        col = pd.DataFrame(list(t.items()), columns=["Sequence", n]).set_index("Sequence")
+        ref = col if ref is None else ref.join(col, how="outer")
+    ref = ref.fillna(0).astype(int)
+    ref = ref.assign(**dict.fromkeys(DG.INITIAL_FLAGS, "")).assign(annotFlag=0)
+    ref = ref.reindex(columns=["annotFlag"] + DG.INITIAL_FLAGS + names).astype({"annotFlag": int})
+    assert list(df.index) == list(ref.index) and list(df.columns) == list(ref.columns)
+    assert df.to_csv() == ref.to_csv()
+    assert n_all == sum(len(g[0]) for g in gathered) and len(order) == len(ref) and list(offs) == [0, len(gathered[0][0]), len(gathered[0][0]), n_all]
