@@ -1,4 +1,5 @@
-"""Writes tests/native/trim_cases.bin for tests/native/trim_check.cu: per case the trim parameters (the mirge_trim_params
+"""usage: make_trim_cases.py [reads per case = 2000] [output file]
+Writes tests/native/trim_cases.bin for tests/native/trim_check.cu: per case the trim parameters (the mirge_trim_params
 bytes the product would pass), the FASTQ bytes and the windows / kept flags the C oracle computes for them.  Runs on the
 build host (it uses the oracle); the GPU box only reads the file."""
 import ctypes as C
@@ -51,7 +52,7 @@ def cases(n_reads):
 
 def main():
     n_reads = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
-    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "trim_cases.bin")
+    out = sys.argv[2] if len(sys.argv) > 2 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "trim_cases.bin")
     blobs = []
     for name, cfg, data, mode in cases(n_reads):
         cp = P.build_trim_params(cfg)
