@@ -652,12 +652,15 @@ def assemble_table(gathered, names):
     seen = mat.any(axis=1) if mat.size else np.zeros(0, dtype=bool)
     order = np.argsort(all_keys, kind="stable")
     order = order[seen[order]]
-    index = pd.Index([k.decode("latin-1") for k in all_keys[order].tolist()], name="Sequence", dtype=object)
-    df = pd.DataFrame(mat[order], index=index, columns=names)
-    df = df.assign(**dict.fromkeys(DG.INITIAL_FLAGS, ""))
-    df = df.assign(annotFlag=0)
-    df = df.reindex(columns=["annotFlag"] + DG.INITIAL_FLAGS + names)
-    df = df.astype({"annotFlag": int})
+    # frame built as digest.build_matrix builds it: beyond ARROW_INDEX_MIN rows no Python object per cell
+    m = int(order.shape[0])
+    index = DG.sequence_index(all_keys[order]) if m else pd.Index([], name="Sequence", dtype=object)
+    frame = {"annotFlag": np.zeros(m, dtype=np.dtype(int))}
+    empty = DG.empty_flag_column(m)
+    frame.update((f, empty) for f in DG.INITIAL_FLAGS)
+    df = pd.DataFrame(frame, index=index, copy=False)
+    for j, name in enumerate(names):
+        df[name] = mat[order, j]
     return df, order, offs, int(all_keys.shape[0])
 
 

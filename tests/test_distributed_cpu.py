@@ -345,4 +345,16 @@ def test_assemble_table_equals_the_reference_join():
     ref = ref.reindex(columns=["annotFlag"] + DG.INITIAL_FLAGS + names).astype({"annotFlag": int})
     assert list(df.index) == list(ref.index) and list(df.columns) == list(ref.columns)
     assert df.to_csv() == ref.to_csv()
+    assert [str(t) for t in df.dtypes] == [str(t) for t in ref.dtypes] and df.index.name == "Sequence"
+    # the Arrow-backed form large tables take (no Python object per row) writes the same file
+    import mirge_b200.digest as DGm
+
+    old_min, DGm.ARROW_INDEX_MIN = DGm.ARROW_INDEX_MIN, 10
+    try:
+        df2 = MD.assemble_table(gathered, names)[0]
+    finally:
+        DGm.ARROW_INDEX_MIN = old_min
+    assert df2.to_csv() == ref.to_csv() and list(df2.index) == list(ref.index)
+    empty = MD.assemble_table([(np.zeros(0, dtype="S1"), [(np.zeros(0, dtype=np.int64),) * 2] * 3)] * 2, names)[0]
+    assert len(empty) == 0 and list(empty.columns) == list(ref.columns)
     assert n_all == sum(len(g[0]) for g in gathered) and len(order) == len(ref) and list(offs) == [0, len(gathered[0][0]), len(gathered[0][0]), n_all]
