@@ -46,7 +46,8 @@ extern "C" {
 #define MIRGE_ERR_CAPACITY (-4) /* a caller-provided buffer / table is too small */
 #define MIRGE_ERR_NODEVICE (-5) /* no usable CUDA device */
 
-#define MIRGE_MAX_ADAPTERS 4
+#define MIRGE_MAX_ADAPTERS 16 /* (more than MIRGE_FAST_ADAPTERS of them: full-DP kernel) */
+#define MIRGE_FAST_ADAPTERS 4
 #define MIRGE_MAX_ADAPTER_LEN 64
 #define MIRGE_MAX_MODS 8
 #define MIRGE_MAX_READ_LEN 512 /* bases per read handled by the trim kernel */

@@ -7,7 +7,7 @@ import os
 
 from . import LIB_PATH
 
-MAX_ADAPTERS = 4
+MAX_ADAPTERS = 16
 MAX_ADAPTER_LEN = 64
 MAX_MODS = 8
 MAX_READ_LEN = 512

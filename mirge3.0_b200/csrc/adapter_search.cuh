@@ -75,7 +75,7 @@ static int fill_dev_params(const mirge_trim_params *p, DevParams &d, int &maxm, 
   if (p->umi_mode != MIRGE_UMI_NONE && (p->umi5 < 0 || p->umi3 < 0)) FILL_FAIL("negative UMI length");
   if (p->umi_mode == MIRGE_UMI_QIAGEN && p->n_adapters < 1) FILL_FAIL("qiagen UMI mode needs an adapter");
   maxm = 0;
-  fast_ok = 1;
+  fast_ok = p->n_adapters <= MIRGE_FAST_ADAPTERS;  // (the bit-parallel kernels stage one match table per adapter in shared memory)
   for (int a = 0; a < p->n_adapters; ++a) {
     const mirge_adapter *s = &p->adapters[a];
     if (s->m < 1 || s->m > MIRGE_MAX_ADAPTER_LEN) FILL_FAIL("adapter %d length %d unsupported", a, s->m);

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_sizes_match_header():
     # sizes derived from the header's field lists
     assert ctypes.sizeof(abi.Adapter) == 9 * 4 + 64 + 64 + 65 * 4 + 65 * 4  # + wildcard_read (ABI v3)
-    assert ctypes.sizeof(abi.TrimParams) == 4 * (1 + 8 * 4 + 9) + 4 * ctypes.sizeof(abi.Adapter)  # + compat (ABI v2)
+    assert ctypes.sizeof(abi.TrimParams) == 4 * (1 + 8 * 4 + 9) + 16 * ctypes.sizeof(abi.Adapter)  # + compat (ABI v2), 16 adapters (v3)
     assert ctypes.sizeof(abi.Table) == 56
     assert ctypes.sizeof(abi.RoundPolicy) == 32
     assert ctypes.sizeof(abi.Library) == 104  # + filter16_bits, max_ref_len, d_filter16 (ABI v2)

@@ -181,6 +181,40 @@ def test_per_adapter_parameters_on_the_bit_parallel_search(hs, seed):
     assert stats.get(("mode", 1), 0) > 100 and stats.get(("mode", 3), 0) > 50 and stats.get("matches", 0) > 100, stats
 
 
+def test_more_adapters_than_the_bit_parallel_kernels_take(hs):
+    """Seven adapters (a kit's worth through file:): fill_dev_params sends them to the full-DP search, and
+    AdapterCutter's choice among them (most matches, then fewest errors, then the first) is the oracle's."""
+    rng = np.random.default_rng(4800)
+    ads = [make_adapter(rng, "random") for _ in range(5)] + [make_adapter(rng, "repeat"), make_adapter(rng, "two_blocks")]
+    cfg = P.TrimConfig(adapters=[("back", a) for a in ads], error_rate=0.15, overlap=4, times=2, quality_cutoff=None)
+    cp, pp = P.build_trim_params(cfg), py_params(cfg)
+    fast_ok = C.c_int(1)
+    err = C.create_string_buffer(512)
+    assert hs.hs_set_params(C.byref(cp), C.byref(fast_ok), err, 512) == 0, err.value
+    assert cp.n_adapters == 7 and fast_ok.value == 0
+    hs.hs_pipeline.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.POINTER(C.c_int32)]
+    win = (C.c_int32 * (2 * cp.n_mods))()
+    mods = pp.modifiers()
+    used = set()
+    for it in range(1500):
+        a = ads[int(rng.integers(len(ads)))]
+        seq = make_read(rng, a, int(rng.integers(0, 5)))
+        if rng.random() < 0.3:
+            seq += mutate(rng, ads[int(rng.integers(len(ads)))], 0.05, 0.02, 0.02)
+        if not seq:
+            continue
+        qual = "I" * len(seq)
+        hs.hs_pipeline(seq.encode(), qual.encode(), len(seq), win)
+        start, stop = 0, len(seq)
+        for mi, mod in enumerate(mods):
+            start, stop = po.apply_modifier(mod, seq, qual, start, stop, pp)
+            assert (win[2 * mi], win[2 * mi + 1]) == (start, stop), (seq, mi, (win[2 * mi], win[2 * mi + 1]), (start, stop))
+        which, mt = po.best_match(pp.adapters, seq, pp.compat)
+        if mt is not None:
+            used.add(pp.adapters.index(which))
+    assert len(used) == 7, used
+
+
 WHERE_SPECS = {  # cutadapt's notation of every placement (params.parse_adapter_spec)
     "back": ("back", "%s"), "front": ("front", "%s"), "suffix": ("back", "%s$"), "prefix": ("front", "^%s"),
     "back_not_internal": ("back", "%sX"), "front_not_internal": ("front", "X%s"),

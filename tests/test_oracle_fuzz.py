@@ -124,6 +124,28 @@ def random_placement_config(rng):
                         cutadapt_compat="4" if rng.random() < 0.2 else "2-3")
 
 
+def random_kit_config(rng):
+    """More adapters than the bit-parallel kernels take (a kit's list through file:): 5-12 of them, mostly plain 3'
+    adapters, some placed or with parameters -- the choice among many matches (most matches, fewest errors, first)."""
+    n = int(rng.integers(5, 13))
+    adapters = []
+    for k in range(n):
+        s = rnd_seq(rng, int(rng.integers(8, 30)))
+        r = rng.random()
+        if r < 0.6:
+            adapters.append(("back", s))
+        elif r < 0.75:
+            adapters.append(("front", s[:12]))
+        elif r < 0.85:
+            adapters.append(("back", s + str(rng.choice(["$", "X"]))))
+        else:
+            adapters.append(("back", s + ";e=%s;o=%d" % (rng.choice(["0.05", "0.2"]), int(rng.integers(2, 8)))))
+    return P.TrimConfig(adapters=adapters, error_rate=float(rng.choice([0.05, 0.12, 0.2])), overlap=int(rng.integers(2, 7)),
+                        indels=bool(rng.random() < 0.8), times=int(rng.integers(1, 4)),
+                        quality_cutoff=str(int(rng.integers(5, 25))) if rng.random() < 0.5 else None,
+                        minimum_length=int(rng.integers(0, 20)), count_mode="head" if rng.random() < 0.7 else "release")
+
+
 def random_reads(rng, cfg, n):
     recs = []
     flat = []  # (5' or 3' form, sequence) of every adapter and half
@@ -223,3 +245,26 @@ def test_c_oracle_equals_python_oracle_on_random_placements(seed):
         keys_py = [k for k, _ in po.digest_read(seq, qual, pp)]
         keys_c = [seq[win[r, s, 0] : win[r, s, 1]] + seq[win[r, s, 2] : win[r, s, 3]] for s in range(E) if kept[r, s]]
         assert keys_c == keys_py, (seed, cfg, r, seq, qual)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_c_oracle_equals_python_oracle_on_adapter_kits(seed):
+    """... and with 5-12 adapters at once (random_kit_config)."""
+    rng = np.random.default_rng(9800 + seed)
+    cfg = random_kit_config(rng)
+    cp = P.build_trim_params(cfg)
+    assert cp.n_adapters >= 5
+    pp = py_params(cfg)
+    data = random_reads(rng, cfg, 250)
+    fq = np.frombuffer(data, dtype=np.uint8)
+    E = P.trim_slots(cp)
+    n, win, kept = coracle.trim(fq, cp)
+    used = set()
+    for r, (_nm, seq, qual) in enumerate(po.parse_fastq(data)):
+        keys_py = [k for k, _ in po.digest_read(seq, qual, pp)]
+        keys_c = [seq[win[r, s, 0] : win[r, s, 1]] + seq[win[r, s, 2] : win[r, s, 3]] for s in range(E) if kept[r, s]]
+        assert keys_c == keys_py, (seed, cfg, r, seq, qual)
+        which, mt = po.best_match(pp.adapters, seq, pp.compat)
+        if mt is not None:
+            used.add(id(which))
+    assert len(used) >= 3, (seed, len(used))

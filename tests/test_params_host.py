@@ -55,6 +55,19 @@ def test_adapter_specification_language(tmp_path):
     assert P.build_trim_params(P.TrimConfig(adapters=[("back", "ACGT")], match_read_wildcards=True)).adapters[0].wildcard_read == 1
 
 
+def test_adapter_lists_beyond_the_bit_parallel_kernels(tmp_path):
+    """A file: list of a whole kit: up to 16 adapters (a linked pair counts twice); more than four of them leave the
+    bit-parallel kernels (one shared-memory match table per adapter) for the full-DP kernel."""
+    fa = tmp_path / "kit.fa"
+    seqs = ["ACGTACGTAC" + "ACGT"[i % 4] * 6 + "TTGCA"[: 1 + i % 5] for i in range(9)]
+    fa.write_text("".join(">a%d\n%s\n" % (i, q) for i, q in enumerate(seqs)))
+    p = P.build_trim_params(P.TrimConfig(adapters=[("back", "file:%s" % fa), ("back", "^GTTCAG...TGGAATTC")]))
+    assert p.n_adapters == 11 and [bytes(p.adapters[i].ascii[: p.adapters[i].m]).decode() for i in range(9)] == seqs
+    assert p.adapters[9].link == 11 | abi.LINK_BACK_OPTIONAL and p.adapters[10].link == abi.LINK_BACK_HALF
+    with pytest.raises(RuntimeError):
+        P.build_trim_params(P.TrimConfig(adapters=[("back", "ACGTACGT" + "ACGT"[i % 4] * (1 + i // 4)) for i in range(abi.MAX_ADAPTERS + 1)]))
+
+
 def test_linked_adapter_specification():
     """"ADAPTER5...ADAPTER3" (docs/source/quick_start.md:208-220): a 5' half pointing at its 3' half in the flat adapter
     list.  -g: both halves required; -a: a half is required only when it is anchored; ;required / ;optional override."""
