@@ -110,6 +110,9 @@ SPEC_CASES = [  # (-a / -g arguments, --match-read-wildcards): the specification
     ([("front", "GTTCAGAGTTCTAC..." + ILL)], False), ([("back", "GTTCAGAGTTCTAC..." + ILL)], False),
     ([("back", "^GTTCAGAGTTCTAC..." + ILL)], False), ([("front", "GTTCAGAGTTCTAC;optional..." + ILL + ";e=0.2")], False),
     ([("back", "GTTCAGAGTTCTAC;required..." + ILL + "$")], False), ([("back", ILL)], True), ([("front", "GTTCAGAGTTCTAC"), ("back", ILL + "X")], True),
+    # -a with non-internal halves: whether a non-internal half counts as "anchored" (= required) is the one point of
+    # cutadapt's _parse_linked the restatement is unsure of (params.parse_adapter_spec: only ^ / $ make a half required)
+    ([("back", "XGTTCAGAGTTCTAC..." + ILL)], False), ([("back", "GTTCAGAGTTCTAC..." + ILL + "X")], False),
 ]
 
 
