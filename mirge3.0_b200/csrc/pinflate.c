@@ -920,8 +920,7 @@ static int run_wave(pgz *z) {
     if (a->end_kind == END_FINAL) ended_final = 1;
     break;
   }
-  for (int s = 0; s <= n_cand; ++s)
-    if (ch[s].sym) { chunk_release(z, &ch[s]); }
+  for (int s = 0; s <= n_cand; ++s) chunk_release(z, &ch[s]); /* whatever the chain did not take (a failed first chunk has no symbol buffer) */
   free(ch);
   free(cand);
   if (rc) { for (int s = 0; s < n_acc; ++s) chunk_release(z, &acc[s]); free(acc); return rc; }
