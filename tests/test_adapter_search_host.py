@@ -17,7 +17,7 @@ import mirge_b200
 from mirge_b200 import abi
 from mirge_b200 import params as P
 from oracle import pyoracle as po
-from tests.util import CONFIG_DATA, CONFIGS, py_params, random_fastq
+from tests.util import host_harness_flags, CONFIG_DATA, CONFIGS, py_params, random_fastq
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 B = np.array(list("ACGT"))
@@ -26,7 +26,7 @@ B = np.array(list("ACGT"))
 @pytest.fixture(scope="module")
 def hs(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("hs") / "libadapter_search_host.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(mirge_b200.PACKAGE_DIR, "csrc"),
+    subprocess.check_call(["g++"] + host_harness_flags() + ["-std=c++17", "-shared", "-fPIC", "-I", os.path.join(mirge_b200.PACKAGE_DIR, "csrc"),
                            "-o", so, os.path.join(HERE, "adapter_search_harness.cpp")])
     lib = C.CDLL(so)
     lib.hs_set_params.argtypes = [C.POINTER(abi.TrimParams), C.POINTER(C.c_int), C.c_char_p, C.c_int]

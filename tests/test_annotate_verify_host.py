@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 import torch
 
+from tests.util import host_harness_flags
 import mirge_b200
 from mirge_b200 import abi
 from mirge_b200 import libraries as LB
@@ -25,7 +26,7 @@ NO_HIT = 0xFFFFFFFFFFFFFFFF
 @pytest.fixture(scope="module")
 def hv(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("hv") / "libannotate_verify_host.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(mirge_b200.PACKAGE_DIR, "csrc"),
+    subprocess.check_call(["g++"] + host_harness_flags() + ["-std=c++17", "-shared", "-fPIC", "-I", os.path.join(mirge_b200.PACKAGE_DIR, "csrc"),
                            "-o", so, os.path.join(HERE, "annotate_verify_harness.cpp")])
     lib = C.CDLL(so)
     lib.hv_best_hit.restype = C.c_uint64

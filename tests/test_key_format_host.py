@@ -9,6 +9,7 @@ import subprocess
 import numpy as np
 import pytest
 
+from tests.util import host_harness_flags
 import mirge_b200
 from tests.test_annotate_verify_host import pack_key
 
@@ -18,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 @pytest.fixture(scope="module")
 def hk(tmp_path_factory):
     so = str(tmp_path_factory.mktemp("hk") / "libkey_format_host.so")
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(mirge_b200.PACKAGE_DIR, "csrc"),
+    subprocess.check_call(["g++"] + host_harness_flags() + ["-std=c++17", "-shared", "-fPIC", "-I", os.path.join(mirge_b200.PACKAGE_DIR, "csrc"),
                            "-o", so, os.path.join(HERE, "key_format_harness.cpp")])
     lib = C.CDLL(so)
     lib.hk_slice.restype = C.c_uint32

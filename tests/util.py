@@ -188,3 +188,17 @@ def write_ebwt(basename, names, seqs, line_rate=6, lines_per_side=1, ftab_chars=
         f.write(b"\x00" * (4 * ((1 << (2 * ftab_chars)) + 1)))
         f.write(b"\x00" * (4 * 2 * ftab_chars))
         f.write(("\n".join(names) + "\n").encode() + b"\x00")
+
+
+def host_harness_flags():
+    """g++ flags for the device headers compiled for the host (tests/test_*_host.py).  MIRGE_TEST_SANITIZE=1 adds
+    AddressSanitizer + UBSan, for which the interpreter must run with the sanitizer runtimes preloaded:
+        LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)" ASAN_OPTIONS=detect_leaks=0 \\
+        MIRGE_TEST_SANITIZE=1 python -m pytest tests/test_adapter_search_host.py tests/test_annotate_verify_host.py tests/test_key_format_host.py
+    (the kernels' per-read arithmetic then runs with every out-of-bounds access of a local array or staging buffer and every
+    undefined shift / overflow turned into a failure)."""
+    import os
+
+    if os.environ.get("MIRGE_TEST_SANITIZE") == "1":
+        return ["-O1", "-g", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined"]
+    return ["-O2"]
