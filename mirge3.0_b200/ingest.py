@@ -381,11 +381,13 @@ class PlainReader:
 
     STRIPE = 8 << 20
 
-    def __init__(self, path: str, threads: Optional[int] = None, name: str = ""):
+    def __init__(self, path: str, threads: Optional[int] = None, name: str = "", start: int = 0, stop: Optional[int] = None):
+        """``start`` / ``stop``: read only that byte range of the file (a rank's share, see fastq_split_points)."""
         self.name = name or path
         self._fd = os.open(path, os.O_RDONLY)
-        self._size = os.fstat(self._fd).st_size
-        self._pos = 0
+        size = os.fstat(self._fd).st_size
+        self._size = size if stop is None else max(min(int(stop), size), 0)
+        self._pos = max(min(int(start), self._size), 0)
         self._threads = int(threads or default_threads())
         self.bytes_out = 0
 
@@ -436,6 +438,67 @@ class PlainReader:
     def __exit__(self, *exc):
         self.close()
         return False
+
+
+def _record_start(buf: bytes, base: int, at_eof: bool) -> Optional[int]:
+    """Offset (in the file) of the first FASTQ record that starts inside ``buf`` (= the file's bytes from ``base``),
+    skipping the partial line ``buf`` begins in.  A record starts with a line '@...' whose second successor is a line
+    '+...' and whose first and third successors have equal lengths: a QUALITY line may begin with '@' too, but then the
+    line two below it is a sequence, never '+'.  None: not decidable inside ``buf``."""
+    nl = buf.find(b"\n")
+    while nl >= 0:
+        p = nl + 1  # start of a line
+        ends = []
+        q = p
+        for _ in range(4):
+            e = buf.find(b"\n", q)
+            if e < 0:
+                break
+            ends.append(e)
+            q = e + 1
+        if len(ends) < 4:
+            if at_eof and p >= len(buf):
+                return base + len(buf)  # the partial line was the last one: the range ends with the file
+            return None
+        l0, l1, l2, l3 = (buf[a:b].rstrip(b"\r") for a, b in zip([p] + [e + 1 for e in ends[:3]], ends))
+        if l0[:1] == b"@" and l2[:1] == b"+" and len(l1) == len(l3):
+            return base + p
+        nl = ends[0]
+    return None
+
+
+def fastq_split_points(path: str, parts: int, window: int = 1 << 16) -> List[int]:
+    """Byte offsets [0, ..., size] that cut an uncompressed FASTQ file into ``parts`` ranges of about equal size, each
+    starting at a record: what N ranks that digest ONE large sample need to read their shares themselves
+    (``PlainReader(path, start=, stop=)``) instead of one process reading for all.  Compressed files cannot be cut this
+    way (one DEFLATE stream has no entry points): ValueError."""
+    if sniff(path) != "plain":
+        raise ValueError("%s is compressed: a single compressed stream cannot be read from the middle" % path)
+    size = os.path.getsize(path)
+    cuts = [0]
+    with open(path, "rb") as f:
+        for k in range(1, int(parts)):
+            target = max(size * k // int(parts), cuts[-1])
+            w = int(window)
+            while True:
+                f.seek(target)
+                buf = f.read(w)
+                at_eof = target + len(buf) >= size
+                # (a range that begins exactly at a record start is found too: the search starts one byte early)
+                lead = 1 if target > 0 else 0
+                if lead:
+                    f.seek(target - 1)
+                    buf = f.read(w + 1)
+                pos = _record_start(buf, target - lead, at_eof) if target > 0 else 0
+                if pos is not None:
+                    break
+                if at_eof:
+                    pos = size
+                    break
+                w *= 4
+            cuts.append(max(pos, cuts[-1]))
+    cuts.append(size)
+    return cuts
 
 
 def open_fastq(path: str, threads: Optional[int] = None, depth: int = 4):

@@ -146,6 +146,52 @@ def test_bzip2_and_xz_inputs(files, tmp_path):
                 read_all(r, 1 << 20)
 
 
+def test_fastq_split_points_and_range_readers(tmp_path):
+    """Record-aligned shares of one plain FASTQ for N ranks: every cut is the start of a record although quality lines
+    begin with '@' and '+' all over the file; the ranges read back to back give the file; compressed files refuse."""
+    rng = np.random.default_rng(21)
+    recs, starts, pos = [], [], 0
+    for i in range(4000):
+        L = int(rng.integers(1, 120))
+        seq = "".join(rng.choice(list("ACGTN"), L))
+        qual = "".join(rng.choice(list("@+IIFF#5:"), L))  # a third of the quality lines start with '@' or '+'
+        if i % 7 == 0:
+            qual = "@" + qual[1:]
+        if i % 11 == 0:
+            qual = "+" + qual[1:]
+        rec = "@r%d %s\n%s\n+%s\n%s\n" % (i, "x" * int(rng.integers(0, 30)), seq, "r%d" % i if i % 5 == 0 else "", qual)
+        starts.append(pos)
+        pos += len(rec)
+        recs.append(rec)
+    data = "".join(recs).encode()
+    for name, blob in (("a.fastq", data), ("crlf.fastq", data.replace(b"\n", b"\r\n")), ("noeol.fastq", data[:-1])):
+        p = str(tmp_path / name)
+        open(p, "wb").write(blob)
+        true = set(starts)
+        if b"\r" in blob:  # record starts of the CRLF file: every record is 4 bytes longer
+            true = {st + 4 * i for i, st in enumerate(starts)}
+        for parts in (1, 2, 3, 7, 64):
+            for window in (50, 1 << 16):
+                cuts = ingest.fastq_split_points(p, parts, window=window)
+                assert len(cuts) == parts + 1 and cuts[0] == 0 and cuts[-1] == len(blob) and cuts == sorted(cuts)
+                assert all(c in true or c == len(blob) for c in cuts), (name, parts, [c for c in cuts if c not in true])
+                if parts <= 7:
+                    assert all(abs((b - a) - len(blob) / parts) < 1000 for a, b in zip(cuts, cuts[1:])), (parts, cuts)
+                got = b""
+                for a, b in zip(cuts, cuts[1:]):
+                    with ingest.PlainReader(p, threads=2, start=a, stop=b) as r:
+                        got += r.read()
+                assert got == blob
+    tiny = str(tmp_path / "tiny.fastq")
+    open(tiny, "wb").write(b"@a\nAC\n+\nII\n")
+    assert ingest.fastq_split_points(tiny, 4) == [0, 11, 11, 11, 11]
+    gz = str(tmp_path / "a.fastq.gz")
+    with gzip.open(gz, "wb") as f:
+        f.write(data)
+    with pytest.raises(ValueError):
+        ingest.fastq_split_points(gz, 2)
+
+
 def test_empty_inputs(files):
     _, _, paths = files
     for k in ("empty", "empty_gz"):
