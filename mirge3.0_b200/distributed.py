@@ -741,6 +741,30 @@ def baking_sharded(args, inFileArray, inFileBaseArray, workDir, device=None, cou
     return df, src, trc, tru
 
 
+def fill_annotation(pdDataFrame, annot_all, ref_all, order, names_of, spike: bool):
+    """What ``bwtAlign`` leaves in the table (manifoldAlign.py:50-56,137-141) from the owners' results: ``annot_all`` /
+    ``ref_all`` = round (0xFF: none) and reference index of every gathered sequence in gather order, ``order`` = the
+    table's rows in that order (assemble_table), ``names_of[round]`` = the reference names of the round's library.
+    The round's column gets the reference name, annotFlag 1; the spike-in column goes unless ``-spk``."""
+    import numpy as np
+
+    a, ref = annot_all[order], ref_all[order]
+    colnames = list(pdDataFrame.columns)
+    for rnd in range(10 if spike else 9):
+        rows = np.nonzero(a == rnd)[0]
+        if rows.size == 0:
+            continue
+        col = pdDataFrame[colnames[1 + rnd]].to_numpy(dtype=object, copy=True)
+        col[rows] = np.asarray(names_of[rnd], dtype=object)[ref[rows]]
+        pdDataFrame[colnames[1 + rnd]] = col
+    flag = pdDataFrame[colnames[0]].to_numpy(copy=True)
+    flag[a != 0xFF] = 1
+    pdDataFrame[colnames[0]] = flag
+    if not spike:
+        pdDataFrame = pdDataFrame.drop(columns=["spike-in"])
+    return pdDataFrame.fillna("")
+
+
 def bwtAlign_sharded(args, pdDataFrame, workDir, ref_db, libraries=None, group=None):
     """Call on every rank after baking_sharded (pdDataFrame: its result on rank 0, None elsewhere).  Every rank
     annotates the sequences it owns; rank 0 returns the DataFrame manifoldAlign.bwtAlign would return."""
@@ -762,26 +786,10 @@ def bwtAlign_sharded(args, pdDataFrame, workDir, ref_db, libraries=None, group=N
     gathered = gather_arrays([annot.astype(np.uint8), ref.astype(np.int64)], 0, group, dev.tdev if "nccl" in str(dist.get_backend(group)) else None)
     if rank != 0:
         return None
-    order = _SHARD["order"]
-    annot_all = np.concatenate([g[0] for g in gathered]) if _SHARD["n_all"] else np.zeros(0, dtype=np.uint8)
-    ref_all = np.concatenate([g[1] for g in gathered]) if _SHARD["n_all"] else np.zeros(0, dtype=np.int64)
-    names_all = np.full(annot_all.shape[0], "", dtype=object)
-    for rnd in range(10 if spike else 9):
-        rows = np.nonzero(annot_all == rnd)[0]
-        if rows.size:
-            names_all[rows] = np.asarray(libs[ROUND_LIBS[rnd]].names, dtype=object)[ref_all[rows]]
-    a, nm = annot_all[order], names_all[order]
-    colnames = list(pdDataFrame.columns)
-    for rnd in range(10 if spike else 9):
-        rows = np.nonzero(a == rnd)[0]
-        if rows.size == 0:
-            continue
-        col = pdDataFrame[colnames[1 + rnd]].to_numpy(dtype=object, copy=True)
-        col[rows] = nm[rows]
-        pdDataFrame[colnames[1 + rnd]] = col
-    flag = pdDataFrame[colnames[0]].to_numpy(copy=True)
-    flag[a != 0xFF] = 1
-    pdDataFrame[colnames[0]] = flag
-    if not spike:
-        pdDataFrame = pdDataFrame.drop(columns=["spike-in"])
-    return pdDataFrame.fillna("")
+    if _SHARD["n_all"]:
+        annot_all = np.concatenate([g[0] for g in gathered])
+        ref_all = np.concatenate([g[1] for g in gathered])
+    else:
+        annot_all, ref_all = np.zeros(0, dtype=np.uint8), np.zeros(0, dtype=np.int64)
+    names_of = {rnd: libs[ROUND_LIBS[rnd]].names for rnd in range(10 if spike else 9)}
+    return fill_annotation(pdDataFrame, annot_all, ref_all, _SHARD["order"], names_of, spike)

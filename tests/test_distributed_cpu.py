@@ -358,3 +358,52 @@ def test_assemble_table_equals_the_reference_join():
     empty = MD.assemble_table([(np.zeros(0, dtype="S1"), [(np.zeros(0, dtype=np.int64),) * 2] * 3)] * 2, names)[0]
     assert len(empty) == 0 and list(empty.columns) == list(ref.columns)
     assert n_all == sum(len(g[0]) for g in gathered) and len(order) == len(ref) and list(offs) == [0, len(gathered[0][0]), len(gathered[0][0]), n_all]
+
+
+def test_fill_annotation_places_the_owners_results_in_table_order():
+    """bwtAlign_sharded's rank-0 half (distributed.fill_annotation): rounds and reference indices arrive in gather order
+    (rank by rank, each rank's keys in its own order), the table is in lexicographic order with unseen keys dropped; every
+    row must get the name of ITS sequence's hit, annotFlag 1 iff annotated, and the spike-in column only with -spk."""
+    rng = np.random.default_rng(31)
+    names = ["s1", "s2"]
+    world = 3
+    gathered, truth = [], {}
+    names_of = {rnd: ["lib%d_ref%d" % (rnd, i) for i in range(50)] for rnd in range(10)}
+    annot_parts, ref_parts = [], []
+    for r in range(world):
+        keys = ["".join(rng.choice(list("ACGT"), int(rng.integers(16, 30)))) for _ in range(int(rng.integers(0, 200)))]
+        keys = sorted(set(keys), key=lambda k: rng.random())
+        karr = np.array([k.encode() for k in keys], dtype="S30") if keys else np.zeros(0, dtype="S1")
+        ps = []
+        for _ in names:
+            ids = np.array(sorted(rng.choice(len(keys), int(rng.integers(0, len(keys) + 1)), replace=False)), dtype=np.int64) if keys else np.zeros(0, dtype=np.int64)
+            ps.append((ids, rng.integers(1, 99, ids.size).astype(np.int64)))
+        gathered.append((karr, ps))
+        annot = rng.choice(np.array([0xFF, 0xFF, 0, 1, 2, 5, 8, 9], dtype=np.uint8), len(keys)).astype(np.uint8)
+        ref = rng.integers(0, 50, len(keys)).astype(np.int64)
+        ref[annot == 0xFF] = 0xFFFFFFF  # what decode_hits gives for "no hit": must never be used as an index
+        annot_parts.append(annot)
+        ref_parts.append(ref)
+        for k, a, x in zip(keys, annot, ref):
+            truth[k] = (int(a), int(x))
+    df, order, offs, n_all = MD.assemble_table(gathered, names)
+    annot_all, ref_all = np.concatenate(annot_parts), np.concatenate(ref_parts)
+    for spike in (True, False):
+        ann = annot_all.copy()
+        if not spike:
+            ann[ann == 9] = 0xFF  # the spike-in round only runs with -spk
+        out = MD.fill_annotation(df.copy(), ann, ref_all, order, names_of, spike)
+        cols = list(out.columns)
+        assert ("spike-in" in cols) == spike and cols[0] == "annotFlag" and cols[-2:] == names
+        flag_cols = cols[1:-2]
+        assert len(flag_cols) == (10 if spike else 9)
+        n_annot = 0
+        for seq, row in out.iterrows():
+            a, x = truth[seq]
+            if a == 9 and not spike:
+                a = 0xFF
+            assert int(row["annotFlag"]) == (1 if a != 0xFF else 0), seq
+            for rnd, c in enumerate(flag_cols):
+                assert row[c] == (names_of[rnd][x] if a == rnd else ""), (seq, c)
+            n_annot += a != 0xFF
+        assert n_annot > 20
